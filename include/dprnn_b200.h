@@ -1,0 +1,131 @@
+/* libdprnn_b200 - C ABI of the B200-native DPRNN separation forward path.
+ *
+ * Drop-in boundary for the reference's `src/models` forward (Aleksashka-i/tss-with-dprnn).  The
+ * reference has no FFI of its own - its boundary is the nn.Module API - so
+ * each entry point below names the reference statement(s) it replaces (paths relative to the
+ * reference root).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference
+ * side.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless stated otherwise;
+ *   - activations are fp32, channels-last: [B, L, C] frames / [B, S, K, F] chunks (the reference
+ *     uses [B, C, L] / [B, F, K, S]); weights that feed a contraction are passed TRANSPOSED
+ *     ([K_in, N_out] row-major) - the host side packs them once per forward from the state_dict;
+ *   - the library never allocates: scratch is passed in, sizes come from *_workspace_bytes();
+ *   - `stream` is a cudaStream_t; all work is enqueued on it and nothing synchronises;
+ *   - return value 0 = ok, 1 = CUDA error, 2 = bad argument; dprnn_last_error() has the text.
+ */
+#ifndef DPRNN_B200_H
+#define DPRNN_B200_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+const char* dprnn_last_error(void);
+/* "arch=sm_100a;..." - which kernels / precision modes this build carries. */
+const char* dprnn_build_info(void);
+
+/* epilogues of dprnn_gemm_* */
+enum { DPRNN_EPI_NONE = 0, DPRNN_EPI_RELU = 1, DPRNN_EPI_SIGMOID = 2, DPRNN_EPI_GATED = 3 };
+
+/* Encoder.forward, src/models/encoder_decoder.py:25-33 (Conv1d(1->N, ksz, stride, bias=False) + ReLU).
+ * wave [B,T], w [N,ksz] -> enc [B, L=(T-ksz)/stride+1, N]. */
+int dprnn_encoder_fwd(const float* wave, const float* w, float* enc, int B, int T, int N, int ksz, int stride,
+                      void* stream);
+
+/* Statistics of nn.GroupNorm(1,C) / norms.GlobLN (src/models/dprnn.py:72-77,130-134, norms.py:6-31):
+ * per-utterance mean and 1/sqrt(biased var + eps) over a contiguous slab of elems_per_utt floats.
+ * mean_rstd [B,2]. Deterministic two-level fp64 reduction. */
+size_t dprnn_utt_stats_workspace_bytes(int B);
+int dprnn_utt_stats(const float* x, int B, long elems_per_utt, float eps, void* workspace, float* mean_rstd,
+                    void* stream);
+
+/* Folds the norm's affine (and an optional per-utterance channel multiplier - the mul / FiLM / att
+ * fusions of src/models/dprnn_spe.py:199-229) into s1[b,c] = gamma*rstd*mul, s0[b,c] = (beta-mean*gamma*rstd)*mul
+ * for use as the GEMM prologue. mulc may be NULL. */
+int dprnn_norm_affine(const float* mean_rstd, const float* gamma, const float* beta, const float* mulc, float* s1,
+                      float* s0, int B, int C, void* stream);
+
+/* intra_norm / inter_norm + residual, src/models/dprnn.py:90-92,98-99:
+ * x[b,r,c] += (y[b,r,c]-mean_b)*rstd_b*gamma_c + beta_c. */
+int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                        int B, long rows_per_utt, int C, void* stream);
+
+/* DPRNN._segmentation, src/models/dprnn.py:189-201 (F.unfold, kernel K, pad K, stride P):
+ * y [B,L,F] -> x [B,S,K,F], x[b,s,k,:] = y[b, s*P+k-K, :] or 0. S = dprnn_num_chunks(L,K,P). Bit-exact. */
+int dprnn_num_chunks(long L, int K, int P);
+int dprnn_unfold(const float* y, float* x, int B, long L, int K, int P, int F, void* stream);
+
+/* self.prelu + DPRNN._overlap_add, src/models/dprnn.py:174,203-217 (F.fold, plain sum):
+ * x [B,S,K,F] -> out [B,L,F]. prelu_a (1 float, device) may be NULL for a pure fold. */
+int dprnn_fold_prelu(const float* x, float* out, int B, long L, int K, int P, int F, const float* prelu_a,
+                     void* stream);
+
+/* masks * encoders then Decoder.forward, src/models/dprnn_spe.py:323-325, dprnn.py:277-281,
+ * encoder_decoder.py:40-49 (ConvTranspose1d(N->1, ksz, stride, bias=False)).
+ * mask: utterance b at mask + b*mask_utt_stride, [L,N]; enc [B,L,N]; wdec [N,ksz];
+ * out: utterance b at out + b*out_utt_stride, T=(L-1)*stride+ksz samples. */
+int dprnn_mask_decode(const float* mask, long mask_utt_stride, const float* enc, const float* wdec, float* out,
+                      long out_utt_stride, int B, long L, int N, int ksz, int stride, void* stream);
+
+/* d0 = (masks * input)[:,0], src/models/dprnn_spe_ira.py:79-80,107-108: out = mask * enc, elementwise. */
+int dprnn_mask_apply(const float* mask, const float* enc, float* out, long elems, void* stream);
+
+/* Attention fusion, src/models/dprnn_spe.py:177-183,217-225: depthwise average conv (stride ksz) of the
+ * normalised encoding, channel dot with v = fusion_linear(e), softmax over time, nearest upsample to L.
+ * Produces rowscale[b,l] = 1 + softmax[b, src(l)] (the per-channel factor v goes through dprnn_norm_affine).
+ * scores [B,La] is scratch/out (La=(L-ksz)/ksz+1); the upsample index map is ATen's, bit-exact. */
+int dprnn_att_rowscale(const float* enc, const float* s1, const float* s0, const float* wavg, const float* bavg,
+                       const float* v, float* scores, float* rowscale, int B, long L, int N, int ksz, void* stream);
+
+/* nn.BatchNorm1d of ResBlock, src/models/dprnn_spe.py:20-21,33,36: per-channel scale/shift.
+ * training!=0: batch statistics of y [rows,C] + running-stat update in place (unbiased var, momentum);
+ * training==0: running statistics (y, workspace unused). C must divide 256. */
+size_t dprnn_bn_workspace_bytes(int C);
+int dprnn_batchnorm_affine(const float* y, long rows, int C, const float* weight, const float* bias,
+                           float* running_mean, float* running_var, int training, float eps, float momentum,
+                           void* workspace, float* scale, float* shift, void* stream);
+
+/* BN apply + PReLU, src/models/dprnn_spe.py:33-34. */
+int dprnn_affine_prelu(const float* y, const float* scale, const float* shift, const float* prelu_a, float* out,
+                       long rows, int C, void* stream);
+/* BN apply + skip + PReLU + MaxPool1d(3), src/models/dprnn_spe.py:36-42. y, skip [B,Lin,C] -> out [B,Lin/3,C]. */
+int dprnn_affine_add_prelu_pool3(const float* y, const float* scale, const float* shift, const float* skip,
+                                 const float* prelu_a, float* out, int B, long Lin, int C, void* stream);
+
+/* Time sum of the speaker encoder output divided by the per-utterance length div[b],
+ * src/models/dprnn_spe.py:159-161. x [B,Lx,C] -> emb [B,C]. */
+int dprnn_time_sum(const float* x, float* emb, int B, long Lx, int C, const float* div, void* stream);
+
+/* Tiny Linear on embeddings (fusion_linear*, pred_linear, aux_linear; src/models/dprnn_spe.py:92-98,123,
+ * dprnn_spe_ira.py:51): out[b,n] (+)= bias[n] + sum_k in[b*ldin+k]*W[n*ldw+k]. W in nn.Linear layout. */
+int dprnn_small_linear(const float* in, long ldin, const float* W, long ldw, const float* bias, float* out,
+                       long ldout, int B, int N, int K, int accumulate, void* stream);
+
+/* Every pointwise contraction of the path in exact fp32 (1x1 Conv1d / Conv2d / nn.Linear:
+ * src/models/dprnn.py:61,70,135,155,157-160; dprnn_spe.py:17-18,117,121):
+ *   C[M,N] = epi( pro(A)[M,K] @ Wt[K,N] + bias_scale*bias )
+ * pro: a = (a*p_scale[b,k] + p_shift[b,k]) * rowscale[row] + p_add[b,k] with b = row / rows_per_utt
+ *      (any of p_scale/p_shift, rowscale, p_add may be NULL);
+ * bias: [N], or [B,N] when bias_per_utt;
+ * DPRNN_EPI_GATED: Wt/bias columns packed per 128-wide tile as 64 'out' + 64 'gate' units and
+ *      C[M,N/2] = tanh(out) * sigmoid(gate)  (src/models/dprnn.py:181). */
+int dprnn_gemm_f32(const float* A, long lda, const float* Wt, long ldw, float* C, long ldc, int M, int N, int K,
+                   const float* bias, int bias_per_utt, float bias_scale, long rows_per_utt, const float* p_scale,
+                   const float* p_shift, const float* p_add, const float* rowscale, int epilogue, void* stream);
+
+/* The sequential half of nn.LSTM, src/models/dprnn.py:23-28,35-36 (gate order i,f,g,o, zero initial
+ * state), exact fp32 on CUDA cores.  gx [rows, ndir*4H] = x W_ih^T + b_ih + b_hh (from dprnn_gemm_f32),
+ * whhT [ndir][H][4H], hout [rows, ndir*H].  Sequence n, step t lives at row
+ *   (n / seq_div)*seq_outer_stride + (n % seq_div)*seq_inner_stride + t*step_stride
+ * (intra-chunk: seq_div=1, outer=K, step=1; inter-chunk: seq_div=K, outer=S*K, inner=1, step=K).
+ * Direction 1 walks t = T-1..0. hidden must be 128. */
+int dprnn_lstm_recurrence_f32(const float* gx, const float* whhT, float* hout, long nseq, int T, long seq_div,
+                              long seq_outer_stride, long seq_inner_stride, long step_stride, int hidden, int ndir,
+                              void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DPRNN_B200_H */

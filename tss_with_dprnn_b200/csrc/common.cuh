@@ -1,0 +1,83 @@
+// Shared helpers for libdprnn_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+
+#define DPRNN_STR2(x) #x
+#define DPRNN_STR(x) DPRNN_STR2(x)
+
+namespace dprnn {
+
+// last-error slot shared by every translation unit of the library (defined in api.cu)
+void set_error(const char* fmt, ...);
+
+#define DPRNN_CHECK_ARG(cond)                                                        \
+    do {                                                                             \
+        if (!(cond)) {                                                               \
+            ::dprnn::set_error("%s:%d: bad argument: %s", __FILE__, __LINE__, #cond); \
+            return 2;                                                                \
+        }                                                                            \
+    } while (0)
+
+#define DPRNN_CHECK_LAUNCH()                                                          \
+    do {                                                                             \
+        cudaError_t e__ = cudaGetLastError();                                        \
+        if (e__ != cudaSuccess) {                                                    \
+            ::dprnn::set_error("%s:%d: launch failed: %s", __FILE__, __LINE__,        \
+                               cudaGetErrorString(e__));                             \
+            return 1;                                                                \
+        }                                                                            \
+    } while (0)
+
+#define DPRNN_CUDA(call)                                                              \
+    do {                                                                             \
+        cudaError_t e__ = (call);                                                    \
+        if (e__ != cudaSuccess) {                                                    \
+            ::dprnn::set_error("%s:%d: %s: %s", __FILE__, __LINE__, #call,            \
+                               cudaGetErrorString(e__));                             \
+            return 1;                                                                \
+        }                                                                            \
+    } while (0)
+
+static inline unsigned cdiv(long a, long b) { return (unsigned)((a + b - 1) / b); }
+
+__device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// Block-wide sum of a double for blocks of up to 1024 threads. All threads get the result.
+__device__ __forceinline__ double block_sum(double v, double* scratch /*[32]*/) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) scratch[wid] = v;
+    __syncthreads();
+    double r = (lane < nw) ? scratch[lane] : 0.0;
+    r = warp_sum(r);
+    return r;
+}
+
+__device__ __forceinline__ float4 ld_stream(const float4* p) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+
+}  // namespace dprnn

@@ -1,0 +1,575 @@
+// Memory-bound stages of the DPRNN forward: waveform encoder / decoder, chunk unfold / fold,
+// per-utterance norm statistics + apply, speaker-fusion helpers, BatchNorm / PReLU / MaxPool of the
+// speaker ResNet.  All activations are fp32, channels-last ([B, L, C] / [B, S, K, F]).
+// The reference line each entry point replaces is cited in include/dprnn_b200.h.
+#include "common.cuh"
+#include "../../include/dprnn_b200.h"
+
+namespace dprnn {
+
+constexpr int kStatParts = 128;   // partial sums per utterance (deterministic two-level reduction)
+
+// ------------------------------------------------------------------------------------------
+// encoder: enc[b,l,c] = relu(sum_j w[c,j] * x[b, l*stride + j])
+// ------------------------------------------------------------------------------------------
+__global__ void encoder_kernel(const float* __restrict__ wave, const float* __restrict__ w,
+                               float* __restrict__ enc, int B, int T, long L, int N, int ksz, int stride) {
+    const int n4 = N >> 2;
+    const long total = (long)B * L * n4;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % n4);
+        const long row = idx / n4;
+        const long b = row / L, l = row % L;
+        const float* x = wave + b * T + l * stride;
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int j = 0; j < ksz; ++j) {
+            const float xv = __ldg(x + j);
+            const float* wc = w + (long)(c4 * 4) * ksz + j;
+            a0 = fmaf(__ldg(wc), xv, a0);
+            a1 = fmaf(__ldg(wc + ksz), xv, a1);
+            a2 = fmaf(__ldg(wc + 2 * ksz), xv, a2);
+            a3 = fmaf(__ldg(wc + 3 * ksz), xv, a3);
+        }
+        float4 o = make_float4(fmaxf(a0, 0.f), fmaxf(a1, 0.f), fmaxf(a2, 0.f), fmaxf(a3, 0.f));
+        reinterpret_cast<float4*>(enc)[idx] = o;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-utterance statistics over a contiguous slab: partial[b][p] = {sum, sumsq} in fp64
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) utt_stats_kernel(const float* __restrict__ x, double* __restrict__ partial,
+                                                        long elems4) {
+    __shared__ double scratch[32];
+    const int b = blockIdx.y, p = blockIdx.x;
+    const float4* xb = reinterpret_cast<const float4*>(x) + (long)b * elems4;
+    const long per = (elems4 + gridDim.x - 1) / gridDim.x;
+    const long beg = p * per, end = min(beg + per, elems4);
+    double ds = 0.0, dq = 0.0;
+    long i = beg + threadIdx.x;
+    while (i < end) {
+        float s = 0.f, q = 0.f;
+#pragma unroll 4
+        for (int u = 0; u < 16 && i < end; ++u, i += blockDim.x) {
+            const float4 v = ld_stream(xb + i);
+            s += (v.x + v.y) + (v.z + v.w);
+            q = fmaf(v.x, v.x, q); q = fmaf(v.y, v.y, q); q = fmaf(v.z, v.z, q); q = fmaf(v.w, v.w, q);
+        }
+        ds += (double)s; dq += (double)q;
+    }
+    ds = block_sum(ds, scratch);
+    dq = block_sum(dq, scratch);
+    if (threadIdx.x == 0) {
+        partial[((long)b * gridDim.x + p) * 2 + 0] = ds;
+        partial[((long)b * gridDim.x + p) * 2 + 1] = dq;
+    }
+}
+
+__global__ void utt_stats_finalize_kernel(const double* __restrict__ partial, float* __restrict__ mean_rstd,
+                                          int nparts, double count, double eps) {
+    const int b = blockIdx.x, lane = threadIdx.x;
+    double s = 0.0, q = 0.0;
+    for (int p = lane; p < nparts; p += 32) {
+        s += partial[((long)b * nparts + p) * 2 + 0];
+        q += partial[((long)b * nparts + p) * 2 + 1];
+    }
+    s = warp_sum(s); q = warp_sum(q);
+    if (lane == 0) {
+        const double mean = s / count;
+        double var = q / count - mean * mean;
+        if (var < 0.0) var = 0.0;
+        mean_rstd[2 * b + 0] = (float)mean;
+        mean_rstd[2 * b + 1] = (float)(1.0 / sqrt(var + eps));
+    }
+}
+
+// s1[b,c] = gamma*rstd*mul ; s0[b,c] = (beta - mean*gamma*rstd)*mul
+__global__ void norm_affine_kernel(const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, const float* __restrict__ mulc,
+                                   float* __restrict__ s1, float* __restrict__ s0, int B, int C) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * C) return;
+    const int b = idx / C, c = idx % C;
+    const float mean = mean_rstd[2 * b], rstd = mean_rstd[2 * b + 1];
+    const float m = mulc ? mulc[idx] : 1.0f;
+    const float g = gamma[c] * rstd;
+    s1[idx] = g * m;
+    s0[idx] = (beta[c] - mean * g) * m;
+}
+
+// x[b,r,c] += (y[b,r,c] - mean_b) * rstd_b * gamma_c + beta_c
+__global__ void norm_residual_kernel(const float* __restrict__ y, float* __restrict__ x,
+                                     const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                     const float* __restrict__ beta, long total4, long per_utt4, int c4n) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        const long b = idx / per_utt4;
+        const int c4 = (int)(idx % c4n);
+        const float mean = __ldg(mean_rstd + 2 * b), rstd = __ldg(mean_rstd + 2 * b + 1);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+        const float4 v = ld_stream(reinterpret_cast<const float4*>(y) + idx);
+        float4 r = reinterpret_cast<float4*>(x)[idx];
+        r.x += (v.x - mean) * rstd * g.x + be.x;
+        r.y += (v.y - mean) * rstd * g.y + be.y;
+        r.z += (v.z - mean) * rstd * g.z + be.z;
+        r.w += (v.w - mean) * rstd * g.w + be.w;
+        reinterpret_cast<float4*>(x)[idx] = r;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// unfold: out[b,s,k,:] = y[b, s*P + k - K, :] (zero outside [0,L))
+// ------------------------------------------------------------------------------------------
+__global__ void unfold_kernel(const float* __restrict__ y, float* __restrict__ out, int B, long L, int S, int K,
+                              int P, int f4n) {
+    const long total = (long)B * S * K * f4n;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int f4 = (int)(idx % f4n);
+        long r = idx / f4n;
+        const int k = (int)(r % K); r /= K;
+        const int s = (int)(r % S);
+        const long b = r / S;
+        const long t = (long)s * P + k - K;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t >= 0 && t < L) v = __ldg(reinterpret_cast<const float4*>(y) + (b * L + t) * f4n + f4);
+        reinterpret_cast<float4*>(out)[idx] = v;
+    }
+}
+
+// fold (+ optional PReLU on the way in): out[b,t,:] = sum_{s: 0 <= t+K-sP < K} prelu(x[b,s,t+K-sP,:])
+__global__ void fold_prelu_kernel(const float* __restrict__ x, float* __restrict__ out, int B, long L, int S,
+                                  int K, int P, int f4n, const float* __restrict__ prelu_a) {
+    const long total = (long)B * L * f4n;
+    const float a = prelu_a ? __ldg(prelu_a) : 1.0f;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int f4 = (int)(idx % f4n);
+        const long r = idx / f4n;
+        const long t = r % L, b = r / L;
+        long s_lo = t / P + 1, s_hi = (t + K) / P;
+        if (s_hi > S - 1) s_hi = S - 1;
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (long s = s_lo; s <= s_hi; ++s) {
+            const long k = t + K - s * P;
+            float4 v = ld_stream(reinterpret_cast<const float4*>(x) + ((b * S + s) * K + k) * f4n + f4);
+            v.x = v.x >= 0.f ? v.x : a * v.x;
+            v.y = v.y >= 0.f ? v.y : a * v.y;
+            v.z = v.z >= 0.f ? v.z : a * v.z;
+            v.w = v.w >= 0.f ? v.w : a * v.w;
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        reinterpret_cast<float4*>(out)[idx] = acc;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// mask * enc -> ConvTranspose1d(N -> 1, ksz, stride): one warp per output sample
+// ------------------------------------------------------------------------------------------
+__global__ void mask_decode_kernel(const float* __restrict__ mask, long mask_utt_stride,
+                                   const float* __restrict__ enc, const float* __restrict__ wdec,
+                                   float* __restrict__ out, long out_utt_stride, int B, long L, int T, int N,
+                                   int ksz, int stride) {
+    const int lane = threadIdx.x & 31;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long o = warp; o < (long)B * T; o += nwarps) {
+        const long b = o / T, t = o % T;
+        float acc = 0.f;
+        for (int j = 0; j < ksz; ++j) {
+            const long tl = t - j;
+            if (tl < 0 || tl % stride) continue;
+            const long l = tl / stride;
+            if (l >= L) continue;
+            const float* m = mask + b * mask_utt_stride + l * N;
+            const float* e = enc + (b * L + l) * N;
+            for (int c = lane; c < N; c += 32) acc = fmaf(m[c] * e[c], __ldg(wdec + c * ksz + j), acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[b * out_utt_stride + t] = acc;
+    }
+}
+
+// out = mask * enc (the IRA re-embedding input d0, dprnn_spe_ira.py:79-80)
+__global__ void mask_apply_kernel(const float* __restrict__ mask, const float* __restrict__ enc,
+                                  float* __restrict__ out, long total4) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        const float4 m = reinterpret_cast<const float4*>(mask)[idx];
+        const float4 e = reinterpret_cast<const float4*>(enc)[idx];
+        reinterpret_cast<float4*>(out)[idx] = make_float4(m.x * e.x, m.y * e.y, m.z * e.z, m.w * e.w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// attention fusion helpers
+// ------------------------------------------------------------------------------------------
+// score[b,la] = sum_c v[b,c] * (bavg[c] + sum_j wavg[c,j] * (enc[b,la*k+j,c]*s1[b,c] + s0[b,c]))
+__global__ void att_scores_kernel(const float* __restrict__ enc, const float* __restrict__ s1,
+                                  const float* __restrict__ s0, const float* __restrict__ wavg,
+                                  const float* __restrict__ bavg, const float* __restrict__ v,
+                                  float* __restrict__ score, int B, long L, long La, int N, int ksz) {
+    const int lane = threadIdx.x & 31;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long o = warp; o < (long)B * La; o += nwarps) {
+        const long b = o / La, la = o % La;
+        float acc = 0.f;
+        for (int c = lane; c < N; c += 32) {
+            float avg = __ldg(bavg + c);
+            for (int j = 0; j < ksz; ++j) {
+                const float xn = enc[(b * L + la * ksz + j) * N + c] * s1[b * N + c] + s0[b * N + c];
+                avg = fmaf(__ldg(wavg + c * ksz + j), xn, avg);
+            }
+            acc = fmaf(avg, v[b * N + c], acc);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) score[o] = acc;
+    }
+}
+
+// in-place softmax over each row of [B, La]; one CTA per row
+__global__ void __launch_bounds__(256) softmax_rows_kernel(float* __restrict__ x, long La) {
+    __shared__ float red[32];
+    __shared__ double scratch[32];
+    float* row = x + (long)blockIdx.x * La;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    float m = -INFINITY;
+    for (long i = threadIdx.x; i < La; i += blockDim.x) m = fmaxf(m, row[i]);
+    m = warp_max(m);
+    if (lane == 0) red[wid] = m;
+    __syncthreads();
+    m = red[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) m = fmaxf(m, red[w]);
+    double s = 0.0;
+    for (long i = threadIdx.x; i < La; i += blockDim.x) s += (double)expf(row[i] - m);
+    s = block_sum(s, scratch);
+    const float inv = (float)(1.0 / s);
+    for (long i = threadIdx.x; i < La; i += blockDim.x) row[i] = expf(row[i] - m) * inv;
+}
+
+// rowscale[b,l] = 1 + sm[b, min(floor(l*scale), La-1)]   (ATen nearest-upsample index rule)
+__global__ void att_rowscale_kernel(const float* __restrict__ sm, float* __restrict__ rowscale, int B, long L,
+                                    long La, float scale) {
+    const long total = (long)B * L;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long b = idx / L, l = idx % L;
+        long src;
+        if (La == L) src = l;
+        else if (L == 2 * La) src = l >> 1;
+        else {
+            src = (long)floorf(__fmul_rn((float)l, scale));
+            if (src > La - 1) src = La - 1;
+        }
+        rowscale[idx] = 1.0f + sm[b * La + src];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// speaker ResNet pieces
+// ------------------------------------------------------------------------------------------
+// per-channel partial sums over rows: partial[p][c] = {sum, sumsq}; blockDim = 256, C in {64,128,256}
+__global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ y, double* __restrict__ partial,
+                                                            long rows, int C) {
+    __shared__ double sh[2][256];
+    const int lanes = 256 / C;
+    const int c = threadIdx.x % C, rl = threadIdx.x / C;
+    const long per = (rows + gridDim.x - 1) / gridDim.x;
+    const long beg = blockIdx.x * per, end = min(beg + per, rows);
+    double ds = 0.0, dq = 0.0;
+    long r = beg + rl;
+    while (r < end) {
+        float s = 0.f, q = 0.f;
+        for (int u = 0; u < 32 && r < end; ++u, r += lanes) {
+            const float v = y[r * C + c];
+            s += v; q = fmaf(v, v, q);
+        }
+        ds += (double)s; dq += (double)q;
+    }
+    sh[0][threadIdx.x] = ds; sh[1][threadIdx.x] = dq;
+    __syncthreads();
+    if (rl == 0) {
+        for (int i = 1; i < lanes; ++i) { ds += sh[0][i * C + c]; dq += sh[1][i * C + c]; }
+        partial[((long)blockIdx.x * C + c) * 2 + 0] = ds;
+        partial[((long)blockIdx.x * C + c) * 2 + 1] = dq;
+    }
+}
+
+// BatchNorm1d scale/shift. training: batch stats from partials (+ running update, momentum 0.1,
+// unbiased variance); eval: running stats.
+__global__ void bn_finalize_kernel(const double* __restrict__ partial, int nparts, double count,
+                                   const float* __restrict__ weight, const float* __restrict__ bias,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ scale, float* __restrict__ shift, int C, int training,
+                                   float eps, float momentum) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float mean, var;
+    if (training) {
+        double s = 0.0, q = 0.0;
+        for (int p = 0; p < nparts; ++p) {
+            s += partial[((long)p * C + c) * 2 + 0];
+            q += partial[((long)p * C + c) * 2 + 1];
+        }
+        const double m = s / count;
+        double v = q / count - m * m;
+        if (v < 0.0) v = 0.0;
+        mean = (float)m; var = (float)v;
+        if (running_mean) {
+            const double unb = count > 1.0 ? v * count / (count - 1.0) : v;
+            running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * mean;
+            running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
+        }
+    } else {
+        mean = running_mean[c]; var = running_var[c];
+    }
+    const float sc = weight[c] / sqrtf(var + eps);
+    scale[c] = sc;
+    shift[c] = bias[c] - mean * sc;
+}
+
+// out = prelu(y*scale[c] + shift[c])
+__global__ void affine_prelu_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, const float* __restrict__ prelu_a,
+                                    float* __restrict__ out, long total4, int c4n) {
+    const float a = __ldg(prelu_a);
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n);
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+        float4 v = reinterpret_cast<const float4*>(y)[idx];
+        v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        v.x = v.x >= 0.f ? v.x : a * v.x; v.y = v.y >= 0.f ? v.y : a * v.y;
+        v.z = v.z >= 0.f ? v.z : a * v.z; v.w = v.w >= 0.f ? v.w : a * v.w;
+        reinterpret_cast<float4*>(out)[idx] = v;
+    }
+}
+
+// out[b,lp,c] = max_{i<3} prelu(y[b,3lp+i,c]*scale[c] + shift[c] + skip[b,3lp+i,c])
+__global__ void affine_add_prelu_pool3_kernel(const float* __restrict__ y, const float* __restrict__ scale,
+                                              const float* __restrict__ shift, const float* __restrict__ skip,
+                                              const float* __restrict__ prelu_a, float* __restrict__ out, int B,
+                                              long Lin, long Lout, int c4n) {
+    const float a = __ldg(prelu_a);
+    const long total = (long)B * Lout * c4n;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n);
+        const long r = idx / c4n;
+        const long lp = r % Lout, b = r / Lout;
+        const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + c4);
+        const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + c4);
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+#pragma unroll
+        for (int i = 0; i < 3; ++i) {
+            const long src = (b * Lin + lp * 3 + i) * c4n + c4;
+            float4 v = reinterpret_cast<const float4*>(y)[src];
+            const float4 k = reinterpret_cast<const float4*>(skip)[src];
+            v.x = fmaf(v.x, sc.x, sh.x) + k.x; v.y = fmaf(v.y, sc.y, sh.y) + k.y;
+            v.z = fmaf(v.z, sc.z, sh.z) + k.z; v.w = fmaf(v.w, sc.w, sh.w) + k.w;
+            v.x = v.x >= 0.f ? v.x : a * v.x; v.y = v.y >= 0.f ? v.y : a * v.y;
+            v.z = v.z >= 0.f ? v.z : a * v.z; v.w = v.w >= 0.f ? v.w : a * v.w;
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+        reinterpret_cast<float4*>(out)[idx] = m;
+    }
+}
+
+// emb[b,c] = (sum_l x[b,l,c]) / div[b]; one CTA (256 threads) per utterance, C in {64,128,256}
+__global__ void __launch_bounds__(256) time_sum_kernel(const float* __restrict__ x, float* __restrict__ emb, long Lx,
+                                                       int C, const float* __restrict__ div) {
+    __shared__ double sh[256];
+    const int lanes = 256 / C;
+    const int c = threadIdx.x % C, rl = threadIdx.x / C;
+    const float* xb = x + (long)blockIdx.x * Lx * C;
+    double s = 0.0;
+    for (long l = rl; l < Lx; l += lanes) s += (double)xb[l * C + c];
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (rl == 0) {
+        for (int i = 1; i < lanes; ++i) s += sh[i * C + c];
+        emb[(long)blockIdx.x * C + c] = (float)s / div[blockIdx.x];
+    }
+}
+
+// out[b,n] (+)= bias[n] + sum_k in[b*ldin + k] * W[n*ldw + k]; one warp per output
+__global__ void small_linear_kernel(const float* __restrict__ in, long ldin, const float* __restrict__ W, long ldw,
+                                    const float* __restrict__ bias, float* __restrict__ out, long ldout, int B, int N,
+                                    int K, int accumulate) {
+    const int lane = threadIdx.x & 31;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    if (warp >= (long)B * N) return;
+    const long b = warp / N, n = warp % N;
+    float acc = 0.f;
+    for (int k = lane; k < K; k += 32) acc = fmaf(in[b * ldin + k], __ldg(W + n * ldw + k), acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        if (bias) acc += bias[n];
+        if (accumulate) acc += out[b * ldout + n];
+        out[b * ldout + n] = acc;
+    }
+}
+
+static inline unsigned grid_for(long total, int threads) {
+    long g = (total + threads - 1) / threads;
+    const long cap = 148L * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace dprnn
+
+using namespace dprnn;
+
+extern "C" {
+
+int dprnn_encoder_fwd(const float* wave, const float* w, float* enc, int B, int T, int N, int ksz, int stride,
+                      void* stream) {
+    DPRNN_CHECK_ARG(wave && w && enc && B > 0 && N > 0 && N % 4 == 0 && ksz > 0 && stride > 0 && T >= ksz);
+    const long L = (T - ksz) / stride + 1;
+    const long total = (long)B * L * (N / 4);
+    encoder_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>(wave, w, enc, B, T, L, N, ksz, stride);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+size_t dprnn_utt_stats_workspace_bytes(int B) { return (size_t)B * kStatParts * 2 * sizeof(double); }
+
+int dprnn_utt_stats(const float* x, int B, long elems_per_utt, float eps, void* workspace, float* mean_rstd,
+                    void* stream) {
+    DPRNN_CHECK_ARG(x && workspace && mean_rstd && B > 0 && elems_per_utt > 0 && elems_per_utt % 4 == 0);
+    DPRNN_CHECK_ARG(B <= 65535);
+    dim3 grid(kStatParts, B);
+    utt_stats_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, (double*)workspace, elems_per_utt / 4);
+    DPRNN_CHECK_LAUNCH();
+    utt_stats_finalize_kernel<<<B, 32, 0, (cudaStream_t)stream>>>((const double*)workspace, mean_rstd, kStatParts,
+                                                                 (double)elems_per_utt, (double)eps);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_norm_affine(const float* mean_rstd, const float* gamma, const float* beta, const float* mulc, float* s1,
+                      float* s0, int B, int C, void* stream) {
+    DPRNN_CHECK_ARG(mean_rstd && gamma && beta && s1 && s0 && B > 0 && C > 0);
+    norm_affine_kernel<<<cdiv((long)B * C, 256), 256, 0, (cudaStream_t)stream>>>(mean_rstd, gamma, beta, mulc, s1, s0,
+                                                                               B, C);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                        int B, long rows_per_utt, int C, void* stream) {
+    DPRNN_CHECK_ARG(y && x && mean_rstd && gamma && beta && B > 0 && rows_per_utt > 0 && C % 4 == 0);
+    const long per4 = rows_per_utt * (C / 4);
+    norm_residual_kernel<<<grid_for(per4 * B, 256), 256, 0, (cudaStream_t)stream>>>(y, x, mean_rstd, gamma, beta,
+                                                                                  per4 * B, per4, C / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_num_chunks(long L, int K, int P) { return (int)((L + K) / P + 1); }
+
+int dprnn_unfold(const float* y, float* x, int B, long L, int K, int P, int F, void* stream) {
+    DPRNN_CHECK_ARG(y && x && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);
+    const int S = dprnn_num_chunks(L, K, P);
+    unfold_kernel<<<grid_for((long)B * S * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, x, B, L, S, K, P,
+                                                                                           F / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_fold_prelu(const float* x, float* out, int B, long L, int K, int P, int F, const float* prelu_a,
+                     void* stream) {
+    DPRNN_CHECK_ARG(x && out && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);
+    const int S = dprnn_num_chunks(L, K, P);
+    fold_prelu_kernel<<<grid_for((long)B * L * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, L, S, K, P,
+                                                                                           F / 4, prelu_a);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_mask_decode(const float* mask, long mask_utt_stride, const float* enc, const float* wdec, float* out,
+                      long out_utt_stride, int B, long L, int N, int ksz, int stride, void* stream) {
+    DPRNN_CHECK_ARG(mask && enc && wdec && out && B > 0 && L > 0 && N > 0 && ksz > 0 && stride > 0);
+    const int T = (int)((L - 1) * stride + ksz);
+    mask_decode_kernel<<<grid_for((long)B * T * 32, 256), 256, 0, (cudaStream_t)stream>>>(
+        mask, mask_utt_stride, enc, wdec, out, out_utt_stride, B, L, T, N, ksz, stride);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_mask_apply(const float* mask, const float* enc, float* out, long elems, void* stream) {
+    DPRNN_CHECK_ARG(mask && enc && out && elems > 0 && elems % 4 == 0);
+    mask_apply_kernel<<<grid_for(elems / 4, 256), 256, 0, (cudaStream_t)stream>>>(mask, enc, out, elems / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_att_rowscale(const float* enc, const float* s1, const float* s0, const float* wavg, const float* bavg,
+                       const float* v, float* scores, float* rowscale, int B, long L, int N, int ksz, void* stream) {
+    DPRNN_CHECK_ARG(enc && s1 && s0 && wavg && bavg && v && scores && rowscale && B > 0 && N > 0 && ksz > 0 && L >= ksz);
+    const long La = (L - ksz) / ksz + 1;
+    att_scores_kernel<<<grid_for((long)B * La * 32, 256), 256, 0, (cudaStream_t)stream>>>(enc, s1, s0, wavg, bavg, v,
+                                                                                        scores, B, L, La, N, ksz);
+    DPRNN_CHECK_LAUNCH();
+    softmax_rows_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(scores, La);
+    DPRNN_CHECK_LAUNCH();
+    const float scale = (float)La / (float)L;   // ATen: static_cast<float>(input_size) / output_size
+    att_rowscale_kernel<<<grid_for((long)B * L, 256), 256, 0, (cudaStream_t)stream>>>(scores, rowscale, B, L, La,
+                                                                                    scale);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+size_t dprnn_bn_workspace_bytes(int C) { return (size_t)kStatParts * C * 2 * sizeof(double); }
+
+int dprnn_batchnorm_affine(const float* y, long rows, int C, const float* weight, const float* bias,
+                           float* running_mean, float* running_var, int training, float eps, float momentum,
+                           void* workspace, float* scale, float* shift, void* stream) {
+    DPRNN_CHECK_ARG(weight && bias && scale && shift && C > 0 && 256 % C == 0);
+    if (training) {
+        DPRNN_CHECK_ARG(y && workspace && rows > 0);
+        channel_stats_kernel<<<kStatParts, 256, 0, (cudaStream_t)stream>>>(y, (double*)workspace, rows, C);
+        DPRNN_CHECK_LAUNCH();
+    } else {
+        DPRNN_CHECK_ARG(running_mean && running_var);
+    }
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>((const double*)workspace, kStatParts,
+                                                                     (double)rows, weight, bias, running_mean,
+                                                                     running_var, scale, shift, C, training, eps,
+                                                                     momentum);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_affine_prelu(const float* y, const float* scale, const float* shift, const float* prelu_a, float* out,
+                       long rows, int C, void* stream) {
+    DPRNN_CHECK_ARG(y && scale && shift && prelu_a && out && rows > 0 && C % 4 == 0);
+    affine_prelu_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, scale, shift, prelu_a, out,
+                                                                                       rows * (C / 4), C / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_affine_add_prelu_pool3(const float* y, const float* scale, const float* shift, const float* skip,
+                                 const float* prelu_a, float* out, int B, long Lin, int C, void* stream) {
+    DPRNN_CHECK_ARG(y && scale && shift && skip && prelu_a && out && B > 0 && Lin >= 3 && C % 4 == 0);
+    const long Lout = Lin / 3;
+    affine_add_prelu_pool3_kernel<<<grid_for((long)B * Lout * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        y, scale, shift, skip, prelu_a, out, B, Lin, Lout, C / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_time_sum(const float* x, float* emb, int B, long Lx, int C, const float* div, void* stream) {
+    DPRNN_CHECK_ARG(x && emb && div && B > 0 && Lx > 0 && C > 0 && 256 % C == 0);
+    time_sum_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(x, emb, Lx, C, div);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_small_linear(const float* in, long ldin, const float* W, long ldw, const float* bias, float* out,
+                       long ldout, int B, int N, int K, int accumulate, void* stream) {
+    DPRNN_CHECK_ARG(in && W && out && B > 0 && N > 0 && K > 0);
+    small_linear_kernel<<<cdiv((long)B * N * 32, 256), 256, 0, (cudaStream_t)stream>>>(in, ldin, W, ldw, bias, out,
+                                                                                     ldout, B, N, K, accumulate);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+}  // extern "C"

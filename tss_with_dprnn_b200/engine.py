@@ -1,0 +1,366 @@
+"""Forward orchestration over the C ABI (include/dprnn_b200.h).
+
+PyTorch is used here for device memory (``torch.empty``), the current CUDA stream and one-off weight
+re-layout (transposes / concatenations of the ``state_dict`` tensors); every arithmetic stage of the
+separation path is a kernel of libdprnn_b200.  No stage has a CPU or ATen fallback.
+
+Internal layout is channels-last: frames ``[B, L, C]``, chunks ``[B, S, K, F]`` (a 128-float row per
+chunk position), so intra-chunk sequences are contiguous rows and inter-chunk sequences a constant
+row stride - see DESIGN.md.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import lib
+
+EPI_NONE, EPI_RELU, EPI_SIGMOID, EPI_GATED = 0, 1, 2, 3
+
+
+def _t(w: torch.Tensor) -> torch.Tensor:
+    """[N_out, K_in, ...1] weight -> contiguous [K_in, N_out]."""
+    return w.detach().reshape(w.shape[0], -1).t().contiguous()
+
+
+class Engine:
+    def __init__(self, model):
+        self.model = model
+        self.precision = 'fp32'
+        self._packed = None
+        self._packed_key = None
+
+    def set_precision(self, mode: str):
+        if mode not in ('fp32', 'bf16'):
+            raise ValueError("precision must be 'fp32' or 'bf16'")
+        if mode == 'bf16' and 'bf16' not in lib().build_info():
+            raise RuntimeError('this build of libdprnn_b200 carries no bf16 tensor-core kernels')
+        self.precision = mode
+
+    # ------------------------------------------------------------------ weights
+    def _weights_key(self):
+        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def packed(self):
+        """Kernel-layout copies of the weights, rebuilt whenever a parameter changes."""
+        key = self._weights_key()
+        if self._packed is None or key != self._packed_key:
+            self._packed = self._pack()
+            self._packed_key = key
+        return self._packed
+
+    def _pack(self):
+        m, cfg = self.model, self.model.cfg
+        sep = m.separation
+        N, F = cfg['input_size'], cfg['feature_size']
+        W = {}
+        W['enc'] = m.encoder.conv1d.weight.detach().reshape(N, -1).contiguous()
+        W['dec'] = m.decoder.weight.detach().reshape(N, -1).contiguous()
+        bw = sep.bottleneck[1].weight.detach().reshape(F, -1)           # [F, N(+E)]
+        W['bott_wt'] = bw[:, :N].t().contiguous()
+        W['bott_w_full'] = bw.contiguous()
+        blocks = []
+        for blk in sep.dprnn_blocks:
+            halves = []
+            for rnn, lin in ((blk.intra_rnn.rnn, blk.intra_linear), (blk.inter_rnn.rnn, blk.inter_linear)):
+                sfx = ['', '_reverse'] if rnn.bidirectional else ['']
+                wih = torch.cat([getattr(rnn, 'weight_ih_l0' + s).detach() for s in sfx], 0)       # [nd*4H, F]
+                bias = torch.cat([(getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s)).detach()
+                                  for s in sfx], 0)
+                whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach().t() for s in sfx], 0)  # [nd, H, 4H]
+                halves.append(dict(wih_t=wih.t().contiguous(), bias=bias.contiguous(), whh_t=whh.contiguous(),
+                                   ndir=len(sfx), lin_t=_t(lin.weight), lin_b=lin.bias.detach()))
+            blocks.append(halves)
+        W['blocks'] = blocks
+        cw = sep.conv2d.weight.detach().reshape(2 * F, F)
+        W['conv2d_t'] = [cw[s * F:(s + 1) * F].t().contiguous() for s in range(2)]
+        W['conv2d_b'] = [sep.conv2d.bias.detach()[s * F:(s + 1) * F].contiguous() for s in range(2)]
+        # gated head: per 128-column tile, 64 'out' units followed by the matching 64 'gate' units
+        wo, wg = sep.out[0].weight.detach().reshape(F, F), sep.gate[0].weight.detach().reshape(F, F)
+        bo, bg = sep.out[0].bias.detach(), sep.gate[0].bias.detach()
+        cols, bias = [], []
+        for t0 in range(0, F, 64):
+            cols += [wo[t0:t0 + 64].t(), wg[t0:t0 + 64].t()]
+            bias += [bo[t0:t0 + 64], bg[t0:t0 + 64]]
+        W['og_t'] = torch.cat(cols, 1).contiguous()       # [F, 2F]
+        W['og_b'] = torch.cat(bias, 0).contiguous()
+        W['end_t'] = _t(sep.end_conv1x1.weight)            # [F, N]
+        if cfg['kind'] != 'bss':
+            se = sep.spk_encoder
+            W['spk_conv0_t'] = _t(se[1].weight)
+            W['spk_res'] = [dict(c1=_t(rb.conv1.weight), c2=_t(rb.conv2.weight),
+                                 down=_t(rb.conv_downsample.weight) if hasattr(rb, 'conv_downsample') else None)
+                            for rb in (se[2], se[3], se[4])]
+            W['spk_conv5_t'] = _t(se[5].weight)
+        return W
+
+    # ------------------------------------------------------------------ helpers
+    @staticmethod
+    def _stream():
+        return torch.cuda.current_stream().cuda_stream
+
+    @staticmethod
+    def _check_input(x, name):
+        if not isinstance(x, torch.Tensor) or not x.is_cuda:
+            raise RuntimeError(f'{name} must be a CUDA tensor: tss_with_dprnn_b200 has no CPU path')
+        if x.dtype != torch.float32:
+            raise TypeError(f'{name} must be float32')
+        return x.contiguous()
+
+    def _norm_params(self, mod):
+        if hasattr(mod, 'gamma'):
+            return mod.gamma.detach(), mod.beta.detach(), 1e-8       # GlobLN (norms.py:9)
+        return mod.weight.detach(), mod.bias.detach(), mod.eps
+
+    def _guard_autograd(self):
+        if torch.is_grad_enabled() and self.model.training and any(p.requires_grad for p in self.model.parameters()):
+            raise NotImplementedError(
+                'backward of the B200 separation path is not built yet (SURVEY.md section 8, cfg 5): call under '
+                'torch.no_grad() or model.eval()')
+
+    def gemm(self, A, Wt, M, N, K, out=None, bias=None, bias_per_utt=False, bias_scale=1.0, rows_per_utt=0,
+             p_scale=None, p_shift=None, p_add=None, rowscale=None, epi=EPI_NONE):
+        n_out = N // 2 if epi == EPI_GATED else N
+        if out is None:
+            out = torch.empty((M, n_out), device=A.device, dtype=torch.float32)
+        lib().call('dprnn_gemm_f32', A, K, Wt, N, out, n_out, M, N, K, bias, int(bias_per_utt), float(bias_scale),
+                   int(rows_per_utt), p_scale, p_shift, p_add, rowscale, epi, self._stream())
+        return out
+
+    def utt_stats(self, x, B, elems, eps):
+        L = lib()
+        ws = torch.empty(L.query('dprnn_utt_stats_workspace_bytes', B), device=x.device, dtype=torch.uint8)
+        mr = torch.empty((B, 2), device=x.device, dtype=torch.float32)
+        L.call('dprnn_utt_stats', x, B, elems, float(eps), ws, mr, self._stream())
+        return mr
+
+    def small_linear(self, x, lin, B, out=None, accumulate=False, w_off=0, K=None, bias=True):
+        Wm = lin.weight.detach()
+        N, Kfull = Wm.shape[0], Wm.reshape(Wm.shape[0], -1).shape[1]
+        K = Kfull - w_off if K is None else K
+        if out is None:
+            out = torch.empty((B, N), device=x.device, dtype=torch.float32)
+        wptr = Wm.data_ptr() + 4 * w_off
+        b = lin.bias.detach() if (bias and lin.bias is not None) else None
+        lib().call('dprnn_small_linear', x, x.shape[1], wptr, Kfull, b, out, N, B, N, K, int(accumulate),
+                   self._stream())
+        return out
+
+    def encode(self, wave):
+        cfg, W = self.model.cfg, self.packed()
+        B, T = wave.shape
+        k, st, N = cfg['kernel_size'], cfg['stride'], cfg['input_size']
+        if T < k:
+            raise ValueError(f'input has {T} samples, fewer than the encoder kernel ({k})')
+        L = (T - k) // st + 1
+        enc = torch.empty((B, L, N), device=wave.device, dtype=torch.float32)
+        lib().call('dprnn_encoder_fwd', wave, W['enc'], enc, B, T, N, k, st, self._stream())
+        return enc, L
+
+    # ------------------------------------------------------------------ speaker branch
+    def _aux_div(self, aux_len, B, device):
+        """aux_T of DPRNNSpe._auxiliary (dprnn_spe.py:159-160), from the caller's scalar (or [B]) tensor."""
+        k = self.model.cfg['kernel_size']
+        al = aux_len if isinstance(aux_len, torch.Tensor) else torch.tensor(float(aux_len))
+        t = (al - k) // (k // 2) + 1
+        t = ((t // 3) // 3) // 3
+        t = t.reshape(-1).float().to(device)
+        return t.expand(B).contiguous() if t.numel() == 1 else t.contiguous()
+
+    def speaker_embedding(self, feats, B, Lr, div):
+        """spk_encoder + time mean (dprnn_spe.py:115-122,156-163). feats [B,Lr,N] -> [B,E]."""
+        L_, W, st = lib(), self.packed(), self._stream()
+        se = self.model.separation.spk_encoder
+        N = self.model.cfg['input_size']
+        training = self.model.training
+        dev = feats.device
+        mr = self.utt_stats(feats, B, Lr * N, se[0].eps)
+        s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
+        L_.call('dprnn_norm_affine', mr, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
+        O = se[1].weight.shape[0]
+        x = self.gemm(feats, W['spk_conv0_t'], B * Lr, O, N, bias=se[1].bias.detach(), rows_per_utt=Lr,
+                      p_scale=s1, p_shift=s0)
+        Lx = Lr
+        for rb, wr in zip((se[2], se[3], se[4]), W['spk_res']):
+            Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
+            rows = B * Lx
+            ws = torch.empty(L_.query('dprnn_bn_workspace_bytes', Cout), device=dev, dtype=torch.uint8)
+            scale = torch.empty(Cout, device=dev); shift = torch.empty(Cout, device=dev)
+
+            def bn(y, bnm):
+                L_.call('dprnn_batchnorm_affine', y, rows, Cout, bnm.weight.detach(), bnm.bias.detach(),
+                        bnm.running_mean, bnm.running_var, int(training), float(bnm.eps),
+                        float(bnm.momentum if bnm.momentum is not None else 0.1), ws, scale, shift, st)
+                if training:
+                    bnm.num_batches_tracked += 1
+
+            y = self.gemm(x, wr['c1'], rows, Cout, Cin)
+            bn(y, rb.batch_norm1)
+            L_.call('dprnn_affine_prelu', y, scale, shift, rb.prelu1.weight.detach(), y, rows, Cout, st)
+            y2 = self.gemm(y, wr['c2'], rows, Cout, Cout)
+            bn(y2, rb.batch_norm2)
+            skip = x if wr['down'] is None else self.gemm(x, wr['down'], rows, Cout, Cin)
+            Lo = Lx // 3
+            out = torch.empty((B, Lo, Cout), device=dev)
+            L_.call('dprnn_affine_add_prelu_pool3', y2, scale, shift, skip, rb.prelu2.weight.detach(), out, B, Lx,
+                    Cout, st)
+            x, Lx = out, Lo
+        E = se[5].weight.shape[0]
+        z = self.gemm(x, W['spk_conv5_t'], B * Lx, E, se[5].weight.shape[1], bias=se[5].bias.detach())
+        emb = torch.empty((B, E), device=dev)
+        L_.call('dprnn_time_sum', z, emb, B, Lx, E, div, st)
+        return emb
+
+    # ------------------------------------------------------------------ masker
+    def masker(self, enc, mr, B, L, emb, speakers):
+        """bottleneck norm + fusion + 1x1 conv, segmentation, DPRNN blocks, PReLU, overlap-add, conv2d,
+        gated head, activation (dprnn.py:166-187 / dprnn_spe.py:125-154,231-248).
+        enc [B,L,N]; mr its GroupNorm statistics; returns one mask [B,L,N] per requested speaker."""
+        L_, W, st = lib(), self.packed(), self._stream()
+        cfg, sep = self.model.cfg, self.model.separation
+        N, F, H = cfg['input_size'], cfg['feature_size'], cfg['hidden_size']
+        K, P = cfg['chunk_length'], cfg['hop_length']
+        dev = enc.device
+        gamma, beta, _ = self._norm_params(sep.bottleneck[0])
+        ft = cfg['fusion_type']
+        mulc = addc = rowscale = None
+        bias, bias_per_utt = sep.bottleneck[1].bias.detach(), False
+        if ft == 'cat':       # constant channels -> a per-utterance bias W_e e + b
+            bias = self.small_linear(emb, sep.bottleneck[1], B, w_off=N)
+            bias_per_utt = True
+        elif ft == 'add':
+            addc = self.small_linear(emb, sep.fusion_linear, B)
+        elif ft == 'mul':
+            mulc = self.small_linear(emb, sep.fusion_linear, B)
+        elif ft == 'film':
+            mulc = self.small_linear(emb, sep.fusion_linear_1, B)
+            addc = self.small_linear(emb, sep.fusion_linear_2, B)
+        elif ft == 'att':
+            mulc = self.small_linear(emb, sep.fusion_linear, B)
+        s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
+        if ft == 'att':
+            k = cfg['kernel_size']
+            n1 = torch.empty_like(s1); n0 = torch.empty_like(s1)
+            L_.call('dprnn_norm_affine', mr, gamma, beta, None, n1, n0, B, N, st)
+            La = (L - k) // k + 1
+            scores = torch.empty((B, La), device=dev)
+            rowscale = torch.empty((B, L), device=dev)
+            L_.call('dprnn_att_rowscale', enc, n1, n0, sep.average.weight.detach(), sep.average.bias.detach(), mulc,
+                    scores, rowscale, B, L, N, k, st)
+        L_.call('dprnn_norm_affine', mr, gamma, beta, mulc, s1, s0, B, N, st)
+        y = self.gemm(enc, W['bott_wt'], B * L, F, N, bias=bias, bias_per_utt=bias_per_utt, rows_per_utt=L,
+                      p_scale=s1, p_shift=s0, p_add=addc, rowscale=rowscale)
+        S = L_.query('dprnn_num_chunks', L, K, P)
+        x = torch.empty((B, S, K, F), device=dev)
+        L_.call('dprnn_unfold', y, x, B, L, K, P, F, st)
+        del y
+        rows = B * S * K
+        for blk, halves in zip(sep.dprnn_blocks, W['blocks']):
+            for which, hw in enumerate(halves):
+                nd = hw['ndir']
+                gx = self.gemm(x, hw['wih_t'], rows, nd * 4 * H, F, bias=hw['bias'])
+                hout = torch.empty((rows, nd * H), device=dev)
+                if which == 0:    # intra: one sequence per (b, s), steps along k
+                    geo = (B * S, K, 1, K, 0, 1)
+                else:             # inter: one sequence per (b, k), steps along s
+                    geo = (B * K, S, K, S * K, 1, K)
+                L_.call('dprnn_lstm_recurrence_f32', gx, hw['whh_t'], hout, geo[0], geo[1], geo[2], geo[3], geo[4],
+                        geo[5], H, nd, st)
+                del gx
+                yl = self.gemm(hout, hw['lin_t'], rows, F, nd * H, bias=hw['lin_b'])
+                del hout
+                nm = blk.intra_norm if which == 0 else blk.inter_norm
+                g_, b_, eps = self._norm_params(nm)
+                mr2 = self.utt_stats(yl, B, S * K * F, eps)
+                L_.call('dprnn_norm_residual', yl, x, mr2, g_, b_, B, S * K, F, st)
+                del yl
+        z = torch.empty((B, L, F), device=dev)
+        L_.call('dprnn_fold_prelu', x, z, B, L, K, P, F, sep.prelu.weight.detach(), st)
+        del x
+        act = EPI_SIGMOID if cfg['activation_type'] == 'sigmoid' else EPI_RELU
+        masks = []
+        for spk in speakers:
+            # conv2d after the fold: every frame is covered by exactly two chunks, hence 2*bias (A.6)
+            cov = 2.0 if K == 2 * P else None
+            if cov is None:
+                raise NotImplementedError('hop_length must be chunk_length/2 (every shipped config)')
+            u = self.gemm(z, W['conv2d_t'][spk], B * L, F, F, bias=W['conv2d_b'][spk], bias_scale=cov)
+            g = self.gemm(u, W['og_t'], B * L, 2 * F, F, bias=W['og_b'], epi=EPI_GATED)
+            masks.append(self.gemm(g, W['end_t'], B * L, N, F, epi=act).view(B, L, N))
+        return masks
+
+    def decode(self, mask, enc, out, B, L, out_utt_stride):
+        cfg, W = self.model.cfg, self.packed()
+        lib().call('dprnn_mask_decode', mask, L * cfg['input_size'], enc, W['dec'], out, out_utt_stride, B, L,
+                   cfg['input_size'], cfg['kernel_size'], cfg['stride'], self._stream())
+
+    # ------------------------------------------------------------------ whole-model forwards
+    def forward_bss(self, mix):
+        self._guard_autograd()
+        mix = self._check_input(mix, 'input')
+        with torch.no_grad():
+            B, T = mix.shape
+            enc, L = self.encode(mix)
+            N = self.model.cfg['input_size']
+            _, _, eps = self._norm_params(self.model.separation.bottleneck[0])
+            mr = self.utt_stats(enc, B, L * N, eps)
+            masks = self.masker(enc, mr, B, L, None, (0, 1))
+            cfg = self.model.cfg
+            Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
+            out = torch.empty((B, 2, Tout), device=mix.device)
+            for s in (0, 1):
+                self.decode(masks[s], enc, out[:, s], B, L, 2 * Tout)
+            return out
+
+    def forward_spe(self, mix, ref, ref_len, embedding=None):
+        self._guard_autograd()
+        mix = self._check_input(mix, 'input')
+        with torch.no_grad():
+            B, T = mix.shape
+            sep, cfg = self.model.separation, self.model.cfg
+            N = cfg['input_size']
+            enc, L = self.encode(mix)
+            if embedding is None:
+                ref = self._check_input(ref, 'aux')
+                feats, Lr = self.encode(ref)
+                emb = self.speaker_embedding(feats, B, Lr, self._aux_div(ref_len, B, mix.device))
+                del feats
+            else:
+                emb = self._check_input(embedding, 'embedding')
+            _, _, eps = self._norm_params(sep.bottleneck[0])
+            mr = self.utt_stats(enc, B, L * N, eps)
+            mask = self.masker(enc, mr, B, L, emb, (0,))[0]
+            Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
+            est = torch.empty((B, Tout), device=mix.device)
+            self.decode(mask, enc, est, B, L, Tout)
+            logits = self.small_linear(emb, sep.pred_linear, B)
+            return est, logits
+
+    def forward_ira(self, mix, ref, ref_len):
+        self._guard_autograd()
+        mix = self._check_input(mix, 'input')
+        ref = self._check_input(ref, 'aux')
+        with torch.no_grad():
+            B, T = mix.shape
+            sep, cfg = self.model.separation, self.model.cfg
+            N = cfg['input_size']
+            enc, L = self.encode(mix)
+            feats, Lr = self.encode(ref)
+            div = self._aux_div(ref_len, B, mix.device)
+            v0 = self.speaker_embedding(feats, B, Lr, div)
+            del feats
+            _, _, eps = self._norm_params(sep.bottleneck[0])
+            mr = self.utt_stats(enc, B, L * N, eps)
+            mask = self.masker(enc, mr, B, L, v0, (0,))[0]
+            d0 = torch.empty_like(enc)
+            lib().call('dprnn_mask_apply', mask, enc, d0, B * L * N, self._stream())
+            v1 = self.speaker_embedding(d0, B, L, div)          # still divided by the reference's length (:84)
+            del d0
+            E = cfg['embeddings_size']
+            v = self.small_linear(v0, sep.aux_linear, B, K=E)                                  # W[:, :E] v0 + b
+            self.small_linear(v1, sep.aux_linear, B, out=v, accumulate=True, w_off=E, bias=False)   # + W[:, E:] v1
+            mask = self.masker(enc, mr, B, L, v, (0,))[0]
+            Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
+            est = torch.empty((B, Tout), device=mix.device)
+            self.decode(mask, enc, est, B, L, Tout)
+            logits = self.small_linear(v, sep.pred_linear, B)
+            return est, logits
