@@ -45,8 +45,14 @@ def parse_header(path: str = HEADER):
     return protos
 
 
+#: kernels launched per C-ABI call (everything else launches exactly one)
+_LAUNCHES = {'dprnn_utt_stats': 2, 'dprnn_att_rowscale': 3}
+
+
 class _Lib:
     def __init__(self):
+        self.launches = 0          # running count of kernel launches issued through call()
+        self.timing = None         # optional {entry-point name: [(start_event, end_event), ...]}
         if not os.path.exists(LIB_PATH):
             raise RuntimeError(
                 f'{LIB_PATH} is missing. Build it with `python -m tss_with_dprnn_b200.build` (needs nvcc). '
@@ -71,9 +77,19 @@ class _Lib:
                 conv.append(a.data_ptr())
             else:
                 conv.append(a)
+        timed = self.timing is not None and name in self.timing
+        if timed:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         rc = getattr(self.cdll, name)(*conv)
         if rc != 0:
             raise RuntimeError(f'{name} failed (rc={rc}): {self.last_error()}')
+        if timed:
+            ev[1].record()
+            self.timing[name].append(ev)
+        self.launches += _LAUNCHES.get(name, 1)
+        if name == 'dprnn_batchnorm_affine' and conv[7]:
+            self.launches += 1     # training mode adds the batch-statistics kernel
 
     def query(self, name: str, *args):
         return getattr(self.cdll, name)(*args)
