@@ -220,9 +220,8 @@ def run_ours(args):
     e2e_value = audio_per_step * max(1, args.steps) / (ms_e2e / 1e3)
 
     # --- per-kernel pass (separate from the timed region): CUDA events around every launch of the dominant kernel
-    dominant = 'dprnn_lstm_recurrence_bf16' if args.precision == 'bf16' else 'dprnn_lstm_recurrence_f32'
-    names = ['dprnn_lstm_recurrence_f32', 'dprnn_lstm_recurrence_bf16', 'dprnn_gemm_f32', 'dprnn_gemm_bf16',
-             'dprnn_utt_stats', 'dprnn_norm_residual', 'dprnn_unfold', 'dprnn_fold_prelu']
+    dominant = 'dprnn_lstm_layer_bf16' if args.precision == 'bf16' else 'dprnn_lstm_recurrence_f32'
+    names = list(L.protos.keys())
     L.timing = {n: [] for n in names}
     with torch.no_grad():
         step_resident()
@@ -242,14 +241,17 @@ def run_ours(args):
     roofline = None
     if dominant in per_kernel:
         k = per_kernel[dominant]
-        flop_per_launch = RECUR_FLOP_PER_UTT * B / 12         # one launch = one RNN layer (both directions)
+        # one launch = one RNN layer (both directions); the fused bf16 kernel also does the input projection
+        flop_per_launch = (RECUR_FLOP_PER_UTT + (PROJ_FLOP_PER_UTT if args.precision == 'bf16' else 0)) * B / 12
         achieved = flop_per_launch / (k['ms_avg'] * 1e-3) / 1e12
         roofline = {'kernel': dominant, 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
                     'frac': achieved / peak_tf, 'traffic': None,
                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (B200_PROFILING.md)',
                     'share_of_step': k['ms_total'] / (ms_total / args.steps),
-                    'note': 'algorithmic flops = h W_hh^T only (2*128*512 per position and direction); '
-                            'the fp32 mode runs this on CUDA cores, so its fraction of the bf16 tensor peak is small by construction'}
+                    'note': ('algorithmic flops = [x_t|h_{t-1}] [W_ih|W_hh]^T, 2*256*512 per chunk position and direction'
+                             if args.precision == 'bf16' else
+                             'algorithmic flops = h W_hh^T only (2*128*512 per position and direction); the fp32 mode '
+                             'runs this on CUDA cores, so its fraction of the bf16 tensor peak is small by construction')}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -280,7 +282,7 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'fp32'), choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--batch', type=int, default=64, help='utterances per GPU (cfg 2: 64)')
     ap.add_argument('--samples', type=int, default=24000, help='samples per utterance (3 s @ 8 kHz)')
     ap.add_argument('--cpu-batch', type=int, default=1, help='utterances per CPU-baseline forward')

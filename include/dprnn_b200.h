@@ -48,9 +48,10 @@ int dprnn_norm_affine(const float* mean_rstd, const float* gamma, const float* b
                       float* s0, int B, int C, void* stream);
 
 /* intra_norm / inter_norm + residual, src/models/dprnn.py:90-92,98-99:
- * x[b,r,c] += (y[b,r,c]-mean_b)*rstd_b*gamma_c + beta_c. */
+ * x[b,r,c] += (y[b,r,c]-mean_b)*rstd_b*gamma_c + beta_c.  x_bf16 (may be NULL): bf16 copy of the updated x,
+ * the TMA-fed input of the next tensor-core LSTM layer. */
 int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const float* gamma, const float* beta,
-                        int B, long rows_per_utt, int C, void* stream);
+                        int B, long rows_per_utt, int C, void* x_bf16, void* stream);
 
 /* DPRNN._segmentation, src/models/dprnn.py:189-201 (F.unfold, kernel K, pad K, stride P):
  * y [B,L,F] -> x [B,S,K,F], x[b,s,k,:] = y[b, s*P+k-K, :] or 0. S = dprnn_num_chunks(L,K,P). Bit-exact. */
@@ -124,6 +125,29 @@ int dprnn_gemm_f32(const float* A, long lda, const float* Wt, long ldw, float* C
 int dprnn_lstm_recurrence_f32(const float* gx, const float* whhT, float* hout, long nseq, int T, long seq_div,
                               long seq_outer_stride, long seq_inner_stride, long step_stride, int hidden, int ndir,
                               void* stream);
+
+/* ---- bf16 tensor-core mode (tcgen05 + TMA; fp32 accumulation in TMEM) ---- */
+
+/* fp32 -> bf16 (round to nearest even) copy of an activation tensor. */
+int dprnn_cast_bf16(const float* x, void* out, long elems, void* stream);
+
+/* One whole nn.LSTM layer (input projection + recurrence, both directions), src/models/dprnn.py:23-28,35-36,
+ * as a fused tcgen05 kernel: per step gates = [x_t | h_{t-1}] @ [W_ih | W_hh]^T with fp32 accumulators in TMEM,
+ * W resident in the shared memory of a CTA pair (cta_group::2), x_t tiles fed by TMA, cell state in registers.
+ * x [rows,128] bf16 (rows = (b,s,k) chunk positions), hout [rows, ndir*128] bf16.
+ * w_packed [ndir*512, 256] bf16: for direction d, CTA rank r, instruction nh: 128 rows
+ *   {[W_ih | W_hh][q*128 + 64*nh + j, :] : q in (2r, 2r+1), j < 64};  bias_perm[d][nh*256 + q*64 + j] =
+ *   (b_ih + b_hh)[q*128 + 64*nh + j].
+ * inter == 0: sequences (b,s) run along k (intra-chunk); inter == 1: sequences (b,k) run along s.
+ * fast_act != 0: tanh.approx-based activations (1 MUFU op each); 0: expf/tanhf. hidden must be 128. */
+int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S,
+                          int K, int inter, int hidden, int ndir, int fast_act, void* stream);
+
+/* nn.Linear(2H -> F) after each LSTM, src/models/dprnn.py:61,70,86,96, on tensor cores:
+ * C[M,N] (fp32, row stride ldc) = A[M,K] (bf16 row-major) @ W[N,K]^T (bf16, nn.Linear layout) + bias[N].
+ * (N,K) in {(128,256),(128,128),(64,128),(256,128)}. */
+int dprnn_linear_bf16(const void* A, const void* W, const float* bias, float* C, long ldc, int M, int N, int K,
+                      void* stream);
 
 #ifdef __cplusplus
 }

@@ -97,7 +97,7 @@ def test_stats_norm_residual(eps):
     rstd = 1 / torch.sqrt(y.reshape(B, -1).var(1, unbiased=False) + eps)
     assert torch.allclose(mr[:, 0].cpu(), mean, rtol=1e-5, atol=1e-6)
     assert torch.allclose(mr[:, 1].cpu(), rstd, rtol=1e-5)
-    L_().call('dprnn_norm_residual', yd, xd, mr, g.to(DEV), b.to(DEV), B, R, C, stream())
+    L_().call('dprnn_norm_residual', yd, xd, mr, g.to(DEV), b.to(DEV), B, R, C, None, stream())
     assert O.peak_rel_err(xd.cpu(), want.permute(0, 2, 1)) < 2e-6
 
 

@@ -1,0 +1,83 @@
+"""Tensor-core (tcgen05 + TMA) kernels against fp64 references computed from the same bf16-rounded inputs."""
+import pytest
+import torch
+
+from oracle import dprnn_oracle as O
+import tss_with_dprnn_b200 as P
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+@pytest.mark.parametrize('M,N,K', [(128, 128, 256), (1000, 128, 256), (48500, 128, 256), (300, 128, 128),
+                                   (257, 64, 128), (129, 256, 128)])
+def test_linear_bf16(M, N, K):
+    A = rnd(M, K, seed=M).bfloat16()
+    W = (rnd(N, K, seed=N) / K ** 0.5).bfloat16()
+    bias = rnd(N, seed=3)
+    ref = (A.double() @ W.double().t() + bias.double()).float()
+    out = torch.full((M, N), float('nan'), device=DEV)
+    P.lib().call('dprnn_linear_bf16', A.to(DEV), W.to(DEV), bias.to(DEV), out, N, M, N, K, stream())
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert O.peak_rel_err(out.cpu(), ref) < 1e-5      # exact products, fp32 accumulation
+
+
+def lstm_bf16_reference(x, rnn, reverse_flags, exact_h_rounding=True):
+    """fp32 restatement of what dprnn_lstm_layer_bf16 computes: bf16 x / weights / recurrent h, fp32 accumulation and
+    state, exact activations. x [nseq, T, 128] (already bf16-representable)."""
+    outs = []
+    for d, rev in enumerate(reverse_flags):
+        sf = '_reverse' if rev else ''
+        wih = getattr(rnn, 'weight_ih_l0' + sf).detach().bfloat16().float()
+        whh = getattr(rnn, 'weight_hh_l0' + sf).detach().bfloat16().float()
+        b = (getattr(rnn, 'bias_ih_l0' + sf) + getattr(rnn, 'bias_hh_l0' + sf)).detach()
+        N, T, H = x.shape[0], x.shape[1], 128
+        h = torch.zeros(N, H); c = torch.zeros(N, H)
+        out = torch.empty(N, T, H)
+        for t in (range(T - 1, -1, -1) if rev else range(T)):
+            g = x[:, t] @ wih.t() + h.bfloat16().float() @ whh.t() + b
+            i, f, gg, o = g.split(H, 1)
+            c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
+            h = torch.sigmoid(o) * torch.tanh(c)
+            out[:, t] = h
+        outs.append(out)
+    return torch.cat(outs, -1)
+
+
+@pytest.mark.parametrize('inter', [0, 1])
+@pytest.mark.parametrize('ndir', [2, 1])
+@pytest.mark.parametrize('fast', [0, 1])
+def test_lstm_layer_bf16(inter, ndir, fast):
+    from tss_with_dprnn_b200.engine import Engine
+    H = 128
+    # intra: 300 sequences (more than one 256-sequence pair tile, ragged tail), T = 37
+    # inter: K = 250 sequences per utterance (one pair tile per utterance, 6 rows of zero-filled padding), T = 21
+    B, S, K = (3, 100, 37) if not inter else (3, 21, 250)
+    rows = B * S * K
+    torch.manual_seed(21 + inter)
+    rnn = torch.nn.LSTM(H, H, batch_first=True, bidirectional=(ndir == 2))
+    x = rnd(B, S, K, H, seed=22).bfloat16()
+    xf = x.float()
+    seqs = xf.reshape(B * S, K, H) if not inter else xf.permute(0, 2, 1, 3).reshape(B * K, S, H)
+    want = lstm_bf16_reference(seqs, rnn, [False, True][:ndir])
+    want = want.reshape(B, S, K, ndir * H) if not inter else want.reshape(B, K, S, ndir * H).permute(0, 2, 1, 3)
+    wp, bp = Engine._pack_lstm_tc(rnn, ['', '_reverse'][:ndir])
+    hout = torch.full((rows, ndir * H), float('nan'), device=DEV, dtype=torch.bfloat16)
+    P.lib().call('dprnn_lstm_layer_bf16', x.reshape(rows, H).to(DEV), wp.to(DEV), bp.to(DEV), hout, B, S, K, inter, H, ndir,
+                 fast, stream())
+    torch.cuda.synchronize()
+    got = hout.float().cpu().view(B, S, K, ndir * H)
+    assert torch.isfinite(got).all()
+    err = O.peak_rel_err(got, want)
+    # bf16 output rounding (2^-9) + rounding flips of the recurrent h; tanh.approx adds ~2^-11
+    assert err < (1.5e-2 if fast else 1e-2), err
+    assert (got - want).abs().mean() < 2e-3

@@ -17,8 +17,6 @@ extern "C" const char* dprnn_last_error(void) { return dprnn::g_err; }
 
 extern "C" const char* dprnn_build_info(void) {
     return "libdprnn_b200;arch=sm_100a;modes=fp32"
-#ifdef DPRNN_HAVE_TC
            ",bf16-tcgen05"
-#endif
            ";cuda=" DPRNN_STR(CUDART_VERSION);
 }

@@ -1,0 +1,304 @@
+// Fused LSTM layer on 5th-gen tensor cores (bf16 mode): per time step ONE tcgen05 accumulation
+//     gates[256 seq, 512] = [x_t | h_{t-1}] (bf16, K=256) @ [W_ih | W_hh]^T      (fp32 accumulators in TMEM)
+// followed by the cell update in registers.  The gate pre-activations never touch HBM: the time-parallel
+// input projection x_t W_ih^T is fed by TMA (one 128x128 bf16 tile of x per step and CTA) and issued as
+// the first half of the K loop, the recurrent half h_{t-1} W_hh^T reads the h tile the epilogue warps
+// wrote to shared memory one step earlier.
+//
+// A CTA PAIR (cluster of 2, tcgen05 cta_group::2) owns 256 sequences of one direction for all T steps:
+//   * each CTA holds its own 128 sequences (A operand rows, TMEM lanes, cell state) and HALF of the weight
+//     rows (B operand): 256 gate columns x K=256 in bf16 = 128 KiB - which is why the pair is needed: the
+//     full [W_ih | W_hh] (256 KiB) does not fit one SM, and the hardware shares the halves across the pair;
+//   * gate columns are permuted so that MMA instruction nh (N=256) produces, for hidden units 64nh..64nh+63,
+//     the four gates at TMEM columns nh*256 + {0,64,128,192} + j;
+//   * warp roles: 0 = TMA producer, 1 = MMA issuer (leader CTA, one elected thread), 2 = TMEM allocator,
+//     4..11 = epilogue (warp%4 = TMEM lane quadrant, (warp-4)/4 = unit half).  Cell state: 64 fp32 registers
+//     per epilogue thread.  h_t goes to shared memory as the next step's A operand (128B-swizzled, bf16) and
+//     from there to HBM with one TMA store per step.
+#include "tc_common.cuh"
+#include "../../include/dprnn_b200.h"
+
+namespace dprnn {
+using namespace tc;
+
+constexpr int NXS = 3;                        // x ring stages, each a K-half [128 seq x 64 feat] bf16 = 16 KiB
+constexpr uint32_t TILE = 128 * 128;          // bytes of one [128 rows x 128 B] swizzled tile
+constexpr uint32_t SM_W = 0, SM_H = 8 * TILE, SM_X = SM_H + 2 * TILE, SM_BIAS = SM_X + NXS * TILE,
+                   SM_BAR = SM_BIAS + 512 * 4, SM_TOTAL = SM_BAR + 128;
+
+struct LstmTcParams {
+    int T;                 // time steps
+    int seq_dim;           // which tensor-map coordinate runs over sequences: 2 (intra) or 1 (inter)
+    int tiles_per_outer;   // 256-sequence tiles per outer index
+    int ndir;
+};
+
+__device__ __forceinline__ float tanh_fast(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+// x tile load whose completion is signalled on the LEADER CTA's mbarrier (cta_group::2 form)
+__device__ __forceinline__ void tma_load_4d_pair(void* smem, const CUtensorMap* m, uint32_t leader_bar, int c0, int c1,
+                                                 int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes "
+        "[%0], [%1, {%3, %4, %5, %6}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(m), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(m), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+__device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+
+template <bool kFastAct>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmH, const float* __restrict__ bias_perm, const LstmTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    uint64_t* x_full = bars;              // [NXS]  (leader's copy is the live one)
+    uint64_t* x_empty = bars + NXS;       // [NXS]
+    uint64_t* w_full = bars + 2 * NXS;
+    uint64_t* d_full = bars + 2 * NXS + 1;
+    uint64_t* h_ready = bars + 2 * NXS + 2;   // leader's copy is the live one
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NXS + 3);
+    float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int job = blockIdx.x >> 1;
+    const int dir = job % p.ndir;
+    const int jt = job / p.ndir;
+    const int outer = jt / p.tiles_per_outer;
+    const int seq0 = (jt % p.tiles_per_outer) * 256 + (int)rank * 128;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmX); prefetch_tmap(&tmW); prefetch_tmap(&tmH);
+        for (int s = 0; s < NXS; ++s) { mbar_init(&x_full[s], 2); mbar_init(&x_empty[s], 1); }
+        mbar_init(w_full, 1);
+        mbar_init(d_full, 1);
+        mbar_init(h_ready, 16);           // one elected lane per epilogue warp, both CTAs
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sbias[i] = bias_perm[dir * 512 + i];
+    if (warp == 2) tmem_alloc<2>(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();                   // barriers of both CTAs initialised before any remote arrive / TMA signal
+    tc_fence_after();
+
+    if (warp == 0 && elect_one()) {       // weights: this CTA's half of the rows of every (nh, kb) tile
+        mbar_expect_tx(w_full, 8 * TILE);
+        const int wrow = ((dir * 2 + (int)rank) * 2) * 128;
+        for (int nh = 0; nh < 2; ++nh)
+            for (int kb = 0; kb < 4; ++kb)
+                tma_load_2d(smem + SM_W + (nh * 4 + kb) * TILE, &tmW, w_full, kb * 64, wrow + nh * 128);
+    }
+    mbar_wait(w_full, 0);
+    cluster_sync_all();                   // both halves of the weights are resident
+    const uint32_t tmem = *tmem_slot;
+
+    // coordinates of (this CTA's 128 sequences, time t): intra (f, t, seq, 0) / inter (f, seq, t, outer)
+    auto c1 = [&](int t) { return p.seq_dim == 2 ? t : seq0; };
+    auto c2 = [&](int t) { return p.seq_dim == 2 ? seq0 : t; };
+
+    if (warp == 0) {
+        // ================= TMA producer: x_t K-halves into the ring =================
+        if (elect_one()) {
+            const uint32_t leader_full0 = map_to_cta(smem_u32(&x_full[0]), 0);
+            int it = 0;
+            for (int step = 0; step < p.T; ++step) {
+                const int t = dir ? p.T - 1 - step : step;
+                for (int half = 0; half < 2; ++half, ++it) {
+                    const int s = it % NXS;
+                    mbar_wait(&x_empty[s], ((it / NXS) & 1) ^ 1);
+                    const uint32_t lbar = leader_full0 + s * 8;
+                    if (rank == 0) mbar_expect_tx_addr(smem_u32(&x_full[s]), 2 * TILE);
+                    else mbar_arrive_remote(lbar);
+                    tma_load_4d_pair(smem + SM_X + s * TILE, &tmX, lbar, half * 64, c1(t), c2(t), outer);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
+            const uint32_t aW = smem_u32(smem + SM_W), aH = smem_u32(smem + SM_H), aX = smem_u32(smem + SM_X);
+            int it = 0;
+            for (int step = 0; step < p.T; ++step) {
+                if (step > 0) {
+                    mbar_wait_cluster(h_ready, (step - 1) & 1);   // D drained and h_{t-1} written in both CTAs
+                    tc_fence_after();
+                }
+                const int s0 = it % NXS, s1 = (it + 1) % NXS;
+                mbar_wait_cluster(&x_full[s0], (it / NXS) & 1);
+                mbar_wait_cluster(&x_full[s1], ((it + 1) / NXS) & 1);
+                tc_fence_after();
+                const int nkb = step > 0 ? 4 : 2;                 // h_0 = 0: skip the recurrent half at step 0
+#pragma unroll
+                for (int nh = 0; nh < 2; ++nh) {
+                    for (int kb = 0; kb < nkb; ++kb) {
+                        const uint32_t a_tile = kb == 0 ? aX + s0 * TILE : kb == 1 ? aX + s1 * TILE : aH + (kb - 2) * TILE;
+                        const uint32_t b_tile = aW + (nh * 4 + kb) * TILE;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16<2>(tmem + nh * 256, umma_desc_sw128(a_tile + kk * 32),
+                                         umma_desc_sw128(b_tile + kk * 32), idesc, (kb | kk) ? 1u : 0u);
+                    }
+                }
+                umma_commit_2cta(&x_empty[s0], 3);
+                umma_commit_2cta(&x_empty[s1], 3);
+                umma_commit_2cta(d_full, 3);
+                it += 2;
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: gates -> (c, h) =================
+        const int e = warp - 4, q = e & 3, hsel = e >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + hsel * 256;
+        const uint32_t leader_hready = map_to_cta(smem_u32(h_ready), 0);
+        uint8_t* sH = smem + SM_H + hsel * TILE;
+        const float* bq = sbias + hsel * 256;
+        float c[64];
+#pragma unroll
+        for (int i = 0; i < 64; ++i) c[i] = 0.f;
+        const bool storer = (warp == 4 && lane == 0);
+
+        for (int step = 0; step < p.T; ++step) {
+            const int t = dir ? p.T - 1 - step : step;
+            mbar_wait(d_full, step & 1);
+            tc_fence_after();
+            if (storer) bulk_wait_read0();            // last step's TMA store has finished reading the h tile
+            named_bar(1, 256);
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                uint32_t ri[16], rf[16], rg[16], ro[16];
+                tmem_ld16_issue(tbase + 0 * 64 + g * 16, ri);
+                tmem_ld16_issue(tbase + 1 * 64 + g * 16, rf);
+                tmem_ld16_issue(tbase + 2 * 64 + g * 16, rg);
+                tmem_ld16_issue(tbase + 3 * 64 + g * 16, ro);
+                tmem_ld_wait();
+                uint32_t packed[8];
+#pragma unroll
+                for (int j = 0; j < 16; j += 2) {
+                    float hv[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int jj = g * 16 + j + u;
+                        const float pi = __uint_as_float(ri[j + u]) + bq[0 * 64 + jj];
+                        const float pf = __uint_as_float(rf[j + u]) + bq[1 * 64 + jj];
+                        const float pg = __uint_as_float(rg[j + u]) + bq[2 * 64 + jj];
+                        const float po = __uint_as_float(ro[j + u]) + bq[3 * 64 + jj];
+                        float ig, fg, gg, og;
+                        if constexpr (kFastAct) {
+                            ig = sigmoid_fast(pi); fg = sigmoid_fast(pf); gg = tanh_fast(pg); og = sigmoid_fast(po);
+                        } else {
+                            ig = sigmoid_acc(pi); fg = sigmoid_acc(pf); gg = tanhf(pg); og = sigmoid_acc(po);
+                        }
+                        const float cn = fmaf(fg, c[jj], ig * gg);
+                        c[jj] = cn;
+                        hv[u] = og * (kFastAct ? tanh_fast(cn) : tanhf(cn));
+                    }
+                    __nv_bfloat162 hb = __floats2bfloat162_rn(hv[0], hv[1]);
+                    packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+                }
+                // 16 units = two 16-byte chunks of this row in the swizzled K-block `hsel`
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, g * 2 + 0)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, g * 2 + 1)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            }
+            fence_async_smem();                        // generic-proxy writes -> visible to tcgen05.mma / TMA
+            tc_fence_before();                         // our tcgen05.ld of D are complete before the MMA overwrites it
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(leader_hready);
+            named_bar(2, 256);
+            if (storer) {
+                tma_store_4d(&tmH, smem + SM_H, dir * 128, c1(t), c2(t), outer);
+                tma_store_4d(&tmH, smem + SM_H + TILE, dir * 128 + 64, c1(t), c2(t), outer);
+                bulk_commit();
+            }
+        }
+        if (storer) bulk_wait0();
+    }
+    __syncwarp();
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc<2>(tmem, 512);
+}
+
+}  // namespace dprnn
+
+using namespace dprnn;
+
+// x [rows,128] bf16; w_packed [ndir*2*2*128, 256] bf16 (see engine._pack_lstm_tc); bias_perm [ndir,512] fp32;
+// hout [rows, ndir*128] bf16.  Geometry: `inter`==0: rows = (b,s,k), sequences (b,s) run along k;
+// `inter`==1: sequences (b,k) run along s.
+extern "C" int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B,
+                                     int S, int K, int inter, int hidden, int ndir, int fast_act, void* stream) {
+    DPRNN_CHECK_ARG(x && w_packed && bias_perm && hout && B > 0 && S > 0 && K > 0);
+    DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2));
+    DPRNN_CHECK_ARG(((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)hout) % 16 == 0);
+    CUtensorMap tmX, tmW, tmH;
+    const uint64_t ldx = 128 * 2, ldh = (uint64_t)ndir * 128 * 2;
+    LstmTcParams p;
+    p.ndir = ndir;
+    uint64_t dX[4], sX[4], dH[4], sH[4];
+    uint32_t box[4] = {64, 1, 1, 1};
+    long njobs;
+    if (!inter) {      // [feat, t=k (K), seq=(b,s) (B*S), 1]
+        dX[0] = 128; dX[1] = K; dX[2] = (uint64_t)B * S; dX[3] = 1;
+        sX[0] = 2; sX[1] = ldx; sX[2] = (uint64_t)K * ldx; sX[3] = (uint64_t)B * S * K * ldx;
+        sH[0] = 2; sH[1] = ldh; sH[2] = (uint64_t)K * ldh; sH[3] = (uint64_t)B * S * K * ldh;
+        box[2] = 128;
+        p.T = K; p.seq_dim = 2; p.tiles_per_outer = (int)(((long)B * S + 255) / 256);
+        njobs = (long)p.tiles_per_outer * ndir;
+    } else {           // [feat, seq=k (K), t=s (S), b (B)]
+        dX[0] = 128; dX[1] = K; dX[2] = S; dX[3] = B;
+        sX[0] = 2; sX[1] = ldx; sX[2] = (uint64_t)K * ldx; sX[3] = (uint64_t)S * K * ldx;
+        sH[0] = 2; sH[1] = ldh; sH[2] = (uint64_t)K * ldh; sH[3] = (uint64_t)S * K * ldh;
+        box[1] = 128;
+        p.T = S; p.seq_dim = 1; p.tiles_per_outer = (K + 255) / 256;
+        njobs = (long)p.tiles_per_outer * B * ndir;
+    }
+    for (int i = 0; i < 4; ++i) dH[i] = dX[i];
+    dH[0] = (uint64_t)ndir * 128;
+    if (make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dX, sX, box)) return 1;
+    if (make_tmap(&tmH, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, hout, dH, sH, box)) return 1;
+    const uint64_t dW[2] = {256, (uint64_t)ndir * 512}, sW[2] = {2, 512};
+    const uint32_t bW[2] = {64, 128};
+    if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dW, sW, bW)) return 1;
+    const size_t smem = SM_TOTAL + 1024;
+    auto kern = fast_act ? lstm_tc_kernel<true> : lstm_tc_kernel<false>;
+    DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
+    kern<<<(unsigned)(njobs * 2), 384, smem, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}

@@ -3,6 +3,7 @@
 // speaker ResNet.  All activations are fp32, channels-last ([B, L, C] / [B, S, K, F]).
 // The reference line each entry point replaces is cited in include/dprnn_b200.h.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include "../../include/dprnn_b200.h"
 
 namespace dprnn {
@@ -100,7 +101,8 @@ __global__ void norm_affine_kernel(const float* __restrict__ mean_rstd, const fl
 // x[b,r,c] += (y[b,r,c] - mean_b) * rstd_b * gamma_c + beta_c
 __global__ void norm_residual_kernel(const float* __restrict__ y, float* __restrict__ x,
                                      const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
-                                     const float* __restrict__ beta, long total4, long per_utt4, int c4n) {
+                                     const float* __restrict__ beta, long total4, long per_utt4, int c4n,
+                                     uint2* __restrict__ x_bf16) {
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
         const long b = idx / per_utt4;
         const int c4 = (int)(idx % c4n);
@@ -114,6 +116,18 @@ __global__ void norm_residual_kernel(const float* __restrict__ y, float* __restr
         r.z += (v.z - mean) * rstd * g.z + be.z;
         r.w += (v.w - mean) * rstd * g.w + be.w;
         reinterpret_cast<float4*>(x)[idx] = r;
+        if (x_bf16) {    // bf16 shadow copy: the TMA-fed A operand of the next tensor-core LSTM layer
+            __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+            x_bf16[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+    }
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ x, uint2* __restrict__ out, long total4) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        const float4 r = reinterpret_cast<const float4*>(x)[idx];
+        __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+        out[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
     }
 }
 
@@ -452,12 +466,20 @@ int dprnn_norm_affine(const float* mean_rstd, const float* gamma, const float* b
     return 0;
 }
 
+int dprnn_cast_bf16(const float* x, void* out, long elems, void* stream) {
+    DPRNN_CHECK_ARG(x && out && elems > 0 && elems % 4 == 0);
+    cast_bf16_kernel<<<grid_for(elems / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint2*)out, elems / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
 int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const float* gamma, const float* beta,
-                        int B, long rows_per_utt, int C, void* stream) {
+                        int B, long rows_per_utt, int C, void* x_bf16, void* stream) {
     DPRNN_CHECK_ARG(y && x && mean_rstd && gamma && beta && B > 0 && rows_per_utt > 0 && C % 4 == 0);
     const long per4 = rows_per_utt * (C / 4);
     norm_residual_kernel<<<grid_for(per4 * B, 256), 256, 0, (cudaStream_t)stream>>>(y, x, mean_rstd, gamma, beta,
-                                                                                  per4 * B, per4, C / 4);
+                                                                                  per4 * B, per4, C / 4,
+                                                                                  (uint2*)x_bf16);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

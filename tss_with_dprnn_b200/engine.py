@@ -26,6 +26,7 @@ class Engine:
     def __init__(self, model):
         self.model = model
         self.precision = 'fp32'
+        self.fast_act = True       # bf16 mode: tanh.approx-based gate activations (1 MUFU op each)
         self._packed = None
         self._packed_key = None
 
@@ -67,8 +68,10 @@ class Engine:
                 bias = torch.cat([(getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s)).detach()
                                   for s in sfx], 0)
                 whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach().t() for s in sfx], 0)  # [nd, H, 4H]
+                wp, bp = self._pack_lstm_tc(rnn, sfx)
                 halves.append(dict(wih_t=wih.t().contiguous(), bias=bias.contiguous(), whh_t=whh.contiguous(),
-                                   ndir=len(sfx), lin_t=_t(lin.weight), lin_b=lin.bias.detach()))
+                                   ndir=len(sfx), lin_t=_t(lin.weight), lin_b=lin.bias.detach(),
+                                   tc_w=wp, tc_bias=bp, lin_bf16=lin.weight.detach().to(torch.bfloat16).contiguous()))
             blocks.append(halves)
         W['blocks'] = blocks
         cw = sep.conv2d.weight.detach().reshape(2 * F, F)
@@ -92,6 +95,23 @@ class Engine:
                             for rb in (se[2], se[3], se[4])]
             W['spk_conv5_t'] = _t(se[5].weight)
         return W
+
+    @staticmethod
+    def _pack_lstm_tc(rnn, sfx):
+        """Weight layout of dprnn_lstm_layer_bf16 (include/dprnn_b200.h): for direction d, CTA rank r and MMA
+        instruction nh, the 128 rows {[W_ih | W_hh][q*H + 64*nh + j] : q in (2r, 2r+1), j < 64}; bias likewise."""
+        H = rnn.hidden_size
+        ws, bs = [], []
+        j = torch.arange(64)
+        for sf in sfx:
+            wcat = torch.cat([getattr(rnn, 'weight_ih_l0' + sf).detach(), getattr(rnn, 'weight_hh_l0' + sf).detach()], 1)
+            b = (getattr(rnn, 'bias_ih_l0' + sf) + getattr(rnn, 'bias_hh_l0' + sf)).detach()
+            for r in range(2):
+                for nh in range(2):
+                    rows = torch.cat([q * H + 64 * nh + j for q in (2 * r, 2 * r + 1)]).to(wcat.device)
+                    ws.append(wcat[rows])
+            bs.append(torch.cat([b[q * H + 64 * nh + j.to(b.device)] for nh in range(2) for q in range(4)]))
+        return torch.cat(ws, 0).to(torch.bfloat16).contiguous(), torch.stack(bs, 0).float().contiguous()
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
@@ -254,9 +274,28 @@ class Engine:
         L_.call('dprnn_unfold', y, x, B, L, K, P, F, st)
         del y
         rows = B * S * K
+        bf16 = self.precision == 'bf16'
+        if bf16:
+            if H != 128 or F != 128:
+                raise NotImplementedError('the tensor-core LSTM kernel is built for feature_size = hidden_size = 128')
+            xb = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+            L_.call('dprnn_cast_bf16', x, xb, rows * F, st)
         for blk, halves in zip(sep.dprnn_blocks, W['blocks']):
             for which, hw in enumerate(halves):
                 nd = hw['ndir']
+                nm = blk.intra_norm if which == 0 else blk.inter_norm
+                g_, b_, eps = self._norm_params(nm)
+                if bf16:
+                    hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
+                    L_.call('dprnn_lstm_layer_bf16', xb, hw['tc_w'], hw['tc_bias'], hb, B, S, K, which, H, nd,
+                            int(self.fast_act), st)
+                    yl = torch.empty((rows, F), device=dev)
+                    L_.call('dprnn_linear_bf16', hb, hw['lin_bf16'], hw['lin_b'], yl, F, rows, F, nd * H, st)
+                    del hb
+                    mr2 = self.utt_stats(yl, B, S * K * F, eps)
+                    L_.call('dprnn_norm_residual', yl, x, mr2, g_, b_, B, S * K, F, xb, st)
+                    del yl
+                    continue
                 gx = self.gemm(x, hw['wih_t'], rows, nd * 4 * H, F, bias=hw['bias'])
                 hout = torch.empty((rows, nd * H), device=dev)
                 if which == 0:    # intra: one sequence per (b, s), steps along k
@@ -268,10 +307,8 @@ class Engine:
                 del gx
                 yl = self.gemm(hout, hw['lin_t'], rows, F, nd * H, bias=hw['lin_b'])
                 del hout
-                nm = blk.intra_norm if which == 0 else blk.inter_norm
-                g_, b_, eps = self._norm_params(nm)
                 mr2 = self.utt_stats(yl, B, S * K * F, eps)
-                L_.call('dprnn_norm_residual', yl, x, mr2, g_, b_, B, S * K, F, st)
+                L_.call('dprnn_norm_residual', yl, x, mr2, g_, b_, B, S * K, F, None, st)
                 del yl
         z = torch.empty((B, L, F), device=dev)
         L_.call('dprnn_fold_prelu', x, z, B, L, K, P, F, sep.prelu.weight.detach(), st)
