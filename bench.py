@@ -148,6 +148,7 @@ def workload_config(args):
     return {'workload': f'cfg2: DPRNN-Spe (cat) TSS inference, {args.samples / SR:g}-s mix + reference @ 8 kHz, '
                         f'batch {args.batch} per GPU, full depth (6 blocks)',
             'batch_per_gpu': args.batch, 'samples': args.samples, 'precision': args.precision,
+            'streams': args.streams,
             'l2': 'no flush needed: each step streams >10 GB of intermediates through a 126 MB L2',
             'parallelism': f'utterance sharding x{args.gpus}, no collective'}
 
@@ -173,6 +174,7 @@ def run_ours(args):
     torch.manual_seed(0)
     model = P.DPRNNSpeTasNet(**KW).eval().to(dev)      # same seeded weights on every rank (replicated, 16 MB)
     model.precision = args.precision
+    model.n_streams = args.streams
     B, T = args.batch, args.samples
     mix_h, ref_h = synth(B, T, rank)
     mix_h, ref_h = mix_h.pin_memory(), ref_h.pin_memory()
@@ -283,6 +285,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
+    ap.add_argument('--streams', type=int, default=int(os.environ.get('DPRNN_STREAMS', '1')),
+                    help='concurrent CUDA streams the batch is split over inside one forward')
     ap.add_argument('--batch', type=int, default=64, help='utterances per GPU (cfg 2: 64)')
     ap.add_argument('--samples', type=int, default=24000, help='samples per utterance (3 s @ 8 kHz)')
     ap.add_argument('--cpu-batch', type=int, default=1, help='utterances per CPU-baseline forward')

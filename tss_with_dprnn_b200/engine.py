@@ -27,6 +27,8 @@ class Engine:
         self.model = model
         self.precision = 'fp32'
         self.fast_act = True       # bf16 mode: tanh.approx-based gate activations (1 MUFU op each)
+        self.n_streams = 1         # >1: the batch is split into that many utterance groups on concurrent streams
+        self._streams = []
         self._packed = None
         self._packed_key = None
 
@@ -231,7 +233,37 @@ class Engine:
         return emb
 
     # ------------------------------------------------------------------ masker
-    def masker(self, enc, mr, B, L, emb, speakers):
+    def masker_split(self, enc, mr, B, L, emb, speakers):
+        """masker() over utterance groups on concurrent CUDA streams.  Utterances are independent (results are
+        bit-identical to the single-stream call); running groups side by side lets one group's memory-bound
+        kernels and partial waves fill the SMs another group's LSTM kernel leaves idle."""
+        n = max(1, min(self.n_streams, B))
+        N = self.model.cfg['input_size']
+        outs = [torch.empty((B, L, N), device=enc.device) for _ in speakers]
+        if n == 1:
+            self.masker(enc, mr, B, L, emb, speakers, outs)
+            return outs
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=enc.device))
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        base, extra = divmod(B, n)
+        b0 = 0
+        for i in range(n):
+            b1 = b0 + base + (1 if i < extra else 0)
+            st = self._streams[i]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                self.masker(enc[b0:b1], mr[b0:b1], b1 - b0, L, None if emb is None else emb[b0:b1], speakers,
+                            [o[b0:b1] for o in outs])
+                done = torch.cuda.Event()
+                done.record(st)
+            main.wait_event(done)
+            b0 = b1
+        return outs
+
+    def masker(self, enc, mr, B, L, emb, speakers, outs=None):
         """bottleneck norm + fusion + 1x1 conv, segmentation, DPRNN blocks, PReLU, overlap-add, conv2d,
         gated head, activation (dprnn.py:166-187 / dprnn_spe.py:125-154,231-248).
         enc [B,L,N]; mr its GroupNorm statistics; returns one mask [B,L,N] per requested speaker."""
@@ -322,7 +354,8 @@ class Engine:
                 raise NotImplementedError('hop_length must be chunk_length/2 (every shipped config)')
             u = self.gemm(z, W['conv2d_t'][spk], B * L, F, F, bias=W['conv2d_b'][spk], bias_scale=cov)
             g = self.gemm(u, W['og_t'], B * L, 2 * F, F, bias=W['og_b'], epi=EPI_GATED)
-            masks.append(self.gemm(g, W['end_t'], B * L, N, F, epi=act).view(B, L, N))
+            out = None if outs is None else outs[len(masks)].view(B * L, N)
+            masks.append(self.gemm(g, W['end_t'], B * L, N, F, out=out, epi=act).view(B, L, N))
         return masks
 
     def decode(self, mask, enc, out, B, L, out_utt_stride):
@@ -340,7 +373,7 @@ class Engine:
             N = self.model.cfg['input_size']
             _, _, eps = self._norm_params(self.model.separation.bottleneck[0])
             mr = self.utt_stats(enc, B, L * N, eps)
-            masks = self.masker(enc, mr, B, L, None, (0, 1))
+            masks = self.masker_split(enc, mr, B, L, None, (0, 1))
             cfg = self.model.cfg
             Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
             out = torch.empty((B, 2, Tout), device=mix.device)
@@ -365,7 +398,7 @@ class Engine:
                 emb = self._check_input(embedding, 'embedding')
             _, _, eps = self._norm_params(sep.bottleneck[0])
             mr = self.utt_stats(enc, B, L * N, eps)
-            mask = self.masker(enc, mr, B, L, emb, (0,))[0]
+            mask = self.masker_split(enc, mr, B, L, emb, (0,))[0]
             Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
             est = torch.empty((B, Tout), device=mix.device)
             self.decode(mask, enc, est, B, L, Tout)
@@ -387,7 +420,7 @@ class Engine:
             del feats
             _, _, eps = self._norm_params(sep.bottleneck[0])
             mr = self.utt_stats(enc, B, L * N, eps)
-            mask = self.masker(enc, mr, B, L, v0, (0,))[0]
+            mask = self.masker_split(enc, mr, B, L, v0, (0,))[0]
             d0 = torch.empty_like(enc)
             lib().call('dprnn_mask_apply', mask, enc, d0, B * L * N, self._stream())
             v1 = self.speaker_embedding(d0, B, L, div)          # still divided by the reference's length (:84)
@@ -395,7 +428,7 @@ class Engine:
             E = cfg['embeddings_size']
             v = self.small_linear(v0, sep.aux_linear, B, K=E)                                  # W[:, :E] v0 + b
             self.small_linear(v1, sep.aux_linear, B, out=v, accumulate=True, w_off=E, bias=False)   # + W[:, E:] v1
-            mask = self.masker(enc, mr, B, L, v, (0,))[0]
+            mask = self.masker_split(enc, mr, B, L, v, (0,))[0]
             Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
             est = torch.empty((B, Tout), device=mix.device)
             self.decode(mask, enc, est, B, L, Tout)

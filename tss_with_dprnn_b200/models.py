@@ -166,6 +166,15 @@ class _TasNetBase(nn.Module):
     def precision(self, mode: str):
         self._engine.set_precision(mode)
 
+    #: number of concurrent CUDA streams the batch is split over inside forward (results do not depend on it)
+    @property
+    def n_streams(self) -> int:
+        return self._engine.n_streams
+
+    @n_streams.setter
+    def n_streams(self, n: int):
+        self._engine.n_streams = max(1, int(n))
+
 
 class DPRNNTasNet(_TasNetBase):
     """Blind separation of two speakers; mirrors src/models/dprnn.py:219-283."""
