@@ -131,6 +131,19 @@ int dprnn_lstm_recurrence_f32(const float* gx, const float* whhT, float* hout, l
 /* fp32 -> bf16 (round to nearest even) copy of an activation tensor. */
 int dprnn_cast_bf16(const float* x, void* out, long elems, void* stream);
 
+/* Pointwise contraction on tensor cores: C[M,N] (fp32) = epi(A[M,K] @ W[N,K]^T + bias), W in nn.Linear / Conv1d
+ * layout (K-major, no transpose).  a_is_bf16 != 0: A and W are bf16 (the Linear after each LSTM,
+ * src/models/dprnn.py:61,70); == 0: A and W are fp32 read as TF32 (conv2d / out / gate / end_conv1x1 of the mask
+ * head, dprnn.py:155-160, and the speaker ResNet convolutions, dprnn_spe.py:17-18,27,121).
+ * N in {64,128,256}; K*elem_size a multiple of 128 bytes.  DPRNN_EPI_GATED: N = 2F, W rows = [out; gate],
+ * C[M,F] = tanh(out) * sigmoid(gate).  stats_partial (may be NULL; dprnn_gemm_tc_stats_bytes(M) bytes): the
+ * epilogue also emits per-row sums so that mean_rstd [M/rows_per_utt, 2] of the FOLLOWING GroupNorm(1,N) / gLN
+ * (eps) is produced without another pass over C. */
+size_t dprnn_gemm_tc_stats_bytes(int M);
+int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias, float* C, long ldc, int M, int N,
+                  int K, int epilogue, void* stats_partial, long rows_per_utt, float eps, float* mean_rstd,
+                  void* stream);
+
 /* One whole nn.LSTM layer (input projection + recurrence, both directions), src/models/dprnn.py:23-28,35-36,
  * as a fused tcgen05 kernel: per step gates = [x_t | h_{t-1}] @ [W_ih | W_hh]^T with fp32 accumulators in TMEM,
  * W resident in the shared memory of a CTA pair (cta_group::2), x_t tiles fed by TMA, cell state in registers.

@@ -152,3 +152,20 @@ def test_bf16_mode_sisdr(case, fast_act):
     target = want + noise                                       # SI-SDR(want, target) ~ 13 dB
     delta = (O.si_sdr_db(est, target) - O.si_sdr_db(want, target)).abs()
     assert delta.max() < 0.05, delta
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+def test_stream_groups_bit_exact(precision):
+    """Splitting the batch over concurrent streams inside forward must not change a single bit."""
+    torch.manual_seed(6)
+    model = P.DPRNNSpeTasNet(**dict(KW, n_repeats=2), fusion_type='film').eval().cuda()
+    model.precision = precision
+    g = torch.Generator().manual_seed(9)
+    mix, ref = (0.05 * torch.randn(7, 6000, generator=g)).cuda(), (0.05 * torch.randn(7, 6000, generator=g)).cuda()
+    with torch.no_grad():
+        model.n_streams = 1
+        e1, l1 = model(mix, ref, torch.tensor(6000.))
+        model.n_streams = 3
+        e3, l3 = model(mix, ref, torch.tensor(6000.))
+        torch.cuda.synchronize()
+    assert torch.equal(e1, e3) and torch.equal(l1, l3)

@@ -81,3 +81,49 @@ def test_lstm_layer_bf16(inter, ndir, fast):
     # bf16 output rounding (2^-9) + rounding flips of the recurrent h; tanh.approx adds ~2^-11
     assert err < (1.5e-2 if fast else 1e-2), err
     assert (got - want).abs().mean() < 2e-3
+
+
+@pytest.mark.parametrize('M,N,K,bf16,epi', [(1000, 128, 256, True, 0), (48500 * 2, 128, 256, True, 0), (300, 128, 128, True, 0),
+                                            (777, 128, 128, False, 0), (1000, 256, 128, False, 0), (513, 256, 256, False, 0),
+                                            (129, 128, 256, False, 0), (640, 64, 128, False, 2), (640, 64, 128, False, 1),
+                                            (900, 256, 128, False, 3), (5, 128, 128, False, 0)])
+def test_gemm_tc(M, N, K, bf16, epi):
+    from tss_with_dprnn_b200.engine import Engine
+    A = rnd(M, K, seed=M)
+    W = rnd(N, K, seed=N + 1) / K ** 0.5
+    bias = rnd(N, seed=3)
+    if bf16:
+        A, W = A.bfloat16(), W.bfloat16()
+        Ar, Wr = A.double(), W.double()
+    else:   # TF32: operands truncated to 10 mantissa bits
+        Ar = (A.view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+        Wr = (W.view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    ref = Ar @ Wr.t() + bias.double()
+    if epi == 1:
+        ref = torch.relu(ref)
+    elif epi == 2:
+        ref = torch.sigmoid(ref)
+    elif epi == 3:
+        ref = torch.tanh(ref[:, :N // 2]) * torch.sigmoid(ref[:, N // 2:])
+    eng = Engine.__new__(Engine)
+    out = Engine.gemm_tc(eng, A.to(DEV), W.to(DEV), M, N, K, bias=bias.to(DEV), epi=epi)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    tol = 1e-5 if epi in (0, 1) else 2e-3          # tanh.approx-based activations in the epilogue
+    assert O.peak_rel_err(out.cpu(), ref.float()) < tol
+
+
+def test_gemm_tc_fused_stats():
+    from tss_with_dprnn_b200.engine import Engine
+    B, R, K, N = 3, 1337, 256, 128           # tiles straddle utterance boundaries (1337 % 128 != 0)
+    A = (rnd(B * R, K, seed=1) + 0.3).bfloat16()
+    W = (rnd(N, K, seed=2) / 16).bfloat16()
+    bias = rnd(N, seed=3)
+    ref = (A.double() @ W.double().t() + bias.double()).view(B, -1)
+    eng = Engine.__new__(Engine)
+    out, mr = Engine.gemm_tc(eng, A.to(DEV), W.to(DEV), B * R, N, K, bias=bias.to(DEV), stats=(R, 1e-5))
+    mean, rstd = ref.mean(1), 1 / torch.sqrt(ref.var(1, unbiased=False) + 1e-5)
+    assert torch.allclose(mr[:, 0].cpu().double(), mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(mr[:, 1].cpu().double(), rstd, rtol=1e-4)
+    out2, mr2 = Engine.gemm_tc(eng, A.to(DEV), W.to(DEV), B * R, N, K, bias=bias.to(DEV), stats=(R, 1e-5))
+    assert torch.equal(mr, mr2)            # deterministic reduction

@@ -89,6 +89,12 @@ class Engine:
         W['og_t'] = torch.cat(cols, 1).contiguous()       # [F, 2F]
         W['og_b'] = torch.cat(bias, 0).contiguous()
         W['end_t'] = _t(sep.end_conv1x1.weight)            # [F, N]
+        # tensor-core (TF32) head: native [N_out, K] layouts
+        W['conv2d_w'] = [cw[s * F:(s + 1) * F].contiguous() for s in range(2)]
+        W['conv2d_b2'] = [(2.0 * sep.conv2d.bias.detach()[s * F:(s + 1) * F]).contiguous() for s in range(2)]
+        W['og_w'] = torch.cat([wo, wg], 0).contiguous()     # [2F, F]: rows [out; gate]
+        W['og_bias'] = torch.cat([bo, bg], 0).contiguous()
+        W['end_w'] = sep.end_conv1x1.weight.detach().reshape(N, F).contiguous()
         if cfg['kind'] != 'bss':
             se = sep.spk_encoder
             W['spk_conv0_t'] = _t(se[1].weight)
@@ -147,6 +153,22 @@ class Engine:
         lib().call('dprnn_gemm_f32', A, K, Wt, N, out, n_out, M, N, K, bias, int(bias_per_utt), float(bias_scale),
                    int(rows_per_utt), p_scale, p_shift, p_add, rowscale, epi, self._stream())
         return out
+
+    def gemm_tc(self, A, W, M, N, K, bias=None, epi=EPI_NONE, out=None, stats=None):
+        """tcgen05 contraction; W in its native [N, K] layout (bf16 if A is bf16, else fp32 read as TF32).
+        stats = (rows_per_utt, eps) additionally returns mean/rstd of the following per-utterance norm."""
+        n_out = N // 2 if epi == EPI_GATED else N
+        if out is None:
+            out = torch.empty((M, n_out), device=A.device, dtype=torch.float32)
+        part = mr = None
+        rpu, eps = 0, 0.0
+        if stats is not None:
+            rpu, eps = stats
+            part = torch.empty(lib().query('dprnn_gemm_tc_stats_bytes', M), device=A.device, dtype=torch.uint8)
+            mr = torch.empty((M // rpu, 2), device=A.device, dtype=torch.float32)
+        lib().call('dprnn_gemm_tc', A, int(A.dtype == torch.bfloat16), W, bias, out, n_out, M, N, K, epi, part,
+                   int(rpu), float(eps), mr, self._stream())
+        return (out, mr) if stats is not None else out
 
     def utt_stats(self, x, B, elems, eps):
         L = lib()
@@ -215,12 +237,19 @@ class Engine:
                 if training:
                     bnm.num_batches_tracked += 1
 
-            y = self.gemm(x, wr['c1'], rows, Cout, Cin)
+            tc = self.precision == 'bf16' and Cin in (128, 256) and Cout in (128, 256)
+
+            def conv(inp, conv_mod, wt, cin, cout):
+                if tc:
+                    return self.gemm_tc(inp, conv_mod.weight.detach(), rows, cout, cin)
+                return self.gemm(inp, wt, rows, cout, cin)
+
+            y = conv(x, rb.conv1, wr['c1'], Cin, Cout)
             bn(y, rb.batch_norm1)
             L_.call('dprnn_affine_prelu', y, scale, shift, rb.prelu1.weight.detach(), y, rows, Cout, st)
-            y2 = self.gemm(y, wr['c2'], rows, Cout, Cout)
+            y2 = conv(y, rb.conv2, wr['c2'], Cout, Cout)
             bn(y2, rb.batch_norm2)
-            skip = x if wr['down'] is None else self.gemm(x, wr['down'], rows, Cout, Cin)
+            skip = x if wr['down'] is None else conv(x, rb.conv_downsample, wr['down'], Cin, Cout)
             Lo = Lx // 3
             out = torch.empty((B, Lo, Cout), device=dev)
             L_.call('dprnn_affine_add_prelu_pool3', y2, scale, shift, skip, rb.prelu2.weight.detach(), out, B, Lx,
@@ -321,10 +350,8 @@ class Engine:
                     hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
                     L_.call('dprnn_lstm_layer_bf16', xb, hw['tc_w'], hw['tc_bias'], hb, B, S, K, which, H, nd,
                             int(self.fast_act), st)
-                    yl = torch.empty((rows, F), device=dev)
-                    L_.call('dprnn_linear_bf16', hb, hw['lin_bf16'], hw['lin_b'], yl, F, rows, F, nd * H, st)
+                    yl, mr2 = self.gemm_tc(hb, hw['lin_bf16'], rows, F, nd * H, bias=hw['lin_b'], stats=(S * K, eps))
                     del hb
-                    mr2 = self.utt_stats(yl, B, S * K * F, eps)
                     L_.call('dprnn_norm_residual', yl, x, mr2, g_, b_, B, S * K, F, xb, st)
                     del yl
                     continue
@@ -352,9 +379,14 @@ class Engine:
             cov = 2.0 if K == 2 * P else None
             if cov is None:
                 raise NotImplementedError('hop_length must be chunk_length/2 (every shipped config)')
+            out = None if outs is None else outs[len(masks)].view(B * L, N)
+            if bf16 and F == 128 and N == 64:
+                u = self.gemm_tc(z, W['conv2d_w'][spk], B * L, F, F, bias=W['conv2d_b2'][spk])
+                g = self.gemm_tc(u, W['og_w'], B * L, 2 * F, F, bias=W['og_bias'], epi=EPI_GATED)
+                masks.append(self.gemm_tc(g, W['end_w'], B * L, N, F, epi=act, out=out).view(B, L, N))
+                continue
             u = self.gemm(z, W['conv2d_t'][spk], B * L, F, F, bias=W['conv2d_b'][spk], bias_scale=cov)
             g = self.gemm(u, W['og_t'], B * L, 2 * F, F, bias=W['og_b'], epi=EPI_GATED)
-            out = None if outs is None else outs[len(masks)].view(B * L, N)
             masks.append(self.gemm(g, W['end_t'], B * L, N, F, out=out, epi=act).view(B, L, N))
         return masks
 
