@@ -21,10 +21,11 @@
 namespace dprnn {
 using namespace tc;
 
-constexpr int NXS = 3;                        // x ring stages, each a K-half [128 seq x 64 feat] bf16 = 16 KiB
+constexpr int NXS = 4;                        // x ring stages, each a K-half [128 seq x 64 feat] bf16 = 16 KiB
 constexpr uint32_t TILE = 128 * 128;          // bytes of one [128 rows x 128 B] swizzled tile
 constexpr uint32_t SM_W = 0, SM_H = 8 * TILE, SM_X = SM_H + 2 * TILE, SM_BIAS = SM_X + NXS * TILE,
                    SM_BAR = SM_BIAS + 512 * 4, SM_TOTAL = SM_BAR + 128;
+static_assert(SM_TOTAL <= 232448, "shared memory budget of one SM (227 KiB)");
 
 struct LstmTcParams {
     int T;                 // time steps
@@ -76,19 +77,53 @@ __device__ __forceinline__ void mbar_expect_tx_addr(uint32_t addr, uint32_t byte
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
 }
 
+// Cell update for 16 hidden units of one sequence row: gates from TMEM (+bias) -> c (registers), h (packed bf16).
+template <bool kFastAct>
+__device__ __forceinline__ void lstm_cell16(uint32_t tcol, const float* __restrict__ bq, float* __restrict__ c,
+                                            uint32_t (&packed)[8]) {
+    uint32_t ri[16], rf[16], rg[16], ro[16];
+    tmem_ld16_issue(tcol + 0 * 64, ri);
+    tmem_ld16_issue(tcol + 1 * 64, rf);
+    tmem_ld16_issue(tcol + 2 * 64, rg);
+    tmem_ld16_issue(tcol + 3 * 64, ro);
+    tmem_ld_wait();
+#pragma unroll
+    for (int j = 0; j < 16; j += 2) {
+        float hv[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const float pi = __uint_as_float(ri[j + u]) + bq[0 * 64 + j + u];
+            const float pf = __uint_as_float(rf[j + u]) + bq[1 * 64 + j + u];
+            const float pg = __uint_as_float(rg[j + u]) + bq[2 * 64 + j + u];
+            const float po = __uint_as_float(ro[j + u]) + bq[3 * 64 + j + u];
+            float ig, fg, gg, og;
+            if constexpr (kFastAct) {
+                ig = sigmoid_fast(pi); fg = sigmoid_fast(pf); gg = tanh_fast(pg); og = sigmoid_fast(po);
+            } else {
+                ig = sigmoid_acc(pi); fg = sigmoid_acc(pf); gg = tanhf(pg); og = sigmoid_acc(po);
+            }
+            const float cn = fmaf(fg, c[j + u], ig * gg);
+            c[j + u] = cn;
+            hv[u] = og * (kFastAct ? tanh_fast(cn) : tanhf(cn));
+        }
+        __nv_bfloat162 hb = __floats2bfloat162_rn(hv[0], hv[1]);
+        packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+    }
+}
+
 template <bool kFastAct>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmH, const float* __restrict__ bias_perm, const LstmTcParams p) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
-    uint64_t* x_full = bars;              // [NXS]  (leader's copy is the live one)
-    uint64_t* x_empty = bars + NXS;       // [NXS]
+    uint64_t* x_full = bars;                  // [NXS]  (leader's copy is the live one)
+    uint64_t* x_empty = bars + NXS;           // [NXS]
     uint64_t* w_full = bars + 2 * NXS;
-    uint64_t* d_full = bars + 2 * NXS + 1;
-    uint64_t* h_ready = bars + 2 * NXS + 2;   // leader's copy is the live one
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NXS + 3);
+    uint64_t* d_full = bars + 2 * NXS + 1;    // [2]  gates of unit-half nh are complete in TMEM
+    uint64_t* h_free = bars + 2 * NXS + 3;    //      every MMA that reads h_{t-1} has completed
+    uint64_t* h_done = bars + 2 * NXS + 4;    // [2]  (leader's copy) D[nh] drained and h half nh written, both CTAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NXS + 6);
     float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -100,11 +135,16 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int seq0 = (jt % p.tiles_per_outer) * 256 + (int)rank * 128;
 
     if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) {         // SWIZZLE_128B tiles need a 1024-byte aligned base
+            printf("lstm_tc_kernel: dynamic shared memory base %u is not 1024-byte aligned\n", smem_u32(smem));
+            __trap();
+        }
         prefetch_tmap(&tmX); prefetch_tmap(&tmW); prefetch_tmap(&tmH);
         for (int s = 0; s < NXS; ++s) { mbar_init(&x_full[s], 2); mbar_init(&x_empty[s], 1); }
         mbar_init(w_full, 1);
-        mbar_init(d_full, 1);
-        mbar_init(h_ready, 16);           // one elected lane per epilogue warp, both CTAs
+        mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
+        mbar_init(h_free, 1);
+        mbar_init(&h_done[0], 16); mbar_init(&h_done[1], 16);   // one elected lane per epilogue warp, both CTAs
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 512; i += blockDim.x) sbias[i] = bias_perm[dir * 512 + i];
@@ -147,96 +187,100 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
+        // TMEM: D0 = columns [0,256) (hidden units 0..63, gates i|f|g|o), D1 = [256,512) (units 64..127).
+        // Per step:  x-part(D0) is issued as soon as the epilogue has drained D0 (during its work on D1);
+        // when h_{t-1} is complete: h-part(D0) -> d_full[0]; h-part(D1) -> h_free; x-part(D1) -> d_full[1].
+        // The epilogue of D0 therefore overlaps the MMAs of D1, and the next x-part(D0) the epilogue of D1.
         if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
             const uint32_t aW = smem_u32(smem + SM_W), aH = smem_u32(smem + SM_H), aX = smem_u32(smem + SM_X);
+            auto mma_kb = [&](int nh, int kb, uint32_t a_tile, bool first) {
+                const uint32_t b_tile = aW + (nh * 4 + kb) * TILE;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16<2>(tmem + nh * 256, umma_desc_sw128(a_tile + kk * 32), umma_desc_sw128(b_tile + kk * 32),
+                                 idesc, (first && kk == 0) ? 0u : 1u);
+            };
             int it = 0;
-            for (int step = 0; step < p.T; ++step) {
-                if (step > 0) {
-                    mbar_wait_cluster(h_ready, (step - 1) & 1);   // D drained and h_{t-1} written in both CTAs
-                    tc_fence_after();
-                }
+            for (int step = 0; step < p.T; ++step, it += 2) {
                 const int s0 = it % NXS, s1 = (it + 1) % NXS;
                 mbar_wait_cluster(&x_full[s0], (it / NXS) & 1);
                 mbar_wait_cluster(&x_full[s1], ((it + 1) / NXS) & 1);
                 tc_fence_after();
-                const int nkb = step > 0 ? 4 : 2;                 // h_0 = 0: skip the recurrent half at step 0
-#pragma unroll
-                for (int nh = 0; nh < 2; ++nh) {
-                    for (int kb = 0; kb < nkb; ++kb) {
-                        const uint32_t a_tile = kb == 0 ? aX + s0 * TILE : kb == 1 ? aX + s1 * TILE : aH + (kb - 2) * TILE;
-                        const uint32_t b_tile = aW + (nh * 4 + kb) * TILE;
-#pragma unroll
-                        for (int kk = 0; kk < 4; ++kk)
-                            umma_bf16<2>(tmem + nh * 256, umma_desc_sw128(a_tile + kk * 32),
-                                         umma_desc_sw128(b_tile + kk * 32), idesc, (kb | kk) ? 1u : 0u);
-                    }
+                if (step == 0) {                                  // h_0 = 0: only the input projection
+                    mma_kb(0, 0, aX + s0 * TILE, true);  mma_kb(0, 1, aX + s1 * TILE, false);
+                    mma_kb(1, 0, aX + s0 * TILE, true);  mma_kb(1, 1, aX + s1 * TILE, false);
+                    umma_commit_2cta(&x_empty[s0], 3); umma_commit_2cta(&x_empty[s1], 3);
+                    umma_commit_2cta(h_free, 3);
+                    umma_commit_2cta(&d_full[0], 3); umma_commit_2cta(&d_full[1], 3);
+                    continue;
                 }
-                umma_commit_2cta(&x_empty[s0], 3);
-                umma_commit_2cta(&x_empty[s1], 3);
-                umma_commit_2cta(d_full, 3);
-                it += 2;
+                const uint32_t par = (step - 1) & 1;
+                mbar_wait_cluster(&h_done[0], par);               // D0 drained by both CTAs
+                tc_fence_after();
+                mma_kb(0, 0, aX + s0 * TILE, true);  mma_kb(0, 1, aX + s1 * TILE, false);
+                mbar_wait_cluster(&h_done[1], par);               // D1 drained, h_{t-1} complete in both CTAs
+                tc_fence_after();
+                mma_kb(0, 2, aH, false);  mma_kb(0, 3, aH + TILE, false);
+                umma_commit_2cta(&d_full[0], 3);
+                mma_kb(1, 2, aH, true);   mma_kb(1, 3, aH + TILE, false);
+                umma_commit_2cta(h_free, 3);
+                mma_kb(1, 0, aX + s0 * TILE, false);  mma_kb(1, 1, aX + s1 * TILE, false);
+                umma_commit_2cta(&x_empty[s0], 3); umma_commit_2cta(&x_empty[s1], 3);
+                umma_commit_2cta(&d_full[1], 3);
             }
         }
     } else if (warp >= 4) {
         // ================= epilogue: gates -> (c, h) =================
-        const int e = warp - 4, q = e & 3, hsel = e >> 2;
+        // all 8 warps work on D0, then on D1: warp -> TMEM lane quadrant q = warp % 4, 32-unit sub-block sub = e / 4
+        const int e = warp - 4, q = e & 3, sub = e >> 2;
         const int row = q * 32 + lane;
-        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + hsel * 256;
-        const uint32_t leader_hready = map_to_cta(smem_u32(h_ready), 0);
-        uint8_t* sH = smem + SM_H + hsel * TILE;
-        const float* bq = sbias + hsel * 256;
-        float c[64];
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + sub * 32;
+        const uint32_t leader_hdone = map_to_cta(smem_u32(&h_done[0]), 0);
+        float c0[32], c1s[32];
 #pragma unroll
-        for (int i = 0; i < 64; ++i) c[i] = 0.f;
+        for (int i = 0; i < 32; ++i) { c0[i] = 0.f; c1s[i] = 0.f; }
         const bool storer = (warp == 4 && lane == 0);
 
         for (int step = 0; step < p.T; ++step) {
             const int t = dir ? p.T - 1 - step : step;
-            mbar_wait(d_full, step & 1);
+            const uint32_t par = step & 1;
+            // ---------------- unit half 0
+            mbar_wait(&d_full[0], par);
             tc_fence_after();
-            if (storer) bulk_wait_read0();            // last step's TMA store has finished reading the h tile
+            uint32_t pk0[8], pk1[8];
+            lstm_cell16<kFastAct>(tbase + 0, sbias + sub * 32 + 0, c0 + 0, pk0);
+            lstm_cell16<kFastAct>(tbase + 16, sbias + sub * 32 + 16, c0 + 16, pk1);
+            tc_fence_before();                         // our tcgen05.ld of D0 are complete
+            mbar_wait(h_free, par);                    // the MMAs that read h_{t-1} have completed
+            if (storer) bulk_wait_read0();             // ... and so has last step's TMA store of the h tile
             named_bar(1, 256);
-#pragma unroll
-            for (int g = 0; g < 4; ++g) {
-                uint32_t ri[16], rf[16], rg[16], ro[16];
-                tmem_ld16_issue(tbase + 0 * 64 + g * 16, ri);
-                tmem_ld16_issue(tbase + 1 * 64 + g * 16, rf);
-                tmem_ld16_issue(tbase + 2 * 64 + g * 16, rg);
-                tmem_ld16_issue(tbase + 3 * 64 + g * 16, ro);
-                tmem_ld_wait();
-                uint32_t packed[8];
-#pragma unroll
-                for (int j = 0; j < 16; j += 2) {
-                    float hv[2];
-#pragma unroll
-                    for (int u = 0; u < 2; ++u) {
-                        const int jj = g * 16 + j + u;
-                        const float pi = __uint_as_float(ri[j + u]) + bq[0 * 64 + jj];
-                        const float pf = __uint_as_float(rf[j + u]) + bq[1 * 64 + jj];
-                        const float pg = __uint_as_float(rg[j + u]) + bq[2 * 64 + jj];
-                        const float po = __uint_as_float(ro[j + u]) + bq[3 * 64 + jj];
-                        float ig, fg, gg, og;
-                        if constexpr (kFastAct) {
-                            ig = sigmoid_fast(pi); fg = sigmoid_fast(pf); gg = tanh_fast(pg); og = sigmoid_fast(po);
-                        } else {
-                            ig = sigmoid_acc(pi); fg = sigmoid_acc(pf); gg = tanhf(pg); og = sigmoid_acc(po);
-                        }
-                        const float cn = fmaf(fg, c[jj], ig * gg);
-                        c[jj] = cn;
-                        hv[u] = og * (kFastAct ? tanh_fast(cn) : tanhf(cn));
-                    }
-                    __nv_bfloat162 hb = __floats2bfloat162_rn(hv[0], hv[1]);
-                    packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
-                }
-                // 16 units = two 16-byte chunks of this row in the swizzled K-block `hsel`
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, g * 2 + 0)) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, g * 2 + 1)) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+            {
+                uint8_t* sH = smem + SM_H;             // K-block 0 = units 0..63; 16 units = two 16-byte chunks
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 0)) = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 1)) = make_uint4(pk0[4], pk0[5], pk0[6], pk0[7]);
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 2)) = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 3)) = make_uint4(pk1[4], pk1[5], pk1[6], pk1[7]);
             }
             fence_async_smem();                        // generic-proxy writes -> visible to tcgen05.mma / TMA
-            tc_fence_before();                         // our tcgen05.ld of D are complete before the MMA overwrites it
             __syncwarp();
-            if (lane == 0) mbar_arrive_remote(leader_hready);
+            if (lane == 0) mbar_arrive_remote(leader_hdone);
+            // ---------------- unit half 1
+            mbar_wait(&d_full[1], par);
+            tc_fence_after();
+            lstm_cell16<kFastAct>(tbase + 256 + 0, sbias + 256 + sub * 32 + 0, c1s + 0, pk0);
+            lstm_cell16<kFastAct>(tbase + 256 + 16, sbias + 256 + sub * 32 + 16, c1s + 16, pk1);
+            tc_fence_before();
+            {
+                uint8_t* sH = smem + SM_H + TILE;      // K-block 1 = units 64..127
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 0)) = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 1)) = make_uint4(pk0[4], pk0[5], pk0[6], pk0[7]);
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 2)) = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
+                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 3)) = make_uint4(pk1[4], pk1[5], pk1[6], pk1[7]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(leader_hdone + 8);
             named_bar(2, 256);
             if (storer) {
                 tma_store_4d(&tmH, smem + SM_H, dir * 128, c1(t), c2(t), outer);
@@ -294,7 +338,7 @@ extern "C" int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const 
     const uint64_t dW[2] = {256, (uint64_t)ndir * 512}, sW[2] = {2, 512};
     const uint32_t bW[2] = {64, 128};
     if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dW, sW, bW)) return 1;
-    const size_t smem = SM_TOTAL + 1024;
+    const size_t smem = SM_TOTAL;   // no alignment slack: the kernel checks the 1024-byte alignment of the base
     auto kern = fast_act ? lstm_tc_kernel<true> : lstm_tc_kernel<false>;
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
