@@ -150,7 +150,8 @@ int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias
  * x [rows,128] bf16 (rows = (b,s,k) chunk positions), hout [rows, ndir*128] bf16.
  * w_packed [ndir*512, 256] bf16: for direction d, CTA rank r, instruction nh: 128 rows
  *   {[W_ih | W_hh][q*128 + 64*nh + j, :] : q in (2r, 2r+1), j < 64};  bias_perm[d][nh*256 + q*64 + j] =
- *   (b_ih + b_hh)[q*128 + 64*nh + j].
+ *   (b_ih + b_hh)[q*128 + 64*nh + j].  Rows / biases of the i, f, o gates (q = 0, 1, 3) are pre-scaled by 1/2 (the
+ *   kernel evaluates sigmoid(x) = 1/2 tanh(x/2) + 1/2).
  * inter == 0: sequences (b,s) run along k (intra-chunk); inter == 1: sequences (b,k) run along s.
  * fast_act != 0: tanh.approx-based activations (1 MUFU op each); 0: expf/tanhf. hidden must be 128. */
 int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S,

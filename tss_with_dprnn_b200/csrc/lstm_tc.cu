@@ -70,14 +70,18 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+// Remote arrive with the default (.release.cta) semantics, as CUTLASS' ClusterBarrier::arrive does: the data the
+// barrier guards (the h tile) is read by the tensor core through the async proxy and has already been published with
+// fence.proxy.async; a .release.cluster here compiles to MEMBAR.ALL.GPU + CCTL.IVALL and cost ~19% of the epilogue.
 __device__ __forceinline__ void mbar_arrive_remote(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx_addr(uint32_t addr, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
 }
 
 // Cell update for 16 hidden units of one sequence row: gates from TMEM (+bias) -> c (registers), h (packed bf16).
+// The i, f, o rows of the weights and biases are pre-scaled by 1/2 on the host (exact), so sigmoid(x) = 1/2 tanh(x') + 1/2.
 template <bool kFastAct>
 __device__ __forceinline__ void lstm_cell16(uint32_t tcol, const float* __restrict__ bq, float* __restrict__ c,
                                             uint32_t (&packed)[8]) {
@@ -86,28 +90,37 @@ __device__ __forceinline__ void lstm_cell16(uint32_t tcol, const float* __restri
     tmem_ld16_issue(tcol + 1 * 64, rf);
     tmem_ld16_issue(tcol + 2 * 64, rg);
     tmem_ld16_issue(tcol + 3 * 64, ro);
+    float4 bi = *reinterpret_cast<const float4*>(bq + 0 * 64), bf = *reinterpret_cast<const float4*>(bq + 1 * 64);
+    float4 bg = *reinterpret_cast<const float4*>(bq + 2 * 64), bo = *reinterpret_cast<const float4*>(bq + 3 * 64);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; j += 2) {
-        float hv[2];
+    for (int j = 0; j < 16; j += 4) {
+        const float b4[4][4] = {{bi.x, bi.y, bi.z, bi.w}, {bf.x, bf.y, bf.z, bf.w}, {bg.x, bg.y, bg.z, bg.w}, {bo.x, bo.y, bo.z, bo.w}};
+        if (j + 4 < 16) {      // next four units' biases while this group's activations are in flight
+            bi = *reinterpret_cast<const float4*>(bq + 0 * 64 + j + 4); bf = *reinterpret_cast<const float4*>(bq + 1 * 64 + j + 4);
+            bg = *reinterpret_cast<const float4*>(bq + 2 * 64 + j + 4); bo = *reinterpret_cast<const float4*>(bq + 3 * 64 + j + 4);
+        }
+        float hv[4];
 #pragma unroll
-        for (int u = 0; u < 2; ++u) {
-            const float pi = __uint_as_float(ri[j + u]) + bq[0 * 64 + j + u];
-            const float pf = __uint_as_float(rf[j + u]) + bq[1 * 64 + j + u];
-            const float pg = __uint_as_float(rg[j + u]) + bq[2 * 64 + j + u];
-            const float po = __uint_as_float(ro[j + u]) + bq[3 * 64 + j + u];
+        for (int u = 0; u < 4; ++u) {
+            const float pi = __uint_as_float(ri[j + u]) + b4[0][u];
+            const float pf = __uint_as_float(rf[j + u]) + b4[1][u];
+            const float pg = __uint_as_float(rg[j + u]) + b4[2][u];
+            const float po = __uint_as_float(ro[j + u]) + b4[3][u];
             float ig, fg, gg, og;
             if constexpr (kFastAct) {
-                ig = sigmoid_fast(pi); fg = sigmoid_fast(pf); gg = tanh_fast(pg); og = sigmoid_fast(po);
+                ig = fmaf(tanh_fast(pi), 0.5f, 0.5f); fg = fmaf(tanh_fast(pf), 0.5f, 0.5f);
+                gg = tanh_fast(pg); og = fmaf(tanh_fast(po), 0.5f, 0.5f);
             } else {
-                ig = sigmoid_acc(pi); fg = sigmoid_acc(pf); gg = tanhf(pg); og = sigmoid_acc(po);
+                ig = sigmoid_acc(2.f * pi); fg = sigmoid_acc(2.f * pf); gg = tanhf(pg); og = sigmoid_acc(2.f * po);
             }
             const float cn = fmaf(fg, c[j + u], ig * gg);
             c[j + u] = cn;
             hv[u] = og * (kFastAct ? tanh_fast(cn) : tanhf(cn));
         }
-        __nv_bfloat162 hb = __floats2bfloat162_rn(hv[0], hv[1]);
-        packed[j >> 1] = *reinterpret_cast<uint32_t*>(&hb);
+        __nv_bfloat162 h01 = __floats2bfloat162_rn(hv[0], hv[1]), h23 = __floats2bfloat162_rn(hv[2], hv[3]);
+        packed[(j >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h01);
+        packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h23);
     }
 }
 

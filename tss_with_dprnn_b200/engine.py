@@ -114,6 +114,12 @@ class Engine:
         for sf in sfx:
             wcat = torch.cat([getattr(rnn, 'weight_ih_l0' + sf).detach(), getattr(rnn, 'weight_hh_l0' + sf).detach()], 1)
             b = (getattr(rnn, 'bias_ih_l0' + sf) + getattr(rnn, 'bias_hh_l0' + sf)).detach()
+            # i, f, o rows pre-scaled by 1/2 (exact): the kernel evaluates sigmoid(x) as 1/2 tanh(x/2) + 1/2
+            half = torch.ones(4 * H, device=wcat.device)
+            half[:2 * H] = 0.5
+            half[3 * H:] = 0.5
+            wcat = wcat * half[:, None]
+            b = b * half
             for r in range(2):
                 for nh in range(2):
                     rows = torch.cat([q * H + 64 * nh + j for q in (2 * r, 2 * r + 1)]).to(wcat.device)
