@@ -144,6 +144,12 @@ int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias
                   int K, int epilogue, void* stats_partial, long rows_per_utt, float eps, float* mean_rstd,
                   void* stream);
 
+/* The Linear(ndir*H -> 128) after each LSTM (src/models/dprnn.py:61,70) as a persistent, pipelined tcgen05 kernel:
+ * C[M,128] (fp32, contiguous) = A[M,K] (bf16) @ W[128,K]^T (bf16) + bias, K in {128,256}; W stays resident in shared
+ * memory, the output goes through swizzled staging + TMA stores.  stats_partial / mean_rstd as in dprnn_gemm_tc. */
+int dprnn_linear_bf16_stats(const void* A, const void* W, const float* bias, float* C, int M, int K,
+                            void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream);
+
 /* One whole nn.LSTM layer (input projection + recurrence, both directions), src/models/dprnn.py:23-28,35-36,
  * as a fused tcgen05 kernel: per step gates = [x_t | h_{t-1}] @ [W_ih | W_hh]^T with fp32 accumulators in TMEM,
  * W resident in the shared memory of a CTA pair (cta_group::2), x_t tiles fed by TMA, cell state in registers.

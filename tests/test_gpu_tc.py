@@ -127,3 +127,22 @@ def test_gemm_tc_fused_stats():
     assert torch.allclose(mr[:, 1].cpu().double(), rstd, rtol=1e-4)
     out2, mr2 = Engine.gemm_tc(eng, A.to(DEV), W.to(DEV), B * R, N, K, bias=bias.to(DEV), stats=(R, 1e-5))
     assert torch.equal(mr, mr2)            # deterministic reduction
+
+
+@pytest.mark.parametrize('B,R,K', [(3, 1337, 256), (1, 48500, 256), (2, 700, 128), (64, 300, 256)])
+def test_linear_persistent(B, R, K):
+    M, N = B * R, 128
+    A = (rnd(M, K, seed=M) + 0.2).bfloat16()
+    W = (rnd(N, K, seed=5) / K ** 0.5).bfloat16()
+    bias = rnd(N, seed=3)
+    ref = A.double() @ W.double().t() + bias.double()
+    out = torch.full((M, N), float('nan'), device=DEV)
+    part = torch.empty(P.lib().query('dprnn_gemm_tc_stats_bytes', M), device=DEV, dtype=torch.uint8)
+    mr = torch.empty(B, 2, device=DEV)
+    P.lib().call('dprnn_linear_bf16_stats', A.to(DEV), W.to(DEV), bias.to(DEV), out, M, K, part, R, 1e-5, mr, stream())
+    torch.cuda.synchronize()
+    assert torch.isfinite(out).all()
+    assert O.peak_rel_err(out.cpu(), ref.float()) < 1e-5
+    rb = ref.view(B, -1)
+    assert torch.allclose(mr[:, 0].cpu().double(), rb.mean(1), rtol=1e-4, atol=1e-5)
+    assert torch.allclose(mr[:, 1].cpu().double(), 1 / torch.sqrt(rb.var(1, unbiased=False) + 1e-5), rtol=1e-4)

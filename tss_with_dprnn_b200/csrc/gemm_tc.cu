@@ -156,9 +156,8 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
 }
 
 // mean / rstd per utterance from the per-row partials written by the GEMM epilogue (fixed reduction order)
-__global__ void __launch_bounds__(256) row_stats_finalize_kernel(const float2* __restrict__ partial,
-                                                                 float* __restrict__ mean_rstd, long rows_per_utt,
-                                                                 int cols, double eps) {
+__global__ void row_stats_finalize_kernel(const float2* __restrict__ partial, float* __restrict__ mean_rstd,
+                                          long rows_per_utt, int cols, double eps) {
     __shared__ double scratch[32];
     const int b = blockIdx.x;
     const float2* p = partial + (long)b * rows_per_utt;
@@ -177,6 +176,14 @@ __global__ void __launch_bounds__(256) row_stats_finalize_kernel(const float2* _
         mean_rstd[2 * b] = (float)mean;
         mean_rstd[2 * b + 1] = (float)(1.0 / sqrt(var + eps));
     }
+}
+
+// host-side launcher shared with linear_persist.cu
+int launch_row_stats_finalize(const void* partial, float* mean_rstd, long n_utt, long rows_per_utt, int cols, double eps,
+                              cudaStream_t st) {
+    row_stats_finalize_kernel<<<(unsigned)n_utt, 256, 0, st>>>((const float2*)partial, mean_rstd, rows_per_utt, cols, eps);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
 }
 
 template <int kElem, int N, int EPI>
@@ -244,9 +251,7 @@ extern "C" int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const 
     }
     if (rc) return rc;
     if (stats_partial) {
-        row_stats_finalize_kernel<<<(unsigned)(M / rows_per_utt), 256, 0, st>>>((const float2*)stats_partial, mean_rstd,
-                                                                              rows_per_utt, N, (double)eps);
-        DPRNN_CHECK_LAUNCH();
+        return launch_row_stats_finalize(stats_partial, mean_rstd, M / rows_per_utt, rows_per_utt, N, (double)eps, st);
     }
     return 0;
 }
