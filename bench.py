@@ -175,8 +175,8 @@ def run_ours(args):
     model = P.DPRNNSpeTasNet(**KW).eval().to(dev)      # same seeded weights on every rank (replicated, 16 MB)
     model.precision = args.precision
     model.n_streams = args.streams
-    if args.l2_group_mb is not None:
-        model._engine.l2_group_bytes = args.l2_group_mb << 20
+    if args.fused_tail is not None:
+        model._engine.fused_tail = bool(args.fused_tail)
     B, T = args.batch, args.samples
     mix_h, ref_h = synth(B, T, rank)
     mix_h, ref_h = mix_h.pin_memory(), ref_h.pin_memory()
@@ -289,7 +289,7 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--streams', type=int, default=int(os.environ.get('DPRNN_STREAMS', '1')),
                     help='concurrent CUDA streams the batch is split over inside one forward')
-    ap.add_argument('--l2-group-mb', type=int, default=None, help='override Engine.l2_group_bytes (MiB)')
+    ap.add_argument('--fused-tail', type=int, default=None, help='1: Linear+norm+residual as one persistent kernel')
     ap.add_argument('--batch', type=int, default=64, help='utterances per GPU (cfg 2: 64)')
     ap.add_argument('--samples', type=int, default=24000, help='samples per utterance (3 s @ 8 kHz)')
     ap.add_argument('--cpu-batch', type=int, default=1, help='utterances per CPU-baseline forward')

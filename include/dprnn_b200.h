@@ -53,6 +53,10 @@ int dprnn_norm_affine(const float* mean_rstd, const float* gamma, const float* b
 int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const float* gamma, const float* beta,
                         int B, long rows_per_utt, int C, void* x_bf16, void* stream);
 
+/* Same with y stored in bf16 (the output of dprnn_linear_bf16out_stats); C a multiple of 8. */
+int dprnn_norm_residual_ybf16(const void* y_bf16, float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                              int B, long rows_per_utt, int C, void* x_bf16, void* stream);
+
 /* DPRNN._segmentation, src/models/dprnn.py:189-201 (F.unfold, kernel K, pad K, stride P):
  * y [B,L,F] -> x [B,S,K,F], x[b,s,k,:] = y[b, s*P+k-K, :] or 0. S = dprnn_num_chunks(L,K,P). Bit-exact. */
 int dprnn_num_chunks(long L, int K, int P);
@@ -149,6 +153,22 @@ int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias
  * memory, the output goes through swizzled staging + TMA stores.  stats_partial / mean_rstd as in dprnn_gemm_tc. */
 int dprnn_linear_bf16_stats(const void* A, const void* W, const float* bias, float* C, int M, int K,
                             void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream);
+
+/* Same kernel with the output rounded to bf16 (C_bf16 [M,128] bf16); the statistics are taken from the fp32 values. */
+int dprnn_linear_bf16out_stats(const void* A, const void* W, const float* bias, void* C_bf16, int M, int K,
+                               void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream);
+
+/* The tail of a DPRNN half-block, dprnn.py:86-92 / 96-99, as ONE persistent tcgen05 kernel (bf16 mode):
+ *   y = h[M,K] (bf16) @ W[128,K]^T (bf16) + bias;  x[M,128] (fp32, in place) += (y - mean_u) * rstd_u * gamma + beta,
+ * mean_u / rstd_u (biased variance, eps) over all rows x 128 columns of utterance u = rows [row_off[u], row_off[u+1])
+ * (row_off: n_utt+1 int64 on the device, row_off[n_utt] == M; utterances need not be tile-aligned or equal-length);
+ * x_bf16 [M,128] receives the bf16 copy of the new x (operand of the next LSTM layer).  y never exists in memory:
+ * pass 0 reduces the statistics from the accumulators, pass 1 recomputes the product and applies the norm; the second
+ * read of h is served from L2.  workspace: dprnn_linear_norm_workspace_bytes(M, n_utt) bytes, 256-byte aligned. */
+size_t dprnn_linear_norm_workspace_bytes(int M, int n_utt);
+int dprnn_linear_norm_residual_bf16(const void* h, const void* W, const float* bias, float* x, void* x_bf16,
+                                    const float* gamma, const float* beta, float eps, const long* row_off, int n_utt,
+                                    long max_rows_per_utt, int M, int K, void* workspace, void* stream);
 
 /* One whole nn.LSTM layer (input projection + recurrence, both directions), src/models/dprnn.py:23-28,35-36,
  * as a fused tcgen05 kernel: per step gates = [x_t | h_{t-1}] @ [W_ih | W_hh]^T with fp32 accumulators in TMEM,

@@ -146,3 +146,69 @@ def test_linear_persistent(B, R, K):
     rb = ref.view(B, -1)
     assert torch.allclose(mr[:, 0].cpu().double(), rb.mean(1), rtol=1e-4, atol=1e-5)
     assert torch.allclose(mr[:, 1].cpu().double(), 1 / torch.sqrt(rb.var(1, unbiased=False) + 1e-5), rtol=1e-4)
+
+
+@pytest.mark.parametrize('lens,K', [([1337, 1337, 1337], 256), ([48500], 256), ([700, 700], 128), ([300] * 64, 256),
+                                    ([750, 2250, 1000, 48500, 1250], 256), ([24250] * 9, 256)])
+def test_linear_norm_residual_fused(lens, K):
+    """Linear + GroupNorm(1,128) statistics + apply + residual in one persistent kernel (linear_norm.cu) against an fp64
+    restatement of dprnn.py:86-92; utterances of unequal length that do not align with the 128-row tiles."""
+    M, N, n = sum(lens), 128, len(lens)
+    h = (rnd(M, K, seed=M % 1000) + 0.2).bfloat16()
+    W = (rnd(N, K, seed=5) / K ** 0.5).bfloat16()
+    bias, gamma, beta = rnd(N, seed=3), 1 + 0.1 * rnd(N, seed=4), 0.1 * rnd(N, seed=6)
+    x0 = rnd(M, N, seed=7)
+    y = h.double() @ W.double().t() + bias.double()
+    want = x0.double().clone()
+    off = [0]
+    for ln in lens:
+        off.append(off[-1] + ln)
+    for u in range(n):
+        yu = y[off[u]:off[u + 1]]
+        mean, var = yu.mean(), yu.var(unbiased=False)
+        want[off[u]:off[u + 1]] += (yu - mean) / torch.sqrt(var + 1e-5) * gamma.double() + beta.double()
+    L = P.lib()
+    ws = torch.empty(L.query('dprnn_linear_norm_workspace_bytes', M, n), device=DEV, dtype=torch.uint8)
+    outs = []
+    for _ in range(2):
+        x = x0.clone().to(DEV)
+        xb = torch.full((M, N), float('nan'), device=DEV, dtype=torch.bfloat16)
+        L.call('dprnn_linear_norm_residual_bf16', h.to(DEV), W.to(DEV), bias.to(DEV), x, xb, gamma.to(DEV), beta.to(DEV),
+               1e-5, torch.tensor(off, dtype=torch.int64, device=DEV), n, max(lens), M, K, ws, stream())
+        torch.cuda.synchronize()
+        outs.append((x.cpu(), xb.cpu()))
+    x, xb = outs[0]
+    assert torch.isfinite(x).all()
+    assert O.peak_rel_err(x, want.float()) < 2e-5
+    assert torch.equal(xb, x.bfloat16())                      # the shadow copy is the rounded new x
+    assert torch.equal(outs[1][0], x)                         # deterministic statistics
+
+
+@pytest.mark.parametrize('B,R,K', [(3, 1337, 256), (1, 48500, 256), (2, 700, 128)])
+def test_linear_bf16out_then_norm_residual(B, R, K):
+    """Linear with bf16 output + fp32-accurate statistics, then norm + residual reading the bf16 y (dprnn.py:86-92)."""
+    M, N = B * R, 128
+    A = (rnd(M, K, seed=M) + 0.2).bfloat16()
+    W = (rnd(N, K, seed=5) / K ** 0.5).bfloat16()
+    bias, gamma, beta = rnd(N, seed=3), 1 + 0.1 * rnd(N, seed=4), 0.1 * rnd(N, seed=6)
+    x0 = rnd(M, N, seed=7)
+    ref = A.double() @ W.double().t() + bias.double()
+    L = P.lib()
+    y = torch.full((M, N), float('nan'), device=DEV, dtype=torch.bfloat16)
+    part = torch.empty(L.query('dprnn_gemm_tc_stats_bytes', M), device=DEV, dtype=torch.uint8)
+    mr = torch.empty(B, 2, device=DEV)
+    L.call('dprnn_linear_bf16out_stats', A.to(DEV), W.to(DEV), bias.to(DEV), y, M, K, part, R, 1e-5, mr, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(y.cpu(), ref.float().bfloat16()) or O.peak_rel_err(y.float().cpu(), ref.float()) < 4e-3
+    rb = ref.view(B, -1)
+    mean, rstd = rb.mean(1), 1 / torch.sqrt(rb.var(1, unbiased=False) + 1e-5)
+    assert torch.allclose(mr[:, 0].cpu().double(), mean, rtol=1e-4, atol=1e-5)      # statistics are NOT from the rounded y
+    assert torch.allclose(mr[:, 1].cpu().double(), rstd, rtol=1e-4)
+    x = x0.clone().to(DEV)
+    xb = torch.empty((M, N), device=DEV, dtype=torch.bfloat16)
+    L.call('dprnn_norm_residual_ybf16', y, x, mr, gamma.to(DEV), beta.to(DEV), B, R, N, xb, stream())
+    torch.cuda.synchronize()
+    yv = y.float().cpu().double().view(B, R, N)
+    want = x0.double().view(B, R, N) + (yv - mean.view(B, 1, 1)) * rstd.view(B, 1, 1) * gamma.double() + beta.double()
+    assert O.peak_rel_err(x.cpu(), want.view(M, N).float()) < 2e-5
+    assert torch.equal(xb.cpu(), x.cpu().bfloat16())

@@ -28,7 +28,7 @@ __device__ __forceinline__ void lp_tma_store_2d(const CUtensorMap* m, const void
                  ::"l"(m), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int KB>     // K / 64
+template <int KB, bool kBf16Out>     // K / 64; output fp32 or bf16
 __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmW,
                                                                 const __grid_constant__ CUtensorMap tmC,
@@ -107,6 +107,45 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * LP_N;
             float s_sum = 0.f, s_sq = 0.f;
+            if constexpr (kBf16Out) {
+                // 64-column chunks: [128 rows x 64 bf16] = one 128B-swizzled staging tile; statistics from the fp32 values
+#pragma unroll 1
+                for (int c0 = 0; c0 < LP_N; c0 += 64, ++chunk_it) {
+                    uint32_t pk[32];
+#pragma unroll
+                    for (int hh = 0; hh < 2; ++hh) {
+                        float v[32];
+                        tmem_ld32(taddr + c0 + hh * 32, v);
+                        if (c0 + 64 == LP_N && hh == 1) {       // accumulator fully read: hand it back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0) mbar_arrive(&acc_empty[acc]);
+                        }
+                        float s = 0.f, qq = 0.f;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 2) {
+                            const float y0 = v[j] + __ldg(a.bias + c0 + hh * 32 + j), y1 = v[j + 1] + __ldg(a.bias + c0 + hh * 32 + j + 1);
+                            s += y0 + y1; qq = fmaf(y0, y0, fmaf(y1, y1, qq));
+                            __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
+                            pk[hh * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&b2);
+                        }
+                        s_sum += s; s_sq += qq;
+                    }
+                    uint8_t* stage = sC + (chunk_it % LP_CST) * LP_BLK;
+                    if (storer) asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(LP_CST - 1) : "memory");
+                    asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+                    for (int j = 0; j < 8; ++j)
+                        *reinterpret_cast<uint4*>(stage + sw128_offset(r_in_tile, j)) =
+                            make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    fence_async_smem();
+                    asm volatile("bar.sync 2, 128;" ::: "memory");
+                    if (storer) {
+                        lp_tma_store_2d(&tmC, stage, c0, tile * 128);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                }
+            } else {
 #pragma unroll 1
             for (int c0 = 0; c0 < LP_N; c0 += 32, ++chunk_it) {
                 float v[32];
@@ -137,6 +176,7 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
+            }
             if (a.stats && row < a.M) a.stats[row] = make_float2(s_sum, s_sq);
         }
         if (storer) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -150,21 +190,22 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
 int launch_row_stats_finalize(const void* partial, float* mean_rstd, long n_utt, long rows_per_utt, int cols, double eps,
                               cudaStream_t st);
 
-template <int KB>
-static int launch_lp(const void* A, const void* W, const float* bias, float* C, int M, void* stats, cudaStream_t st) {
+template <int KB, bool kBf16Out>
+static int launch_lp(const void* A, const void* W, const float* bias, void* C, int M, void* stats, cudaStream_t st) {
     constexpr int K = KB * 64;
     CUtensorMap tmA, tmW, tmC;
     const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {2, (uint64_t)K * 2};
     const uint32_t bA[2] = {64, 128};
     const uint64_t dW[2] = {(uint64_t)K, (uint64_t)LP_N}, sW[2] = {2, (uint64_t)K * 2};
     const uint32_t bW[2] = {64, (uint32_t)LP_N};
-    const uint64_t dC[2] = {(uint64_t)LP_N, (uint64_t)M}, sC[2] = {4, (uint64_t)LP_N * 4};
-    const uint32_t bC[2] = {32, 128};
+    const uint64_t esz = kBf16Out ? 2 : 4;
+    const uint64_t dC[2] = {(uint64_t)LP_N, (uint64_t)M}, sC[2] = {esz, (uint64_t)LP_N * esz};
+    const uint32_t bC[2] = {kBf16Out ? 64u : 32u, 128};
     if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dA, sA, bA)) return 1;
     if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dW, sW, bW)) return 1;
-    if (make_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dC, sC, bC)) return 1;
+    if (make_tmap(&tmC, kBf16Out ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dC, sC, bC)) return 1;
     const size_t smem = (size_t)(KB + LP_AST + LP_CST) * LP_BLK + 1024;
-    auto kern = linear_persist_kernel<KB>;
+    auto kern = linear_persist_kernel<KB, kBf16Out>;
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -180,17 +221,30 @@ static int launch_lp(const void* A, const void* W, const float* bias, float* C, 
 
 using namespace dprnn;
 
-extern "C" int dprnn_linear_bf16_stats(const void* A, const void* W, const float* bias, float* C, int M, int K,
-                                       void* stats_partial, long rows_per_utt, float eps, float* mean_rstd,
-                                       void* stream) {
+static int linear_stats_impl(const void* A, const void* W, const float* bias, void* C, bool bf16_out, int M, int K,
+                             void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream) {
     DPRNN_CHECK_ARG(A && W && bias && C && M > 0 && (K == 128 || K == 256));
     DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) % 16 == 0);
     if (stats_partial) DPRNN_CHECK_ARG(rows_per_utt > 0 && M % rows_per_utt == 0 && mean_rstd);
     cudaStream_t st = (cudaStream_t)stream;
-    const int rc = K == 256 ? launch_lp<4>(A, W, bias, C, M, stats_partial, st) : launch_lp<2>(A, W, bias, C, M, stats_partial, st);
+    int rc;
+    if (bf16_out) rc = K == 256 ? launch_lp<4, true>(A, W, bias, C, M, stats_partial, st) : launch_lp<2, true>(A, W, bias, C, M, stats_partial, st);
+    else rc = K == 256 ? launch_lp<4, false>(A, W, bias, C, M, stats_partial, st) : launch_lp<2, false>(A, W, bias, C, M, stats_partial, st);
     if (rc) return rc;
     if (stats_partial) {
         return launch_row_stats_finalize(stats_partial, mean_rstd, M / rows_per_utt, rows_per_utt, LP_N, (double)eps, st);
     }
     return 0;
+}
+
+extern "C" int dprnn_linear_bf16_stats(const void* A, const void* W, const float* bias, float* C, int M, int K,
+                                       void* stats_partial, long rows_per_utt, float eps, float* mean_rstd,
+                                       void* stream) {
+    return linear_stats_impl(A, W, bias, C, false, M, K, stats_partial, rows_per_utt, eps, mean_rstd, stream);
+}
+
+extern "C" int dprnn_linear_bf16out_stats(const void* A, const void* W, const float* bias, void* C_bf16, int M, int K,
+                                          void* stats_partial, long rows_per_utt, float eps, float* mean_rstd,
+                                          void* stream) {
+    return linear_stats_impl(A, W, bias, C_bf16, true, M, K, stats_partial, rows_per_utt, eps, mean_rstd, stream);
 }

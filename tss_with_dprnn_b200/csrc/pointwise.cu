@@ -123,6 +123,41 @@ __global__ void norm_residual_kernel(const float* __restrict__ y, float* __restr
     }
 }
 
+// Same with y in bf16 (output of the tensor-core Linear), 8 elements per thread
+__global__ void norm_residual_ybf16_kernel(const uint4* __restrict__ y, float* __restrict__ x,
+                                           const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, long total8, long per_utt8, int c8n,
+                                           uint4* __restrict__ x_bf16) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total8; idx += (long)gridDim.x * blockDim.x) {
+        const long b = idx / per_utt8;
+        const int c8 = (int)(idx % c8n);
+        const float mean = __ldg(mean_rstd + 2 * b), rstd = __ldg(mean_rstd + 2 * b + 1);
+        uint4 yv;
+        asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                     : "=r"(yv.x), "=r"(yv.y), "=r"(yv.z), "=r"(yv.w) : "l"(y + idx));
+        const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w};
+        float4 r[2] = {reinterpret_cast<float4*>(x)[2 * idx], reinterpret_cast<float4*>(x)[2 * idx + 1]};
+        uint32_t ob[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8 + h);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8 + h);
+            const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[2 * h]));
+            const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[2 * h + 1]));
+            r[h].x += (y01.x - mean) * rstd * g.x + be.x;
+            r[h].y += (y01.y - mean) * rstd * g.y + be.y;
+            r[h].z += (y23.x - mean) * rstd * g.z + be.z;
+            r[h].w += (y23.y - mean) * rstd * g.w + be.w;
+            __nv_bfloat162 lo = __floats2bfloat162_rn(r[h].x, r[h].y), hi = __floats2bfloat162_rn(r[h].z, r[h].w);
+            ob[2 * h] = *reinterpret_cast<uint32_t*>(&lo);
+            ob[2 * h + 1] = *reinterpret_cast<uint32_t*>(&hi);
+        }
+        reinterpret_cast<float4*>(x)[2 * idx] = r[0];
+        reinterpret_cast<float4*>(x)[2 * idx + 1] = r[1];
+        if (x_bf16) x_bf16[idx] = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+    }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ x, uint2* __restrict__ out, long total4) {
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
         const float4 r = reinterpret_cast<const float4*>(x)[idx];
@@ -480,6 +515,16 @@ int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const 
     norm_residual_kernel<<<grid_for(per4 * B, 256), 256, 0, (cudaStream_t)stream>>>(y, x, mean_rstd, gamma, beta,
                                                                                   per4 * B, per4, C / 4,
                                                                                   (uint2*)x_bf16);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_norm_residual_ybf16(const void* y_bf16, float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                              int B, long rows_per_utt, int C, void* x_bf16, void* stream) {
+    DPRNN_CHECK_ARG(y_bf16 && x && mean_rstd && gamma && beta && B > 0 && rows_per_utt > 0 && C % 8 == 0);
+    const long per8 = rows_per_utt * (C / 8);
+    norm_residual_ybf16_kernel<<<grid_for(per8 * B, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)y_bf16, x, mean_rstd, gamma, beta, per8 * B, per8, C / 8, (uint4*)x_bf16);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

@@ -28,7 +28,8 @@ class Engine:
         self.precision = 'fp32'
         self.fast_act = True       # bf16 mode: tanh.approx-based gate activations (1 MUFU op each)
         self.n_streams = 1         # >1: the batch is split into that many utterance groups on concurrent streams
-        self.l2_group_bytes = 1 << 40    # Linear->norm utterance grouping (measured: small groups lose to tail effects)
+        self.fused_tail = False    # bf16 mode: Linear + norm + residual as one persistent kernel (linear_norm.cu)
+        self._row_off = {}
         self._streams = []
         self._packed = None
         self._packed_key = None
@@ -140,6 +141,13 @@ class Engine:
         if x.dtype != torch.float32:
             raise TypeError(f'{name} must be float32')
         return x.contiguous()
+
+    def _row_offsets(self, B, R, dev):
+        """int64 [B+1] first chunk-position row of every utterance (equal-length batch)."""
+        key = (B, R, str(dev))
+        if key not in self._row_off:
+            self._row_off[key] = (torch.arange(B + 1, dtype=torch.int64) * R).to(dev)
+        return self._row_off[key]
 
     def _norm_params(self, mod):
         if hasattr(mod, 'gamma'):
@@ -357,21 +365,22 @@ class Engine:
                     hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
                     L_.call('dprnn_lstm_layer_bf16', xb, hw['tc_w'], hw['tc_bias'], hb, B, S, K, which, H, nd,
                             int(self.fast_act), st)
-                    # Linear -> norm -> residual per small utterance group: the fp32 Linear output of a group
-                    # (<= l2_group_bytes) is consumed by the norm kernel right away, i.e. out of the 126 MB L2,
-                    # and its buffer is reused by the next group, so it never costs HBM bandwidth.
                     R = S * K
-                    G = max(1, min(B, int(self.l2_group_bytes // (R * F * 4))))
-                    ybuf = torch.empty((G * R, F), device=dev)
-                    x2, xb2 = x.view(B * R, F), xb
-                    for b0 in range(0, B, G):
-                        g = min(G, B - b0)
-                        r0, nr = b0 * R, g * R
-                        part = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', nr), device=dev, dtype=torch.uint8)
-                        mr2 = torch.empty((g, 2), device=dev)
-                        L_.call('dprnn_linear_bf16_stats', hb[r0:r0 + nr], hw['lin_bf16'], hw['lin_b'], ybuf, nr, nd * H,
-                                part, R, float(eps), mr2, st)
-                        L_.call('dprnn_norm_residual', ybuf, x2[r0:r0 + nr], mr2, g_, b_, g, R, F, xb2[r0:r0 + nr], st)
+                    if self.fused_tail:
+                        # Linear + norm statistics + norm apply + residual in one persistent kernel (linear_norm.cu)
+                        ws = torch.empty(L_.query('dprnn_linear_norm_workspace_bytes', rows, B), device=dev,
+                                         dtype=torch.uint8)
+                        L_.call('dprnn_linear_norm_residual_bf16', hb, hw['lin_bf16'], hw['lin_b'], x, xb, g_, b_,
+                                float(eps), self._row_offsets(B, R, dev), B, R, rows, nd * H, ws, st)
+                        del hb, ws
+                        continue
+                    # Linear (bf16 output, statistics from the fp32 accumulators) -> finalize -> norm + residual
+                    ybuf = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+                    part = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', rows), device=dev, dtype=torch.uint8)
+                    mr2 = torch.empty((B, 2), device=dev)
+                    L_.call('dprnn_linear_bf16out_stats', hb, hw['lin_bf16'], hw['lin_b'], ybuf, rows, nd * H, part, R,
+                            float(eps), mr2, st)
+                    L_.call('dprnn_norm_residual_ybf16', ybuf, x, mr2, g_, b_, B, R, F, xb, st)
                     del hb, ybuf
                     continue
                 gx = self.gemm(x, hw['wih_t'], rows, nd * 4 * H, F, bias=hw['bias'])
