@@ -201,8 +201,9 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
         // TMEM: D0 = columns [0,256) (hidden units 0..63, gates i|f|g|o), D1 = [256,512) (units 64..127).
-        // Per step:  x-part(D0) is issued as soon as the epilogue has drained D0 (during its work on D1);
-        // when h_{t-1} is complete: h-part(D0) -> d_full[0]; h-part(D1) -> h_free; x-part(D1) -> d_full[1].
+        // Per step:  x-part(D0) and the first K-half of h-part(D0) (units 0..63 of h_{t-1}) are issued as soon as the
+        // epilogue has drained D0 and written that half (during its work on D1); when h_{t-1} is complete:
+        // second K-half of h-part(D0) -> d_full[0]; h-part(D1) -> h_free; x-part(D1) -> d_full[1].
         // The epilogue of D0 therefore overlaps the MMAs of D1, and the next x-part(D0) the epilogue of D1.
         if (rank == 0 && elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(256, 256);
@@ -232,9 +233,10 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                 mbar_wait_cluster(&h_done[0], par);               // D0 drained by both CTAs
                 tc_fence_after();
                 mma_kb(0, 0, aX + s0 * TILE, true);  mma_kb(0, 1, aX + s1 * TILE, false);
+                mma_kb(0, 2, aH, false);                          // units 0..63 of h_{t-1} were published with h_done[0]
                 mbar_wait_cluster(&h_done[1], par);               // D1 drained, h_{t-1} complete in both CTAs
                 tc_fence_after();
-                mma_kb(0, 2, aH, false);  mma_kb(0, 3, aH + TILE, false);
+                mma_kb(0, 3, aH + TILE, false);                   // only K=64 of D0 is left on the step's critical path
                 umma_commit_2cta(&d_full[0], 3);
                 mma_kb(1, 2, aH, true);   mma_kb(1, 3, aH + TILE, false);
                 umma_commit_2cta(h_free, 3);
