@@ -189,6 +189,58 @@ int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias
 int dprnn_linear_bf16(const void* A, const void* W, const float* bias, float* C, long ldc, int M, int N, int K,
                       void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Ragged (variable-length) batches - SURVEY.md section 8d cfg 3: the reference's test loop runs B = 1 on full-length
+ * utterances (src/inferencers/inferencer_spe.py:25-45); these entry points give the same per-utterance results for
+ * utterances of different lengths packed back to back (no padding enters a statistic, recurrence or softmax).
+ *   frame space: utterance b = rows [frame_off[b], frame_off[b]+T_b); its first L_b = T_b-(ksz-1) rows are frames, the
+ *                rest junk (the encoder runs over the packed waveform, stride 1); frame_utt[row] = b (int32).
+ *   chunk space: utterance b = chunks [chunk_off[b], chunk_off[b]+S_b), K rows each; chunk_utt[chunk] = b (int32).
+ * All index arrays live on the device; offsets / lengths are int64.  Row-wise stages use the uniform entry points.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* GroupNorm(1,C) / gLN statistics of rows [off[b], off[b]+len[b]) x C (dprnn.py:130-136, dprnn_spe.py:116,136). */
+size_t dprnn_utt_stats_ragged_workspace_bytes(int B);
+int dprnn_utt_stats_ragged(const float* x, int C, const long* off, const long* len, int B, float eps, void* workspace,
+                           float* mean_rstd, void* stream);
+/* mean/rstd per utterance (rows [row_off[b], row_off[b+1])) from the per-row sums of dprnn_linear_bf16*_stats. */
+int dprnn_row_stats_finalize_ragged(const void* stats_partial, const long* row_off, int B, int cols, float eps,
+                                    float* mean_rstd, void* stream);
+/* dprnn_norm_residual on the packed chunk space; y fp32 or bf16. */
+int dprnn_norm_residual_ragged(const void* y, int y_is_bf16, float* x, const float* mean_rstd, const float* gamma,
+                               const float* beta, const int* chunk_utt, long total_chunks, int K, int C, void* x_bf16,
+                               void* stream);
+/* dprnn_unfold / dprnn_fold_prelu between the packed frame and chunk spaces (integer maps bit-exact per utterance). */
+int dprnn_unfold_ragged(const float* y, float* x, const int* chunk_utt, const long* chunk_off, const long* frame_off,
+                        const long* L, long total_chunks, int K, int P, int F, void* stream);
+int dprnn_fold_prelu_ragged(const float* x, float* out, const int* frame_utt, const long* frame_off, const long* L,
+                            const long* chunk_off, const long* S, long total_rows, int K, int P, int F,
+                            const float* prelu_a, void* stream);
+/* dprnn_mask_decode for stride 1: out[frame_off[b]+t], t < T_b. */
+int dprnn_mask_decode_ragged(const float* mask, const float* enc, const float* wdec, float* out, const int* frame_utt,
+                             const long* frame_off, const long* L, long total_rows, int N, int ksz, void* stream);
+/* dprnn_att_rowscale; scores of utterance b are kept at rows frame_off[b] .. +La[b] of a frame-space scratch. */
+int dprnn_att_rowscale_ragged(const float* enc, const float* s1, const float* s0, const float* wavg, const float* bavg,
+                              const float* v, float* scores, float* rowscale, const int* frame_utt,
+                              const long* frame_off, const long* L, const long* La, int B, long total_rows, int N,
+                              int ksz, void* stream);
+/* dprnn_affine_add_prelu_pool3: out row r (utterance out_utt[r]) = max over rows in_off[b]+3*(r-out_off[b])+{0,1,2}. */
+int dprnn_affine_add_prelu_pool3_ragged(const float* y, const float* scale, const float* shift, const float* skip,
+                                        const float* prelu_a, float* out, const int* out_utt, const long* in_off,
+                                        const long* out_off, long total_out_rows, int C, void* stream);
+int dprnn_time_sum_ragged(const float* x, float* emb, const long* off, const long* len, int B, int C, const float* div,
+                          void* stream);
+/* dprnn_gemm_f32 with the utterance of every row given explicitly (prologue / per-utterance bias). */
+int dprnn_gemm_f32_ragged(const float* A, long lda, const float* Wt, long ldw, float* C, long ldc, int M, int N, int K,
+                          const float* bias, int bias_per_utt, float bias_scale, const int* row_utt,
+                          const float* p_scale, const float* p_shift, const float* p_add, const float* rowscale,
+                          int epilogue, void* stream);
+/* Inter-chunk layer of dprnn_lstm_layer_bf16 on the packed chunk space: utt_jobs = n_utt x {int32 first chunk, int32
+ * number of chunks}, in the order the pair-jobs should be scheduled (longest first). */
+int dprnn_lstm_inter_bf16_ragged(const void* x, const void* w_packed, const float* bias_perm, void* hout,
+                                 long total_chunks, int K, const void* utt_jobs, int n_utt, int hidden, int ndir,
+                                 int fast_act, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -21,6 +21,7 @@ struct GemmParams {
     long rows_per_utt;
     const float* p_scale; const float* p_shift; const float* p_add; const float* rowscale;
     int epi;
+    const int* row_utt;      // ragged batches: utterance of every row (else NULL: row / rows_per_utt)
 };
 
 __device__ __forceinline__ float apply_act(float v, int epi) {
@@ -41,7 +42,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
     const int ar = tid >> 2, akq = tid & 3;                 // A: row ar, k = akq*4..+3
     const long arow = m0 + ar;
     const bool arow_ok = arow < p.M;
-    const long ab = (p.p_scale || p.p_add) && arow_ok ? arow / p.rows_per_utt : 0;
+    const long ab = (p.p_scale || p.p_add) && arow_ok ? (p.row_utt ? (long)__ldg(p.row_utt + arow) : arow / p.rows_per_utt) : 0;
     const float rs = (p.rowscale && arow_ok) ? p.rowscale[arow] : 1.0f;
 
     float4 areg, breg[2];
@@ -121,7 +122,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
         const long row = m0 + ty * 4 + i;
         if (row >= p.M) continue;
         const float* bias = p.bias;
-        if (bias && p.bias_per_utt) bias += (row / p.rows_per_utt) * p.N;
+        if (bias && p.bias_per_utt) bias += (p.row_utt ? (long)__ldg(p.row_utt + row) : row / p.rows_per_utt) * p.N;
         if (p.epi == DPRNN_EPI_GATED) {
             const int c0 = n0 + tx * 4, c1 = n0 + 64 + tx * 4;
             if (c1 < p.N) {
@@ -155,22 +156,39 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
 
 using namespace dprnn;
 
-extern "C" int dprnn_gemm_f32(const float* A, long lda, const float* Wt, long ldw, float* C, long ldc, int M, int N,
-                              int K, const float* bias, int bias_per_utt, float bias_scale, long rows_per_utt,
-                              const float* p_scale, const float* p_shift, const float* p_add, const float* rowscale,
-                              int epilogue, void* stream) {
+static int gemm_f32_impl(const float* A, long lda, const float* Wt, long ldw, float* C, long ldc, int M, int N,
+                         int K, const float* bias, int bias_per_utt, float bias_scale, long rows_per_utt,
+                         const float* p_scale, const float* p_shift, const float* p_add, const float* rowscale,
+                         int epilogue, const int* row_utt, void* stream) {
     DPRNN_CHECK_ARG(A && Wt && C && M > 0 && N > 0 && K > 0);
     DPRNN_CHECK_ARG(N % 4 == 0 && K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && ldc % 4 == 0);
     DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)Wt | (uintptr_t)C) % 16 == 0);
     DPRNN_CHECK_ARG(epilogue >= DPRNN_EPI_NONE && epilogue <= DPRNN_EPI_GATED);
     DPRNN_CHECK_ARG(epilogue != DPRNN_EPI_GATED || N % 128 == 0);
     DPRNN_CHECK_ARG((p_scale == nullptr) == (p_shift == nullptr));
-    if (bias_per_utt || p_scale || p_add) DPRNN_CHECK_ARG(rows_per_utt > 0);
+    if ((bias_per_utt || p_scale || p_add) && !row_utt) DPRNN_CHECK_ARG(rows_per_utt > 0);
     if (rows_per_utt <= 0) rows_per_utt = M;
     GemmParams p{A, lda, Wt, ldw, C, ldc, M, N, K, bias, bias_per_utt, bias_scale, rows_per_utt,
-                 p_scale, p_shift, p_add, rowscale, epilogue};
+                 p_scale, p_shift, p_add, rowscale, epilogue, row_utt};
     dim3 grid(cdiv(M, BM), cdiv(N, BN));
     gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     DPRNN_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int dprnn_gemm_f32(const float* A, long lda, const float* Wt, long ldw, float* C, long ldc, int M, int N,
+                              int K, const float* bias, int bias_per_utt, float bias_scale, long rows_per_utt,
+                              const float* p_scale, const float* p_shift, const float* p_add, const float* rowscale,
+                              int epilogue, void* stream) {
+    return gemm_f32_impl(A, lda, Wt, ldw, C, ldc, M, N, K, bias, bias_per_utt, bias_scale, rows_per_utt, p_scale, p_shift,
+                         p_add, rowscale, epilogue, nullptr, stream);
+}
+
+extern "C" int dprnn_gemm_f32_ragged(const float* A, long lda, const float* Wt, long ldw, float* C, long ldc, int M,
+                                     int N, int K, const float* bias, int bias_per_utt, float bias_scale,
+                                     const int* row_utt, const float* p_scale, const float* p_shift, const float* p_add,
+                                     const float* rowscale, int epilogue, void* stream) {
+    DPRNN_CHECK_ARG(row_utt);
+    return gemm_f32_impl(A, lda, Wt, ldw, C, ldc, M, N, K, bias, bias_per_utt, bias_scale, 0, p_scale, p_shift, p_add,
+                         rowscale, epilogue, row_utt, stream);
 }

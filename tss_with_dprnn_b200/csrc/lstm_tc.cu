@@ -32,6 +32,7 @@ struct LstmTcParams {
     int seq_dim;           // which tensor-map coordinate runs over sequences: 2 (intra) or 1 (inter)
     int tiles_per_outer;   // 256-sequence tiles per outer index
     int ndir;
+    const int2* jobs;      // ragged inter-chunk layer: per utterance {first chunk, number of chunks}; else NULL
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -144,8 +145,13 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
     const int job = blockIdx.x >> 1;
     const int dir = job % p.ndir;
     const int jt = job / p.ndir;
-    const int outer = jt / p.tiles_per_outer;
+    int outer = jt / p.tiles_per_outer;
     const int seq0 = (jt % p.tiles_per_outer) * 256 + (int)rank * 128;
+    int T = p.T, t_base = 0;
+    if (p.jobs) {          // one pair-job per utterance: its S_b chunks start at chunk t_base of the packed chunk space
+        const int2 j = p.jobs[jt];
+        t_base = j.x; T = j.y; outer = 0;
+    }
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) {         // SWIZZLE_128B tiles need a 1024-byte aligned base
@@ -179,15 +185,15 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 
     // coordinates of (this CTA's 128 sequences, time t): intra (f, t, seq, 0) / inter (f, seq, t, outer)
     auto c1 = [&](int t) { return p.seq_dim == 2 ? t : seq0; };
-    auto c2 = [&](int t) { return p.seq_dim == 2 ? seq0 : t; };
+    auto c2 = [&](int t) { return p.seq_dim == 2 ? seq0 : t_base + t; };
 
     if (warp == 0) {
         // ================= TMA producer: x_t K-halves into the ring =================
         if (elect_one()) {
             const uint32_t leader_full0 = map_to_cta(smem_u32(&x_full[0]), 0);
             int it = 0;
-            for (int step = 0; step < p.T; ++step) {
-                const int t = dir ? p.T - 1 - step : step;
+            for (int step = 0; step < T; ++step) {
+                const int t = dir ? T - 1 - step : step;
                 for (int half = 0; half < 2; ++half, ++it) {
                     const int s = it % NXS;
                     mbar_wait(&x_empty[s], ((it / NXS) & 1) ^ 1);
@@ -216,7 +222,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
                                  idesc, (first && kk == 0) ? 0u : 1u);
             };
             int it = 0;
-            for (int step = 0; step < p.T; ++step, it += 2) {
+            for (int step = 0; step < T; ++step, it += 2) {
                 const int s0 = it % NXS, s1 = (it + 1) % NXS;
                 mbar_wait_cluster(&x_full[s0], (it / NXS) & 1);
                 mbar_wait_cluster(&x_full[s1], ((it + 1) / NXS) & 1);
@@ -257,8 +263,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         for (int i = 0; i < 32; ++i) { c0[i] = 0.f; c1s[i] = 0.f; }
         const bool storer = (warp == 4 && lane == 0);
 
-        for (int step = 0; step < p.T; ++step) {
-            const int t = dir ? p.T - 1 - step : step;
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? T - 1 - step : step;
             const uint32_t par = step & 1;
             // ---------------- unit half 0
             mbar_wait(&d_full[0], par);
@@ -319,8 +325,8 @@ using namespace dprnn;
 // x [rows,128] bf16; w_packed [ndir*2*2*128, 256] bf16 (see engine._pack_lstm_tc); bias_perm [ndir,512] fp32;
 // hout [rows, ndir*128] bf16.  Geometry: `inter`==0: rows = (b,s,k), sequences (b,s) run along k;
 // `inter`==1: sequences (b,k) run along s.
-extern "C" int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B,
-                                     int S, int K, int inter, int hidden, int ndir, int fast_act, void* stream) {
+static int lstm_layer_impl(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
+                           int inter, int hidden, int ndir, int fast_act, const int2* jobs, int n_jobs, void* stream) {
     DPRNN_CHECK_ARG(x && w_packed && bias_perm && hout && B > 0 && S > 0 && K > 0);
     DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2));
     DPRNN_CHECK_ARG(((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)hout) % 16 == 0);
@@ -328,6 +334,7 @@ extern "C" int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const 
     const uint64_t ldx = 128 * 2, ldh = (uint64_t)ndir * 128 * 2;
     LstmTcParams p;
     p.ndir = ndir;
+    p.jobs = jobs;
     uint64_t dX[4], sX[4], dH[4], sH[4];
     uint32_t box[4] = {64, 1, 1, 1};
     long njobs;
@@ -345,6 +352,10 @@ extern "C" int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const 
         box[1] = 128;
         p.T = S; p.seq_dim = 1; p.tiles_per_outer = (K + 255) / 256;
         njobs = (long)p.tiles_per_outer * B * ndir;
+        if (jobs) {        // ragged: B == 1, S = total chunks of the packed batch, one pair-job per utterance and direction
+            DPRNN_CHECK_ARG(B == 1 && K <= 256 && n_jobs > 0);
+            njobs = (long)n_jobs * ndir;
+        }
     }
     for (int i = 0; i < 4; ++i) dH[i] = dX[i];
     dH[0] = (uint64_t)ndir * 128;
@@ -360,4 +371,20 @@ extern "C" int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const 
     kern<<<(unsigned)(njobs * 2), 384, smem, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);
     DPRNN_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B,
+                                     int S, int K, int inter, int hidden, int ndir, int fast_act, void* stream) {
+    return lstm_layer_impl(x, w_packed, bias_perm, hout, B, S, K, inter, hidden, ndir, fast_act, nullptr, 0, stream);
+}
+
+// Inter-chunk layer of a ragged batch: x / hout are the packed chunk space [total_chunks, K, .]; utt_jobs[j] =
+// {first chunk, number of chunks} of one utterance (the caller orders them longest first: the pair-jobs are scheduled
+// in that order, which is the LPT rule for the tail of the grid).
+extern "C" int dprnn_lstm_inter_bf16_ragged(const void* x, const void* w_packed, const float* bias_perm, void* hout,
+                                            long total_chunks, int K, const void* utt_jobs, int n_utt, int hidden,
+                                            int ndir, int fast_act, void* stream) {
+    DPRNN_CHECK_ARG(utt_jobs && n_utt > 0 && total_chunks > 0 && total_chunks < (1L << 31));
+    return lstm_layer_impl(x, w_packed, bias_perm, hout, 1, (int)total_chunks, K, 1, hidden, ndir, fast_act,
+                           (const int2*)utt_jobs, n_utt, stream);
 }

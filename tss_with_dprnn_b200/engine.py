@@ -13,6 +13,7 @@ from __future__ import annotations
 import torch
 
 from ._lib import lib
+from .ragged import RaggedMixin
 
 EPI_NONE, EPI_RELU, EPI_SIGMOID, EPI_GATED = 0, 1, 2, 3
 
@@ -22,7 +23,7 @@ def _t(w: torch.Tensor) -> torch.Tensor:
     return w.detach().reshape(w.shape[0], -1).t().contiguous()
 
 
-class Engine:
+class Engine(RaggedMixin):
     def __init__(self, model):
         self.model = model
         self.precision = 'fp32'

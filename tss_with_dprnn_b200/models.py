@@ -183,6 +183,11 @@ class DPRNNTasNet(_TasNetBase):
     def forward(self, input):
         return self._engine.forward_bss(input)
 
+    def forward_ragged(self, inputs):
+        """Batch of utterances of DIFFERENT lengths: list of [T_b] -> list of [2, T_b]; every result equals
+        ``forward(inputs[b][None])[0]`` (the reference's B = 1 test loop, src/inferencers/inferencer.py:54-71)."""
+        return self._engine.forward_bss_ragged(inputs)
+
 
 class DPRNNSpeTasNet(_TasNetBase):
     """Target-speaker separation with a ResNet speaker encoder; mirrors src/models/dprnn_spe.py:250-327."""
@@ -199,6 +204,12 @@ class DPRNNSpeTasNet(_TasNetBase):
     def forward(self, input, aux, aux_len):
         return self._engine.forward_spe(input, aux, aux_len)
 
+    def forward_ragged(self, inputs, auxs):
+        """Batch of utterances of DIFFERENT lengths: lists of [T_b] mixtures and [Tr_b] references ->
+        (list of [T_b] estimates, logits [B, num_spks]); utterance b gets ``forward(inputs[b][None], auxs[b][None],
+        tensor(float(Tr_b)))`` of eval() mode - the reference's B = 1 test loop (src/inferencers/inferencer_spe.py:25-45)."""
+        return self._engine.forward_spe_ragged(inputs, auxs)
+
     def forward_with_embedding(self, input, embedding):
         """Masker + decoder with an externally supplied speaker embedding [B,E] (what DPRNNRawNet does
         with RawNet3's output, dprnn_rawnet.py:72-105)."""
@@ -211,3 +222,6 @@ class DPRNNSpeIRATasNet(DPRNNSpeTasNet):
 
     def forward(self, input, aux, aux_len):
         return self._engine.forward_ira(input, aux, aux_len)
+
+    def forward_ragged(self, inputs, auxs):
+        return self._engine.forward_ira_ragged(inputs, auxs)

@@ -1,0 +1,365 @@
+"""Ragged (variable-length) batches over the C ABI: full-length utterances of different durations packed back to
+back (cfg 3).  The result for every utterance equals what the reference's B = 1 test loop
+gives for it (src/inferencers/inferencer_spe.py:25-45, inferencer.py:54-71): no padding enters a norm statistic,
+a recurrence, the attention softmax or the speaker time-mean.
+
+Layouts (see csrc/ragged.cu): the *frame space* gives utterance b the rows [frame_off[b], frame_off[b] + T_b) - the
+same indices as its samples in the packed waveform - of which the first L_b are frames; the *chunk space* gives it
+S_b chunks of K rows.  Row-wise stages (1x1 convolutions, the intra-chunk LSTM, the Linear, casts) run on the packed
+buffers with the uniform kernels; the per-utterance stages use the ``*_ragged`` entry points.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import lib
+
+EPI_NONE, EPI_RELU, EPI_SIGMOID, EPI_GATED = 0, 1, 2, 3
+
+
+class RaggedLayout:
+    """Index arrays of one packed batch (host lists + device tensors)."""
+
+    def __init__(self, lengths, cfg, device):
+        k, st = cfg['kernel_size'], cfg['stride']
+        if st != 1:
+            raise NotImplementedError('ragged batches need encoder stride 1 (every shipped config: kernel 2, stride 1)')
+        K, P = cfg['chunk_length'], cfg['hop_length']
+        self.B = len(lengths)
+        self.T = [int(t) for t in lengths]
+        if min(self.T) < k:
+            raise ValueError(f'an utterance is shorter than the encoder kernel ({k} samples)')
+        self.L = [t - (k - 1) for t in self.T]
+        self.S = [(l + K) // P + 1 for l in self.L]
+        self.La = [(l - k) // k + 1 for l in self.L]
+        self.K, self.k = K, k
+        self.total_rows = sum(self.T)
+        self.total_chunks = sum(self.S)
+        fo, co = [0], [0]
+        for t, s in zip(self.T, self.S):
+            fo.append(fo[-1] + t)
+            co.append(co[-1] + s)
+        self.frame_off_h, self.chunk_off_h = fo, co
+        i64 = dict(dtype=torch.int64, device=device)
+        self.frame_off = torch.tensor(fo[:-1], **i64)
+        self.chunk_off = torch.tensor(co[:-1], **i64)
+        self.row_off = torch.tensor([c * K for c in co], **i64)            # [B+1] chunk-space rows
+        self.L_d = torch.tensor(self.L, **i64)
+        self.S_d = torch.tensor(self.S, **i64)
+        self.La_d = torch.tensor(self.La, **i64)
+        ar = torch.arange(self.B, dtype=torch.int32)
+        self.frame_utt = torch.repeat_interleave(ar, torch.tensor(self.T)).to(device)
+        self.chunk_utt = torch.repeat_interleave(ar, torch.tensor(self.S)).to(device)
+        order = sorted(range(self.B), key=lambda b: -self.S[b])            # longest first (LPT)
+        self.jobs = torch.tensor([[co[b], self.S[b]] for b in order], dtype=torch.int32, device=device)
+        self.device = device
+        self._pool = None
+
+    def pool_stages(self):
+        """Packed layouts of the three MaxPool1d(3) stages of the speaker ResNet (dprnn_spe.py:39-42)."""
+        if self._pool is None:
+            stages = []
+            in_off, in_len = self.frame_off_h[:-1], self.L
+            i64 = dict(dtype=torch.int64, device=self.device)
+            for _ in range(3):
+                out_len = [n // 3 for n in in_len]
+                if min(out_len) < 1:
+                    raise ValueError('an utterance is too short for the speaker encoder (needs >= 27 frames)')
+                out_off = [0]
+                for n in out_len:
+                    out_off.append(out_off[-1] + n)
+                utt = torch.repeat_interleave(torch.arange(self.B, dtype=torch.int32), torch.tensor(out_len))
+                stages.append(dict(in_off=torch.tensor(in_off, **i64), out_off=torch.tensor(out_off[:-1], **i64),
+                                   out_len=torch.tensor(out_len, **i64), out_utt=utt.to(self.device),
+                                   total_out=out_off[-1]))
+                in_off, in_len = out_off[:-1], out_len
+            self._pool = stages
+        return self._pool
+
+
+class RaggedMixin:
+    """Ragged counterparts of Engine.encode / speaker_embedding / masker / decode and the whole-model forwards."""
+
+    # ------------------------------------------------------------------ packing
+    def _pack_waves(self, waves, name):
+        if isinstance(waves, torch.Tensor) and waves.dim() == 2:
+            waves = list(waves)
+        ws = []
+        for w in waves:
+            w = self._check_input(w, name)
+            if w.dim() == 2 and w.shape[0] == 1:
+                w = w[0]
+            if w.dim() != 1:
+                raise ValueError(f'{name}: ragged batches take a list of 1-D waveforms')
+            ws.append(w)
+        lay = RaggedLayout([w.numel() for w in ws], self.model.cfg, ws[0].device)
+        return torch.cat(ws), lay
+
+    def encode_ragged(self, flat, lay):
+        cfg, W = self.model.cfg, self.packed()
+        N, k = cfg['input_size'], cfg['kernel_size']
+        enc = torch.empty((lay.total_rows, N), device=flat.device, dtype=torch.float32)
+        if k > 1:
+            enc[lay.total_rows - (k - 1):].zero_()       # rows past the last frame of the packed waveform
+        lib().call('dprnn_encoder_fwd', flat, W['enc'], enc, 1, lay.total_rows, N, k, 1, self._stream())
+        return enc
+
+    def _stats_ragged(self, x, C, off, length, B, eps):
+        L_ = lib()
+        ws = torch.empty(L_.query('dprnn_utt_stats_ragged_workspace_bytes', B), device=x.device, dtype=torch.uint8)
+        mr = torch.empty((B, 2), device=x.device, dtype=torch.float32)
+        L_.call('dprnn_utt_stats_ragged', x, C, off, length, B, float(eps), ws, mr, self._stream())
+        return mr
+
+    def _gemm_ragged(self, A, Wt, M, N, K, row_utt, bias=None, bias_per_utt=False, p_scale=None, p_shift=None,
+                     p_add=None, rowscale=None, epi=EPI_NONE):
+        out = torch.empty((M, N), device=A.device, dtype=torch.float32)
+        lib().call('dprnn_gemm_f32_ragged', A, K, Wt, N, out, N, M, N, K, bias, int(bias_per_utt), 1.0, row_utt,
+                   p_scale, p_shift, p_add, rowscale, epi, self._stream())
+        return out
+
+    # ------------------------------------------------------------------ speaker branch
+    def _aux_div_ragged(self, ref_lengths, device):
+        """aux_T of DPRNNSpe._auxiliary (dprnn_spe.py:159-160) per utterance, from its own reference length."""
+        k = self.model.cfg['kernel_size']
+        al = torch.tensor([float(t) for t in ref_lengths])
+        t = (al - k) // (k // 2) + 1
+        t = ((t // 3) // 3) // 3
+        return t.float().to(device).contiguous()
+
+    def speaker_embedding_ragged(self, feats, lay, div):
+        """spk_encoder + time mean (dprnn_spe.py:115-122,156-163) on a frame-space tensor [total_rows, N] -> [B,E].
+        BatchNorm uses its running statistics: a packed batch reproduces per-utterance eval()-mode results."""
+        if self.model.training:
+            raise NotImplementedError('ragged batches reproduce eval()-mode results (train-mode BatchNorm statistics '
+                                      'would couple the utterances of a batch); call model.eval() first')
+        L_, W, st = lib(), self.packed(), self._stream()
+        se = self.model.separation.spk_encoder
+        N = self.model.cfg['input_size']
+        B, dev = lay.B, feats.device
+        mr = self._stats_ragged(feats, N, lay.frame_off, lay.L_d, B, se[0].eps)
+        s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
+        L_.call('dprnn_norm_affine', mr, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
+        O = se[1].weight.shape[0]
+        x = self._gemm_ragged(feats, W['spk_conv0_t'], lay.total_rows, O, N, lay.frame_utt, bias=se[1].bias.detach(),
+                              p_scale=s1, p_shift=s0)
+        rows = lay.total_rows
+        for rb, wr, stage in zip((se[2], se[3], se[4]), W['spk_res'], lay.pool_stages()):
+            Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
+            scale = torch.empty(Cout, device=dev); shift = torch.empty(Cout, device=dev)
+
+            def bn(bnm):
+                L_.call('dprnn_batchnorm_affine', None, rows, Cout, bnm.weight.detach(), bnm.bias.detach(),
+                        bnm.running_mean, bnm.running_var, 0, float(bnm.eps), 0.1, None, scale, shift, st)
+
+            tc = self.precision == 'bf16' and Cin in (128, 256) and Cout in (128, 256)
+
+            def conv(inp, conv_mod, wt, cin, cout):
+                if tc:
+                    return self.gemm_tc(inp, conv_mod.weight.detach(), rows, cout, cin)
+                return self.gemm(inp, wt, rows, cout, cin)
+
+            y = conv(x, rb.conv1, wr['c1'], Cin, Cout)
+            bn(rb.batch_norm1)
+            L_.call('dprnn_affine_prelu', y, scale, shift, rb.prelu1.weight.detach(), y, rows, Cout, st)
+            y2 = conv(y, rb.conv2, wr['c2'], Cout, Cout)
+            bn(rb.batch_norm2)
+            skip = x if wr['down'] is None else conv(x, rb.conv_downsample, wr['down'], Cin, Cout)
+            out = torch.empty((stage['total_out'], Cout), device=dev)
+            L_.call('dprnn_affine_add_prelu_pool3_ragged', y2, scale, shift, skip, rb.prelu2.weight.detach(), out,
+                    stage['out_utt'], stage['in_off'], stage['out_off'], stage['total_out'], Cout, st)
+            x, rows = out, stage['total_out']
+        E = se[5].weight.shape[0]
+        z = self.gemm(x, W['spk_conv5_t'], rows, E, se[5].weight.shape[1], bias=se[5].bias.detach())
+        last = lay.pool_stages()[-1]
+        emb = torch.empty((B, E), device=dev)
+        L_.call('dprnn_time_sum_ragged', z, emb, last['out_off'], last['out_len'], B, E, div, st)
+        return emb
+
+    # ------------------------------------------------------------------ masker
+    def masker_ragged(self, enc, mr, lay, emb, speakers):
+        """Engine.masker on a packed batch: enc [total_rows, N] (frame space) -> one mask [total_rows, N] per speaker."""
+        L_, W, st = lib(), self.packed(), self._stream()
+        cfg, sep = self.model.cfg, self.model.separation
+        N, F, H = cfg['input_size'], cfg['feature_size'], cfg['hidden_size']
+        K, P = cfg['chunk_length'], cfg['hop_length']
+        if K != 2 * P:
+            raise NotImplementedError('hop_length must be chunk_length/2 (every shipped config)')
+        B, dev, TR = lay.B, enc.device, lay.total_rows
+        gamma, beta, _ = self._norm_params(sep.bottleneck[0])
+        ft = cfg['fusion_type']
+        mulc = addc = rowscale = None
+        bias, bias_per_utt = sep.bottleneck[1].bias.detach(), False
+        if ft == 'cat':
+            bias = self.small_linear(emb, sep.bottleneck[1], B, w_off=N)
+            bias_per_utt = True
+        elif ft == 'add':
+            addc = self.small_linear(emb, sep.fusion_linear, B)
+        elif ft == 'mul':
+            mulc = self.small_linear(emb, sep.fusion_linear, B)
+        elif ft == 'film':
+            mulc = self.small_linear(emb, sep.fusion_linear_1, B)
+            addc = self.small_linear(emb, sep.fusion_linear_2, B)
+        elif ft == 'att':
+            mulc = self.small_linear(emb, sep.fusion_linear, B)
+        s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
+        if ft == 'att':
+            n1 = torch.empty_like(s1); n0 = torch.empty_like(s1)
+            L_.call('dprnn_norm_affine', mr, gamma, beta, None, n1, n0, B, N, st)
+            scores = torch.zeros(TR, device=dev)
+            rowscale = torch.empty(TR, device=dev)
+            L_.call('dprnn_att_rowscale_ragged', enc, n1, n0, sep.average.weight.detach(), sep.average.bias.detach(),
+                    mulc, scores, rowscale, lay.frame_utt, lay.frame_off, lay.L_d, lay.La_d, B, TR, N,
+                    cfg['kernel_size'], st)
+        L_.call('dprnn_norm_affine', mr, gamma, beta, mulc, s1, s0, B, N, st)
+        y = self._gemm_ragged(enc, W['bott_wt'], TR, F, N, lay.frame_utt, bias=bias, bias_per_utt=bias_per_utt,
+                              p_scale=s1, p_shift=s0, p_add=addc, rowscale=rowscale)
+        TC = lay.total_chunks
+        rows = TC * K
+        x = torch.empty((rows, F), device=dev)
+        L_.call('dprnn_unfold_ragged', y, x, lay.chunk_utt, lay.chunk_off, lay.frame_off, lay.L_d, TC, K, P, F, st)
+        del y
+        bf16 = self.precision == 'bf16'
+        if bf16:
+            if H != 128 or F != 128:
+                raise NotImplementedError('the tensor-core LSTM kernel is built for feature_size = hidden_size = 128')
+            xb = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+            L_.call('dprnn_cast_bf16', x, xb, rows * F, st)
+        for blk, halves in zip(sep.dprnn_blocks, W['blocks']):
+            for which, hw in enumerate(halves):
+                nd = hw['ndir']
+                nm = blk.intra_norm if which == 0 else blk.inter_norm
+                g_, b_, eps = self._norm_params(nm)
+                mr2 = torch.empty((B, 2), device=dev)
+                if bf16:
+                    hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
+                    if which == 0:      # every chunk is one length-K sequence: the packed chunk space is a uniform batch
+                        L_.call('dprnn_lstm_layer_bf16', xb, hw['tc_w'], hw['tc_bias'], hb, 1, TC, K, 0, H, nd,
+                                int(self.fast_act), st)
+                    else:               # one pair-job per utterance and direction, S_b steps each
+                        L_.call('dprnn_lstm_inter_bf16_ragged', xb, hw['tc_w'], hw['tc_bias'], hb, TC, K, lay.jobs, B,
+                                H, nd, int(self.fast_act), st)
+                    ybuf = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+                    part = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', rows), device=dev, dtype=torch.uint8)
+                    self._linear_stats_ragged(hb, hw, ybuf, rows, nd * H, part, lay, eps, mr2)
+                    L_.call('dprnn_norm_residual_ragged', ybuf, 1, x, mr2, g_, b_, lay.chunk_utt, TC, K, F, xb, st)
+                    del hb, ybuf
+                    continue
+                gx = self.gemm(x, hw['wih_t'], rows, nd * 4 * H, F, bias=hw['bias'])
+                hout = torch.empty((rows, nd * H), device=dev)
+                if which == 0:
+                    L_.call('dprnn_lstm_recurrence_f32', gx, hw['whh_t'], hout, TC, K, 1, K, 0, 1, H, nd, st)
+                else:                   # exact-fp32 mode: one launch per utterance (parity mode, not the fast path)
+                    for b in range(B):
+                        r0, Sb = lay.chunk_off_h[b] * K, lay.S[b]
+                        L_.call('dprnn_lstm_recurrence_f32', gx[r0:], hw['whh_t'], hout[r0:], K, Sb, K, Sb * K, 1, K, H,
+                                nd, st)
+                del gx
+                yl = self.gemm(hout, hw['lin_t'], rows, F, nd * H, bias=hw['lin_b'])
+                del hout
+                mr2 = self._stats_ragged(yl, F, lay.row_off[:-1], lay.S_d * K, B, eps)
+                L_.call('dprnn_norm_residual_ragged', yl, 0, x, mr2, g_, b_, lay.chunk_utt, TC, K, F, None, st)
+                del yl
+        z = torch.empty((TR, F), device=dev)
+        L_.call('dprnn_fold_prelu_ragged', x, z, lay.frame_utt, lay.frame_off, lay.L_d, lay.chunk_off, lay.S_d, TR, K, P,
+                F, sep.prelu.weight.detach(), st)
+        del x
+        act = EPI_SIGMOID if cfg['activation_type'] == 'sigmoid' else EPI_RELU
+        masks = []
+        for spk in speakers:
+            if bf16 and F == 128 and N == 64:
+                u = self.gemm_tc(z, W['conv2d_w'][spk], TR, F, F, bias=W['conv2d_b2'][spk])
+                g = self.gemm_tc(u, W['og_w'], TR, 2 * F, F, bias=W['og_bias'], epi=EPI_GATED)
+                masks.append(self.gemm_tc(g, W['end_w'], TR, N, F, epi=act))
+                continue
+            u = self.gemm(z, W['conv2d_t'][spk], TR, F, F, bias=W['conv2d_b'][spk], bias_scale=2.0)
+            g = self.gemm(u, W['og_t'], TR, 2 * F, F, bias=W['og_b'], epi=EPI_GATED)
+            masks.append(self.gemm(g, W['end_t'], TR, N, F, epi=act))
+        return masks
+
+    def _linear_stats_ragged(self, hb, hw, ybuf, rows, Kdim, part, lay, eps, mr2):
+        """Tensor-core Linear with bf16 output and per-row sums, then the per-utterance reduction."""
+        L_, st = lib(), self._stream()
+        # rows_per_utt = rows, mean_rstd scratch: the kernel's own finalize treats the batch as one utterance; the
+        # per-utterance statistics come from the ragged finalize over the same per-row sums
+        scratch = torch.empty((1, 2), device=hb.device)
+        L_.call('dprnn_linear_bf16out_stats', hb, hw['lin_bf16'], hw['lin_b'], ybuf, rows, Kdim, part, rows, float(eps),
+                scratch, st)
+        L_.call('dprnn_row_stats_finalize_ragged', part, lay.row_off, lay.B, hw['lin_bf16'].shape[0], float(eps), mr2, st)
+
+    def decode_ragged(self, mask, enc, lay):
+        cfg, W = self.model.cfg, self.packed()
+        out = torch.empty(lay.total_rows, device=enc.device)
+        lib().call('dprnn_mask_decode_ragged', mask, enc, W['dec'], out, lay.frame_utt, lay.frame_off, lay.L_d,
+                   lay.total_rows, cfg['input_size'], cfg['kernel_size'], self._stream())
+        return out
+
+    @staticmethod
+    def _split(flat, lay):
+        return [flat[lay.frame_off_h[b]:lay.frame_off_h[b + 1]] for b in range(lay.B)]
+
+    # ------------------------------------------------------------------ whole-model forwards
+    def forward_bss_ragged(self, mixes):
+        """list of [T_b] mixtures -> list of [2, T_b] estimates (DPRNNTasNet.forward per utterance, dprnn.py:271-283)."""
+        with torch.no_grad():
+            flat, lay = self._pack_waves(mixes, 'input')
+            enc = self.encode_ragged(flat, lay)
+            N = self.model.cfg['input_size']
+            _, _, eps = self._norm_params(self.model.separation.bottleneck[0])
+            mr = self._stats_ragged(enc, N, lay.frame_off, lay.L_d, lay.B, eps)
+            masks = self.masker_ragged(enc, mr, lay, None, (0, 1))
+            outs = [self._split(self.decode_ragged(m, enc, lay), lay) for m in masks]
+            return [torch.stack([outs[0][b], outs[1][b]]) for b in range(lay.B)]
+
+    def forward_spe_ragged(self, mixes, refs, embedding=None):
+        """lists of [T_b] mixtures and [Tr_b] references -> (list of [T_b] estimates, logits [B, num_spks]);
+        DPRNNSpeTasNet.forward per utterance with aux_len = Tr_b (dprnn_spe.py:314-327, inferencer_spe.py:31-32)."""
+        with torch.no_grad():
+            flat, lay = self._pack_waves(mixes, 'input')
+            sep, cfg = self.model.separation, self.model.cfg
+            N = cfg['input_size']
+            enc = self.encode_ragged(flat, lay)
+            if embedding is None:
+                rflat, rlay = self._pack_waves(refs, 'aux')
+                if rlay.B != lay.B:
+                    raise ValueError('need one reference per mixture')
+                feats = self.encode_ragged(rflat, rlay)
+                emb = self.speaker_embedding_ragged(feats, rlay, self._aux_div_ragged(rlay.T, flat.device))
+                del feats
+            else:
+                emb = self._check_input(embedding, 'embedding')
+            _, _, eps = self._norm_params(sep.bottleneck[0])
+            mr = self._stats_ragged(enc, N, lay.frame_off, lay.L_d, lay.B, eps)
+            mask = self.masker_ragged(enc, mr, lay, emb, (0,))[0]
+            est = self.decode_ragged(mask, enc, lay)
+            logits = self.small_linear(emb, sep.pred_linear, lay.B)
+            return self._split(est, lay), logits
+
+    def forward_ira_ragged(self, mixes, refs):
+        """DPRNNSpeIRATasNet.forward per utterance (dprnn_spe_ira.py:53-115,179-190) on a packed batch."""
+        with torch.no_grad():
+            flat, lay = self._pack_waves(mixes, 'input')
+            rflat, rlay = self._pack_waves(refs, 'aux')
+            if rlay.B != lay.B:
+                raise ValueError('need one reference per mixture')
+            sep, cfg = self.model.separation, self.model.cfg
+            N, B = cfg['input_size'], lay.B
+            enc = self.encode_ragged(flat, lay)
+            feats = self.encode_ragged(rflat, rlay)
+            div = self._aux_div_ragged(rlay.T, flat.device)
+            v0 = self.speaker_embedding_ragged(feats, rlay, div)
+            del feats
+            _, _, eps = self._norm_params(sep.bottleneck[0])
+            mr = self._stats_ragged(enc, N, lay.frame_off, lay.L_d, B, eps)
+            mask = self.masker_ragged(enc, mr, lay, v0, (0,))[0]
+            d0 = torch.empty_like(enc)
+            lib().call('dprnn_mask_apply', mask, enc, d0, enc.numel(), self._stream())
+            v1 = self.speaker_embedding_ragged(d0, lay, div)       # still divided by the reference's length (:84)
+            del d0
+            E = cfg['embeddings_size']
+            v = self.small_linear(v0, sep.aux_linear, B, K=E)
+            self.small_linear(v1, sep.aux_linear, B, out=v, accumulate=True, w_off=E, bias=False)
+            mask = self.masker_ragged(enc, mr, lay, v, (0,))[0]
+            est = self.decode_ragged(mask, enc, lay)
+            logits = self.small_linear(v, sep.pred_linear, B)
+            return self._split(est, lay), logits
