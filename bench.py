@@ -88,63 +88,55 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-# reference arm / CPU baseline: the reference's own classes (baseline/_ref, installed unmodified) when present,
-# else the oracle port (torch CPU restatement calling the same ATen LSTM the reference calls)
+# workloads
 # ----------------------------------------------------------------------------------------------------------
-def cpu_forward_fn():
-    ref_root = os.path.join(ROOT, 'baseline', '_ref')
-    torch.manual_seed(0)
-    if os.path.isdir(os.path.join(ref_root, 'src', 'models')):
-        sys.path.insert(0, ref_root)
-        from src.models.dprnn_spe import DPRNNSpeTasNet as RefModel
-        model = RefModel(**KW).eval()
-        return 'reference', (lambda mix, ref, rl: model(mix, ref, rl)[0])
-    from oracle import dprnn_oracle as O
-    import tss_with_dprnn_b200 as P
-    sd = P.DPRNNSpeTasNet(**KW).state_dict()
-    cfg = O.Config(fusion_type='cat')
-    return 'port', (lambda mix, ref, rl: O.spe_forward(mix, ref, rl, sd, cfg)[0])
+def load_test_set_lengths():
+    """(mixture, reference) sample counts of the reference's 3 000 full-length test utterances
+    (tests/golden/test_set_lengths.txt, extracted from datasets/tss/test_set.pkl)."""
+    rows = []
+    with open(os.path.join(ROOT, 'tests', 'golden', 'test_set_lengths.txt')) as f:
+        for ln in f:
+            if ln.strip() and not ln.startswith('#'):
+                a, b = ln.split()
+                rows.append((int(a), int(b)))
+    return rows
 
 
-def time_cpu(batch, T, steps, warmup):
-    kind, fwd = cpu_forward_fn()
-    cores = os.cpu_count()
-    torch.set_num_threads(cores)
-    mix, ref = synth(batch, T, 0)
-    rl = torch.tensor(float(T))
-    times = []
-    with torch.no_grad():
-        for i in range(warmup + steps):
-            t0 = time.perf_counter()
-            fwd(mix, ref, rl)
-            dt = time.perf_counter() - t0
-            if i >= warmup:
-                times.append(dt)
-    return kind, cores, times
+def cfg3_buckets(world, bucket=64, K=250, P=125):
+    """Length-sorted buckets of `bucket` utterances, assigned to ranks by the LPT rule on their chunk count
+    (SURVEY.md section 8d cfg 3).  Returns per rank a list of buckets, each a list of (T, Tr)."""
+    rows = sorted(load_test_set_lengths())
+    buckets = [rows[i:i + bucket] for i in range(0, len(rows), bucket)]
+    cost = lambda bk: sum((t - 1 + K) // P + 1 for t, _ in bk)
+    load, per_rank = [0] * world, [[] for _ in range(world)]
+    for bk in sorted(buckets, key=cost, reverse=True):
+        r = load.index(min(load))
+        per_rank[r].append(bk)
+        load[r] += cost(bk)
+    return per_rank
 
 
-def run_reference(args):
-    rank = int(os.environ.get('RANK', 0))
-    if rank != 0:
-        return
-    batch = args.cpu_batch
-    kind, cores, times = time_cpu(batch, args.samples, args.steps, args.warmup)
-    total = sum(times)
-    value = batch * args.samples / SR * len(times) / total
-    sample = f'{batch} x {args.samples / SR:g}-s utterance(s) per step (bounded sample of the batch-{args.batch} workload)'
-    line = {
-        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'audio-s/s', 'n_gpus': args.gpus,
-        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args),
-        'cpu_baseline': {'value': value, 'unit': 'audio-s/s', 'cores': cores, 'kind': kind, 'sample': sample},
-        'e2e': {'value': value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
-        'gpu_launches': 0,
-    }
-    print(json.dumps(line))
+def pick_steps(buckets, n):
+    """n buckets spread evenly over a rank's share of the length distribution (a bounded, representative sample)."""
+    if n >= len(buckets):
+        return list(buckets)
+    return [buckets[int(round(i * (len(buckets) - 1) / max(1, n - 1)))] for i in range(n)]
+
+
+def model_for(workload):
+    if workload == 'cfg3':
+        return 'DPRNNSpeIRATasNet', KW
+    return 'DPRNNSpeTasNet', KW
 
 
 def workload_config(args):
+    if args.workload == 'cfg3':
+        return {'workload': 'cfg3: DPRNN-Spe-IRA (cat) TSS inference on the full-length test-set length distribution '
+                            f'(24000..111920 samples), length-sorted buckets of {args.batch} utterances packed as ragged '
+                            'batches, buckets LPT-assigned to ranks; one step = one bucket',
+                'batch_per_gpu': args.batch, 'precision': args.precision, 'streams': 1,
+                'l2': 'no flush needed: each step streams >10 GB of intermediates through a 126 MB L2',
+                'parallelism': f'utterance sharding x{args.gpus}, no collective'}
     return {'workload': f'cfg2: DPRNN-Spe (cat) TSS inference, {args.samples / SR:g}-s mix + reference @ 8 kHz, '
                         f'batch {args.batch} per GPU, full depth (6 blocks)',
             'batch_per_gpu': args.batch, 'samples': args.samples, 'precision': args.precision,
@@ -154,6 +146,152 @@ def workload_config(args):
 
 
 # ----------------------------------------------------------------------------------------------------------
+# reference arm / CPU baseline: the reference's own classes (baseline/_ref, installed unmodified) when present,
+# else the oracle port (torch CPU restatement calling the same ATen LSTM the reference calls)
+# ----------------------------------------------------------------------------------------------------------
+def cpu_forward_fn(workload):
+    ref_root = os.path.join(ROOT, 'baseline', '_ref')
+    torch.manual_seed(0)
+    cls, kw = model_for(workload)
+    if os.path.isdir(os.path.join(ref_root, 'src', 'models')):
+        sys.path.insert(0, ref_root)
+        if cls == 'DPRNNSpeIRATasNet':
+            from src.models.dprnn_spe_ira import DPRNNSpeIRATasNet as RefModel
+        else:
+            from src.models.dprnn_spe import DPRNNSpeTasNet as RefModel
+        model = RefModel(**kw).eval()
+        return 'reference', (lambda mix, ref, rl: model(mix, ref, rl)[0])
+    from oracle import dprnn_oracle as O
+    import tss_with_dprnn_b200 as P
+    sd = getattr(P, cls)(**kw).state_dict()
+    cfg = O.Config(fusion_type='cat')
+    fwd = O.ira_forward if cls == 'DPRNNSpeIRATasNet' else O.spe_forward
+    return 'port', (lambda mix, ref, rl: fwd(mix, ref, rl, sd, cfg)[0])
+
+
+def cpu_sample(args):
+    """(batch, T, Tr, description) of the bounded CPU sample of the workload."""
+    if args.workload == 'cfg3':
+        rows = sorted(load_test_set_lengths())
+        t, tr = rows[len(rows) // 2]
+        return 1, t, tr, f'1 utterance of the median test-set length ({t} samples, reference {tr}) per forward'
+    return args.cpu_batch, args.samples, args.samples, \
+        f'{args.cpu_batch} x {args.samples / SR:g}-s utterance(s) per forward (bounded sample of the batch-{args.batch} workload)'
+
+
+def time_cpu(args, steps, warmup):
+    kind, fwd = cpu_forward_fn(args.workload)
+    cores = os.cpu_count()
+    torch.set_num_threads(cores)
+    batch, T, Tr, desc = cpu_sample(args)
+    g = torch.Generator().manual_seed(1234)
+    mix = 0.05 * torch.randn(batch, T, generator=g)
+    ref = 0.05 * torch.randn(batch, Tr, generator=g)
+    rl = torch.tensor(float(Tr))
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            fwd(mix, ref, rl)
+            dt = time.perf_counter() - t0
+            if i >= warmup:
+                times.append(dt)
+    return kind, cores, times, batch * T / SR, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return
+    kind, cores, times, audio, desc = time_cpu(args, args.steps, args.warmup)
+    total = sum(times)
+    value = audio * len(times) / total
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'audio-s/s', 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': workload_config(args),
+        'cpu_baseline': {'value': value, 'unit': 'audio-s/s', 'cores': cores, 'kind': kind, 'sample': desc},
+        'e2e': {'value': value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------------------
+class Cfg2:
+    """BASELINE.json configs[1]: equal-length 3-s batch through the reference-facing forward(mix, ref, ref_len)."""
+
+    def __init__(self, args, model, rank, dev):
+        B, T = args.batch, args.samples
+        self.model, self.B, self.T, self.dev = model, B, T, dev
+        mix_h, ref_h = synth(B, T, rank)
+        self.mix_h, self.ref_h = mix_h.pin_memory(), ref_h.pin_memory()
+        self.mix, self.ref = self.mix_h.to(dev), self.ref_h.to(dev)
+        self.rl = torch.tensor(float(T))
+        self.out_h = torch.empty((B, T), dtype=torch.float32).pin_memory()
+        self.n_steps = 1
+
+    def audio(self, i):
+        return self.B * self.T / SR
+
+    def positions(self, i):            # chunk positions (LSTM steps x sequences) of the step, per RNN layer
+        return self.B * POS_PER_UTT
+
+    def resident(self, i):
+        return self.model(self.mix, self.ref, self.rl)
+
+    def e2e(self, i):
+        m = self.mix_h.to(self.dev, non_blocking=True)
+        r = self.ref_h.to(self.dev, non_blocking=True)
+        est, _ = self.model(m, r, self.rl)
+        self.out_h.copy_(est, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # the caller has the separated audio on the host
+
+    def bytes(self, i):
+        return 2 * self.B * self.T * 4, self.B * self.T * 4
+
+
+class Cfg3:
+    """BASELINE.json configs[2]: full-length variable-duration utterances as ragged batches (model.forward_ragged)."""
+
+    def __init__(self, args, model, rank, world, dev, n_steps):
+        self.model, self.dev = model, dev
+        buckets = pick_steps(cfg3_buckets(world, args.batch)[rank], n_steps)
+        self.n_steps = len(buckets)
+        self.steps = []
+        g = torch.Generator().manual_seed(4321 + rank)
+        for bk in buckets:
+            Ts, Trs = [t for t, _ in bk], [tr for _, tr in bk]
+            mix_h = (0.05 * torch.randn(sum(Ts), generator=g)).pin_memory()
+            ref_h = (0.05 * torch.randn(sum(Trs), generator=g)).pin_memory()
+            self.steps.append(dict(Ts=Ts, Trs=Trs, mix_h=mix_h, ref_h=ref_h, mix=mix_h.to(dev), ref=ref_h.to(dev),
+                                   out_h=torch.empty(sum(Ts), dtype=torch.float32).pin_memory()))
+
+    def audio(self, i):
+        return sum(self.steps[i % self.n_steps]['Ts']) / SR
+
+    def positions(self, i):
+        return 2 * sum(250 * ((t - 1 + 250) // 125 + 1) for t in self.steps[i % self.n_steps]['Ts'])   # two masker passes
+
+    def resident(self, i):
+        s = self.steps[i % self.n_steps]
+        return self.model.forward_ragged((s['mix'], s['Ts']), (s['ref'], s['Trs']))
+
+    def e2e(self, i):
+        s = self.steps[i % self.n_steps]
+        m = s['mix_h'].to(self.dev, non_blocking=True)
+        r = s['ref_h'].to(self.dev, non_blocking=True)
+        est, _ = self.model.forward_ragged((m, s['Ts']), (r, s['Trs']))
+        flat = est[0]._base if est[0]._base is not None else torch.cat(est)     # estimates are views of one packed buffer
+        s['out_h'].copy_(flat, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def bytes(self, i):
+        s = self.steps[i % self.n_steps]
+        return (sum(s['Ts']) + sum(s['Trs'])) * 4, sum(s['Ts']) * 4
+
+
 def run_ours(args):
     import torch.distributed as dist
     import tss_with_dprnn_b200 as P
@@ -172,40 +310,25 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     torch.manual_seed(0)
-    model = P.DPRNNSpeTasNet(**KW).eval().to(dev)      # same seeded weights on every rank (replicated, 16 MB)
+    cls, kw = model_for(args.workload)
+    model = getattr(P, cls)(**kw).eval().to(dev)      # same seeded weights on every rank (replicated, 16 MB)
     model.precision = args.precision
     model.n_streams = args.streams
     if args.fused_tail is not None:
         model._engine.fused_tail = bool(args.fused_tail)
-    B, T = args.batch, args.samples
-    mix_h, ref_h = synth(B, T, rank)
-    mix_h, ref_h = mix_h.pin_memory(), ref_h.pin_memory()
-    mix, ref = mix_h.to(dev), ref_h.to(dev)
-    rl = torch.tensor(float(T))
     L = P.lib()
-
-    def step_resident():
-        return model(mix, ref, rl)
-
-    out_h = torch.empty((B, T), dtype=torch.float32).pin_memory()
-
-    def step_e2e():
-        m = mix_h.to(dev, non_blocking=True)
-        r = ref_h.to(dev, non_blocking=True)
-        est, _ = model(m, r, rl)
-        out_h.copy_(est, non_blocking=True)
-        torch.cuda.current_stream().synchronize()      # the caller has the separated audio on the host
+    wl = Cfg3(args, model, rank, world, dev, args.steps) if args.workload == 'cfg3' else Cfg2(args, model, rank, dev)
 
     def timed(fn, steps, warmup):
         with torch.no_grad():
-            for _ in range(warmup):
-                fn()
+            for i in range(warmup):
+                fn(i)
             barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             n0 = L.launches
             ev0.record()
-            for _ in range(steps):
-                fn()
+            for i in range(steps):
+                fn(i)
             ev1.record()
             barrier()
             ms = ev0.elapsed_time(ev1)
@@ -214,22 +337,34 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()), L.launches - n0
 
+    def total_over_ranks(v):
+        t = torch.tensor([v], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
     with ClockSampler(local) as clk:
-        ms_total, launches = timed(step_resident, args.steps, args.warmup)
+        # every distinct step is warmed up at least once (ragged layouts, tensor maps, allocator pools)
+        ms_total, launches = timed(wl.resident, args.steps, max(args.warmup, wl.n_steps))
     clocks = clk.summary()
-    ms_e2e, _ = timed(step_e2e, max(1, args.steps), 1)
+    ms_e2e, _ = timed(wl.e2e, args.steps, max(1, wl.n_steps))
 
-    audio_per_step = world * B * T / SR
-    value = audio_per_step * args.steps / (ms_total / 1e3)
-    e2e_value = audio_per_step * max(1, args.steps) / (ms_e2e / 1e3)
+    audio_steps = total_over_ranks(sum(wl.audio(i) for i in range(args.steps)))     # whole job, all ranks
+    value = audio_steps / (ms_total / 1e3)
+    e2e_value = audio_steps / (ms_e2e / 1e3)
+    h2d = sum(wl.bytes(i)[0] for i in range(args.steps)) / args.steps
+    d2h = sum(wl.bytes(i)[1] for i in range(args.steps)) / args.steps
 
-    # --- per-kernel pass (separate from the timed region): CUDA events around every launch of the dominant kernel
+    # --- per-kernel pass (separate from the timed region, one stream so that launches do not overlap): CUDA events
+    # around every launch of step 0
     dominant = 'dprnn_lstm_layer_bf16' if args.precision == 'bf16' else 'dprnn_lstm_recurrence_f32'
     names = list(L.protos.keys())
+    model.n_streams = 1
     L.timing = {n: [] for n in names}
     with torch.no_grad():
-        step_resident()
+        wl.resident(0)
     torch.cuda.synchronize()
+    model.n_streams = args.streams
     per_kernel = {}
     for n, evs in L.timing.items():
         if evs:
@@ -243,26 +378,31 @@ def run_ours(args):
         pass
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)     # kernel timed inside a long step -> sustained figure
     roofline = None
-    if dominant in per_kernel:
-        k = per_kernel[dominant]
-        # one launch = one RNN layer (both directions); the fused bf16 kernel also does the input projection
-        flop_per_launch = (RECUR_FLOP_PER_UTT + (PROJ_FLOP_PER_UTT if args.precision == 'bf16' else 0)) * B / 12
-        achieved = flop_per_launch / (k['ms_avg'] * 1e-3) / 1e12
-        roofline = {'kernel': dominant, 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf, 'unit': 'TFLOP/s',
-                    'frac': achieved / peak_tf, 'traffic': None,
+    lstm_names = [n for n in per_kernel if n in (dominant, 'dprnn_lstm_inter_bf16_ragged')]
+    if lstm_names:
+        ms_lstm = sum(per_kernel[n]['ms_total'] for n in lstm_names)
+        n_launch = sum(per_kernel[n]['launches'] for n in lstm_names)
+        # one launch = one RNN layer (both directions) over every chunk position of the step; the fused bf16 kernel
+        # also does the input projection: 2 * 2 * 128 * 512 flop per position and direction (else 2 * 128 * 512)
+        flop_per_pos = 2 * (2 if args.precision == 'bf16' else 1) * 2 * 128 * 512
+        flop_per_launch = flop_per_pos * wl.positions(0) / (2 if args.workload == 'cfg3' else 1)
+        achieved = flop_per_launch * n_launch / (ms_lstm * 1e-3) / 1e12
+        roofline = {'kernel': '+'.join(lstm_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
+                    'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None,
                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (B200_PROFILING.md)',
-                    'share_of_step': k['ms_total'] / (ms_total / args.steps),
-                    'note': ('algorithmic flops = [x_t|h_{t-1}] [W_ih|W_hh]^T, 2*256*512 per chunk position and direction'
+                    'launch_ms_avg': ms_lstm / n_launch,
+                    'share_of_step_single_stream': ms_lstm / sum(k['ms_total'] for k in per_kernel.values()),
+                    'note': ('algorithmic flops = [x_t|h_{t-1}] [W_ih|W_hh]^T, 2*256*512 per chunk position and direction; '
+                             'launches timed one by one on a single stream'
                              if args.precision == 'bf16' else
                              'algorithmic flops = h W_hh^T only (2*128*512 per position and direction); the fp32 mode '
                              'runs this on CUDA cores, so its fraction of the bf16 tensor peak is small by construction')}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        kind, cores, times = time_cpu(args.cpu_batch, T, 2, 1)
-        v = args.cpu_batch * T / SR * len(times) / sum(times)
-        cpu = {'value': v, 'unit': 'audio-s/s', 'cores': cores, 'kind': kind,
-               'sample': f'{args.cpu_batch} x {T / SR:g}-s utterance(s), 1 warm-up + 2 timed forwards, fp32, eval()'}
+        kind, cores, times, audio, desc = time_cpu(args, 2, 1)
+        cpu = {'value': audio * len(times) / sum(times), 'unit': 'audio-s/s', 'cores': cores, 'kind': kind,
+               'sample': desc + ', 1 warm-up + 2 timed forwards, fp32, eval()'}
 
     if rank == 0:
         line = {
@@ -270,8 +410,7 @@ def run_ours(args):
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'bf16 gate/linear contractions, f32 accumulate+state',
             'data': 'synthetic', 'config': workload_config(args), 'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 2 * B * T * 4,
-                    'd2h_bytes_per_step': B * T * 4},
+            'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'kernels': per_kernel,
             'build': L.build_info(),
         }
@@ -286,11 +425,13 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3'],
+                    help='cfg2 (headline): DPRNN-Spe cat, 3-s batch 64; cfg3: DPRNN-Spe-IRA on the ragged test-set lengths')
     ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
-    ap.add_argument('--streams', type=int, default=int(os.environ.get('DPRNN_STREAMS', '1')),
-                    help='concurrent CUDA streams the batch is split over inside one forward')
+    ap.add_argument('--streams', type=int, default=int(os.environ.get('DPRNN_STREAMS', '3')),
+                    help='concurrent CUDA streams the batch is split over inside one forward (cfg2)')
     ap.add_argument('--fused-tail', type=int, default=None, help='1: Linear+norm+residual as one persistent kernel')
-    ap.add_argument('--batch', type=int, default=64, help='utterances per GPU (cfg 2: 64)')
+    ap.add_argument('--batch', type=int, default=64, help='utterances per GPU and step (cfg 2: 64; cfg 3: bucket size)')
     ap.add_argument('--samples', type=int, default=24000, help='samples per utterance (3 s @ 8 kHz)')
     ap.add_argument('--cpu-batch', type=int, default=1, help='utterances per CPU-baseline forward')
     ap.add_argument('--no-cpu-baseline', action='store_true')

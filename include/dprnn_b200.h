@@ -154,7 +154,9 @@ int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias
 int dprnn_linear_bf16_stats(const void* A, const void* W, const float* bias, float* C, int M, int K,
                             void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream);
 
-/* Same kernel with the output rounded to bf16 (C_bf16 [M,128] bf16); the statistics are taken from the fp32 values. */
+/* Same kernel with the output rounded to bf16 (C_bf16 [M,128] bf16); the statistics are taken from the fp32 values.
+ * For both: mean_rstd == NULL with stats_partial != NULL leaves the per-row {sum, sumsq} for the caller to reduce
+ * (dprnn_row_stats_finalize_ragged). */
 int dprnn_linear_bf16out_stats(const void* A, const void* W, const float* bias, void* C_bf16, int M, int K,
                                void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream);
 

@@ -225,13 +225,13 @@ static int linear_stats_impl(const void* A, const void* W, const float* bias, vo
                              void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream) {
     DPRNN_CHECK_ARG(A && W && bias && C && M > 0 && (K == 128 || K == 256));
     DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) % 16 == 0);
-    if (stats_partial) DPRNN_CHECK_ARG(rows_per_utt > 0 && M % rows_per_utt == 0 && mean_rstd);
+    if (stats_partial && mean_rstd) DPRNN_CHECK_ARG(rows_per_utt > 0 && M % rows_per_utt == 0);
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
     if (bf16_out) rc = K == 256 ? launch_lp<4, true>(A, W, bias, C, M, stats_partial, st) : launch_lp<2, true>(A, W, bias, C, M, stats_partial, st);
     else rc = K == 256 ? launch_lp<4, false>(A, W, bias, C, M, stats_partial, st) : launch_lp<2, false>(A, W, bias, C, M, stats_partial, st);
     if (rc) return rc;
-    if (stats_partial) {
+    if (stats_partial && mean_rstd) {     // mean_rstd == NULL: the caller reduces the per-row sums itself (ragged batches)
         return launch_row_stats_finalize(stats_partial, mean_rstd, M / rows_per_utt, rows_per_utt, LP_N, (double)eps, st);
     }
     return 0;

@@ -47,9 +47,9 @@ class RaggedLayout:
         self.L_d = torch.tensor(self.L, **i64)
         self.S_d = torch.tensor(self.S, **i64)
         self.La_d = torch.tensor(self.La, **i64)
-        ar = torch.arange(self.B, dtype=torch.int32)
-        self.frame_utt = torch.repeat_interleave(ar, torch.tensor(self.T)).to(device)
-        self.chunk_utt = torch.repeat_interleave(ar, torch.tensor(self.S)).to(device)
+        ar = torch.arange(self.B, dtype=torch.int32, device=device)
+        self.frame_utt = torch.repeat_interleave(ar, torch.tensor(self.T, device=device), output_size=self.total_rows)
+        self.chunk_utt = torch.repeat_interleave(ar, self.S_d, output_size=self.total_chunks)
         order = sorted(range(self.B), key=lambda b: -self.S[b])            # longest first (LPT)
         self.jobs = torch.tensor([[co[b], self.S[b]] for b in order], dtype=torch.int32, device=device)
         self.device = device
@@ -68,10 +68,11 @@ class RaggedLayout:
                 out_off = [0]
                 for n in out_len:
                     out_off.append(out_off[-1] + n)
-                utt = torch.repeat_interleave(torch.arange(self.B, dtype=torch.int32), torch.tensor(out_len))
+                out_len_d = torch.tensor(out_len, **i64)
+                utt = torch.repeat_interleave(torch.arange(self.B, dtype=torch.int32, device=self.device), out_len_d,
+                                              output_size=out_off[-1])
                 stages.append(dict(in_off=torch.tensor(in_off, **i64), out_off=torch.tensor(out_off[:-1], **i64),
-                                   out_len=torch.tensor(out_len, **i64), out_utt=utt.to(self.device),
-                                   total_out=out_off[-1]))
+                                   out_len=out_len_d, out_utt=utt, total_out=out_off[-1]))
                 in_off, in_len = out_off[:-1], out_len
             self._pool = stages
         return self._pool
@@ -82,6 +83,13 @@ class RaggedMixin:
 
     # ------------------------------------------------------------------ packing
     def _pack_waves(self, waves, name):
+        """list of 1-D waveforms, or an already packed (flat [sum T_b], lengths) pair -> (flat, RaggedLayout)."""
+        if isinstance(waves, tuple) and len(waves) == 2 and isinstance(waves[0], torch.Tensor) and waves[0].dim() == 1 \
+                and not isinstance(waves[1], torch.Tensor):
+            flat, lengths = self._check_input(waves[0], name), [int(t) for t in waves[1]]
+            if sum(lengths) != flat.numel():
+                raise ValueError(f'{name}: the lengths do not add up to the packed waveform')
+            return flat, self._layout(lengths, flat.device)
         if isinstance(waves, torch.Tensor) and waves.dim() == 2:
             waves = list(waves)
         ws = []
@@ -92,8 +100,19 @@ class RaggedMixin:
             if w.dim() != 1:
                 raise ValueError(f'{name}: ragged batches take a list of 1-D waveforms')
             ws.append(w)
-        lay = RaggedLayout([w.numel() for w in ws], self.model.cfg, ws[0].device)
-        return torch.cat(ws), lay
+        return torch.cat(ws), self._layout([w.numel() for w in ws], ws[0].device)
+
+    def _layout(self, lengths, device):
+        """RaggedLayout of a batch, cached for the most recent length patterns (index arrays are pure functions of them)."""
+        cache = self.__dict__.setdefault('_layouts', {})
+        key = (tuple(lengths), str(device))
+        lay = cache.pop(key, None)
+        if lay is None:
+            lay = RaggedLayout(lengths, self.model.cfg, device)
+        cache[key] = lay                     # most recently used last
+        while len(cache) > 64:
+            cache.pop(next(iter(cache)))
+        return lay
 
     def encode_ragged(self, flat, lay):
         cfg, W = self.model.cfg, self.packed()
@@ -280,11 +299,8 @@ class RaggedMixin:
     def _linear_stats_ragged(self, hb, hw, ybuf, rows, Kdim, part, lay, eps, mr2):
         """Tensor-core Linear with bf16 output and per-row sums, then the per-utterance reduction."""
         L_, st = lib(), self._stream()
-        # rows_per_utt = rows, mean_rstd scratch: the kernel's own finalize treats the batch as one utterance; the
-        # per-utterance statistics come from the ragged finalize over the same per-row sums
-        scratch = torch.empty((1, 2), device=hb.device)
-        L_.call('dprnn_linear_bf16out_stats', hb, hw['lin_bf16'], hw['lin_b'], ybuf, rows, Kdim, part, rows, float(eps),
-                scratch, st)
+        L_.call('dprnn_linear_bf16out_stats', hb, hw['lin_bf16'], hw['lin_b'], ybuf, rows, Kdim, part, 0, float(eps),
+                None, st)          # mean_rstd = NULL: per-row sums only
         L_.call('dprnn_row_stats_finalize_ragged', part, lay.row_off, lay.B, hw['lin_bf16'].shape[0], float(eps), mr2, st)
 
     def decode_ragged(self, mask, enc, lay):
