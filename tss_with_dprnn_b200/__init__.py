@@ -4,7 +4,7 @@ Drop-in for the model classes of Aleksashka-i/tss-with-dprnn (``src/models``): s
 ``state_dict`` layout and ``forward`` signatures, with every stage of the forward executed by the
 hand-written CUDA kernels of ``csrc/`` through the C ABI declared in ``include/dprnn_b200.h``.
 """
-from .models import DPRNNTasNet, DPRNNSpeTasNet, DPRNNSpeIRATasNet  # noqa: F401
+from .models import DPRNNTasNet, DPRNNSpeTasNet, DPRNNSpeIRATasNet, DPRNNRawNetTasNet  # noqa: F401
 from ._lib import lib  # noqa: F401
 
-__all__ = ['DPRNNTasNet', 'DPRNNSpeTasNet', 'DPRNNSpeIRATasNet', 'lib']
+__all__ = ['DPRNNTasNet', 'DPRNNSpeTasNet', 'DPRNNSpeIRATasNet', 'DPRNNRawNetTasNet', 'lib']

@@ -98,7 +98,7 @@ class Engine(RaggedMixin):
         W['og_w'] = torch.cat([wo, wg], 0).contiguous()     # [2F, F]: rows [out; gate]
         W['og_bias'] = torch.cat([bo, bg], 0).contiguous()
         W['end_w'] = sep.end_conv1x1.weight.detach().reshape(N, F).contiguous()
-        if cfg['kind'] != 'bss':
+        if cfg['kind'] in ('spe', 'ira'):      # ResNet speaker encoder ('rawnet' carries RawNet3 instead)
             se = sep.spk_encoder
             W['spk_conv0_t'] = _t(se[1].weight)
             W['spk_res'] = [dict(c1=_t(rb.conv1.weight), c2=_t(rb.conv2.weight),

@@ -20,6 +20,7 @@ import torch
 from torch import nn
 
 from .engine import Engine
+from .rawnet import RawNet3
 
 
 class _GlobLN(nn.Module):
@@ -126,6 +127,10 @@ class _Masker(nn.Module):
         self.pred_linear = nn.Linear(E, num_spks)
         if kind == 'ira':
             self.aux_linear = nn.Linear(2 * E, E)      # dprnn_spe_ira.py:51
+        if kind == 'rawnet':
+            # DPRNNRawNet.__init__ builds the whole DPRNNSpe first (the ResNet above consumes the RNG exactly as in the
+            # reference) and then replaces the speaker encoder with RawNet3 (dprnn_rawnet.py:57-70)
+            self.spk_encoder = RawNet3(nOut=E)
 
 
 class _TasNetBase(nn.Module):
@@ -225,3 +230,26 @@ class DPRNNSpeIRATasNet(DPRNNSpeTasNet):
 
     def forward_ragged(self, inputs, auxs):
         return self._engine.forward_ira_ragged(inputs, auxs)
+
+
+class DPRNNRawNetTasNet(_TasNetBase):
+    """Target-speaker separation with a RawNet3 speaker encoder on the raw 16 kHz reference; mirrors
+    src/models/dprnn_rawnet.py:107-182.  ``forward(input, aux)`` has no ``aux_len`` (dprnn_rawnet.py:171).
+    The masker, fusion and decoder are the CUDA path; RawNet3 itself is the stage-1 GPU restatement of rawnet.py."""
+    kind = 'rawnet'
+
+    def __init__(self, input_size, feature_size=128, hidden_size=128, chunk_length=200, kernel_size=2,
+                 hop_length=None, n_repeats=6, bidirectional=True, rnn_type='LSTM', norm_type='gLN',
+                 activation_type='sigmoid', dropout=0, stride=None, O=128, P=256, embeddings_size=128,
+                 num_spks=251, fusion_type='cat'):
+        super().__init__(input_size, feature_size, hidden_size, chunk_length, kernel_size, hop_length, n_repeats,
+                         bidirectional, rnn_type, norm_type, activation_type, dropout, stride, O=O, P=P,
+                         embeddings_size=embeddings_size, num_spks=num_spks, fusion_type=fusion_type)
+
+    def forward(self, input, aux):
+        self.separation.spk_encoder.allow_tf32 = self.precision == 'bf16'
+        emb = self.separation.spk_encoder.embed(aux)
+        return self._engine.forward_spe(input, None, None, embedding=emb)
+
+    def forward_with_embedding(self, input, embedding):
+        return self._engine.forward_spe(input, None, None, embedding=embedding)
