@@ -123,9 +123,14 @@ def pick_steps(buckets, n):
     return [buckets[int(round(i * (len(buckets) - 1) / max(1, n - 1)))] for i in range(n)]
 
 
+KW4 = dict(KW, embeddings_size=256, fusion_type='att')
+
+
 def model_for(workload):
     if workload == 'cfg3':
         return 'DPRNNSpeIRATasNet', KW
+    if workload == 'cfg4':
+        return 'DPRNNRawNetTasNet', KW4
     return 'DPRNNSpeTasNet', KW
 
 
@@ -136,6 +141,14 @@ def workload_config(args):
                             'batches, buckets LPT-assigned to ranks; one step = one bucket',
                 'batch_per_gpu': args.batch, 'precision': args.precision, 'streams': 1,
                 'l2': 'no flush needed: each step streams >10 GB of intermediates through a 126 MB L2',
+                'parallelism': f'utterance sharding x{args.gpus}, no collective'}
+    if args.workload == 'cfg4':
+        return {'workload': f'cfg4: DPRNN-RawNet3 (attention fusion) TSS inference, {args.samples / SR:g}-s mix @ 8 kHz + '
+                            f'{args.samples / SR:g}-s raw reference @ 16 kHz, batch {args.batch} per GPU (128 across 8), full '
+                            'depth; RawNet3 = stage-1 GPU library restatement, masker/fusion/decoder = CUDA path',
+                'batch_per_gpu': args.batch, 'samples': args.samples, 'precision': args.precision,
+                'streams': args.streams,
+                'l2': 'no flush needed: each step streams >2 GB of intermediates through a 126 MB L2',
                 'parallelism': f'utterance sharding x{args.gpus}, no collective'}
     return {'workload': f'cfg2: DPRNN-Spe (cat) TSS inference, {args.samples / SR:g}-s mix + reference @ 8 kHz, '
                         f'batch {args.batch} per GPU, full depth (6 blocks)',
@@ -153,7 +166,7 @@ def cpu_forward_fn(workload):
     ref_root = os.path.join(ROOT, 'baseline', '_ref')
     torch.manual_seed(0)
     cls, kw = model_for(workload)
-    if os.path.isdir(os.path.join(ref_root, 'src', 'models')):
+    if workload != 'cfg4' and os.path.isdir(os.path.join(ref_root, 'src', 'models')):
         sys.path.insert(0, ref_root)
         if cls == 'DPRNNSpeIRATasNet':
             from src.models.dprnn_spe_ira import DPRNNSpeIRATasNet as RefModel
@@ -164,6 +177,10 @@ def cpu_forward_fn(workload):
     from oracle import dprnn_oracle as O
     import tss_with_dprnn_b200 as P
     sd = getattr(P, cls)(**kw).state_dict()
+    if workload == 'cfg4':      # the reference's RawNet3 needs asteroid_filterbanks (absent): always the oracle port
+        from oracle import rawnet_oracle as RO
+        cfg4 = O.Config(fusion_type='att')
+        return 'port', (lambda mix, ref, rl: RO.rawnet_tasnet_forward(mix, ref, sd, cfg4)[0])
     cfg = O.Config(fusion_type='cat')
     fwd = O.ira_forward if cls == 'DPRNNSpeIRATasNet' else O.spe_forward
     return 'port', (lambda mix, ref, rl: fwd(mix, ref, rl, sd, cfg)[0])
@@ -175,6 +192,9 @@ def cpu_sample(args):
         rows = sorted(load_test_set_lengths())
         t, tr = rows[len(rows) // 2]
         return 1, t, tr, f'1 utterance of the median test-set length ({t} samples, reference {tr}) per forward'
+    if args.workload == 'cfg4':
+        return args.cpu_batch, args.samples, 2 * args.samples, \
+            f'{args.cpu_batch} x {args.samples / SR:g}-s utterance(s) per forward (bounded sample of the batch-{args.batch} workload)'
     return args.cpu_batch, args.samples, args.samples, \
         f'{args.cpu_batch} x {args.samples / SR:g}-s utterance(s) per forward (bounded sample of the batch-{args.batch} workload)'
 
@@ -252,6 +272,29 @@ class Cfg2:
         return 2 * self.B * self.T * 4, self.B * self.T * 4
 
 
+class Cfg4(Cfg2):
+    """BASELINE.json configs[3]: DPRNN-RawNet3 (att), raw 16 kHz reference, forward(mix, ref16k)."""
+
+    def __init__(self, args, model, rank, dev):
+        super().__init__(args, model, rank, dev)
+        g = torch.Generator().manual_seed(1236 + 1000 * rank)
+        self.ref_h = (0.05 * torch.randn(self.B, 2 * self.T, generator=g)).pin_memory()
+        self.ref = self.ref_h.to(dev)
+
+    def resident(self, i):
+        return self.model(self.mix, self.ref)
+
+    def e2e(self, i):
+        m = self.mix_h.to(self.dev, non_blocking=True)
+        r = self.ref_h.to(self.dev, non_blocking=True)
+        est, _ = self.model(m, r)
+        self.out_h.copy_(est, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def bytes(self, i):
+        return 3 * self.B * self.T * 4, self.B * self.T * 4
+
+
 class Cfg3:
     """BASELINE.json configs[2]: full-length variable-duration utterances as ragged batches (model.forward_ragged)."""
 
@@ -317,7 +360,12 @@ def run_ours(args):
     if args.fused_tail is not None:
         model._engine.fused_tail = bool(args.fused_tail)
     L = P.lib()
-    wl = Cfg3(args, model, rank, world, dev, args.steps) if args.workload == 'cfg3' else Cfg2(args, model, rank, dev)
+    if args.workload == 'cfg3':
+        wl = Cfg3(args, model, rank, world, dev, args.steps)
+    elif args.workload == 'cfg4':
+        wl = Cfg4(args, model, rank, dev)
+    else:
+        wl = Cfg2(args, model, rank, dev)
 
     def timed(fn, steps, warmup):
         with torch.no_grad():
@@ -425,17 +473,20 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3'],
-                    help='cfg2 (headline): DPRNN-Spe cat, 3-s batch 64; cfg3: DPRNN-Spe-IRA on the ragged test-set lengths')
+    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4'],
+                    help='cfg2 (headline): DPRNN-Spe cat, 3-s batch 64; cfg3: DPRNN-Spe-IRA on the ragged test-set lengths; '
+                         'cfg4: DPRNN-RawNet3 att, batch 16 per GPU')
     ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--streams', type=int, default=int(os.environ.get('DPRNN_STREAMS', '3')),
                     help='concurrent CUDA streams the batch is split over inside one forward (cfg2)')
     ap.add_argument('--fused-tail', type=int, default=None, help='1: Linear+norm+residual as one persistent kernel')
-    ap.add_argument('--batch', type=int, default=64, help='utterances per GPU and step (cfg 2: 64; cfg 3: bucket size)')
+    ap.add_argument('--batch', type=int, default=None, help='utterances per GPU and step (cfg 2: 64; cfg 3: bucket size)')
     ap.add_argument('--samples', type=int, default=24000, help='samples per utterance (3 s @ 8 kHz)')
     ap.add_argument('--cpu-batch', type=int, default=1, help='utterances per CPU-baseline forward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
+    if args.batch is None:
+        args.batch = 16 if args.workload == 'cfg4' else 64
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
     if args.impl == 'reference':
