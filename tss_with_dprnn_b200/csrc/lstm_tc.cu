@@ -81,26 +81,24 @@ __device__ __forceinline__ void mbar_expect_tx_addr(uint32_t addr, uint32_t byte
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
 }
 
-// Cell update for 16 hidden units of one sequence row: gates from TMEM (+bias) -> c (registers), h (packed bf16).
+// Cell update for 8 hidden units of one sequence row: gates from TMEM (+bias) -> c (registers), h (packed bf16, one
+// 16-byte chunk).  8 units at a time keeps the live register set small enough for 128 registers per thread, which
+// leaves room on the SM for a memory-bound CTA of another stream next to this kernel.
 // The i, f, o rows of the weights and biases are pre-scaled by 1/2 on the host (exact), so sigmoid(x) = 1/2 tanh(x') + 1/2.
 template <bool kFastAct>
-__device__ __forceinline__ void lstm_cell16(uint32_t tcol, const float* __restrict__ bq, float* __restrict__ c,
-                                            uint32_t (&packed)[8]) {
-    uint32_t ri[16], rf[16], rg[16], ro[16];
-    tmem_ld16_issue(tcol + 0 * 64, ri);
-    tmem_ld16_issue(tcol + 1 * 64, rf);
-    tmem_ld16_issue(tcol + 2 * 64, rg);
-    tmem_ld16_issue(tcol + 3 * 64, ro);
-    float4 bi = *reinterpret_cast<const float4*>(bq + 0 * 64), bf = *reinterpret_cast<const float4*>(bq + 1 * 64);
-    float4 bg = *reinterpret_cast<const float4*>(bq + 2 * 64), bo = *reinterpret_cast<const float4*>(bq + 3 * 64);
+__device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restrict__ bq, float* __restrict__ c,
+                                           uint32_t (&packed)[4]) {
+    uint32_t ri[8], rf[8], rg[8], ro[8];
+    tmem_ld8_issue(tcol + 0 * 64, ri);
+    tmem_ld8_issue(tcol + 1 * 64, rf);
+    tmem_ld8_issue(tcol + 2 * 64, rg);
+    tmem_ld8_issue(tcol + 3 * 64, ro);
     tmem_ld_wait();
 #pragma unroll
-    for (int j = 0; j < 16; j += 4) {
+    for (int j = 0; j < 8; j += 4) {
+        const float4 bi = *reinterpret_cast<const float4*>(bq + 0 * 64 + j), bf = *reinterpret_cast<const float4*>(bq + 1 * 64 + j);
+        const float4 bg = *reinterpret_cast<const float4*>(bq + 2 * 64 + j), bo = *reinterpret_cast<const float4*>(bq + 3 * 64 + j);
         const float b4[4][4] = {{bi.x, bi.y, bi.z, bi.w}, {bf.x, bf.y, bf.z, bf.w}, {bg.x, bg.y, bg.z, bg.w}, {bo.x, bo.y, bo.z, bo.w}};
-        if (j + 4 < 16) {      // next four units' biases while this group's activations are in flight
-            bi = *reinterpret_cast<const float4*>(bq + 0 * 64 + j + 4); bf = *reinterpret_cast<const float4*>(bq + 1 * 64 + j + 4);
-            bg = *reinterpret_cast<const float4*>(bq + 2 * 64 + j + 4); bo = *reinterpret_cast<const float4*>(bq + 3 * 64 + j + 4);
-        }
         float hv[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
@@ -269,19 +267,18 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             // ---------------- unit half 0
             mbar_wait(&d_full[0], par);
             tc_fence_after();
-            uint32_t pk0[8], pk1[8];
-            lstm_cell16<kFastAct>(tbase + 0, sbias + sub * 32 + 0, c0 + 0, pk0);
-            lstm_cell16<kFastAct>(tbase + 16, sbias + sub * 32 + 16, c0 + 16, pk1);
+            uint32_t pk[4][4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g) lstm_cell8<kFastAct>(tbase + 8 * g, sbias + sub * 32 + 8 * g, c0 + 8 * g, pk[g]);
             tc_fence_before();                         // our tcgen05.ld of D0 are complete
             mbar_wait(h_free, par);                    // the MMAs that read h_{t-1} have completed
             if (storer) bulk_wait_read0();             // ... and so has last step's TMA store of the h tile
             named_bar(1, 256);
             {
-                uint8_t* sH = smem + SM_H;             // K-block 0 = units 0..63; 16 units = two 16-byte chunks
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 0)) = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 1)) = make_uint4(pk0[4], pk0[5], pk0[6], pk0[7]);
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 2)) = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 3)) = make_uint4(pk1[4], pk1[5], pk1[6], pk1[7]);
+                uint8_t* sH = smem + SM_H;             // K-block 0 = units 0..63; 8 units = one 16-byte chunk
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + g)) = make_uint4(pk[g][0], pk[g][1], pk[g][2], pk[g][3]);
             }
             fence_async_smem();                        // generic-proxy writes -> visible to tcgen05.mma / TMA
             __syncwarp();
@@ -289,15 +286,15 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             // ---------------- unit half 1
             mbar_wait(&d_full[1], par);
             tc_fence_after();
-            lstm_cell16<kFastAct>(tbase + 256 + 0, sbias + 256 + sub * 32 + 0, c1s + 0, pk0);
-            lstm_cell16<kFastAct>(tbase + 256 + 16, sbias + 256 + sub * 32 + 16, c1s + 16, pk1);
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                lstm_cell8<kFastAct>(tbase + 256 + 8 * g, sbias + 256 + sub * 32 + 8 * g, c1s + 8 * g, pk[g]);
             tc_fence_before();
             {
                 uint8_t* sH = smem + SM_H + TILE;      // K-block 1 = units 64..127
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 0)) = make_uint4(pk0[0], pk0[1], pk0[2], pk0[3]);
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 1)) = make_uint4(pk0[4], pk0[5], pk0[6], pk0[7]);
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 2)) = make_uint4(pk1[0], pk1[1], pk1[2], pk1[3]);
-                *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + 3)) = make_uint4(pk1[4], pk1[5], pk1[6], pk1[7]);
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + g)) = make_uint4(pk[g][0], pk[g][1], pk[g][2], pk[g][3]);
             }
             fence_async_smem();
             __syncwarp();

@@ -32,6 +32,8 @@ class Engine(RaggedMixin):
         self.fused_tail = False    # bf16 mode: Linear + norm + residual as one persistent kernel (linear_norm.cu)
         self._row_off = {}
         self._streams = []
+        self.use_graphs = True     # eval forwards of a repeated shape are captured into a CUDA graph and replayed
+        self._graphs = {}
         self._packed = None
         self._packed_key = None
 
@@ -278,40 +280,23 @@ class Engine(RaggedMixin):
         return emb
 
     # ------------------------------------------------------------------ masker
-    def masker_split(self, enc, mr, B, L, emb, speakers):
-        """masker() over utterance groups on concurrent CUDA streams.  Utterances are independent (results are
-        bit-identical to the single-stream call); running groups side by side lets one group's memory-bound
-        kernels and partial waves fill the SMs another group's LSTM kernel leaves idle."""
-        n = max(1, min(self.n_streams, B))
-        N = self.model.cfg['input_size']
-        outs = [torch.empty((B, L, N), device=enc.device) for _ in speakers]
-        if n == 1:
-            self.masker(enc, mr, B, L, emb, speakers, outs)
-            return outs
-        while len(self._streams) < n:
-            self._streams.append(torch.cuda.Stream(device=enc.device))
-        main = torch.cuda.current_stream()
-        ready = torch.cuda.Event()
-        ready.record(main)
-        base, extra = divmod(B, n)
-        b0 = 0
-        for i in range(n):
-            b1 = b0 + base + (1 if i < extra else 0)
-            st = self._streams[i]
-            st.wait_event(ready)
-            with torch.cuda.stream(st):
-                self.masker(enc[b0:b1], mr[b0:b1], b1 - b0, L, None if emb is None else emb[b0:b1], speakers,
-                            [o[b0:b1] for o in outs])
-                done = torch.cuda.Event()
-                done.record(st)
-            main.wait_event(done)
-            b0 = b1
-        return outs
-
     def masker(self, enc, mr, B, L, emb, speakers, outs=None):
         """bottleneck norm + fusion + 1x1 conv, segmentation, DPRNN blocks, PReLU, overlap-add, conv2d,
         gated head, activation (dprnn.py:166-187 / dprnn_spe.py:125-154,231-248).
         enc [B,L,N]; mr its GroupNorm statistics; returns one mask [B,L,N] per requested speaker."""
+        s = self._masker_pre(enc, mr, B, L, emb)
+        for bi in range(len(self.model.separation.dprnn_blocks)):
+            for which in (0, 1):
+                if s['bf16']:
+                    self._half_lstm(s, bi, which)
+                    self._half_tail(s, bi, which)
+                else:
+                    self._half_fp32(s, bi, which)
+        return self._masker_post(s, speakers, outs)
+
+    def _masker_pre(self, enc, mr, B, L, emb):
+        """bottleneck norm + speaker fusion + 1x1 conv, segmentation, bf16 shadow; allocates the per-group buffers the
+        blocks reuse (so that nothing is allocated or freed while two streams work on the group)."""
         L_, W, st = lib(), self.packed(), self._stream()
         cfg, sep = self.model.cfg, self.model.separation
         N, F, H = cfg['input_size'], cfg['feature_size'], cfg['hidden_size']
@@ -352,55 +337,84 @@ class Engine(RaggedMixin):
         del y
         rows = B * S * K
         bf16 = self.precision == 'bf16'
+        s = dict(B=B, L=L, S=S, K=K, P=P, F=F, H=H, N=N, rows=rows, x=x, bf16=bf16, dev=dev)
         if bf16:
             if H != 128 or F != 128:
                 raise NotImplementedError('the tensor-core LSTM kernel is built for feature_size = hidden_size = 128')
-            xb = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
-            L_.call('dprnn_cast_bf16', x, xb, rows * F, st)
-        for blk, halves in zip(sep.dprnn_blocks, W['blocks']):
-            for which, hw in enumerate(halves):
-                nd = hw['ndir']
-                nm = blk.intra_norm if which == 0 else blk.inter_norm
-                g_, b_, eps = self._norm_params(nm)
-                if bf16:
-                    hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
-                    L_.call('dprnn_lstm_layer_bf16', xb, hw['tc_w'], hw['tc_bias'], hb, B, S, K, which, H, nd,
-                            int(self.fast_act), st)
-                    R = S * K
-                    if self.fused_tail:
-                        # Linear + norm statistics + norm apply + residual in one persistent kernel (linear_norm.cu)
-                        ws = torch.empty(L_.query('dprnn_linear_norm_workspace_bytes', rows, B), device=dev,
-                                         dtype=torch.uint8)
-                        L_.call('dprnn_linear_norm_residual_bf16', hb, hw['lin_bf16'], hw['lin_b'], x, xb, g_, b_,
-                                float(eps), self._row_offsets(B, R, dev), B, R, rows, nd * H, ws, st)
-                        del hb, ws
-                        continue
-                    # Linear (bf16 output, statistics from the fp32 accumulators) -> finalize -> norm + residual
-                    ybuf = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
-                    part = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', rows), device=dev, dtype=torch.uint8)
-                    mr2 = torch.empty((B, 2), device=dev)
-                    L_.call('dprnn_linear_bf16out_stats', hb, hw['lin_bf16'], hw['lin_b'], ybuf, rows, nd * H, part, R,
-                            float(eps), mr2, st)
-                    L_.call('dprnn_norm_residual_ybf16', ybuf, x, mr2, g_, b_, B, R, F, xb, st)
-                    del hb, ybuf
-                    continue
-                gx = self.gemm(x, hw['wih_t'], rows, nd * 4 * H, F, bias=hw['bias'])
-                hout = torch.empty((rows, nd * H), device=dev)
-                if which == 0:    # intra: one sequence per (b, s), steps along k
-                    geo = (B * S, K, 1, K, 0, 1)
-                else:             # inter: one sequence per (b, k), steps along s
-                    geo = (B * K, S, K, S * K, 1, K)
-                L_.call('dprnn_lstm_recurrence_f32', gx, hw['whh_t'], hout, geo[0], geo[1], geo[2], geo[3], geo[4],
-                        geo[5], H, nd, st)
-                del gx
-                yl = self.gemm(hout, hw['lin_t'], rows, F, nd * H, bias=hw['lin_b'])
-                del hout
-                mr2 = self.utt_stats(yl, B, S * K * F, eps)
-                L_.call('dprnn_norm_residual', yl, x, mr2, g_, b_, B, S * K, F, None, st)
-                del yl
+            s['xb'] = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+            L_.call('dprnn_cast_bf16', x, s['xb'], rows * F, st)
+            ndmax = max(hw['ndir'] for halves in W['blocks'] for hw in halves)
+            s['hb'] = torch.empty((rows * ndmax * H,), device=dev, dtype=torch.bfloat16)
+            s['ybuf'] = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+            s['part'] = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', rows), device=dev, dtype=torch.uint8)
+            s['mr2'] = torch.empty((B, 2), device=dev)
+            if self.fused_tail:
+                s['ws'] = torch.empty(L_.query('dprnn_linear_norm_workspace_bytes', rows, B), device=dev, dtype=torch.uint8)
+        return s
+
+    def _half_lstm(self, s, bi, which):
+        """bf16 mode: one nn.LSTM layer (intra: which=0, inter: which=1) as the fused tcgen05 kernel -> s['hb']."""
+        hw = self.packed()['blocks'][bi][which]
+        lib().call('dprnn_lstm_layer_bf16', s['xb'], hw['tc_w'], hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'], which,
+                   s['H'], hw['ndir'], int(self.fast_act), self._stream())
+
+    def _half_tail(self, s, bi, which):
+        """bf16 mode: Linear -> GroupNorm / gLN -> residual (dprnn.py:86-92 / 96-99) on s['hb'] -> s['x'], s['xb']."""
+        if self.fused_tail:
+            # Linear + norm statistics + norm apply + residual in one persistent kernel (linear_norm.cu)
+            hw = self.packed()['blocks'][bi][which]
+            blk = self.model.separation.dprnn_blocks[bi]
+            g_, b_, eps = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
+            R = s['S'] * s['K']
+            lib().call('dprnn_linear_norm_residual_bf16', s['hb'], hw['lin_bf16'], hw['lin_b'], s['x'], s['xb'], g_, b_,
+                       float(eps), self._row_offsets(s['B'], R, s['dev']), s['B'], R, s['rows'], hw['ndir'] * s['H'],
+                       s['ws'], self._stream())
+            return
+        self._half_linear(s, bi, which)
+        self._half_norm(s, bi, which)
+
+    def _half_linear(self, s, bi, which):
+        """Linear with bf16 output; per-utterance mean / rstd of the following norm from the fp32 accumulators."""
+        hw = self.packed()['blocks'][bi][which]
+        blk = self.model.separation.dprnn_blocks[bi]
+        _, _, eps = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
+        lib().call('dprnn_linear_bf16out_stats', s['hb'], hw['lin_bf16'], hw['lin_b'], s['ybuf'], s['rows'],
+                   hw['ndir'] * s['H'], s['part'], s['S'] * s['K'], float(eps), s['mr2'], self._stream())
+
+    def _half_norm(self, s, bi, which):
+        blk = self.model.separation.dprnn_blocks[bi]
+        g_, b_, _ = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
+        lib().call('dprnn_norm_residual_ybf16', s['ybuf'], s['x'], s['mr2'], g_, b_, s['B'], s['S'] * s['K'], s['F'],
+                   s['xb'], self._stream())
+
+    def _half_fp32(self, s, bi, which):
+        """exact-fp32 mode: input projection GEMM, recurrence, Linear, statistics, norm + residual on CUDA cores."""
+        L_, st = lib(), self._stream()
+        hw = self.packed()['blocks'][bi][which]
+        blk = self.model.separation.dprnn_blocks[bi]
+        g_, b_, eps = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
+        B, S, K, F, H, rows, x, nd = s['B'], s['S'], s['K'], s['F'], s['H'], s['rows'], s['x'], hw['ndir']
+        gx = self.gemm(x, hw['wih_t'], rows, nd * 4 * H, F, bias=hw['bias'])
+        hout = torch.empty((rows, nd * H), device=s['dev'])
+        if which == 0:    # intra: one sequence per (b, s), steps along k
+            geo = (B * S, K, 1, K, 0, 1)
+        else:             # inter: one sequence per (b, k), steps along s
+            geo = (B * K, S, K, S * K, 1, K)
+        L_.call('dprnn_lstm_recurrence_f32', gx, hw['whh_t'], hout, geo[0], geo[1], geo[2], geo[3], geo[4],
+                geo[5], H, nd, st)
+        del gx
+        yl = self.gemm(hout, hw['lin_t'], rows, F, nd * H, bias=hw['lin_b'])
+        del hout
+        mr2 = self.utt_stats(yl, B, S * K * F, eps)
+        L_.call('dprnn_norm_residual', yl, x, mr2, g_, b_, B, S * K, F, None, st)
+
+    def _masker_post(self, s, speakers, outs=None):
+        """PReLU + overlap-add, conv2d (after the fold), gated head, end conv + activation -> masks."""
+        L_, W, st = lib(), self.packed(), self._stream()
+        cfg, sep = self.model.cfg, self.model.separation
+        B, L, K, P, F, N, x, dev, bf16 = s['B'], s['L'], s['K'], s['P'], s['F'], s['N'], s['x'], s['dev'], s['bf16']
         z = torch.empty((B, L, F), device=dev)
         L_.call('dprnn_fold_prelu', x, z, B, L, K, P, F, sep.prelu.weight.detach(), st)
-        del x
         act = EPI_SIGMOID if cfg['activation_type'] == 'sigmoid' else EPI_RELU
         masks = []
         for spk in speakers:
@@ -425,73 +439,163 @@ class Engine(RaggedMixin):
                    cfg['input_size'], cfg['kernel_size'], cfg['stride'], self._stream())
 
     # ------------------------------------------------------------------ whole-model forwards
+    def _graphed(self, tag, inputs, fn):
+        """fn(*inputs) -> tuple of tensors, replayed from a CUDA graph once the same (shape, weights, settings) has been
+        seen before: a forward is ~400 kernel launches (x utterance groups), i.e. ~10 ms of host time that a graph
+        replay does not pay - it matters most for the reference's B = 1 inference loop and for multi-stream batches.
+        The first call of a key runs eagerly (one-off shapes never pay for a capture); the graph owns its buffers
+        (static addresses: the TMA tensor maps baked into the captured launches stay valid); results are returned as
+        fresh copies."""
+        L_ = lib()
+        if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
+            return fn(*inputs)
+        key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
+               self.fast_act, self.fused_tail, self._weights_key())
+        ent = self._graphs.get(key)
+        if ent is None:
+            self._graphs[key] = 'seen'
+            while len(self._graphs) > 4:          # a graph pins every intermediate of its forward: keep few
+                self._graphs.pop(next(iter(self._graphs)))
+            return fn(*inputs)
+        if ent == 'seen':
+            static_in = [torch.empty_like(t) for t in inputs]
+            for d, t in zip(static_in, inputs):
+                d.copy_(t)
+            torch.cuda.current_stream().synchronize()
+            g = torch.cuda.CUDAGraph()
+            n0 = L_.launches
+            with torch.cuda.graph(g):
+                out = fn(*static_in)
+            ent = (g, static_in, tuple(out), L_.launches - n0)
+            L_.launches = n0
+            self._graphs[key] = ent
+        g, static_in, out, n_launch = ent
+        for d, t in zip(static_in, inputs):
+            d.copy_(t, non_blocking=True)
+        g.replay()
+        L_.launches += n_launch
+        return tuple(o.clone() for o in out)
+
+    def _run_groups(self, B, fn, couples_batch=False):
+        """Run fn(b0, b1) -> tuple of [b1-b0, ...] tensors for utterance groups on concurrent streams and concatenate.
+        Utterances are independent (unless train-mode BatchNorm couples them), so the results do not depend on the
+        grouping; side by side, one group's memory-bound and GEMM kernels (encoders, speaker ResNet, head) fill the
+        SMs that another group's LSTM kernel leaves idle in its partial second wave."""
+        n = 1 if couples_batch else max(1, min(self.n_streams, B))
+        if n == 1:
+            return fn(0, B)
+        dev = torch.cuda.current_device()
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=dev))
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        base, extra = divmod(B, n)
+        b0, parts = 0, []
+        for i in range(n):
+            b1 = b0 + base + (1 if i < extra else 0)
+            st = self._streams[i]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                out = fn(b0, b1)
+                done = torch.cuda.Event()
+                done.record(st)
+            main.wait_event(done)
+            if not torch.cuda.is_current_stream_capturing():
+                for t in out:
+                    t.record_stream(main)
+            parts.append(out)
+            b0 = b1
+        return tuple(torch.cat([p[j] for p in parts], 0) for j in range(len(parts[0])))
+
     def forward_bss(self, mix):
         self._guard_autograd()
         mix = self._check_input(mix, 'input')
-        with torch.no_grad():
-            B, T = mix.shape
-            enc, L = self.encode(mix)
-            N = self.model.cfg['input_size']
+        cfg = self.model.cfg
+        N = cfg['input_size']
+
+        def group_of(mixs, b0, b1):
+            m = mixs[b0:b1]
+            B = b1 - b0
+            enc, L = self.encode(m)
             _, _, eps = self._norm_params(self.model.separation.bottleneck[0])
             mr = self.utt_stats(enc, B, L * N, eps)
-            masks = self.masker_split(enc, mr, B, L, None, (0, 1))
-            cfg = self.model.cfg
+            masks = self.masker(enc, mr, B, L, None, (0, 1))
             Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
             out = torch.empty((B, 2, Tout), device=mix.device)
             for s in (0, 1):
                 self.decode(masks[s], enc, out[:, s], B, L, 2 * Tout)
-            return out
+            return (out,)
+
+        with torch.no_grad():
+            return self._graphed('bss', (mix,), lambda m: self._run_groups(m.shape[0], lambda b0, b1: group_of(m, b0, b1)))[0]
 
     def forward_spe(self, mix, ref, ref_len, embedding=None):
         self._guard_autograd()
         mix = self._check_input(mix, 'input')
-        with torch.no_grad():
-            B, T = mix.shape
-            sep, cfg = self.model.separation, self.model.cfg
-            N = cfg['input_size']
-            enc, L = self.encode(mix)
-            if embedding is None:
-                ref = self._check_input(ref, 'aux')
-                feats, Lr = self.encode(ref)
-                emb = self.speaker_embedding(feats, B, Lr, self._aux_div(ref_len, B, mix.device))
+        sep, cfg = self.model.separation, self.model.cfg
+        N = cfg['input_size']
+
+        def group(m, r, d, e, b0, b1):
+            B = b1 - b0
+            enc, L = self.encode(m[b0:b1])
+            if e is None:
+                feats, Lr = self.encode(r[b0:b1])
+                emb = self.speaker_embedding(feats, B, Lr, d[b0:b1])
                 del feats
             else:
-                emb = self._check_input(embedding, 'embedding')
+                emb = e[b0:b1]
             _, _, eps = self._norm_params(sep.bottleneck[0])
             mr = self.utt_stats(enc, B, L * N, eps)
-            mask = self.masker_split(enc, mr, B, L, emb, (0,))[0]
+            mask = self.masker(enc, mr, B, L, emb, (0,))[0]
             Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
-            est = torch.empty((B, Tout), device=mix.device)
+            est = torch.empty((B, Tout), device=m.device)
             self.decode(mask, enc, est, B, L, Tout)
-            logits = self.small_linear(emb, sep.pred_linear, B)
-            return est, logits
+            return est, self.small_linear(emb, sep.pred_linear, B)
+
+        with torch.no_grad():
+            B = mix.shape[0]
+            if embedding is None:
+                ref = self._check_input(ref, 'aux')
+                div = self._aux_div(ref_len, B, mix.device)
+                # train-mode BatchNorm statistics run over the whole batch (dprnn_spe.py:20-21): no grouping then
+                return self._graphed('spe', (mix, ref, div), lambda m, r, d: self._run_groups(
+                    B, lambda b0, b1: group(m, r, d, None, b0, b1), couples_batch=self.model.training))
+            embedding = self._check_input(embedding, 'embedding')
+            return self._graphed('spe_emb', (mix, embedding), lambda m, e: self._run_groups(
+                B, lambda b0, b1: group(m, None, None, e, b0, b1)))
 
     def forward_ira(self, mix, ref, ref_len):
         self._guard_autograd()
         mix = self._check_input(mix, 'input')
         ref = self._check_input(ref, 'aux')
-        with torch.no_grad():
-            B, T = mix.shape
-            sep, cfg = self.model.separation, self.model.cfg
-            N = cfg['input_size']
-            enc, L = self.encode(mix)
-            feats, Lr = self.encode(ref)
-            div = self._aux_div(ref_len, B, mix.device)
+        sep, cfg = self.model.separation, self.model.cfg
+        N, E = cfg['input_size'], cfg['embeddings_size']
+
+        def group(m, r, d, b0, b1):
+            B = b1 - b0
+            div = d[b0:b1]
+            enc, L = self.encode(m[b0:b1])
+            feats, Lr = self.encode(r[b0:b1])
             v0 = self.speaker_embedding(feats, B, Lr, div)
             del feats
             _, _, eps = self._norm_params(sep.bottleneck[0])
             mr = self.utt_stats(enc, B, L * N, eps)
-            mask = self.masker_split(enc, mr, B, L, v0, (0,))[0]
+            mask = self.masker(enc, mr, B, L, v0, (0,))[0]
             d0 = torch.empty_like(enc)
             lib().call('dprnn_mask_apply', mask, enc, d0, B * L * N, self._stream())
             v1 = self.speaker_embedding(d0, B, L, div)          # still divided by the reference's length (:84)
             del d0
-            E = cfg['embeddings_size']
             v = self.small_linear(v0, sep.aux_linear, B, K=E)                                  # W[:, :E] v0 + b
             self.small_linear(v1, sep.aux_linear, B, out=v, accumulate=True, w_off=E, bias=False)   # + W[:, E:] v1
-            mask = self.masker_split(enc, mr, B, L, v, (0,))[0]
+            mask = self.masker(enc, mr, B, L, v, (0,))[0]
             Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
-            est = torch.empty((B, Tout), device=mix.device)
+            est = torch.empty((B, Tout), device=m.device)
             self.decode(mask, enc, est, B, L, Tout)
-            logits = self.small_linear(v, sep.pred_linear, B)
-            return est, logits
+            return est, self.small_linear(v, sep.pred_linear, B)
+
+        with torch.no_grad():
+            B = mix.shape[0]
+            div_all = self._aux_div(ref_len, B, mix.device)
+            return self._graphed('ira', (mix, ref, div_all), lambda m, r, d: self._run_groups(
+                B, lambda b0, b1: group(m, r, d, b0, b1), couples_batch=self.model.training))
