@@ -61,6 +61,8 @@ int dprnn_norm_residual_ybf16(const void* y_bf16, float* x, const float* mean_rs
  * y [B,L,F] -> x [B,S,K,F], x[b,s,k,:] = y[b, s*P+k-K, :] or 0. S = dprnn_num_chunks(L,K,P). Bit-exact. */
 int dprnn_num_chunks(long L, int K, int P);
 int dprnn_unfold(const float* y, float* x, int B, long L, int K, int P, int F, void* stream);
+/* Same, also writing the bf16 copy x_bf16 [B,S,K,F] (operand of the first tensor-core LSTM layer). */
+int dprnn_unfold_bf16(const float* y, float* x, void* x_bf16, int B, long L, int K, int P, int F, void* stream);
 
 /* self.prelu + DPRNN._overlap_add, src/models/dprnn.py:174,203-217 (F.fold, plain sum):
  * x [B,S,K,F] -> out [B,L,F]. prelu_a (1 float, device) may be NULL for a pure fold. */
@@ -132,6 +134,13 @@ int dprnn_lstm_recurrence_f32(const float* gx, const float* whhT, float* hout, l
 
 /* ---- bf16 tensor-core mode (tcgen05 + TMA; fp32 accumulation in TMEM) ---- */
 
+/* The prologue of dprnn_gemm_f32 as a pass of its own (the tensor-core GEMM feeds its operands from shared memory
+ * straight into the MMA): out[row,c] = (a*p_scale[b,c] + p_shift[b,c]) * rowscale[row] + p_add[b,c], b = row/rows_per_utt
+ * - bottleneck norm + speaker fusion, dprnn_spe.py:136-143, and the speaker encoder's GroupNorm, dprnn_spe.py:116. */
+int dprnn_prologue_apply(const float* a, float* out, long rows, int C, long rows_per_utt, const float* p_scale,
+                         const float* p_shift, const float* p_add, const float* rowscale, void* stream);
+
+
 /* fp32 -> bf16 (round to nearest even) copy of an activation tensor. */
 int dprnn_cast_bf16(const float* x, void* out, long elems, void* stream);
 
@@ -142,7 +151,8 @@ int dprnn_cast_bf16(const float* x, void* out, long elems, void* stream);
  * N in {64,128,256}; K*elem_size a multiple of 128 bytes.  DPRNN_EPI_GATED: N = 2F, W rows = [out; gate],
  * C[M,F] = tanh(out) * sigmoid(gate).  stats_partial (may be NULL; dprnn_gemm_tc_stats_bytes(M) bytes): the
  * epilogue also emits per-row sums so that mean_rstd [M/rows_per_utt, 2] of the FOLLOWING GroupNorm(1,N) / gLN
- * (eps) is produced without another pass over C. */
+ * (eps) is produced without another pass over C.  With stats_partial == NULL, rows_per_utt > 0 makes bias a
+ * per-utterance bias [M/rows_per_utt, N]. */
 size_t dprnn_gemm_tc_stats_bytes(int M);
 int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias, float* C, long ldc, int M, int N,
                   int K, int epilogue, void* stats_partial, long rows_per_utt, float eps, float* mean_rstd,
@@ -237,6 +247,11 @@ int dprnn_gemm_f32_ragged(const float* A, long lda, const float* Wt, long ldw, f
                           const float* bias, int bias_per_utt, float bias_scale, const int* row_utt,
                           const float* p_scale, const float* p_shift, const float* p_add, const float* rowscale,
                           int epilogue, void* stream);
+/* dprnn_prologue_apply / dprnn_gemm_tc (per-utterance bias [n_utt,N]) with the utterance of every row given explicitly. */
+int dprnn_prologue_apply_ragged(const float* a, float* out, long rows, int C, const int* row_utt, const float* p_scale,
+                                const float* p_shift, const float* p_add, const float* rowscale, void* stream);
+int dprnn_gemm_tc_ragged(const void* A, int a_is_bf16, const void* W, const float* bias_per_utt, const int* row_utt,
+                         float* C, long ldc, int M, int N, int K, int epilogue, void* stream);
 /* Inter-chunk layer of dprnn_lstm_layer_bf16 on the packed chunk space: utt_jobs = n_utt x {int32 first chunk, int32
  * number of chunks}, in the order the pair-jobs should be scheduled (longest first). */
 int dprnn_lstm_inter_bf16_ragged(const void* x, const void* w_packed, const float* bias_perm, void* hout,

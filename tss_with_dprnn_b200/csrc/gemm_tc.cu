@@ -50,6 +50,8 @@ struct GemmTcArgs {
     int M; int num_kb;
     float2* stats_partial;     // [M] per-row {sum, sumsq} over the N output columns, or NULL
     long rows_per_utt;
+    int bias_per_utt;          // bias is [M / rows_per_utt, N] (a per-utterance bias: the 'cat' speaker fusion, A.6)
+    const int* row_utt;        // ragged batches: utterance of every row (else NULL: row / rows_per_utt)
 };
 
 template <int kElem, int N, int EPI>
@@ -127,8 +129,12 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                     v[j] = gt_tanh(v[j] + __ldg(a.bias + c0 + j)) * gt_sigmoid(g[j] + __ldg(a.bias + N_OUT + c0 + j));
             } else {
 #pragma unroll
+                const float* bias = a.bias;
+                if (bias && a.bias_per_utt)
+                    bias += (row < a.M ? (a.row_utt ? (long)__ldg(a.row_utt + row) : row / a.rows_per_utt) : 0) * (long)N;
+#pragma unroll
                 for (int j = 0; j < 32; ++j) {
-                    float x = v[j] + (a.bias ? __ldg(a.bias + c0 + j) : 0.f);
+                    float x = v[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
                     if constexpr (EPI == DPRNN_EPI_RELU) x = fmaxf(x, 0.f);
                     if constexpr (EPI == DPRNN_EPI_SIGMOID) x = gt_sigmoid(x);
                     v[j] = x;
@@ -221,18 +227,21 @@ static int dispatch_epi(const void* A, const void* W, const GemmTcArgs& args, in
 
 using namespace dprnn;
 
-extern "C" size_t dprnn_gemm_tc_stats_bytes(int M) { return (size_t)M * sizeof(float2); }
+extern "C" size_t dprnn_gemm_tc_stats_bytes(int M) { return (size_t)M * sizeof(float2) + 256; }   // + scheduler ticket
 
-extern "C" int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias, float* C, long ldc, int M,
-                             int N, int K, int epilogue, void* stats_partial, long rows_per_utt, float eps,
-                             float* mean_rstd, void* stream) {
+static int gemm_tc_impl(const void* A, int a_is_bf16, const void* W, const float* bias, float* C, long ldc, int M,
+                        int N, int K, int epilogue, void* stats_partial, long rows_per_utt, float eps,
+                        float* mean_rstd, const int* row_utt, void* stream) {
     DPRNN_CHECK_ARG(A && W && C && M > 0 && N > 0 && K > 0 && ldc % 4 == 0);
     DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) % 16 == 0);
     const int elem = a_is_bf16 ? 2 : 4;
     DPRNN_CHECK_ARG((K * elem) % 128 == 0);
     DPRNN_CHECK_ARG(epilogue != DPRNN_EPI_GATED || bias);
     cudaStream_t st = (cudaStream_t)stream;
-    GemmTcArgs args{bias, C, ldc, M, K * elem / 128, (float2*)stats_partial, rows_per_utt};
+    // without stats_partial, rows_per_utt > 0 selects a per-utterance bias [M / rows_per_utt, N]
+    const int bias_per_utt = (!stats_partial && (rows_per_utt > 0 || row_utt) && bias) ? 1 : 0;
+    if (bias_per_utt) DPRNN_CHECK_ARG((row_utt || M % rows_per_utt == 0) && epilogue != DPRNN_EPI_GATED);
+    GemmTcArgs args{bias, C, ldc, M, K * elem / 128, (float2*)stats_partial, rows_per_utt, bias_per_utt, row_utt};
     if (stats_partial) {
         DPRNN_CHECK_ARG(rows_per_utt > 0 && M % rows_per_utt == 0 && mean_rstd && epilogue == DPRNN_EPI_NONE);
     }
@@ -254,4 +263,19 @@ extern "C" int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const 
         return launch_row_stats_finalize(stats_partial, mean_rstd, M / rows_per_utt, rows_per_utt, N, (double)eps, st);
     }
     return 0;
+}
+
+extern "C" int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias, float* C, long ldc, int M,
+                             int N, int K, int epilogue, void* stats_partial, long rows_per_utt, float eps,
+                             float* mean_rstd, void* stream) {
+    return gemm_tc_impl(A, a_is_bf16, W, bias, C, ldc, M, N, K, epilogue, stats_partial, rows_per_utt, eps, mean_rstd,
+                        nullptr, stream);
+}
+
+// per-utterance bias [n_utt, N] selected through row_utt (ragged batches)
+extern "C" int dprnn_gemm_tc_ragged(const void* A, int a_is_bf16, const void* W, const float* bias_per_utt,
+                                    const int* row_utt, float* C, long ldc, int M, int N, int K, int epilogue,
+                                    void* stream) {
+    DPRNN_CHECK_ARG(bias_per_utt && row_utt);
+    return gemm_tc_impl(A, a_is_bf16, W, bias_per_utt, C, ldc, M, N, K, epilogue, nullptr, 0, 0.f, nullptr, row_utt, stream);
 }

@@ -14,13 +14,16 @@
 namespace dprnn {
 using namespace tc;
 
-constexpr int LP_N = 128, LP_AST = 6, LP_CST = 2;
+constexpr int LP_N = 128, LP_AST = 6, LP_CST = 2, LP_TQ = 4;
 constexpr uint32_t LP_BLK = 128 * 128;                 // one [128 rows x 128 B] swizzled tile = 16 KiB
 
 struct LinPersistArgs {
     const float* bias;
     float2* stats;        // [M] per-row {sum, sumsq}, or NULL
     int M, tiles;
+    unsigned* ticket;     // zeroed before launch: tiles are handed out dynamically (NULL: static round-robin).  With
+                          // one CTA per SM and other kernels sharing the GPU (utterance groups on other streams), some
+                          // CTAs start late; a static partition would make the whole launch wait for them.
 };
 
 __device__ __forceinline__ void lp_tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
@@ -38,7 +41,9 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
     uint8_t* sW = smem;                                 // KB blocks
     uint8_t* sA = sW + KB * LP_BLK;                     // LP_AST blocks
     uint8_t* sC = sA + LP_AST * LP_BLK;                 // LP_CST staging blocks [128 rows x 32 fp32]
-    __shared__ __align__(8) uint64_t a_full[LP_AST], a_empty[LP_AST], w_full, acc_full[2], acc_empty[2];
+    __shared__ __align__(8) uint64_t a_full[LP_AST], a_empty[LP_AST], w_full, acc_full[2], acc_empty[2], tq_full[LP_TQ],
+        tq_empty[LP_TQ];
+    __shared__ int tile_q[LP_TQ];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -48,6 +53,7 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
         for (int s = 0; s < LP_AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
         mbar_init(&w_full, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
+        for (int s = 0; s < LP_TQ; ++s) { mbar_init(&tq_full[s], 1); mbar_init(&tq_empty[s], 5); }
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc<1>(&tmem_base_s, 256);
@@ -61,7 +67,14 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
             mbar_expect_tx(&w_full, KB * LP_BLK);
             for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * LP_BLK, &tmW, &w_full, kb * 64, 0);
             int it = 0;
-            for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x) {
+            for (int n = 0;; ++n) {
+                int tile = a.ticket ? (int)atomicAdd(a.ticket, 1u) : (int)blockIdx.x + n * (int)gridDim.x;
+                if (tile >= a.tiles) tile = -1;
+                const int qs = n % LP_TQ;
+                mbar_wait(&tq_empty[qs], ((n / LP_TQ) & 1) ^ 1);
+                tile_q[qs] = tile;
+                mbar_arrive(&tq_full[qs]);
+                if (tile < 0) break;
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % LP_AST;
                     mbar_wait(&a_empty[s], ((it / LP_AST) & 1) ^ 1);
@@ -75,8 +88,13 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_bf16(128, LP_N);
             mbar_wait(&w_full, 0);
-            int it = 0, n = 0;
-            for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++n) {
+            int it = 0;
+            for (int n = 0;; ++n) {
+                const int qs = n % LP_TQ;
+                mbar_wait(&tq_full[qs], (n / LP_TQ) & 1);
+                const int tile = tile_q[qs];
+                mbar_arrive(&tq_empty[qs]);
+                if (tile < 0) break;
                 const int acc = n & 1;
                 mbar_wait(&acc_empty[acc], ((n >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
                 tc_fence_after();
@@ -99,8 +117,14 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
         const int q = warp & 3;
         const int r_in_tile = q * 32 + lane;
         const bool storer = (warp == 2 && lane == 0);
-        int n = 0, chunk_it = 0;
-        for (int tile = blockIdx.x; tile < a.tiles; tile += gridDim.x, ++n) {
+        int chunk_it = 0;
+        for (int n = 0;; ++n) {
+            const int qs = n % LP_TQ;
+            mbar_wait(&tq_full[qs], (n / LP_TQ) & 1);
+            const int tile = tile_q[qs];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tq_empty[qs]);
+            if (tile < 0) break;
             const int acc = n & 1;
             const long row = (long)tile * 128 + r_in_tile;
             mbar_wait(&acc_full[acc], (n >> 1) & 1);
@@ -211,7 +235,12 @@ static int launch_lp(const void* A, const void* W, const float* bias, void* C, i
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int tiles = (int)cdiv(M, 128);
-    LinPersistArgs args{bias, (float2*)stats, M, tiles};
+    unsigned* ticket = nullptr;
+    if (stats) {        // the ticket lives behind the per-row sums (dprnn_gemm_tc_stats_bytes reserves the room)
+        ticket = (unsigned*)((uint8_t*)stats + (size_t)M * sizeof(float2));
+        DPRNN_CUDA(cudaMemsetAsync(ticket, 0, sizeof(unsigned), st));
+    }
+    LinPersistArgs args{bias, (float2*)stats, M, tiles, ticket};
     kern<<<tiles < sms ? tiles : sms, 192, smem, st>>>(tmA, tmW, tmC, args);
     DPRNN_CHECK_LAUNCH();
     return 0;

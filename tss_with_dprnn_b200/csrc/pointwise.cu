@@ -158,6 +158,30 @@ __global__ void norm_residual_ybf16_kernel(const uint4* __restrict__ y, float* _
     }
 }
 
+// out = (a*p_scale[b,c] + p_shift[b,c]) * rowscale[row] + p_add[b,c]: the per-utterance norm + speaker fusion that the
+// exact-fp32 GEMM applies as a prologue, materialised for the tensor-core GEMM (whose operands go smem -> MMA directly)
+__global__ void prologue_apply_kernel(const float* __restrict__ a, float* __restrict__ out, long total4, int c4n,
+                                      long rows_per_utt, const float* __restrict__ p_scale,
+                                      const float* __restrict__ p_shift, const float* __restrict__ p_add,
+                                      const float* __restrict__ rowscale, const int* __restrict__ row_utt) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n);
+        const long row = idx / c4n, b = row_utt ? (long)__ldg(row_utt + row) : row / rows_per_utt;
+        float4 v = ld_stream(reinterpret_cast<const float4*>(a) + idx);
+        if (p_scale) {
+            const float4 sc = __ldg(reinterpret_cast<const float4*>(p_scale) + b * c4n + c4);
+            const float4 sh = __ldg(reinterpret_cast<const float4*>(p_shift) + b * c4n + c4);
+            v.x = fmaf(v.x, sc.x, sh.x); v.y = fmaf(v.y, sc.y, sh.y); v.z = fmaf(v.z, sc.z, sh.z); v.w = fmaf(v.w, sc.w, sh.w);
+        }
+        if (rowscale) { const float rs = __ldg(rowscale + row); v.x *= rs; v.y *= rs; v.z *= rs; v.w *= rs; }
+        if (p_add) {
+            const float4 ad = __ldg(reinterpret_cast<const float4*>(p_add) + b * c4n + c4);
+            v.x += ad.x; v.y += ad.y; v.z += ad.z; v.w += ad.w;
+        }
+        reinterpret_cast<float4*>(out)[idx] = v;
+    }
+}
+
 __global__ void cast_bf16_kernel(const float* __restrict__ x, uint2* __restrict__ out, long total4) {
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
         const float4 r = reinterpret_cast<const float4*>(x)[idx];
@@ -170,7 +194,7 @@ __global__ void cast_bf16_kernel(const float* __restrict__ x, uint2* __restrict_
 // unfold: out[b,s,k,:] = y[b, s*P + k - K, :] (zero outside [0,L))
 // ------------------------------------------------------------------------------------------
 __global__ void unfold_kernel(const float* __restrict__ y, float* __restrict__ out, int B, long L, int S, int K,
-                              int P, int f4n) {
+                              int P, int f4n, uint2* __restrict__ out_bf16) {
     const long total = (long)B * S * K * f4n;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int f4 = (int)(idx % f4n);
@@ -182,6 +206,10 @@ __global__ void unfold_kernel(const float* __restrict__ y, float* __restrict__ o
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t >= 0 && t < L) v = __ldg(reinterpret_cast<const float4*>(y) + (b * L + t) * f4n + f4);
         reinterpret_cast<float4*>(out)[idx] = v;
+        if (out_bf16) {      // bf16 shadow for the first tensor-core LSTM layer (saves a separate cast pass)
+            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+            out_bf16[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
     }
 }
 
@@ -501,6 +529,26 @@ int dprnn_norm_affine(const float* mean_rstd, const float* gamma, const float* b
     return 0;
 }
 
+int dprnn_prologue_apply(const float* a, float* out, long rows, int C, long rows_per_utt, const float* p_scale,
+                         const float* p_shift, const float* p_add, const float* rowscale, void* stream) {
+    DPRNN_CHECK_ARG(a && out && rows > 0 && C % 4 == 0 && rows_per_utt > 0);
+    DPRNN_CHECK_ARG((p_scale == nullptr) == (p_shift == nullptr));
+    prologue_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        a, out, rows * (C / 4), C / 4, rows_per_utt, p_scale, p_shift, p_add, rowscale, nullptr);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_prologue_apply_ragged(const float* a, float* out, long rows, int C, const int* row_utt, const float* p_scale,
+                                const float* p_shift, const float* p_add, const float* rowscale, void* stream) {
+    DPRNN_CHECK_ARG(a && out && rows > 0 && C % 4 == 0 && row_utt);
+    DPRNN_CHECK_ARG((p_scale == nullptr) == (p_shift == nullptr));
+    prologue_apply_kernel<<<grid_for(rows * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        a, out, rows * (C / 4), C / 4, 1, p_scale, p_shift, p_add, rowscale, row_utt);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
 int dprnn_cast_bf16(const float* x, void* out, long elems, void* stream) {
     DPRNN_CHECK_ARG(x && out && elems > 0 && elems % 4 == 0);
     cast_bf16_kernel<<<grid_for(elems / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint2*)out, elems / 4);
@@ -535,7 +583,16 @@ int dprnn_unfold(const float* y, float* x, int B, long L, int K, int P, int F, v
     DPRNN_CHECK_ARG(y && x && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);
     const int S = dprnn_num_chunks(L, K, P);
     unfold_kernel<<<grid_for((long)B * S * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, x, B, L, S, K, P,
-                                                                                           F / 4);
+                                                                                           F / 4, nullptr);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_unfold_bf16(const float* y, float* x, void* x_bf16, int B, long L, int K, int P, int F, void* stream) {
+    DPRNN_CHECK_ARG(y && x && x_bf16 && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);
+    const int S = dprnn_num_chunks(L, K, P);
+    unfold_kernel<<<grid_for((long)B * S * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, x, B, L, S, K, P,
+                                                                                           F / 4, (uint2*)x_bf16);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

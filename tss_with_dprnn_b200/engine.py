@@ -65,6 +65,7 @@ class Engine(RaggedMixin):
         W['dec'] = m.decoder.weight.detach().reshape(N, -1).contiguous()
         bw = sep.bottleneck[1].weight.detach().reshape(F, -1)           # [F, N(+E)]
         W['bott_wt'] = bw[:, :N].t().contiguous()
+        W['bott_w_x'] = bw[:, :N].contiguous()          # [F, N] native layout for the tensor-core path
         W['bott_w_full'] = bw.contiguous()
         blocks = []
         for blk in sep.dprnn_blocks:
@@ -172,14 +173,14 @@ class Engine(RaggedMixin):
                    int(rows_per_utt), p_scale, p_shift, p_add, rowscale, epi, self._stream())
         return out
 
-    def gemm_tc(self, A, W, M, N, K, bias=None, epi=EPI_NONE, out=None, stats=None):
+    def gemm_tc(self, A, W, M, N, K, bias=None, epi=EPI_NONE, out=None, stats=None, bias_rows_per_utt=0):
         """tcgen05 contraction; W in its native [N, K] layout (bf16 if A is bf16, else fp32 read as TF32).
         stats = (rows_per_utt, eps) additionally returns mean/rstd of the following per-utterance norm."""
         n_out = N // 2 if epi == EPI_GATED else N
         if out is None:
             out = torch.empty((M, n_out), device=A.device, dtype=torch.float32)
         part = mr = None
-        rpu, eps = 0, 0.0
+        rpu, eps = int(bias_rows_per_utt), 0.0
         if stats is not None:
             rpu, eps = stats
             part = torch.empty(lib().query('dprnn_gemm_tc_stats_bytes', M), device=A.device, dtype=torch.uint8)
@@ -239,8 +240,14 @@ class Engine(RaggedMixin):
         s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
         L_.call('dprnn_norm_affine', mr, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
         O = se[1].weight.shape[0]
-        x = self.gemm(feats, W['spk_conv0_t'], B * Lr, O, N, bias=se[1].bias.detach(), rows_per_utt=Lr,
-                      p_scale=s1, p_shift=s0)
+        if self.precision == 'bf16' and N % 32 == 0 and O in (64, 128, 256):
+            fn = torch.empty_like(feats)            # GroupNorm applied, then the 1x1 conv on the tensor cores (TF32)
+            L_.call('dprnn_prologue_apply', feats, fn, B * Lr, N, Lr, s1, s0, None, None, st)
+            x = self.gemm_tc(fn, se[1].weight.detach(), B * Lr, O, N, bias=se[1].bias.detach())
+            del fn
+        else:
+            x = self.gemm(feats, W['spk_conv0_t'], B * Lr, O, N, bias=se[1].bias.detach(), rows_per_utt=Lr,
+                          p_scale=s1, p_shift=s0)
         Lx = Lr
         for rb, wr in zip((se[2], se[3], se[4]), W['spk_res']):
             Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
@@ -274,7 +281,10 @@ class Engine(RaggedMixin):
                     Cout, st)
             x, Lx = out, Lo
         E = se[5].weight.shape[0]
-        z = self.gemm(x, W['spk_conv5_t'], B * Lx, E, se[5].weight.shape[1], bias=se[5].bias.detach())
+        if self.precision == 'bf16' and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
+            z = self.gemm_tc(x, se[5].weight.detach(), B * Lx, E, se[5].weight.shape[1], bias=se[5].bias.detach())
+        else:
+            z = self.gemm(x, W['spk_conv5_t'], B * Lx, E, se[5].weight.shape[1], bias=se[5].bias.detach())
         emb = torch.empty((B, E), device=dev)
         L_.call('dprnn_time_sum', z, emb, B, Lx, E, div, st)
         return emb
@@ -329,12 +339,16 @@ class Engine(RaggedMixin):
             L_.call('dprnn_att_rowscale', enc, n1, n0, sep.average.weight.detach(), sep.average.bias.detach(), mulc,
                     scores, rowscale, B, L, N, k, st)
         L_.call('dprnn_norm_affine', mr, gamma, beta, mulc, s1, s0, B, N, st)
-        y = self.gemm(enc, W['bott_wt'], B * L, F, N, bias=bias, bias_per_utt=bias_per_utt, rows_per_utt=L,
-                      p_scale=s1, p_shift=s0, p_add=addc, rowscale=rowscale)
+        if self.precision == 'bf16' and N % 32 == 0 and F in (64, 128, 256):
+            en = torch.empty_like(enc)              # norm + fusion applied, then the 1x1 conv on the tensor cores (TF32)
+            L_.call('dprnn_prologue_apply', enc, en, B * L, N, L, s1, s0, addc, rowscale, st)
+            y = self.gemm_tc(en, W['bott_w_x'], B * L, F, N, bias=bias, bias_rows_per_utt=L if bias_per_utt else 0)
+            del en
+        else:
+            y = self.gemm(enc, W['bott_wt'], B * L, F, N, bias=bias, bias_per_utt=bias_per_utt, rows_per_utt=L,
+                          p_scale=s1, p_shift=s0, p_add=addc, rowscale=rowscale)
         S = L_.query('dprnn_num_chunks', L, K, P)
         x = torch.empty((B, S, K, F), device=dev)
-        L_.call('dprnn_unfold', y, x, B, L, K, P, F, st)
-        del y
         rows = B * S * K
         bf16 = self.precision == 'bf16'
         s = dict(B=B, L=L, S=S, K=K, P=P, F=F, H=H, N=N, rows=rows, x=x, bf16=bf16, dev=dev)
@@ -342,7 +356,11 @@ class Engine(RaggedMixin):
             if H != 128 or F != 128:
                 raise NotImplementedError('the tensor-core LSTM kernel is built for feature_size = hidden_size = 128')
             s['xb'] = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
-            L_.call('dprnn_cast_bf16', x, s['xb'], rows * F, st)
+            L_.call('dprnn_unfold_bf16', y, x, s['xb'], B, L, K, P, F, st)
+        else:
+            L_.call('dprnn_unfold', y, x, B, L, K, P, F, st)
+        del y
+        if bf16:
             ndmax = max(hw['ndir'] for halves in W['blocks'] for hw in halves)
             s['hb'] = torch.empty((rows * ndmax * H,), device=dev, dtype=torch.bfloat16)
             s['ybuf'] = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)

@@ -160,8 +160,14 @@ class RaggedMixin:
         s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
         L_.call('dprnn_norm_affine', mr, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
         O = se[1].weight.shape[0]
-        x = self._gemm_ragged(feats, W['spk_conv0_t'], lay.total_rows, O, N, lay.frame_utt, bias=se[1].bias.detach(),
-                              p_scale=s1, p_shift=s0)
+        if self.precision == 'bf16' and N % 32 == 0 and O in (64, 128, 256):     # same arithmetic as the uniform path
+            fn = torch.empty_like(feats)
+            L_.call('dprnn_prologue_apply_ragged', feats, fn, lay.total_rows, N, lay.frame_utt, s1, s0, None, None, st)
+            x = self.gemm_tc(fn, se[1].weight.detach(), lay.total_rows, O, N, bias=se[1].bias.detach())
+            del fn
+        else:
+            x = self._gemm_ragged(feats, W['spk_conv0_t'], lay.total_rows, O, N, lay.frame_utt, bias=se[1].bias.detach(),
+                                  p_scale=s1, p_shift=s0)
         rows = lay.total_rows
         for rb, wr, stage in zip((se[2], se[3], se[4]), W['spk_res'], lay.pool_stages()):
             Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
@@ -189,7 +195,10 @@ class RaggedMixin:
                     stage['out_utt'], stage['in_off'], stage['out_off'], stage['total_out'], Cout, st)
             x, rows = out, stage['total_out']
         E = se[5].weight.shape[0]
-        z = self.gemm(x, W['spk_conv5_t'], rows, E, se[5].weight.shape[1], bias=se[5].bias.detach())
+        if self.precision == 'bf16' and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
+            z = self.gemm_tc(x, se[5].weight.detach(), rows, E, se[5].weight.shape[1], bias=se[5].bias.detach())
+        else:
+            z = self.gemm(x, W['spk_conv5_t'], rows, E, se[5].weight.shape[1], bias=se[5].bias.detach())
         last = lay.pool_stages()[-1]
         emb = torch.empty((B, E), device=dev)
         L_.call('dprnn_time_sum_ragged', z, emb, last['out_off'], last['out_len'], B, E, div, st)
@@ -231,8 +240,18 @@ class RaggedMixin:
                     mulc, scores, rowscale, lay.frame_utt, lay.frame_off, lay.L_d, lay.La_d, B, TR, N,
                     cfg['kernel_size'], st)
         L_.call('dprnn_norm_affine', mr, gamma, beta, mulc, s1, s0, B, N, st)
-        y = self._gemm_ragged(enc, W['bott_wt'], TR, F, N, lay.frame_utt, bias=bias, bias_per_utt=bias_per_utt,
-                              p_scale=s1, p_shift=s0, p_add=addc, rowscale=rowscale)
+        if self.precision == 'bf16' and N % 32 == 0 and F in (64, 128, 256):
+            en = torch.empty_like(enc)
+            L_.call('dprnn_prologue_apply_ragged', enc, en, TR, N, lay.frame_utt, s1, s0, addc, rowscale, st)
+            if bias_per_utt:
+                y = torch.empty((TR, F), device=dev)
+                L_.call('dprnn_gemm_tc_ragged', en, 0, W['bott_w_x'], bias, lay.frame_utt, y, F, TR, F, N, EPI_NONE, st)
+            else:
+                y = self.gemm_tc(en, W['bott_w_x'], TR, F, N, bias=bias)
+            del en
+        else:
+            y = self._gemm_ragged(enc, W['bott_wt'], TR, F, N, lay.frame_utt, bias=bias, bias_per_utt=bias_per_utt,
+                                  p_scale=s1, p_shift=s0, p_add=addc, rowscale=rowscale)
         TC = lay.total_chunks
         rows = TC * K
         x = torch.empty((rows, F), device=dev)
