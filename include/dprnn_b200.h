@@ -27,7 +27,7 @@ const char* dprnn_last_error(void);
 const char* dprnn_build_info(void);
 
 /* epilogues of dprnn_gemm_* */
-enum { DPRNN_EPI_NONE = 0, DPRNN_EPI_RELU = 1, DPRNN_EPI_SIGMOID = 2, DPRNN_EPI_GATED = 3 };
+enum { DPRNN_EPI_NONE = 0, DPRNN_EPI_RELU = 1, DPRNN_EPI_SIGMOID = 2, DPRNN_EPI_GATED = 3, DPRNN_EPI_AFFINE_PRELU = 4 };
 
 /* Encoder.forward, src/models/encoder_decoder.py:25-33 (Conv1d(1->N, ksz, stride, bias=False) + ReLU).
  * wave [B,T], w [N,ksz] -> enc [B, L=(T-ksz)/stride+1, N]. */
@@ -157,6 +157,12 @@ size_t dprnn_gemm_tc_stats_bytes(int M);
 int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias, float* C, long ldc, int M, int N,
                   int K, int epilogue, void* stats_partial, long rows_per_utt, float eps, float* mean_rstd,
                   void* stream);
+
+/* 1x1 conv -> BatchNorm1d (eval: per-channel scale/shift from dprnn_batchnorm_affine) -> PReLU in one pass
+ * (ResBlock, src/models/dprnn_spe.py:32-34): C[M,N] = prelu(A @ W^T * scale[n] + shift[n]); fp32 (TF32) operands,
+ * N in {128,256}. */
+int dprnn_gemm_tc_affine_prelu(const void* A, const void* W, const float* scale, const float* shift,
+                               const float* prelu_a, float* C, long ldc, int M, int N, int K, void* stream);
 
 /* The Linear(ndir*H -> 128) after each LSTM (src/models/dprnn.py:61,70) as a persistent, pipelined tcgen05 kernel:
  * C[M,128] (fp32, contiguous) = A[M,K] (bf16) @ W[128,K]^T (bf16) + bias, K in {128,256}; W stays resident in shared

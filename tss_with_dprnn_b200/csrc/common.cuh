@@ -80,4 +80,22 @@ __device__ __forceinline__ float4 ld_stream(const float4* p) {
     return r;
 }
 
+// The two decoder taps of one frame for kernel 2 / stride 1 / N = 64: p_j = sum_c mask[c]*enc[c]*w[c,j], in a fixed
+// summation order (shared by the uniform and the ragged decoder so that packing a batch changes no bit).
+__device__ __forceinline__ void decode_taps64(const float* __restrict__ m, const float* __restrict__ e,
+                                              const float* __restrict__ sw, float& p0, float& p1) {
+    float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+    for (int c4 = 0; c4 < 16; ++c4) {
+        const float4 mv = ld_stream(reinterpret_cast<const float4*>(m) + c4);
+        const float4 ev = ld_stream(reinterpret_cast<const float4*>(e) + c4);
+        const float z0 = mv.x * ev.x, z1 = mv.y * ev.y, z2 = mv.z * ev.z, z3 = mv.w * ev.w;
+        a0 = fmaf(z0, sw[8 * c4 + 0], a0); a1 = fmaf(z0, sw[8 * c4 + 1], a1);
+        a0 = fmaf(z1, sw[8 * c4 + 2], a0); a1 = fmaf(z1, sw[8 * c4 + 3], a1);
+        a0 = fmaf(z2, sw[8 * c4 + 4], a0); a1 = fmaf(z2, sw[8 * c4 + 5], a1);
+        a0 = fmaf(z3, sw[8 * c4 + 6], a0); a1 = fmaf(z3, sw[8 * c4 + 7], a1);
+    }
+    p0 = a0; p1 = a1;
+}
+
 }  // namespace dprnn

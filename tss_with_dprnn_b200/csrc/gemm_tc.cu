@@ -52,6 +52,7 @@ struct GemmTcArgs {
     long rows_per_utt;
     int bias_per_utt;          // bias is [M / rows_per_utt, N] (a per-utterance bias: the 'cat' speaker fusion, A.6)
     const int* row_utt;        // ragged batches: utterance of every row (else NULL: row / rows_per_utt)
+    const float *post_scale, *post_shift, *prelu_a;      // DPRNN_EPI_AFFINE_PRELU
 };
 
 template <int kElem, int N, int EPI>
@@ -137,6 +138,10 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                     float x = v[j] + (bias ? __ldg(bias + c0 + j) : 0.f);
                     if constexpr (EPI == DPRNN_EPI_RELU) x = fmaxf(x, 0.f);
                     if constexpr (EPI == DPRNN_EPI_SIGMOID) x = gt_sigmoid(x);
+                    if constexpr (EPI == DPRNN_EPI_AFFINE_PRELU) {
+                        x = fmaf(x, __ldg(a.post_scale + c0 + j), __ldg(a.post_shift + c0 + j));
+                        x = x >= 0.f ? x : __ldg(a.prelu_a) * x;
+                    }
                     v[j] = x;
                 }
             }
@@ -217,6 +222,9 @@ static int dispatch_epi(const void* A, const void* W, const GemmTcArgs& args, in
         case DPRNN_EPI_NONE: return launch_gemm_tc<kElem, N, DPRNN_EPI_NONE>(A, W, args, K, st);
         case DPRNN_EPI_RELU: return launch_gemm_tc<kElem, N, DPRNN_EPI_RELU>(A, W, args, K, st);
         case DPRNN_EPI_SIGMOID: return launch_gemm_tc<kElem, N, DPRNN_EPI_SIGMOID>(A, W, args, K, st);
+        case DPRNN_EPI_AFFINE_PRELU:
+            if constexpr (kElem == 4 && N >= 128) return launch_gemm_tc<kElem, N, DPRNN_EPI_AFFINE_PRELU>(A, W, args, K, st);
+            break;
         default: break;
     }
     set_error("dprnn_gemm_tc: epilogue %d not built for N=%d", epi, N);
@@ -241,7 +249,8 @@ static int gemm_tc_impl(const void* A, int a_is_bf16, const void* W, const float
     // without stats_partial, rows_per_utt > 0 selects a per-utterance bias [M / rows_per_utt, N]
     const int bias_per_utt = (!stats_partial && (rows_per_utt > 0 || row_utt) && bias) ? 1 : 0;
     if (bias_per_utt) DPRNN_CHECK_ARG((row_utt || M % rows_per_utt == 0) && epilogue != DPRNN_EPI_GATED);
-    GemmTcArgs args{bias, C, ldc, M, K * elem / 128, (float2*)stats_partial, rows_per_utt, bias_per_utt, row_utt};
+    GemmTcArgs args{bias, C, ldc, M, K * elem / 128, (float2*)stats_partial, rows_per_utt, bias_per_utt, row_utt,
+                    nullptr, nullptr, nullptr};
     if (stats_partial) {
         DPRNN_CHECK_ARG(rows_per_utt > 0 && M % rows_per_utt == 0 && mean_rstd && epilogue == DPRNN_EPI_NONE);
     }
@@ -278,4 +287,13 @@ extern "C" int dprnn_gemm_tc_ragged(const void* A, int a_is_bf16, const void* W,
                                     void* stream) {
     DPRNN_CHECK_ARG(bias_per_utt && row_utt);
     return gemm_tc_impl(A, a_is_bf16, W, bias_per_utt, C, ldc, M, N, K, epilogue, nullptr, 0, 0.f, nullptr, row_utt, stream);
+}
+
+extern "C" int dprnn_gemm_tc_affine_prelu(const void* A, const void* W, const float* scale, const float* shift,
+                                          const float* prelu_a, float* C, long ldc, int M, int N, int K, void* stream) {
+    DPRNN_CHECK_ARG(A && W && scale && shift && prelu_a && C && M > 0 && (N == 128 || N == 256) && K > 0 && ldc % 4 == 0);
+    DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) % 16 == 0 && (K * 4) % 128 == 0);
+    GemmTcArgs args{nullptr, C, ldc, M, K * 4 / 128, nullptr, 0, 0, nullptr, scale, shift, prelu_a};
+    return N == 128 ? dispatch_epi<4, 128>(A, W, args, K, DPRNN_EPI_AFFINE_PRELU, (cudaStream_t)stream)
+                    : dispatch_epi<4, 256>(A, W, args, K, DPRNN_EPI_AFFINE_PRELU, (cudaStream_t)stream);
 }

@@ -239,7 +239,7 @@ __global__ void fold_prelu_kernel(const float* __restrict__ x, float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
-// mask * enc -> ConvTranspose1d(N -> 1, ksz, stride): one warp per output sample
+// mask * enc -> ConvTranspose1d(N -> 1, ksz, stride): one warp per output sample (general ksz / stride)
 // ------------------------------------------------------------------------------------------
 __global__ void mask_decode_kernel(const float* __restrict__ mask, long mask_utt_stride,
                                    const float* __restrict__ enc, const float* __restrict__ wdec,
@@ -263,6 +263,34 @@ __global__ void mask_decode_kernel(const float* __restrict__ mask, long mask_utt
         acc = warp_sum(acc);
         if (lane == 0) out[b * out_utt_stride + t] = acc;
     }
+}
+
+// The shipped geometry (kernel 2, stride 1, N = 64): one thread per frame reads its 2 x 256 contiguous bytes with
+// sixteen 16-byte loads in flight, forms the two taps p0 = <m.e, w[:,0]>, p1 = <m.e, w[:,1]> and
+// out[t] = p0[t] + p1[t-1]; the neighbour's p1 comes through shared memory (thread 0 recomputes its left halo).
+__global__ void __launch_bounds__(256) mask_decode_k2s1_kernel(const float* __restrict__ mask, long mask_utt_stride,
+                                                               const float* __restrict__ enc,
+                                                               const float* __restrict__ wdec, float* __restrict__ out,
+                                                               long out_utt_stride, long L, int blocks_per_utt) {
+    __shared__ float sw[128];
+    __shared__ float sp1[256];
+    if (threadIdx.x < 128) sw[threadIdx.x] = wdec[threadIdx.x];         // wdec [64, 2]
+    const long b = blockIdx.x / blocks_per_utt;
+    const long t = (long)(blockIdx.x % blocks_per_utt) * 256 + threadIdx.x;   // output sample, 0 .. L
+    __syncthreads();
+    const float* mb = mask + b * mask_utt_stride;
+    const float* eb = enc + b * L * 64;
+    float p0 = 0.f, p1 = 0.f;
+    if (t < L) decode_taps64(mb + t * 64, eb + t * 64, sw, p0, p1);
+    sp1[threadIdx.x] = p1;
+    float left = 0.f;
+    if (threadIdx.x == 0 && t >= 1 && t - 1 < L) {
+        float q0;
+        decode_taps64(mb + (t - 1) * 64, eb + (t - 1) * 64, sw, q0, left);
+    }
+    __syncthreads();
+    if (threadIdx.x > 0) left = sp1[threadIdx.x - 1];
+    if (t <= L) out[b * out_utt_stride + t] = p0 + left;
 }
 
 // out = mask * enc (the IRA re-embedding input d0, dprnn_spe_ira.py:79-80)
@@ -611,6 +639,14 @@ int dprnn_mask_decode(const float* mask, long mask_utt_stride, const float* enc,
                       long out_utt_stride, int B, long L, int N, int ksz, int stride, void* stream) {
     DPRNN_CHECK_ARG(mask && enc && wdec && out && B > 0 && L > 0 && N > 0 && ksz > 0 && stride > 0);
     const int T = (int)((L - 1) * stride + ksz);
+    if (ksz == 2 && stride == 1 && N == 64 && mask_utt_stride % 4 == 0 &&
+        ((uintptr_t)mask | (uintptr_t)enc) % 16 == 0) {
+        const int bpu = (int)cdiv(L + 1, 256);
+        mask_decode_k2s1_kernel<<<(unsigned)((long)B * bpu), 256, 0, (cudaStream_t)stream>>>(
+            mask, mask_utt_stride, enc, wdec, out, out_utt_stride, L, bpu);
+        DPRNN_CHECK_LAUNCH();
+        return 0;
+    }
     mask_decode_kernel<<<grid_for((long)B * T * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         mask, mask_utt_stride, enc, wdec, out, out_utt_stride, B, L, T, N, ksz, stride);
     DPRNN_CHECK_LAUNCH();

@@ -204,6 +204,38 @@ __global__ void mask_decode_ragged_kernel(const float* __restrict__ mask, const 
     }
 }
 
+// kernel 2 / stride 1 / N = 64 fast path: same per-frame arithmetic as mask_decode_k2s1_kernel (pointwise.cu)
+__global__ void __launch_bounds__(256) mask_decode_k2s1_ragged_kernel(const float* __restrict__ mask,
+                                                                      const float* __restrict__ enc,
+                                                                      const float* __restrict__ wdec,
+                                                                      float* __restrict__ out,
+                                                                      const int* __restrict__ frame_utt,
+                                                                      const long* __restrict__ frame_off,
+                                                                      const long* __restrict__ L, long total_rows) {
+    __shared__ float sw[128];
+    __shared__ float sp1[256];
+    if (threadIdx.x < 128) sw[threadIdx.x] = wdec[threadIdx.x];
+    const long row = (long)blockIdx.x * 256 + threadIdx.x;
+    __syncthreads();
+    long t = 0, Lb = 0;
+    if (row < total_rows) {
+        const int b = __ldg(frame_utt + row);
+        t = row - __ldg(frame_off + b);
+        Lb = __ldg(L + b);
+    }
+    float p0 = 0.f, p1 = 0.f;
+    if (row < total_rows && t < Lb) decode_taps64(mask + row * 64, enc + row * 64, sw, p0, p1);
+    sp1[threadIdx.x] = p1;
+    float left = 0.f;
+    if (threadIdx.x == 0 && row < total_rows && t >= 1) {
+        float q0;
+        decode_taps64(mask + (row - 1) * 64, enc + (row - 1) * 64, sw, q0, left);
+    }
+    __syncthreads();
+    if (threadIdx.x > 0) left = (t >= 1) ? sp1[threadIdx.x - 1] : 0.f;
+    if (row < total_rows) out[row] = p0 + left;          // t == 0: no left tap; t == L_b: only the left tap
+}
+
 // ---------------------------------------------------------------- attention fusion (dprnn_spe.py:212-229)
 __global__ void att_scores_ragged_kernel(const float* __restrict__ enc, const float* __restrict__ s1,
                                          const float* __restrict__ s0, const float* __restrict__ wavg,
@@ -390,6 +422,12 @@ int dprnn_fold_prelu_ragged(const float* x, float* out, const int* frame_utt, co
 int dprnn_mask_decode_ragged(const float* mask, const float* enc, const float* wdec, float* out, const int* frame_utt,
                              const long* frame_off, const long* L, long total_rows, int N, int ksz, void* stream) {
     DPRNN_CHECK_ARG(mask && enc && wdec && out && frame_utt && frame_off && L && total_rows > 0 && N > 0 && ksz > 0);
+    if (ksz == 2 && N == 64 && ((uintptr_t)mask | (uintptr_t)enc) % 16 == 0) {
+        mask_decode_k2s1_ragged_kernel<<<cdiv(total_rows, 256), 256, 0, (cudaStream_t)stream>>>(
+            mask, enc, wdec, out, frame_utt, frame_off, L, total_rows);
+        DPRNN_CHECK_LAUNCH();
+        return 0;
+    }
     mask_decode_ragged_kernel<<<rgrid(total_rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(
         mask, enc, wdec, out, frame_utt, frame_off, L, total_rows, N, ksz);
     DPRNN_CHECK_LAUNCH();

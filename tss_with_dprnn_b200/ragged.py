@@ -184,9 +184,15 @@ class RaggedMixin:
                     return self.gemm_tc(inp, conv_mod.weight.detach(), rows, cout, cin)
                 return self.gemm(inp, wt, rows, cout, cin)
 
-            y = conv(x, rb.conv1, wr['c1'], Cin, Cout)
-            bn(rb.batch_norm1)
-            L_.call('dprnn_affine_prelu', y, scale, shift, rb.prelu1.weight.detach(), y, rows, Cout, st)
+            if tc:          # same fused conv + BN + PReLU pass as the uniform eval path
+                bn(rb.batch_norm1)
+                y = torch.empty((rows, Cout), device=dev)
+                L_.call('dprnn_gemm_tc_affine_prelu', x, rb.conv1.weight.detach(), scale, shift,
+                        rb.prelu1.weight.detach(), y, Cout, rows, Cout, Cin, st)
+            else:
+                y = conv(x, rb.conv1, wr['c1'], Cin, Cout)
+                bn(rb.batch_norm1)
+                L_.call('dprnn_affine_prelu', y, scale, shift, rb.prelu1.weight.detach(), y, rows, Cout, st)
             y2 = conv(y, rb.conv2, wr['c2'], Cout, Cout)
             bn(rb.batch_norm2)
             skip = x if wr['down'] is None else conv(x, rb.conv_downsample, wr['down'], Cin, Cout)
