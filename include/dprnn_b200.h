@@ -158,6 +158,17 @@ int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias
                   int K, int epilogue, void* stats_partial, long rows_per_utt, float eps, float* mean_rstd,
                   void* stream);
 
+/* dprnn_gemm_tc as a persistent, pipelined kernel for the many-row 1x1 convolutions (W resident in shared memory,
+ * dynamic tile scheduling, TMEM double buffering, staged TMA stores): C[M,N_out] = epi(A @ W^T + bias).
+ * bias: [N], or per utterance [*, N] selected by row / bias_rows_per_utt (> 0) or bias_row_utt[row] (ragged);
+ * DPRNN_EPI_AFFINE_PRELU: prelu(acc * post_scale[n] + post_shift[n]).  dprnn_gemm_persist_supported() tells whether
+ * (operand type, N, K, epilogue) is built; workspace: dprnn_gemm_persist_workspace_bytes() bytes (scheduler ticket). */
+size_t dprnn_gemm_persist_workspace_bytes(void);
+int dprnn_gemm_persist_supported(int a_is_bf16, int N, int K, int epilogue);
+int dprnn_gemm_persist(const void* A, int a_is_bf16, const void* W, const float* bias, long bias_rows_per_utt,
+                       const int* bias_row_utt, const float* post_scale, const float* post_shift, const float* prelu_a,
+                       float* C, long ldc, int M, int N, int K, int epilogue, void* workspace, void* stream);
+
 /* 1x1 conv -> BatchNorm1d (eval: per-channel scale/shift from dprnn_batchnorm_affine) -> PReLU in one pass
  * (ResBlock, src/models/dprnn_spe.py:32-34): C[M,N] = prelu(A @ W^T * scale[n] + shift[n]); fp32 (TF32) operands,
  * N in {128,256}. */

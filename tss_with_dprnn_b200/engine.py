@@ -15,7 +15,7 @@ import torch
 from ._lib import lib
 from .ragged import RaggedMixin
 
-EPI_NONE, EPI_RELU, EPI_SIGMOID, EPI_GATED = 0, 1, 2, 3
+EPI_NONE, EPI_RELU, EPI_SIGMOID, EPI_GATED, EPI_AFFINE_PRELU = 0, 1, 2, 3, 4
 
 
 def _t(w: torch.Tensor) -> torch.Tensor:
@@ -173,20 +173,39 @@ class Engine(RaggedMixin):
                    int(rows_per_utt), p_scale, p_shift, p_add, rowscale, epi, self._stream())
         return out
 
-    def gemm_tc(self, A, W, M, N, K, bias=None, epi=EPI_NONE, out=None, stats=None, bias_rows_per_utt=0):
+    def gemm_tc(self, A, W, M, N, K, bias=None, epi=EPI_NONE, out=None, stats=None, bias_rows_per_utt=0,
+                bias_row_utt=None, post=None):
         """tcgen05 contraction; W in its native [N, K] layout (bf16 if A is bf16, else fp32 read as TF32).
-        stats = (rows_per_utt, eps) additionally returns mean/rstd of the following per-utterance norm."""
+        stats = (rows_per_utt, eps) additionally returns mean/rstd of the following per-utterance norm;
+        bias_rows_per_utt / bias_row_utt select a per-utterance bias; post = (scale, shift, prelu_a) applies
+        BatchNorm-eval affine + PReLU to the result (EPI_AFFINE_PRELU)."""
+        L_ = lib()
+        if post is not None:
+            epi = EPI_AFFINE_PRELU
         n_out = N // 2 if epi == EPI_GATED else N
         if out is None:
             out = torch.empty((M, n_out), device=A.device, dtype=torch.float32)
+        is_bf16 = int(A.dtype == torch.bfloat16)
+        if stats is None and L_.query('dprnn_gemm_persist_supported', is_bf16, N, K, epi):
+            ws = torch.empty(L_.query('dprnn_gemm_persist_workspace_bytes'), device=A.device, dtype=torch.uint8)
+            ps, psh, pa = post if post is not None else (None, None, None)
+            L_.call('dprnn_gemm_persist', A, is_bf16, W, bias, int(bias_rows_per_utt), bias_row_utt, ps, psh, pa, out,
+                    n_out, M, N, K, epi, ws, self._stream())
+            return out
+        if post is not None:
+            L_.call('dprnn_gemm_tc_affine_prelu', A, W, post[0], post[1], post[2], out, n_out, M, N, K, self._stream())
+            return out
+        if bias_row_utt is not None:
+            L_.call('dprnn_gemm_tc_ragged', A, is_bf16, W, bias, bias_row_utt, out, n_out, M, N, K, epi, self._stream())
+            return out
         part = mr = None
         rpu, eps = int(bias_rows_per_utt), 0.0
         if stats is not None:
             rpu, eps = stats
-            part = torch.empty(lib().query('dprnn_gemm_tc_stats_bytes', M), device=A.device, dtype=torch.uint8)
+            part = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', M), device=A.device, dtype=torch.uint8)
             mr = torch.empty((M // rpu, 2), device=A.device, dtype=torch.float32)
-        lib().call('dprnn_gemm_tc', A, int(A.dtype == torch.bfloat16), W, bias, out, n_out, M, N, K, epi, part,
-                   int(rpu), float(eps), mr, self._stream())
+        L_.call('dprnn_gemm_tc', A, is_bf16, W, bias, out, n_out, M, N, K, epi, part,
+                int(rpu), float(eps), mr, self._stream())
         return (out, mr) if stats is not None else out
 
     def utt_stats(self, x, B, elems, eps):
@@ -272,9 +291,8 @@ class Engine(RaggedMixin):
             if tc and not training:
                 # eval mode: the BatchNorm scale / shift are known before the conv -> conv + BN + PReLU in one pass
                 bn(None, rb.batch_norm1)
-                y = torch.empty((rows, Cout), device=dev)
-                L_.call('dprnn_gemm_tc_affine_prelu', x, rb.conv1.weight.detach(), scale, shift,
-                        rb.prelu1.weight.detach(), y, Cout, rows, Cout, Cin, st)
+                y = self.gemm_tc(x, rb.conv1.weight.detach(), rows, Cout, Cin,
+                                 post=(scale, shift, rb.prelu1.weight.detach()))
             else:
                 y = conv(x, rb.conv1, wr['c1'], Cin, Cout)
                 bn(y, rb.batch_norm1)

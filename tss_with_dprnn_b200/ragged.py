@@ -186,9 +186,8 @@ class RaggedMixin:
 
             if tc:          # same fused conv + BN + PReLU pass as the uniform eval path
                 bn(rb.batch_norm1)
-                y = torch.empty((rows, Cout), device=dev)
-                L_.call('dprnn_gemm_tc_affine_prelu', x, rb.conv1.weight.detach(), scale, shift,
-                        rb.prelu1.weight.detach(), y, Cout, rows, Cout, Cin, st)
+                y = self.gemm_tc(x, rb.conv1.weight.detach(), rows, Cout, Cin,
+                                 post=(scale, shift, rb.prelu1.weight.detach()))
             else:
                 y = conv(x, rb.conv1, wr['c1'], Cin, Cout)
                 bn(rb.batch_norm1)
@@ -249,11 +248,7 @@ class RaggedMixin:
         if self.precision == 'bf16' and N % 32 == 0 and F in (64, 128, 256):
             en = torch.empty_like(enc)
             L_.call('dprnn_prologue_apply_ragged', enc, en, TR, N, lay.frame_utt, s1, s0, addc, rowscale, st)
-            if bias_per_utt:
-                y = torch.empty((TR, F), device=dev)
-                L_.call('dprnn_gemm_tc_ragged', en, 0, W['bott_w_x'], bias, lay.frame_utt, y, F, TR, F, N, EPI_NONE, st)
-            else:
-                y = self.gemm_tc(en, W['bott_w_x'], TR, F, N, bias=bias)
+            y = self.gemm_tc(en, W['bott_w_x'], TR, F, N, bias=bias, bias_row_utt=lay.frame_utt if bias_per_utt else None)
             del en
         else:
             y = self._gemm_ragged(enc, W['bott_wt'], TR, F, N, lay.frame_utt, bias=bias, bias_per_utt=bias_per_utt,
