@@ -139,7 +139,7 @@ def workload_config(args):
         return {'workload': 'cfg3: DPRNN-Spe-IRA (cat) TSS inference on the full-length test-set length distribution '
                             f'(24000..111920 samples), length-sorted buckets of {args.batch} utterances packed as ragged '
                             'batches, buckets LPT-assigned to ranks; one step = one bucket',
-                'batch_per_gpu': args.batch, 'precision': args.precision, 'streams': 1,
+                'batch_per_gpu': args.batch, 'precision': args.precision, 'streams': args.streams,
                 'l2': 'no flush needed: each step streams >10 GB of intermediates through a 126 MB L2',
                 'parallelism': f'utterance sharding x{args.gpus}, no collective'}
     if args.workload == 'cfg4':
@@ -326,7 +326,7 @@ class Cfg3:
         m = s['mix_h'].to(self.dev, non_blocking=True)
         r = s['ref_h'].to(self.dev, non_blocking=True)
         est, _ = self.model.forward_ragged((m, s['Ts']), (r, s['Trs']))
-        flat = est[0]._base if est[0]._base is not None else torch.cat(est)     # estimates are views of one packed buffer
+        flat = torch.cat(est)
         s['out_h'].copy_(flat, non_blocking=True)
         torch.cuda.current_stream().synchronize()
 

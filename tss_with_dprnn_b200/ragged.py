@@ -335,8 +335,80 @@ class RaggedMixin:
         return [flat[lay.frame_off_h[b]:lay.frame_off_h[b + 1]] for b in range(lay.B)]
 
     # ------------------------------------------------------------------ whole-model forwards
+    def _as_list(self, waves, name):
+        """per-utterance 1-D views of a list / [B,T] tensor / packed (flat, lengths) pair"""
+        if isinstance(waves, tuple) and len(waves) == 2 and isinstance(waves[0], torch.Tensor) and waves[0].dim() == 1 \
+                and not isinstance(waves[1], torch.Tensor):
+            flat = self._check_input(waves[0], name)
+            lengths = [int(t) for t in waves[1]]
+            if sum(lengths) != flat.numel():
+                raise ValueError(f'{name}: the lengths do not add up to the packed waveform')
+            return list(flat.split(lengths))
+        return list(waves)
+
+    def _ragged_groups(self, n_utt, run):
+        """run(indices) -> (list of per-utterance tensors, [len(indices), C] tensor or None) for interleaved utterance
+        groups on concurrent streams (as Engine._run_groups); results are re-assembled in the caller's order."""
+        n = max(1, min(self.n_streams, n_utt))
+        if n == 1:
+            return run(list(range(n_utt)))
+        while len(self._streams) < n:
+            self._streams.append(torch.cuda.Stream(device=torch.cuda.current_device()))
+        main = torch.cuda.current_stream()
+        ready = torch.cuda.Event()
+        ready.record(main)
+        groups = [list(range(g, n_utt, n)) for g in range(n)]
+        results = []
+        for g, idx in enumerate(groups):
+            st = self._streams[g]
+            st.wait_event(ready)
+            with torch.cuda.stream(st):
+                res = run(idx)
+                done = torch.cuda.Event()
+                done.record(st)
+            main.wait_event(done)
+            for t in res[0]:
+                t.record_stream(main)
+            results.append(res)
+        ests = [None] * n_utt
+        second = None
+        if results[0][1] is not None:
+            second = torch.empty((n_utt,) + tuple(results[0][1].shape[1:]), device=results[0][1].device)
+        for idx, (est, extra) in zip(groups, results):
+            for j, b in enumerate(idx):
+                ests[b] = est[j]
+            if extra is not None:
+                second[torch.tensor(idx, device=second.device)] = extra
+        return ests, second
+
     def forward_bss_ragged(self, mixes):
         """list of [T_b] mixtures -> list of [2, T_b] estimates (DPRNNTasNet.forward per utterance, dprnn.py:271-283)."""
+        mixes = self._as_list(mixes, 'input')
+        with torch.no_grad():
+            return self._ragged_groups(len(mixes), lambda idx: (self._bss_ragged_group([mixes[i] for i in idx]), None))[0]
+
+    def forward_spe_ragged(self, mixes, refs, embedding=None):
+        """lists of [T_b] mixtures and [Tr_b] references -> (list of [T_b] estimates, logits [B, num_spks]);
+        DPRNNSpeTasNet.forward per utterance with aux_len = Tr_b (dprnn_spe.py:314-327, inferencer_spe.py:31-32)."""
+        mixes = self._as_list(mixes, 'input')
+        refs = None if embedding is not None else self._as_list(refs, 'aux')
+        if refs is not None and len(refs) != len(mixes):
+            raise ValueError('need one reference per mixture')
+        with torch.no_grad():
+            return self._ragged_groups(len(mixes), lambda idx: self._spe_ragged_group(
+                [mixes[i] for i in idx], None if refs is None else [refs[i] for i in idx],
+                None if embedding is None else embedding[torch.tensor(idx, device=embedding.device)]))
+
+    def forward_ira_ragged(self, mixes, refs):
+        """DPRNNSpeIRATasNet.forward per utterance (dprnn_spe_ira.py:53-115,179-190) on a packed batch."""
+        mixes, refs = self._as_list(mixes, 'input'), self._as_list(refs, 'aux')
+        if len(refs) != len(mixes):
+            raise ValueError('need one reference per mixture')
+        with torch.no_grad():
+            return self._ragged_groups(len(mixes), lambda idx: self._ira_ragged_group([mixes[i] for i in idx],
+                                                                                     [refs[i] for i in idx]))
+
+    def _bss_ragged_group(self, mixes):
         with torch.no_grad():
             flat, lay = self._pack_waves(mixes, 'input')
             enc = self.encode_ragged(flat, lay)
@@ -347,9 +419,7 @@ class RaggedMixin:
             outs = [self._split(self.decode_ragged(m, enc, lay), lay) for m in masks]
             return [torch.stack([outs[0][b], outs[1][b]]) for b in range(lay.B)]
 
-    def forward_spe_ragged(self, mixes, refs, embedding=None):
-        """lists of [T_b] mixtures and [Tr_b] references -> (list of [T_b] estimates, logits [B, num_spks]);
-        DPRNNSpeTasNet.forward per utterance with aux_len = Tr_b (dprnn_spe.py:314-327, inferencer_spe.py:31-32)."""
+    def _spe_ragged_group(self, mixes, refs, embedding=None):
         with torch.no_grad():
             flat, lay = self._pack_waves(mixes, 'input')
             sep, cfg = self.model.separation, self.model.cfg
@@ -371,8 +441,7 @@ class RaggedMixin:
             logits = self.small_linear(emb, sep.pred_linear, lay.B)
             return self._split(est, lay), logits
 
-    def forward_ira_ragged(self, mixes, refs):
-        """DPRNNSpeIRATasNet.forward per utterance (dprnn_spe_ira.py:53-115,179-190) on a packed batch."""
+    def _ira_ragged_group(self, mixes, refs):
         with torch.no_grad():
             flat, lay = self._pack_waves(mixes, 'input')
             rflat, rlay = self._pack_waves(refs, 'aux')
