@@ -90,6 +90,28 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # workloads
 # ----------------------------------------------------------------------------------------------------------
+def ncu_traffic_per_launch(kernel_substr):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed `ncu --set full` capture
+    (profiles/r1_top3_ncu_full.txt; B = 64 cfg-2 shape) - None if the file or the kernel is missing."""
+    try:
+        text = open(os.path.join(ROOT, 'profiles', 'r1_top3_ncu_full.txt')).read()
+    except OSError:
+        return None
+    unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
+    vals = []
+    for block in text.split('Kernel Name = ')[1:]:
+        if kernel_substr not in block.splitlines()[0]:
+            continue
+        tot = 0.0
+        for ln in block.splitlines():
+            if ln.startswith('dram__bytes_read.sum =') or ln.startswith('dram__bytes_write.sum ='):
+                _, rhs = ln.split('=')
+                v, u = rhs.split()
+                tot += float(v) * unit.get(u, 1.0)
+        vals.append(tot)
+    return sum(vals) / len(vals) if vals else None
+
+
 def load_test_set_lengths():
     """(mixture, reference) sample counts of the reference's 3 000 full-length test utterances
     (tests/golden/test_set_lengths.txt, extracted from datasets/tss/test_set.pkl)."""
@@ -436,7 +458,11 @@ def run_ours(args):
         flop_per_launch = flop_per_pos * wl.positions(0) / (2 if args.workload == 'cfg3' else 1)
         achieved = flop_per_launch * n_launch / (ms_lstm * 1e-3) / 1e12
         roofline = {'kernel': '+'.join(lstm_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
-                    'unit': 'TFLOP/s', 'frac': achieved / peak_tf, 'traffic': None,
+                    'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
+                    'traffic': (ncu_traffic_per_launch('lstm_tc_kernel') if args.workload == 'cfg2' and args.batch == 64
+                                and args.precision == 'bf16' else None),
+                    'traffic_note': 'DRAM read+write bytes per launch, ncu --set full (profiles/r1_top3_ncu_full.txt); '
+                                    'algorithmic: read xb 2 x 0.79 GB + write hb 1.59 GB = 3.18 GB',
                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (B200_PROFILING.md)',
                     'launch_ms_avg': ms_lstm / n_launch,
                     'share_of_step_single_stream': ms_lstm / sum(k['ms_total'] for k in per_kernel.values()),

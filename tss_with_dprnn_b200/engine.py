@@ -427,8 +427,9 @@ class Engine(RaggedMixin):
     def _half_norm(self, s, bi, which):
         blk = self.model.separation.dprnn_blocks[bi]
         g_, b_, _ = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
+        last = bi == len(self.model.separation.dprnn_blocks) - 1 and which == 1     # nothing reads the bf16 shadow then
         lib().call('dprnn_norm_residual_ybf16', s['ybuf'], s['x'], s['mr2'], g_, b_, s['B'], s['S'] * s['K'], s['F'],
-                   s['xb'], self._stream())
+                   None if last else s['xb'], self._stream())
 
     def _half_fp32(self, s, bi, which):
         """exact-fp32 mode: input projection GEMM, recurrence, Linear, statistics, norm + residual on CUDA cores."""
