@@ -149,6 +149,8 @@ KW4 = dict(KW, embeddings_size=256, fusion_type='att')
 
 
 def model_for(workload):
+    if workload == 'cfg1':
+        return 'DPRNNTasNet', {k: v for k, v in KW.items() if k != 'fusion_type'}
     if workload == 'cfg3':
         return 'DPRNNSpeIRATasNet', KW
     if workload == 'cfg4':
@@ -163,6 +165,12 @@ def workload_config(args):
                             'batches, buckets LPT-assigned to ranks; one step = one bucket',
                 'batch_per_gpu': args.batch, 'precision': args.precision, 'streams': args.streams,
                 'l2': 'no flush needed: each step streams >10 GB of intermediates through a 126 MB L2',
+                'parallelism': f'utterance sharding x{args.gpus}, no collective'}
+    if args.workload == 'cfg1':
+        return {'workload': f'cfg1: DPRNN-TasNet BSS forward, 2 speakers, one {args.samples / SR:g}-s 8 kHz mixture, batch '
+                            f'{args.batch} (the reference runs this configuration on the CPU: see cpu_baseline)',
+                'batch_per_gpu': args.batch, 'samples': args.samples, 'precision': args.precision, 'streams': 1,
+                'l2': 'L2 flushed between timed steps (256 MB write): one utterance fits the 126 MB L2',
                 'parallelism': f'utterance sharding x{args.gpus}, no collective'}
     if args.workload == 'cfg4':
         return {'workload': f'cfg4: DPRNN-RawNet3 (attention fusion) TSS inference, {args.samples / SR:g}-s mix @ 8 kHz + '
@@ -190,6 +198,10 @@ def cpu_forward_fn(workload):
     cls, kw = model_for(workload)
     if workload != 'cfg4' and os.path.isdir(os.path.join(ref_root, 'src', 'models')):
         sys.path.insert(0, ref_root)
+        if cls == 'DPRNNTasNet':
+            from src.models.dprnn import DPRNNTasNet as RefModel
+            model = RefModel(**kw).eval()
+            return 'reference', (lambda mix, ref, rl: model(mix))
         if cls == 'DPRNNSpeIRATasNet':
             from src.models.dprnn_spe_ira import DPRNNSpeIRATasNet as RefModel
         else:
@@ -203,6 +215,8 @@ def cpu_forward_fn(workload):
         from oracle import rawnet_oracle as RO
         cfg4 = O.Config(fusion_type='att')
         return 'port', (lambda mix, ref, rl: RO.rawnet_tasnet_forward(mix, ref, sd, cfg4)[0])
+    if workload == 'cfg1':
+        return 'port', (lambda mix, ref, rl: O.tasnet_forward(mix, sd, O.Config()))
     cfg = O.Config(fusion_type='cat')
     fwd = O.ira_forward if cls == 'DPRNNSpeIRATasNet' else O.spe_forward
     return 'port', (lambda mix, ref, rl: fwd(mix, ref, rl, sd, cfg)[0])
@@ -292,6 +306,28 @@ class Cfg2:
 
     def bytes(self, i):
         return 2 * self.B * self.T * 4, self.B * self.T * 4
+
+
+class Cfg1(Cfg2):
+    """BASELINE.json configs[0]: DPRNN-TasNet, one 3-s mixture (what the reference's example / test loop runs, B = 1)."""
+
+    def __init__(self, args, model, rank, dev):
+        super().__init__(args, model, rank, dev)
+        self.out_h = torch.empty((self.B, 2, self.T), dtype=torch.float32).pin_memory()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > L2: written between timed steps
+
+    def resident(self, i):
+        self.flush.zero_()
+        return self.model(self.mix)
+
+    def e2e(self, i):
+        self.flush.zero_()
+        est = self.model(self.mix_h.to(self.dev, non_blocking=True))
+        self.out_h.copy_(est, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    def bytes(self, i):
+        return self.B * self.T * 4, 2 * self.B * self.T * 4
 
 
 class Cfg4(Cfg2):
@@ -386,6 +422,8 @@ def run_ours(args):
         wl = Cfg3(args, model, rank, world, dev, args.steps)
     elif args.workload == 'cfg4':
         wl = Cfg4(args, model, rank, dev)
+    elif args.workload == 'cfg1':
+        wl = Cfg1(args, model, rank, dev)
     else:
         wl = Cfg2(args, model, rank, dev)
 
@@ -499,8 +537,8 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4'],
-                    help='cfg2 (headline): DPRNN-Spe cat, 3-s batch 64; cfg3: DPRNN-Spe-IRA on the ragged test-set lengths; '
+    ap.add_argument('--workload', default='cfg2', choices=['cfg1', 'cfg2', 'cfg3', 'cfg4'],
+                    help='cfg1: DPRNN-TasNet B=1; cfg2 (headline): DPRNN-Spe cat, 3-s batch 64; cfg3: DPRNN-Spe-IRA on the ragged test-set lengths; '
                          'cfg4: DPRNN-RawNet3 att, batch 16 per GPU')
     ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--streams', type=int, default=int(os.environ.get('DPRNN_STREAMS', '3')),
@@ -512,7 +550,9 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = 16 if args.workload == 'cfg4' else 64
+        args.batch = {'cfg1': 1, 'cfg4': 16}.get(args.workload, 64)
+    if args.workload == 'cfg1':
+        args.streams = 1
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3
     if args.impl == 'reference':
