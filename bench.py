@@ -124,18 +124,14 @@ def load_test_set_lengths():
     return rows
 
 
-def cfg3_buckets(world, bucket=64, K=250, P=125):
+def cfg3_buckets(world, bucket=64):
     """Length-sorted buckets of `bucket` utterances, assigned to ranks by the LPT rule on their chunk count
     (SURVEY.md section 8d cfg 3).  Returns per rank a list of buckets, each a list of (T, Tr)."""
-    rows = sorted(load_test_set_lengths())
-    buckets = [rows[i:i + bucket] for i in range(0, len(rows), bucket)]
-    cost = lambda bk: sum((t - 1 + K) // P + 1 for t, _ in bk)
-    load, per_rank = [0] * world, [[] for _ in range(world)]
-    for bk in sorted(buckets, key=cost, reverse=True):
-        r = load.index(min(load))
-        per_rank[r].append(bk)
-        load[r] += cost(bk)
-    return per_rank
+    from tss_with_dprnn_b200.sharding import chunk_count, length_buckets, lpt_assign
+    rows = load_test_set_lengths()
+    buckets = [[rows[i] for i in idx] for idx in length_buckets([t for t, _ in rows], bucket)]
+    costs = [sum(chunk_count(t) for t, _ in bk) for bk in buckets]
+    return [[buckets[i] for i in idx] for idx in lpt_assign(costs, world)]
 
 
 def pick_steps(buckets, n):
@@ -440,24 +436,17 @@ def run_ours(args):
             ev1.record()
             barrier()
             ms = ev0.elapsed_time(ev1)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), L.launches - n0
+        return ms, L.launches - n0
 
-    def total_over_ranks(v):
-        t = torch.tensor([v], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
-
+    from tss_with_dprnn_b200.sharding import reduce_timing
+    audio_local = sum(wl.audio(i) for i in range(args.steps))
     with ClockSampler(local) as clk:
         # every distinct step is warmed up at least once (ragged layouts, tensor maps, allocator pools)
-        ms_total, launches = timed(wl.resident, args.steps, max(args.warmup, wl.n_steps))
+        ms_local, launches = timed(wl.resident, args.steps, max(args.warmup, wl.n_steps))
     clocks = clk.summary()
-    ms_e2e, _ = timed(wl.e2e, args.steps, max(1, wl.n_steps))
-
-    audio_steps = total_over_ranks(sum(wl.audio(i) for i in range(args.steps)))     # whole job, all ranks
+    ms_total, audio_steps = reduce_timing(ms_local, audio_local, dev)     # max over ranks of device time, whole-job audio
+    ms_local_e2e, _ = timed(wl.e2e, args.steps, max(1, wl.n_steps))
+    ms_e2e, _ = reduce_timing(ms_local_e2e, audio_local, dev)
     value = audio_steps / (ms_total / 1e3)
     e2e_value = audio_steps / (ms_e2e / 1e3)
     h2d = sum(wl.bytes(i)[0] for i in range(args.steps)) / args.steps

@@ -1,0 +1,69 @@
+"""The N > 1 path on the CPU (gloo, world_size 2): utterance sharding has no data-path collective, so what runs across
+ranks is the deterministic shard assignment and the timing reduction bench.py / an evaluation driver performs."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from tss_with_dprnn_b200.sharding import chunk_count, length_buckets, lpt_assign, reduce_timing  # noqa: E402
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    import bench
+    per_rank = bench.cfg3_buckets(world, 64)
+    mine = per_rank[rank]
+    # every rank computes the same global assignment; exchange a checksum of the own shard and the shard sizes
+    ids = torch.tensor([sum(t for bk in mine for t, _ in bk), sum(len(bk) for bk in mine),
+                        sum(chunk_count(t) for bk in mine for t, _ in bk)], dtype=torch.int64)
+    gathered = [torch.zeros_like(ids) for _ in range(world)]
+    dist.all_gather(gathered, ids)
+    ms, work = reduce_timing(10.0 + rank, float(ids[0]) / 8000, torch.device('cpu'))
+    q.put((rank, [g.tolist() for g in gathered], ms, work))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_two_rank_sharding_and_timing_reduction():
+    world, port = 2, 29655
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    import bench
+    rows = bench.load_test_set_lengths()
+    (r0, g0, ms0, w0), (r1, g1, ms1, w1) = res
+    assert g0 == g1                                           # both ranks see the same gathered picture
+    assert g0[0][0] + g0[1][0] == sum(t for t, _ in rows)     # the shards partition the test set (samples ...
+    assert g0[0][1] + g0[1][1] == len(rows) == 3000           # ... and utterances)
+    c0, c1 = g0[0][2], g0[1][2]
+    assert abs(c0 - c1) / max(c0, c1) < 0.03                  # LPT balance on the masker cost (chunk count)
+    assert ms0 == ms1 == 11.0                                 # max over ranks
+    assert abs(w0 - sum(t for t, _ in rows) / 8000) < 1e-6 and w0 == w1      # whole-job audio seconds
+
+
+def test_lpt_and_buckets_properties():
+    lengths = [24000 + 37 * i % 9000 for i in range(1000)]
+    buckets = length_buckets(lengths, 64)
+    assert sorted(i for b in buckets for i in b) == list(range(1000))
+    assert all(max(lengths[i] for i in a) <= min(lengths[i] for i in b) for a, b in zip(buckets, buckets[1:]))
+    costs = [sum(chunk_count(lengths[i]) for i in b) for b in buckets]
+    for world in (1, 2, 4, 8):
+        parts = lpt_assign(costs, world)
+        assert sorted(i for p in parts for i in p) == list(range(len(buckets)))
+        loads = [sum(costs[i] for i in p) for p in parts]
+        assert max(loads) - min(loads) <= max(costs)
+    assert chunk_count(24000) == 194 and chunk_count(111920) == 898
