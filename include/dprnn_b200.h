@@ -275,6 +275,17 @@ int dprnn_lstm_inter_bf16_ragged(const void* x, const void* w_packed, const floa
                                  long total_chunks, int K, const void* utt_jobs, int n_utt, int hidden, int ndir,
                                  int fast_act, void* stream);
 
+/* RawNet3 front-end of DPRNN-RawNet (src/models/rawnet/RawNet3.py:23-32,76-83, RawNetBasicBlock.py:8-28; cfg 4):
+ * PreEmphasis -> InstanceNorm1d(1, eps 1e-4, affine in_w/in_b) -> ParamSincFB(n_filters, kernel, stride) -> abs -> log(.+1e-6)
+ * -> minus time mean.  wave [B,T] (16 kHz) -> out [B, T', n_filters] channels-last, T' = (T-kernel)/stride+1.
+ * low_hz/band_hz [n_filters/2], window/n_half [kernel/2]: the filterbank's parameters and buffers; filt_scratch
+ * [kernel*n_filters] floats, stats_scratch [2B] floats.  The filter formula restates asteroid_filterbanks 0.4.0
+ * (third-party; parity unpinned). */
+int dprnn_rawnet_frontend(const float* wave, int B, long T, const float* in_w, const float* in_b, const float* low_hz,
+                          const float* band_hz, const float* window, const float* n_half, int n_filters, int kernel,
+                          int stride, float sample_rate, float* filt_scratch, float* stats_scratch, float* out,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

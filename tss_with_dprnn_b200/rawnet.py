@@ -3,11 +3,13 @@
 Parameter containers with the reference's module tree (so ``chkpts/dprnn-rawnet/*.pt`` strict-load and seeded
 default initialisation reproduces the reference's weights), plus the forward.
 
-STAGE 1: RawNet3 is not on north_star's kernel list (~8 % of the model's
-flops, run once per enrolment utterance); its forward here is a restatement with torch ops ON THE GPU (cuDNN / cuBLAS
-library calls) that produces the [B, nOut] embedding - everything downstream of the embedding (attention fusion, the
-whole masker, decoder) is the hand-written CUDA path.  Hand kernels for the sinc front-end and the Res2Net blocks are
-the first "next" row of section 8f.  There is no CPU path: the tensors must be CUDA tensors.
+The front-end (PreEmphasis, InstanceNorm, parameterised sinc filterbank, log-abs, mean normalisation) runs as
+hand-written kernels (csrc/rawnet.cu).  STAGE 1 for the rest: RawNet3 is not
+on north_star's kernel list (~8 % of the model's flops, run once per enrolment utterance); its Res2Net blocks and the
+attentive statistics pooling are restated here with torch ops ON THE GPU (cuDNN / cuBLAS library calls) and produce the
+[B, nOut] embedding - everything downstream of the embedding (attention fusion, the whole masker, decoder) is the
+hand-written CUDA path.  Hand kernels for the Res2Net blocks are the first "next" row of section 8f.  There is no CPU
+path: the tensors must be CUDA tensors.
 
 The sinc front-end restates ``asteroid_filterbanks==0.4.0`` ``ParamSincFB`` / ``Encoder`` (third-party, not vendored in
 the reference, not installable here): parity for that part is UNPINNED.
@@ -20,6 +22,8 @@ import numpy as np
 import torch
 import torch.nn.functional as F
 from torch import nn
+
+from ._lib import lib
 
 
 class _PreEmphasis(nn.Module):
@@ -150,13 +154,18 @@ class RawNet3(nn.Module):
 
     def _embed(self, x):
         bn = lambda t, m: F.batch_norm(t, m.running_mean, m.running_var, m.weight, m.bias, False, 0.0, m.eps)
-        xi = F.pad(x.unsqueeze(1), (1, 0), 'reflect')
-        xi = F.conv1d(xi, self.preprocess[0].flipped_filter)
-        inorm = self.preprocess[1]
-        xi = F.instance_norm(xi, None, None, inorm.weight, inorm.bias, True, 0.0, inorm.eps)
-        fb = self.conv1.filterbank
-        f = torch.log(torch.abs(F.conv1d(xi, fb.filters(), stride=fb.stride)) + 1e-6)
-        f = f - f.mean(-1, keepdim=True)
+        # front-end (PreEmphasis, InstanceNorm, sinc filterbank, log-abs, mean normalisation): hand-written kernels
+        fb, inorm = self.conv1.filterbank, self.preprocess[1]
+        x = x.contiguous()
+        B, T = x.shape
+        Tp = (T - fb.kernel_size) // fb.stride + 1
+        feat = torch.empty((B, Tp, fb.n_filters), device=x.device, dtype=torch.float32)
+        filt = torch.empty(fb.kernel_size * fb.n_filters, device=x.device, dtype=torch.float32)
+        stats = torch.empty(2 * B, device=x.device, dtype=torch.float32)
+        lib().call('dprnn_rawnet_frontend', x, B, T, inorm.weight.detach(), inorm.bias.detach(), fb.low_hz_.detach(),
+                   fb.band_hz_.detach(), fb.window_, fb.n_, fb.n_filters, fb.kernel_size, fb.stride,
+                   float(fb.sample_rate), filt, stats, feat, torch.cuda.current_stream().cuda_stream)
+        f = feat.permute(0, 2, 1)                     # [B, 256, T'] view for the (stage-1) Res2Net blocks below
         x1 = self.layer1.run(f)
         x2 = self.layer2.run(x1)
         x1p = F.max_pool1d(x1, 3)
