@@ -286,6 +286,21 @@ int dprnn_rawnet_frontend(const float* wave, int B, long T, const float* in_w, c
                           int stride, float sample_rate, float* filt_scratch, float* stats_scratch, float* out,
                           void* stream);
 
+/* ---- the callers' side of the path ---- */
+
+/* SI-SDR in dB per utterance (asteroid recipe: zero-mean, eps 1e-8; src/trainers/trainer_spe.py:39,
+ * src/inferencers/inferencer_spe.py:37-43).  Utterance b = samples [off[b], off[b]+len[b]) of est / target, or
+ * [b*uniform_len, +uniform_len) when off == len == NULL. */
+int dprnn_si_sdr(const float* est, const float* target, const long* off, const long* len, long uniform_len, int B,
+                 float* out_db, void* stream);
+/* torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam(lr, (beta1, beta2), eps, weight_decay)
+ * .step() over one flat fp32 parameter / gradient buffer (src/trainers/trainer.py:42-43,115-116; step >= 1 is Adam's
+ * step count; max_norm <= 0 disables clipping).  total_norm_out[0] receives the global gradient norm. */
+size_t dprnn_clip_adam_workspace_bytes(void);
+int dprnn_clip_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long n, float lr,
+                         float beta1, float beta2, float eps, float weight_decay, float max_norm, int step,
+                         void* workspace, float* total_norm_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

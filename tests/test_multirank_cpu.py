@@ -67,3 +67,39 @@ def test_lpt_and_buckets_properties():
         loads = [sum(costs[i] for i in p) for p in parts]
         assert max(loads) - min(loads) <= max(costs)
     assert chunk_count(24000) == 194 and chunk_count(111920) == 898
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from tss_with_dprnn_b200.dp import FlatParams, allreduce_mean
+    torch.manual_seed(0)                                     # identical replicas
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.PReLU(), torch.nn.Linear(16, 4))
+    net[1].weight.requires_grad_(False)                      # frozen parameters stay out of the flat buffer
+    fp = FlatParams(net)
+    for _, p in fp.named:
+        p.grad.fill_(float(rank + 1))
+    allreduce_mean(fp.grad)
+    q.put((rank, fp.numel, float(fp.grad.min()), float(fp.grad.max()),
+           bool(net[0].weight.data_ptr() == fp.flat.data_ptr())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_flat_gradient_allreduce_two_ranks():
+    """cfg 5's single exchange step: mean all-reduce of one flat gradient buffer (gloo on the CPU here, NCCL on GPUs)."""
+    world, port = 2, 29656
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    for rank, numel, lo, hi, aliased in res:
+        assert numel == 8 * 16 + 16 + 16 * 4 + 4             # PReLU weight excluded
+        assert lo == hi == 1.5                               # mean of 1 and 2 on both ranks
+        assert aliased                                       # parameters are views of the flat buffer

@@ -1,0 +1,71 @@
+"""Data-parallel step plumbing for the training config (cfg 5): ONE exchange step per iteration -
+an all-reduce (mean) of a single flat fp32 gradient buffer (4.04 M parameters = 16.2 MB for the FiLM model) over NCCL /
+NVLink - followed by gradient clipping and Adam as one fused kernel over the same flat buffers
+(src/trainers/trainer.py:42-43,115-116; scripts/train/config_tss.yaml:36-39,59).
+
+The reference has no distributed code (single process, single GPU); this is new functionality next to the path.  The
+backward kernels that fill the gradient buffer are NOT built yet, so cfg 5 cannot run end to end; this module and its
+tests cover the exchange step and the optimiser so that the backward can be dropped in.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import lib
+
+
+class FlatParams:
+    """The trainable parameters of a module as views into one contiguous fp32 buffer (plus a same-shaped gradient
+    buffer), in ``named_parameters()`` order restricted to ``requires_grad`` - the set the reference hands to Adam
+    (src/trainers/trainer.py:42-43: the frozen ``separation.average.*`` of the attention fusion are excluded)."""
+
+    def __init__(self, module: torch.nn.Module):
+        self.named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
+        if not self.named:
+            raise ValueError('no trainable parameters')
+        dev = self.named[0][1].device
+        self.numel = sum(p.numel() for _, p in self.named)
+        self.flat = torch.empty(self.numel, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        off = 0
+        for _, p in self.named:
+            n = p.numel()
+            self.flat[off:off + n].copy_(p.detach().reshape(-1))
+            p.data = self.flat[off:off + n].view_as(p)              # parameters now alias the flat buffer
+            p.grad = self.grad[off:off + n].view_as(p)
+            off += n
+
+    def zero_grad(self):
+        self.grad.zero_()
+
+
+def allreduce_mean(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
+    """The exchange step: in-place mean over the ranks of the flat gradient buffer (one collective per iteration;
+    NCCL on GPU tensors, gloo in the CPU tests)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
+        flat_grad.div_(dist.get_world_size(group))
+    return flat_grad
+
+
+class ClipAdam:
+    """clip_grad_norm_(max_norm) + Adam(lr, betas, eps, weight_decay) over FlatParams, one fused pass on the GPU."""
+
+    def __init__(self, fp: FlatParams, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, max_norm=5.0):
+        if not fp.flat.is_cuda:
+            raise RuntimeError('ClipAdam runs on the GPU (no CPU path)')
+        self.fp, self.lr, self.betas, self.eps, self.wd, self.max_norm = fp, lr, betas, eps, weight_decay, max_norm
+        self.exp_avg = torch.zeros_like(fp.flat)
+        self.exp_avg_sq = torch.zeros_like(fp.flat)
+        self.step_count = 0
+        self.ws = torch.empty(lib().query('dprnn_clip_adam_workspace_bytes'), dtype=torch.uint8, device=fp.flat.device)
+        self.total_norm = torch.zeros(1, device=fp.flat.device)
+
+    def step(self):
+        self.step_count += 1
+        lib().call('dprnn_clip_adam_step', self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.fp.numel,
+                   float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
+                   float(self.max_norm), self.step_count, self.ws, self.total_norm,
+                   torch.cuda.current_stream().cuda_stream)
+        return self.total_norm
