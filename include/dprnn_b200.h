@@ -27,7 +27,8 @@ const char* dprnn_last_error(void);
 const char* dprnn_build_info(void);
 
 /* epilogues of dprnn_gemm_* */
-enum { DPRNN_EPI_NONE = 0, DPRNN_EPI_RELU = 1, DPRNN_EPI_SIGMOID = 2, DPRNN_EPI_GATED = 3, DPRNN_EPI_AFFINE_PRELU = 4 };
+enum { DPRNN_EPI_NONE = 0, DPRNN_EPI_RELU = 1, DPRNN_EPI_SIGMOID = 2, DPRNN_EPI_GATED = 3, DPRNN_EPI_AFFINE_PRELU = 4,
+       DPRNN_EPI_RELU_AFFINE = 5 };
 
 /* Encoder.forward, src/models/encoder_decoder.py:25-33 (Conv1d(1->N, ksz, stride, bias=False) + ReLU).
  * wave [B,T], w [N,ksz] -> enc [B, L=(T-ksz)/stride+1, N]. */
@@ -285,6 +286,42 @@ int dprnn_rawnet_frontend(const float* wave, int B, long T, const float* in_w, c
                           const float* band_hz, const float* window, const float* n_half, int n_filters, int kernel,
                           int stride, float sample_rate, float* filt_scratch, float* stats_scratch, float* out,
                           void* stream);
+
+/* ---- RawNet3 Res2Net blocks + attentive statistics pooling (src/models/rawnet/RawNetBasicBlock.py:111-142,
+ * RawNet3.py:88-134), channels-last [B*T, C] activations ---- */
+
+/* conv (as a contraction over K, any K with K*4 % 128 == 0) -> + bias -> ReLU -> BatchNorm-eval affine (-> + residual):
+ * C[M,N] = relu(A @ W^T + bias) * scale[n] + shift[n] (+ residual[row*ldres + n]); TF32 operands, N in {128, 256};
+ * scale/shift may be NULL (plain ReLU); bias_rows_per_utt > 0: bias is per utterance [M/rows, N].  (Bottle2neck: conv1/bn1, convs[i]/bns[i], conv3/bn3 + residual; layer4;
+ * attention[0..2].) */
+int dprnn_gemm_tc_relu_affine(const void* A, const void* W, const float* bias, long bias_rows_per_utt,
+                              const float* scale, const float* shift, const float* residual, long ldres, float* C,
+                              long ldc, int M, int N, int K, void* stream);
+/* Exact-fp32 twin on CUDA cores (parity mode); Wt = transposed weight [K, N] with row stride ldw, A / C may be column
+ * slices (lda / ldc). */
+int dprnn_gemm_f32_relu_affine(const float* A, long lda, const float* Wt, long ldw, const float* bias,
+                               long bias_rows_per_utt, const float* scale, const float* shift, const float* residual,
+                               long ldres, float* C, long ldc, int M, int N, int K, void* stream);
+/* im2col of a kernel-3 dilated conv with the Res2Net input sum: col[r, tap*C + c] = (a + b)[r + (tap-1)*dil, c] inside
+ * the utterance (T rows each), 0 outside; b may be NULL.  a, b: column slices of [rows, ld*] buffers. */
+int dprnn_res2_gather(const float* a, long lda, const float* b, long ldb, float* col, long rows, long T, int C, int dil,
+                      void* stream);
+/* MaxPool1d(k) over time, optional second operand added first: out[b,t',c] = max_i (x (+ y))[b, k*t'+i, c];
+ * out may be a column slice (ldo). */
+int dprnn_maxpool_time(const float* x, const float* y, float* out, long ldo, int B, long T, int C, int k, void* stream);
+/* per (utterance, channel) over T rows: mean -> mean[b,c]; with std != NULL also sqrt(clamp(unbiased var, 1e-4, 1e4)). */
+int dprnn_col_mean_std(const float* x, float* mean, float* std, int B, long T, int C, void* stream);
+/* AFMS (RawNetBasicBlock.py:48-55): out = (x + alpha[c]) * gate[b,c]; out may be a column slice (ldo). */
+int dprnn_afms_apply(const float* x, const float* alpha, const float* gate, float* out, long ldo, int B, long T, int C,
+                     void* stream);
+/* out = a + b elementwise (n % 4 == 0). */
+int dprnn_add2(const float* a, const float* b, float* out, long n, void* stream);
+/* out[b,c] = act(x[b,c] * scale[c] + shift[c]); act: 0 none, 1 sigmoid. */
+int dprnn_affine_vec(const float* x, const float* scale, const float* shift, float* out, int B, int C, int act,
+                     void* stream);
+/* Attentive statistics pooling (RawNet3.py:119-124): w = softmax over time of logits[b,:,c];
+ * out[b, c] = sum_t x w, out[b, C + c] = sqrt(clamp(sum_t x^2 w - mu^2, 1e-4, 1e4)). */
+int dprnn_att_stats_pool(const float* x, const float* logits, float* out, int B, long T, int C, void* stream);
 
 /* ---- the callers' side of the path ---- */
 

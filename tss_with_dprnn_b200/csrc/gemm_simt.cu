@@ -22,6 +22,7 @@ struct GemmParams {
     const float* p_scale; const float* p_shift; const float* p_add; const float* rowscale;
     int epi;
     const int* row_utt;      // ragged batches: utterance of every row (else NULL: row / rows_per_utt)
+    const float *post_scale, *post_shift, *residual; long ldres;     // DPRNN_EPI_RELU_AFFINE
 };
 
 __device__ __forceinline__ float apply_act(float v, int epi) {
@@ -145,6 +146,11 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(const GemmParams p) {
                 for (int j = 0; j < 4; ++j) {
                     const float v = acc[i][h * 4 + j] + (bias ? bias[c + j] * p.bias_scale : 0.f);
                     o[j] = apply_act(v, p.epi);
+                    if (p.epi == DPRNN_EPI_RELU_AFFINE) {
+                        o[j] = fmaxf(v, 0.f);
+                        if (p.post_scale) o[j] = fmaf(o[j], p.post_scale[c + j], p.post_shift[c + j]);
+                        if (p.residual) o[j] += p.residual[row * p.ldres + c + j];
+                    }
                 }
                 *reinterpret_cast<float4*>(p.C + row * p.ldc + c) = make_float4(o[0], o[1], o[2], o[3]);
             }
@@ -169,7 +175,7 @@ static int gemm_f32_impl(const float* A, long lda, const float* Wt, long ldw, fl
     if ((bias_per_utt || p_scale || p_add) && !row_utt) DPRNN_CHECK_ARG(rows_per_utt > 0);
     if (rows_per_utt <= 0) rows_per_utt = M;
     GemmParams p{A, lda, Wt, ldw, C, ldc, M, N, K, bias, bias_per_utt, bias_scale, rows_per_utt,
-                 p_scale, p_shift, p_add, rowscale, epilogue, row_utt};
+                 p_scale, p_shift, p_add, rowscale, epilogue, row_utt, nullptr, nullptr, nullptr, 0};
     dim3 grid(cdiv(M, BM), cdiv(N, BN));
     gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
     DPRNN_CHECK_LAUNCH();
@@ -191,4 +197,23 @@ extern "C" int dprnn_gemm_f32_ragged(const float* A, long lda, const float* Wt, 
     DPRNN_CHECK_ARG(row_utt);
     return gemm_f32_impl(A, lda, Wt, ldw, C, ldc, M, N, K, bias, bias_per_utt, bias_scale, 0, p_scale, p_shift, p_add,
                          rowscale, epilogue, row_utt, stream);
+}
+
+// exact-fp32 twin of dprnn_gemm_tc_relu_affine (Wt is the transposed weight [K, N], row stride ldw)
+extern "C" int dprnn_gemm_f32_relu_affine(const float* A, long lda, const float* Wt, long ldw, const float* bias,
+                                          long bias_rows_per_utt, const float* scale, const float* shift,
+                                          const float* residual, long ldres, float* C, long ldc, int M, int N, int K,
+                                          void* stream) {
+    DPRNN_CHECK_ARG(A && Wt && C && M > 0 && N > 0 && K > 0);
+    DPRNN_CHECK_ARG(N % 4 == 0 && K % 4 == 0 && lda % 4 == 0 && ldw % 4 == 0 && ldc % 4 == 0);
+    DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)Wt | (uintptr_t)C) % 16 == 0);
+    DPRNN_CHECK_ARG((scale == nullptr) == (shift == nullptr));
+    DPRNN_CHECK_ARG(bias_rows_per_utt == 0 || (bias && bias_rows_per_utt > 0));
+    GemmParams p{A, lda, Wt, ldw, C, ldc, M, N, K, bias, bias_rows_per_utt > 0 ? 1 : 0, 1.0f,
+                 bias_rows_per_utt > 0 ? bias_rows_per_utt : (long)M, nullptr, nullptr, nullptr, nullptr,
+                 DPRNN_EPI_RELU_AFFINE, nullptr, scale, shift, residual, ldres};
+    dim3 grid(cdiv(M, BM), cdiv(N, BN));
+    gemm_simt_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
 }

@@ -52,7 +52,8 @@ struct GemmTcArgs {
     long rows_per_utt;
     int bias_per_utt;          // bias is [M / rows_per_utt, N] (a per-utterance bias: the 'cat' speaker fusion, A.6)
     const int* row_utt;        // ragged batches: utterance of every row (else NULL: row / rows_per_utt)
-    const float *post_scale, *post_shift, *prelu_a;      // DPRNN_EPI_AFFINE_PRELU
+    const float *post_scale, *post_shift, *prelu_a;      // DPRNN_EPI_AFFINE_PRELU / DPRNN_EPI_RELU_AFFINE
+    const float* residual; long ldres;                    // DPRNN_EPI_RELU_AFFINE: added after the affine
 };
 
 template <int kElem, int N, int EPI>
@@ -129,7 +130,6 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                 for (int j = 0; j < 32; ++j)
                     v[j] = gt_tanh(v[j] + __ldg(a.bias + c0 + j)) * gt_sigmoid(g[j] + __ldg(a.bias + N_OUT + c0 + j));
             } else {
-#pragma unroll
                 const float* bias = a.bias;
                 if (bias && a.bias_per_utt)
                     bias += (row < a.M ? (a.row_utt ? (long)__ldg(a.row_utt + row) : row / a.rows_per_utt) : 0) * (long)N;
@@ -141,6 +141,11 @@ __global__ void __launch_bounds__(192) gemm_tc_kernel(const __grid_constant__ CU
                     if constexpr (EPI == DPRNN_EPI_AFFINE_PRELU) {
                         x = fmaf(x, __ldg(a.post_scale + c0 + j), __ldg(a.post_shift + c0 + j));
                         x = x >= 0.f ? x : __ldg(a.prelu_a) * x;
+                    }
+                    if constexpr (EPI == DPRNN_EPI_RELU_AFFINE) {
+                        x = fmaxf(x, 0.f);
+                        if (a.post_scale) x = fmaf(x, __ldg(a.post_scale + c0 + j), __ldg(a.post_shift + c0 + j));
+                        if (a.residual && row < a.M) x += __ldg(a.residual + row * a.ldres + c0 + j);
                     }
                     v[j] = x;
                 }
@@ -225,6 +230,9 @@ static int dispatch_epi(const void* A, const void* W, const GemmTcArgs& args, in
         case DPRNN_EPI_AFFINE_PRELU:
             if constexpr (kElem == 4 && N >= 128) return launch_gemm_tc<kElem, N, DPRNN_EPI_AFFINE_PRELU>(A, W, args, K, st);
             break;
+        case DPRNN_EPI_RELU_AFFINE:
+            if constexpr (kElem == 4 && N >= 128) return launch_gemm_tc<kElem, N, DPRNN_EPI_RELU_AFFINE>(A, W, args, K, st);
+            break;
         default: break;
     }
     set_error("dprnn_gemm_tc: epilogue %d not built for N=%d", epi, N);
@@ -250,7 +258,7 @@ static int gemm_tc_impl(const void* A, int a_is_bf16, const void* W, const float
     const int bias_per_utt = (!stats_partial && (rows_per_utt > 0 || row_utt) && bias) ? 1 : 0;
     if (bias_per_utt) DPRNN_CHECK_ARG((row_utt || M % rows_per_utt == 0) && epilogue != DPRNN_EPI_GATED);
     GemmTcArgs args{bias, C, ldc, M, K * elem / 128, (float2*)stats_partial, rows_per_utt, bias_per_utt, row_utt,
-                    nullptr, nullptr, nullptr};
+                    nullptr, nullptr, nullptr, nullptr, 0};
     if (stats_partial) {
         DPRNN_CHECK_ARG(rows_per_utt > 0 && M % rows_per_utt == 0 && mean_rstd && epilogue == DPRNN_EPI_NONE);
     }
@@ -293,7 +301,20 @@ extern "C" int dprnn_gemm_tc_affine_prelu(const void* A, const void* W, const fl
                                           const float* prelu_a, float* C, long ldc, int M, int N, int K, void* stream) {
     DPRNN_CHECK_ARG(A && W && scale && shift && prelu_a && C && M > 0 && (N == 128 || N == 256) && K > 0 && ldc % 4 == 0);
     DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) % 16 == 0 && (K * 4) % 128 == 0);
-    GemmTcArgs args{nullptr, C, ldc, M, K * 4 / 128, nullptr, 0, 0, nullptr, scale, shift, prelu_a};
+    GemmTcArgs args{nullptr, C, ldc, M, K * 4 / 128, nullptr, 0, 0, nullptr, scale, shift, prelu_a, nullptr, 0};
     return N == 128 ? dispatch_epi<4, 128>(A, W, args, K, DPRNN_EPI_AFFINE_PRELU, (cudaStream_t)stream)
                     : dispatch_epi<4, 256>(A, W, args, K, DPRNN_EPI_AFFINE_PRELU, (cudaStream_t)stream);
+}
+
+extern "C" int dprnn_gemm_tc_relu_affine(const void* A, const void* W, const float* bias, long bias_rows_per_utt,
+                                         const float* scale, const float* shift, const float* residual, long ldres,
+                                         float* C, long ldc, int M, int N, int K, void* stream) {
+    DPRNN_CHECK_ARG(A && W && C && M > 0 && (N == 128 || N == 256) && K > 0 && ldc % 4 == 0);
+    DPRNN_CHECK_ARG(bias_rows_per_utt == 0 || (bias && bias_rows_per_utt > 0 && M % bias_rows_per_utt == 0));
+    DPRNN_CHECK_ARG((scale == nullptr) == (shift == nullptr));
+    DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) % 16 == 0 && (K * 4) % 128 == 0);
+    GemmTcArgs args{bias, C, ldc, M, K * 4 / 128, nullptr, bias_rows_per_utt, bias_rows_per_utt > 0 ? 1 : 0, nullptr,
+                    scale, shift, nullptr, residual, ldres};
+    return N == 128 ? dispatch_epi<4, 128>(A, W, args, K, DPRNN_EPI_RELU_AFFINE, (cudaStream_t)stream)
+                    : dispatch_epi<4, 256>(A, W, args, K, DPRNN_EPI_RELU_AFFINE, (cudaStream_t)stream);
 }

@@ -144,3 +144,193 @@ extern "C" int dprnn_rawnet_frontend(const float* wave, int B, long T, const flo
     DPRNN_CHECK_LAUNCH();
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Res2Net blocks + attentive statistics pooling: the stages around the contractions (which run in gemm_tc.cu)
+// ---------------------------------------------------------------------------------------------------------
+namespace dprnn {
+
+static inline unsigned rn_grid(long total, int threads) {
+    long g = (total + threads - 1) / threads;
+    const long cap = 148L * 16;
+    return (unsigned)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__global__ void res2_gather_kernel(const float* __restrict__ a, long lda, const float* __restrict__ b, long ldb,
+                                   float* __restrict__ col, long rows, long T, int c4n, int dil) {
+    const long total = rows * 3 * c4n;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n);
+        const long rt = idx / c4n;
+        const int tap = (int)(rt % 3);
+        const long r = rt / 3;
+        const long t = r % T, ts = t + (long)(tap - 1) * dil;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ts >= 0 && ts < T) {
+            const long rs = r + (long)(tap - 1) * dil;
+            v = *reinterpret_cast<const float4*>(a + rs * lda + 4 * c4);
+            if (b) {
+                const float4 w = *reinterpret_cast<const float4*>(b + rs * ldb + 4 * c4);
+                v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
+        }
+        reinterpret_cast<float4*>(col)[idx] = v;          // col[r][tap*C + c]
+    }
+}
+
+__global__ void maxpool_time_kernel(const float* __restrict__ x, const float* __restrict__ y, float* __restrict__ out,
+                                    long ldo, int B, long T, long To, int c4n, int k) {
+    const long total = (long)B * To * c4n;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n);
+        const long r = idx / c4n;
+        const long to = r % To, b = r / To;
+        float4 m = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        for (int i = 0; i < k; ++i) {
+            const long src = ((b * T + to * k + i) * c4n + c4);
+            float4 v = reinterpret_cast<const float4*>(x)[src];
+            if (y) {
+                const float4 w = reinterpret_cast<const float4*>(y)[src];
+                v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+            }
+            m.x = fmaxf(m.x, v.x); m.y = fmaxf(m.y, v.y); m.z = fmaxf(m.z, v.z); m.w = fmaxf(m.w, v.w);
+        }
+        *reinterpret_cast<float4*>(out + r * ldo + 4 * c4) = m;
+    }
+}
+
+// one CTA per (utterance, 32-channel group): mean (and clamped unbiased std) over time, fixed reduction order
+__global__ void __launch_bounds__(256) col_mean_std_kernel(const float* __restrict__ x, float* __restrict__ mean,
+                                                           float* __restrict__ stdv, long T, int C) {
+    __shared__ double sh[2][8][32];
+    const int b = blockIdx.y, cl = threadIdx.x & 31, c = blockIdx.x * 32 + cl, r = threadIdx.x >> 5;
+    const float* xb = x + (long)b * T * C;
+    double s = 0.0, q = 0.0;
+    if (c < C) for (long t = r; t < T; t += 8) { const double v = xb[t * C + c]; s += v; q += v * v; }
+    sh[0][r][cl] = s; sh[1][r][cl] = q;
+    __syncthreads();
+    if (r == 0 && c < C) {
+        for (int i = 1; i < 8; ++i) { s += sh[0][i][cl]; q += sh[1][i][cl]; }
+        const double m = s / (double)T;
+        mean[(long)b * C + c] = (float)m;
+        if (stdv) {
+            double var = T > 1 ? (q - (double)T * m * m) / (double)(T - 1) : 0.0;      // torch.var: unbiased
+            var = fmin(fmax(var, 1e-4), 1e4);
+            stdv[(long)b * C + c] = (float)sqrt(var);
+        }
+    }
+}
+
+__global__ void afms_apply_kernel(const float* __restrict__ x, const float* __restrict__ alpha,
+                                  const float* __restrict__ gate, float* __restrict__ out, long ldo, long T, long total4,
+                                  int c4n) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n);
+        const long r = idx / c4n, b = r / T;
+        const float4 v = reinterpret_cast<const float4*>(x)[idx];
+        const float4 al = __ldg(reinterpret_cast<const float4*>(alpha) + c4);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gate) + b * c4n + c4);
+        *reinterpret_cast<float4*>(out + r * ldo + 4 * c4) =
+            make_float4((v.x + al.x) * g.x, (v.y + al.y) * g.y, (v.z + al.z) * g.z, (v.w + al.w) * g.w);
+    }
+}
+
+__global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long total4) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        const float4 u = reinterpret_cast<const float4*>(a)[idx], v = reinterpret_cast<const float4*>(b)[idx];
+        reinterpret_cast<float4*>(out)[idx] = make_float4(u.x + v.x, u.y + v.y, u.z + v.z, u.w + v.w);
+    }
+}
+
+__global__ void affine_vec_kernel(const float* __restrict__ x, const float* __restrict__ scale,
+                                  const float* __restrict__ shift, float* __restrict__ out, int total, int C, int act) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= total) return;
+    const int c = idx % C;
+    float v = x[idx];
+    if (scale) v = fmaf(v, scale[c], shift[c]);
+    if (act == 1) v = sigmoid_acc(v);
+    out[idx] = v;
+}
+
+// one thread per (utterance, channel): softmax over time of the logits, weighted mean / std of x
+__global__ void att_stats_pool_kernel(const float* __restrict__ x, const float* __restrict__ logits,
+                                      float* __restrict__ out, int B, long T, int C) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * C) return;
+    const int b = idx / C, c = idx % C;
+    const float* xb = x + (long)b * T * C + c;
+    const float* lb = logits + (long)b * T * C + c;
+    float m = -INFINITY;
+    for (long t = 0; t < T; ++t) m = fmaxf(m, lb[t * C]);
+    double se = 0.0, sx = 0.0, sxx = 0.0;
+    for (long t = 0; t < T; ++t) {
+        const double e = (double)expf(lb[t * C] - m), v = xb[t * C];
+        se += e; sx += e * v; sxx += e * v * v;
+    }
+    const double mu = sx / se;
+    double var = sxx / se - mu * mu;
+    var = fmin(fmax(var, 1e-4), 1e4);
+    out[(long)b * 2 * C + c] = (float)mu;
+    out[(long)b * 2 * C + C + c] = (float)sqrt(var);
+}
+
+}  // namespace dprnn
+
+extern "C" int dprnn_res2_gather(const float* a, long lda, const float* b, long ldb, float* col, long rows, long T, int C,
+                                 int dil, void* stream) {
+    DPRNN_CHECK_ARG(a && col && rows > 0 && T > 0 && rows % T == 0 && C % 4 == 0 && dil > 0 && lda % 4 == 0 && (!b || ldb % 4 == 0));
+    res2_gather_kernel<<<rn_grid(rows * 3 * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(a, lda, b, ldb, col, rows, T,
+                                                                                          C / 4, dil);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_maxpool_time(const float* x, const float* y, float* out, long ldo, int B, long T, int C, int k,
+                                  void* stream) {
+    DPRNN_CHECK_ARG(x && out && B > 0 && T >= k && k > 0 && C % 4 == 0 && ldo % 4 == 0);
+    const long To = T / k;
+    maxpool_time_kernel<<<rn_grid((long)B * To * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, y, out, ldo, B, T, To,
+                                                                                               C / 4, k);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_col_mean_std(const float* x, float* mean, float* stdv, int B, long T, int C, void* stream) {
+    DPRNN_CHECK_ARG(x && mean && B > 0 && B <= 65535 && T > 0 && C > 0);
+    dim3 grid(cdiv(C, 32), B);
+    col_mean_std_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, mean, stdv, T, C);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_afms_apply(const float* x, const float* alpha, const float* gate, float* out, long ldo, int B, long T,
+                                int C, void* stream) {
+    DPRNN_CHECK_ARG(x && alpha && gate && out && B > 0 && T > 0 && C % 4 == 0 && ldo % 4 == 0);
+    afms_apply_kernel<<<rn_grid((long)B * T * (C / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, alpha, gate, out, ldo, T,
+                                                                                            (long)B * T * (C / 4), C / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_add2(const float* a, const float* b, float* out, long n, void* stream) {
+    DPRNN_CHECK_ARG(a && b && out && n > 0 && n % 4 == 0);
+    add2_kernel<<<rn_grid(n / 4, 256), 256, 0, (cudaStream_t)stream>>>(a, b, out, n / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_affine_vec(const float* x, const float* scale, const float* shift, float* out, int B, int C, int act,
+                                void* stream) {
+    DPRNN_CHECK_ARG(x && out && B > 0 && C > 0 && ((scale == nullptr) == (shift == nullptr)));
+    affine_vec_kernel<<<cdiv((long)B * C, 256), 256, 0, (cudaStream_t)stream>>>(x, scale, shift, out, B * C, C, act);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_att_stats_pool(const float* x, const float* logits, float* out, int B, long T, int C, void* stream) {
+    DPRNN_CHECK_ARG(x && logits && out && B > 0 && T > 0 && C > 0);
+    att_stats_pool_kernel<<<cdiv((long)B * C, 128), 128, 0, (cudaStream_t)stream>>>(x, logits, out, B, T, C);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
