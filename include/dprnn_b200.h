@@ -338,6 +338,60 @@ int dprnn_clip_adam_step(float* params, const float* grads, float* exp_avg, floa
                          float beta1, float beta2, float eps, float weight_decay, float max_norm, int step,
                          void* workspace, float* total_norm_out, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------
+ * Backward of the path (cfg 5: DPRNN-Spe training step; src/trainers/trainer_spe.py:37-56), exact fp32.
+ * Data gradients of the contractions reuse dprnn_gemm_f32 (dX = dY @ W with W [N_out, K_in] as the [K, N] operand);
+ * dprnn_unfold / dprnn_fold_prelu(prelu_a = NULL) are each other's adjoints.
+ * --------------------------------------------------------------------------------------------------------- */
+
+/* Training forward of the recurrence: dprnn_lstm_recurrence_f32 that also stores the gate activations i,f,g,o
+ * (gates [rows, ndir*4H]) and the cell state (cstate [rows, ndir*H]) of every step. */
+int dprnn_lstm_recurrence_f32_train(const float* gx, const float* whhT, float* hout, float* gates, float* cstate,
+                                    long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride,
+                                    long step_stride, int hidden, int ndir, void* stream);
+/* BPTT: dh_out [rows, ndir*H] = gradient of the layer output; whh [ndir][4H][H] (PyTorch layout);
+ * dgates [rows, ndir*4H] = gradient of the gate pre-activations of every step (same sequence geometry as forward). */
+int dprnn_lstm_bptt_f32(const float* dh_out, const float* gates, const float* cstate, const float* whh, float* dgates,
+                        long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride, long step_stride,
+                        int hidden, int ndir, void* stream);
+/* C[N1,N2] (ldc) (+)= A[M,N1]^T @ B[M,N2]: weight gradients (two-stage deterministic reduction over the rows). */
+size_t dprnn_gemm_atb_workspace_bytes(long M, int N1, int N2);
+int dprnn_gemm_atb(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N1, int N2,
+                   int accumulate, void* workspace, void* stream);
+/* out[n] (+)= sum_m X[m,n] (* Y[m,n] if Y): bias gradients, BatchNorm reductions. */
+size_t dprnn_col_sum_workspace_bytes(int N);
+int dprnn_col_sum(const float* X, long ldx, const float* Y, long ldy, long M, int N, float* out, int accumulate,
+                  void* workspace, void* stream);
+/* GroupNorm(1,C) / gLN backward per utterance: z = gamma*(y-mean)*rstd + beta; given dz: dy (=, or += if
+ * accumulate_dy), dgamma += , dbeta += . */
+size_t dprnn_gn_bwd_workspace_bytes(int B, int C);
+int dprnn_groupnorm_bwd(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
+                        long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
+                        void* workspace, void* stream);
+/* PReLU adjoint: dx = dy * (x > 0 ? 1 : a); da[0] += sum dy*x*[x <= 0]; workspace: 148*16 doubles. */
+int dprnn_prelu_bwd(const float* dy, const float* x, const float* prelu_a, float* dx, long n, float* da, void* workspace,
+                    void* stream);
+/* MaxPool1d(3) adjoint: dv [B,Lin,C] from dy [B,Lin/3,C] and the pooled input v (first maximum wins). */
+int dprnn_pool3_bwd(const float* dy, const float* v, float* dv, int B, long Lin, int C, void* stream);
+/* tanh(po)*sigmoid(pg) adjoint; pre = [po | pg] [rows, 2F] -> dpre [rows, 2F]. */
+int dprnn_gated_bwd(const float* dg, const float* pre, float* dpre, long rows, int F, void* stream);
+int dprnn_mul(const float* a, const float* b, float* out, long n, void* stream);
+int dprnn_axpy(const float* a, float alpha, float* out, long n, int accumulate, void* stream);
+/* dpre = dy * act'(y) from the activation OUTPUT y: act 1 = ReLU, 2 = sigmoid. */
+int dprnn_act_bwd(const float* dy, const float* y, float* dpre, long n, int act, void* stream);
+/* Decoder (ConvTranspose1d N->1, kernel 2, stride 1) adjoint wrt its input: dz[b,l,c] = dest[b,l] w[c,0] + dest[b,l+1] w[c,1]. */
+int dprnn_decoder_bwd(const float* dest, const float* wdec, float* dz, int B, long L, int N, void* stream);
+/* dw[c,j] (+)= sum_{b,l} z[b,l,c] * sig[b,l+j]: weight gradient of the kernel-2 stride-1 decoder / encoder. */
+size_t dprnn_convw2_workspace_bytes(int N);
+int dprnn_convw2_grad(const float* z, const float* sig, int B, long L, int N, float* dw, int accumulate, void* workspace,
+                      void* stream);
+/* out[b,c] = sum_l X[b,l,c] (* Y[b,l,c]); out[b,l,c] (+)= v[b,c] * (X ? X[b,l,c] : 1). */
+int dprnn_utt_col_sum(const float* X, const float* Y, int B, long L, int C, float* out, void* stream);
+int dprnn_bcast_mul(const float* v, const float* X, float* out, int B, long L, int C, int accumulate, void* stream);
+/* BatchNorm1d (train) adjoint: dy = gamma*rstd*(dout - m1 - yhat*m2), m1 = mean(dout), m2 = mean(dout*yhat) per channel. */
+int dprnn_bn_bwd_apply(const float* dout, const float* y, const float* mean, const float* rstd, const float* gamma,
+                       const float* m1, const float* m2, float* dy, long rows, int C, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,97 @@
+"""Backward building blocks (cfg 5) against torch autograd / fp64 restatements."""
+import pytest
+import torch
+
+import tss_with_dprnn_b200 as P
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def rnd(*shape, seed=0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
+
+
+def rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
+
+
+@pytest.mark.parametrize('M,N1,N2', [(1000, 128, 64), (48500, 512, 128), (20001, 256, 128), (33, 64, 64)])
+def test_gemm_atb(M, N1, N2):
+    L = P.lib()
+    A, B = rnd(M, N1, seed=1), rnd(M, N2, seed=2)
+    want = A.double().t() @ B.double()
+    C = torch.full((N1, N2), 3.0, device=DEV)
+    ws = torch.empty(L.query('dprnn_gemm_atb_workspace_bytes', M, N1, N2), device=DEV, dtype=torch.uint8)
+    L.call('dprnn_gemm_atb', A.to(DEV), N1, B.to(DEV), N2, C, N2, M, N1, N2, 0, ws, st())
+    assert rel(C.cpu(), want) < 1e-5
+    L.call('dprnn_gemm_atb', A.to(DEV), N1, B.to(DEV), N2, C, N2, M, N1, N2, 1, ws, st())
+    assert rel(C.cpu(), 2 * want) < 1e-5
+    out = torch.zeros(N1, device=DEV)
+    ws2 = torch.empty(L.query('dprnn_col_sum_workspace_bytes', N1), device=DEV, dtype=torch.uint8)
+    L.call('dprnn_col_sum', A.to(DEV), N1, None, 0, M, N1, out, 0, ws2, st())
+    assert rel(out.cpu(), A.double().sum(0)) < 1e-5
+
+
+def test_groupnorm_bwd():
+    L = P.lib()
+    B, R, C = 3, 777, 128
+    y = rnd(B, R, C, seed=3).double().requires_grad_(True)
+    gamma = (1 + 0.1 * rnd(C, seed=4)).double().requires_grad_(True)
+    beta = rnd(C, seed=5).double().requires_grad_(True)
+    mean = y.mean((1, 2), keepdim=True); var = y.var((1, 2), unbiased=False, keepdim=True)
+    z = (y - mean) / torch.sqrt(var + 1e-5) * gamma + beta
+    dz = rnd(B, R, C, seed=6).double()
+    z.backward(dz)
+    mr = torch.stack([mean.flatten(), 1 / torch.sqrt(var.flatten() + 1e-5)], 1).float().to(DEV)
+    dy = torch.empty(B, R, C, device=DEV); dg = torch.zeros(C, device=DEV); db = torch.zeros(C, device=DEV)
+    ws = torch.empty(L.query('dprnn_gn_bwd_workspace_bytes', B, C), device=DEV, dtype=torch.uint8)
+    L.call('dprnn_groupnorm_bwd', dz.float().to(DEV), y.detach().float().to(DEV), mr, gamma.detach().float().to(DEV), B, R, C,
+           dy, 0, dg, db, ws, st())
+    assert rel(dy.cpu(), y.grad) < 2e-5
+    assert rel(dg.cpu(), gamma.grad) < 2e-5 and rel(db.cpu(), beta.grad) < 2e-5
+
+
+@pytest.mark.parametrize('inter', [0, 1])
+@pytest.mark.parametrize('ndir', [2, 1])
+def test_lstm_train_forward_and_bptt(inter, ndir):
+    """dprnn_lstm_recurrence_f32_train + dprnn_lstm_bptt_f32 against autograd through nn.LSTM (fp64)."""
+    L = P.lib()
+    H = 128
+    B, S, K = (2, 5, 11) if not inter else (2, 7, 9)
+    torch.manual_seed(7 + inter)
+    rnn = torch.nn.LSTM(H, H, batch_first=True, bidirectional=(ndir == 2)).double()
+    x = rnd(B, S, K, H, seed=8).double().requires_grad_(True)
+    seqs = x.reshape(B * S, K, H) if not inter else x.permute(0, 2, 1, 3).reshape(B * K, S, H)
+    out, _ = rnn(seqs)
+    out_l = out.reshape(B, S, K, ndir * H) if not inter else out.reshape(B, K, S, ndir * H).permute(0, 2, 1, 3)
+    dout = rnd(B, S, K, ndir * H, seed=9).double()
+    out_l.backward(dout)
+    rows = B * S * K
+    sfx = ['', '_reverse'][:ndir]
+    wih = torch.cat([getattr(rnn, 'weight_ih_l0' + s) for s in sfx], 0).detach().float()       # [nd*4H, H]
+    bias = torch.cat([getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s) for s in sfx], 0).detach().float()
+    whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s) for s in sfx], 0).detach().float()      # [nd, 4H, H]
+    gx = (x.detach().float().reshape(rows, H) @ wih.t() + bias).to(DEV)
+    geo = (B * S, K, 1, K, 0, 1) if not inter else (B * K, S, K, S * K, 1, K)
+    hout = torch.empty(rows, ndir * H, device=DEV); gates = torch.empty(rows, ndir * 4 * H, device=DEV)
+    cst = torch.empty(rows, ndir * H, device=DEV)
+    L.call('dprnn_lstm_recurrence_f32_train', gx, whh.transpose(1, 2).contiguous().to(DEV), hout, gates, cst, *geo, H, ndir, st())
+    assert rel(hout.cpu(), out_l.detach().reshape(rows, -1)) < 1e-5
+    dg = torch.empty(rows, ndir * 4 * H, device=DEV)
+    L.call('dprnn_lstm_bptt_f32', dout.float().reshape(rows, -1).contiguous().to(DEV), gates, cst, whh.contiguous().to(DEV), dg,
+           *geo, H, ndir, st())
+    torch.cuda.synchronize()
+    dgc = dg.cpu().double()
+    # dx = dgates @ W_ih ; dW_ih = dgates^T x ; db = colsum(dgates)
+    dx = dgc @ wih.double()
+    assert rel(dx, x.grad.reshape(rows, H)) < 1e-4
+    dwih = dgc.t() @ x.detach().reshape(rows, H)
+    want_wih = torch.cat([getattr(rnn, 'weight_ih_l0' + s).grad for s in sfx], 0)
+    assert rel(dwih, want_wih) < 1e-4
+    want_b = torch.cat([getattr(rnn, 'bias_ih_l0' + s).grad for s in sfx], 0)
+    assert rel(dgc.sum(0), want_b) < 1e-4
