@@ -354,6 +354,9 @@ int dprnn_lstm_recurrence_f32_train(const float* gx, const float* whhT, float* h
 int dprnn_lstm_bptt_f32(const float* dh_out, const float* gates, const float* cstate, const float* whh, float* dgates,
                         long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride, long step_stride,
                         int hidden, int ndir, void* stream);
+/* h_prev for the W_hh gradient: out[row(n,t)] = h[row(n, previous step of the direction)], 0 at the first step. */
+int dprnn_shift_rows(const float* h, float* out, long nseq, int T, long seq_div, long seq_outer_stride,
+                     long seq_inner_stride, long step_stride, int hidden, int ndir, void* stream);
 /* C[N1,N2] (ldc) (+)= A[M,N1]^T @ B[M,N2]: weight gradients (two-stage deterministic reduction over the rows). */
 size_t dprnn_gemm_atb_workspace_bytes(long M, int N1, int N2);
 int dprnn_gemm_atb(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N1, int N2,
@@ -375,6 +378,8 @@ int dprnn_prelu_bwd(const float* dy, const float* x, const float* prelu_a, float
 int dprnn_pool3_bwd(const float* dy, const float* v, float* dv, int B, long Lin, int C, void* stream);
 /* tanh(po)*sigmoid(pg) adjoint; pre = [po | pg] [rows, 2F] -> dpre [rows, 2F]. */
 int dprnn_gated_bwd(const float* dg, const float* pre, float* dpre, long rows, int F, void* stream);
+/* its forward with unpacked halves: out [rows,F] = tanh(pre[:, :F]) * sigmoid(pre[:, F:]) (training forward keeps pre). */
+int dprnn_gated_fwd(const float* pre, float* out, long rows, int F, void* stream);
 int dprnn_mul(const float* a, const float* b, float* out, long n, void* stream);
 int dprnn_axpy(const float* a, float alpha, float* out, long n, int accumulate, void* stream);
 /* dpre = dy * act'(y) from the activation OUTPUT y: act 1 = ReLU, 2 = sigmoid. */

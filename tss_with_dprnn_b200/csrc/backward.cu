@@ -19,7 +19,8 @@ static inline unsigned bgrid(long total, int threads) {
 constexpr int AT_TILE = 64, AT_RK = 16;
 __global__ void __launch_bounds__(256) gemm_atb_partial_kernel(const float* __restrict__ A, long lda,
                                                                const float* __restrict__ B, long ldb, long M, int N1,
-                                                               int N2, long rows_per_chunk, float* __restrict__ partial) {
+                                                               int N2, long rows_per_chunk, float* __restrict__ partial,
+                                                               int vec) {
     __shared__ __align__(16) float As[AT_RK][AT_TILE], Bs[AT_RK][AT_TILE];
     const int i0 = blockIdx.x * AT_TILE, j0 = blockIdx.y * AT_TILE;
     const long r0 = (long)blockIdx.z * rows_per_chunk, r1 = min(r0 + rows_per_chunk, M);
@@ -33,8 +34,21 @@ __global__ void __launch_bounds__(256) gemm_atb_partial_kernel(const float* __re
     for (long r = r0; r < r1; r += AT_RK) {
         float4 av = make_float4(0.f, 0.f, 0.f, 0.f), bv = av;
         if (r + lr < r1) {
-            if (i0 + lc < N1) av = *reinterpret_cast<const float4*>(A + (r + lr) * lda + i0 + lc);
-            if (j0 + lc < N2) bv = *reinterpret_cast<const float4*>(B + (r + lr) * ldb + j0 + lc);
+            if (vec) {
+                if (i0 + lc < N1) av = *reinterpret_cast<const float4*>(A + (r + lr) * lda + i0 + lc);
+                if (j0 + lc < N2) bv = *reinterpret_cast<const float4*>(B + (r + lr) * ldb + j0 + lc);
+            } else {        // widths / strides that are not multiples of 4 (e.g. the 251 speaker logits): scalar loads
+                const float* ap = A + (r + lr) * lda + i0 + lc;
+                const float* bp = B + (r + lr) * ldb + j0 + lc;
+                if (i0 + lc + 0 < N1) av.x = ap[0];
+                if (i0 + lc + 1 < N1) av.y = ap[1];
+                if (i0 + lc + 2 < N1) av.z = ap[2];
+                if (i0 + lc + 3 < N1) av.w = ap[3];
+                if (j0 + lc + 0 < N2) bv.x = bp[0];
+                if (j0 + lc + 1 < N2) bv.y = bp[1];
+                if (j0 + lc + 2 < N2) bv.z = bp[2];
+                if (j0 + lc + 3 < N2) bv.w = bp[3];
+            }
         }
         __syncthreads();
         *reinterpret_cast<float4*>(&As[lr][lc]) = av;
@@ -234,6 +248,14 @@ __global__ void gated_bwd_kernel(const float* __restrict__ dgv, const float* __r
     }
 }
 
+__global__ void gated_fwd_kernel(const float* __restrict__ pre, float* __restrict__ out, long rows, int F) {
+    const long total = rows * F;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const long r = idx / F; const int c = (int)(idx % F);
+        out[idx] = tanhf(pre[r * 2 * F + c]) * sigmoid_acc(pre[r * 2 * F + F + c]);
+    }
+}
+
 // elementwise helpers: out = a * b ; out (+)= alpha * a ; dpre = dy * act'(y)
 __global__ void mul_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, long n) {
     for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) out[i] = a[i] * b[i];
@@ -327,11 +349,40 @@ __global__ void bn_bwd_apply_kernel(const float* __restrict__ dout, const float*
     }
 }
 
+// h_prev of the recurrence for the W_hh gradient: out[row(n,t), d*H + j] = h[row(n, t -/+ 1), d*H + j] (the step the
+// forward of direction d visited before t), 0 at the first step.  Rows follow the forward's sequence geometry.
+__global__ void shift_rows_kernel(const float* __restrict__ h, float* __restrict__ out, long nseq, int T, long seq_div,
+                                  long seq_outer, long seq_inner, long step_stride, int Hd, int ndir) {
+    const int h4n = ndir * Hd / 4, d4 = Hd / 4;
+    const long total = nseq * T * h4n;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % h4n);
+        const long nt = idx / h4n;
+        const int t = (int)(nt % T);
+        const long n = nt / T;
+        const int dir = c4 / d4;
+        const long base = (n / seq_div) * seq_outer + (n % seq_div) * seq_inner;
+        const int tp = dir ? t + 1 : t - 1;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (tp >= 0 && tp < T) v = reinterpret_cast<const float4*>(h)[(base + (long)tp * step_stride) * h4n + c4];
+        reinterpret_cast<float4*>(out)[(base + (long)t * step_stride) * h4n + c4] = v;
+    }
+}
+
 }  // namespace dprnn
 
 using namespace dprnn;
 
 extern "C" {
+
+int dprnn_shift_rows(const float* h, float* out, long nseq, int T, long seq_div, long seq_outer_stride,
+                     long seq_inner_stride, long step_stride, int hidden, int ndir, void* stream) {
+    DPRNN_CHECK_ARG(h && out && nseq > 0 && T > 0 && seq_div > 0 && hidden % 4 == 0 && (ndir == 1 || ndir == 2));
+    shift_rows_kernel<<<bgrid(nseq * T * (ndir * hidden / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        h, out, nseq, T, seq_div, seq_outer_stride, seq_inner_stride, step_stride, hidden, ndir);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
 
 size_t dprnn_gemm_atb_workspace_bytes(long M, int N1, int N2) {
     const long chunks = (M + 8191) / 8192 < 1 ? 1 : ((M + 8191) / 8192 > 512 ? 512 : (M + 8191) / 8192);
@@ -340,13 +391,13 @@ size_t dprnn_gemm_atb_workspace_bytes(long M, int N1, int N2) {
 
 int dprnn_gemm_atb(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N1, int N2,
                    int accumulate, void* workspace, void* stream) {
-    DPRNN_CHECK_ARG(A && B && C && workspace && M > 0 && N1 > 0 && N2 > 0 && N1 % 4 == 0 && N2 % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0);
-    DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)B) % 16 == 0);
+    DPRNN_CHECK_ARG(A && B && C && workspace && M > 0 && N1 > 0 && N2 > 0);
+    const int vec = (N1 % 4 == 0 && N2 % 4 == 0 && lda % 4 == 0 && ldb % 4 == 0 && ((uintptr_t)A | (uintptr_t)B) % 16 == 0) ? 1 : 0;
     long chunks = (M + 8191) / 8192;
     chunks = chunks < 1 ? 1 : (chunks > 512 ? 512 : chunks);
     const long rpc = ((M + chunks - 1) / chunks + AT_RK - 1) / AT_RK * AT_RK;
     dim3 grid(cdiv(N1, AT_TILE), cdiv(N2, AT_TILE), (unsigned)chunks);
-    gemm_atb_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, N1, N2, rpc, (float*)workspace);
+    gemm_atb_partial_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(A, lda, B, ldb, M, N1, N2, rpc, (float*)workspace, vec);
     DPRNN_CHECK_LAUNCH();
     chunk_reduce_kernel<<<bgrid((long)N1 * N2, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, (int)chunks,
                                                                                     (long)N1 * N2, C, ldc, N2, accumulate);
@@ -414,6 +465,13 @@ int dprnn_pool3_bwd(const float* dy, const float* v, float* dv, int B, long Lin,
 int dprnn_gated_bwd(const float* dg, const float* pre, float* dpre, long rows, int F, void* stream) {
     DPRNN_CHECK_ARG(dg && pre && dpre && rows > 0 && F > 0);
     gated_bwd_kernel<<<bgrid(rows * F, 256), 256, 0, (cudaStream_t)stream>>>(dg, pre, dpre, rows, F);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_gated_fwd(const float* pre, float* out, long rows, int F, void* stream) {
+    DPRNN_CHECK_ARG(pre && out && rows > 0 && F > 0);
+    gated_fwd_kernel<<<bgrid(rows * F, 256), 256, 0, (cudaStream_t)stream>>>(pre, out, rows, F);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

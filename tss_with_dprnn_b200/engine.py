@@ -158,6 +158,9 @@ class Engine(RaggedMixin):
             return mod.gamma.detach(), mod.beta.detach(), 1e-8       # GlobLN (norms.py:9)
         return mod.weight.detach(), mod.bias.detach(), mod.eps
 
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and self.model.training and any(p.requires_grad for p in self.model.parameters())
+
     def _guard_autograd(self):
         if torch.is_grad_enabled() and self.model.training and any(p.requires_grad for p in self.model.parameters()):
             raise NotImplementedError(
@@ -575,7 +578,8 @@ class Engine(RaggedMixin):
             return self._graphed('bss', (mix,), lambda m: self._run_groups(m.shape[0], lambda b0, b1: group_of(m, b0, b1)))[0]
 
     def forward_spe(self, mix, ref, ref_len, embedding=None):
-        self._guard_autograd()
+        if embedding is not None:
+            self._guard_autograd()
         mix = self._check_input(mix, 'input')
         sep, cfg = self.model.separation, self.model.cfg
         N = cfg['input_size']
@@ -597,6 +601,11 @@ class Engine(RaggedMixin):
             self.decode(mask, enc, est, B, L, Tout)
             return est, self.small_linear(emb, sep.pred_linear, B)
 
+        if embedding is None and self._wants_grad():
+            # training step (cfg 5): forward that keeps what the hand-written backward needs, as one autograd node
+            from .train import forward_with_grad
+            ref = self._check_input(ref, 'aux')
+            return forward_with_grad(self.model, mix, ref, self._aux_div(ref_len, mix.shape[0], mix.device))
         with torch.no_grad():
             B = mix.shape[0]
             if embedding is None:

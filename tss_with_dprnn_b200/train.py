@@ -1,0 +1,498 @@
+"""Training step of the separation path (cfg 5: DPRNN-Spe, src/trainers/trainer_spe.py:14-72): forward in train mode
+(BatchNorm batch statistics, running-stat updates) that keeps what the backward needs, and the hand-written backward
+(csrc/backward.cu, csrc/lstm_simt.cu) - exact fp32 on CUDA cores, correctness first.  The loss lives in the caller
+(asteroid's PIT / SI-SDR wrapper + CrossEntropyLoss in the reference trainer), so the model is exposed to autograd as ONE
+``torch.autograd.Function``: forward -> (est, logits), backward(d_est, d_logits) -> parameter gradients.
+
+Memory: per half-block the forward keeps the LSTM gates / cell state / output and the Linear output (13 A, A = one
+[B,S,K,128] fp32 tensor = 0.40 GB at B = 16); the block inputs are NOT kept - the residual stream is reversible
+(x_in = x_out - norm(y)), so the backward walks it back while it walks the blocks in reverse.
+
+Supported: DPRNNSpeTasNet with fusion_type in {film, add, mul, cat}, 'ln' / 'gLN' norms, sigmoid / relu mask activation,
+kernel_size 2 / stride 1, feature_size = hidden_size = 128.  The attention fusion, the IRA model and DPRNN-TasNet keep
+raising NotImplementedError in train mode.
+"""
+from __future__ import annotations
+
+import torch
+
+from ._lib import lib
+
+EPI_NONE, EPI_RELU, EPI_SIGMOID, EPI_GATED = 0, 1, 2, 3
+
+
+def _st():
+    return torch.cuda.current_stream().cuda_stream
+
+
+class _Ops:
+    """Thin wrappers that allocate outputs / workspaces (PyTorch = device memory only)."""
+
+    def __init__(self, dev):
+        self.dev = dev
+        self.L = lib()
+
+    def empty(self, *shape):
+        return torch.empty(shape, device=self.dev, dtype=torch.float32)
+
+    def gemm(self, A, Wt, M, N, K, bias=None, epi=EPI_NONE, lda=None, ldw=None, **pro):
+        """C[M,N] = epi(pro(A)[M,K] @ Wt[K,N] + bias)"""
+        out = self.empty(M, N // 2 if epi == EPI_GATED else N)
+        self.L.call('dprnn_gemm_f32', A, lda or K, Wt, ldw or N, out, out.shape[1], M, N, K, bias,
+                    int(pro.get('bias_per_utt', False)), 1.0, int(pro.get('rows_per_utt', 0)), pro.get('p_scale'),
+                    pro.get('p_shift'), pro.get('p_add'), None, epi, _st())
+        return out
+
+    def atb(self, A, B, M, N1, N2, out, lda=None, ldb=None, ldc=None, accumulate=True):
+        """out[N1,N2] (+)= A[M,N1]^T B[M,N2]"""
+        ws = torch.empty(self.L.query('dprnn_gemm_atb_workspace_bytes', M, N1, N2), device=self.dev, dtype=torch.uint8)
+        self.L.call('dprnn_gemm_atb', A, lda or N1, B, ldb or N2, out, ldc or N2, M, N1, N2, int(accumulate), ws, _st())
+
+    def colsum(self, X, M, N, out, Y=None, ldx=None, accumulate=True):
+        ws = torch.empty(self.L.query('dprnn_col_sum_workspace_bytes', N), device=self.dev, dtype=torch.uint8)
+        self.L.call('dprnn_col_sum', X, ldx or N, Y, ldx or N, M, N, out, int(accumulate), ws, _st())
+
+    def utt_stats(self, x, B, elems, eps):
+        ws = torch.empty(self.L.query('dprnn_utt_stats_workspace_bytes', B), device=self.dev, dtype=torch.uint8)
+        mr = self.empty(B, 2)
+        self.L.call('dprnn_utt_stats', x, B, elems, float(eps), ws, mr, _st())
+        return mr
+
+    def gn_bwd(self, dz, y, mr, gamma, B, rows_per_utt, C, dgamma, dbeta, dy=None, accumulate_dy=False):
+        ws = torch.empty(self.L.query('dprnn_gn_bwd_workspace_bytes', B, C), device=self.dev, dtype=torch.uint8)
+        if dy is None:
+            dy = self.empty(B * rows_per_utt, C)
+        self.L.call('dprnn_groupnorm_bwd', dz, y, mr, gamma, B, rows_per_utt, C, dy, int(accumulate_dy), dgamma, dbeta, ws, _st())
+        return dy
+
+    def prelu_bwd(self, dy, x, a, da):
+        dx = torch.empty_like(x)
+        ws = torch.empty(148 * 16 * 8, device=self.dev, dtype=torch.uint8)
+        self.L.call('dprnn_prelu_bwd', dy, x, a, dx, x.numel(), da, ws, _st())
+        return dx
+
+    def axpy(self, a, out, alpha=1.0, accumulate=True):
+        self.L.call('dprnn_axpy', a, float(alpha), out, a.numel(), int(accumulate), _st())
+
+    def mul(self, a, b):
+        out = torch.empty_like(a)
+        self.L.call('dprnn_mul', a, b, out, a.numel(), _st())
+        return out
+
+
+def _norm_params(mod):
+    if hasattr(mod, 'gamma'):
+        return mod.gamma, mod.beta, 1e-8
+    return mod.weight, mod.bias, mod.eps
+
+
+def _check_supported(model):
+    cfg = model.cfg
+    if cfg['kind'] != 'spe' or cfg['fusion_type'] not in ('film', 'add', 'mul', 'cat'):
+        raise NotImplementedError("training is built for DPRNNSpeTasNet with fusion_type in {'film','add','mul','cat'} "
+                                  '(cfg 5: film); other models keep their forward-only path')
+    if cfg['kernel_size'] != 2 or cfg['stride'] != 1 or cfg['feature_size'] != 128 or cfg['hidden_size'] != 128 \
+            or cfg['chunk_length'] != 2 * cfg['hop_length'] or cfg['input_size'] not in (32, 64, 128):
+        raise NotImplementedError('training is built for the shipped geometry (kernel 2, stride 1, F = H = 128, hop = K/2)')
+
+
+# --------------------------------------------------------------------------------------------------------------
+# forward (train mode)
+# --------------------------------------------------------------------------------------------------------------
+def forward_train(model, mix, ref, div):
+    """-> est [B,T], logits [B,num_spks], ctx (everything the backward needs)."""
+    _check_supported(model)
+    L_, cfg, sep = lib(), model.cfg, model.separation
+    dev = mix.device
+    ops = _Ops(dev)
+    st = _st()
+    N, F, H, K, P = cfg['input_size'], cfg['feature_size'], cfg['hidden_size'], cfg['chunk_length'], cfg['hop_length']
+    B, T = mix.shape
+    Lm, Lr = T - 1, ref.shape[1] - 1
+    ctx = dict(B=B, T=T, L=Lm, Lr=Lr, mix=mix, ref=ref, div=div)
+    w_enc = model.encoder.conv1d.weight.detach().reshape(N, 2).contiguous()
+    enc = ops.empty(B, Lm, N)
+    L_.call('dprnn_encoder_fwd', mix, w_enc, enc, B, T, N, 2, 1, st)
+    feats = ops.empty(B, Lr, N)
+    L_.call('dprnn_encoder_fwd', ref, w_enc, feats, B, ref.shape[1], N, 2, 1, st)
+    ctx.update(enc=enc, feats=feats)
+
+    # ---- speaker encoder (dprnn_spe.py:115-122,156-163), BatchNorm in train mode
+    se = sep.spk_encoder
+    mr_s = ops.utt_stats(feats, B, Lr * N, se[0].eps)
+    s1 = ops.empty(B, N); s0 = ops.empty(B, N)
+    L_.call('dprnn_norm_affine', mr_s, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
+    gnf = torch.empty_like(feats)                                  # GroupNorm(feats): kept for dW of conv0
+    L_.call('dprnn_prologue_apply', feats, gnf, B * Lr, N, Lr, s1, s0, None, None, st)
+    O = se[1].weight.shape[0]
+    x = ops.gemm(gnf, se[1].weight.detach().reshape(O, N).t().contiguous(), B * Lr, O, N, bias=se[1].bias.detach())
+    ctx.update(mr_s=mr_s, gnf=gnf)
+    res, Lx = [], Lr
+    for rb in (se[2], se[3], se[4]):
+        Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
+        rows = B * Lx
+        rc = dict(x=x, Lx=Lx, Cin=Cin, Cout=Cout)
+        ws = torch.empty(L_.query('dprnn_bn_workspace_bytes', Cout), device=dev, dtype=torch.uint8)
+
+        def bn(y, bnm):
+            scale, shift = ops.empty(Cout), ops.empty(Cout)
+            L_.call('dprnn_batchnorm_affine', y, rows, Cout, bnm.weight.detach(), bnm.bias.detach(), bnm.running_mean,
+                    bnm.running_var, 1, float(bnm.eps), float(bnm.momentum if bnm.momentum is not None else 0.1), ws,
+                    scale, shift, st)
+            bnm.num_batches_tracked += 1
+            return scale, shift
+
+        y1 = ops.gemm(x, rb.conv1.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
+        sc1, sh1 = bn(y1, rb.batch_norm1)
+        a1 = ops.empty(rows, Cout)
+        L_.call('dprnn_affine_prelu', y1, sc1, sh1, rb.prelu1.weight.detach(), a1, rows, Cout, st)
+        y2 = ops.gemm(a1, rb.conv2.weight.detach().reshape(Cout, Cout).t().contiguous(), rows, Cout, Cout)
+        sc2, sh2 = bn(y2, rb.batch_norm2)
+        if hasattr(rb, 'conv_downsample'):
+            skip = ops.gemm(x, rb.conv_downsample.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
+        else:
+            skip = x
+        Lo = Lx // 3
+        out = ops.empty(B, Lo, Cout)
+        L_.call('dprnn_affine_add_prelu_pool3', y2, sc2, sh2, skip, rb.prelu2.weight.detach(), out, B, Lx, Cout, st)
+        rc.update(y1=y1, sc1=sc1, sh1=sh1, a1=a1, y2=y2, sc2=sc2, sh2=sh2, skip=skip)
+        res.append(rc)
+        x, Lx = out.view(B * Lo, Cout), Lo
+    E = se[5].weight.shape[0]
+    C5 = se[5].weight.shape[1]
+    z5 = ops.gemm(x, se[5].weight.detach().reshape(E, C5).t().contiguous(), B * Lx, E, C5, bias=se[5].bias.detach())
+    emb = ops.empty(B, E)
+    L_.call('dprnn_time_sum', z5, emb, B, Lx, E, div, st)
+    ctx.update(res=res, x3=x, L3=Lx, emb=emb)
+
+    # ---- bottleneck norm + fusion + 1x1 conv (dprnn_spe.py:136-143)
+    gamma, beta, eps = _norm_params(sep.bottleneck[0])
+    mr_e = ops.utt_stats(enc, B, Lm * N, eps)
+    ft = cfg['fusion_type']
+
+    def lin(m):
+        out = ops.empty(B, m.weight.shape[0])
+        L_.call('dprnn_small_linear', emb, E, m.weight.detach(), E, m.bias.detach(), out, out.shape[1], B, out.shape[1], E, 0, st)
+        return out
+
+    mulc = addc = None
+    bw = sep.bottleneck[1].weight.detach().reshape(F, -1)
+    bias, bias_per_utt = sep.bottleneck[1].bias.detach(), False
+    if ft == 'film':
+        mulc, addc = lin(sep.fusion_linear_1), lin(sep.fusion_linear_2)
+    elif ft == 'add':
+        addc = lin(sep.fusion_linear)
+    elif ft == 'mul':
+        mulc = lin(sep.fusion_linear)
+    elif ft == 'cat':
+        bias = ops.empty(B, F)
+        L_.call('dprnn_small_linear', emb, E, bw.data_ptr() + 4 * N, N + E, sep.bottleneck[1].bias.detach(), bias, F, B, F, E, 0, st)
+        bias_per_utt = True
+    s1e, s0e = ops.empty(B, N), ops.empty(B, N)
+    L_.call('dprnn_norm_affine', mr_e, gamma.detach(), beta.detach(), mulc, s1e, s0e, B, N, st)
+    fused = torch.empty_like(enc)                                   # fusion(GroupNorm(enc)): kept for dW of the 1x1 conv
+    L_.call('dprnn_prologue_apply', enc, fused, B * Lm, N, Lm, s1e, s0e, addc, None, st)
+    y = ops.gemm(fused, bw[:, :N].t().contiguous(), B * Lm, F, N, bias=bias, bias_per_utt=bias_per_utt, rows_per_utt=Lm)
+    S = L_.query('dprnn_num_chunks', Lm, K, P)
+    xs = ops.empty(B, S, K, F)
+    L_.call('dprnn_unfold', y, xs, B, Lm, K, P, F, st)
+    del y
+    rows = B * S * K
+    ctx.update(mr_e=mr_e, mulc=mulc, addc=addc, fused=fused, S=S, rows=rows)
+
+    # ---- DPRNN blocks (dprnn.py:79-99)
+    halves = []
+    for blk in sep.dprnn_blocks:
+        for which, (rnn, linm, nm) in enumerate(((blk.intra_rnn.rnn, blk.intra_linear, blk.intra_norm),
+                                                 (blk.inter_rnn.rnn, blk.inter_linear, blk.inter_norm))):
+            sfx = ['', '_reverse'] if rnn.bidirectional else ['']
+            nd = len(sfx)
+            wih = torch.cat([getattr(rnn, 'weight_ih_l0' + s).detach() for s in sfx], 0)              # [nd*4H, F]
+            b = torch.cat([(getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s)).detach() for s in sfx], 0)
+            whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach() for s in sfx], 0).contiguous()   # [nd,4H,H]
+            gx = ops.gemm(xs, wih.t().contiguous(), rows, nd * 4 * H, F, bias=b)
+            geo = (B * S, K, 1, K, 0, 1) if which == 0 else (B * K, S, K, S * K, 1, K)
+            hout, gates, cst = ops.empty(rows, nd * H), ops.empty(rows, nd * 4 * H), ops.empty(rows, nd * H)
+            L_.call('dprnn_lstm_recurrence_f32_train', gx, whh.transpose(1, 2).contiguous(), hout, gates, cst, *geo, H, nd, st)
+            del gx
+            yl = ops.gemm(hout, linm.weight.detach().t().contiguous(), rows, F, nd * H, bias=linm.bias.detach())
+            g_, b_, eps_ = _norm_params(nm)
+            mr = ops.utt_stats(yl, B, S * K * F, eps_)
+            L_.call('dprnn_norm_residual', yl, xs, mr, g_.detach(), b_.detach(), B, S * K, F, None, st)
+            halves.append(dict(nd=nd, geo=geo, hout=hout, gates=gates, cst=cst, yl=yl, mr=mr, wih=wih, whh=whh,
+                               rnn=rnn, lin=linm, norm=nm, sfx=sfx))
+    ctx.update(halves=halves, xs=xs)
+
+    # ---- PReLU, overlap-add, conv2d (speaker 0), gated head, end conv, mask, decoder (dprnn_spe.py:231-248,323-325)
+    z = ops.empty(B, Lm, F)
+    L_.call('dprnn_fold_prelu', xs, z, B, Lm, K, P, F, sep.prelu.weight.detach(), st)
+    cw = sep.conv2d.weight.detach().reshape(2 * F, F)
+    u = ops.gemm(z, cw[:F].t().contiguous(), B * Lm, F, F, bias=(2.0 * sep.conv2d.bias.detach()[:F]).contiguous())
+    wog = torch.cat([sep.out[0].weight.detach().reshape(F, F), sep.gate[0].weight.detach().reshape(F, F)], 0)   # [2F,F]
+    bog = torch.cat([sep.out[0].bias.detach(), sep.gate[0].bias.detach()], 0)
+    pre = ops.gemm(u, wog.t().contiguous(), B * Lm, 2 * F, F, bias=bog)
+    g = ops.empty(B * Lm, F)
+    L_.call('dprnn_gated_fwd', pre, g, B * Lm, F, st)
+    act = EPI_SIGMOID if cfg['activation_type'] == 'sigmoid' else EPI_RELU
+    m = ops.gemm(g, sep.end_conv1x1.weight.detach().reshape(N, F).t().contiguous(), B * Lm, N, F, epi=act)
+    est = ops.empty(B, T)
+    w_dec = model.decoder.weight.detach().reshape(N, 2).contiguous()
+    L_.call('dprnn_mask_decode', m, Lm * N, enc, w_dec, est, T, B, Lm, N, 2, 1, st)
+    logits = ops.empty(B, sep.pred_linear.weight.shape[0])
+    L_.call('dprnn_small_linear', emb, E, sep.pred_linear.weight.detach(), E, sep.pred_linear.bias.detach(), logits,
+            logits.shape[1], B, logits.shape[1], E, 0, st)
+    ctx.update(z=z, u=u, pre=pre, g=g, m=m, wog=wog, cw=cw)
+    return est, logits, ctx
+
+
+# --------------------------------------------------------------------------------------------------------------
+# backward
+# --------------------------------------------------------------------------------------------------------------
+def backward_train(model, ctx, d_est, d_logits):
+    """-> {parameter name: gradient tensor} for every trainable parameter of the model."""
+    L_, cfg, sep = lib(), model.cfg, model.separation
+    dev = d_est.device
+    ops = _Ops(dev)
+    st = _st()
+    N, F, H, K, P = cfg['input_size'], cfg['feature_size'], cfg['hidden_size'], cfg['chunk_length'], cfg['hop_length']
+    B, T, Lm, Lr, S, rows = ctx['B'], ctx['T'], ctx['L'], ctx['Lr'], ctx['S'], ctx['rows']
+    enc, feats, emb, div = ctx['enc'], ctx['feats'], ctx['emb'], ctx['div']
+    E = emb.shape[1]
+    G = {n: torch.zeros_like(p) for n, p in model.named_parameters() if p.requires_grad}
+    d_est, d_logits = d_est.contiguous().float(), d_logits.contiguous().float()
+    ML = B * Lm
+
+    # ---- decoder, mask, end conv, gated head, conv2d
+    m, g, pre, u, z = ctx['m'], ctx['g'], ctx['pre'], ctx['u'], ctx['z']
+    dze = ops.empty(B, Lm, N)
+    w_dec = model.decoder.weight.detach().reshape(N, 2).contiguous()
+    L_.call('dprnn_decoder_bwd', d_est, w_dec, dze, B, Lm, N, st)
+    me = ops.mul(m, enc.view(ML, N))
+    wsw = torch.empty(L_.query('dprnn_convw2_workspace_bytes', N), device=dev, dtype=torch.uint8)
+    L_.call('dprnn_convw2_grad', me, d_est, B, Lm, N, G['decoder.weight'], 1, wsw, st)
+    del me
+    dm = ops.mul(dze.view(ML, N), enc.view(ML, N))
+    denc = ops.mul(dze.view(ML, N), m)                              # gradient reaching enc through the mask product
+    dpm = torch.empty_like(dm)
+    L_.call('dprnn_act_bwd', dm, m, dpm, dm.numel(), 2 if cfg['activation_type'] == 'sigmoid' else 1, st)
+    ops.atb(dpm, g, ML, N, F, G['separation.end_conv1x1.weight'])
+    dg = ops.gemm(dpm, sep.end_conv1x1.weight.detach().reshape(N, F), ML, F, N)
+    dpre = torch.empty_like(pre)
+    L_.call('dprnn_gated_bwd', dg, pre, dpre, ML, F, st)
+    gout, ggate = G['separation.out.0.weight'], G['separation.gate.0.weight']
+    ops.atb(dpre, u, ML, F, F, gout, lda=2 * F)
+    ops.atb(dpre.data_ptr() + 4 * F, u, ML, F, F, ggate, lda=2 * F)
+    ops.colsum(dpre, ML, F, G['separation.out.0.bias'], ldx=2 * F)
+    ops.colsum(dpre.data_ptr() + 4 * F, ML, F, G['separation.gate.0.bias'], ldx=2 * F)
+    du = ops.gemm(dpre, ctx['wog'], ML, F, 2 * F)
+    gcw = G['separation.conv2d.weight']                             # [2F,F,1,1]; only the speaker-0 rows get gradient
+    ops.atb(du, z, ML, F, F, gcw)
+    dbc = ops.empty(F)
+    ops.colsum(du, ML, F, dbc, accumulate=False)
+    L_.call('dprnn_axpy', dbc, 2.0, G['separation.conv2d.bias'], F, 1, st)        # the folded conv adds the bias twice
+    dz = ops.gemm(du, ctx['cw'][:F].contiguous(), ML, F, F)
+    del du, dpre, dg, dpm, dm
+    # fold adjoint = unfold; then the PReLU adjoint on the final residual stream
+    xs = ctx['xs']
+    dxp = ops.empty(B, S, K, F)
+    L_.call('dprnn_unfold', dz, dxp, B, Lm, K, P, F, st)
+    dx = ops.prelu_bwd(dxp, xs, sep.prelu.weight.detach(), G['separation.prelu.weight'])
+    del dxp, dz
+
+    # ---- DPRNN blocks in reverse; the residual stream is walked back with x_in = x_out - norm(y)
+    names = {}
+    for n_, mod in model.named_modules():
+        names[id(mod)] = n_
+    for hv in reversed(ctx['halves']):
+        nd, geo, yl, mr = hv['nd'], hv['geo'], hv['yl'], hv['mr']
+        g_, b_, _ = _norm_params(hv['norm'])
+        pn = names[id(hv['norm'])]
+        gname = pn + ('.gamma' if hasattr(hv['norm'], 'gamma') else '.weight')
+        bname = pn + ('.beta' if hasattr(hv['norm'], 'gamma') else '.bias')
+        L_.call('dprnn_norm_residual', yl, xs, mr, (-g_.detach()).contiguous(), (-b_.detach()).contiguous(), B, S * K, F,
+                None, st)                                            # xs: x_out -> x_in
+        dy = ops.gn_bwd(dx, yl, mr, g_.detach(), B, S * K, F, G[gname], G[bname])
+        ln = names[id(hv['lin'])]
+        ops.atb(dy, hv['hout'], rows, F, nd * H, G[ln + '.weight'])
+        ops.colsum(dy, rows, F, G[ln + '.bias'])
+        dh = ops.gemm(dy, hv['lin'].weight.detach().contiguous(), rows, nd * H, F)
+        del dy
+        dgates = ops.empty(rows, nd * 4 * H)
+        L_.call('dprnn_lstm_bptt_f32', dh, hv['gates'], hv['cst'], hv['whh'], dgates, *geo, H, nd, st)
+        del dh
+        hprev = ops.empty(rows, nd * H)
+        L_.call('dprnn_shift_rows', hv['hout'], hprev, *geo, H, nd, st)
+        rn = names[id(hv['rnn'])]
+        for d, sf in enumerate(hv['sfx']):
+            dgd = dgates.data_ptr() + 4 * d * 4 * H
+            ops.atb(dgd, xs, rows, 4 * H, F, G[f'{rn}.weight_ih_l0{sf}'], lda=nd * 4 * H)
+            ops.atb(dgd, hprev.data_ptr() + 4 * d * H, rows, 4 * H, H, G[f'{rn}.weight_hh_l0{sf}'], lda=nd * 4 * H, ldb=nd * H)
+            ops.colsum(dgd, rows, 4 * H, G[f'{rn}.bias_ih_l0{sf}'], ldx=nd * 4 * H)
+            ops.colsum(dgd, rows, 4 * H, G[f'{rn}.bias_hh_l0{sf}'], ldx=nd * 4 * H)
+        dxl = ops.gemm(dgates, hv['wih'].contiguous(), rows, F, nd * 4 * H)
+        ops.axpy(dxl, dx)                                            # dx (gradient of x_in) = dx_out + LSTM-branch gradient
+        del dgates, hprev, dxl
+        hv['hout'] = hv['gates'] = hv['cst'] = hv['yl'] = None       # free as we go
+
+    # ---- unfold adjoint = fold; bottleneck conv; fusion; bottleneck norm
+    dyb = ops.empty(B, Lm, F)
+    L_.call('dprnn_fold_prelu', dx, dyb, B, Lm, K, P, F, None, st)
+    del dx
+    fused, mulc, addc, mr_e = ctx['fused'], ctx['mulc'], ctx['addc'], ctx['mr_e']
+    gbw = G['separation.bottleneck.1.weight']                       # [F, N(+E), 1]
+    ldw = gbw.shape[1]
+    ops.atb(dyb, fused, ML, F, N, gbw, ldc=ldw)
+    ops.colsum(dyb, ML, F, G['separation.bottleneck.1.bias'])
+    bw = sep.bottleneck[1].weight.detach().reshape(F, -1)
+    dfused = ops.gemm(dyb, bw, ML, N, F, ldw=ldw)                    # first N input channels of the conv
+    demb = torch.zeros_like(emb)
+    ft = cfg['fusion_type']
+    gamma, beta, _ = _norm_params(sep.bottleneck[0])
+    bn0 = 'separation.bottleneck.0'
+    gname = bn0 + ('.gamma' if hasattr(sep.bottleneck[0], 'gamma') else '.weight')
+    bname = bn0 + ('.beta' if hasattr(sep.bottleneck[0], 'gamma') else '.bias')
+
+    def lin_bwd(mod, name, dv):
+        """dv [B, out]: gradient of mod(emb) -> weight / bias gradients, demb += dv @ W"""
+        ops.atb(dv, emb, B, dv.shape[1], E, G[name + '.weight'])
+        ops.colsum(dv, B, dv.shape[1], G[name + '.bias'])
+        wt = mod.weight.detach().t().contiguous()                   # [E, out]: demb[b,e] += sum_j dv[b,j] W[j,e]
+        L_.call('dprnn_small_linear', dv, dv.shape[1], wt, dv.shape[1], None, demb, E, B, E, dv.shape[1], 1, st)
+
+    if ft == 'cat':
+        # constant channels: y += W_e e per utterance -> de = sum_t dy @ W_e ; dW_e = (sum_t dy)^T e
+        sdy = ops.empty(B, F)
+        L_.call('dprnn_utt_col_sum', dyb, None, B, Lm, F, sdy, st)
+        ops.atb(sdy, emb, B, F, E, gbw.data_ptr() + 4 * N, ldc=ldw)
+        t = ops.gemm(sdy, bw.data_ptr() + 4 * N, B, E, F, ldw=ldw)
+        ops.axpy(t, demb)
+        dgn = dfused
+    else:
+        # fused = gn * mulc + addc (mulc / addc may be absent)
+        if addc is not None:
+            da2 = ops.empty(B, N)
+            L_.call('dprnn_utt_col_sum', dfused, None, B, Lm, N, da2, st)
+            lin_bwd(sep.fusion_linear_2 if ft == 'film' else sep.fusion_linear, 'separation.fusion_linear_2' if ft == 'film'
+                    else 'separation.fusion_linear', da2)
+        if mulc is not None:
+            # gn(enc) recomputed from the statistics
+            s1, s0 = ops.empty(B, N), ops.empty(B, N)
+            L_.call('dprnn_norm_affine', mr_e, gamma.detach(), beta.detach(), None, s1, s0, B, N, st)
+            gn = torch.empty_like(enc)
+            L_.call('dprnn_prologue_apply', enc, gn, ML, N, Lm, s1, s0, None, None, st)
+            da1 = ops.empty(B, N)
+            L_.call('dprnn_utt_col_sum', dfused, gn, B, Lm, N, da1, st)
+            lin_bwd(sep.fusion_linear_1 if ft == 'film' else sep.fusion_linear, 'separation.fusion_linear_1' if ft == 'film'
+                    else 'separation.fusion_linear', da1)
+            dgn = torch.empty_like(dfused)
+            L_.call('dprnn_bcast_mul', mulc, dfused, dgn, B, Lm, N, 0, st)
+            del gn
+        else:
+            dgn = dfused
+    # GroupNorm(enc) adjoint, accumulated onto the gradient that reached enc through the mask product
+    ops.gn_bwd(dgn, enc, mr_e, gamma.detach(), B, Lm, N, G[gname], G[bname], dy=denc, accumulate_dy=True)
+    del dgn, dfused, dyb
+
+    # ---- pred_linear, then the speaker encoder
+    lin_bwd(sep.pred_linear, 'separation.pred_linear', d_logits)
+    se = sep.spk_encoder
+    L3, x3 = ctx['L3'], ctx['x3']
+    C5 = se[5].weight.shape[1]
+    dscaled = torch.empty_like(demb)
+    L_.call('dprnn_bcast_mul', (1.0 / div).contiguous().view(B, 1).expand(B, E).contiguous(), demb, dscaled, B, 1, E, 0, st)
+    dz5 = ops.empty(B * L3, E)
+    L_.call('dprnn_bcast_mul', dscaled, None, dz5, B, L3, E, 0, st)
+    ops.atb(dz5, x3, B * L3, E, C5, G['separation.spk_encoder.5.weight'])
+    ops.colsum(dz5, B * L3, E, G['separation.spk_encoder.5.bias'])
+    dout = ops.gemm(dz5, se[5].weight.detach().reshape(E, C5).contiguous(), B * L3, C5, E)
+    del dz5
+    for bi, (rb, rc) in reversed(list(enumerate(zip((se[2], se[3], se[4]), ctx['res'])))):
+        pre_n = f'separation.spk_encoder.{bi + 2}'
+        Cin, Cout, Lx, x = rc['Cin'], rc['Cout'], rc['Lx'], rc['x']
+        rws = B * Lx
+        # recompute v2 = BN2(y2) + skip and p2 = prelu(v2)
+        v2 = ops.empty(rws, Cout)
+        one = torch.ones(1, device=dev)
+        L_.call('dprnn_affine_prelu', rc['y2'], rc['sc2'], rc['sh2'], one, v2, rws, Cout, st)      # slope 1 = identity
+        ops.axpy(rc['skip'], v2)
+        p2 = ops.empty(rws, Cout)
+        ident_s, ident_b = torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev)
+        L_.call('dprnn_affine_prelu', v2, ident_s, ident_b, rb.prelu2.weight.detach(), p2, rws, Cout, st)
+        dp2 = ops.empty(rws, Cout)
+        L_.call('dprnn_pool3_bwd', dout, p2, dp2, B, Lx, Cout, st)
+        dv2 = ops.prelu_bwd(dp2, v2, rb.prelu2.weight.detach(), G[pre_n + '.prelu2.weight'])
+        del p2, dp2, v2
+
+        def bn_bwd(dv, y, scale, shift, bnm, name):
+            gmm = bnm.weight.detach()
+            rstd = (scale / gmm).contiguous()
+            mean = ((bnm.bias.detach() - shift) / scale).contiguous()
+            s_d, s_dy = ops.empty(Cout), ops.empty(Cout)
+            ops.colsum(dv, rws, Cout, s_d, accumulate=False)
+            ops.colsum(dv, rws, Cout, s_dy, Y=y, accumulate=False)
+            s_dyh = (rstd * (s_dy - mean * s_d)).contiguous()        # sum dv * yhat
+            G[name + '.weight'] += s_dyh
+            G[name + '.bias'] += s_d
+            dy = ops.empty(rws, Cout)
+            L_.call('dprnn_bn_bwd_apply', dv, y, mean, rstd, gmm, (s_d / rws).contiguous(), (s_dyh / rws).contiguous(), dy,
+                    rws, Cout, st)
+            return dy
+
+        dy2 = bn_bwd(dv2, rc['y2'], rc['sc2'], rc['sh2'], rb.batch_norm2, pre_n + '.batch_norm2')
+        ops.atb(dy2, rc['a1'], rws, Cout, Cout, G[pre_n + '.conv2.weight'])
+        da1 = ops.gemm(dy2, rb.conv2.weight.detach().reshape(Cout, Cout).contiguous(), rws, Cout, Cout)
+        v1 = ops.empty(rws, Cout)
+        L_.call('dprnn_affine_prelu', rc['y1'], rc['sc1'], rc['sh1'], one, v1, rws, Cout, st)
+        dv1 = ops.prelu_bwd(da1, v1, rb.prelu1.weight.detach(), G[pre_n + '.prelu1.weight'])
+        dy1 = bn_bwd(dv1, rc['y1'], rc['sc1'], rc['sh1'], rb.batch_norm1, pre_n + '.batch_norm1')
+        ops.atb(dy1, x, rws, Cout, Cin, G[pre_n + '.conv1.weight'])
+        dxr = ops.gemm(dy1, rb.conv1.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
+        if hasattr(rb, 'conv_downsample'):
+            ops.atb(dv2, x, rws, Cout, Cin, G[pre_n + '.conv_downsample.weight'])
+            t = ops.gemm(dv2, rb.conv_downsample.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
+            ops.axpy(t, dxr)
+        else:
+            ops.axpy(dv2, dxr)
+        dout = dxr
+        del dy1, dy2, da1, dv1, dv2, v1
+    O = se[1].weight.shape[0]
+    ops.atb(dout, ctx['gnf'], B * Lr, O, N, G['separation.spk_encoder.1.weight'])
+    ops.colsum(dout, B * Lr, O, G['separation.spk_encoder.1.bias'])
+    dgnf = ops.gemm(dout, se[1].weight.detach().reshape(O, N).contiguous(), B * Lr, N, O)
+    dfeats = ops.gn_bwd(dgnf, feats, ctx['mr_s'], se[0].weight.detach(), B, Lr, N, G['separation.spk_encoder.0.weight'],
+                        G['separation.spk_encoder.0.bias'])
+    del dgnf, dout
+
+    # ---- encoder (shared by the mixture and the reference)
+    genc = G['encoder.conv1d.weight']
+    for d_, e_, sig in ((denc, enc, ctx['mix']), (dfeats, feats, ctx['ref'])):
+        dpe = torch.empty_like(d_)
+        L_.call('dprnn_act_bwd', d_, e_, dpe, d_.numel(), 1, st)
+        L_.call('dprnn_convw2_grad', dpe, sig, B, e_.shape[1], N, genc, 1, wsw, st)
+    return G
+
+
+class SpeTrainFunction(torch.autograd.Function):
+    """The whole DPRNN-Spe forward / backward as one autograd node over the model's trainable parameters."""
+
+    @staticmethod
+    def forward(fctx, model, mix, ref, div, *params):
+        est, logits, ctx = forward_train(model, mix, ref, div)
+        fctx.model, fctx.saved = model, ctx
+        fctx.names = [n for n, p in model.named_parameters() if p.requires_grad]
+        return est, logits
+
+    @staticmethod
+    def backward(fctx, d_est, d_logits):
+        if d_logits is None:
+            d_logits = torch.zeros((fctx.saved['B'], fctx.model.separation.pred_linear.weight.shape[0]), device=d_est.device)
+        if d_est is None:
+            d_est = torch.zeros((fctx.saved['B'], fctx.saved['T']), device=d_logits.device)
+        G = backward_train(fctx.model, fctx.saved, d_est, d_logits)
+        fctx.saved = None
+        return (None, None, None, None) + tuple(G[n] for n in fctx.names)
+
+
+def forward_with_grad(model, mix, ref, div):
+    params = [p for _, p in model.named_parameters() if p.requires_grad]
+    return SpeTrainFunction.apply(model, mix, ref, div, *params)
