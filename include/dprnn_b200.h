@@ -330,6 +330,12 @@ int dprnn_att_stats_pool(const float* x, const float* logits, float* out, int B,
  * [b*uniform_len, +uniform_len) when off == len == NULL. */
 int dprnn_si_sdr(const float* est, const float* target, const long* off, const long* len, long uniform_len, int B,
                  float* out_db, void* stream);
+/* The TrainerSpe loss (src/trainers/trainer_spe.py:39-43): loss = mean_b -SI-SDR(est_b, target_b) + ce_gamma *
+ * mean_b CrossEntropy(logits_b, spk_b) (one source, so asteroid's PIT wrapper is the identity).  est / target [B,T],
+ * logits [B,C], spk [B] int64.  terms [B,2] receives the per-utterance (neg SI-SDR, ce_gamma * CE); loss3 = {total,
+ * SI-SDR part, CE part}; d_est [B,T] / d_logits [B,C] receive d loss / d est and d loss / d logits. */
+int dprnn_train_loss(const float* est, const float* target, long T, const float* logits, int C, const long* spk,
+                     float ce_gamma, int B, float* terms, float* loss3, float* d_est, float* d_logits, void* stream);
 /* torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam(lr, (beta1, beta2), eps, weight_decay)
  * .step() over one flat fp32 parameter / gradient buffer (src/trainers/trainer.py:42-43,115-116; step >= 1 is Adam's
  * step count; max_norm <= 0 disables clipping).  total_norm_out[0] receives the global gradient norm. */

@@ -56,3 +56,81 @@ def test_backward_matches_oracle_autograd(fusion, extra):
             worst = (n, err)
         assert err < 2e-3, (n, err)
     print('worst gradient error', worst)
+
+
+def oracle_loss(est, target, logits, spk, gamma=0.5):
+    """TrainerSpe loss (trainer_spe.py:39-43) restated: mean negative SI-SDR + gamma * CrossEntropy."""
+    return (-O.si_sdr_db(est, target)).mean() + gamma * torch.nn.functional.cross_entropy(logits, spk)
+
+
+def test_loss_kernel_matches_autograd():
+    from tss_with_dprnn_b200._lib import lib
+    g = torch.Generator().manual_seed(3)
+    B, T, C = 5, 4001, 251
+    est = (0.1 * torch.randn(B, T, generator=g) + 0.02).double().requires_grad_(True)
+    tgt = 0.05 * torch.randn(B, T, generator=g).double() + 0.7 * est.detach()
+    logits = torch.randn(B, C, generator=g).double().requires_grad_(True)
+    spk = torch.randint(0, C, (B,), generator=g)
+    want = oracle_loss(est, tgt, logits, spk)
+    want.backward()
+    e, t, l = est.detach().float().cuda(), tgt.float().cuda(), logits.detach().float().cuda()
+    terms, loss3 = torch.empty(B, 2, device='cuda'), torch.empty(3, device='cuda')
+    d_est, d_log = torch.empty_like(e), torch.empty_like(l)
+    lib().call('dprnn_train_loss', e, t, T, l, C, spk.cuda(), 0.5, B, terms, loss3, d_est, d_log,
+               torch.cuda.current_stream().cuda_stream)
+    assert abs(float(loss3[0]) - float(want.detach())) < 1e-4 * max(1.0, abs(float(want.detach())))
+    assert abs(float(loss3[1] + loss3[2]) - float(loss3[0])) < 1e-5
+    assert O.peak_rel_err(d_est.cpu(), est.grad.float()) < 1e-4
+    assert O.peak_rel_err(d_log.cpu(), logits.grad.float()) < 1e-5
+
+
+def test_train_steps_match_torch_adam():
+    """Two full iterations (forward, loss, backward, clip 5, Adam 5e-4 / wd 1e-5) against the CPU restatement driven
+    by torch.optim.Adam + clip_grad_norm_ (trainer_spe.py:37-56)."""
+    from tss_with_dprnn_b200.train import SpeTrainStep
+    kw = dict(KW)
+    torch.manual_seed(21)
+    model = P.DPRNNSpeTasNet(**kw, fusion_type='film').train()
+    g = torch.Generator().manual_seed(22)
+    B, T, Tr = 2, 1501, 1300
+    batches = [(0.05 * torch.randn(B, T, generator=g), 0.05 * torch.randn(B, Tr, generator=g),
+                0.05 * torch.randn(B, T, generator=g), torch.randint(0, 251, (B,), generator=g)) for _ in range(2)]
+    # ---- CPU side: fp64 leaves, torch optimiser
+    sd = {k: v.detach().clone().double() for k, v in model.state_dict().items()}
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    leaves = [sd[n].requires_grad_(True) for n in names]
+    opt = torch.optim.Adam(leaves, lr=5e-4, weight_decay=1e-5)
+    cfg = O.Config(**{k: kw[k] for k in ('input_size', 'feature_size', 'hidden_size', 'chunk_length', 'kernel_size',
+                                         'hop_length', 'n_repeats', 'bidirectional', 'norm_type', 'activation_type')},
+                   fusion_type='film')
+    losses_o, norms_o = [], []
+    for mix, ref, tgt, spk in batches:
+        opt.zero_grad()
+        new_stats = {}
+        est, logits = O.spe_forward(mix.double(), ref.double(), torch.tensor(float(Tr)), sd, cfg, training=True,
+                                    new_stats=new_stats, fast=False)
+        loss = oracle_loss(est, tgt.double(), logits, spk)
+        loss.backward()
+        norms_o.append(float(torch.nn.utils.clip_grad_norm_(leaves, 5.0)))
+        opt.step()
+        with torch.no_grad():
+            for k, v in new_stats.items():
+                sd[k] = v.detach()
+        losses_o.append(float(loss))
+    # ---- GPU side
+    model = model.cuda()
+    stepper = SpeTrainStep(model)
+    for i, (mix, ref, tgt, spk) in enumerate(batches):
+        loss3 = stepper.step(mix.cuda(), ref.cuda(), tgt.cuda(), spk.cuda(), ref_len=Tr)
+        assert abs(float(loss3[0]) - losses_o[i]) < 2e-3 * max(1.0, abs(losses_o[i])), (i, float(loss3[0]), losses_o[i])
+        assert abs(float(stepper.opt.total_norm) - norms_o[i]) < 5e-3 * norms_o[i], (i, float(stepper.opt.total_norm), norms_o[i])
+    # Adam normalises the update to ~lr per element, so compare the parameter CHANGE (two steps of <= 5e-4 each)
+    worst = 0.0
+    for n, leaf in zip(names, leaves):
+        got = dict(model.named_parameters())[n].detach().cpu().double()
+        worst = max(worst, float((got - leaf.detach()).abs().max()))
+    assert worst < 1e-4, worst        # vs. a total movement of up to 1e-3 per element
+    sdg = model.state_dict()
+    for k in sd:
+        if 'running_' in k:
+            assert O.peak_rel_err(sdg[k].cpu(), sd[k].float()) < 1e-4, k

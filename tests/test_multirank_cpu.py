@@ -81,7 +81,7 @@ def _grad_worker(rank, world, port, q):
     for _, p in fp.named:
         p.grad.fill_(float(rank + 1))
     allreduce_mean(fp.grad)
-    q.put((rank, fp.numel, float(fp.grad.min()), float(fp.grad.max()),
+    q.put((rank, fp.numel, min(float(p.grad.min()) for _, p in fp.named), float(fp.grad.max()),
            bool(net[0].weight.data_ptr() == fp.flat.data_ptr())))
     dist.destroy_process_group()
 

@@ -7,7 +7,8 @@
 //   * clip_grad_norm_(params, max_norm) + Adam(lr, betas, eps, weight_decay) over ONE flat fp32 buffer
 //     (src/trainers/trainer.py:42-43,115-116; scripts/train/config_tss.yaml:36-39,59): the global norm is reduced
 //     deterministically, the update is a single pass.
-// The backward kernels that would fill the gradient buffer are not built yet (cfg 5).
+//   * the TrainerSpe loss (src/trainers/trainer_spe.py:39-43): mean negative SI-SDR + ce_gamma * CrossEntropy(logits, spk),
+//     forward value and the gradients w.r.t. est / logits in one launch (the backward of the path starts from them).
 #include "common.cuh"
 #include "../../include/dprnn_b200.h"
 
@@ -37,6 +38,73 @@ __global__ void __launch_bounds__(256) si_sdr_kernel(const float* __restrict__ e
         const double n2 = ee - 2.0 * alpha * et + s2;          // |e - s|^2
         out_db[b] = (float)(10.0 * log10(s2 / (fmax(n2, 0.0) + eps) + eps));
     }
+}
+
+// loss_b = -SI-SDR(est_b, tgt_b) + gamma * CE(logits_b, spk_b); one CTA per utterance.  Writes the two terms to
+// terms[b*2 + {0,1}] and the gradients of  (1/B) sum_b loss_b  to d_est / d_logits.
+// With e', t' the zero-mean signals, a = |s|^2, n = |e' - s|^2, r = a / (n + eps):
+//   dr/de' = (2 alpha tt/(tt+eps)) t' / (n+eps) - a/(n+eps)^2 * (2 (e' - alpha t') - 2 (et - alpha tt)/(tt+eps) t')
+// and dL/dr = -10 / (ln 10 (r + eps)).  e' and t' are zero-mean, so the mean-removal adjoint is the identity on them.
+__global__ void __launch_bounds__(256) train_loss_kernel(const float* __restrict__ est, const float* __restrict__ tgt,
+                                                         long T, const float* __restrict__ logits, int C,
+                                                         const long* __restrict__ spk, float gamma, int B,
+                                                         float* __restrict__ terms, float* __restrict__ d_est,
+                                                         float* __restrict__ d_logits) {
+    __shared__ double scratch[32];
+    __shared__ double coef[4];
+    const int b = blockIdx.x;
+    const float* e = est + (long)b * T;
+    const float* t = tgt + (long)b * T;
+    double se = 0, st = 0, see = 0, stt = 0, set = 0;
+    for (long i = threadIdx.x; i < T; i += 256) {
+        const double a = e[i], c = t[i];
+        se += a; st += c; see += a * a; stt += c * c; set += a * c;
+    }
+    se = block_sum(se, scratch); st = block_sum(st, scratch); see = block_sum(see, scratch);
+    stt = block_sum(stt, scratch); set = block_sum(set, scratch);
+    if (threadIdx.x == 0) {
+        const double N = (double)T, eps = 1e-8;
+        const double ee = see - se * se / N, tt = stt - st * st / N, et = set - se * st / N;
+        const double alpha = et / (tt + eps);
+        const double a2 = alpha * alpha * tt;
+        const double n2 = fmax(ee - 2.0 * alpha * et + a2, 0.0);
+        const double r = a2 / (n2 + eps);
+        terms[b * 2] = (float)(-10.0 * log10(r + eps));
+        const double dLdr = -10.0 / (log(10.0) * (r + eps)) / (double)B;
+        const double proj = (et - alpha * tt) / (tt + eps);                 // <e' - alpha t', t'> / (tt + eps)
+        // d r / d e' = 2 alpha tt/((tt+eps)(n+eps)) t' - a/(n+eps)^2 * 2 (e' - alpha t' - proj t')
+        const double ce_ = -2.0 * a2 / ((n2 + eps) * (n2 + eps));           // coefficient of e'
+        const double ct_full = 2.0 * alpha * tt / (tt + eps) / (n2 + eps) - ce_ * (alpha + proj);
+        coef[0] = dLdr * ce_; coef[1] = dLdr * ct_full; coef[2] = se / N; coef[3] = st / N;
+    }
+    __syncthreads();
+    const double c_e = coef[0], c_t = coef[1], me = coef[2], mt = coef[3];
+    for (long i = threadIdx.x; i < T; i += 256)
+        d_est[(long)b * T + i] = (float)(c_e * ((double)e[i] - me) + c_t * ((double)t[i] - mt));
+    // cross entropy over C classes
+    const float* lg = logits + (long)b * C;
+    double mx = -1e300;
+    for (int j = threadIdx.x; j < C; j += 256) mx = fmax(mx, (double)lg[j]);
+    __syncthreads();
+    for (int o = 16; o > 0; o >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    if ((threadIdx.x & 31) == 0) scratch[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = scratch[0];
+    for (int w = 1; w < 8; ++w) mx = fmax(mx, scratch[w]);
+    double sum = 0.0;
+    for (int j = threadIdx.x; j < C; j += 256) sum += exp((double)lg[j] - mx);
+    sum = block_sum(sum, scratch);
+    const long y = spk[b];
+    if (threadIdx.x == 0) terms[b * 2 + 1] = (float)(gamma * (mx + log(sum) - (double)lg[y]));
+    for (int j = threadIdx.x; j < C; j += 256)
+        d_logits[(long)b * C + j] = (float)((double)gamma / B * (exp((double)lg[j] - mx) / sum - (j == y ? 1.0 : 0.0)));
+}
+
+__global__ void train_loss_final_kernel(const float* __restrict__ terms, int B, float* __restrict__ loss) {
+    double s0 = 0.0, s1 = 0.0;
+    for (int i = threadIdx.x; i < B; i += 32) { s0 += terms[i * 2]; s1 += terms[i * 2 + 1]; }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if (threadIdx.x == 0) { loss[0] = (float)((s0 + s1) / B); loss[1] = (float)(s0 / B); loss[2] = (float)(s1 / B); }
 }
 
 __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ g, long n, double* __restrict__ partial) {
@@ -86,6 +154,18 @@ extern "C" int dprnn_si_sdr(const float* est, const float* target, const long* o
                             int B, float* out_db, void* stream) {
     DPRNN_CHECK_ARG(est && target && out_db && B > 0 && ((off && len) || uniform_len > 0));
     si_sdr_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(est, target, off, len, uniform_len, out_db);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_train_loss(const float* est, const float* target, long T, const float* logits, int C, const long* spk,
+                                float ce_gamma, int B, float* terms, float* loss3, float* d_est, float* d_logits,
+                                void* stream) {
+    DPRNN_CHECK_ARG(est && target && logits && spk && terms && loss3 && d_est && d_logits && B > 0 && T > 0 && C > 0);
+    train_loss_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(est, target, T, logits, C, spk, ce_gamma, B, terms, d_est,
+                                                           d_logits);
+    DPRNN_CHECK_LAUNCH();
+    train_loss_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(terms, B, loss3);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

@@ -19,21 +19,27 @@ class FlatParams:
     buffer), in ``named_parameters()`` order restricted to ``requires_grad`` - the set the reference hands to Adam
     (src/trainers/trainer.py:42-43: the frozen ``separation.average.*`` of the attention fusion are excluded)."""
 
+    ALIGN = 64                                                      # elements
+
     def __init__(self, module: torch.nn.Module):
         self.named = [(n, p) for n, p in module.named_parameters() if p.requires_grad]
         if not self.named:
             raise ValueError('no trainable parameters')
         dev = self.named[0][1].device
         self.numel = sum(p.numel() for _, p in self.named)
-        self.flat = torch.empty(self.numel, dtype=torch.float32, device=dev)
-        self.grad = torch.zeros(self.numel, dtype=torch.float32, device=dev)
+        # every parameter starts on a 256-byte boundary (the kernels read weights with 16-byte vector loads); the
+        # padding stays zero in both buffers, so norms, the all-reduce and Adam are unaffected by it
+        pad = lambda n: (n + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.size = sum(pad(p.numel()) for _, p in self.named)
+        self.flat = torch.zeros(self.size, dtype=torch.float32, device=dev)
+        self.grad = torch.zeros(self.size, dtype=torch.float32, device=dev)
         off = 0
         for _, p in self.named:
             n = p.numel()
             self.flat[off:off + n].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + n].view_as(p)              # parameters now alias the flat buffer
             p.grad = self.grad[off:off + n].view_as(p)
-            off += n
+            off += pad(n)
 
     def zero_grad(self):
         self.grad.zero_()
@@ -64,7 +70,7 @@ class ClipAdam:
 
     def step(self):
         self.step_count += 1
-        lib().call('dprnn_clip_adam_step', self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.fp.numel,
+        lib().call('dprnn_clip_adam_step', self.fp.flat, self.fp.grad, self.exp_avg, self.exp_avg_sq, self.fp.size,
                    float(self.lr), float(self.betas[0]), float(self.betas[1]), float(self.eps), float(self.wd),
                    float(self.max_norm), self.step_count, self.ws, self.total_norm,
                    torch.cuda.current_stream().cuda_stream)

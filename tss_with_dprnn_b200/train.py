@@ -248,8 +248,9 @@ def forward_train(model, mix, ref, div):
 # --------------------------------------------------------------------------------------------------------------
 # backward
 # --------------------------------------------------------------------------------------------------------------
-def backward_train(model, ctx, d_est, d_logits):
-    """-> {parameter name: gradient tensor} for every trainable parameter of the model."""
+def backward_train(model, ctx, d_est, d_logits, G=None):
+    """-> {parameter name: gradient tensor} for every trainable parameter of the model.  ``G`` may be given (zeroed
+    views into a flat gradient buffer, dp.FlatParams); every kernel accumulates into it."""
     L_, cfg, sep = lib(), model.cfg, model.separation
     dev = d_est.device
     ops = _Ops(dev)
@@ -258,7 +259,8 @@ def backward_train(model, ctx, d_est, d_logits):
     B, T, Lm, Lr, S, rows = ctx['B'], ctx['T'], ctx['L'], ctx['Lr'], ctx['S'], ctx['rows']
     enc, feats, emb, div = ctx['enc'], ctx['feats'], ctx['emb'], ctx['div']
     E = emb.shape[1]
-    G = {n: torch.zeros_like(p) for n, p in model.named_parameters() if p.requires_grad}
+    if G is None:
+        G = {n: torch.zeros_like(p) for n, p in model.named_parameters() if p.requires_grad}
     d_est, d_logits = d_est.contiguous().float(), d_logits.contiguous().float()
     ML = B * Lm
 
@@ -496,3 +498,51 @@ class SpeTrainFunction(torch.autograd.Function):
 def forward_with_grad(model, mix, ref, div):
     params = [p for _, p in model.named_parameters() if p.requires_grad]
     return SpeTrainFunction.apply(model, mix, ref, div, *params)
+
+
+class SpeTrainStep:
+    """One iteration of TrainerSpe.train (src/trainers/trainer_spe.py:27-56) as device work only:
+    zero_grad -> forward -> loss = mean neg-SI-SDR + ce_gamma * CE -> backward -> [all-reduce (mean) of the flat gradient
+    buffer over the data-parallel group] -> clip_grad_norm_(max_norm) -> Adam(lr, weight_decay).
+
+    The model's trainable parameters are re-seated as views into one flat fp32 buffer (dp.FlatParams), the backward
+    accumulates straight into the matching flat gradient buffer, and the exchange step is ONE collective on it
+    (SURVEY.md section 8e).  The reference has no data-parallel code; with world size 1 the step is the reference's."""
+
+    def __init__(self, model, lr=5e-4, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-5, max_norm=5.0, ce_gamma=0.5,
+                 group=None):
+        from .dp import FlatParams, ClipAdam
+        _check_supported(model)
+        if next(model.parameters()).device.type != 'cuda':
+            raise RuntimeError('SpeTrainStep runs on the GPU (no CPU path)')
+        model.train()
+        self.model, self.group, self.ce_gamma = model, group, float(ce_gamma)
+        self.fp = FlatParams(model)
+        self.opt = ClipAdam(self.fp, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay, max_norm=max_norm)
+        self.G = {n: p.grad for n, p in self.fp.named}
+        dev = self.fp.flat.device
+        self.loss3 = torch.zeros(3, device=dev)
+
+    def loss_and_grads(self, mix, ref, target, spk_idx, ref_len=None):
+        """forward + loss + backward into the flat gradient buffer (no exchange, no update).  -> loss3 (device tensor:
+        total, SI-SDR part, CE part)."""
+        model = self.model
+        mix, ref, target = mix.contiguous().float(), ref.contiguous().float(), target.contiguous().float()
+        B, T = mix.shape
+        div = model._engine._aux_div(ref.shape[1] if ref_len is None else ref_len, B, mix.device)
+        self.fp.zero_grad()
+        est, logits, ctx = forward_train(model, mix, ref, div)
+        C = logits.shape[1]
+        d_est, d_logits = torch.empty_like(est), torch.empty_like(logits)
+        terms = torch.empty(B, 2, device=mix.device)
+        lib().call('dprnn_train_loss', est, target, T, logits, C, spk_idx.contiguous().long(), self.ce_gamma, B, terms,
+                   self.loss3, d_est, d_logits, _st())
+        backward_train(model, ctx, d_est, d_logits, G=self.G)
+        return self.loss3
+
+    def step(self, mix, ref, target, spk_idx, ref_len=None):
+        from .dp import allreduce_mean
+        loss3 = self.loss_and_grads(mix, ref, target, spk_idx, ref_len)
+        allreduce_mean(self.fp.grad, self.group)
+        self.opt.step()
+        return loss3
