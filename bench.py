@@ -142,6 +142,7 @@ def pick_steps(buckets, n):
 
 
 KW4 = dict(KW, embeddings_size=256, fusion_type='att')
+KW5 = dict(KW, fusion_type='film')
 
 
 def model_for(workload):
@@ -151,6 +152,8 @@ def model_for(workload):
         return 'DPRNNSpeIRATasNet', KW
     if workload == 'cfg4':
         return 'DPRNNRawNetTasNet', KW4
+    if workload == 'cfg5':
+        return 'DPRNNSpeTasNet', KW5
     return 'DPRNNSpeTasNet', KW
 
 
@@ -176,6 +179,16 @@ def workload_config(args):
                 'streams': args.streams,
                 'l2': 'no flush needed: each step streams >2 GB of intermediates through a 126 MB L2',
                 'parallelism': f'utterance sharding x{args.gpus}, no collective'}
+    if args.workload == 'cfg5':
+        return {'workload': f'cfg5: DPRNN-Spe (FiLM) training step, {args.samples / SR:g}-s crops @ 8 kHz, batch {args.batch} '
+                            'per GPU, full depth; one step = zero_grad + forward + (neg SI-SDR + 0.5 CE) + backward + '
+                            'all-reduce(mean) of the flat gradient buffer + clip_grad_norm_(5) + Adam(5e-4, wd 1e-5)',
+                'batch_per_gpu': args.batch, 'samples': args.samples,
+                'precision': ('fp32 (CUDA cores, exact)' if args.precision == 'fp32' else
+                              'TF32 tensor-core gate/Linear contractions and weight gradients, fp32 recurrences'), 'streams': 1,
+                'samples_per_step': args.batch * args.gpus,
+                'l2': 'no flush needed: each step streams >100 GB of saved activations through a 126 MB L2',
+                'parallelism': f'data parallel x{args.gpus}, one NCCL all-reduce of 16 MB per step'}
     return {'workload': f'cfg2: DPRNN-Spe (cat) TSS inference, {args.samples / SR:g}-s mix + reference @ 8 kHz, '
                         f'batch {args.batch} per GPU, full depth (6 blocks)',
             'batch_per_gpu': args.batch, 'samples': args.samples, 'precision': args.precision,
@@ -202,6 +215,8 @@ def cpu_forward_fn(workload):
             from src.models.dprnn_spe_ira import DPRNNSpeIRATasNet as RefModel
         else:
             from src.models.dprnn_spe import DPRNNSpeTasNet as RefModel
+        if workload == 'cfg5':
+            return 'reference', cpu_train_step(RefModel(**kw).train())
         model = RefModel(**kw).eval()
         return 'reference', (lambda mix, ref, rl: model(mix, ref, rl)[0])
     from oracle import dprnn_oracle as O
@@ -213,9 +228,30 @@ def cpu_forward_fn(workload):
         return 'port', (lambda mix, ref, rl: RO.rawnet_tasnet_forward(mix, ref, sd, cfg4)[0])
     if workload == 'cfg1':
         return 'port', (lambda mix, ref, rl: O.tasnet_forward(mix, sd, O.Config()))
+    if workload == 'cfg5':      # the port of the model classes is the package's own torch.nn containers + the oracle
+        raise RuntimeError('cfg5 CPU arm needs baseline/_ref (the reference model classes drive torch autograd)')
     cfg = O.Config(fusion_type='cat')
     fwd = O.ira_forward if cls == 'DPRNNSpeIRATasNet' else O.spe_forward
     return 'port', (lambda mix, ref, rl: fwd(mix, ref, rl, sd, cfg)[0])
+
+
+def cpu_train_step(model):
+    """The TrainerSpe iteration on the CPU with the reference's own model class (trainer_spe.py:31-56)."""
+    opt = torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=5e-4, weight_decay=1e-5)
+    g = torch.Generator().manual_seed(77)
+
+    def step(mix, ref, rl):
+        target = 0.05 * torch.randn(mix.shape, generator=g)
+        spk = torch.randint(0, 251, (mix.shape[0],), generator=g)
+        with torch.enable_grad():
+            opt.zero_grad()
+            est, logits = model(mix, ref, rl)
+            loss = train_loss_cpu(est, target, logits, spk)
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 5)
+            opt.step()
+        return float(loss)
+    return step
 
 
 def cpu_sample(args):
@@ -349,6 +385,52 @@ class Cfg4(Cfg2):
         return 3 * self.B * self.T * 4, self.B * self.T * 4
 
 
+def train_loss_cpu(est, target, logits, spk, gamma=0.5):
+    """TrainerSpe's loss (trainer_spe.py:39-43) restated for the CPU arm: asteroid's pairwise_neg_sisdr with one source
+    (zero-mean, eps 1e-8) + gamma * CrossEntropy."""
+    e = est - est.mean(-1, keepdim=True)
+    t = target - target.mean(-1, keepdim=True)
+    s = (e * t).sum(-1, keepdim=True) * t / (t.pow(2).sum(-1, keepdim=True) + 1e-8)
+    sdr = 10 * torch.log10(s.pow(2).sum(-1) / ((e - s).pow(2).sum(-1) + 1e-8) + 1e-8)
+    return (-sdr).mean() + gamma * torch.nn.functional.cross_entropy(logits, spk)
+
+
+class Cfg5:
+    """BASELINE.json configs[4]: the TrainerSpe iteration (trainer_spe.py:27-56) on equal-length 3-s crops."""
+
+    def __init__(self, args, model, rank, dev):
+        from tss_with_dprnn_b200.train import SpeTrainStep
+        B, T = args.batch, args.samples
+        self.B, self.T, self.dev = B, T, dev
+        self.stepper = SpeTrainStep(model)
+        g = torch.Generator().manual_seed(555 + 1000 * rank)
+        self.h = [(0.05 * torch.randn(B, T, generator=g)).pin_memory() for _ in range(3)]      # mix, ref, target
+        self.spk_h = torch.randint(0, 251, (B,), generator=g).pin_memory()
+        self.d = [x.to(dev) for x in self.h]
+        self.spk = self.spk_h.to(dev)
+        self.loss_h = torch.empty(3).pin_memory()
+        self.n_steps = 1
+
+    def audio(self, i):
+        return self.B * self.T / SR
+
+    def positions(self, i):
+        return self.B * POS_PER_UTT
+
+    def resident(self, i):
+        return self.stepper.step(self.d[0], self.d[1], self.d[2], self.spk, ref_len=self.T)
+
+    def e2e(self, i):
+        d = [x.to(self.dev, non_blocking=True) for x in self.h]
+        spk = self.spk_h.to(self.dev, non_blocking=True)
+        loss3 = self.stepper.step(d[0], d[1], d[2], spk, ref_len=self.T)
+        self.loss_h.copy_(loss3, non_blocking=True)
+        torch.cuda.current_stream().synchronize()      # trainer_spe.py:44 loss.item()
+
+    def bytes(self, i):
+        return 3 * self.B * self.T * 4 + self.B * 8, 12
+
+
 class Cfg3:
     """BASELINE.json configs[2]: full-length variable-duration utterances as ragged batches (model.forward_ragged)."""
 
@@ -420,6 +502,8 @@ def run_ours(args):
         wl = Cfg4(args, model, rank, dev)
     elif args.workload == 'cfg1':
         wl = Cfg1(args, model, rank, dev)
+    elif args.workload == 'cfg5':
+        wl = Cfg5(args, model.train(), rank, dev)
     else:
         wl = Cfg2(args, model, rank, dev)
 
@@ -476,12 +560,14 @@ def run_ours(args):
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)     # kernel timed inside a long step -> sustained figure
     roofline = None
     lstm_names = [n for n in per_kernel if n in (dominant, 'dprnn_lstm_inter_bf16_ragged')]
+    if args.workload == 'cfg5':
+        lstm_names = [n for n in per_kernel if n in ('dprnn_lstm_recurrence_f32_train', 'dprnn_lstm_bptt_f32')]
     if lstm_names:
         ms_lstm = sum(per_kernel[n]['ms_total'] for n in lstm_names)
         n_launch = sum(per_kernel[n]['launches'] for n in lstm_names)
         # one launch = one RNN layer (both directions) over every chunk position of the step; the fused bf16 kernel
         # also does the input projection: 2 * 2 * 128 * 512 flop per position and direction (else 2 * 128 * 512)
-        flop_per_pos = 2 * (2 if args.precision == 'bf16' else 1) * 2 * 128 * 512
+        flop_per_pos = 2 * (2 if args.precision == 'bf16' and args.workload != 'cfg5' else 1) * 2 * 128 * 512
         flop_per_launch = flop_per_pos * wl.positions(0) / (2 if args.workload == 'cfg3' else 1)
         achieved = flop_per_launch * n_launch / (ms_lstm * 1e-3) / 1e12
         roofline = {'kernel': '+'.join(lstm_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
@@ -495,7 +581,7 @@ def run_ours(args):
                     'share_of_step_single_stream': ms_lstm / sum(k['ms_total'] for k in per_kernel.values()),
                     'note': ('algorithmic flops = [x_t|h_{t-1}] [W_ih|W_hh]^T, 2*256*512 per chunk position and direction; '
                              'launches timed one by one on a single stream'
-                             if args.precision == 'bf16' else
+                             if args.precision == 'bf16' and args.workload != 'cfg5' else
                              'algorithmic flops = h W_hh^T only (2*128*512 per position and direction); the fp32 mode '
                              'runs this on CUDA cores, so its fraction of the bf16 tensor peak is small by construction')}
 
@@ -503,13 +589,14 @@ def run_ours(args):
     if rank == 0 and not args.no_cpu_baseline:
         kind, cores, times, audio, desc = time_cpu(args, 2, 1)
         cpu = {'value': audio * len(times) / sum(times), 'unit': 'audio-s/s', 'cores': cores, 'kind': kind,
-               'sample': desc + ', 1 warm-up + 2 timed forwards, fp32, eval()'}
+               'sample': desc + (', 1 warm-up + 2 timed training iterations, fp32, train()' if args.workload == 'cfg5'
+                                  else ', 1 warm-up + 2 timed forwards, fp32, eval()')}
 
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'bf16 gate/linear contractions, f32 accumulate+state',
+            'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'tf32 gate/linear contractions, f32 accumulate+state' if args.workload == 'cfg5' else 'bf16 gate/linear contractions, f32 accumulate+state',
             'data': 'synthetic', 'config': workload_config(args), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'kernels': per_kernel,
@@ -526,9 +613,9 @@ def main():
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--workload', default='cfg2', choices=['cfg1', 'cfg2', 'cfg3', 'cfg4'],
+    ap.add_argument('--workload', default='cfg2', choices=['cfg1', 'cfg2', 'cfg3', 'cfg4', 'cfg5'],
                     help='cfg1: DPRNN-TasNet B=1; cfg2 (headline): DPRNN-Spe cat, 3-s batch 64; cfg3: DPRNN-Spe-IRA on the ragged test-set lengths; '
-                         'cfg4: DPRNN-RawNet3 att, batch 16 per GPU')
+                         'cfg4: DPRNN-RawNet3 att, batch 16 per GPU; cfg5: DPRNN-Spe FiLM training step, batch 16 per GPU')
     ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--streams', type=int, default=int(os.environ.get('DPRNN_STREAMS', '3')),
                     help='concurrent CUDA streams the batch is split over inside one forward (cfg2)')
@@ -539,8 +626,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     args = ap.parse_args()
     if args.batch is None:
-        args.batch = {'cfg1': 1, 'cfg4': 16}.get(args.workload, 64)
-    if args.workload == 'cfg1':
+        args.batch = {'cfg1': 1, 'cfg4': 16, 'cfg5': 16}.get(args.workload, 64)
+    if args.workload in ('cfg1', 'cfg5'):
         args.streams = 1
     if args.warmup < 3 and args.impl == 'ours':
         args.warmup = 3

@@ -367,6 +367,13 @@ int dprnn_shift_rows(const float* h, float* out, long nseq, int T, long seq_div,
 size_t dprnn_gemm_atb_workspace_bytes(long M, int N1, int N2);
 int dprnn_gemm_atb(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N1, int N2,
                    int accumulate, void* workspace, void* stream);
+/* dprnn_gemm_atb on the tensor cores: both operands are read straight from fp32 memory as MN-major TF32 tiles (TMA,
+ * 128B swizzle), fp32 accumulation in TMEM, deterministic split-row reduction.  Built for one of N1 / N2 == 128 and the
+ * other a multiple of 128 (the LSTM / Linear weight gradients); dprnn_gemm_atb_tc_supported() tells. */
+int dprnn_gemm_atb_tc_supported(int N1, int N2, long lda, long ldb);
+size_t dprnn_gemm_atb_tc_workspace_bytes(int N1, int N2);
+int dprnn_gemm_atb_tc(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N1, int N2,
+                      int accumulate, void* workspace, void* stream);
 /* out[n] (+)= sum_m X[m,n] (* Y[m,n] if Y): bias gradients, BatchNorm reductions. */
 size_t dprnn_col_sum_workspace_bytes(int N);
 int dprnn_col_sum(const float* X, long ldx, const float* Y, long ldy, long M, int N, float* out, int accumulate,

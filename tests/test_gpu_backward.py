@@ -37,6 +37,30 @@ def test_gemm_atb(M, N1, N2):
     assert rel(out.cpu(), A.double().sum(0)) < 1e-5
 
 
+@pytest.mark.parametrize('M,N1,N2,lda,ldb', [(50017, 512, 128, 1024, 256), (48500, 128, 256, 128, 256),
+                                             (20000, 128, 128, 128, 128), (4100, 256, 128, 256, 128),
+                                             (100, 512, 128, 512, 128)])
+def test_gemm_atb_tensor_core(M, N1, N2, lda, ldb):
+    """The MN-major TF32 weight-gradient contraction against fp64 (operands are column slices of wider row-major
+    tensors, as the per-direction slices of dgates / h_prev are)."""
+    L = P.lib()
+    assert L.query('dprnn_gemm_atb_tc_supported', N1, N2, lda, ldb)
+    Af, Bf = rnd(M, lda, seed=1).to(DEV), rnd(M, ldb, seed=2).to(DEV)
+    a_off, b_off = lda - N1, ldb - N2                    # the last N columns of each
+    want = Af[:, a_off:].double().t() @ Bf[:, b_off:].double()
+    C = torch.full((N1, N2 + 4), 3.0, device=DEV)       # ldc > N2: the padding must stay untouched
+    ws = torch.empty(L.query('dprnn_gemm_atb_tc_workspace_bytes', N1, N2), device=DEV, dtype=torch.uint8)
+    L.call('dprnn_gemm_atb_tc', Af.data_ptr() + 4 * a_off, lda, Bf.data_ptr() + 4 * b_off, ldb, C, N2 + 4, M, N1, N2, 0,
+           ws, st())
+    scale = float(want.abs().max())
+    assert float((C[:, :N2].double() - want).abs().max()) < 3e-3 * scale
+    assert float((C[:, N2:] - 3.0).abs().max()) == 0.0
+    first = C.clone()
+    L.call('dprnn_gemm_atb_tc', Af.data_ptr() + 4 * a_off, lda, Bf.data_ptr() + 4 * b_off, ldb, C, N2 + 4, M, N1, N2, 1,
+           ws, st())
+    assert torch.equal(C[:, :N2], 2 * first[:, :N2])     # deterministic reduction order, accumulate adds exactly
+
+
 def test_groupnorm_bwd():
     L = P.lib()
     B, R, C = 3, 777, 128

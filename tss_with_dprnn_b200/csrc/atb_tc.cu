@@ -1,0 +1,194 @@
+// Weight-gradient contraction of the training step (cfg 5) on the tensor cores:
+//     C[N1,N2] (+)= A[M,N1]^T B[M,N2]        (M = every chunk position of the batch, ~10^6; N1, N2 <= 1024)
+// e.g. dW_ih = dgates^T x, dW_hh = dgates^T h_{t-1}, dW_linear = dy^T h  (backward of src/models/dprnn.py:51-70).
+// Both operands are row-major activations, i.e. the contraction index (the row) is the SLOW index: for tcgen05 they
+// are MN-major operands.  For 32-bit MN-major operands the only swizzled shared-memory layout the tensor core reads is
+// SWIZZLE_128B with a 32-byte base (32-byte chunks of each 128-byte line XOR-ed with the line index mod 4).  TMA writes
+// exactly that with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B: [32 rows x 32 columns] fp32 boxes land as 128-byte lines,
+// 4-line groups of 512 B (= SBO), column groups of 32 one box apart (= LBO); tcgen05.mma kind::tf32 consumes them with
+// the a_major / b_major bits set - no transposition pass, no conversion pass.
+// One operand (128 columns wide) takes the MMA's M role, the other is cut into N tiles of 256 (or 128) columns.  grid = (column tiles, row splits) ~ one CTA per SM; every CTA streams its row range through
+// a 4-stage TMA ring, accumulates in TMEM (fp32) and writes one [tile, 128] partial; a second kernel adds the
+// partials in a fixed order (deterministic) into C.
+#include "tc_common.cuh"
+#include "../../include/dprnn_b200.h"
+
+namespace dprnn {
+using namespace tc;
+
+constexpr int AB_KB = 32;        // contraction rows per stage (4 MMAs of K = 8)
+constexpr int AB_NST = 4;
+constexpr uint32_t AB_GROUP = AB_KB * 128;      // bytes of one 32-column group of a stage = LBO
+
+// MN-major SWIZZLE_128B_BASE32B operand: start>>4 [0,14), LBO>>4 [16,30) = distance between 32-column groups, SBO>>4
+// [32,46) = distance between 4-row groups (512), version 1 [46,48), layout SWIZZLE_128B_BASE32B = 1 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr) {
+    return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(AB_GROUP >> 4) << 16) | ((uint64_t)(512 >> 4) << 32) |
+           ((uint64_t)1 << 46) | ((uint64_t)1 << 61);
+}
+// kind::tf32, D = f32, A and B MN-major (bits 15, 16)
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_mn(int M, int N) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(192) atb_tc_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                     const __grid_constant__ CUtensorMap tmY, long M,
+                                                     long rows_per_split, int nyt, int ycols,
+                                                     float* __restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[AB_NST], bar_empty[AB_NST], bar_done;
+    __shared__ uint32_t tmem_base_s;
+    const uint32_t X_BYTES = 4 * AB_GROUP, Y_BYTES = (uint32_t)(nyt / 32) * AB_GROUP, STAGE = X_BYTES + Y_BYTES;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const long r0 = (long)split * rows_per_split;
+    const long r1 = r0 + rows_per_split < M ? r0 + rows_per_split : M;
+    const int num_kb = r1 > r0 ? (int)((r1 - r0 + AB_KB - 1) / AB_KB) : 0;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmX);
+        prefetch_tmap(&tmY);
+        for (int s = 0; s < AB_NST; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc<1>(&tmem_base_s, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % AB_NST;
+                mbar_wait(&bar_empty[s], ((kb / AB_NST) & 1) ^ 1);
+                mbar_expect_tx(&bar_full[s], STAGE);
+                const int row = (int)(r0 + (long)kb * AB_KB);
+                tma_load_3d(smem + s * STAGE, &tmX, &bar_full[s], 0, row, 0);
+                tma_load_3d(smem + s * STAGE + X_BYTES, &tmY, &bar_full[s], 0, row, tile * (nyt / 32));
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_tf32_mn(128, nyt);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % AB_NST;
+                mbar_wait(&bar_full[s], (kb / AB_NST) & 1);
+                tc_fence_after();
+                const uint32_t sx = smem_u32(smem + s * STAGE), sy = sx + X_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < AB_KB / 8; ++kk) {
+                    const uint32_t acc = (kb | kk) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem), "l"(umma_desc_sw128_mn(sx + kk * 1024)), "l"(umma_desc_sw128_mn(sy + kk * 1024)),
+                          "r"(idesc), "r"(acc) : "memory");
+                }
+                umma_commit(&bar_empty[s]);
+            }
+            umma_commit(&bar_done);
+        }
+        __syncwarp();
+    } else {
+        // epilogue warps 2..5 -> TMEM lane quadrant warp % 4; lane = column of X, TMEM column = column of Y
+        const int q = warp & 3;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+        float* dst = partial + ((long)split * ycols + (long)tile * nyt) * 128 + q * 32 + lane;
+        if (num_kb > 0) {
+            mbar_wait(&bar_done, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < nyt; c0 += 32) {
+            float v[32];
+            if (num_kb > 0) {
+                tmem_ld32(taddr + c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) dst[(long)(c0 + j) * 128] = v[j];       // 32 lanes -> 128 contiguous bytes
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<1>(tmem, 256);
+}
+
+// C (+)= sum over splits (fixed order).  partial[split][y][x]; x_is_row: C[x, y] else C[y, x]
+__global__ void atb_tc_reduce_kernel(const float* __restrict__ partial, int splits, int ycols, float* __restrict__ C,
+                                     long ldc, int x_is_row, int accumulate) {
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= (long)ycols * 128) return;
+    const int y = (int)(e >> 7), x = (int)(e & 127);
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(long)k * ycols * 128 + e];
+    float* dst = x_is_row ? C + (long)x * ldc + y : C + (long)y * ldc + x;
+    *dst = accumulate ? *dst + s : s;
+}
+
+static void atb_tc_plan(long M, int ycols, int* nyt, int* tiles, int* splits, long* rows_per_split) {
+    *nyt = ycols % 256 == 0 ? 256 : 128;
+    *tiles = ycols / *nyt;
+    long sp = 148 / *tiles;
+    const long max_sp = (M + 4 * AB_KB - 1) / (4 * AB_KB);       // at least 4 stages of rows per split
+    if (sp > max_sp) sp = max_sp;
+    if (sp < 1) sp = 1;
+    long rps = (M + sp - 1) / sp;
+    rps = (rps + AB_KB - 1) / AB_KB * AB_KB;
+    *rows_per_split = rps;
+    *splits = (int)((M + rps - 1) / rps);
+}
+
+}  // namespace dprnn
+
+using namespace dprnn;
+
+extern "C" int dprnn_gemm_atb_tc_supported(int N1, int N2, long lda, long ldb) {
+    const bool shape = (N1 == 128 && N2 % 128 == 0 && N2 <= 4096) || (N2 == 128 && N1 % 128 == 0 && N1 <= 4096);
+    return shape && lda % 4 == 0 && ldb % 4 == 0 && N1 > 0 && N2 > 0;
+}
+
+extern "C" size_t dprnn_gemm_atb_tc_workspace_bytes(int N1, int N2) {
+    return (size_t)148 * (size_t)(N1 > N2 ? N1 : N2) * 128 * sizeof(float);
+}
+
+extern "C" int dprnn_gemm_atb_tc(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N1,
+                                 int N2, int accumulate, void* workspace, void* stream) {
+    DPRNN_CHECK_ARG(A && B && C && workspace && M > 0 && M < (1L << 31) && dprnn_gemm_atb_tc_supported(N1, N2, lda, ldb));
+    DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)B) % 16 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    // X = the 128-column operand (MMA M role); prefer X = B so that C rows are written along x (coalesced)
+    const bool x_is_b = N2 == 128;
+    const float* X = x_is_b ? B : A;
+    const float* Y = x_is_b ? A : B;
+    const long ldx = x_is_b ? ldb : lda, ldy = x_is_b ? lda : ldb;
+    const int ycols = x_is_b ? N1 : N2;
+    int nyt, tiles, splits;
+    long rps;
+    atb_tc_plan(M, ycols, &nyt, &tiles, &splits, &rps);
+    CUtensorMap tmX, tmY;
+    // dims innermost first: 32 columns (one 128-byte line), rows, column groups
+    const uint64_t dX[3] = {32, (uint64_t)M, 4}, sX[3] = {4, (uint64_t)ldx * 4, 128};
+    const uint32_t bX[3] = {32, AB_KB, 4};
+    const uint64_t dY[3] = {32, (uint64_t)M, (uint64_t)(ycols / 32)}, sY[3] = {4, (uint64_t)ldy * 4, 128};
+    const uint32_t bY[3] = {32, AB_KB, (uint32_t)(nyt / 32)};
+    if (make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, X, dX, sX, bX, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    if (make_tmap(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, Y, dY, sY, bY, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    const size_t smem = (size_t)AB_NST * (4 + nyt / 32) * AB_GROUP + 1024;
+    DPRNN_CUDA(cudaFuncSetAttribute(atb_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    atb_tc_kernel<<<dim3(tiles, splits), 192, smem, st>>>(tmX, tmY, M, rps, nyt, ycols, (float*)workspace);
+    DPRNN_CHECK_LAUNCH();
+    const long total = (long)ycols * 128;
+    atb_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, splits, ycols, C, ldc,
+                                                                        x_is_b ? 0 : 1, accumulate);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}

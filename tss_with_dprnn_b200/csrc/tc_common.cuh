@@ -207,6 +207,6 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
 PFN_encodeTiled get_encode_tiled();
 // rank <= 5; dims/strides innermost first; strides in BYTES for dims 1..rank-1; 128B swizzle
 int make_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box);
+              const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B);
 
 }  // namespace dprnn

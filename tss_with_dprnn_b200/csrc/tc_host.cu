@@ -16,7 +16,7 @@ PFN_encodeTiled get_encode_tiled() {
 }
 
 int make_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void* base, const uint64_t* dims,
-              const uint64_t* strides_bytes, const uint32_t* box) {
+              const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swizzle) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -27,7 +27,7 @@ int make_tmap(CUtensorMap* map, CUtensorMapDataType dtype, int rank, const void*
     for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
     for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i + 1];
     CUresult r = enc(map, dtype, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (CUresult %d) rank=%d dims=[%llu,%llu,...] box=[%u,%u,...]", (int)r,

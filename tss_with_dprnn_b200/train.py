@@ -28,9 +28,10 @@ def _st():
 class _Ops:
     """Thin wrappers that allocate outputs / workspaces (PyTorch = device memory only)."""
 
-    def __init__(self, dev):
+    def __init__(self, dev, tf32=False):
         self.dev = dev
         self.L = lib()
+        self.tf32 = tf32                # big contractions on the tensor cores (TF32 operands, fp32 accumulation)
 
     def empty(self, *shape):
         return torch.empty(shape, device=self.dev, dtype=torch.float32)
@@ -43,8 +44,23 @@ class _Ops:
                     pro.get('p_shift'), pro.get('p_add'), None, epi, _st())
         return out
 
+    def mm(self, A, W, M, N, K, bias=None):
+        """C[M,N] = A[M,K] @ W[N,K]^T + bias with W in nn.Linear layout; tensor cores in tf32 mode."""
+        if not (self.tf32 and K % 32 == 0 and N % 64 == 0 and M >= 128):
+            return self.gemm(A, W.t().contiguous(), M, N, K, bias=bias)
+        out = self.empty(M, N)
+        step = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 64)
+        for n0 in range(0, N, step):
+            self.L.call('dprnn_gemm_tc', A, 0, W[n0:n0 + step], None if bias is None else bias[n0:n0 + step],
+                        out.data_ptr() + 4 * n0, N, M, step, K, EPI_NONE, None, 0, 0.0, None, _st())
+        return out
+
     def atb(self, A, B, M, N1, N2, out, lda=None, ldb=None, ldc=None, accumulate=True):
         """out[N1,N2] (+)= A[M,N1]^T B[M,N2]"""
+        if self.tf32 and M >= 4096 and self.L.query('dprnn_gemm_atb_tc_supported', N1, N2, lda or N1, ldb or N2):
+            ws = torch.empty(self.L.query('dprnn_gemm_atb_tc_workspace_bytes', N1, N2), device=self.dev, dtype=torch.uint8)
+            self.L.call('dprnn_gemm_atb_tc', A, lda or N1, B, ldb or N2, out, ldc or N2, M, N1, N2, int(accumulate), ws, _st())
+            return
         ws = torch.empty(self.L.query('dprnn_gemm_atb_workspace_bytes', M, N1, N2), device=self.dev, dtype=torch.uint8)
         self.L.call('dprnn_gemm_atb', A, lda or N1, B, ldb or N2, out, ldc or N2, M, N1, N2, int(accumulate), ws, _st())
 
@@ -104,12 +120,12 @@ def forward_train(model, mix, ref, div):
     _check_supported(model)
     L_, cfg, sep = lib(), model.cfg, model.separation
     dev = mix.device
-    ops = _Ops(dev)
+    ops = _Ops(dev, tf32=model.precision == 'bf16')
     st = _st()
     N, F, H, K, P = cfg['input_size'], cfg['feature_size'], cfg['hidden_size'], cfg['chunk_length'], cfg['hop_length']
     B, T = mix.shape
     Lm, Lr = T - 1, ref.shape[1] - 1
-    ctx = dict(B=B, T=T, L=Lm, Lr=Lr, mix=mix, ref=ref, div=div)
+    ctx = dict(B=B, T=T, L=Lm, Lr=Lr, mix=mix, ref=ref, div=div, tf32=ops.tf32)
     w_enc = model.encoder.conv1d.weight.detach().reshape(N, 2).contiguous()
     enc = ops.empty(B, Lm, N)
     L_.call('dprnn_encoder_fwd', mix, w_enc, enc, B, T, N, 2, 1, st)
@@ -210,12 +226,12 @@ def forward_train(model, mix, ref, div):
             wih = torch.cat([getattr(rnn, 'weight_ih_l0' + s).detach() for s in sfx], 0)              # [nd*4H, F]
             b = torch.cat([(getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s)).detach() for s in sfx], 0)
             whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach() for s in sfx], 0).contiguous()   # [nd,4H,H]
-            gx = ops.gemm(xs, wih.t().contiguous(), rows, nd * 4 * H, F, bias=b)
+            gx = ops.mm(xs, wih, rows, nd * 4 * H, F, bias=b)
             geo = (B * S, K, 1, K, 0, 1) if which == 0 else (B * K, S, K, S * K, 1, K)
             hout, gates, cst = ops.empty(rows, nd * H), ops.empty(rows, nd * 4 * H), ops.empty(rows, nd * H)
             L_.call('dprnn_lstm_recurrence_f32_train', gx, whh.transpose(1, 2).contiguous(), hout, gates, cst, *geo, H, nd, st)
             del gx
-            yl = ops.gemm(hout, linm.weight.detach().t().contiguous(), rows, F, nd * H, bias=linm.bias.detach())
+            yl = ops.mm(hout, linm.weight.detach(), rows, F, nd * H, bias=linm.bias.detach())
             g_, b_, eps_ = _norm_params(nm)
             mr = ops.utt_stats(yl, B, S * K * F, eps_)
             L_.call('dprnn_norm_residual', yl, xs, mr, g_.detach(), b_.detach(), B, S * K, F, None, st)
@@ -253,7 +269,7 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
     views into a flat gradient buffer, dp.FlatParams); every kernel accumulates into it."""
     L_, cfg, sep = lib(), model.cfg, model.separation
     dev = d_est.device
-    ops = _Ops(dev)
+    ops = _Ops(dev, tf32=ctx['tf32'])
     st = _st()
     N, F, H, K, P = cfg['input_size'], cfg['feature_size'], cfg['hidden_size'], cfg['chunk_length'], cfg['hop_length']
     B, T, Lm, Lr, S, rows = ctx['B'], ctx['T'], ctx['L'], ctx['Lr'], ctx['S'], ctx['rows']
@@ -317,7 +333,7 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
         ln = names[id(hv['lin'])]
         ops.atb(dy, hv['hout'], rows, F, nd * H, G[ln + '.weight'])
         ops.colsum(dy, rows, F, G[ln + '.bias'])
-        dh = ops.gemm(dy, hv['lin'].weight.detach().contiguous(), rows, nd * H, F)
+        dh = ops.mm(dy, hv['lin'].weight.detach().t().contiguous(), rows, nd * H, F)
         del dy
         dgates = ops.empty(rows, nd * 4 * H)
         L_.call('dprnn_lstm_bptt_f32', dh, hv['gates'], hv['cst'], hv['whh'], dgates, *geo, H, nd, st)
@@ -331,7 +347,7 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
             ops.atb(dgd, hprev.data_ptr() + 4 * d * H, rows, 4 * H, H, G[f'{rn}.weight_hh_l0{sf}'], lda=nd * 4 * H, ldb=nd * H)
             ops.colsum(dgd, rows, 4 * H, G[f'{rn}.bias_ih_l0{sf}'], ldx=nd * 4 * H)
             ops.colsum(dgd, rows, 4 * H, G[f'{rn}.bias_hh_l0{sf}'], ldx=nd * 4 * H)
-        dxl = ops.gemm(dgates, hv['wih'].contiguous(), rows, F, nd * 4 * H)
+        dxl = ops.mm(dgates, hv['wih'].t().contiguous(), rows, F, nd * 4 * H)
         ops.axpy(dxl, dx)                                            # dx (gradient of x_in) = dx_out + LSTM-branch gradient
         del dgates, hprev, dxl
         hv['hout'] = hv['gates'] = hv['cst'] = hv['yl'] = None       # free as we go
