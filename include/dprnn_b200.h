@@ -323,6 +323,13 @@ int dprnn_affine_vec(const float* x, const float* scale, const float* shift, flo
  * out[b, c] = sum_t x w, out[b, C + c] = sqrt(clamp(sum_t x^2 w - mu^2, 1e-4, 1e4)). */
 int dprnn_att_stats_pool(const float* x, const float* logits, float* out, int B, long T, int C, void* stream);
 
+/* Polyphase FIR resampling of the reference utterance before RawNet3 (torchaudio.transforms.Resample(8000, 16000) in
+ * src/inferencers/inferencer_rawnet.py:21-23,36 and src/trainers/trainer_rawnet.py:14-16,31): x [B,T] -> out [B,To],
+ * out[b, q*nw + i] = sum_k kernel[i,k] * x[b, q*orig + k - width] (zero outside), kernel [nw, taps] from the host
+ * (windowed-sinc, tss_with_dprnn_b200/resample.py). */
+int dprnn_resample_fir(const float* x, const float* kernel, float* out, int B, long T, long To, int orig, int nw,
+                       int taps, int width, void* stream);
+
 /* ---- the callers' side of the path ---- */
 
 /* SI-SDR in dB per utterance (asteroid recipe: zero-mean, eps 1e-8; src/trainers/trainer_spe.py:39,

@@ -145,7 +145,7 @@ def test_train_steps_match_torch_adam():
         with torch.no_grad():
             for k, v in new_stats.items():
                 sd[k] = v.detach()
-        losses_o.append(float(loss))
+        losses_o.append(float(loss.detach()))
     # ---- GPU side
     model = model.cuda()
     stepper = SpeTrainStep(model)
@@ -163,3 +163,38 @@ def test_train_steps_match_torch_adam():
     for k in sd:
         if 'running_' in k:
             assert O.peak_rel_err(sdg[k].cpu(), sd[k].float()) < 1e-4, k
+
+
+def test_checkpoint_roundtrip_in_reference_format(tmp_path):
+    """{'epoch','optimizer','model'} (trainer.py:294-306): torch.optim.Adam accepts the optimizer state, and a stepper
+    restored from the file continues bit-identically."""
+    from tss_with_dprnn_b200.train import SpeTrainStep
+    kw = dict(KW)
+    g = torch.Generator().manual_seed(31)
+    B, T = 2, 1501
+    batch = lambda: (0.05 * torch.randn(B, T, generator=g).cuda(), 0.05 * torch.randn(B, T, generator=g).cuda(),
+                     0.05 * torch.randn(B, T, generator=g).cuda(), torch.randint(0, 251, (B,), generator=g).cuda())
+    torch.manual_seed(5)
+    a = SpeTrainStep(P.DPRNNSpeTasNet(**kw, fusion_type='film').cuda())
+    a.step(*batch())
+    path = str(tmp_path / '1_last.pt')
+    a.save_checkpoint(path, epoch=1)
+    cpt = torch.load(path, map_location='cpu')
+    assert set(cpt) == {'epoch', 'optimizer', 'model'} and cpt['epoch'] == 1
+    # torch's own Adam over the same parameter list loads it
+    ref_params = [torch.nn.Parameter(v.clone()) for n, v in cpt['model'].items()
+                  if n in dict(a.model.named_parameters()) and dict(a.model.named_parameters())[n].requires_grad]
+    opt = torch.optim.Adam(ref_params, lr=5e-4, weight_decay=1e-5)
+    opt.load_state_dict(cpt['optimizer'])
+    assert float(opt.state[ref_params[0]]['step']) == 1.0
+    # resume in a fresh stepper and compare the next iteration
+    torch.manual_seed(99)
+    b = SpeTrainStep(P.DPRNNSpeTasNet(**kw, fusion_type='film').cuda())
+    assert b.load_checkpoint(path) == 1
+    nxt = batch()
+    la, lb = a.step(*nxt).clone(), b.step(*nxt).clone()
+    assert torch.equal(la, lb)
+    for (n, pa), (_, pb) in zip(a.model.named_parameters(), b.model.named_parameters()):
+        assert torch.equal(pa, pb), n
+    for k, v in a.model.state_dict().items():
+        assert torch.equal(v, b.model.state_dict()[k]), k

@@ -6,5 +6,6 @@ hand-written CUDA kernels of ``csrc/`` through the C ABI declared in ``include/d
 """
 from .models import DPRNNTasNet, DPRNNSpeTasNet, DPRNNSpeIRATasNet, DPRNNRawNetTasNet  # noqa: F401
 from ._lib import lib  # noqa: F401
+from .resample import Resample  # noqa: F401
 
-__all__ = ['DPRNNTasNet', 'DPRNNSpeTasNet', 'DPRNNSpeIRATasNet', 'DPRNNRawNetTasNet', 'lib']
+__all__ = ['DPRNNTasNet', 'DPRNNSpeTasNet', 'DPRNNSpeIRATasNet', 'DPRNNRawNetTasNet', 'Resample', 'lib']

@@ -116,6 +116,31 @@ __global__ void __launch_bounds__(256) time_mean_sub_kernel(float* __restrict__ 
     if (c < C) for (long t = r; t < Tp; t += 8) xb[t * C + c] -= m;
 }
 
+// Polyphase FIR resampling of the reference utterance (torchaudio.transforms.Resample as the RawNet inferencer / trainer
+// apply it, src/inferencers/inferencer_rawnet.py:21-23,36): out[b, q*nw + i] = sum_k kern[i, k] * x[b, q*orig + k - width]
+// (zero outside the signal), taps = 2*width + orig.
+__global__ void __launch_bounds__(256) resample_fir_kernel(const float* __restrict__ x, const float* __restrict__ kern,
+                                                           float* __restrict__ out, long T, long To, int orig, int nw,
+                                                           int taps, int width, long total) {
+    extern __shared__ float ks[];
+    for (int i = threadIdx.x; i < nw * taps; i += blockDim.x) ks[i] = kern[i];
+    __syncthreads();
+    for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+        const long b = e / To, n = e - b * To;
+        const long q = n / nw;
+        const int i = (int)(n - q * nw);
+        const float* xb = x + b * T;
+        const long base = q * orig - width;
+        const float* kk = ks + i * taps;
+        float acc = 0.f;
+        for (int k = 0; k < taps; ++k) {
+            const long j = base + k;
+            if (j >= 0 && j < T) acc = fmaf(kk[k], __ldg(xb + j), acc);
+        }
+        out[e] = acc;
+    }
+}
+
 }  // namespace dprnn
 
 using namespace dprnn;
@@ -331,6 +356,19 @@ extern "C" int dprnn_affine_vec(const float* x, const float* scale, const float*
 extern "C" int dprnn_att_stats_pool(const float* x, const float* logits, float* out, int B, long T, int C, void* stream) {
     DPRNN_CHECK_ARG(x && logits && out && B > 0 && T > 0 && C > 0);
     att_stats_pool_kernel<<<cdiv((long)B * C, 128), 128, 0, (cudaStream_t)stream>>>(x, logits, out, B, T, C);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_resample_fir(const float* x, const float* kernel, float* out, int B, long T, long To, int orig, int nw,
+                                  int taps, int width, void* stream) {
+    DPRNN_CHECK_ARG(x && kernel && out && B > 0 && T > 0 && To > 0 && orig > 0 && nw > 0 && taps > 0 && width >= 0);
+    DPRNN_CHECK_ARG((size_t)nw * taps * sizeof(float) <= 48 * 1024);
+    const long total = (long)B * To;
+    const long want = (total + 255) / 256;
+    const unsigned grid = (unsigned)(want < 148L * 16 ? want : 148L * 16);
+    resample_fir_kernel<<<grid, 256, (size_t)nw * taps * sizeof(float), (cudaStream_t)stream>>>(
+        x, kernel, out, T, To, orig, nw, taps, width, total);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

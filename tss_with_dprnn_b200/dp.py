@@ -34,8 +34,10 @@ class FlatParams:
         self.flat = torch.zeros(self.size, dtype=torch.float32, device=dev)
         self.grad = torch.zeros(self.size, dtype=torch.float32, device=dev)
         off = 0
+        self.offsets = []
         for _, p in self.named:
             n = p.numel()
+            self.offsets.append(off)
             self.flat[off:off + n].copy_(p.detach().reshape(-1))
             p.data = self.flat[off:off + n].view_as(p)              # parameters now alias the flat buffer
             p.grad = self.grad[off:off + n].view_as(p)
@@ -75,3 +77,36 @@ class ClipAdam:
                    float(self.max_norm), self.step_count, self.ws, self.total_norm,
                    torch.cuda.current_stream().cuda_stream)
         return self.total_norm
+
+    # ---- torch.optim.Adam.state_dict() layout, so that the reference's Trainer ({'epoch','optimizer','model'} checkpoints,
+    # src/trainers/trainer.py:294-306) and this stepper can resume from each other's files
+    def state_dict(self):
+        state = {}
+        if self.step_count > 0:
+            for i, ((_, p), off) in enumerate(zip(self.fp.named, self.fp.offsets)):
+                n = p.numel()
+                state[i] = {'step': torch.tensor(float(self.step_count)),
+                            'exp_avg': self.exp_avg[off:off + n].view_as(p).clone(),
+                            'exp_avg_sq': self.exp_avg_sq[off:off + n].view_as(p).clone()}
+        group = {'lr': self.lr, 'betas': tuple(self.betas), 'eps': self.eps, 'weight_decay': self.wd, 'amsgrad': False,
+                 'maximize': False, 'foreach': None, 'capturable': False, 'differentiable': False, 'fused': None,
+                 'decoupled_weight_decay': False, 'params': list(range(len(self.fp.named)))}
+        return {'state': state, 'param_groups': [group]}
+
+    def load_state_dict(self, sd):
+        group = sd['param_groups'][0]
+        if len(group['params']) != len(self.fp.named):
+            raise ValueError(f"optimizer state has {len(group['params'])} parameters, the model has {len(self.fp.named)}")
+        if group.get('amsgrad') or group.get('maximize'):
+            raise NotImplementedError('amsgrad / maximize are not built (the reference trains with plain Adam)')
+        self.lr, self.betas, self.eps, self.wd = group['lr'], tuple(group['betas']), group['eps'], group['weight_decay']
+        self.exp_avg.zero_(); self.exp_avg_sq.zero_()
+        self.step_count = 0
+        for i, ((_, p), off) in enumerate(zip(self.fp.named, self.fp.offsets)):
+            st = sd['state'].get(group['params'][i])
+            if st is None:
+                continue
+            n = p.numel()
+            self.exp_avg[off:off + n].copy_(st['exp_avg'].reshape(-1))
+            self.exp_avg_sq[off:off + n].copy_(st['exp_avg_sq'].reshape(-1))
+            self.step_count = max(self.step_count, int(float(st['step'])))

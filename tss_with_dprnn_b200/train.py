@@ -562,3 +562,25 @@ class SpeTrainStep:
         allreduce_mean(self.fp.grad, self.group)
         self.opt.step()
         return loss3
+
+    # ---- checkpoints in the reference's format (src/trainers/trainer.py:294-306: {'epoch', 'optimizer', 'model'})
+    def checkpoint(self, epoch: int):
+        return {'epoch': int(epoch), 'optimizer': self.opt.state_dict(),
+                'model': {k: v.detach().clone() for k, v in self.model.state_dict().items()}}
+
+    def save_checkpoint(self, path, epoch: int):
+        torch.save(self.checkpoint(epoch), path)
+
+    def load_checkpoint(self, cpt):
+        """cpt: the dict (or a path to it) written by this class or by the reference's Trainer._save_checkpoint."""
+        if not isinstance(cpt, dict):
+            cpt = torch.load(cpt, map_location='cpu')
+        with torch.no_grad():                                   # in place: the parameters stay views of the flat buffer
+            own = self.model.state_dict()
+            missing = set(own) - set(cpt['model'])
+            if missing:
+                raise KeyError(f'checkpoint lacks {sorted(missing)[:3]}...')
+            for k, v in own.items():
+                v.copy_(cpt['model'][k])
+        self.opt.load_state_dict(cpt['optimizer'])
+        return cpt['epoch']
