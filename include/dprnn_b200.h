@@ -362,6 +362,12 @@ int dprnn_clip_adam_step(float* params, const float* grads, float* exp_avg, floa
 int dprnn_lstm_recurrence_f32_train(const float* gx, const float* whhT, float* hout, float* gates, float* cstate,
                                     long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride,
                                     long step_stride, int hidden, int ndir, void* stream);
+/* Training forward on the tensor cores: dprnn_lstm_layer_bf16 (bf16 operands [x_t | h_{t-1}] [W_ih | W_hh]^T, fp32
+ * accumulation, fp32 cell state) whose epilogue also stores gates [rows, ndir*4H], cstate [rows, ndir*H] and h in fp32
+ * (hout_f32 [rows, ndir*H]); hout_bf16 as in dprnn_lstm_layer_bf16. */
+int dprnn_lstm_layer_bf16_train(const void* x, const void* w_packed, const float* bias_perm, void* hout_bf16, float* gates,
+                                float* cstate, float* hout_f32, int B, int S, int K, int inter, int hidden, int ndir,
+                                int fast_act, void* stream);
 /* BPTT: dh_out [rows, ndir*H] = gradient of the layer output; whh [ndir][4H][H] (PyTorch layout);
  * dgates [rows, ndir*4H] = gradient of the gate pre-activations of every step (same sequence geometry as forward). */
 int dprnn_lstm_bptt_f32(const float* dh_out, const float* gates, const float* cstate, const float* whh, float* dgates,

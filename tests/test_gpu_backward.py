@@ -119,3 +119,36 @@ def test_lstm_train_forward_and_bptt(inter, ndir):
     assert rel(dwih, want_wih) < 1e-4
     want_b = torch.cat([getattr(rnn, 'bias_ih_l0' + s).grad for s in sfx], 0)
     assert rel(dgc.sum(0), want_b) < 1e-4
+
+
+@pytest.mark.parametrize('inter', [0, 1])
+def test_lstm_tensor_core_train_forward_saves_what_bptt_needs(inter):
+    """dprnn_lstm_layer_bf16_train against the exact fp32 training recurrence: gate activations, cell state and h of
+    every step land at the same [rows, .] positions (bf16-operand tolerance), padded tile rows are never written."""
+    from tss_with_dprnn_b200.engine import Engine
+    L = P.lib()
+    B, S, K, H, F, nd = 2, 5, 250, 128, 128, 2
+    torch.manual_seed(3)
+    rnn = torch.nn.LSTM(F, H, 1, batch_first=True, bidirectional=True).to(DEV)
+    rows = B * S * K
+    xs = (0.5 * rnd(rows, F, seed=4)).to(DEV)
+    sfx = ['', '_reverse']
+    wih = torch.cat([getattr(rnn, 'weight_ih_l0' + s).detach() for s in sfx], 0)
+    b = torch.cat([(getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s)).detach() for s in sfx], 0)
+    whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach() for s in sfx], 0).contiguous()
+    gx = xs @ wih.t() + b
+    geo = (B * S, K, 1, K, 0, 1) if inter == 0 else (B * K, S, K, S * K, 1, K)
+    h0, g0, c0 = (torch.empty(rows, n, device=DEV) for n in (nd * H, nd * 4 * H, nd * H))
+    L.call('dprnn_lstm_recurrence_f32_train', gx.contiguous(), whh.transpose(1, 2).contiguous(), h0, g0, c0, *geo, H, nd, st())
+    xb = xs.to(torch.bfloat16)
+    wp, bp = Engine._pack_lstm_tc(rnn, sfx)
+    hb = torch.empty(rows, nd * H, device=DEV, dtype=torch.bfloat16)
+    h1, g1, c1 = (torch.full((rows + 1, n), 7.0, device=DEV) for n in (nd * H, nd * 4 * H, nd * H))
+    for fast in (0, 1):
+        L.call('dprnn_lstm_layer_bf16_train', xb, wp, bp, hb, g1, c1, h1, B, S, K, inter, H, nd, fast, st())
+        assert float((g1[:rows] - g0).abs().max()) < 3e-2
+        assert float((c1[:rows] - c0).abs().max()) < 5e-2
+        assert float((h1[:rows] - h0).abs().max()) < 3e-2
+        assert float((hb.float() - h1[:rows]).abs().max()) < 1e-2          # the bf16 copy of the same h
+        for t_ in (g1, c1, h1):
+            assert float((t_[rows:] - 7.0).abs().max()) == 0.0             # nothing written past the real rows

@@ -59,9 +59,10 @@ def test_backward_matches_oracle_autograd(fusion, extra):
 
 
 def test_backward_tensor_core_mode():
-    """precision = 'bf16' puts the LSTM gate / Linear contractions of the training step and their weight gradients on the
-    tensor cores (TF32 operands, fp32 accumulation): gradients stay within 5 % of the fp64 autograd result (peak-
-    normalised per parameter; typically < 1 %) and point the same way (cosine > 0.9999 over all parameters)."""
+    """precision = 'bf16' runs the training step's LSTMs on the tensor-core kernel of the inference path (bf16 operands,
+    fp32 accumulation / cell state) and the Linear / weight-gradient contractions as TF32 tensor-core GEMMs.  Against
+    the fp64 autograd result the gradients keep their direction (cosine > 0.999 over all parameters) and every
+    parameter's gradient stays within 10 % peak-normalised (mixed-precision tolerance, stated here)."""
     kw = dict(KW)
     torch.manual_seed(11)
     model = P.DPRNNSpeTasNet(**kw, fusion_type='film').train()
@@ -73,18 +74,24 @@ def test_backward_tensor_core_mode():
     model = model.cuda()
     model.precision = 'bf16'
     est, logits = model(mix.cuda(), ref.cuda(), torch.tensor(float(Tr)))
-    assert O.peak_rel_err(est.detach().cpu(), est_o.float()) < 3e-3
+    assert O.peak_rel_err(est.detach().cpu(), est_o.float()) < 1e-2
     ((est * w_est.cuda()).sum() + (logits * w_log.cuda()).sum()).backward()
     dot = na = nb = 0.0
+    worst = ('', 0.0)
     for n, p in model.named_parameters():
         if not p.requires_grad:
             continue
         want = grads_o[n]
         got = p.grad.cpu().double()
         err = float((got - want).abs().max()) / max(float(want.abs().max()), 1e-12)
-        assert err < 5e-2, (n, err)
+        if err > worst[1]:
+            worst = (n, err)
         dot += float((got * want).sum()); na += float((got * got).sum()); nb += float((want * want).sum())
-    assert dot / (na * nb) ** 0.5 > 0.9999
+    cos = dot / (na * nb) ** 0.5
+    print('tensor-core mode: worst gradient error', worst, 'cosine', cos,
+          'est err', O.peak_rel_err(est.detach().cpu(), est_o.float()))
+    assert worst[1] < 0.10, worst
+    assert cos > 0.999
 
 
 def oracle_loss(est, target, logits, spk, gamma=0.5):

@@ -33,6 +33,12 @@ struct LstmTcParams {
     int tiles_per_outer;   // 256-sequence tiles per outer index
     int ndir;
     const int2* jobs;      // ragged inter-chunk layer: per utterance {first chunk, number of chunks}; else NULL
+    // training forward (cfg 5): what BPTT needs, stored by the epilogue as the values are produced
+    float* gates;          // [rows, ndir*4H] gate ACTIVATIONS i,f,g,o
+    float* cst;            // [rows, ndir*H]  cell state after the step
+    float* hf;             // [rows, ndir*H]  h in fp32 (operand of the weight-gradient contractions)
+    int K, S;              // chunk length / chunks per utterance (linear row of (sequence, t))
+    long seq_limit;        // number of real sequences along the sequence coordinate (tiles are padded to 256)
 };
 
 __device__ __forceinline__ float tanh_fast(float x) {
@@ -81,25 +87,33 @@ __device__ __forceinline__ void mbar_expect_tx_addr(uint32_t addr, uint32_t byte
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
 }
 
+// 256-bit store (STG.256): 8 consecutive floats = one full 32-byte sector per thread
+__device__ __forceinline__ void st_global_v8(float* p, const float (&a)[4], const float (&b)[4]) {
+    asm volatile("st.global.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(b[0]), "f"(b[1]), "f"(b[2]), "f"(b[3]) : "memory");
+}
+
 // Cell update for 8 hidden units of one sequence row: gates from TMEM (+bias) -> c (registers), h (packed bf16, one
 // 16-byte chunk).  8 units at a time keeps the live register set small enough for 128 registers per thread, which
 // leaves room on the SM for a memory-bound CTA of another stream next to this kernel.
 // The i, f, o rows of the weights and biases are pre-scaled by 1/2 on the host (exact), so sigmoid(x) = 1/2 tanh(x') + 1/2.
-template <bool kFastAct>
+template <bool kFastAct, bool kTrain>
 __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restrict__ bq, float* __restrict__ c,
-                                           uint32_t (&packed)[4]) {
+                                           uint32_t (&packed)[4], float* __restrict__ gdst = nullptr,
+                                           float* __restrict__ cdst = nullptr, float* __restrict__ hdst = nullptr) {
     uint32_t ri[8], rf[8], rg[8], ro[8];
     tmem_ld8_issue(tcol + 0 * 64, ri);
     tmem_ld8_issue(tcol + 1 * 64, rf);
     tmem_ld8_issue(tcol + 2 * 64, rg);
     tmem_ld8_issue(tcol + 3 * 64, ro);
     tmem_ld_wait();
+    float keep[kTrain ? 6 : 1][4];
 #pragma unroll
     for (int j = 0; j < 8; j += 4) {
         const float4 bi = *reinterpret_cast<const float4*>(bq + 0 * 64 + j), bf = *reinterpret_cast<const float4*>(bq + 1 * 64 + j);
         const float4 bg = *reinterpret_cast<const float4*>(bq + 2 * 64 + j), bo = *reinterpret_cast<const float4*>(bq + 3 * 64 + j);
         const float b4[4][4] = {{bi.x, bi.y, bi.z, bi.w}, {bf.x, bf.y, bf.z, bf.w}, {bg.x, bg.y, bg.z, bg.w}, {bo.x, bo.y, bo.z, bo.w}};
-        float hv[4];
+        float hv[4], sv[5][4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
             const float pi = __uint_as_float(ri[j + u]) + b4[0][u];
@@ -116,6 +130,24 @@ __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restric
             const float cn = fmaf(fg, c[j + u], ig * gg);
             c[j + u] = cn;
             hv[u] = og * (kFastAct ? tanh_fast(cn) : tanhf(cn));
+            if constexpr (kTrain) { sv[0][u] = ig; sv[1][u] = fg; sv[2][u] = gg; sv[3][u] = og; sv[4][u] = cn; }
+        }
+        if constexpr (kTrain) {
+            if (gdst) {            // one 32-byte (full sector) store per array and pair of j iterations
+                if (j == 0) {
+#pragma unroll
+                    for (int g = 0; g < 5; ++g)
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) keep[g][u] = sv[g][u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) keep[5][u] = hv[u];
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 4; ++g) st_global_v8(gdst + g * 128, keep[g], sv[g]);
+                    st_global_v8(cdst, keep[4], sv[4]);
+                    st_global_v8(hdst, keep[5], hv);
+                }
+            }
         }
         __nv_bfloat162 h01 = __floats2bfloat162_rn(hv[0], hv[1]), h23 = __floats2bfloat162_rn(hv[2], hv[3]);
         packed[(j >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h01);
@@ -123,7 +155,7 @@ __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restric
     }
 }
 
-template <bool kFastAct>
+template <bool kFastAct, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmH, const float* __restrict__ bias_perm, const LstmTcParams p) {
@@ -260,16 +292,29 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
         for (int i = 0; i < 32; ++i) { c0[i] = 0.f; c1s[i] = 0.f; }
         const bool storer = (warp == 4 && lane == 0);
+        const long seq = (long)seq0 + row;
+        const bool live = kTrain && seq < p.seq_limit;
 
         for (int step = 0; step < T; ++step) {
             const int t = dir ? T - 1 - step : step;
             const uint32_t par = step & 1;
+            float *gd = nullptr, *cd = nullptr, *hd = nullptr;
+            if constexpr (kTrain) {
+                if (live) {
+                    const long lr = p.seq_dim == 2 ? seq * p.K + t : ((long)outer * p.S + t) * p.K + seq;
+                    gd = p.gates + (lr * p.ndir + dir) * 512 + sub * 32;
+                    cd = p.cst + (lr * p.ndir + dir) * 128 + sub * 32;
+                    hd = p.hf + (lr * p.ndir + dir) * 128 + sub * 32;
+                }
+            }
             // ---------------- unit half 0
             mbar_wait(&d_full[0], par);
             tc_fence_after();
             uint32_t pk[4][4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g) lstm_cell8<kFastAct>(tbase + 8 * g, sbias + sub * 32 + 8 * g, c0 + 8 * g, pk[g]);
+            for (int g = 0; g < 4; ++g)
+                lstm_cell8<kFastAct, kTrain>(tbase + 8 * g, sbias + sub * 32 + 8 * g, c0 + 8 * g, pk[g],
+                                             gd ? gd + 8 * g : nullptr, cd + 8 * g, hd + 8 * g);
             tc_fence_before();                         // our tcgen05.ld of D0 are complete
             mbar_wait(h_free, par);                    // the MMAs that read h_{t-1} have completed
             if (storer) bulk_wait_read0();             // ... and so has last step's TMA store of the h tile
@@ -288,7 +333,8 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             tc_fence_after();
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-                lstm_cell8<kFastAct>(tbase + 256 + 8 * g, sbias + 256 + sub * 32 + 8 * g, c1s + 8 * g, pk[g]);
+                lstm_cell8<kFastAct, kTrain>(tbase + 256 + 8 * g, sbias + 256 + sub * 32 + 8 * g, c1s + 8 * g, pk[g],
+                                             gd ? gd + 64 + 8 * g : nullptr, cd + 64 + 8 * g, hd + 64 + 8 * g);
             tc_fence_before();
             {
                 uint8_t* sH = smem + SM_H + TILE;      // K-block 1 = units 64..127
@@ -323,7 +369,8 @@ using namespace dprnn;
 // hout [rows, ndir*128] bf16.  Geometry: `inter`==0: rows = (b,s,k), sequences (b,s) run along k;
 // `inter`==1: sequences (b,k) run along s.
 static int lstm_layer_impl(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
-                           int inter, int hidden, int ndir, int fast_act, const int2* jobs, int n_jobs, void* stream) {
+                           int inter, int hidden, int ndir, int fast_act, const int2* jobs, int n_jobs, void* stream,
+                           float* gates = nullptr, float* cstate = nullptr, float* hout_f32 = nullptr) {
     DPRNN_CHECK_ARG(x && w_packed && bias_perm && hout && B > 0 && S > 0 && K > 0);
     DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2));
     DPRNN_CHECK_ARG(((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)hout) % 16 == 0);
@@ -332,6 +379,9 @@ static int lstm_layer_impl(const void* x, const void* w_packed, const float* bia
     LstmTcParams p;
     p.ndir = ndir;
     p.jobs = jobs;
+    p.gates = gates; p.cst = cstate; p.hf = hout_f32;
+    p.K = K; p.S = S;
+    p.seq_limit = inter ? K : (long)B * S;
     uint64_t dX[4], sX[4], dH[4], sH[4];
     uint32_t box[4] = {64, 1, 1, 1};
     long njobs;
@@ -362,7 +412,8 @@ static int lstm_layer_impl(const void* x, const void* w_packed, const float* bia
     const uint32_t bW[2] = {64, 128};
     if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dW, sW, bW)) return 1;
     const size_t smem = SM_TOTAL;   // no alignment slack: the kernel checks the 1024-byte alignment of the base
-    auto kern = fast_act ? lstm_tc_kernel<true> : lstm_tc_kernel<false>;
+    auto kern = gates ? (fast_act ? lstm_tc_kernel<true, true> : lstm_tc_kernel<false, true>)
+                      : (fast_act ? lstm_tc_kernel<true, false> : lstm_tc_kernel<false, false>);
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
     kern<<<(unsigned)(njobs * 2), 384, smem, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);
@@ -373,6 +424,17 @@ static int lstm_layer_impl(const void* x, const void* w_packed, const float* bia
 extern "C" int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B,
                                      int S, int K, int inter, int hidden, int ndir, int fast_act, void* stream) {
     return lstm_layer_impl(x, w_packed, bias_perm, hout, B, S, K, inter, hidden, ndir, fast_act, nullptr, 0, stream);
+}
+
+// Training forward (cfg 5): the same kernel, whose epilogue also stores the gate activations, the cell state and h in
+// fp32 for every step - what dprnn_lstm_bptt_f32 and the weight-gradient contractions read.
+extern "C" int dprnn_lstm_layer_bf16_train(const void* x, const void* w_packed, const float* bias_perm, void* hout_bf16,
+                                           float* gates, float* cstate, float* hout_f32, int B, int S, int K, int inter,
+                                           int hidden, int ndir, int fast_act, void* stream) {
+    DPRNN_CHECK_ARG(gates && cstate && hout_f32);
+    DPRNN_CHECK_ARG(((uintptr_t)gates | (uintptr_t)cstate | (uintptr_t)hout_f32) % 16 == 0);
+    return lstm_layer_impl(x, w_packed, bias_perm, hout_bf16, B, S, K, inter, hidden, ndir, fast_act, nullptr, 0, stream,
+                           gates, cstate, hout_f32);
 }
 
 // Inter-chunk layer of a ragged batch: x / hout are the packed chunk space [total_chunks, K, .]; utt_jobs[j] =

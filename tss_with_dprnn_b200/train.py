@@ -226,11 +226,23 @@ def forward_train(model, mix, ref, div):
             wih = torch.cat([getattr(rnn, 'weight_ih_l0' + s).detach() for s in sfx], 0)              # [nd*4H, F]
             b = torch.cat([(getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s)).detach() for s in sfx], 0)
             whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach() for s in sfx], 0).contiguous()   # [nd,4H,H]
-            gx = ops.mm(xs, wih, rows, nd * 4 * H, F, bias=b)
             geo = (B * S, K, 1, K, 0, 1) if which == 0 else (B * K, S, K, S * K, 1, K)
             hout, gates, cst = ops.empty(rows, nd * H), ops.empty(rows, nd * 4 * H), ops.empty(rows, nd * H)
-            L_.call('dprnn_lstm_recurrence_f32_train', gx, whh.transpose(1, 2).contiguous(), hout, gates, cst, *geo, H, nd, st)
-            del gx
+            if ops.tf32:
+                # tensor-core recurrence (bf16 operands, fp32 accumulation and cell state), input projection fused:
+                # the kernel of the inference path, whose epilogue also stores what BPTT needs
+                from .engine import Engine
+                xb = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+                L_.call('dprnn_cast_bf16', xs, xb, rows * F, st)
+                wp, bp = Engine._pack_lstm_tc(rnn, sfx)
+                hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
+                L_.call('dprnn_lstm_layer_bf16_train', xb, wp, bp, hb, gates, cst, hout, B, S, K, which, H, nd,
+                        int(model._engine.fast_act), st)
+                del xb, hb
+            else:
+                gx = ops.mm(xs, wih, rows, nd * 4 * H, F, bias=b)
+                L_.call('dprnn_lstm_recurrence_f32_train', gx, whh.transpose(1, 2).contiguous(), hout, gates, cst, *geo, H, nd, st)
+                del gx
             yl = ops.mm(hout, linm.weight.detach(), rows, F, nd * H, bias=linm.bias.detach())
             g_, b_, eps_ = _norm_params(nm)
             mr = ops.utt_stats(yl, B, S * K * F, eps_)
