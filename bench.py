@@ -585,6 +585,23 @@ def run_ours(args):
                              'algorithmic flops = h W_hh^T only (2*128*512 per position and direction); the fp32 mode '
                              'runs this on CUDA cores, so its fraction of the bf16 tensor peak is small by construction')}
 
+    if args.workload == 'cfg5' and 'dprnn_lstm_bptt_f32' in per_kernel:
+        # dominant kernel of the training step: the fp32 BPTT recurrence.  It streams the saved gate activations, two
+        # cell states and d h_out and writes d gates: 4H + 2H + H + 4H floats per chunk position and direction.
+        k = per_kernel['dprnn_lstm_bptt_f32']
+        peak_bw = peaks.get('hbm_gbs', 6400.0)
+        bytes_per_launch = wl.positions(0) * 2 * (4 * 128 + 2 * 128 + 128 + 4 * 128) * 4
+        achieved = bytes_per_launch / (k['ms_avg'] * 1e-3) / 1e9
+        roofline = {'kernel': 'dprnn_lstm_bptt_f32', 'bound': 'hbm', 'achieved': achieved, 'peak': peak_bw, 'unit': 'GB/s',
+                    'frac': achieved / peak_bw, 'traffic': None,
+                    'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6400 (B200_PROFILING.md)',
+                    'launch_ms_avg': k['ms_avg'],
+                    'share_of_step_single_stream': k['ms_total'] / sum(v['ms_total'] for v in per_kernel.values()),
+                    'note': 'algorithmic bytes = 11 H floats per chunk position and direction (gates, c_t, c_{t-1}, dh in; '
+                            'dgates out); the recurrence d h_{t-1} = d gates_t W_hh runs on CUDA cores (fp32, exact) and is '
+                            'latency-bound at 16 utterances per GPU (97..125 CTAs of 32 sequences), not bandwidth-bound: '
+                            'DESIGN.md section 4.6'}
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
         kind, cores, times, audio, desc = time_cpu(args, 2, 1)
@@ -592,6 +609,16 @@ def run_ours(args):
                'sample': desc + (', 1 warm-up + 2 timed training iterations, fp32, train()' if args.workload == 'cfg5'
                                   else ', 1 warm-up + 2 timed forwards, fp32, eval()')}
 
+    replica_spread = None
+    if args.workload == 'cfg5':
+        # data-parallel replicas must hold identical parameters after the all-reduced updates
+        chk = wl.stepper.fp.flat.double().sum().reshape(1)
+        if world > 1:
+            allc = [torch.zeros_like(chk) for _ in range(world)]
+            dist.all_gather(allc, chk)
+            replica_spread = float(max(float(c) for c in allc) - min(float(c) for c in allc))
+        else:
+            replica_spread = 0.0
     if rank == 0:
         line = {
             'metric': METRIC, 'value': value, 'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps,
@@ -602,6 +629,10 @@ def run_ours(args):
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'kernels': per_kernel,
             'build': L.build_info(),
         }
+        if args.workload == 'cfg5':
+            line['train'] = {'samples_per_s': args.batch * world * args.steps / (ms_total / 1e3),
+                             'replica_param_checksum_spread': replica_spread,
+                             'grad_allreduce_bytes': int(wl.stepper.fp.size * 4)}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
