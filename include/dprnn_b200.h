@@ -339,10 +339,16 @@ int dprnn_si_sdr(const float* est, const float* target, const long* off, const l
                  float* out_db, void* stream);
 /* The TrainerSpe loss (src/trainers/trainer_spe.py:39-43): loss = mean_b -SI-SDR(est_b, target_b) + ce_gamma *
  * mean_b CrossEntropy(logits_b, spk_b) (one source, so asteroid's PIT wrapper is the identity).  est / target [B,T],
- * logits [B,C], spk [B] int64.  terms [B,2] receives the per-utterance (neg SI-SDR, ce_gamma * CE); loss3 = {total,
+ * logits [B,C], spk [B] int64 (logits == NULL: SI-SDR term only, as the BSS trainer).  terms [B,2] receives the per-utterance (neg SI-SDR, ce_gamma * CE); loss3 = {total,
  * SI-SDR part, CE part}; d_est [B,T] / d_logits [B,C] receive d loss / d est and d loss / d logits. */
 int dprnn_train_loss(const float* est, const float* target, long T, const float* logits, int C, const long* spk,
                      float ce_gamma, int B, float* terms, float* loss3, float* d_est, float* d_logits, void* stream);
+/* Two-source permutation-invariant assignment (asteroid PITLossWrapper(pairwise_neg_sisdr, pit_from='pw_mtx'),
+ * src/trainers/trainer.py:39): est, target [B,2,T] -> perm [B] (0 = identity, 1 = swapped; ties -> identity),
+ * target_perm [B,2,T] = the targets in matched order, pairwise [B,2,2] (may be NULL) = the neg-SI-SDR matrix.
+ * The PIT loss is then dprnn_train_loss over the 2B matched rows with logits == NULL (no cross-entropy term). */
+int dprnn_pit2_assign(const float* est, const float* target, int B, long T, float* target_perm, int* perm,
+                      float* pairwise, void* stream);
 /* torch.nn.utils.clip_grad_norm_(params, max_norm) followed by torch.optim.Adam(lr, (beta1, beta2), eps, weight_decay)
  * .step() over one flat fp32 parameter / gradient buffer (src/trainers/trainer.py:42-43,115-116; step >= 1 is Adam's
  * step count; max_norm <= 0 disables clipping).  total_norm_out[0] receives the global gradient norm. */
@@ -417,7 +423,18 @@ size_t dprnn_convw2_workspace_bytes(int N);
 int dprnn_convw2_grad(const float* z, const float* sig, int B, long L, int N, float* dw, int accumulate, void* workspace,
                       void* stream);
 /* out[b,c] = sum_l X[b,l,c] (* Y[b,l,c]); out[b,l,c] (+)= v[b,c] * (X ? X[b,l,c] : 1). */
-int dprnn_utt_col_sum(const float* X, const float* Y, int B, long L, int C, float* out, void* stream);
+size_t dprnn_utt_col_sum_workspace_bytes(int B, int C);
+int dprnn_utt_col_sum(const float* X, const float* Y, int B, long L, int C, float* out, void* workspace, void* stream);
+/* Attention-fusion backward (src/models/dprnn_spe.py:177-183,217-225; fused = n * v[b,c] * r[b,l], r = 1 + softmax(s)[src(l)],
+ * s[b,j] = sum_c v * avg(n)):  dprnn_row_dot3: out[row] = sum_c A*Bm*v[utt] (= d r);  dprnn_att_softmax_bwd: upsample
+ * adjoint + softmax adjoint per utterance, w2 [B,L] = d s spread back over the frames of the average conv (ds [B,La]
+ * scratch/out);  dprnn_att_bwd_apply: g = dfused*r + w2*wavg[c, l%ksz], dn = v*g (gradient of the normalised encoding),
+ * tdv = n*g (its sum over time is the gradient of v = fusion_linear(e)). */
+int dprnn_row_dot3(const float* A, const float* Bm, const float* v, long rows, long rows_per_utt, int C, float* out,
+                   void* stream);
+int dprnn_att_softmax_bwd(const float* dr, const float* a, int B, long L, int ksz, float* w2, float* ds, void* stream);
+int dprnn_att_bwd_apply(const float* dfused, const float* n, const float* v, const float* r, const float* w2,
+                        const float* wavg, int B, long L, int C, int ksz, float* dn, float* tdv, void* stream);
 int dprnn_bcast_mul(const float* v, const float* X, float* out, int B, long L, int C, int accumulate, void* stream);
 /* BatchNorm1d (train) adjoint: dy = gamma*rstd*(dout - m1 - yhat*m2), m1 = mean(dout), m2 = mean(dout*yhat) per channel. */
 int dprnn_bn_bwd_apply(const float* dout, const float* y, const float* mean, const float* rstd, const float* gamma,

@@ -28,13 +28,16 @@ def oracle_grads(model, kw, fusion, mix, ref, Tr, w_est, w_log):
     return est.detach(), logits.detach(), {n: v.grad for n, v in leaves.items()}
 
 
-@pytest.mark.parametrize('fusion,extra', [('film', {}), ('cat', {}), ('add', {}), ('mul', dict(norm_type='gLN', bidirectional=False))])
+@pytest.mark.parametrize('fusion,extra', [('film', {}), ('cat', {}), ('add', {}), ('mul', dict(norm_type='gLN', bidirectional=False)),
+                                          ('att', {}), ('att', dict(norm_type='gLN', T=1502))])
 def test_backward_matches_oracle_autograd(fusion, extra):
+    extra = dict(extra)
+    T = extra.pop('T', 1501)               # 1502 -> odd frame count: the generic nearest-upsample index rule of 'att'
     kw = dict(KW, **extra)
     torch.manual_seed(11)
     model = P.DPRNNSpeTasNet(**kw, fusion_type=fusion).train()
     g = torch.Generator().manual_seed(12)
-    B, T, Tr = 2, 1501, 1300
+    B, Tr = 2, 1300
     mix, ref = 0.05 * torch.randn(B, T, generator=g), 0.05 * torch.randn(B, Tr, generator=g)
     w_est, w_log = torch.randn(B, T, generator=g), torch.randn(B, 251, generator=g)
     est_o, log_o, grads_o = oracle_grads(model, kw, fusion, mix, ref, Tr, w_est, w_log)
@@ -205,3 +208,85 @@ def test_checkpoint_roundtrip_in_reference_format(tmp_path):
         assert torch.equal(pa, pb), n
     for k, v in a.model.state_dict().items():
         assert torch.equal(v, b.model.state_dict()[k]), k
+
+
+# ---------------------------------------------------------------------------------------------------- BSS (DPRNNTasNet)
+KW_BSS = {k: v for k, v in KW.items()}
+
+
+def oracle_pit_loss(est, tgt):
+    """PITLossWrapper(pairwise_neg_sisdr, pit_from='pw_mtx') for two sources (trainer.py:39), restated: mean over the
+    batch of the smaller of the two permutations' mean neg-SI-SDR."""
+    pw = torch.stack([torch.stack([-O.si_sdr_db(est[:, i], tgt[:, j]) for j in range(2)], -1) for i in range(2)], 1)
+    ident, swap = (pw[:, 0, 0] + pw[:, 1, 1]) / 2, (pw[:, 0, 1] + pw[:, 1, 0]) / 2
+    return torch.minimum(ident, swap).mean(), pw, (swap < ident)
+
+
+def test_tasnet_backward_matches_oracle_autograd():
+    kw = dict(KW_BSS)
+    torch.manual_seed(41)
+    model = P.DPRNNTasNet(**kw).train()
+    g = torch.Generator().manual_seed(42)
+    B, T = 2, 1501
+    mix, w_est = 0.05 * torch.randn(B, T, generator=g), torch.randn(B, 2, T, generator=g)
+    sd = {k: v.detach().clone().double() for k, v in model.state_dict().items()}
+    leaves = {n: sd[n].requires_grad_(True) for n, p in model.named_parameters() if p.requires_grad}
+    cfg = O.Config(**{k: kw[k] for k in ('input_size', 'feature_size', 'hidden_size', 'chunk_length', 'kernel_size',
+                                         'hop_length', 'n_repeats', 'bidirectional', 'norm_type', 'activation_type')})
+    est_o = O.tasnet_forward(mix.double(), sd, cfg, fast=False)
+    (est_o * w_est.double()).sum().backward()
+    model = model.cuda()
+    est = model(mix.cuda())
+    assert est.requires_grad and est.shape == (B, 2, T)
+    assert O.peak_rel_err(est.detach().cpu(), est_o.detach().float()) < 2e-5
+    (est * w_est.cuda()).sum().backward()
+    worst = ('', 0.0)
+    for n, p in model.named_parameters():
+        want = leaves[n].grad.float()
+        denom = max(float(want.abs().max()), 1e-6 * max(float(v.grad.abs().max()) for v in leaves.values()))
+        err = float((p.grad.cpu() - want).abs().max()) / denom
+        worst = max(worst, (n, err), key=lambda t: t[1])
+        assert err < 2e-3, (n, err)
+    print('worst gradient error (TasNet)', worst)
+
+
+def test_pit_assignment_and_bss_train_step():
+    from tss_with_dprnn_b200._lib import lib
+    from tss_with_dprnn_b200.train import TrainStep
+    g = torch.Generator().manual_seed(51)
+    B, T = 4, 3001
+    tgt = 0.1 * torch.randn(B, 2, T, generator=g)
+    est = tgt + 0.05 * torch.randn(B, 2, T, generator=g)
+    est[1] = est[1].flip(0)                                     # utterances 1 and 3: the swapped assignment is the better one
+    est[3] = est[3].flip(0)
+    want_loss, pw_o, swapped_o = oracle_pit_loss(est.double(), tgt.double())
+    tperm, perm = torch.empty(B, 2, T, device='cuda'), torch.empty(B, device='cuda', dtype=torch.int32)
+    pw = torch.empty(B, 2, 2, device='cuda')
+    lib().call('dprnn_pit2_assign', est.cuda(), tgt.cuda(), B, T, tperm, perm, pw, torch.cuda.current_stream().cuda_stream)
+    assert perm.cpu().tolist() == [int(v) for v in swapped_o] == [0, 1, 0, 1]
+    assert float((pw.cpu() - pw_o.float()).abs().max()) < 1e-3
+    assert torch.equal(tperm.cpu()[1], tgt[1].flip(0)) and torch.equal(tperm.cpu()[0], tgt[0])
+    # one full BSS iteration (PIT loss, clip 5, Adam 1e-3 as scripts/train/config_bss.yaml) against the oracle + torch
+    kw = dict(KW_BSS)
+    torch.manual_seed(43)
+    model = P.DPRNNTasNet(**kw).train()
+    Bm, Tm = 2, 1501
+    mix = 0.05 * torch.randn(Bm, Tm, generator=g)
+    targets = 0.05 * torch.randn(Bm, 2, Tm, generator=g)
+    sd = {k: v.detach().clone().double() for k, v in model.state_dict().items()}
+    names = [n for n, p in model.named_parameters() if p.requires_grad]
+    leaves = [sd[n].requires_grad_(True) for n in names]
+    cfg = O.Config(**{k: kw[k] for k in ('input_size', 'feature_size', 'hidden_size', 'chunk_length', 'kernel_size',
+                                         'hop_length', 'n_repeats', 'bidirectional', 'norm_type', 'activation_type')})
+    opt = torch.optim.Adam(leaves, lr=1e-3)
+    loss_o, _, _ = oracle_pit_loss(O.tasnet_forward(mix.double(), sd, cfg, fast=False), targets.double())
+    loss_o.backward()
+    norm_o = float(torch.nn.utils.clip_grad_norm_(leaves, 5.0))
+    opt.step()
+    stepper = TrainStep(model.cuda(), lr=1e-3, weight_decay=0.0)
+    loss3 = stepper.step(mix.cuda(), target=targets.cuda())
+    assert abs(float(loss3[0]) - float(loss_o.detach())) < 2e-3 * max(1.0, abs(float(loss_o.detach())))
+    assert abs(float(stepper.opt.total_norm) - norm_o) < 5e-3 * norm_o
+    worst = max(float((dict(model.named_parameters())[n].detach().cpu().double() - leaf.detach()).abs().max())
+                for n, leaf in zip(names, leaves))
+    assert worst < 1e-4, worst

@@ -309,20 +309,104 @@ __global__ void __launch_bounds__(256) convw2_partial_kernel(const float* __rest
 // encoder adjoint wrt the waveform is not needed (inputs carry no gradient); its weight gradient is convw2 with
 // z := denc * [enc > 0] and sig := the waveform.
 
-// per-utterance, per-channel sum over time: out[b,c] = sum_l X[b,l,c] (* Y[b,l,c]) - the FiLM / time-mean adjoints
+// per-utterance, per-channel sum over time: out[b,c] = sum_l X[b,l,c] (* Y[b,l,c]) - the FiLM / time-mean adjoints.
+// grid (UCS_PARTS, B): partial sums in fp64, then a fixed-order finalize.
+constexpr int UCS_PARTS = 32;
 __global__ void __launch_bounds__(256) utt_col_sum_kernel(const float* __restrict__ X, const float* __restrict__ Y,
-                                                          long L, int C, float* __restrict__ out) {
+                                                          long L, int C, double* __restrict__ partial) {
     __shared__ double sh[256];
     const int lanes = 256 / C, c = threadIdx.x % C, rl = threadIdx.x / C;
-    const float* xb = X + (long)blockIdx.x * L * C;
-    const float* yb = Y ? Y + (long)blockIdx.x * L * C : nullptr;
+    const float* xb = X + (long)blockIdx.y * L * C;
+    const float* yb = Y ? Y + (long)blockIdx.y * L * C : nullptr;
+    const long per = (L + UCS_PARTS - 1) / UCS_PARTS;
+    const long l0 = blockIdx.x * per, l1 = min(l0 + per, L);
     double s = 0.0;
-    for (long l = rl; l < L; l += lanes) s += (double)(yb ? xb[l * C + c] * yb[l * C + c] : xb[l * C + c]);
+    for (long l = l0 + rl; l < l1; l += lanes) s += (double)(yb ? xb[l * C + c] * yb[l * C + c] : xb[l * C + c]);
     sh[threadIdx.x] = s;
     __syncthreads();
     if (rl == 0) {
         for (int i = 1; i < lanes; ++i) s += sh[i * C + c];
-        out[(long)blockIdx.x * C + c] = (float)s;
+        partial[((long)blockIdx.y * UCS_PARTS + blockIdx.x) * C + c] = s;
+    }
+}
+__global__ void utt_col_sum_final_kernel(const double* __restrict__ partial, int C, long total, float* __restrict__ out) {
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    if (e >= total) return;
+    const long b = e / C;
+    const int c = (int)(e % C);
+    double s = 0.0;
+    for (int p = 0; p < UCS_PARTS; ++p) s += partial[(b * UCS_PARTS + p) * C + c];
+    out[e] = (float)s;
+}
+
+// ---------------------------------------------------------------- attention fusion backward (dprnn_spe.py:177-183,217-225)
+// fused[b,l,c] = n[b,l,c] * v[b,c] * r[b,l],  r = 1 + softmax_j(s)[src(l)],  s[b,j] = sum_c v[b,c] * (bavg[c] + sum_i
+// wavg[c,i] n[b, j*ksz+i, c]).   dr[row] = sum_c dfused * n * v                                   (warp per row)
+__global__ void row_dot3_kernel(const float* __restrict__ A, const float* __restrict__ Bm, const float* __restrict__ v,
+                                long rows, long rows_per_utt, int C, float* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const long warp = (blockIdx.x * (long)blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long r = warp; r < rows; r += nwarps) {
+        const float* vb = v + (r / rows_per_utt) * C;
+        float acc = 0.f;
+        for (int c = lane; c < C; c += 32) acc = fmaf(A[r * C + c] * Bm[r * C + c], vb[c], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) out[r] = acc;
+    }
+}
+
+__device__ __forceinline__ long att_src(long l, long L, long La, float scale) {      // ATen nearest-upsample index rule
+    if (La == L) return l;
+    if (L == 2 * La) return l >> 1;
+    long src = (long)floorf(__fmul_rn((float)l, scale));
+    return src > La - 1 ? La - 1 : src;
+}
+
+// one CTA per utterance: da[j] = sum_{l : src(l) = j} dr[l] (upsample adjoint, fixed order);  ds = a * (da - <a, da>)
+// (softmax adjoint);  w2[l] = ds[l / ksz] for l < La*ksz, else 0 (what reaches the frames through the average conv)
+__global__ void __launch_bounds__(256) att_softmax_bwd_kernel(const float* __restrict__ dr, const float* __restrict__ a,
+                                                              long L, long La, int ksz, float scale,
+                                                              float* __restrict__ w2, float* __restrict__ ds) {
+    __shared__ double scratch[32];
+    const long b = blockIdx.x;
+    const float* drb = dr + b * L;
+    const float* ab = a + b * La;
+    float* dsb = ds + b * La;
+    float* w2b = w2 + b * L;
+    const float inv = (float)L / (float)La;
+    double dot = 0.0;
+    for (long j = threadIdx.x; j < La; j += 256) {
+        long lo = (long)floorf((float)j * inv) - 2, hi = (long)ceilf((float)(j + 1) * inv) + 2;
+        if (lo < 0) lo = 0;
+        if (hi > L - 1 || j == La - 1) hi = L - 1;
+        float s = 0.f;
+        for (long l = lo; l <= hi; ++l)
+            if (att_src(l, L, La, scale) == j) s += drb[l];
+        dsb[j] = s;
+        dot += (double)ab[j] * (double)s;
+    }
+    dot = block_sum(dot, scratch);
+    const float fdot = (float)dot;
+    for (long j = threadIdx.x; j < La; j += 256) {
+        const float v = ab[j] * (dsb[j] - fdot);
+        dsb[j] = v;
+        for (int i = 0; i < ksz; ++i) w2b[j * ksz + i] = v;
+    }
+    for (long l = La * ksz + threadIdx.x; l < L; l += 256) w2b[l] = 0.f;
+}
+
+// g = dfused * r[row] + w2[row] * wavg[c, l % ksz];   dn = v[b,c] * g;   tdv = n * g  (summed over time by the caller)
+__global__ void att_bwd_apply_kernel(const float* __restrict__ dfused, const float* __restrict__ n,
+                                     const float* __restrict__ v, const float* __restrict__ r,
+                                     const float* __restrict__ w2, const float* __restrict__ wavg, long L, int C, int ksz,
+                                     long total, float* __restrict__ dn, float* __restrict__ tdv) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c = (int)(idx % C);
+        const long row = idx / C, b = row / L, l = row - b * L;
+        const float g = fmaf(w2[row], wavg[c * ksz + (int)(l % ksz)], dfused[idx] * r[row]);
+        dn[idx] = v[b * C + c] * g;
+        tdv[idx] = n[idx] * g;
     }
 }
 
@@ -519,9 +603,41 @@ int dprnn_convw2_grad(const float* z, const float* sig, int B, long L, int N, fl
     return 0;
 }
 
-int dprnn_utt_col_sum(const float* X, const float* Y, int B, long L, int C, float* out, void* stream) {
-    DPRNN_CHECK_ARG(X && out && B > 0 && L > 0 && C > 0 && 256 % C == 0);
-    utt_col_sum_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(X, Y, L, C, out);
+size_t dprnn_utt_col_sum_workspace_bytes(int B, int C) { return (size_t)B * UCS_PARTS * C * sizeof(double); }
+
+int dprnn_utt_col_sum(const float* X, const float* Y, int B, long L, int C, float* out, void* workspace, void* stream) {
+    DPRNN_CHECK_ARG(X && out && workspace && B > 0 && B <= 65535 && L > 0 && C > 0 && 256 % C == 0);
+    utt_col_sum_kernel<<<dim3(UCS_PARTS, B), 256, 0, (cudaStream_t)stream>>>(X, Y, L, C, (double*)workspace);
+    DPRNN_CHECK_LAUNCH();
+    const long total = (long)B * C;
+    utt_col_sum_final_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>((const double*)workspace, C,
+                                                                                              total, out);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_row_dot3(const float* A, const float* Bm, const float* v, long rows, long rows_per_utt, int C, float* out,
+                   void* stream) {
+    DPRNN_CHECK_ARG(A && Bm && v && out && rows > 0 && rows_per_utt > 0 && rows % rows_per_utt == 0 && C > 0);
+    row_dot3_kernel<<<bgrid(rows * 32, 256), 256, 0, (cudaStream_t)stream>>>(A, Bm, v, rows, rows_per_utt, C, out);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_att_softmax_bwd(const float* dr, const float* a, int B, long L, int ksz, float* w2, float* ds, void* stream) {
+    DPRNN_CHECK_ARG(dr && a && w2 && ds && B > 0 && ksz > 0 && L >= ksz);
+    const long La = (L - ksz) / ksz + 1;
+    att_softmax_bwd_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(dr, a, L, La, ksz, (float)La / (float)L, w2, ds);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_att_bwd_apply(const float* dfused, const float* n, const float* v, const float* r, const float* w2,
+                        const float* wavg, int B, long L, int C, int ksz, float* dn, float* tdv, void* stream) {
+    DPRNN_CHECK_ARG(dfused && n && v && r && w2 && wavg && dn && tdv && B > 0 && L > 0 && C > 0 && ksz > 0);
+    const long total = (long)B * L * C;
+    att_bwd_apply_kernel<<<bgrid(total, 256), 256, 0, (cudaStream_t)stream>>>(dfused, n, v, r, w2, wavg, L, C, ksz, total,
+                                                                            dn, tdv);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

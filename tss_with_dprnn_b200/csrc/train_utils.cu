@@ -81,6 +81,10 @@ __global__ void __launch_bounds__(256) train_loss_kernel(const float* __restrict
     const double c_e = coef[0], c_t = coef[1], me = coef[2], mt = coef[3];
     for (long i = threadIdx.x; i < T; i += 256)
         d_est[(long)b * T + i] = (float)(c_e * ((double)e[i] - me) + c_t * ((double)t[i] - mt));
+    if (!logits) {                       // BSS trainer: SI-SDR only
+        if (threadIdx.x == 0) terms[b * 2 + 1] = 0.f;
+        return;
+    }
     // cross entropy over C classes
     const float* lg = logits + (long)b * C;
     double mx = -1e300;
@@ -98,6 +102,51 @@ __global__ void __launch_bounds__(256) train_loss_kernel(const float* __restrict
     if (threadIdx.x == 0) terms[b * 2 + 1] = (float)(gamma * (mx + log(sum) - (double)lg[y]));
     for (int j = threadIdx.x; j < C; j += 256)
         d_logits[(long)b * C + j] = (float)((double)gamma / B * (exp((double)lg[j] - mx) / sum - (j == y ? 1.0 : 0.0)));
+}
+
+// Permutation-invariant assignment for two sources (asteroid PITLossWrapper(pairwise_neg_sisdr, pit_from='pw_mtx') as
+// src/trainers/trainer.py:39 builds it): per utterance the pairwise neg-SI-SDR matrix of est [B,2,T] x target [B,2,T],
+// the permutation with the smaller summed loss (ties: identity, the first in asteroid's permutation list), and the
+// targets re-ordered accordingly (target_perm [B,2,T]) so that the loss / gradient kernel runs on matched rows.
+__global__ void __launch_bounds__(256) pit2_kernel(const float* __restrict__ est, const float* __restrict__ tgt, long T,
+                                                   float* __restrict__ tgt_perm, int* __restrict__ perm,
+                                                   float* __restrict__ pw) {
+    __shared__ double scratch[32];
+    __shared__ int choice;
+    const int b = blockIdx.x;
+    const float* e0 = est + (long)b * 2 * T; const float* e1 = e0 + T;
+    const float* t0 = tgt + (long)b * 2 * T; const float* t1 = t0 + T;
+    double s[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = 0.0;
+    for (long i = threadIdx.x; i < T; i += 256) {
+        const double a0 = e0[i], a1 = e1[i], c0 = t0[i], c1 = t1[i];
+        s[0] += a0; s[1] += a1; s[2] += c0; s[3] += c1;
+        s[4] += a0 * a0; s[5] += a1 * a1; s[6] += c0 * c0; s[7] += c1 * c1;
+        s[8] += a0 * c0; s[9] += a0 * c1; s[10] += a1 * c0; s[11] += a1 * c1;
+    }
+#pragma unroll
+    for (int i = 0; i < 12; ++i) s[i] = block_sum(s[i], scratch);
+    if (threadIdx.x == 0) {
+        const double N = (double)T, eps = 1e-8;
+        double L[2][2];
+        for (int i = 0; i < 2; ++i)
+            for (int j = 0; j < 2; ++j) {
+                const double ee = s[4 + i] - s[i] * s[i] / N, tt = s[6 + j] - s[2 + j] * s[2 + j] / N;
+                const double et = s[8 + 2 * i + j] - s[i] * s[2 + j] / N;
+                const double alpha = et / (tt + eps), a2 = alpha * alpha * tt;
+                const double n2 = fmax(ee - 2.0 * alpha * et + a2, 0.0);
+                L[i][j] = -10.0 * log10(a2 / (n2 + eps) + eps);
+                if (pw) pw[b * 4 + i * 2 + j] = (float)L[i][j];
+            }
+        choice = (L[0][1] + L[1][0] < L[0][0] + L[1][1]) ? 1 : 0;
+        perm[b] = choice;
+    }
+    __syncthreads();
+    const float* src0 = choice ? t1 : t0;
+    const float* src1 = choice ? t0 : t1;
+    float* d0 = tgt_perm + (long)b * 2 * T;
+    for (long i = threadIdx.x; i < T; i += 256) { d0[i] = src0[i]; d0[T + i] = src1[i]; }
 }
 
 __global__ void train_loss_final_kernel(const float* __restrict__ terms, int B, float* __restrict__ loss) {
@@ -161,11 +210,20 @@ extern "C" int dprnn_si_sdr(const float* est, const float* target, const long* o
 extern "C" int dprnn_train_loss(const float* est, const float* target, long T, const float* logits, int C, const long* spk,
                                 float ce_gamma, int B, float* terms, float* loss3, float* d_est, float* d_logits,
                                 void* stream) {
-    DPRNN_CHECK_ARG(est && target && logits && spk && terms && loss3 && d_est && d_logits && B > 0 && T > 0 && C > 0);
+    DPRNN_CHECK_ARG(est && target && terms && loss3 && d_est && B > 0 && T > 0);
+    DPRNN_CHECK_ARG(!logits || (spk && d_logits && C > 0));
     train_loss_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(est, target, T, logits, C, spk, ce_gamma, B, terms, d_est,
                                                            d_logits);
     DPRNN_CHECK_LAUNCH();
     train_loss_final_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(terms, B, loss3);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_pit2_assign(const float* est, const float* target, int B, long T, float* target_perm, int* perm,
+                                 float* pairwise, void* stream) {
+    DPRNN_CHECK_ARG(est && target && target_perm && perm && B > 0 && T > 0);
+    pit2_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(est, target, T, target_perm, perm, pairwise);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

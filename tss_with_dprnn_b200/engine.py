@@ -164,8 +164,8 @@ class Engine(RaggedMixin):
     def _guard_autograd(self):
         if torch.is_grad_enabled() and self.model.training and any(p.requires_grad for p in self.model.parameters()):
             raise NotImplementedError(
-                'backward of the B200 separation path is not built yet (SURVEY.md section 8, cfg 5): call under '
-                'torch.no_grad() or model.eval()')
+                'the backward of this model / fusion is not built (train.py covers DPRNNTasNet and DPRNNSpeTasNet with '
+                "fusion film | add | mul | cat | att): call under torch.no_grad() or model.eval()")
 
     def gemm(self, A, Wt, M, N, K, out=None, bias=None, bias_per_utt=False, bias_scale=1.0, rows_per_utt=0,
              p_scale=None, p_shift=None, p_add=None, rowscale=None, epi=EPI_NONE):
@@ -556,9 +556,13 @@ class Engine(RaggedMixin):
         return tuple(torch.cat([p[j] for p in parts], 0) for j in range(len(parts[0])))
 
     def forward_bss(self, mix):
-        self._guard_autograd()
         mix = self._check_input(mix, 'input')
         cfg = self.model.cfg
+        if cfg['kind'] == 'bss' and self._wants_grad():
+            # training (scripts/train/config_bss.yaml): one autograd node over the hand-written forward / backward
+            from .train import forward_with_grad
+            return forward_with_grad(self.model, mix)
+        self._guard_autograd()
         N = cfg['input_size']
 
         def group_of(mixs, b0, b1):

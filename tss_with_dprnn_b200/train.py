@@ -68,6 +68,13 @@ class _Ops:
         ws = torch.empty(self.L.query('dprnn_col_sum_workspace_bytes', N), device=self.dev, dtype=torch.uint8)
         self.L.call('dprnn_col_sum', X, ldx or N, Y, ldx or N, M, N, out, int(accumulate), ws, _st())
 
+    def utt_colsum(self, X, Y, B, L, C):
+        """out[b,c] = sum_l X[b,l,c] (* Y[b,l,c])"""
+        out = self.empty(B, C)
+        ws = torch.empty(self.L.query('dprnn_utt_col_sum_workspace_bytes', B, C), device=self.dev, dtype=torch.uint8)
+        self.L.call('dprnn_utt_col_sum', X, Y, B, L, C, out, ws, _st())
+        return out
+
     def utt_stats(self, x, B, elems, eps):
         ws = torch.empty(self.L.query('dprnn_utt_stats_workspace_bytes', B), device=self.dev, dtype=torch.uint8)
         mr = self.empty(B, 2)
@@ -104,9 +111,11 @@ def _norm_params(mod):
 
 def _check_supported(model):
     cfg = model.cfg
-    if cfg['kind'] != 'spe' or cfg['fusion_type'] not in ('film', 'add', 'mul', 'cat'):
-        raise NotImplementedError("training is built for DPRNNSpeTasNet with fusion_type in {'film','add','mul','cat'} "
-                                  '(cfg 5: film); other models keep their forward-only path')
+    if cfg['kind'] not in ('spe', 'bss') or (cfg['kind'] == 'spe' and cfg['fusion_type'] not in
+                                                  ('film', 'add', 'mul', 'cat', 'att')):
+        raise NotImplementedError("training is built for DPRNNTasNet (scripts/train/config_bss.yaml) and DPRNNSpeTasNet "
+                                  "with fusion_type in {'film','add','mul','cat','att'} (cfg 5: film; "
+                                  "scripts/train/config_tss.yaml: att); other models keep their forward-only path")
     if cfg['kernel_size'] != 2 or cfg['stride'] != 1 or cfg['feature_size'] != 128 or cfg['hidden_size'] != 128 \
             or cfg['chunk_length'] != 2 * cfg['hop_length'] or cfg['input_size'] not in (32, 64, 128):
         raise NotImplementedError('training is built for the shipped geometry (kernel 2, stride 1, F = H = 128, hop = K/2)')
@@ -115,8 +124,9 @@ def _check_supported(model):
 # --------------------------------------------------------------------------------------------------------------
 # forward (train mode)
 # --------------------------------------------------------------------------------------------------------------
-def forward_train(model, mix, ref, div):
-    """-> est [B,T], logits [B,num_spks], ctx (everything the backward needs)."""
+def forward_train(model, mix, ref=None, div=None):
+    """DPRNNSpeTasNet: -> est [B,T], logits [B,num_spks], ctx (everything the backward needs).
+    DPRNNTasNet (ref = div = None): -> est [B,2,T], None, ctx."""
     _check_supported(model)
     L_, cfg, sep = lib(), model.cfg, model.separation
     dev = mix.device
@@ -124,67 +134,72 @@ def forward_train(model, mix, ref, div):
     st = _st()
     N, F, H, K, P = cfg['input_size'], cfg['feature_size'], cfg['hidden_size'], cfg['chunk_length'], cfg['hop_length']
     B, T = mix.shape
-    Lm, Lr = T - 1, ref.shape[1] - 1
+    is_spe = cfg['kind'] == 'spe'
+    Lm, Lr = T - 1, (ref.shape[1] - 1 if is_spe else 0)
     ctx = dict(B=B, T=T, L=Lm, Lr=Lr, mix=mix, ref=ref, div=div, tf32=ops.tf32)
     w_enc = model.encoder.conv1d.weight.detach().reshape(N, 2).contiguous()
     enc = ops.empty(B, Lm, N)
     L_.call('dprnn_encoder_fwd', mix, w_enc, enc, B, T, N, 2, 1, st)
-    feats = ops.empty(B, Lr, N)
-    L_.call('dprnn_encoder_fwd', ref, w_enc, feats, B, ref.shape[1], N, 2, 1, st)
-    ctx.update(enc=enc, feats=feats)
+    feats = emb = None
+    E = 0
+    if is_spe:
+        feats = ops.empty(B, Lr, N)
+        L_.call('dprnn_encoder_fwd', ref, w_enc, feats, B, ref.shape[1], N, 2, 1, st)
+    ctx.update(enc=enc, feats=feats, emb=None)
 
-    # ---- speaker encoder (dprnn_spe.py:115-122,156-163), BatchNorm in train mode
-    se = sep.spk_encoder
-    mr_s = ops.utt_stats(feats, B, Lr * N, se[0].eps)
-    s1 = ops.empty(B, N); s0 = ops.empty(B, N)
-    L_.call('dprnn_norm_affine', mr_s, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
-    gnf = torch.empty_like(feats)                                  # GroupNorm(feats): kept for dW of conv0
-    L_.call('dprnn_prologue_apply', feats, gnf, B * Lr, N, Lr, s1, s0, None, None, st)
-    O = se[1].weight.shape[0]
-    x = ops.gemm(gnf, se[1].weight.detach().reshape(O, N).t().contiguous(), B * Lr, O, N, bias=se[1].bias.detach())
-    ctx.update(mr_s=mr_s, gnf=gnf)
-    res, Lx = [], Lr
-    for rb in (se[2], se[3], se[4]):
-        Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
-        rows = B * Lx
-        rc = dict(x=x, Lx=Lx, Cin=Cin, Cout=Cout)
-        ws = torch.empty(L_.query('dprnn_bn_workspace_bytes', Cout), device=dev, dtype=torch.uint8)
+    if is_spe:
+        # ---- speaker encoder (dprnn_spe.py:115-122,156-163), BatchNorm in train mode
+        se = sep.spk_encoder
+        mr_s = ops.utt_stats(feats, B, Lr * N, se[0].eps)
+        s1 = ops.empty(B, N); s0 = ops.empty(B, N)
+        L_.call('dprnn_norm_affine', mr_s, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
+        gnf = torch.empty_like(feats)                                  # GroupNorm(feats): kept for dW of conv0
+        L_.call('dprnn_prologue_apply', feats, gnf, B * Lr, N, Lr, s1, s0, None, None, st)
+        O = se[1].weight.shape[0]
+        x = ops.gemm(gnf, se[1].weight.detach().reshape(O, N).t().contiguous(), B * Lr, O, N, bias=se[1].bias.detach())
+        ctx.update(mr_s=mr_s, gnf=gnf)
+        res, Lx = [], Lr
+        for rb in (se[2], se[3], se[4]):
+            Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
+            rows = B * Lx
+            rc = dict(x=x, Lx=Lx, Cin=Cin, Cout=Cout)
+            ws = torch.empty(L_.query('dprnn_bn_workspace_bytes', Cout), device=dev, dtype=torch.uint8)
 
-        def bn(y, bnm):
-            scale, shift = ops.empty(Cout), ops.empty(Cout)
-            L_.call('dprnn_batchnorm_affine', y, rows, Cout, bnm.weight.detach(), bnm.bias.detach(), bnm.running_mean,
-                    bnm.running_var, 1, float(bnm.eps), float(bnm.momentum if bnm.momentum is not None else 0.1), ws,
-                    scale, shift, st)
-            bnm.num_batches_tracked += 1
-            return scale, shift
+            def bn(y, bnm):
+                scale, shift = ops.empty(Cout), ops.empty(Cout)
+                L_.call('dprnn_batchnorm_affine', y, rows, Cout, bnm.weight.detach(), bnm.bias.detach(), bnm.running_mean,
+                        bnm.running_var, 1, float(bnm.eps), float(bnm.momentum if bnm.momentum is not None else 0.1), ws,
+                        scale, shift, st)
+                bnm.num_batches_tracked += 1
+                return scale, shift
 
-        y1 = ops.gemm(x, rb.conv1.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
-        sc1, sh1 = bn(y1, rb.batch_norm1)
-        a1 = ops.empty(rows, Cout)
-        L_.call('dprnn_affine_prelu', y1, sc1, sh1, rb.prelu1.weight.detach(), a1, rows, Cout, st)
-        y2 = ops.gemm(a1, rb.conv2.weight.detach().reshape(Cout, Cout).t().contiguous(), rows, Cout, Cout)
-        sc2, sh2 = bn(y2, rb.batch_norm2)
-        if hasattr(rb, 'conv_downsample'):
-            skip = ops.gemm(x, rb.conv_downsample.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
-        else:
-            skip = x
-        Lo = Lx // 3
-        out = ops.empty(B, Lo, Cout)
-        L_.call('dprnn_affine_add_prelu_pool3', y2, sc2, sh2, skip, rb.prelu2.weight.detach(), out, B, Lx, Cout, st)
-        rc.update(y1=y1, sc1=sc1, sh1=sh1, a1=a1, y2=y2, sc2=sc2, sh2=sh2, skip=skip)
-        res.append(rc)
-        x, Lx = out.view(B * Lo, Cout), Lo
-    E = se[5].weight.shape[0]
-    C5 = se[5].weight.shape[1]
-    z5 = ops.gemm(x, se[5].weight.detach().reshape(E, C5).t().contiguous(), B * Lx, E, C5, bias=se[5].bias.detach())
-    emb = ops.empty(B, E)
-    L_.call('dprnn_time_sum', z5, emb, B, Lx, E, div, st)
-    ctx.update(res=res, x3=x, L3=Lx, emb=emb)
+            y1 = ops.gemm(x, rb.conv1.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
+            sc1, sh1 = bn(y1, rb.batch_norm1)
+            a1 = ops.empty(rows, Cout)
+            L_.call('dprnn_affine_prelu', y1, sc1, sh1, rb.prelu1.weight.detach(), a1, rows, Cout, st)
+            y2 = ops.gemm(a1, rb.conv2.weight.detach().reshape(Cout, Cout).t().contiguous(), rows, Cout, Cout)
+            sc2, sh2 = bn(y2, rb.batch_norm2)
+            if hasattr(rb, 'conv_downsample'):
+                skip = ops.gemm(x, rb.conv_downsample.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
+            else:
+                skip = x
+            Lo = Lx // 3
+            out = ops.empty(B, Lo, Cout)
+            L_.call('dprnn_affine_add_prelu_pool3', y2, sc2, sh2, skip, rb.prelu2.weight.detach(), out, B, Lx, Cout, st)
+            rc.update(y1=y1, sc1=sc1, sh1=sh1, a1=a1, y2=y2, sc2=sc2, sh2=sh2, skip=skip)
+            res.append(rc)
+            x, Lx = out.view(B * Lo, Cout), Lo
+        E = se[5].weight.shape[0]
+        C5 = se[5].weight.shape[1]
+        z5 = ops.gemm(x, se[5].weight.detach().reshape(E, C5).t().contiguous(), B * Lx, E, C5, bias=se[5].bias.detach())
+        emb = ops.empty(B, E)
+        L_.call('dprnn_time_sum', z5, emb, B, Lx, E, div, st)
+        ctx.update(res=res, x3=x, L3=Lx, emb=emb)
 
     # ---- bottleneck norm + fusion + 1x1 conv (dprnn_spe.py:136-143)
     gamma, beta, eps = _norm_params(sep.bottleneck[0])
     mr_e = ops.utt_stats(enc, B, Lm * N, eps)
-    ft = cfg['fusion_type']
+    ft = cfg['fusion_type'] if is_spe else None
 
     def lin(m):
         out = ops.empty(B, m.weight.shape[0])
@@ -204,17 +219,27 @@ def forward_train(model, mix, ref, div):
         bias = ops.empty(B, F)
         L_.call('dprnn_small_linear', emb, E, bw.data_ptr() + 4 * N, N + E, sep.bottleneck[1].bias.detach(), bias, F, B, F, E, 0, st)
         bias_per_utt = True
+    rowscale = att_a = None
+    if ft == 'att':                                                 # dprnn_spe.py:177-183,217-225
+        ksz = cfg['kernel_size']
+        mulc = lin(sep.fusion_linear)
+        n1, n0 = ops.empty(B, N), ops.empty(B, N)
+        L_.call('dprnn_norm_affine', mr_e, gamma.detach(), beta.detach(), None, n1, n0, B, N, st)
+        att_a = ops.empty(B, (Lm - ksz) // ksz + 1)                 # softmax over the averaged frames (kept for the backward)
+        rowscale = ops.empty(B, Lm)
+        L_.call('dprnn_att_rowscale', enc, n1, n0, sep.average.weight.detach(), sep.average.bias.detach(), mulc, att_a,
+                rowscale, B, Lm, N, ksz, st)
     s1e, s0e = ops.empty(B, N), ops.empty(B, N)
     L_.call('dprnn_norm_affine', mr_e, gamma.detach(), beta.detach(), mulc, s1e, s0e, B, N, st)
     fused = torch.empty_like(enc)                                   # fusion(GroupNorm(enc)): kept for dW of the 1x1 conv
-    L_.call('dprnn_prologue_apply', enc, fused, B * Lm, N, Lm, s1e, s0e, addc, None, st)
+    L_.call('dprnn_prologue_apply', enc, fused, B * Lm, N, Lm, s1e, s0e, addc, rowscale, st)
     y = ops.gemm(fused, bw[:, :N].t().contiguous(), B * Lm, F, N, bias=bias, bias_per_utt=bias_per_utt, rows_per_utt=Lm)
     S = L_.query('dprnn_num_chunks', Lm, K, P)
     xs = ops.empty(B, S, K, F)
     L_.call('dprnn_unfold', y, xs, B, Lm, K, P, F, st)
     del y
     rows = B * S * K
-    ctx.update(mr_e=mr_e, mulc=mulc, addc=addc, fused=fused, S=S, rows=rows)
+    ctx.update(mr_e=mr_e, mulc=mulc, addc=addc, fused=fused, S=S, rows=rows, rowscale=rowscale, att_a=att_a)
 
     # ---- DPRNN blocks (dprnn.py:79-99)
     halves = []
@@ -255,21 +280,30 @@ def forward_train(model, mix, ref, div):
     z = ops.empty(B, Lm, F)
     L_.call('dprnn_fold_prelu', xs, z, B, Lm, K, P, F, sep.prelu.weight.detach(), st)
     cw = sep.conv2d.weight.detach().reshape(2 * F, F)
-    u = ops.gemm(z, cw[:F].t().contiguous(), B * Lm, F, F, bias=(2.0 * sep.conv2d.bias.detach()[:F]).contiguous())
+    cb = sep.conv2d.bias.detach()
     wog = torch.cat([sep.out[0].weight.detach().reshape(F, F), sep.gate[0].weight.detach().reshape(F, F)], 0)   # [2F,F]
     bog = torch.cat([sep.out[0].bias.detach(), sep.gate[0].bias.detach()], 0)
-    pre = ops.gemm(u, wog.t().contiguous(), B * Lm, 2 * F, F, bias=bog)
-    g = ops.empty(B * Lm, F)
-    L_.call('dprnn_gated_fwd', pre, g, B * Lm, F, st)
     act = EPI_SIGMOID if cfg['activation_type'] == 'sigmoid' else EPI_RELU
-    m = ops.gemm(g, sep.end_conv1x1.weight.detach().reshape(N, F).t().contiguous(), B * Lm, N, F, epi=act)
-    est = ops.empty(B, T)
     w_dec = model.decoder.weight.detach().reshape(N, 2).contiguous()
-    L_.call('dprnn_mask_decode', m, Lm * N, enc, w_dec, est, T, B, Lm, N, 2, 1, st)
-    logits = ops.empty(B, sep.pred_linear.weight.shape[0])
-    L_.call('dprnn_small_linear', emb, E, sep.pred_linear.weight.detach(), E, sep.pred_linear.bias.detach(), logits,
-            logits.shape[1], B, logits.shape[1], E, 0, st)
-    ctx.update(z=z, u=u, pre=pre, g=g, m=m, wog=wog, cw=cw)
+    # DPRNN-Spe keeps speaker 0 only (dprnn_spe.py:325); DPRNN-TasNet decodes both (dprnn.py:277-281)
+    spks = (0,) if is_spe else (0, 1)
+    est = ops.empty(B, T) if is_spe else ops.empty(B, 2, T)
+    heads = []
+    for sp in spks:
+        u = ops.gemm(z, cw[sp * F:(sp + 1) * F].t().contiguous(), B * Lm, F, F,
+                     bias=(2.0 * cb[sp * F:(sp + 1) * F]).contiguous())       # overlap-add sums two chunks: bias twice
+        pre = ops.gemm(u, wog.t().contiguous(), B * Lm, 2 * F, F, bias=bog)
+        g = ops.empty(B * Lm, F)
+        L_.call('dprnn_gated_fwd', pre, g, B * Lm, F, st)
+        m = ops.gemm(g, sep.end_conv1x1.weight.detach().reshape(N, F).t().contiguous(), B * Lm, N, F, epi=act)
+        L_.call('dprnn_mask_decode', m, Lm * N, enc, w_dec, est.data_ptr() + 4 * sp * T, len(spks) * T, B, Lm, N, 2, 1, st)
+        heads.append(dict(u=u, pre=pre, g=g, m=m))
+    logits = None
+    if is_spe:
+        logits = ops.empty(B, sep.pred_linear.weight.shape[0])
+        L_.call('dprnn_small_linear', emb, E, sep.pred_linear.weight.detach(), E, sep.pred_linear.bias.detach(), logits,
+                logits.shape[1], B, logits.shape[1], E, 0, st)
+    ctx.update(z=z, heads=heads, wog=wog, cw=cw)
     return est, logits, ctx
 
 
@@ -286,42 +320,58 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
     N, F, H, K, P = cfg['input_size'], cfg['feature_size'], cfg['hidden_size'], cfg['chunk_length'], cfg['hop_length']
     B, T, Lm, Lr, S, rows = ctx['B'], ctx['T'], ctx['L'], ctx['Lr'], ctx['S'], ctx['rows']
     enc, feats, emb, div = ctx['enc'], ctx['feats'], ctx['emb'], ctx['div']
-    E = emb.shape[1]
+    is_spe = cfg['kind'] == 'spe'
+    E = emb.shape[1] if is_spe else 0
     if G is None:
         G = {n: torch.zeros_like(p) for n, p in model.named_parameters() if p.requires_grad}
-    d_est, d_logits = d_est.contiguous().float(), d_logits.contiguous().float()
+    d_est = d_est.contiguous().float()
+    if is_spe:
+        d_logits = d_logits.contiguous().float()
     ML = B * Lm
 
-    # ---- decoder, mask, end conv, gated head, conv2d
-    m, g, pre, u, z = ctx['m'], ctx['g'], ctx['pre'], ctx['u'], ctx['z']
-    dze = ops.empty(B, Lm, N)
+    # ---- decoder, mask, end conv, gated head, conv2d (per decoded speaker)
+    z = ctx['z']
     w_dec = model.decoder.weight.detach().reshape(N, 2).contiguous()
-    L_.call('dprnn_decoder_bwd', d_est, w_dec, dze, B, Lm, N, st)
-    me = ops.mul(m, enc.view(ML, N))
     wsw = torch.empty(L_.query('dprnn_convw2_workspace_bytes', N), device=dev, dtype=torch.uint8)
-    L_.call('dprnn_convw2_grad', me, d_est, B, Lm, N, G['decoder.weight'], 1, wsw, st)
-    del me
-    dm = ops.mul(dze.view(ML, N), enc.view(ML, N))
-    denc = ops.mul(dze.view(ML, N), m)                              # gradient reaching enc through the mask product
-    dpm = torch.empty_like(dm)
-    L_.call('dprnn_act_bwd', dm, m, dpm, dm.numel(), 2 if cfg['activation_type'] == 'sigmoid' else 1, st)
-    ops.atb(dpm, g, ML, N, F, G['separation.end_conv1x1.weight'])
-    dg = ops.gemm(dpm, sep.end_conv1x1.weight.detach().reshape(N, F), ML, F, N)
-    dpre = torch.empty_like(pre)
-    L_.call('dprnn_gated_bwd', dg, pre, dpre, ML, F, st)
     gout, ggate = G['separation.out.0.weight'], G['separation.gate.0.weight']
-    ops.atb(dpre, u, ML, F, F, gout, lda=2 * F)
-    ops.atb(dpre.data_ptr() + 4 * F, u, ML, F, F, ggate, lda=2 * F)
-    ops.colsum(dpre, ML, F, G['separation.out.0.bias'], ldx=2 * F)
-    ops.colsum(dpre.data_ptr() + 4 * F, ML, F, G['separation.gate.0.bias'], ldx=2 * F)
-    du = ops.gemm(dpre, ctx['wog'], ML, F, 2 * F)
-    gcw = G['separation.conv2d.weight']                             # [2F,F,1,1]; only the speaker-0 rows get gradient
-    ops.atb(du, z, ML, F, F, gcw)
-    dbc = ops.empty(F)
-    ops.colsum(du, ML, F, dbc, accumulate=False)
-    L_.call('dprnn_axpy', dbc, 2.0, G['separation.conv2d.bias'], F, 1, st)        # the folded conv adds the bias twice
-    dz = ops.gemm(du, ctx['cw'][:F].contiguous(), ML, F, F)
-    del du, dpre, dg, dpm, dm
+    gcw, gcb = G['separation.conv2d.weight'], G['separation.conv2d.bias']       # [2F,F,1,1]: rows of the decoded speakers
+    denc = dz = None
+    for sp, hd in enumerate(ctx['heads']):
+        m, g, pre, u = hd['m'], hd['g'], hd['pre'], hd['u']
+        de = d_est if is_spe else d_est[:, sp].contiguous()
+        dze = ops.empty(B, Lm, N)
+        L_.call('dprnn_decoder_bwd', de, w_dec, dze, B, Lm, N, st)
+        me = ops.mul(m, enc.view(ML, N))
+        L_.call('dprnn_convw2_grad', me, de, B, Lm, N, G['decoder.weight'], 1, wsw, st)
+        del me
+        dm = ops.mul(dze.view(ML, N), enc.view(ML, N))
+        t = ops.mul(dze.view(ML, N), m)                             # gradient reaching enc through the mask product
+        if denc is None:
+            denc = t
+        else:
+            ops.axpy(t, denc)
+        dpm = torch.empty_like(dm)
+        L_.call('dprnn_act_bwd', dm, m, dpm, dm.numel(), 2 if cfg['activation_type'] == 'sigmoid' else 1, st)
+        ops.atb(dpm, g, ML, N, F, G['separation.end_conv1x1.weight'])
+        dg = ops.gemm(dpm, sep.end_conv1x1.weight.detach().reshape(N, F), ML, F, N)
+        dpre = torch.empty_like(pre)
+        L_.call('dprnn_gated_bwd', dg, pre, dpre, ML, F, st)
+        ops.atb(dpre, u, ML, F, F, gout, lda=2 * F)
+        ops.atb(dpre.data_ptr() + 4 * F, u, ML, F, F, ggate, lda=2 * F)
+        ops.colsum(dpre, ML, F, G['separation.out.0.bias'], ldx=2 * F)
+        ops.colsum(dpre.data_ptr() + 4 * F, ML, F, G['separation.gate.0.bias'], ldx=2 * F)
+        du = ops.gemm(dpre, ctx['wog'], ML, F, 2 * F)
+        ops.atb(du, z, ML, F, F, gcw.data_ptr() + 4 * sp * F * F)
+        dbc = ops.empty(F)
+        ops.colsum(du, ML, F, dbc, accumulate=False)
+        L_.call('dprnn_axpy', dbc, 2.0, gcb.data_ptr() + 4 * sp * F, F, 1, st)    # the folded conv adds the bias twice
+        t = ops.gemm(du, ctx['cw'][sp * F:(sp + 1) * F].contiguous(), ML, F, F)
+        if dz is None:
+            dz = t
+        else:
+            ops.axpy(t, dz)
+        del du, dpre, dg, dpm, dm, dze, t
+        hd.clear()
     # fold adjoint = unfold; then the PReLU adjoint on the final residual stream
     xs = ctx['xs']
     dxp = ops.empty(B, S, K, F)
@@ -375,8 +425,8 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
     ops.colsum(dyb, ML, F, G['separation.bottleneck.1.bias'])
     bw = sep.bottleneck[1].weight.detach().reshape(F, -1)
     dfused = ops.gemm(dyb, bw, ML, N, F, ldw=ldw)                    # first N input channels of the conv
-    demb = torch.zeros_like(emb)
-    ft = cfg['fusion_type']
+    demb = torch.zeros_like(emb) if is_spe else None
+    ft = cfg['fusion_type'] if is_spe else None
     gamma, beta, _ = _norm_params(sep.bottleneck[0])
     bn0 = 'separation.bottleneck.0'
     gname = bn0 + ('.gamma' if hasattr(sep.bottleneck[0], 'gamma') else '.weight')
@@ -391,17 +441,31 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
 
     if ft == 'cat':
         # constant channels: y += W_e e per utterance -> de = sum_t dy @ W_e ; dW_e = (sum_t dy)^T e
-        sdy = ops.empty(B, F)
-        L_.call('dprnn_utt_col_sum', dyb, None, B, Lm, F, sdy, st)
+        sdy = ops.utt_colsum(dyb, None, B, Lm, F)
         ops.atb(sdy, emb, B, F, E, gbw.data_ptr() + 4 * N, ldc=ldw)
         t = ops.gemm(sdy, bw.data_ptr() + 4 * N, B, E, F, ldw=ldw)
         ops.axpy(t, demb)
         dgn = dfused
+    elif ft == 'att':
+        # fused = n * v * r with r = 1 + softmax(<avg(n), v>)[src(l)]  (include/dprnn_b200.h, attention-fusion backward)
+        ksz = cfg['kernel_size']
+        s1, s0 = ops.empty(B, N), ops.empty(B, N)
+        L_.call('dprnn_norm_affine', mr_e, gamma.detach(), beta.detach(), None, s1, s0, B, N, st)
+        gn = torch.empty_like(enc)
+        L_.call('dprnn_prologue_apply', enc, gn, ML, N, Lm, s1, s0, None, None, st)
+        dr = ops.empty(B, Lm)
+        L_.call('dprnn_row_dot3', dfused, gn, mulc, ML, Lm, N, dr, st)
+        w2, ds = ops.empty(B, Lm), torch.empty_like(ctx['att_a'])
+        L_.call('dprnn_att_softmax_bwd', dr, ctx['att_a'], B, Lm, ksz, w2, ds, st)
+        dgn, tdv = torch.empty_like(dfused), torch.empty_like(dfused)
+        L_.call('dprnn_att_bwd_apply', dfused, gn, mulc, ctx['rowscale'], w2, sep.average.weight.detach(), B, Lm, N, ksz,
+                dgn, tdv, st)
+        lin_bwd(sep.fusion_linear, 'separation.fusion_linear', ops.utt_colsum(tdv, None, B, Lm, N))
+        del gn, tdv, dr, w2
     else:
         # fused = gn * mulc + addc (mulc / addc may be absent)
         if addc is not None:
-            da2 = ops.empty(B, N)
-            L_.call('dprnn_utt_col_sum', dfused, None, B, Lm, N, da2, st)
+            da2 = ops.utt_colsum(dfused, None, B, Lm, N)
             lin_bwd(sep.fusion_linear_2 if ft == 'film' else sep.fusion_linear, 'separation.fusion_linear_2' if ft == 'film'
                     else 'separation.fusion_linear', da2)
         if mulc is not None:
@@ -410,8 +474,7 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
             L_.call('dprnn_norm_affine', mr_e, gamma.detach(), beta.detach(), None, s1, s0, B, N, st)
             gn = torch.empty_like(enc)
             L_.call('dprnn_prologue_apply', enc, gn, ML, N, Lm, s1, s0, None, None, st)
-            da1 = ops.empty(B, N)
-            L_.call('dprnn_utt_col_sum', dfused, gn, B, Lm, N, da1, st)
+            da1 = ops.utt_colsum(dfused, gn, B, Lm, N)
             lin_bwd(sep.fusion_linear_1 if ft == 'film' else sep.fusion_linear, 'separation.fusion_linear_1' if ft == 'film'
                     else 'separation.fusion_linear', da1)
             dgn = torch.empty_like(dfused)
@@ -423,83 +486,101 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
     ops.gn_bwd(dgn, enc, mr_e, gamma.detach(), B, Lm, N, G[gname], G[bname], dy=denc, accumulate_dy=True)
     del dgn, dfused, dyb
 
-    # ---- pred_linear, then the speaker encoder
-    lin_bwd(sep.pred_linear, 'separation.pred_linear', d_logits)
-    se = sep.spk_encoder
-    L3, x3 = ctx['L3'], ctx['x3']
-    C5 = se[5].weight.shape[1]
-    dscaled = torch.empty_like(demb)
-    L_.call('dprnn_bcast_mul', (1.0 / div).contiguous().view(B, 1).expand(B, E).contiguous(), demb, dscaled, B, 1, E, 0, st)
-    dz5 = ops.empty(B * L3, E)
-    L_.call('dprnn_bcast_mul', dscaled, None, dz5, B, L3, E, 0, st)
-    ops.atb(dz5, x3, B * L3, E, C5, G['separation.spk_encoder.5.weight'])
-    ops.colsum(dz5, B * L3, E, G['separation.spk_encoder.5.bias'])
-    dout = ops.gemm(dz5, se[5].weight.detach().reshape(E, C5).contiguous(), B * L3, C5, E)
-    del dz5
-    for bi, (rb, rc) in reversed(list(enumerate(zip((se[2], se[3], se[4]), ctx['res'])))):
-        pre_n = f'separation.spk_encoder.{bi + 2}'
-        Cin, Cout, Lx, x = rc['Cin'], rc['Cout'], rc['Lx'], rc['x']
-        rws = B * Lx
-        # recompute v2 = BN2(y2) + skip and p2 = prelu(v2)
-        v2 = ops.empty(rws, Cout)
-        one = torch.ones(1, device=dev)
-        L_.call('dprnn_affine_prelu', rc['y2'], rc['sc2'], rc['sh2'], one, v2, rws, Cout, st)      # slope 1 = identity
-        ops.axpy(rc['skip'], v2)
-        p2 = ops.empty(rws, Cout)
-        ident_s, ident_b = torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev)
-        L_.call('dprnn_affine_prelu', v2, ident_s, ident_b, rb.prelu2.weight.detach(), p2, rws, Cout, st)
-        dp2 = ops.empty(rws, Cout)
-        L_.call('dprnn_pool3_bwd', dout, p2, dp2, B, Lx, Cout, st)
-        dv2 = ops.prelu_bwd(dp2, v2, rb.prelu2.weight.detach(), G[pre_n + '.prelu2.weight'])
-        del p2, dp2, v2
+    if is_spe:
+        # ---- pred_linear, then the speaker encoder
+        lin_bwd(sep.pred_linear, 'separation.pred_linear', d_logits)
+        se = sep.spk_encoder
+        L3, x3 = ctx['L3'], ctx['x3']
+        C5 = se[5].weight.shape[1]
+        dscaled = torch.empty_like(demb)
+        L_.call('dprnn_bcast_mul', (1.0 / div).contiguous().view(B, 1).expand(B, E).contiguous(), demb, dscaled, B, 1, E, 0, st)
+        dz5 = ops.empty(B * L3, E)
+        L_.call('dprnn_bcast_mul', dscaled, None, dz5, B, L3, E, 0, st)
+        ops.atb(dz5, x3, B * L3, E, C5, G['separation.spk_encoder.5.weight'])
+        ops.colsum(dz5, B * L3, E, G['separation.spk_encoder.5.bias'])
+        dout = ops.gemm(dz5, se[5].weight.detach().reshape(E, C5).contiguous(), B * L3, C5, E)
+        del dz5
+        for bi, (rb, rc) in reversed(list(enumerate(zip((se[2], se[3], se[4]), ctx['res'])))):
+            pre_n = f'separation.spk_encoder.{bi + 2}'
+            Cin, Cout, Lx, x = rc['Cin'], rc['Cout'], rc['Lx'], rc['x']
+            rws = B * Lx
+            # recompute v2 = BN2(y2) + skip and p2 = prelu(v2)
+            v2 = ops.empty(rws, Cout)
+            one = torch.ones(1, device=dev)
+            L_.call('dprnn_affine_prelu', rc['y2'], rc['sc2'], rc['sh2'], one, v2, rws, Cout, st)      # slope 1 = identity
+            ops.axpy(rc['skip'], v2)
+            p2 = ops.empty(rws, Cout)
+            ident_s, ident_b = torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev)
+            L_.call('dprnn_affine_prelu', v2, ident_s, ident_b, rb.prelu2.weight.detach(), p2, rws, Cout, st)
+            dp2 = ops.empty(rws, Cout)
+            L_.call('dprnn_pool3_bwd', dout, p2, dp2, B, Lx, Cout, st)
+            dv2 = ops.prelu_bwd(dp2, v2, rb.prelu2.weight.detach(), G[pre_n + '.prelu2.weight'])
+            del p2, dp2, v2
 
-        def bn_bwd(dv, y, scale, shift, bnm, name):
-            gmm = bnm.weight.detach()
-            rstd = (scale / gmm).contiguous()
-            mean = ((bnm.bias.detach() - shift) / scale).contiguous()
-            s_d, s_dy = ops.empty(Cout), ops.empty(Cout)
-            ops.colsum(dv, rws, Cout, s_d, accumulate=False)
-            ops.colsum(dv, rws, Cout, s_dy, Y=y, accumulate=False)
-            s_dyh = (rstd * (s_dy - mean * s_d)).contiguous()        # sum dv * yhat
-            G[name + '.weight'] += s_dyh
-            G[name + '.bias'] += s_d
-            dy = ops.empty(rws, Cout)
-            L_.call('dprnn_bn_bwd_apply', dv, y, mean, rstd, gmm, (s_d / rws).contiguous(), (s_dyh / rws).contiguous(), dy,
-                    rws, Cout, st)
-            return dy
+            def bn_bwd(dv, y, scale, shift, bnm, name):
+                gmm = bnm.weight.detach()
+                rstd = (scale / gmm).contiguous()
+                mean = ((bnm.bias.detach() - shift) / scale).contiguous()
+                s_d, s_dy = ops.empty(Cout), ops.empty(Cout)
+                ops.colsum(dv, rws, Cout, s_d, accumulate=False)
+                ops.colsum(dv, rws, Cout, s_dy, Y=y, accumulate=False)
+                s_dyh = (rstd * (s_dy - mean * s_d)).contiguous()        # sum dv * yhat
+                G[name + '.weight'] += s_dyh
+                G[name + '.bias'] += s_d
+                dy = ops.empty(rws, Cout)
+                L_.call('dprnn_bn_bwd_apply', dv, y, mean, rstd, gmm, (s_d / rws).contiguous(), (s_dyh / rws).contiguous(), dy,
+                        rws, Cout, st)
+                return dy
 
-        dy2 = bn_bwd(dv2, rc['y2'], rc['sc2'], rc['sh2'], rb.batch_norm2, pre_n + '.batch_norm2')
-        ops.atb(dy2, rc['a1'], rws, Cout, Cout, G[pre_n + '.conv2.weight'])
-        da1 = ops.gemm(dy2, rb.conv2.weight.detach().reshape(Cout, Cout).contiguous(), rws, Cout, Cout)
-        v1 = ops.empty(rws, Cout)
-        L_.call('dprnn_affine_prelu', rc['y1'], rc['sc1'], rc['sh1'], one, v1, rws, Cout, st)
-        dv1 = ops.prelu_bwd(da1, v1, rb.prelu1.weight.detach(), G[pre_n + '.prelu1.weight'])
-        dy1 = bn_bwd(dv1, rc['y1'], rc['sc1'], rc['sh1'], rb.batch_norm1, pre_n + '.batch_norm1')
-        ops.atb(dy1, x, rws, Cout, Cin, G[pre_n + '.conv1.weight'])
-        dxr = ops.gemm(dy1, rb.conv1.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
-        if hasattr(rb, 'conv_downsample'):
-            ops.atb(dv2, x, rws, Cout, Cin, G[pre_n + '.conv_downsample.weight'])
-            t = ops.gemm(dv2, rb.conv_downsample.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
-            ops.axpy(t, dxr)
-        else:
-            ops.axpy(dv2, dxr)
-        dout = dxr
-        del dy1, dy2, da1, dv1, dv2, v1
-    O = se[1].weight.shape[0]
-    ops.atb(dout, ctx['gnf'], B * Lr, O, N, G['separation.spk_encoder.1.weight'])
-    ops.colsum(dout, B * Lr, O, G['separation.spk_encoder.1.bias'])
-    dgnf = ops.gemm(dout, se[1].weight.detach().reshape(O, N).contiguous(), B * Lr, N, O)
-    dfeats = ops.gn_bwd(dgnf, feats, ctx['mr_s'], se[0].weight.detach(), B, Lr, N, G['separation.spk_encoder.0.weight'],
-                        G['separation.spk_encoder.0.bias'])
-    del dgnf, dout
+            dy2 = bn_bwd(dv2, rc['y2'], rc['sc2'], rc['sh2'], rb.batch_norm2, pre_n + '.batch_norm2')
+            ops.atb(dy2, rc['a1'], rws, Cout, Cout, G[pre_n + '.conv2.weight'])
+            da1 = ops.gemm(dy2, rb.conv2.weight.detach().reshape(Cout, Cout).contiguous(), rws, Cout, Cout)
+            v1 = ops.empty(rws, Cout)
+            L_.call('dprnn_affine_prelu', rc['y1'], rc['sc1'], rc['sh1'], one, v1, rws, Cout, st)
+            dv1 = ops.prelu_bwd(da1, v1, rb.prelu1.weight.detach(), G[pre_n + '.prelu1.weight'])
+            dy1 = bn_bwd(dv1, rc['y1'], rc['sc1'], rc['sh1'], rb.batch_norm1, pre_n + '.batch_norm1')
+            ops.atb(dy1, x, rws, Cout, Cin, G[pre_n + '.conv1.weight'])
+            dxr = ops.gemm(dy1, rb.conv1.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
+            if hasattr(rb, 'conv_downsample'):
+                ops.atb(dv2, x, rws, Cout, Cin, G[pre_n + '.conv_downsample.weight'])
+                t = ops.gemm(dv2, rb.conv_downsample.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
+                ops.axpy(t, dxr)
+            else:
+                ops.axpy(dv2, dxr)
+            dout = dxr
+            del dy1, dy2, da1, dv1, dv2, v1
+        O = se[1].weight.shape[0]
+        ops.atb(dout, ctx['gnf'], B * Lr, O, N, G['separation.spk_encoder.1.weight'])
+        ops.colsum(dout, B * Lr, O, G['separation.spk_encoder.1.bias'])
+        dgnf = ops.gemm(dout, se[1].weight.detach().reshape(O, N).contiguous(), B * Lr, N, O)
+        dfeats = ops.gn_bwd(dgnf, feats, ctx['mr_s'], se[0].weight.detach(), B, Lr, N, G['separation.spk_encoder.0.weight'],
+                            G['separation.spk_encoder.0.bias'])
+        del dgnf, dout
 
     # ---- encoder (shared by the mixture and the reference)
     genc = G['encoder.conv1d.weight']
-    for d_, e_, sig in ((denc, enc, ctx['mix']), (dfeats, feats, ctx['ref'])):
+    for d_, e_, sig in (((denc, enc, ctx['mix']), (dfeats, feats, ctx['ref'])) if is_spe else ((denc, enc, ctx['mix']),)):
         dpe = torch.empty_like(d_)
         L_.call('dprnn_act_bwd', d_, e_, dpe, d_.numel(), 1, st)
         L_.call('dprnn_convw2_grad', dpe, sig, B, e_.shape[1], N, genc, 1, wsw, st)
     return G
+
+
+class TasNetTrainFunction(torch.autograd.Function):
+    """The whole DPRNN-TasNet forward / backward as one autograd node over the model's trainable parameters."""
+
+    @staticmethod
+    def forward(fctx, model, mix, *params):
+        est, _, ctx = forward_train(model, mix)
+        fctx.model, fctx.saved = model, ctx
+        fctx.names = [n for n, p in model.named_parameters() if p.requires_grad]
+        return est
+
+    @staticmethod
+    def backward(fctx, d_est):
+        G = backward_train(fctx.model, fctx.saved, d_est, None)
+        fctx.saved = None
+        return (None, None) + tuple(G[n] for n in fctx.names)
 
 
 class SpeTrainFunction(torch.autograd.Function):
@@ -523,13 +604,16 @@ class SpeTrainFunction(torch.autograd.Function):
         return (None, None, None, None) + tuple(G[n] for n in fctx.names)
 
 
-def forward_with_grad(model, mix, ref, div):
+def forward_with_grad(model, mix, ref=None, div=None):
     params = [p for _, p in model.named_parameters() if p.requires_grad]
+    if model.cfg['kind'] == 'bss':
+        return TasNetTrainFunction.apply(model, mix, *params)
     return SpeTrainFunction.apply(model, mix, ref, div, *params)
 
 
 class SpeTrainStep:
-    """One iteration of TrainerSpe.train (src/trainers/trainer_spe.py:27-56) as device work only:
+    """One iteration of TrainerSpe.train (src/trainers/trainer_spe.py:27-56) - or, for DPRNNTasNet, of Trainer.train
+    (src/trainers/trainer.py:100-118: PIT neg-SI-SDR, no speaker loss) - as device work only:
     zero_grad -> forward -> loss = mean neg-SI-SDR + ce_gamma * CE -> backward -> [all-reduce (mean) of the flat gradient
     buffer over the data-parallel group] -> clip_grad_norm_(max_norm) -> Adam(lr, weight_decay).
 
@@ -551,14 +635,26 @@ class SpeTrainStep:
         dev = self.fp.flat.device
         self.loss3 = torch.zeros(3, device=dev)
 
-    def loss_and_grads(self, mix, ref, target, spk_idx, ref_len=None):
+    def loss_and_grads(self, mix, ref=None, target=None, spk_idx=None, ref_len=None):
         """forward + loss + backward into the flat gradient buffer (no exchange, no update).  -> loss3 (device tensor:
-        total, SI-SDR part, CE part)."""
+        total, SI-SDR part, CE part).  DPRNNSpeTasNet: (mix, ref, target [B,T], spk_idx [B]); DPRNNTasNet: (mix,
+        target=targets [B,2,T]) with the two-source PIT assignment of Trainer (src/trainers/trainer.py:39,108-112)."""
         model = self.model
-        mix, ref, target = mix.contiguous().float(), ref.contiguous().float(), target.contiguous().float()
+        mix, target = mix.contiguous().float(), target.contiguous().float()
         B, T = mix.shape
-        div = model._engine._aux_div(ref.shape[1] if ref_len is None else ref_len, B, mix.device)
         self.fp.zero_grad()
+        if model.cfg['kind'] == 'bss':
+            est, _, ctx = forward_train(model, mix)
+            tperm = torch.empty_like(target)
+            self.perm = torch.empty(B, device=mix.device, dtype=torch.int32)
+            lib().call('dprnn_pit2_assign', est, target, B, T, tperm, self.perm, None, _st())
+            d_est = torch.empty_like(est)
+            terms = torch.empty(2 * B, 2, device=mix.device)
+            lib().call('dprnn_train_loss', est, tperm, T, None, 0, None, 0.0, 2 * B, terms, self.loss3, d_est, None, _st())
+            backward_train(model, ctx, d_est, None, G=self.G)
+            return self.loss3
+        ref = ref.contiguous().float()
+        div = model._engine._aux_div(ref.shape[1] if ref_len is None else ref_len, B, mix.device)
         est, logits, ctx = forward_train(model, mix, ref, div)
         C = logits.shape[1]
         d_est, d_logits = torch.empty_like(est), torch.empty_like(logits)
@@ -568,7 +664,7 @@ class SpeTrainStep:
         backward_train(model, ctx, d_est, d_logits, G=self.G)
         return self.loss3
 
-    def step(self, mix, ref, target, spk_idx, ref_len=None):
+    def step(self, mix, ref=None, target=None, spk_idx=None, ref_len=None):
         from .dp import allreduce_mean
         loss3 = self.loss_and_grads(mix, ref, target, spk_idx, ref_len)
         allreduce_mean(self.fp.grad, self.group)
@@ -596,3 +692,6 @@ class SpeTrainStep:
                 v.copy_(cpt['model'][k])
         self.opt.load_state_dict(cpt['optimizer'])
         return cpt['epoch']
+
+
+TrainStep = SpeTrainStep        # the same stepper drives both trainers (the model kind selects the loss)
