@@ -110,27 +110,31 @@ class Engine(RaggedMixin):
             W['spk_conv5_t'] = _t(se[5].weight)
         return W
 
+    _lstm_perm_cache = {}
+
     @staticmethod
     def _pack_lstm_tc(rnn, sfx):
         """Weight layout of dprnn_lstm_layer_bf16 (include/dprnn_b200.h): for direction d, CTA rank r and MMA
         instruction nh, the 128 rows {[W_ih | W_hh][q*H + 64*nh + j] : q in (2r, 2r+1), j < 64}; bias likewise."""
         H = rnn.hidden_size
+        dev = rnn.weight_ih_l0.device
+        key = (H, str(dev))
+        cache = Engine._lstm_perm_cache
+        if key not in cache:        # row permutations and the 1/2 pre-scale are fixed: built once per device
+            j = torch.arange(64)
+            wrows = torch.cat([torch.cat([q * H + 64 * nh + j for q in (2 * r, 2 * r + 1)]) for r in range(2) for nh in range(2)])
+            brows = torch.cat([q * H + 64 * nh + j for nh in range(2) for q in range(4)])
+            half = torch.ones(4 * H)
+            half[:2 * H] = 0.5      # i, f, o rows pre-scaled by 1/2 (exact): the kernel evaluates sigmoid(x) as
+            half[3 * H:] = 0.5      # 1/2 tanh(x/2) + 1/2
+            cache[key] = (wrows.to(dev), brows.to(dev), half.to(dev))
+        wrows, brows, half = cache[key]
         ws, bs = [], []
-        j = torch.arange(64)
         for sf in sfx:
             wcat = torch.cat([getattr(rnn, 'weight_ih_l0' + sf).detach(), getattr(rnn, 'weight_hh_l0' + sf).detach()], 1)
             b = (getattr(rnn, 'bias_ih_l0' + sf) + getattr(rnn, 'bias_hh_l0' + sf)).detach()
-            # i, f, o rows pre-scaled by 1/2 (exact): the kernel evaluates sigmoid(x) as 1/2 tanh(x/2) + 1/2
-            half = torch.ones(4 * H, device=wcat.device)
-            half[:2 * H] = 0.5
-            half[3 * H:] = 0.5
-            wcat = wcat * half[:, None]
-            b = b * half
-            for r in range(2):
-                for nh in range(2):
-                    rows = torch.cat([q * H + 64 * nh + j for q in (2 * r, 2 * r + 1)]).to(wcat.device)
-                    ws.append(wcat[rows])
-            bs.append(torch.cat([b[q * H + 64 * nh + j.to(b.device)] for nh in range(2) for q in range(4)]))
+            ws.append((wcat * half[:, None])[wrows])
+            bs.append((b * half)[brows])
         return torch.cat(ws, 0).to(torch.bfloat16).contiguous(), torch.stack(bs, 0).float().contiguous()
 
     # ------------------------------------------------------------------ helpers

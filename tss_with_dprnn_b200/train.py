@@ -407,8 +407,10 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
             dgd = dgates.data_ptr() + 4 * d * 4 * H
             ops.atb(dgd, xs, rows, 4 * H, F, G[f'{rn}.weight_ih_l0{sf}'], lda=nd * 4 * H)
             ops.atb(dgd, hprev.data_ptr() + 4 * d * H, rows, 4 * H, H, G[f'{rn}.weight_hh_l0{sf}'], lda=nd * 4 * H, ldb=nd * H)
-            ops.colsum(dgd, rows, 4 * H, G[f'{rn}.bias_ih_l0{sf}'], ldx=nd * 4 * H)
-            ops.colsum(dgd, rows, 4 * H, G[f'{rn}.bias_hh_l0{sf}'], ldx=nd * 4 * H)
+            db = ops.empty(4 * H)                                    # b_ih and b_hh enter as a sum: one reduction, two adds
+            ops.colsum(dgd, rows, 4 * H, db, ldx=nd * 4 * H, accumulate=False)
+            ops.axpy(db, G[f'{rn}.bias_ih_l0{sf}'])
+            ops.axpy(db, G[f'{rn}.bias_hh_l0{sf}'])
         dxl = ops.mm(dgates, hv['wih'].t().contiguous(), rows, F, nd * 4 * H)
         ops.axpy(dxl, dx)                                            # dx (gradient of x_in) = dx_out + LSTM-branch gradient
         del dgates, hprev, dxl
