@@ -379,6 +379,12 @@ int dprnn_lstm_layer_bf16_train(const void* x, const void* w_packed, const float
 int dprnn_lstm_bptt_f32(const float* dh_out, const float* gates, const float* cstate, const float* whh, float* dgates,
                         long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride, long step_stride,
                         int hidden, int ndir, void* stream);
+/* dprnn_lstm_bptt_f32 with the recurrent contraction d h_{t-1} = d gates_t @ W_hh on the tensor cores (tcgen05, CTA pair,
+ * bf16 operands, fp32 accumulation in TMEM; everything element-wise and the d gates output stay fp32).
+ * whhT_bf16: [ndir][H][4H] bf16 = W_hh^T per direction.  fast_act: tanh.approx for tanh(c_t), as the forward kernel. */
+int dprnn_lstm_bptt_tc(const float* dh_out, const float* gates, const float* cstate, const void* whhT_bf16, float* dgates,
+                       long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride, long step_stride,
+                       int hidden, int ndir, int fast_act, void* stream);
 /* h_prev for the W_hh gradient: out[row(n,t)] = h[row(n, previous step of the direction)], 0 at the first step. */
 int dprnn_shift_rows(const float* h, float* out, long nseq, int T, long seq_div, long seq_outer_stride,
                      long seq_inner_stride, long step_stride, int hidden, int ndir, void* stream);

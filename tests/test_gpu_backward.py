@@ -82,11 +82,13 @@ def test_groupnorm_bwd():
 
 @pytest.mark.parametrize('inter', [0, 1])
 @pytest.mark.parametrize('ndir', [2, 1])
-def test_lstm_train_forward_and_bptt(inter, ndir):
+def test_lstm_train_forward_and_bptt(inter, ndir, big=False):
     """dprnn_lstm_recurrence_f32_train + dprnn_lstm_bptt_f32 against autograd through nn.LSTM (fp64)."""
     L = P.lib()
     H = 128
-    B, S, K = (2, 5, 11) if not inter else (2, 7, 9)
+    B, S, K = (2, 5, 11) if not inter else (2, 7, 9)          # 10 / 18 sequences: one padded 256-sequence tile
+    if big:
+        B, S, K = 3, 50, 100                                  # 150 / 300 sequences: both CTAs of a pair, two pair-jobs
     torch.manual_seed(7 + inter)
     rnn = torch.nn.LSTM(H, H, batch_first=True, bidirectional=(ndir == 2)).double()
     x = rnd(B, S, K, H, seed=8).double().requires_grad_(True)
@@ -111,6 +113,15 @@ def test_lstm_train_forward_and_bptt(inter, ndir):
            *geo, H, ndir, st())
     torch.cuda.synchronize()
     dgc = dg.cpu().double()
+    # the tensor-core BPTT (bf16 recurrent contraction) from the same saved activations: within bf16 tolerance of the exact
+    # kernel; rows past the real ones are never written
+    dg2 = torch.full((rows + 1, ndir * 4 * H), 7.0, device=DEV)
+    whhT = whh.transpose(1, 2).contiguous().to(torch.bfloat16).to(DEV)
+    for fast in (0, 1):
+        L.call('dprnn_lstm_bptt_tc', dout.float().reshape(rows, -1).contiguous().to(DEV), gates, cst, whhT, dg2, *geo, H,
+               ndir, fast, st())
+        assert float((dg2[:rows] - dg).abs().max()) < 2e-2 * float(dg.abs().max())
+        assert float((dg2[rows:] - 7.0).abs().max()) == 0.0
     # dx = dgates @ W_ih ; dW_ih = dgates^T x ; db = colsum(dgates)
     dx = dgc @ wih.double()
     assert rel(dx, x.grad.reshape(rows, H)) < 1e-4
@@ -119,6 +130,11 @@ def test_lstm_train_forward_and_bptt(inter, ndir):
     assert rel(dwih, want_wih) < 1e-4
     want_b = torch.cat([getattr(rnn, 'bias_ih_l0' + s).grad for s in sfx], 0)
     assert rel(dgc.sum(0), want_b) < 1e-4
+
+
+@pytest.mark.parametrize('inter', [0, 1])
+def test_lstm_bptt_many_sequences(inter):
+    test_lstm_train_forward_and_bptt(inter, 2, big=True)
 
 
 @pytest.mark.parametrize('inter', [0, 1])

@@ -1,0 +1,277 @@
+// BPTT of one LSTM layer with the recurrent contraction on 5th-gen tensor cores (training step, tensor-core mode):
+//     d h_{t-1}[256 seq, 128] = d gates_t[256 seq, 512] (bf16) @ W_hh[512, 128] (bf16)      (fp32 accumulators in TMEM)
+// Same inputs / outputs as the exact fp32 kernel (lstm_bwd_kernel, lstm_simt.cu): d h_out, the saved gate activations and
+// cell states in, the gradient of the gate pre-activations (fp32, row-major) out.
+//
+// A CTA PAIR (cluster of 2, tcgen05 cta_group::2, M = 256) owns 256 sequences of one direction for all T steps; each CTA
+// holds its 128 sequences' d gates tile (A operand, 8 K-blocks of [128 x 64] bf16, 128 KiB, rewritten every step) and
+// half of W_hh^T (B operand, 64 of the 128 output columns x K = 512, 64 KiB, resident).
+//
+// The element-wise part keeps the COALESCED thread mapping of the SIMT kernel (half-warp = one sequence row, lane = 4
+// consecutive hidden units), because the step streams 5.5 KB per row through it (4 gates, c_t, c_{t-1}, d h_out in,
+// 4 d gates out) and a thread-per-row mapping would touch 32 cache lines per load instruction.  TMEM, however, is read
+// thread-per-row (tcgen05.ld 32x32b), so the recurrent d h goes TMEM -> registers -> padded shared-memory staging
+// ([128 rows x 64 units] fp32, one unit-half at a time) -> the coalesced mapping.  Per step:
+//     wait D[prev] | for unit-half p in {0,1}: stage D[prev][:, 64p..64p+63]; cell backward for those units (all 128 rows):
+//     d gates -> global (fp32) and -> the A tile (bf16, 128B-swizzled K-major); publish -> the MMA warp issues the K-blocks of
+//     that unit-half (the MMAs of half 0 overlap the element-wise work of half 1) | commit -> D[cur]   (TMEM ping-pong)
+// K index = gate*128 + unit, i.e. K-block kb = 2*gate + unit_half: W_hh^T needs no permutation.
+#include "tc_common.cuh"
+#include "../../include/dprnn_b200.h"
+
+namespace dprnn {
+using namespace tc;
+
+namespace bptt {
+constexpr int H = 128, G4 = 512;
+constexpr uint32_t A_TILE = 128 * 128;        // [128 rows x 128 B]
+constexpr uint32_t W_TILE = 64 * 128;         // [64 rows x 128 B]
+constexpr int STG_LD = 68;                    // floats per staging row (64 + 4: conflict-free float4 rows)
+constexpr uint32_t SM_W = 0, SM_A = 8 * W_TILE, SM_STG = SM_A + 8 * A_TILE, SM_BAR = SM_STG + 128 * STG_LD * 4,
+                   SM_TOTAL = SM_BAR + 128;
+static_assert(SM_TOTAL <= 232448, "shared memory budget of one SM (227 KiB)");
+}  // namespace bptt
+
+struct LstmBpttTcParams {
+    const float* dh_out;   // [rows, ndir*H]
+    const float* gates;    // [rows, ndir*4H] activations i,f,g,o
+    const float* cstate;   // [rows, ndir*H]
+    float* dgates;         // [rows, ndir*4H]
+    long nseq; int T;
+    int seq_div; long seq_outer, seq_inner, step_stride;
+    int ndir;
+};
+
+__device__ __forceinline__ float bptt_tanh(float x, bool fast) {
+    if (fast) {
+        float y;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+        return y;
+    }
+    return tanhf(x);
+}
+__device__ __forceinline__ uint32_t bptt_cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void bptt_cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t bptt_map_to_cta(uint32_t addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void bptt_arrive_remote(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void bptt_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+
+template <bool kFastAct>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcParams p) {
+    using namespace bptt;
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    uint64_t* w_full = bars;
+    uint64_t* d_full = bars + 1;              // MMAs of the step complete (multicast commit, both CTAs)
+    uint64_t* a_ready = bars + 2;             // [2] (leader's copy) A K-blocks of unit-half p written by both CTAs
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    float* stg = reinterpret_cast<float*>(smem + SM_STG);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = bptt_cluster_ctarank();
+    const int job = blockIdx.x >> 1;
+    const int dir = job % p.ndir;
+    const long n0 = (long)(job / p.ndir) * 256 + (long)rank * 128;
+    const int T = p.T;
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) {
+            printf("lstm_bptt_tc_kernel: dynamic shared memory base %u is not 1024-byte aligned\n", smem_u32(smem));
+            __trap();
+        }
+        prefetch_tmap(&tmW);
+        mbar_init(w_full, 1);
+        mbar_init(d_full, 1);
+        mbar_init(&a_ready[0], 16); mbar_init(&a_ready[1], 16);     // one elected lane per epilogue warp, both CTAs
+        fence_barrier_init();
+    }
+    if (warp == 2) tmem_alloc<2>(tmem_slot, 256);
+    tc_fence_before();
+    bptt_cluster_sync();
+    tc_fence_after();
+
+    if (warp == 0 && elect_one()) {           // this CTA's 64 output columns of W_hh^T, all 8 K-blocks
+        mbar_expect_tx(w_full, 8 * W_TILE);
+        for (int kb = 0; kb < 8; ++kb)
+            tma_load_2d(smem + SM_W + kb * W_TILE, &tmW, w_full, kb * 64, dir * 128 + (int)rank * 64);
+    }
+    mbar_wait(w_full, 0);
+    bptt_cluster_sync();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 1) {
+        // ================= MMA issuer (leader CTA only) =================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(256, 128);
+            const uint32_t aW = smem_u32(smem + SM_W), aA = smem_u32(smem + SM_A);
+            for (int s = 0; s + 1 < T; ++s) {
+                const uint32_t d = tmem + (uint32_t)(s & 1) * 128;
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait_cluster(&a_ready[half], s & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int kb = q4 * 2 + half;
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            umma_bf16<2>(d, umma_desc_sw128(aA + kb * A_TILE + kk * 32),
+                                         umma_desc_sw128(aW + kb * W_TILE + kk * 32), idesc,
+                                         (half | q4 | kk) ? 1u : 0u);
+                    }
+                }
+                umma_commit_2cta(d_full, 3);
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ================= element-wise backward of the cell =================
+        const int e = warp - 4, q = e & 3, ch = e >> 2;      // TMEM staging role: lane quadrant q, 32-column half ch
+        const int hw = lane >> 4, l16 = lane & 15;           // coalesced role: half-warp = row, 4 units per lane
+        const int ldg = p.ndir * G4, ldh = p.ndir * H;
+        const uint32_t leader_ready = bptt_map_to_cta(smem_u32(&a_ready[0]), 0);
+        int base[8];
+        bool ok[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const long n = n0 + e * 16 + it * 2 + hw;
+            ok[it] = n < p.nseq;
+            base[it] = ok[it] ? (int)((n / p.seq_div) * p.seq_outer + (n % p.seq_div) * p.seq_inner) : 0;
+        }
+        float dc[2][8][4];
+#pragma unroll
+        for (int a = 0; a < 2; ++a)
+#pragma unroll
+            for (int b = 0; b < 8; ++b)
+#pragma unroll
+                for (int c = 0; c < 4; ++c) dc[a][b][c] = 0.f;
+
+        for (int s = 0; s < T; ++s) {
+            const int fstep = T - 1 - s;                      // forward step being differentiated
+            const int t = dir ? T - 1 - fstep : fstep;
+            const int tprev = dir ? t + 1 : t - 1;
+            if (s > 0) {
+                mbar_wait(d_full, (s - 1) & 1);
+                tc_fence_after();
+            }
+#pragma unroll
+            for (int ph = 0; ph < 2; ++ph) {
+                if (s > 0) {                                  // recurrent d h of units 64ph..64ph+63: TMEM -> staging
+                    float v[32];
+                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((s - 1) & 1) * 128 + ph * 64 + ch * 32, v);
+                    float* dst = stg + (q * 32 + lane) * STG_LD + ch * 32;
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    tc_fence_before();
+                }
+                bptt_named_bar(1, 256);
+                const int u0 = ph * 64 + l16 * 4;
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const int row = e * 16 + it * 2 + hw;
+                    const long rowi = (long)base[it] + (long)t * p.step_stride;
+                    float4 gi = make_float4(0.f, 0.f, 0.f, 0.f), gf = gi, gg = gi, go = gi, cv = gi, cp = gi, dho = gi, dhr = gi;
+                    if (ok[it]) {
+                        const float* g = p.gates + rowi * ldg + dir * G4 + u0;
+                        gi = ld_stream(reinterpret_cast<const float4*>(g));
+                        gf = ld_stream(reinterpret_cast<const float4*>(g + H));
+                        gg = ld_stream(reinterpret_cast<const float4*>(g + 2 * H));
+                        go = ld_stream(reinterpret_cast<const float4*>(g + 3 * H));
+                        cv = *reinterpret_cast<const float4*>(p.cstate + rowi * ldh + dir * H + u0);
+                        if (fstep > 0)
+                            cp = *reinterpret_cast<const float4*>(p.cstate + ((long)base[it] + (long)tprev * p.step_stride) * ldh + dir * H + u0);
+                        dho = ld_stream(reinterpret_cast<const float4*>(p.dh_out + rowi * ldh + dir * H + u0));
+                    }
+                    if (s > 0) dhr = *reinterpret_cast<const float4*>(stg + row * STG_LD + l16 * 4);
+                    const float ia[4] = {gi.x, gi.y, gi.z, gi.w}, fa[4] = {gf.x, gf.y, gf.z, gf.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w},
+                                oa[4] = {go.x, go.y, go.z, go.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w}, pa[4] = {cp.x, cp.y, cp.z, cp.w},
+                                da[4] = {dho.x + dhr.x, dho.y + dhr.y, dho.z + dhr.z, dho.w + dhr.w};
+                    float dpi[4], dpf[4], dpg[4], dpo[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float dh = da[u];
+                        const float tcv = bptt_tanh(ca[u], kFastAct);
+                        const float dct = dc[ph][it][u] + dh * oa[u] * (1.f - tcv * tcv);
+                        dpo[u] = dh * tcv * oa[u] * (1.f - oa[u]);
+                        dpi[u] = dct * ga[u] * ia[u] * (1.f - ia[u]);
+                        dpf[u] = dct * pa[u] * fa[u] * (1.f - fa[u]);
+                        dpg[u] = dct * ia[u] * (1.f - ga[u] * ga[u]);
+                        dc[ph][it][u] = dct * fa[u];
+                    }
+                    if (ok[it]) {
+                        float* o = p.dgates + rowi * ldg + dir * G4 + u0;
+                        *reinterpret_cast<float4*>(o) = make_float4(dpi[0], dpi[1], dpi[2], dpi[3]);
+                        *reinterpret_cast<float4*>(o + H) = make_float4(dpf[0], dpf[1], dpf[2], dpf[3]);
+                        *reinterpret_cast<float4*>(o + 2 * H) = make_float4(dpg[0], dpg[1], dpg[2], dpg[3]);
+                        *reinterpret_cast<float4*>(o + 3 * H) = make_float4(dpo[0], dpo[1], dpo[2], dpo[3]);
+                    }
+                    if (fstep > 0) {
+                        // A operand: K-block kb = 2*gate + ph, column (unit % 64) -> 16-byte chunk l16/2, byte (l16&1)*8
+                        const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)(l16 >> 1)) + (uint32_t)(l16 & 1) * 8;
+                        uint8_t* at = smem + SM_A + ph * A_TILE + off;
+                        auto pack = [](float a, float b) {
+                            __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+                            return *reinterpret_cast<uint32_t*>(&v);
+                        };
+                        *reinterpret_cast<uint2*>(at + 0 * 2 * A_TILE) = make_uint2(pack(dpi[0], dpi[1]), pack(dpi[2], dpi[3]));
+                        *reinterpret_cast<uint2*>(at + 1 * 2 * A_TILE) = make_uint2(pack(dpf[0], dpf[1]), pack(dpf[2], dpf[3]));
+                        *reinterpret_cast<uint2*>(at + 2 * 2 * A_TILE) = make_uint2(pack(dpg[0], dpg[1]), pack(dpg[2], dpg[3]));
+                        *reinterpret_cast<uint2*>(at + 3 * 2 * A_TILE) = make_uint2(pack(dpo[0], dpo[1]), pack(dpo[2], dpo[3]));
+                    }
+                }
+                if (fstep > 0) {
+                    fence_async_smem();                       // generic-proxy writes of the A tile -> visible to tcgen05.mma
+                    __syncwarp();
+                    if (lane == 0) bptt_arrive_remote(leader_ready + ph * 8);
+                }
+                bptt_named_bar(2, 256);                       // staging may be overwritten
+            }
+        }
+    }
+    __syncwarp();
+    tc_fence_before();
+    bptt_cluster_sync();
+    if (warp == 2) tmem_dealloc<2>(tmem, 256);
+}
+
+}  // namespace dprnn
+
+using namespace dprnn;
+
+// whhT_bf16: [ndir][H = 128 output columns j][4H = 512 gate rows k] bf16 = W_hh^T per direction (k = gate*128 + unit)
+extern "C" int dprnn_lstm_bptt_tc(const float* dh_out, const float* gates, const float* cstate, const void* whhT_bf16,
+                                  float* dgates, long nseq, int T, long seq_div, long seq_outer_stride,
+                                  long seq_inner_stride, long step_stride, int hidden, int ndir, int fast_act,
+                                  void* stream) {
+    DPRNN_CHECK_ARG(dh_out && gates && cstate && whhT_bf16 && dgates && nseq > 0 && T > 0 && seq_div > 0);
+    DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2) && seq_div < (1L << 31));
+    DPRNN_CHECK_ARG(((uintptr_t)dh_out | (uintptr_t)gates | (uintptr_t)cstate | (uintptr_t)whhT_bf16 | (uintptr_t)dgates) % 16 == 0);
+    // row indices are kept as int32 inside the kernel
+    const long max_row = ((nseq - 1) / seq_div) * seq_outer_stride + ((nseq - 1) % seq_div) * seq_inner_stride +
+                         (long)(T - 1) * step_stride;
+    DPRNN_CHECK_ARG(max_row < (1L << 31));
+    CUtensorMap tmW;
+    const uint64_t dW[2] = {512, (uint64_t)ndir * 128}, sW[2] = {2, 1024};
+    const uint32_t bW[2] = {64, 64};
+    if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, whhT_bf16, dW, sW, bW)) return 1;
+    LstmBpttTcParams p{dh_out, gates, cstate, dgates, nseq, T, (int)seq_div, seq_outer_stride, seq_inner_stride, step_stride, ndir};
+    const long njobs = (nseq + 255) / 256 * ndir;
+    DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
+    auto kern = fast_act ? lstm_bptt_tc_kernel<true> : lstm_bptt_tc_kernel<false>;
+    DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bptt::SM_TOTAL));
+    kern<<<(unsigned)(njobs * 2), 384, bptt::SM_TOTAL, (cudaStream_t)stream>>>(tmW, p);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}

@@ -398,7 +398,12 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
         dh = ops.mm(dy, hv['lin'].weight.detach().t().contiguous(), rows, nd * H, F)
         del dy
         dgates = ops.empty(rows, nd * 4 * H)
-        L_.call('dprnn_lstm_bptt_f32', dh, hv['gates'], hv['cst'], hv['whh'], dgates, *geo, H, nd, st)
+        if ops.tf32:
+            whhT = hv['whh'].transpose(1, 2).contiguous().to(torch.bfloat16)              # [nd, H, 4H]
+            L_.call('dprnn_lstm_bptt_tc', dh, hv['gates'], hv['cst'], whhT, dgates, *geo, H, nd,
+                    int(model._engine.fast_act), st)
+        else:
+            L_.call('dprnn_lstm_bptt_f32', dh, hv['gates'], hv['cst'], hv['whh'], dgates, *geo, H, nd, st)
         del dh
         hprev = ops.empty(rows, nd * H)
         L_.call('dprnn_shift_rows', hv['hout'], hprev, *geo, H, nd, st)
