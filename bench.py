@@ -561,7 +561,7 @@ def run_ours(args):
     roofline = None
     lstm_names = [n for n in per_kernel if n in (dominant, 'dprnn_lstm_inter_bf16_ragged')]
     if args.workload == 'cfg5':
-        lstm_names = [n for n in per_kernel if n in ('dprnn_lstm_recurrence_f32_train', 'dprnn_lstm_bptt_f32')]
+        lstm_names = [n for n in per_kernel if n in ('dprnn_lstm_recurrence_f32_train', 'dprnn_lstm_bptt_f32', 'dprnn_lstm_layer_bf16_train', 'dprnn_lstm_bptt_tc')]
     if lstm_names:
         ms_lstm = sum(per_kernel[n]['ms_total'] for n in lstm_names)
         n_launch = sum(per_kernel[n]['launches'] for n in lstm_names)
@@ -585,22 +585,24 @@ def run_ours(args):
                              'algorithmic flops = h W_hh^T only (2*128*512 per position and direction); the fp32 mode '
                              'runs this on CUDA cores, so its fraction of the bf16 tensor peak is small by construction')}
 
-    if args.workload == 'cfg5' and 'dprnn_lstm_bptt_f32' in per_kernel:
+    bptt_name = 'dprnn_lstm_bptt_tc' if 'dprnn_lstm_bptt_tc' in per_kernel else 'dprnn_lstm_bptt_f32'
+    if args.workload == 'cfg5' and bptt_name in per_kernel:
         # dominant kernel of the training step: the fp32 BPTT recurrence.  It streams the saved gate activations, two
         # cell states and d h_out and writes d gates: 4H + 2H + H + 4H floats per chunk position and direction.
-        k = per_kernel['dprnn_lstm_bptt_f32']
+        k = per_kernel[bptt_name]
         peak_bw = peaks.get('hbm_gbs', 6400.0)
         bytes_per_launch = wl.positions(0) * 2 * (4 * 128 + 2 * 128 + 128 + 4 * 128) * 4
         achieved = bytes_per_launch / (k['ms_avg'] * 1e-3) / 1e9
-        roofline = {'kernel': 'dprnn_lstm_bptt_f32', 'bound': 'hbm', 'achieved': achieved, 'peak': peak_bw, 'unit': 'GB/s',
+        roofline = {'kernel': bptt_name, 'bound': 'hbm', 'achieved': achieved, 'peak': peak_bw, 'unit': 'GB/s',
                     'frac': achieved / peak_bw, 'traffic': None,
                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6400 (B200_PROFILING.md)',
                     'launch_ms_avg': k['ms_avg'],
                     'share_of_step_single_stream': k['ms_total'] / sum(v['ms_total'] for v in per_kernel.values()),
-                    'note': 'algorithmic bytes = 11 H floats per chunk position and direction (gates, c_t, c_{t-1}, dh in; '
-                            'dgates out); the recurrence d h_{t-1} = d gates_t W_hh runs on CUDA cores (fp32, exact) and is '
-                            'latency-bound at 16 utterances per GPU (97..125 CTAs of 32 sequences), not bandwidth-bound: '
-                            'DESIGN.md section 4.6'}
+                    'note': 'dominant kernel of the training step (BPTT).  Algorithmic bytes = 11 H floats per chunk position '
+                            'and direction (gates, c_t, c_{t-1}, dh in; dgates out).  Tensor-core mode: d h_{t-1} = d gates_t '
+                            'W_hh on tcgen05 (CTA pair); at 16 utterances per GPU only 98..126 of 148 SMs hold a CTA and the '
+                            'element-wise cell backward between the MMAs is issue/latency-bound (ncu: 27 % issue slots, top '
+                            'stall = first use of the streamed loads): DESIGN.md section 5.2'}
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:

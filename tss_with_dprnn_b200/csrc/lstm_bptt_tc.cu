@@ -10,7 +10,7 @@
 // The element-wise part keeps the COALESCED thread mapping of the SIMT kernel (half-warp = one sequence row, lane = 4
 // consecutive hidden units), because the step streams 5.5 KB per row through it (4 gates, c_t, c_{t-1}, d h_out in,
 // 4 d gates out) and a thread-per-row mapping would touch 32 cache lines per load instruction.  TMEM, however, is read
-// thread-per-row (tcgen05.ld 32x32b), so the recurrent d h goes TMEM -> registers -> padded shared-memory staging
+// thread-per-row (tcgen05.ld 32x32b), so the recurrent d h goes TMEM -> registers -> padded, warp-private staging rows
 // ([128 rows x 64 units] fp32, one unit-half at a time) -> the coalesced mapping.  Per step:
 //     wait D[prev] | for unit-half p in {0,1}: stage D[prev][:, 64p..64p+63]; cell backward for those units (all 128 rows):
 //     d gates -> global (fp32) and -> the A tile (bf16, 128B-swizzled K-major); publish -> the MMA warp issues the K-blocks of
@@ -26,6 +26,8 @@ namespace bptt {
 constexpr int H = 128, G4 = 512;
 constexpr uint32_t A_TILE = 128 * 128;        // [128 rows x 128 B]
 constexpr uint32_t W_TILE = 64 * 128;         // [64 rows x 128 B]
+constexpr int NEW = 16;                       // element-wise warps (issue-bound part: more warps hide its latencies)
+constexpr int ITS = 128 / NEW / 2;            // row pairs per warp and unit-half
 constexpr int STG_LD = 68;                    // floats per staging row (64 + 4: conflict-free float4 rows)
 constexpr uint32_t SM_W = 0, SM_A = 8 * W_TILE, SM_STG = SM_A + 8 * A_TILE, SM_BAR = SM_STG + 128 * STG_LD * 4,
                    SM_TOTAL = SM_BAR + 128;
@@ -69,7 +71,7 @@ __device__ __forceinline__ void bptt_arrive_remote(uint32_t cluster_addr) {
 __device__ __forceinline__ void bptt_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 template <bool kFastAct>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * bptt::NEW, 1)
 lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcParams p) {
     using namespace bptt;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -95,7 +97,7 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
         prefetch_tmap(&tmW);
         mbar_init(w_full, 1);
         mbar_init(d_full, 1);
-        mbar_init(&a_ready[0], 16); mbar_init(&a_ready[1], 16);     // one elected lane per epilogue warp, both CTAs
+        mbar_init(&a_ready[0], 2 * NEW); mbar_init(&a_ready[1], 2 * NEW);     // one elected lane per element-wise warp, both CTAs
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<2>(tmem_slot, 256);
@@ -138,30 +140,85 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
         __syncwarp();
     } else if (warp >= 4) {
         // ================= element-wise backward of the cell =================
-        const int e = warp - 4, q = e & 3, ch = e >> 2;      // TMEM staging role: lane quadrant q, 32-column half ch
+        // warp -> TMEM lane quadrant q (= warp % 4, the only lanes it may read) and the wq-th group of 2*ITS rows inside it:
+        // the rows a warp differentiates are rows whose recurrent d h it can fetch itself, so staging is warp-private
+        const int e = warp - 4, q = e & 3, wq = e >> 2;
         const int hw = lane >> 4, l16 = lane & 15;           // coalesced role: half-warp = row, 4 units per lane
         const int ldg = p.ndir * G4, ldh = p.ndir * H;
         const uint32_t leader_ready = bptt_map_to_cta(smem_u32(&a_ready[0]), 0);
-        int base[8];
-        bool ok[8];
+        float* stgw = stg + e * (2 * ITS) * STG_LD;          // this warp's staging rows
+        int base[ITS];
+        bool ok[ITS];
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-            const long n = n0 + e * 16 + it * 2 + hw;
+        for (int it = 0; it < ITS; ++it) {
+            const long n = n0 + q * 32 + wq * (2 * ITS) + it * 2 + hw;
             ok[it] = n < p.nseq;
             base[it] = ok[it] ? (int)((n / p.seq_div) * p.seq_outer + (n % p.seq_div) * p.seq_inner) : 0;
         }
-        float dc[2][8][4];
+        float dc[2][ITS][4];
 #pragma unroll
         for (int a = 0; a < 2; ++a)
 #pragma unroll
-            for (int b = 0; b < 8; ++b)
+            for (int b = 0; b < ITS; ++b)
 #pragma unroll
                 for (int c = 0; c < 4; ++c) dc[a][b][c] = 0.f;
+
+        // The step streams 7 float4 per (row, lane) through registers; with only 8 warps per SM the loads of the NEXT
+        // (row pair | unit-half | step) are issued before the current one is computed (software double buffering).
+        struct Ld { float4 gi, gf, gg, go, cv, cp, dho; };
+        auto issue = [&](int s_, int ph_, bool valid, int base_, Ld& L) {
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            L.gi = z; L.gf = z; L.gg = z; L.go = z; L.cv = z; L.cp = z; L.dho = z;
+            if (s_ < T && valid) {
+                const int fs = T - 1 - s_;
+                const int t_ = dir ? T - 1 - fs : fs;
+                const int tp = dir ? t_ + 1 : t_ - 1;
+                const long rowi = (long)base_ + (long)t_ * p.step_stride;
+                const int u0 = ph_ * 64 + l16 * 4;
+                const float* g = p.gates + rowi * ldg + dir * G4 + u0;
+                L.gi = ld_stream(reinterpret_cast<const float4*>(g));
+                L.gf = ld_stream(reinterpret_cast<const float4*>(g + H));
+                L.gg = ld_stream(reinterpret_cast<const float4*>(g + 2 * H));
+                L.go = ld_stream(reinterpret_cast<const float4*>(g + 3 * H));
+                L.cv = *reinterpret_cast<const float4*>(p.cstate + rowi * ldh + dir * H + u0);
+                if (fs > 0)
+                    L.cp = *reinterpret_cast<const float4*>(p.cstate + ((long)base_ + (long)tp * p.step_stride) * ldh + dir * H + u0);
+                L.dho = ld_stream(reinterpret_cast<const float4*>(p.dh_out + rowi * ldh + dir * H + u0));
+            }
+        };
+        // L2 prefetch of the step after the next one's register prefetch can reach: the addresses of every step are known up
+        // front, so DRAM latency is taken off the recurrence's critical path (two lanes per half-warp cover its two lines)
+        auto prefetch_step = [&](int s_) {
+            if (s_ >= T || (l16 & 7) != 0) return;
+            const int fs = T - 1 - s_;
+            const int t_ = dir ? T - 1 - fs : fs;
+            const int tp = dir ? t_ + 1 : t_ - 1;
+#pragma unroll
+            for (int it = 0; it < ITS; ++it) {
+                if (!ok[it]) continue;
+                const long rowi = (long)base[it] + (long)t_ * p.step_stride;
+#pragma unroll
+                for (int ph_ = 0; ph_ < 2; ++ph_) {
+                    const int u0 = ph_ * 64 + l16 * 4;
+                    const float* g = p.gates + rowi * ldg + dir * G4 + u0;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + H));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 2 * H));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 3 * H));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dh_out + rowi * ldh + dir * H + u0));
+                    if (fs > 0)     // c_{t-1} of that step (it is c_t of the step after it)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cstate + ((long)base[it] + (long)tp * p.step_stride) * ldh + dir * H + u0));
+                }
+            }
+        };
+        Ld cur, nxt;
+        issue(0, 0, ok[0], base[0], cur);
+        prefetch_step(1);
 
         for (int s = 0; s < T; ++s) {
             const int fstep = T - 1 - s;                      // forward step being differentiated
             const int t = dir ? T - 1 - fstep : fstep;
-            const int tprev = dir ? t + 1 : t - 1;
+            prefetch_step(s + 2);
             if (s > 0) {
                 mbar_wait(d_full, (s - 1) & 1);
                 tc_fence_after();
@@ -169,35 +226,37 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
 #pragma unroll
             for (int ph = 0; ph < 2; ++ph) {
                 if (s > 0) {                                  // recurrent d h of units 64ph..64ph+63: TMEM -> staging
-                    float v[32];
-                    tmem_ld32(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((s - 1) & 1) * 128 + ph * 64 + ch * 32, v);
-                    float* dst = stg + (q * 32 + lane) * STG_LD + ch * 32;
+                    __syncwarp();                             // the previous unit-half's reads of the staging rows are done
+                    const bool mine = lane >= wq * (2 * ITS) && lane < (wq + 1) * (2 * ITS);
+                    float* dst = stgw + (lane - wq * (2 * ITS)) * STG_LD;
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(dst + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int cq = 0; cq < 4; ++cq) {
+                        float v[16];
+                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((s - 1) & 1) * 128 + ph * 64 + cq * 16, v);
+                        if (mine) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4)
+                                *reinterpret_cast<float4*>(dst + cq * 16 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        }
+                    }
                     tc_fence_before();
+                    __syncwarp();
                 }
-                bptt_named_bar(1, 256);
                 const int u0 = ph * 64 + l16 * 4;
 #pragma unroll
-                for (int it = 0; it < 8; ++it) {
-                    const int row = e * 16 + it * 2 + hw;
+                for (int it = 0; it < ITS; ++it) {
+                    // next in the order (step, unit-half, row pair)
+                    if (it < ITS - 1) issue(s, ph, ok[it + 1], base[it + 1], nxt);
+                    else if (ph == 0) issue(s, 1, ok[0], base[0], nxt);
+                    else issue(s + 1, 0, ok[0], base[0], nxt);
+                    const int row = q * 32 + wq * (2 * ITS) + it * 2 + hw;
                     const long rowi = (long)base[it] + (long)t * p.step_stride;
-                    float4 gi = make_float4(0.f, 0.f, 0.f, 0.f), gf = gi, gg = gi, go = gi, cv = gi, cp = gi, dho = gi, dhr = gi;
-                    if (ok[it]) {
-                        const float* g = p.gates + rowi * ldg + dir * G4 + u0;
-                        gi = ld_stream(reinterpret_cast<const float4*>(g));
-                        gf = ld_stream(reinterpret_cast<const float4*>(g + H));
-                        gg = ld_stream(reinterpret_cast<const float4*>(g + 2 * H));
-                        go = ld_stream(reinterpret_cast<const float4*>(g + 3 * H));
-                        cv = *reinterpret_cast<const float4*>(p.cstate + rowi * ldh + dir * H + u0);
-                        if (fstep > 0)
-                            cp = *reinterpret_cast<const float4*>(p.cstate + ((long)base[it] + (long)tprev * p.step_stride) * ldh + dir * H + u0);
-                        dho = ld_stream(reinterpret_cast<const float4*>(p.dh_out + rowi * ldh + dir * H + u0));
-                    }
-                    if (s > 0) dhr = *reinterpret_cast<const float4*>(stg + row * STG_LD + l16 * 4);
-                    const float ia[4] = {gi.x, gi.y, gi.z, gi.w}, fa[4] = {gf.x, gf.y, gf.z, gf.w}, ga[4] = {gg.x, gg.y, gg.z, gg.w},
-                                oa[4] = {go.x, go.y, go.z, go.w}, ca[4] = {cv.x, cv.y, cv.z, cv.w}, pa[4] = {cp.x, cp.y, cp.z, cp.w},
-                                da[4] = {dho.x + dhr.x, dho.y + dhr.y, dho.z + dhr.z, dho.w + dhr.w};
+                    float4 dhr = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (s > 0) dhr = *reinterpret_cast<const float4*>(stgw + (it * 2 + hw) * STG_LD + l16 * 4);
+                    const float ia[4] = {cur.gi.x, cur.gi.y, cur.gi.z, cur.gi.w}, fa[4] = {cur.gf.x, cur.gf.y, cur.gf.z, cur.gf.w},
+                                ga[4] = {cur.gg.x, cur.gg.y, cur.gg.z, cur.gg.w}, oa[4] = {cur.go.x, cur.go.y, cur.go.z, cur.go.w},
+                                ca[4] = {cur.cv.x, cur.cv.y, cur.cv.z, cur.cv.w}, pa[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w},
+                                da[4] = {cur.dho.x + dhr.x, cur.dho.y + dhr.y, cur.dho.z + dhr.z, cur.dho.w + dhr.w};
                     float dpi[4], dpf[4], dpg[4], dpo[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -230,13 +289,13 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                         *reinterpret_cast<uint2*>(at + 2 * 2 * A_TILE) = make_uint2(pack(dpg[0], dpg[1]), pack(dpg[2], dpg[3]));
                         *reinterpret_cast<uint2*>(at + 3 * 2 * A_TILE) = make_uint2(pack(dpo[0], dpo[1]), pack(dpo[2], dpo[3]));
                     }
+                    cur = nxt;
                 }
                 if (fstep > 0) {
                     fence_async_smem();                       // generic-proxy writes of the A tile -> visible to tcgen05.mma
                     __syncwarp();
                     if (lane == 0) bptt_arrive_remote(leader_ready + ph * 8);
                 }
-                bptt_named_bar(2, 256);                       // staging may be overwritten
             }
         }
     }
@@ -271,7 +330,7 @@ extern "C" int dprnn_lstm_bptt_tc(const float* dh_out, const float* gates, const
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
     auto kern = fast_act ? lstm_bptt_tc_kernel<true> : lstm_bptt_tc_kernel<false>;
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bptt::SM_TOTAL));
-    kern<<<(unsigned)(njobs * 2), 384, bptt::SM_TOTAL, (cudaStream_t)stream>>>(tmW, p);
+    kern<<<(unsigned)(njobs * 2), 128 + 32 * bptt::NEW, bptt::SM_TOTAL, (cudaStream_t)stream>>>(tmW, p);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }
