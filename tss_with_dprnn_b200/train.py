@@ -103,6 +103,16 @@ class _Ops:
         return out
 
 
+_SIDE = {}
+
+
+def _side_stream(dev):
+    key = torch.device(dev).index if torch.device(dev).index is not None else torch.cuda.current_device()
+    if key not in _SIDE:
+        _SIDE[key] = torch.cuda.Stream(device=key)
+    return _SIDE[key]
+
+
 def _norm_params(mod):
     if hasattr(mod, 'gamma'):
         return mod.gamma, mod.beta, 1e-8
@@ -383,18 +393,43 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
     names = {}
     for n_, mod in model.named_modules():
         names[id(mod)] = n_
+    # The gradient CHAIN (norm adjoint -> d h -> BPTT -> d x) runs on the caller's stream; the weight / bias gradients of each
+    # half-block hang off it and run on a side stream, where they overlap the next half-block's BPTT (which occupies only
+    # the SMs its 256-sequence tiles land on).  xs is rewritten in place at the top of every iteration, so the chain waits
+    # for the side stream's reads of xs (xs_read) before doing that; buffers handed to the side stream are
+    # record_stream()-ed so that the caching allocator does not recycle them early.
+    main = torch.cuda.current_stream()
+    side = _side_stream(dev)
+    side.wait_stream(main)
+    xs_read = None
+
+    def on_side(fn, *tensors):
+        ev = torch.cuda.Event()
+        ev.record(main)
+        side.wait_event(ev)
+        with torch.cuda.stream(side):
+            fn()
+        for t_ in tensors:
+            t_.record_stream(side)
+
     for hv in reversed(ctx['halves']):
         nd, geo, yl, mr = hv['nd'], hv['geo'], hv['yl'], hv['mr']
         g_, b_, _ = _norm_params(hv['norm'])
         pn = names[id(hv['norm'])]
         gname = pn + ('.gamma' if hasattr(hv['norm'], 'gamma') else '.weight')
         bname = pn + ('.beta' if hasattr(hv['norm'], 'gamma') else '.bias')
+        if xs_read is not None:
+            main.wait_event(xs_read)
         L_.call('dprnn_norm_residual', yl, xs, mr, (-g_.detach()).contiguous(), (-b_.detach()).contiguous(), B, S * K, F,
                 None, st)                                            # xs: x_out -> x_in
         dy = ops.gn_bwd(dx, yl, mr, g_.detach(), B, S * K, F, G[gname], G[bname])
         ln = names[id(hv['lin'])]
-        ops.atb(dy, hv['hout'], rows, F, nd * H, G[ln + '.weight'])
-        ops.colsum(dy, rows, F, G[ln + '.bias'])
+        hout = hv['hout']
+
+        def lin_grads(dy=dy, hout=hout, ln=ln, nd=nd):
+            ops.atb(dy, hout, rows, F, nd * H, G[ln + '.weight'])
+            ops.colsum(dy, rows, F, G[ln + '.bias'])
+        on_side(lin_grads, dy, hout)
         dh = ops.mm(dy, hv['lin'].weight.detach().t().contiguous(), rows, nd * H, F)
         del dy
         dgates = ops.empty(rows, nd * 4 * H)
@@ -405,21 +440,28 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
         else:
             L_.call('dprnn_lstm_bptt_f32', dh, hv['gates'], hv['cst'], hv['whh'], dgates, *geo, H, nd, st)
         del dh
-        hprev = ops.empty(rows, nd * H)
-        L_.call('dprnn_shift_rows', hv['hout'], hprev, *geo, H, nd, st)
         rn = names[id(hv['rnn'])]
-        for d, sf in enumerate(hv['sfx']):
-            dgd = dgates.data_ptr() + 4 * d * 4 * H
-            ops.atb(dgd, xs, rows, 4 * H, F, G[f'{rn}.weight_ih_l0{sf}'], lda=nd * 4 * H)
-            ops.atb(dgd, hprev.data_ptr() + 4 * d * H, rows, 4 * H, H, G[f'{rn}.weight_hh_l0{sf}'], lda=nd * 4 * H, ldb=nd * H)
-            db = ops.empty(4 * H)                                    # b_ih and b_hh enter as a sum: one reduction, two adds
-            ops.colsum(dgd, rows, 4 * H, db, ldx=nd * 4 * H, accumulate=False)
-            ops.axpy(db, G[f'{rn}.bias_ih_l0{sf}'])
-            ops.axpy(db, G[f'{rn}.bias_hh_l0{sf}'])
+        xs_read = torch.cuda.Event()
+
+        def rnn_grads(dgates=dgates, hout=hout, rn=rn, nd=nd, geo=geo, sfx=hv['sfx'], xs_read=xs_read):
+            for d, sf in enumerate(sfx):                             # the reads of xs first: the chain waits for them
+                ops.atb(dgates.data_ptr() + 4 * d * 4 * H, xs, rows, 4 * H, F, G[f'{rn}.weight_ih_l0{sf}'], lda=nd * 4 * H)
+            xs_read.record(torch.cuda.current_stream())
+            hprev = ops.empty(rows, nd * H)
+            L_.call('dprnn_shift_rows', hout, hprev, *geo, H, nd, _st())
+            for d, sf in enumerate(sfx):
+                dgd = dgates.data_ptr() + 4 * d * 4 * H
+                ops.atb(dgd, hprev.data_ptr() + 4 * d * H, rows, 4 * H, H, G[f'{rn}.weight_hh_l0{sf}'], lda=nd * 4 * H, ldb=nd * H)
+                db = ops.empty(4 * H)                                # b_ih and b_hh enter as a sum: one reduction, two adds
+                ops.colsum(dgd, rows, 4 * H, db, ldx=nd * 4 * H, accumulate=False)
+                ops.axpy(db, G[f'{rn}.bias_ih_l0{sf}'])
+                ops.axpy(db, G[f'{rn}.bias_hh_l0{sf}'])
+        on_side(rnn_grads, dgates, hout)
         dxl = ops.mm(dgates, hv['wih'].t().contiguous(), rows, F, nd * 4 * H)
         ops.axpy(dxl, dx)                                            # dx (gradient of x_in) = dx_out + LSTM-branch gradient
-        del dgates, hprev, dxl
+        del dgates, dxl, hout
         hv['hout'] = hv['gates'] = hv['cst'] = hv['yl'] = None       # free as we go
+    main.wait_stream(side)
 
     # ---- unfold adjoint = fold; bottleneck conv; fusion; bottleneck norm
     dyb = ops.empty(B, Lm, F)
