@@ -52,6 +52,11 @@ __device__ __forceinline__ float bptt_tanh(float x, bool fast) {
     }
     return tanhf(x);
 }
+// d gates is written once and read back much later (3.2 GB per layer): streaming stores keep it from evicting the
+// L2-prefetched inputs of the next step
+__device__ __forceinline__ void st_stream4(float* p, float a, float b, float c, float d) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 __device__ __forceinline__ uint32_t bptt_cluster_ctarank() {
     uint32_t r;
     asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
@@ -213,12 +218,11 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
         };
         Ld cur, nxt;
         issue(0, 0, ok[0], base[0], cur);
-        prefetch_step(1);
 
         for (int s = 0; s < T; ++s) {
             const int fstep = T - 1 - s;                      // forward step being differentiated
             const int t = dir ? T - 1 - fstep : fstep;
-            prefetch_step(s + 2);
+            prefetch_step(s + 1);
             if (s > 0) {
                 mbar_wait(d_full, (s - 1) & 1);
                 tc_fence_after();
@@ -271,10 +275,10 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                     }
                     if (ok[it]) {
                         float* o = p.dgates + rowi * ldg + dir * G4 + u0;
-                        *reinterpret_cast<float4*>(o) = make_float4(dpi[0], dpi[1], dpi[2], dpi[3]);
-                        *reinterpret_cast<float4*>(o + H) = make_float4(dpf[0], dpf[1], dpf[2], dpf[3]);
-                        *reinterpret_cast<float4*>(o + 2 * H) = make_float4(dpg[0], dpg[1], dpg[2], dpg[3]);
-                        *reinterpret_cast<float4*>(o + 3 * H) = make_float4(dpo[0], dpo[1], dpo[2], dpo[3]);
+                        st_stream4(o, dpi[0], dpi[1], dpi[2], dpi[3]);
+                        st_stream4(o + H, dpf[0], dpf[1], dpf[2], dpf[3]);
+                        st_stream4(o + 2 * H, dpg[0], dpg[1], dpg[2], dpg[3]);
+                        st_stream4(o + 3 * H, dpo[0], dpo[1], dpo[2], dpo[3]);
                     }
                     if (fstep > 0) {
                         // A operand: K-block kb = 2*gate + ph, column (unit % 64) -> 16-byte chunk l16/2, byte (l16&1)*8
