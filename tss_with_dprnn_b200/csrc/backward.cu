@@ -116,34 +116,47 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restr
                                                             const float* __restrict__ mean_rstd,
                                                             const float* __restrict__ gamma, long rows_per_utt, int C,
                                                             double* __restrict__ utt_part, float* __restrict__ ch_part) {
+    // thread = 4 consecutive channels (float4 loads), 256 / (C/4) rows per pass; fp32 partials per thread (a few hundred
+    // terms), fp64 across the block
     __shared__ double scratch[32];
-    __shared__ float shg[256], shb[256];
+    __shared__ float4 shg[256], shb[256];
     const int b = blockIdx.y, p = blockIdx.x, nparts = gridDim.x;
-    const int lanes = 256 / C, c = threadIdx.x % C, rl = threadIdx.x / C;
-    const float mean = mean_rstd[2 * b], rstd = mean_rstd[2 * b + 1], g = gamma[c];
+    const int c4n = C / 4, lanes = 256 / c4n, c4 = threadIdx.x % c4n, rl = threadIdx.x / c4n;
+    const float mean = mean_rstd[2 * b], rstd = mean_rstd[2 * b + 1];
+    const float4 g = reinterpret_cast<const float4*>(gamma)[c4];
     const long per = (rows_per_utt + nparts - 1) / nparts;
     const long r0 = (long)p * per, r1 = min(r0 + per, rows_per_utt);
-    const float* dzb = dz + (long)b * rows_per_utt * C;
-    const float* yb = y + (long)b * rows_per_utt * C;
-    double s1 = 0.0, s2 = 0.0;
-    float dg = 0.f, db = 0.f;
-    for (long r = r0 + rl; r < r1; r += lanes) {
-        const float d = dzb[r * C + c], yh = (yb[r * C + c] - mean) * rstd;
-        dg = fmaf(d, yh, dg); db += d;
-        s1 += (double)(d * g); s2 += (double)(d * g * yh);
+    const float4* dzb = reinterpret_cast<const float4*>(dz + (long)b * rows_per_utt * C);
+    const float4* yb = reinterpret_cast<const float4*>(y + (long)b * rows_per_utt * C);
+    float4 dg = make_float4(0.f, 0.f, 0.f, 0.f), db = dg;
+    float f1 = 0.f, f2 = 0.f;
+    if (rl < lanes) {
+        for (long r = r0 + rl; r < r1; r += lanes) {
+            const float4 d = ld_stream(dzb + r * c4n + c4), yv = ld_stream(yb + r * c4n + c4);
+            const float4 yh = make_float4((yv.x - mean) * rstd, (yv.y - mean) * rstd, (yv.z - mean) * rstd, (yv.w - mean) * rstd);
+            dg.x = fmaf(d.x, yh.x, dg.x); dg.y = fmaf(d.y, yh.y, dg.y); dg.z = fmaf(d.z, yh.z, dg.z); dg.w = fmaf(d.w, yh.w, dg.w);
+            db.x += d.x; db.y += d.y; db.z += d.z; db.w += d.w;
+            const float4 e = make_float4(d.x * g.x, d.y * g.y, d.z * g.z, d.w * g.w);
+            f1 += (e.x + e.y) + (e.z + e.w);
+            f2 += (e.x * yh.x + e.y * yh.y) + (e.z * yh.z + e.w * yh.w);
+        }
     }
     shg[threadIdx.x] = dg; shb[threadIdx.x] = db;
-    s1 = block_sum(s1, scratch);
-    s2 = block_sum(s2, scratch);
+    double s1 = block_sum((double)f1, scratch);
+    double s2 = block_sum((double)f2, scratch);
     __syncthreads();
     if (threadIdx.x == 0) {
         utt_part[((long)b * nparts + p) * 2 + 0] = s1;
         utt_part[((long)b * nparts + p) * 2 + 1] = s2;
     }
     if (rl == 0) {
-        for (int i = 1; i < lanes; ++i) { dg += shg[i * C + c]; db += shb[i * C + c]; }
-        ch_part[(((long)b * nparts + p) * C + c) * 2 + 0] = dg;
-        ch_part[(((long)b * nparts + p) * C + c) * 2 + 1] = db;
+        for (int i = 1; i < lanes; ++i) {
+            const float4 a = shg[i * c4n + c4], c = shb[i * c4n + c4];
+            dg.x += a.x; dg.y += a.y; dg.z += a.z; dg.w += a.w;
+            db.x += c.x; db.y += c.y; db.z += c.z; db.w += c.w;
+        }
+        float* o = ch_part + (((long)b * nparts + p) * C + c4 * 4) * 2;
+        o[0] = dg.x; o[1] = db.x; o[2] = dg.y; o[3] = db.y; o[4] = dg.z; o[5] = db.z; o[6] = dg.w; o[7] = db.w;
     }
 }
 

@@ -44,15 +44,15 @@ class _Ops:
                     pro.get('p_shift'), pro.get('p_add'), None, epi, _st())
         return out
 
-    def mm(self, A, W, M, N, K, bias=None):
-        """C[M,N] = A[M,K] @ W[N,K]^T + bias with W in nn.Linear layout; tensor cores in tf32 mode."""
+    def mm(self, A, W, M, N, K, bias=None, epi=EPI_NONE):
+        """C[M,N] = epi(A[M,K] @ W[N,K]^T + bias) with W in nn.Linear layout; tensor cores in tf32 mode."""
         if not (self.tf32 and K % 32 == 0 and N % 64 == 0 and M >= 128):
-            return self.gemm(A, W.t().contiguous(), M, N, K, bias=bias)
+            return self.gemm(A, W.t().contiguous(), M, N, K, bias=bias, epi=epi)
         out = self.empty(M, N)
         step = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 64)
         for n0 in range(0, N, step):
             self.L.call('dprnn_gemm_tc', A, 0, W[n0:n0 + step], None if bias is None else bias[n0:n0 + step],
-                        out.data_ptr() + 4 * n0, N, M, step, K, EPI_NONE, None, 0, 0.0, None, _st())
+                        out.data_ptr() + 4 * n0, N, M, step, K, epi, None, 0, 0.0, None, _st())
         return out
 
     def atb(self, A, B, M, N1, N2, out, lda=None, ldb=None, ldc=None, accumulate=True):
@@ -158,7 +158,9 @@ def forward_train(model, mix, ref=None, div=None):
     ctx.update(enc=enc, feats=feats, emb=None)
 
     if is_spe:
-        # ---- speaker encoder (dprnn_spe.py:115-122,156-163), BatchNorm in train mode
+        # ---- speaker encoder (dprnn_spe.py:115-122,156-163), BatchNorm in train mode.  Its contractions stay exact fp32 in
+    # both modes: the train-mode BatchNorm chain and the scalar PReLU slope gradients are cancellation-heavy (TF32 there
+    # moved one slope gradient by 40 %) and the branch is < 3 % of the step
         se = sep.spk_encoder
         mr_s = ops.utt_stats(feats, B, Lr * N, se[0].eps)
         s1 = ops.empty(B, N); s0 = ops.empty(B, N)
@@ -300,12 +302,12 @@ def forward_train(model, mix, ref=None, div=None):
     est = ops.empty(B, T) if is_spe else ops.empty(B, 2, T)
     heads = []
     for sp in spks:
-        u = ops.gemm(z, cw[sp * F:(sp + 1) * F].t().contiguous(), B * Lm, F, F,
+        u = ops.mm(z, cw[sp * F:(sp + 1) * F], B * Lm, F, F,
                      bias=(2.0 * cb[sp * F:(sp + 1) * F]).contiguous())       # overlap-add sums two chunks: bias twice
-        pre = ops.gemm(u, wog.t().contiguous(), B * Lm, 2 * F, F, bias=bog)
+        pre = ops.mm(u, wog, B * Lm, 2 * F, F, bias=bog)
         g = ops.empty(B * Lm, F)
         L_.call('dprnn_gated_fwd', pre, g, B * Lm, F, st)
-        m = ops.gemm(g, sep.end_conv1x1.weight.detach().reshape(N, F).t().contiguous(), B * Lm, N, F, epi=act)
+        m = ops.mm(g, sep.end_conv1x1.weight.detach().reshape(N, F), B * Lm, N, F, epi=act)
         L_.call('dprnn_mask_decode', m, Lm * N, enc, w_dec, est.data_ptr() + 4 * sp * T, len(spks) * T, B, Lm, N, 2, 1, st)
         heads.append(dict(u=u, pre=pre, g=g, m=m))
     logits = None
@@ -363,19 +365,19 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
         dpm = torch.empty_like(dm)
         L_.call('dprnn_act_bwd', dm, m, dpm, dm.numel(), 2 if cfg['activation_type'] == 'sigmoid' else 1, st)
         ops.atb(dpm, g, ML, N, F, G['separation.end_conv1x1.weight'])
-        dg = ops.gemm(dpm, sep.end_conv1x1.weight.detach().reshape(N, F), ML, F, N)
+        dg = ops.mm(dpm, sep.end_conv1x1.weight.detach().reshape(N, F).t().contiguous(), ML, F, N)
         dpre = torch.empty_like(pre)
         L_.call('dprnn_gated_bwd', dg, pre, dpre, ML, F, st)
         ops.atb(dpre, u, ML, F, F, gout, lda=2 * F)
         ops.atb(dpre.data_ptr() + 4 * F, u, ML, F, F, ggate, lda=2 * F)
         ops.colsum(dpre, ML, F, G['separation.out.0.bias'], ldx=2 * F)
         ops.colsum(dpre.data_ptr() + 4 * F, ML, F, G['separation.gate.0.bias'], ldx=2 * F)
-        du = ops.gemm(dpre, ctx['wog'], ML, F, 2 * F)
+        du = ops.mm(dpre, ctx['wog'].t().contiguous(), ML, F, 2 * F)
         ops.atb(du, z, ML, F, F, gcw.data_ptr() + 4 * sp * F * F)
         dbc = ops.empty(F)
         ops.colsum(du, ML, F, dbc, accumulate=False)
         L_.call('dprnn_axpy', dbc, 2.0, gcb.data_ptr() + 4 * sp * F, F, 1, st)    # the folded conv adds the bias twice
-        t = ops.gemm(du, ctx['cw'][sp * F:(sp + 1) * F].contiguous(), ML, F, F)
+        t = ops.mm(du, ctx['cw'][sp * F:(sp + 1) * F].t().contiguous(), ML, F, F)
         if dz is None:
             dz = t
         else:
@@ -473,7 +475,7 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
     ops.atb(dyb, fused, ML, F, N, gbw, ldc=ldw)
     ops.colsum(dyb, ML, F, G['separation.bottleneck.1.bias'])
     bw = sep.bottleneck[1].weight.detach().reshape(F, -1)
-    dfused = ops.gemm(dyb, bw, ML, N, F, ldw=ldw)                    # first N input channels of the conv
+    dfused = ops.mm(dyb, bw[:, :N].t().contiguous(), ML, N, F)                    # first N input channels of the conv
     demb = torch.zeros_like(emb) if is_spe else None
     ft = cfg['fusion_type'] if is_spe else None
     gamma, beta, _ = _norm_params(sep.bottleneck[0])
