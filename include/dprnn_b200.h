@@ -369,9 +369,11 @@ int dprnn_lstm_recurrence_f32_train(const float* gx, const float* whhT, float* h
                                     long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride,
                                     long step_stride, int hidden, int ndir, void* stream);
 /* Training forward on the tensor cores: dprnn_lstm_layer_bf16 (bf16 operands [x_t | h_{t-1}] [W_ih | W_hh]^T, fp32
- * accumulation, fp32 cell state) whose epilogue also stores gates [rows, ndir*4H], cstate [rows, ndir*H] and h in fp32
+ * accumulation, fp32 cell state) whose epilogue also stores what BPTT needs: the gate ACTIVATIONS as bf16, packed per
+ * 8-unit chunk - gates_packed [rows][ndir][16 chunks][4 gates i,f,g,o][8 units] (rows*ndir*512 bf16; element
+ * (row, d, gate q, unit u) at ((row*ndir + d)*16 + u/8)*32 + q*8 + u%8) -, cstate [rows, ndir*H] and h in fp32
  * (hout_f32 [rows, ndir*H]); hout_bf16 as in dprnn_lstm_layer_bf16. */
-int dprnn_lstm_layer_bf16_train(const void* x, const void* w_packed, const float* bias_perm, void* hout_bf16, float* gates,
+int dprnn_lstm_layer_bf16_train(const void* x, const void* w_packed, const float* bias_perm, void* hout_bf16, void* gates_packed,
                                 float* cstate, float* hout_f32, int B, int S, int K, int inter, int hidden, int ndir,
                                 int fast_act, void* stream);
 /* BPTT: dh_out [rows, ndir*H] = gradient of the layer output; whh [ndir][4H][H] (PyTorch layout);
@@ -381,8 +383,9 @@ int dprnn_lstm_bptt_f32(const float* dh_out, const float* gates, const float* cs
                         int hidden, int ndir, void* stream);
 /* dprnn_lstm_bptt_f32 with the recurrent contraction d h_{t-1} = d gates_t @ W_hh on the tensor cores (tcgen05, CTA pair,
  * bf16 operands, fp32 accumulation in TMEM; everything element-wise and the d gates output stay fp32).
- * whhT_bf16: [ndir][H][4H] bf16 = W_hh^T per direction.  fast_act: tanh.approx for tanh(c_t), as the forward kernel. */
-int dprnn_lstm_bptt_tc(const float* dh_out, const float* gates, const float* cstate, const void* whhT_bf16, float* dgates,
+ * gates_packed: the bf16 layout dprnn_lstm_layer_bf16_train writes.  whhT_bf16: [ndir][H][4H] bf16 = W_hh^T per
+ * direction.  fast_act: tanh.approx for tanh(c_t), as the forward kernel. */
+int dprnn_lstm_bptt_tc(const float* dh_out, const void* gates_packed, const float* cstate, const void* whhT_bf16, float* dgates,
                        long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride, long step_stride,
                        int hidden, int ndir, int fast_act, void* stream);
 /* h_prev for the W_hh gradient: out[row(n,t)] = h[row(n, previous step of the direction)], 0 at the first step. */

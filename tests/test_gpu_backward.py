@@ -16,6 +16,17 @@ def rnd(*shape, seed=0):
     return torch.randn(*shape, generator=torch.Generator().manual_seed(seed))
 
 
+def pack_gates(g, nd, H=128):
+    """fp32 row-major gates [rows, nd*4H] -> the bf16 layout of the tensor-core kernels [rows][nd][16][4][8]."""
+    rows = g.shape[0]
+    return g.view(rows, nd, 4, H // 8, 8).permute(0, 1, 3, 2, 4).contiguous().to(torch.bfloat16).view(rows, nd * 4 * H)
+
+
+def unpack_gates(gp, nd, H=128):
+    rows = gp.shape[0]
+    return gp.view(rows, nd, H // 8, 4, 8).permute(0, 1, 3, 2, 4).contiguous().float().view(rows, nd * 4 * H)
+
+
 def rel(a, b):
     return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-30))
 
@@ -117,8 +128,9 @@ def test_lstm_train_forward_and_bptt(inter, ndir, big=False):
     # kernel; rows past the real ones are never written
     dg2 = torch.full((rows + 1, ndir * 4 * H), 7.0, device=DEV)
     whhT = whh.transpose(1, 2).contiguous().to(torch.bfloat16).to(DEV)
+    gates_p = pack_gates(gates, ndir)
     for fast in (0, 1):
-        L.call('dprnn_lstm_bptt_tc', dout.float().reshape(rows, -1).contiguous().to(DEV), gates, cst, whhT, dg2, *geo, H,
+        L.call('dprnn_lstm_bptt_tc', dout.float().reshape(rows, -1).contiguous().to(DEV), gates_p, cst, whhT, dg2, *geo, H,
                ndir, fast, st())
         assert float((dg2[:rows] - dg).abs().max()) < 2e-2 * float(dg.abs().max())
         assert float((dg2[rows:] - 7.0).abs().max()) == 0.0
@@ -159,9 +171,11 @@ def test_lstm_tensor_core_train_forward_saves_what_bptt_needs(inter):
     xb = xs.to(torch.bfloat16)
     wp, bp = Engine._pack_lstm_tc(rnn, sfx)
     hb = torch.empty(rows, nd * H, device=DEV, dtype=torch.bfloat16)
-    h1, g1, c1 = (torch.full((rows + 1, n), 7.0, device=DEV) for n in (nd * H, nd * 4 * H, nd * H))
+    h1, c1 = (torch.full((rows + 1, n), 7.0, device=DEV) for n in (nd * H, nd * H))
+    g1p = torch.full((rows + 1, nd * 4 * H), 7.0, device=DEV, dtype=torch.bfloat16)
     for fast in (0, 1):
-        L.call('dprnn_lstm_layer_bf16_train', xb, wp, bp, hb, g1, c1, h1, B, S, K, inter, H, nd, fast, st())
+        L.call('dprnn_lstm_layer_bf16_train', xb, wp, bp, hb, g1p, c1, h1, B, S, K, inter, H, nd, fast, st())
+        g1 = unpack_gates(g1p, nd)
         assert float((g1[:rows] - g0).abs().max()) < 3e-2
         assert float((c1[:rows] - c0).abs().max()) < 5e-2
         assert float((h1[:rows] - h0).abs().max()) < 3e-2

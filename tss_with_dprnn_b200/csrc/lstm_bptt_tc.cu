@@ -1,7 +1,8 @@
 // BPTT of one LSTM layer with the recurrent contraction on 5th-gen tensor cores (training step, tensor-core mode):
 //     d h_{t-1}[256 seq, 128] = d gates_t[256 seq, 512] (bf16) @ W_hh[512, 128] (bf16)      (fp32 accumulators in TMEM)
-// Same inputs / outputs as the exact fp32 kernel (lstm_bwd_kernel, lstm_simt.cu): d h_out, the saved gate activations and
-// cell states in, the gradient of the gate pre-activations (fp32, row-major) out.
+// Inputs: d h_out (fp32, row-major), the gate activations saved by the tensor-core forward (bf16, packed per 8-unit chunk)
+// and the cell states (fp32); output: the gradient of the gate pre-activations (fp32, row-major), as the exact fp32 kernel
+// (lstm_bwd_kernel, lstm_simt.cu) produces it.
 //
 // A CTA PAIR (cluster of 2, tcgen05 cta_group::2, M = 256) owns 256 sequences of one direction for all T steps; each CTA
 // holds its 128 sequences' d gates tile (A operand, 8 K-blocks of [128 x 64] bf16, 128 KiB, rewritten every step) and
@@ -36,7 +37,8 @@ static_assert(SM_TOTAL <= 232448, "shared memory budget of one SM (227 KiB)");
 
 struct LstmBpttTcParams {
     const float* dh_out;   // [rows, ndir*H]
-    const float* gates;    // [rows, ndir*4H] activations i,f,g,o
+    const uint2* gates;    // activations i,f,g,o as bf16, packed [rows][ndir][16 chunks of 8 units][4 gates][8] (the
+                           // layout dprnn_lstm_layer_bf16_train writes); one uint2 = 4 units of one gate
     const float* cstate;   // [rows, ndir*H]
     float* dgates;         // [rows, ndir*4H]
     long nseq; int T;
@@ -170,21 +172,20 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
 
         // The step streams 7 float4 per (row, lane) through registers; with only 8 warps per SM the loads of the NEXT
         // (row pair | unit-half | step) are issued before the current one is computed (software double buffering).
-        struct Ld { float4 gi, gf, gg, go, cv, cp, dho; };
+        struct Ld { uint2 gi, gf, gg, go; float4 cv, cp, dho; };
         auto issue = [&](int s_, int ph_, bool valid, int base_, Ld& L) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            L.gi = z; L.gf = z; L.gg = z; L.go = z; L.cv = z; L.cp = z; L.dho = z;
+            const uint2 zu = make_uint2(0u, 0u);
+            L.gi = zu; L.gf = zu; L.gg = zu; L.go = zu; L.cv = z; L.cp = z; L.dho = z;
             if (s_ < T && valid) {
                 const int fs = T - 1 - s_;
                 const int t_ = dir ? T - 1 - fs : fs;
                 const int tp = dir ? t_ + 1 : t_ - 1;
                 const long rowi = (long)base_ + (long)t_ * p.step_stride;
                 const int u0 = ph_ * 64 + l16 * 4;
-                const float* g = p.gates + rowi * ldg + dir * G4 + u0;
-                L.gi = ld_stream(reinterpret_cast<const float4*>(g));
-                L.gf = ld_stream(reinterpret_cast<const float4*>(g + H));
-                L.gg = ld_stream(reinterpret_cast<const float4*>(g + 2 * H));
-                L.go = ld_stream(reinterpret_cast<const float4*>(g + 3 * H));
+                // chunk = u0 / 8 (8 uint2 each: 2 per gate), 4-unit half (u0 / 4) & 1 inside it
+                const uint2* g = p.gates + ((rowi * p.ndir + dir) * 16 + (u0 >> 3)) * 8 + ((u0 >> 2) & 1);
+                L.gi = __ldg(g); L.gf = __ldg(g + 2); L.gg = __ldg(g + 4); L.go = __ldg(g + 6);
                 L.cv = *reinterpret_cast<const float4*>(p.cstate + rowi * ldh + dir * H + u0);
                 if (fs > 0)
                     L.cp = *reinterpret_cast<const float4*>(p.cstate + ((long)base_ + (long)tp * p.step_stride) * ldh + dir * H + u0);
@@ -205,11 +206,11 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
 #pragma unroll
                 for (int ph_ = 0; ph_ < 2; ++ph_) {
                     const int u0 = ph_ * 64 + l16 * 4;
-                    const float* g = p.gates + rowi * ldg + dir * G4 + u0;
+                    // packed gates: 512 B = 4 lines per (row, direction, unit-half); lanes 0 and 8 of the half-warp fetch two
+                    // consecutive lines each (chunks 0-3 / 4-7)
+                    const uint2* g = p.gates + ((rowi * p.ndir + dir) * 16 + (u0 >> 3)) * 8;
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + H));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 2 * H));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 3 * H));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 16));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dh_out + rowi * ldh + dir * H + u0));
                     if (fs > 0)     // c_{t-1} of that step (it is c_t of the step after it)
                         asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cstate + ((long)base[it] + (long)tp * p.step_stride) * ldh + dir * H + u0));
@@ -257,9 +258,14 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                     const long rowi = (long)base[it] + (long)t * p.step_stride;
                     float4 dhr = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (s > 0) dhr = *reinterpret_cast<const float4*>(stgw + (it * 2 + hw) * STG_LD + l16 * 4);
-                    const float ia[4] = {cur.gi.x, cur.gi.y, cur.gi.z, cur.gi.w}, fa[4] = {cur.gf.x, cur.gf.y, cur.gf.z, cur.gf.w},
-                                ga[4] = {cur.gg.x, cur.gg.y, cur.gg.z, cur.gg.w}, oa[4] = {cur.go.x, cur.go.y, cur.go.z, cur.go.w},
-                                ca[4] = {cur.cv.x, cur.cv.y, cur.cv.z, cur.cv.w}, pa[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w},
+                    auto unpack = [](uint2 v, float (&o)[4]) {
+                        const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+                        const float2 b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+                        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y;
+                    };
+                    float ia[4], fa[4], ga[4], oa[4];
+                    unpack(cur.gi, ia); unpack(cur.gf, fa); unpack(cur.gg, ga); unpack(cur.go, oa);
+                    const float ca[4] = {cur.cv.x, cur.cv.y, cur.cv.z, cur.cv.w}, pa[4] = {cur.cp.x, cur.cp.y, cur.cp.z, cur.cp.w},
                                 da[4] = {cur.dho.x + dhr.x, cur.dho.y + dhr.y, cur.dho.z + dhr.z, cur.dho.w + dhr.w};
                     float dpi[4], dpf[4], dpg[4], dpo[4];
 #pragma unroll
@@ -314,7 +320,7 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
 using namespace dprnn;
 
 // whhT_bf16: [ndir][H = 128 output columns j][4H = 512 gate rows k] bf16 = W_hh^T per direction (k = gate*128 + unit)
-extern "C" int dprnn_lstm_bptt_tc(const float* dh_out, const float* gates, const float* cstate, const void* whhT_bf16,
+extern "C" int dprnn_lstm_bptt_tc(const float* dh_out, const void* gates, const float* cstate, const void* whhT_bf16,
                                   float* dgates, long nseq, int T, long seq_div, long seq_outer_stride,
                                   long seq_inner_stride, long step_stride, int hidden, int ndir, int fast_act,
                                   void* stream) {
@@ -329,7 +335,7 @@ extern "C" int dprnn_lstm_bptt_tc(const float* dh_out, const float* gates, const
     const uint64_t dW[2] = {512, (uint64_t)ndir * 128}, sW[2] = {2, 1024};
     const uint32_t bW[2] = {64, 64};
     if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, whhT_bf16, dW, sW, bW)) return 1;
-    LstmBpttTcParams p{dh_out, gates, cstate, dgates, nseq, T, (int)seq_div, seq_outer_stride, seq_inner_stride, step_stride, ndir};
+    LstmBpttTcParams p{dh_out, (const uint2*)gates, cstate, dgates, nseq, T, (int)seq_div, seq_outer_stride, seq_inner_stride, step_stride, ndir};
     const long njobs = (nseq + 255) / 256 * ndir;
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
     auto kern = fast_act ? lstm_bptt_tc_kernel<true> : lstm_bptt_tc_kernel<false>;

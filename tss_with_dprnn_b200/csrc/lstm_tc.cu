@@ -34,7 +34,7 @@ struct LstmTcParams {
     int ndir;
     const int2* jobs;      // ragged inter-chunk layer: per utterance {first chunk, number of chunks}; else NULL
     // training forward (cfg 5): what BPTT needs, stored by the epilogue as the values are produced
-    float* gates;          // [rows, ndir*4H] gate ACTIVATIONS i,f,g,o
+    uint32_t* gates;       // gate ACTIVATIONS i,f,g,o as bf16, packed [rows][ndir][16 chunks][4 gates][8 units]
     float* cst;            // [rows, ndir*H]  cell state after the step
     float* hf;             // [rows, ndir*H]  h in fp32 (operand of the weight-gradient contractions)
     int K, S;              // chunk length / chunks per utterance (linear row of (sequence, t))
@@ -93,13 +93,22 @@ __device__ __forceinline__ void st_global_v8(float* p, const float (&a)[4], cons
                  ::"l"(p), "f"(a[0]), "f"(a[1]), "f"(a[2]), "f"(a[3]), "f"(b[0]), "f"(b[1]), "f"(b[2]), "f"(b[3]) : "memory");
 }
 
+__device__ __forceinline__ void st_global_v8u(uint32_t* p, const uint32_t (&a)[4], const uint32_t (&b)[4]) {
+    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 ::"l"(p), "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]), "r"(b[2]), "r"(b[3]) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
 // Cell update for 8 hidden units of one sequence row: gates from TMEM (+bias) -> c (registers), h (packed bf16, one
 // 16-byte chunk).  8 units at a time keeps the live register set small enough for 128 registers per thread, which
 // leaves room on the SM for a memory-bound CTA of another stream next to this kernel.
 // The i, f, o rows of the weights and biases are pre-scaled by 1/2 on the host (exact), so sigmoid(x) = 1/2 tanh(x') + 1/2.
 template <bool kFastAct, bool kTrain>
 __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restrict__ bq, float* __restrict__ c,
-                                           uint32_t (&packed)[4], float* __restrict__ gdst = nullptr,
+                                           uint32_t (&packed)[4], uint32_t* __restrict__ gdst = nullptr,
                                            float* __restrict__ cdst = nullptr, float* __restrict__ hdst = nullptr) {
     uint32_t ri[8], rf[8], rg[8], ro[8];
     tmem_ld8_issue(tcol + 0 * 64, ri);
@@ -107,7 +116,8 @@ __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restric
     tmem_ld8_issue(tcol + 2 * 64, rg);
     tmem_ld8_issue(tcol + 3 * 64, ro);
     tmem_ld_wait();
-    float keep[kTrain ? 6 : 1][4];
+    float keep[kTrain ? 2 : 1][4];
+    uint32_t gk[kTrain ? 4 : 1][4];      // bf16 pairs of the 4 gates of the call's 8 units
 #pragma unroll
     for (int j = 0; j < 8; j += 4) {
         const float4 bi = *reinterpret_cast<const float4*>(bq + 0 * 64 + j), bf = *reinterpret_cast<const float4*>(bq + 1 * 64 + j);
@@ -133,19 +143,22 @@ __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restric
             if constexpr (kTrain) { sv[0][u] = ig; sv[1][u] = fg; sv[2][u] = gg; sv[3][u] = og; sv[4][u] = cn; }
         }
         if constexpr (kTrain) {
-            if (gdst) {            // one 32-byte (full sector) store per array and pair of j iterations
+            if (gdst) {
+                // the 8 units of the call leave as 64 contiguous bytes of bf16 gates [i8 | f8 | g8 | o8] (two 32-byte
+                // stores) plus one 32-byte store each for c and h (fp32): 4 full-sector stores per thread and call
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    gk[g][(j >> 1) + 0] = pack_bf16x2(sv[g][0], sv[g][1]);
+                    gk[g][(j >> 1) + 1] = pack_bf16x2(sv[g][2], sv[g][3]);
+                }
                 if (j == 0) {
 #pragma unroll
-                    for (int g = 0; g < 5; ++g)
-#pragma unroll
-                        for (int u = 0; u < 4; ++u) keep[g][u] = sv[g][u];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) keep[5][u] = hv[u];
+                    for (int u = 0; u < 4; ++u) { keep[0][u] = sv[4][u]; keep[1][u] = hv[u]; }
                 } else {
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) st_global_v8(gdst + g * 128, keep[g], sv[g]);
-                    st_global_v8(cdst, keep[4], sv[4]);
-                    st_global_v8(hdst, keep[5], hv);
+                    st_global_v8u(gdst, gk[0], gk[1]);
+                    st_global_v8u(gdst + 8, gk[2], gk[3]);
+                    st_global_v8(cdst, keep[0], sv[4]);
+                    st_global_v8(hdst, keep[1], hv);
                 }
             }
         }
@@ -298,11 +311,12 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         for (int step = 0; step < T; ++step) {
             const int t = dir ? T - 1 - step : step;
             const uint32_t par = step & 1;
-            float *gd = nullptr, *cd = nullptr, *hd = nullptr;
+            uint32_t* gd = nullptr;
+            float *cd = nullptr, *hd = nullptr;
             if constexpr (kTrain) {
                 if (live) {
                     const long lr = p.seq_dim == 2 ? seq * p.K + t : ((long)outer * p.S + t) * p.K + seq;
-                    gd = p.gates + (lr * p.ndir + dir) * 512 + sub * 32;
+                    gd = p.gates + (lr * p.ndir + dir) * 256 + sub * 64;      // uint32 units: 16 per 8-unit chunk
                     cd = p.cst + (lr * p.ndir + dir) * 128 + sub * 32;
                     hd = p.hf + (lr * p.ndir + dir) * 128 + sub * 32;
                 }
@@ -314,7 +328,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int g = 0; g < 4; ++g)
                 lstm_cell8<kFastAct, kTrain>(tbase + 8 * g, sbias + sub * 32 + 8 * g, c0 + 8 * g, pk[g],
-                                             gd ? gd + 8 * g : nullptr, cd + 8 * g, hd + 8 * g);
+                                             gd ? gd + 16 * g : nullptr, cd + 8 * g, hd + 8 * g);
             tc_fence_before();                         // our tcgen05.ld of D0 are complete
             mbar_wait(h_free, par);                    // the MMAs that read h_{t-1} have completed
             if (storer) bulk_wait_read0();             // ... and so has last step's TMA store of the h tile
@@ -334,7 +348,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
 #pragma unroll
             for (int g = 0; g < 4; ++g)
                 lstm_cell8<kFastAct, kTrain>(tbase + 256 + 8 * g, sbias + 256 + sub * 32 + 8 * g, c1s + 8 * g, pk[g],
-                                             gd ? gd + 64 + 8 * g : nullptr, cd + 64 + 8 * g, hd + 64 + 8 * g);
+                                             gd ? gd + 128 + 16 * g : nullptr, cd + 64 + 8 * g, hd + 64 + 8 * g);
             tc_fence_before();
             {
                 uint8_t* sH = smem + SM_H + TILE;      // K-block 1 = units 64..127
@@ -370,7 +384,7 @@ using namespace dprnn;
 // `inter`==1: sequences (b,k) run along s.
 static int lstm_layer_impl(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
                            int inter, int hidden, int ndir, int fast_act, const int2* jobs, int n_jobs, void* stream,
-                           float* gates = nullptr, float* cstate = nullptr, float* hout_f32 = nullptr) {
+                           void* gates = nullptr, float* cstate = nullptr, float* hout_f32 = nullptr) {
     DPRNN_CHECK_ARG(x && w_packed && bias_perm && hout && B > 0 && S > 0 && K > 0);
     DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2));
     DPRNN_CHECK_ARG(((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)hout) % 16 == 0);
@@ -379,7 +393,7 @@ static int lstm_layer_impl(const void* x, const void* w_packed, const float* bia
     LstmTcParams p;
     p.ndir = ndir;
     p.jobs = jobs;
-    p.gates = gates; p.cst = cstate; p.hf = hout_f32;
+    p.gates = (uint32_t*)gates; p.cst = cstate; p.hf = hout_f32;
     p.K = K; p.S = S;
     p.seq_limit = inter ? K : (long)B * S;
     uint64_t dX[4], sX[4], dH[4], sH[4];
@@ -426,10 +440,11 @@ extern "C" int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const 
     return lstm_layer_impl(x, w_packed, bias_perm, hout, B, S, K, inter, hidden, ndir, fast_act, nullptr, 0, stream);
 }
 
-// Training forward (cfg 5): the same kernel, whose epilogue also stores the gate activations, the cell state and h in
-// fp32 for every step - what dprnn_lstm_bptt_f32 and the weight-gradient contractions read.
+// Training forward (cfg 5): the same kernel, whose epilogue also stores the gate activations (bf16, packed per 8-unit
+// chunk: [rows][ndir][16][i8|f8|g8|o8]), the cell state and h (fp32) of every step - what dprnn_lstm_bptt_tc and the
+// weight-gradient contractions read.
 extern "C" int dprnn_lstm_layer_bf16_train(const void* x, const void* w_packed, const float* bias_perm, void* hout_bf16,
-                                           float* gates, float* cstate, float* hout_f32, int B, int S, int K, int inter,
+                                           void* gates, float* cstate, float* hout_f32, int B, int S, int K, int inter,
                                            int hidden, int ndir, int fast_act, void* stream) {
     DPRNN_CHECK_ARG(gates && cstate && hout_f32);
     DPRNN_CHECK_ARG(((uintptr_t)gates | (uintptr_t)cstate | (uintptr_t)hout_f32) % 16 == 0);

@@ -264,7 +264,9 @@ def forward_train(model, mix, ref=None, div=None):
             b = torch.cat([(getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s)).detach() for s in sfx], 0)
             whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach() for s in sfx], 0).contiguous()   # [nd,4H,H]
             geo = (B * S, K, 1, K, 0, 1) if which == 0 else (B * K, S, K, S * K, 1, K)
-            hout, gates, cst = ops.empty(rows, nd * H), ops.empty(rows, nd * 4 * H), ops.empty(rows, nd * H)
+            hout, cst = ops.empty(rows, nd * H), ops.empty(rows, nd * H)
+            # saved gate activations: fp32 row-major in the exact mode, bf16 packed per 8-unit chunk in the tensor-core mode
+            gates = torch.empty((rows, nd * 4 * H), device=dev, dtype=torch.bfloat16 if ops.tf32 else torch.float32)
             if ops.tf32:
                 # tensor-core recurrence (bf16 operands, fp32 accumulation and cell state), input projection fused:
                 # the kernel of the inference path, whose epilogue also stores what BPTT needs
