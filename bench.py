@@ -592,16 +592,17 @@ def run_ours(args):
         # cell states and d h_out and writes d gates: 4H + 2H + H + 4H floats per chunk position and direction.
         k = per_kernel[bptt_name]
         peak_bw = peaks.get('hbm_gbs', 6400.0)
-        bytes_per_launch = wl.positions(0) * 2 * (4 * 128 + 2 * 128 + 128 + 4 * 128) * 4
+        gate_bytes = 4 * 128 * (2 if bptt_name == 'dprnn_lstm_bptt_tc' else 4)     # saved gates: packed bf16 / fp32
+        bytes_per_launch = wl.positions(0) * 2 * (gate_bytes + (2 * 128 + 128 + 4 * 128) * 4)
         achieved = bytes_per_launch / (k['ms_avg'] * 1e-3) / 1e9
         roofline = {'kernel': bptt_name, 'bound': 'hbm', 'achieved': achieved, 'peak': peak_bw, 'unit': 'GB/s',
                     'frac': achieved / peak_bw, 'traffic': None,
                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6400 (B200_PROFILING.md)',
                     'launch_ms_avg': k['ms_avg'],
                     'share_of_step_single_stream': k['ms_total'] / sum(v['ms_total'] for v in per_kernel.values()),
-                    'note': 'dominant kernel of the training step (BPTT).  Algorithmic bytes = 11 H floats per chunk position '
-                            'and direction (gates, c_t, c_{t-1}, dh in; dgates out).  Tensor-core mode: d h_{t-1} = d gates_t '
-                            'W_hh on tcgen05 (CTA pair); at 16 utterances per GPU only 98..126 of 148 SMs hold a CTA and the '
+                    'note': 'dominant kernel of the training step (BPTT).  Algorithmic bytes per chunk position and direction: 4 H '
+                            'saved gate activations (bf16 in tensor-core mode), c_t, c_{t-1}, dh (3 H fp32) in; dgates (4 H fp32) out.  Tensor-core mode: d h_{t-1} = d gates_t '
+                            'W_hh on tcgen05 (CTA pair); at 16 utterances per GPU only 64..98 of 148 SMs hold a CTA and the '
                             'element-wise cell backward between the MMAs is issue/latency-bound (ncu: 27 % issue slots, top '
                             'stall = first use of the streamed loads): DESIGN.md section 5.2'}
 
