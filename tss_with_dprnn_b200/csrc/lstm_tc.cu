@@ -21,6 +21,8 @@
 namespace dprnn {
 using namespace tc;
 
+constexpr int NEPI = 8;                       // epilogue warps: NEPI/4 per TMEM lane quadrant, 64/(NEPI/4) units per thread and half
+constexpr int UPT = 64 / (NEPI / 4);          // units per thread and unit-half
 constexpr int NXS = 4;                        // x ring stages, each a K-half [128 seq x 64 feat] bf16 = 16 KiB
 constexpr uint32_t TILE = 128 * 128;          // bytes of one [128 rows x 128 B] swizzled tile
 constexpr uint32_t SM_W = 0, SM_H = 8 * TILE, SM_X = SM_H + 2 * TILE, SM_BIAS = SM_X + NXS * TILE,
@@ -169,7 +171,7 @@ __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restric
 }
 
 template <bool kFastAct, bool kTrain>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * NEPI, 1)
 lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                const __grid_constant__ CUtensorMap tmH, const float* __restrict__ bias_perm, const LstmTcParams p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -206,7 +208,7 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         mbar_init(w_full, 1);
         mbar_init(&d_full[0], 1); mbar_init(&d_full[1], 1);
         mbar_init(h_free, 1);
-        mbar_init(&h_done[0], 16); mbar_init(&h_done[1], 16);   // one elected lane per epilogue warp, both CTAs
+        mbar_init(&h_done[0], 2 * NEPI); mbar_init(&h_done[1], 2 * NEPI);   // one elected lane per epilogue warp, both CTAs
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 512; i += blockDim.x) sbias[i] = bias_perm[dir * 512 + i];
@@ -296,14 +298,16 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
         }
     } else if (warp >= 4) {
         // ================= epilogue: gates -> (c, h) =================
-        // all 8 warps work on D0, then on D1: warp -> TMEM lane quadrant q = warp % 4, 32-unit sub-block sub = e / 4
+        // all NEPI warps work on D0, then on D1: warp -> TMEM lane quadrant q = warp % 4, UPT-unit sub-block sub = e / 4
+        // (16 warps x 16 units per thread measured the same step time as 8 x 32: the step is bound by the MUFU pipe and
+        // the MMA <-> epilogue hand-off, not by the per-thread chain)
         const int e = warp - 4, q = e & 3, sub = e >> 2;
         const int row = q * 32 + lane;
-        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + sub * 32;
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + sub * UPT;
         const uint32_t leader_hdone = map_to_cta(smem_u32(&h_done[0]), 0);
-        float c0[32], c1s[32];
+        float c0[UPT], c1s[UPT];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) { c0[i] = 0.f; c1s[i] = 0.f; }
+        for (int i = 0; i < UPT; ++i) { c0[i] = 0.f; c1s[i] = 0.f; }
         const bool storer = (warp == 4 && lane == 0);
         const long seq = (long)seq0 + row;
         const bool live = kTrain && seq < p.seq_limit;
@@ -316,28 +320,28 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             if constexpr (kTrain) {
                 if (live) {
                     const long lr = p.seq_dim == 2 ? seq * p.K + t : ((long)outer * p.S + t) * p.K + seq;
-                    gd = p.gates + (lr * p.ndir + dir) * 256 + sub * 64;      // uint32 units: 16 per 8-unit chunk
-                    cd = p.cst + (lr * p.ndir + dir) * 128 + sub * 32;
-                    hd = p.hf + (lr * p.ndir + dir) * 128 + sub * 32;
+                    gd = p.gates + (lr * p.ndir + dir) * 256 + sub * (2 * UPT);      // uint32 units: 16 per 8-unit chunk
+                    cd = p.cst + (lr * p.ndir + dir) * 128 + sub * UPT;
+                    hd = p.hf + (lr * p.ndir + dir) * 128 + sub * UPT;
                 }
             }
             // ---------------- unit half 0
             mbar_wait(&d_full[0], par);
             tc_fence_after();
-            uint32_t pk[4][4];
+            uint32_t pk[UPT / 8][4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                lstm_cell8<kFastAct, kTrain>(tbase + 8 * g, sbias + sub * 32 + 8 * g, c0 + 8 * g, pk[g],
+            for (int g = 0; g < UPT / 8; ++g)
+                lstm_cell8<kFastAct, kTrain>(tbase + 8 * g, sbias + sub * UPT + 8 * g, c0 + 8 * g, pk[g],
                                              gd ? gd + 16 * g : nullptr, cd + 8 * g, hd + 8 * g);
             tc_fence_before();                         // our tcgen05.ld of D0 are complete
             mbar_wait(h_free, par);                    // the MMAs that read h_{t-1} have completed
             if (storer) bulk_wait_read0();             // ... and so has last step's TMA store of the h tile
-            named_bar(1, 256);
+            named_bar(1, 32 * NEPI);
             {
                 uint8_t* sH = smem + SM_H;             // K-block 0 = units 0..63; 8 units = one 16-byte chunk
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + g)) = make_uint4(pk[g][0], pk[g][1], pk[g][2], pk[g][3]);
+                for (int g = 0; g < UPT / 8; ++g)
+                    *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * (UPT / 8) + g)) = make_uint4(pk[g][0], pk[g][1], pk[g][2], pk[g][3]);
             }
             fence_async_smem();                        // generic-proxy writes -> visible to tcgen05.mma / TMA
             __syncwarp();
@@ -346,20 +350,20 @@ lstm_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ 
             mbar_wait(&d_full[1], par);
             tc_fence_after();
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                lstm_cell8<kFastAct, kTrain>(tbase + 256 + 8 * g, sbias + 256 + sub * 32 + 8 * g, c1s + 8 * g, pk[g],
+            for (int g = 0; g < UPT / 8; ++g)
+                lstm_cell8<kFastAct, kTrain>(tbase + 256 + 8 * g, sbias + 256 + sub * UPT + 8 * g, c1s + 8 * g, pk[g],
                                              gd ? gd + 128 + 16 * g : nullptr, cd + 64 + 8 * g, hd + 64 + 8 * g);
             tc_fence_before();
             {
                 uint8_t* sH = smem + SM_H + TILE;      // K-block 1 = units 64..127
 #pragma unroll
-                for (int g = 0; g < 4; ++g)
-                    *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * 4 + g)) = make_uint4(pk[g][0], pk[g][1], pk[g][2], pk[g][3]);
+                for (int g = 0; g < UPT / 8; ++g)
+                    *reinterpret_cast<uint4*>(sH + sw128_offset(row, sub * (UPT / 8) + g)) = make_uint4(pk[g][0], pk[g][1], pk[g][2], pk[g][3]);
             }
             fence_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_remote(leader_hdone + 8);
-            named_bar(2, 256);
+            named_bar(2, 32 * NEPI);
             if (storer) {
                 tma_store_4d(&tmH, smem + SM_H, dir * 128, c1(t), c2(t), outer);
                 tma_store_4d(&tmH, smem + SM_H + TILE, dir * 128 + 64, c1(t), c2(t), outer);
@@ -430,7 +434,7 @@ static int lstm_layer_impl(const void* x, const void* w_packed, const float* bia
                       : (fast_act ? lstm_tc_kernel<true, false> : lstm_tc_kernel<false, false>);
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
-    kern<<<(unsigned)(njobs * 2), 384, smem, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);
+    kern<<<(unsigned)(njobs * 2), 128 + 32 * NEPI, smem, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }
