@@ -332,6 +332,9 @@ int dprnn_resample_fir(const float* x, const float* kernel, float* out, int B, l
 
 /* ---- the callers' side of the path ---- */
 
+/* 16-bit PCM -> float32 with the normalisation of soundfile.read(dtype='float32') (x / 32768; the reference's datasets
+ * read their wav segments that way, src/datasets/librimix_spe.py:50-55): pcm [n] int16 -> out [n]. */
+int dprnn_pcm16_to_f32(const void* pcm, float* out, long n, void* stream);
 /* SI-SDR in dB per utterance (asteroid recipe: zero-mean, eps 1e-8; src/trainers/trainer_spe.py:39,
  * src/inferencers/inferencer_spe.py:37-43).  Utterance b = samples [off[b], off[b]+len[b]) of est / target, or
  * [b*uniform_len, +uniform_len) when off == len == NULL. */

@@ -156,6 +156,13 @@ __global__ void train_loss_final_kernel(const float* __restrict__ terms, int B, 
     if (threadIdx.x == 0) { loss[0] = (float)((s0 + s1) / B); loss[1] = (float)(s0 / B); loss[2] = (float)(s1 / B); }
 }
 
+// 16-bit PCM -> float32 as libsndfile / soundfile.read(dtype='float32') normalises it (x / 32768, exact): the packed
+// shards of shards.py travel to the device as int16 (half the H2D bytes) and are widened here
+__global__ void pcm16_to_f32_kernel(const short* __restrict__ in, float* __restrict__ out, long n) {
+    for (long i = blockIdx.x * (long)blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x)
+        out[i] = (float)in[i] * (1.0f / 32768.0f);
+}
+
 __global__ void __launch_bounds__(256) sqnorm_partial_kernel(const float* __restrict__ g, long n, double* __restrict__ partial) {
     __shared__ double scratch[32];
     const long per = (n + gridDim.x - 1) / gridDim.x;
@@ -224,6 +231,15 @@ extern "C" int dprnn_pit2_assign(const float* est, const float* target, int B, l
                                  float* pairwise, void* stream) {
     DPRNN_CHECK_ARG(est && target && target_perm && perm && B > 0 && T > 0);
     pit2_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(est, target, T, target_perm, perm, pairwise);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+extern "C" int dprnn_pcm16_to_f32(const void* pcm, float* out, long n, void* stream) {
+    DPRNN_CHECK_ARG(pcm && out && n > 0);
+    const long want = (n + 255) / 256;
+    pcm16_to_f32_kernel<<<(unsigned)(want < 148L * 16 ? want : 148L * 16), 256, 0, (cudaStream_t)stream>>>(
+        (const short*)pcm, out, n);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

@@ -14,6 +14,20 @@ from ._lib import lib
 from .sharding import length_buckets, lpt_assign, chunk_count
 
 
+class _Pcm:
+    """A pinned int16 host buffer whose .to(device) lands as float32 (x / 32768) through dprnn_pcm16_to_f32."""
+
+    def __init__(self, host):
+        self.host = host
+
+    def to(self, dev, non_blocking=True):
+        raw = self.host.to(dev, non_blocking=non_blocking)
+        out = torch.empty(raw.numel(), device=dev, dtype=torch.float32)
+        lib().call('dprnn_pcm16_to_f32', raw, out, raw.numel(), torch.cuda.current_stream().cuda_stream)
+        raw.record_stream(torch.cuda.current_stream())
+        return out
+
+
 def si_sdr(est: torch.Tensor, target: torch.Tensor, lengths=None) -> torch.Tensor:
     """SI-SDR in dB per utterance on the GPU.  est / target: [B, T], or packed 1-D tensors with `lengths`."""
     if not est.is_cuda:
@@ -49,6 +63,8 @@ def evaluate(model, mixtures, references=None, targets=None, bucket: int = 64, r
     def stage(idx):
         """pinned packed host buffers -> device, on the copy stream"""
         def pack(items):
+            if items[idx[0]].dtype == torch.int16:        # 16-bit PCM (shards.py): half the H2D bytes, widened on the GPU
+                return _Pcm(torch.cat([items[i].reshape(-1) for i in idx]).pin_memory())
             flat = torch.cat([items[i].reshape(-1).float() for i in idx]).pin_memory()
             return flat
         with torch.cuda.stream(copy_stream):
