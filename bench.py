@@ -494,6 +494,8 @@ def run_ours(args):
     model = getattr(P, cls)(**kw).eval().to(dev)      # same seeded weights on every rank (replicated, 16 MB)
     model.precision = args.precision
     model.n_streams = args.streams
+    model._engine.lstm_slices = args.lstm_slices
+    model._engine.lstm_pairs = args.lstm_pairs
     if args.fused_tail is not None:
         model._engine.fused_tail = bool(args.fused_tail)
     L = P.lib()
@@ -654,6 +656,10 @@ def main():
     ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
     ap.add_argument('--streams', type=int, default=int(os.environ.get('DPRNN_STREAMS', '3')),
                     help='concurrent CUDA streams the batch is split over inside one forward (cfg2)')
+    ap.add_argument('--lstm-slices', type=int, default=int(os.environ.get('DPRNN_LSTM_SLICES', '1')),
+                    help='time slices per LSTM job of the persistent kernel (1 = one job per CTA pair)')
+    ap.add_argument('--lstm-pairs', type=int, default=int(os.environ.get('DPRNN_LSTM_PAIRS', '0')),
+                    help='cap on the resident CTA pairs of the persistent LSTM kernel (0 = all)')
     ap.add_argument('--fused-tail', type=int, default=None, help='1: Linear+norm+residual as one persistent kernel')
     ap.add_argument('--batch', type=int, default=None, help='utterances per GPU and step (cfg 2: 64; cfg 3: bucket size)')
     ap.add_argument('--samples', type=int, default=24000, help='samples per utterance (3 s @ 8 kHz)')

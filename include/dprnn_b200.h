@@ -270,6 +270,16 @@ int dprnn_prologue_apply_ragged(const float* a, float* out, long rows, int C, co
                                 const float* p_shift, const float* p_add, const float* rowscale, void* stream);
 int dprnn_gemm_tc_ragged(const void* A, int a_is_bf16, const void* W, const float* bias_per_utt, const int* row_utt,
                          float* C, long ldc, int M, int N, int K, int epilogue, void* stream);
+/* dprnn_lstm_layer_bf16 as a persistent kernel over time-sliced jobs (csrc/lstm_tc_sliced.cu): every (tile, direction) job
+ * is cut into nslices slices handed out by an atomic ticket to <= #SM/2 resident CTA pairs, which turns ceil(jobs/74)
+ * waves into ceil(nslices*jobs/74)/nslices.  Same arguments and results (bit for bit) as dprnn_lstm_layer_bf16;
+ * workspace (dprnn_lstm_sliced_workspace_bytes) holds the ticket, per-job completion counters and the cell-state
+ * hand-off; it is re-armed by every call.  max_pairs > 0 caps the number of resident CTA pairs (the SMs left over serve
+ * the memory-bound kernels of concurrent streams). */
+size_t dprnn_lstm_sliced_workspace_bytes(int B, int S, int K, int inter, int ndir);
+int dprnn_lstm_layer_bf16_sliced(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
+                                 int inter, int hidden, int ndir, int fast_act, int nslices, int max_pairs, void* workspace,
+                                 void* stream);
 /* Inter-chunk layer of dprnn_lstm_layer_bf16 on the packed chunk space: utt_jobs = n_utt x {int32 first chunk, int32
  * number of chunks}, in the order the pair-jobs should be scheduled (longest first). */
 int dprnn_lstm_inter_bf16_ragged(const void* x, const void* w_packed, const float* bias_perm, void* hout,

@@ -212,3 +212,29 @@ def test_linear_bf16out_then_norm_residual(B, R, K):
     want = x0.double().view(B, R, N) + (yv - mean.view(B, 1, 1)) * rstd.view(B, 1, 1) * gamma.double() + beta.double()
     assert O.peak_rel_err(x.cpu(), want.view(M, N).float()) < 2e-5
     assert torch.equal(xb.cpu(), x.cpu().bfloat16())
+
+
+@pytest.mark.parametrize('inter', [0, 1])
+@pytest.mark.parametrize('nslices', [1, 2, 3, 7])
+def test_lstm_sliced_persistent_is_bit_identical(inter, nslices):
+    """The persistent, time-sliced LSTM kernel (cell state through a global scratch, h re-read from the stored rows)
+    returns bit for bit what the one-job-per-pair kernel returns."""
+    from tss_with_dprnn_b200.engine import Engine
+    L = P.lib()
+    B, S, K, H, nd = 5, 30, 250, 128, 2                      # intra: 150 sequences; inter: 5 tiles x 2 dirs, T = 30
+    torch.manual_seed(3 + inter)
+    rnn = torch.nn.LSTM(H, H, 1, batch_first=True, bidirectional=True).cuda()
+    rows = B * S * K
+    xb = (0.5 * torch.randn(rows, H, generator=torch.Generator().manual_seed(4))).cuda().to(torch.bfloat16)
+    wp, bp = Engine._pack_lstm_tc(rnn, ['', '_reverse'])
+    st = torch.cuda.current_stream().cuda_stream
+    want = torch.empty(rows, nd * H, device='cuda', dtype=torch.bfloat16)
+    L.call('dprnn_lstm_layer_bf16', xb, wp, bp, want, B, S, K, inter, H, nd, 1, st)
+    got = torch.full((rows + 1, nd * H), 7.0, device='cuda', dtype=torch.bfloat16)
+    ws = torch.empty(L.query('dprnn_lstm_sliced_workspace_bytes', B, S, K, inter, nd), device='cuda', dtype=torch.uint8)
+    for _ in range(2):                                       # the workspace is re-armed by every call
+        L.call('dprnn_lstm_layer_bf16_sliced', xb, wp, bp, got, B, S, K, inter, H, nd, 1, nslices, 3 if nslices == 3 else 0,
+               ws, st)
+        torch.cuda.synchronize()
+        assert torch.equal(got[:rows], want)
+        assert float((got[rows:].float() - 7.0).abs().max()) == 0.0

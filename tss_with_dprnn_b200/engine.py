@@ -27,6 +27,8 @@ class Engine(RaggedMixin):
     def __init__(self, model):
         self.model = model
         self.precision = 'fp32'
+        self.lstm_slices = 1           # > 1: time-sliced persistent LSTM kernel (bf16 mode, uniform batches)
+        self.lstm_pairs = 0            # > 0: cap on the CTA pairs that kernel keeps resident (0 = all SM pairs)
         self.fast_act = True       # bf16 mode: tanh.approx-based gate activations (1 MUFU op each)
         self.n_streams = 1         # >1: the batch is split into that many utterance groups on concurrent streams
         self.fused_tail = False    # bf16 mode: Linear + norm + residual as one persistent kernel (linear_norm.cu)
@@ -405,6 +407,18 @@ class Engine(RaggedMixin):
     def _half_lstm(self, s, bi, which):
         """bf16 mode: one nn.LSTM layer (intra: which=0, inter: which=1) as the fused tcgen05 kernel -> s['hb']."""
         hw = self.packed()['blocks'][bi][which]
+        if self.lstm_slices > 1:
+            # persistent CTA pairs over time-sliced jobs (lstm_tc_sliced.cu): bit-identical results, fewer idle SMs when
+            # the layer has more pair-jobs than the GPU has SM pairs
+            key = ('lstm_ws', s['B'], s['S'], s['K'], which, hw['ndir'], torch.cuda.current_stream().cuda_stream)
+            ws = s.get(key)
+            if ws is None:
+                ws = s[key] = torch.empty(lib().query('dprnn_lstm_sliced_workspace_bytes', s['B'], s['S'], s['K'], which,
+                                                      hw['ndir']), device=s['dev'], dtype=torch.uint8)
+            lib().call('dprnn_lstm_layer_bf16_sliced', s['xb'], hw['tc_w'], hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'],
+                       which, s['H'], hw['ndir'], int(self.fast_act), int(self.lstm_slices), int(self.lstm_pairs), ws,
+                       self._stream())
+            return
         lib().call('dprnn_lstm_layer_bf16', s['xb'], hw['tc_w'], hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'], which,
                    s['H'], hw['ndir'], int(self.fast_act), self._stream())
 
@@ -501,7 +515,7 @@ class Engine(RaggedMixin):
         if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
         key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
-               self.fast_act, self.fused_tail, self._weights_key())
+               self.fast_act, self.fused_tail, self.lstm_slices, self.lstm_pairs, self._weights_key())
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = 'seen'
