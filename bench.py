@@ -496,6 +496,7 @@ def run_ours(args):
     model.n_streams = args.streams
     model._engine.lstm_slices = args.lstm_slices
     model._engine.lstm_pairs = args.lstm_pairs
+    model._engine.lstm_pingpong = bool(args.lstm_pingpong)
     if args.fused_tail is not None:
         model._engine.fused_tail = bool(args.fused_tail)
     L = P.lib()
@@ -562,7 +563,8 @@ def run_ours(args):
         pass
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)     # kernel timed inside a long step -> sustained figure
     roofline = None
-    lstm_names = [n for n in per_kernel if n in (dominant, 'dprnn_lstm_inter_bf16_ragged')]
+    lstm_names = [n for n in per_kernel if n in (dominant, 'dprnn_lstm_inter_bf16_ragged', 'dprnn_lstm_layer_bf16_pp',
+                                                 'dprnn_lstm_layer_bf16_sliced')]
     if args.workload == 'cfg5':
         lstm_names = [n for n in per_kernel if n in ('dprnn_lstm_recurrence_f32_train', 'dprnn_lstm_bptt_f32', 'dprnn_lstm_layer_bf16_train', 'dprnn_lstm_bptt_tc')]
     if lstm_names:
@@ -575,7 +577,7 @@ def run_ours(args):
         achieved = flop_per_launch * n_launch / (ms_lstm * 1e-3) / 1e12
         roofline = {'kernel': '+'.join(lstm_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                     'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                    'traffic': (ncu_traffic_per_launch('lstm_tc_kernel') if args.workload == 'cfg2' and args.batch == 64
+                    'traffic': (ncu_traffic_per_launch('lstm_tc_') if args.workload == 'cfg2' and args.batch == 64
                                 and args.precision == 'bf16' else None),
                     'traffic_note': 'DRAM read+write bytes per launch, ncu --set full (profiles/r1_top3_ncu_full.txt); '
                                     'algorithmic: read xb 2 x 0.79 GB + write hb 1.59 GB = 3.18 GB',
@@ -658,6 +660,8 @@ def main():
                     help='concurrent CUDA streams the batch is split over inside one forward (cfg2)')
     ap.add_argument('--lstm-slices', type=int, default=int(os.environ.get('DPRNN_LSTM_SLICES', '1')),
                     help='time slices per LSTM job of the persistent kernel (1 = one job per CTA pair)')
+    ap.add_argument('--lstm-pingpong', type=int, default=int(os.environ.get('DPRNN_LSTM_PINGPONG', '1')),
+                    help='1 (default): half-job ping-pong LSTM kernel; 0: one job per CTA pair')
     ap.add_argument('--lstm-pairs', type=int, default=int(os.environ.get('DPRNN_LSTM_PAIRS', '0')),
                     help='cap on the resident CTA pairs of the persistent LSTM kernel (0 = all)')
     ap.add_argument('--fused-tail', type=int, default=None, help='1: Linear+norm+residual as one persistent kernel')

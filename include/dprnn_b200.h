@@ -270,6 +270,12 @@ int dprnn_prologue_apply_ragged(const float* a, float* out, long rows, int C, co
                                 const float* p_shift, const float* p_add, const float* rowscale, void* stream);
 int dprnn_gemm_tc_ragged(const void* A, int a_is_bf16, const void* W, const float* bias_per_utt, const int* row_utt,
                          float* C, long ldc, int M, int N, int K, int epilogue, void* stream);
+/* dprnn_lstm_layer_bf16 with two half-jobs (64 rows per CTA each, cta_group::2 M = 128) per CTA pair in ping-pong, so that
+ * one half-job's MMA -> epilogue hand-off runs under the other's cell update (csrc/lstm_tc_pp.cu).  Same arguments and
+ * results; w_packed rows for direction d, CTA rank r, MMA nh: {[W_ih | W_hh][gate*H + 64*nh + 32*r + u] : gate < 4, u < 32}
+ * (same 1/2 pre-scale of the i, f, o rows); bias_perm as dprnn_lstm_layer_bf16. */
+int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
+                             int inter, int hidden, int ndir, int fast_act, void* stream);
 /* dprnn_lstm_layer_bf16 as a persistent kernel over time-sliced jobs (csrc/lstm_tc_sliced.cu): every (tile, direction) job
  * is cut into nslices slices handed out by an atomic ticket to <= #SM/2 resident CTA pairs, which turns ceil(jobs/74)
  * waves into ceil(nslices*jobs/74)/nslices.  Same arguments and results (bit for bit) as dprnn_lstm_layer_bf16;

@@ -238,3 +238,29 @@ def test_lstm_sliced_persistent_is_bit_identical(inter, nslices):
         torch.cuda.synchronize()
         assert torch.equal(got[:rows], want)
         assert float((got[rows:].float() - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('inter', [0, 1])
+def test_lstm_half_job_pingpong_matches(inter):
+    """The half-job ping-pong kernel (M = 128 MMAs, 2x2 accumulator layout, re-packed weight rows) against the one-job
+    kernel on the same inputs."""
+    from tss_with_dprnn_b200.engine import Engine
+    L = P.lib()
+    B, S, K, H, nd = 5, 30, 250, 128, 2
+    torch.manual_seed(5 + inter)
+    rnn = torch.nn.LSTM(H, H, 1, batch_first=True, bidirectional=True).cuda()
+    rows = B * S * K
+    xb = (0.5 * torch.randn(rows, H, generator=torch.Generator().manual_seed(6))).cuda().to(torch.bfloat16)
+    wp, bp = Engine._pack_lstm_tc(rnn, ['', '_reverse'])
+    wp2, bp2 = Engine._pack_lstm_tc(rnn, ['', '_reverse'], half_jobs=True)
+    assert torch.equal(bp, bp2)
+    st = torch.cuda.current_stream().cuda_stream
+    want = torch.empty(rows, nd * H, device='cuda', dtype=torch.bfloat16)
+    L.call('dprnn_lstm_layer_bf16', xb, wp, bp, want, B, S, K, inter, H, nd, 1, st)
+    got = torch.full((rows + 1, nd * H), 7.0, device='cuda', dtype=torch.bfloat16)
+    L.call('dprnn_lstm_layer_bf16_pp', xb, wp2, bp2, got, B, S, K, inter, H, nd, 1, st)
+    torch.cuda.synchronize()
+    err = float((got[:rows].float() - want.float()).abs().max())
+    print('half-job kernel: max |diff| vs one-job kernel', err, 'bit-identical', torch.equal(got[:rows], want))
+    assert err < 2e-2
+    assert float((got[rows:].float() - 7.0).abs().max()) == 0.0

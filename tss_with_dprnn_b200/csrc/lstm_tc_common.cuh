@@ -94,15 +94,16 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // 16-byte chunk).  8 units at a time keeps the live register set small enough for 128 registers per thread, which
 // leaves room on the SM for a memory-bound CTA of another stream next to this kernel.
 // The i, f, o rows of the weights and biases are pre-scaled by 1/2 on the host (exact), so sigmoid(x) = 1/2 tanh(x') + 1/2.
-template <bool kFastAct, bool kTrain>
+// kGS = distance in TMEM columns between the four gates of a unit (64: one-job kernels; 32: the half-job kernel).
+template <bool kFastAct, bool kTrain, int kGS = 64>
 __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restrict__ bq, float* __restrict__ c,
                                            uint32_t (&packed)[4], uint32_t* __restrict__ gdst = nullptr,
                                            float* __restrict__ cdst = nullptr, float* __restrict__ hdst = nullptr) {
     uint32_t ri[8], rf[8], rg[8], ro[8];
-    tmem_ld8_issue(tcol + 0 * 64, ri);
-    tmem_ld8_issue(tcol + 1 * 64, rf);
-    tmem_ld8_issue(tcol + 2 * 64, rg);
-    tmem_ld8_issue(tcol + 3 * 64, ro);
+    tmem_ld8_issue(tcol + 0 * kGS, ri);
+    tmem_ld8_issue(tcol + 1 * kGS, rf);
+    tmem_ld8_issue(tcol + 2 * kGS, rg);
+    tmem_ld8_issue(tcol + 3 * kGS, ro);
     tmem_ld_wait();
     float keep[kTrain ? 2 : 1][4];
     uint32_t gk[kTrain ? 4 : 1][4];      // bf16 pairs of the 4 gates of the call's 8 units

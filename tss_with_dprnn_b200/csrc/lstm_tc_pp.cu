@@ -1,0 +1,259 @@
+// The fused tcgen05 LSTM layer (lstm_tc.cu) with TWO HALF-JOBS per CTA pair in ping-pong.
+//
+// In lstm_tc_kernel the epilogue phases of a step run at the MUFU roofline (2.6 us of the 3.9 us step for 128 rows per
+// CTA) and the rest is the hand-off h complete -> MMA -> commit -> TMEM load, during which the MUFU pipe idles.  A second
+// independent job would fill that gap but does not fit the shared memory next to the resident weights - two HALF jobs
+// do: the pair's 256 sequences are split into half-job A (rows 0..63 of each CTA) and B (rows 64..127).  Each half-job
+// is a cta_group::2 MMA with M = 128 (64 rows per CTA); its accumulator for unit-half nh occupies 128 TMEM columns with
+// the M = 128 "2x2" layout: lanes 0..63 hold N-columns 0..127, lanes 64..127 hold N-columns 128..255 of the same 64 rows.
+// The weight rows are packed so that N-column c of MMA nh is  gate (c % 128) / 32  of unit  64 nh + 32 (c / 128) + c % 32:
+// every lane then owns all four gates of 32 units.  Shared memory (weights, h and x tiles) and TMEM (4 x 128 columns) are
+// exactly those of the one-job kernel; the x tiles (128 rows) serve both half-jobs.
+// Warps 4..7 run half-job A's cell updates, warps 8..11 half-job B's, each with its own barriers; the MMA thread
+// alternates A(t), B(t), A(t+1), ...: while it waits for A's h_t, B's MMAs are in flight and B's epilogue keeps the MUFU
+// pipe busy, and vice versa.  Inference, uniform batches.
+#include "lstm_tc_common.cuh"
+
+namespace dprnn {
+using namespace tc;
+
+constexpr uint32_t PP_BAR_BYTES = 256;
+constexpr uint32_t PP_SM_TOTAL = SM_BAR + PP_BAR_BYTES;
+static_assert(PP_SM_TOTAL <= 232448, "shared memory budget of one SM (227 KiB)");
+constexpr uint32_t HALF_ROWS = 64 * 128;      // byte offset of rows 64..127 inside a [128 x 128 B] tile
+
+template <bool kFastAct>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmH64, const float* __restrict__ bias_perm, const LstmTcParams p) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
+    uint64_t* x_full = bars;                  // [NXS]  (leader's copy is the live one)
+    uint64_t* x_empty = bars + NXS;           // [NXS]
+    uint64_t* w_full = bars + 2 * NXS;
+    uint64_t* d_full = bars + 2 * NXS + 1;    // [2 half-jobs][2 unit halves]
+    uint64_t* h_free = bars + 2 * NXS + 5;    // [2]
+    uint64_t* h_done = bars + 2 * NXS + 7;    // [2][2]  (leader's copy)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NXS + 11);
+    float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int job = blockIdx.x >> 1;
+    const int dir = job % p.ndir;
+    const int jt = job / p.ndir;
+    const int outer = jt / p.tiles_per_outer;
+    const int seq0 = (jt % p.tiles_per_outer) * 256 + (int)rank * 128;
+    const int T = p.T;
+
+    if (threadIdx.x == 0) {
+        if (smem_u32(smem) & 1023u) {
+            printf("lstm_tc_pp_kernel: dynamic shared memory base %u is not 1024-byte aligned\n", smem_u32(smem));
+            __trap();
+        }
+        prefetch_tmap(&tmX); prefetch_tmap(&tmW); prefetch_tmap(&tmH64);
+        for (int s = 0; s < NXS; ++s) { mbar_init(&x_full[s], 2); mbar_init(&x_empty[s], 1); }
+        mbar_init(w_full, 1);
+        for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&h_done[i], 8); }   // 4 warps x 2 CTAs
+        mbar_init(&h_free[0], 1); mbar_init(&h_free[1], 1);
+        fence_barrier_init();
+    }
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) sbias[i] = bias_perm[dir * 512 + i];
+    if (warp == 2) tmem_alloc<2>(tmem_slot, 512);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+
+    if (warp == 0 && elect_one()) {
+        mbar_expect_tx(w_full, 8 * TILE);
+        const int wrow = ((dir * 2 + (int)rank) * 2) * 128;
+        for (int nh = 0; nh < 2; ++nh)
+            for (int kb = 0; kb < 4; ++kb)
+                tma_load_2d(smem + SM_W + (nh * 4 + kb) * TILE, &tmW, w_full, kb * 64, wrow + nh * 128);
+    }
+    mbar_wait(w_full, 0);
+    cluster_sync_all();
+    const uint32_t tmem = *tmem_slot;
+
+    auto c1 = [&](int t, int sq) { return p.seq_dim == 2 ? t : sq; };
+    auto c2 = [&](int t, int sq) { return p.seq_dim == 2 ? sq : t; };
+
+    if (warp == 0) {
+        // ================= TMA producer: x_t K-halves (128 rows: both half-jobs) into the ring =================
+        if (elect_one()) {
+            const uint32_t leader_full0 = map_to_cta(smem_u32(&x_full[0]), 0);
+            int it = 0;
+            for (int step = 0; step < T; ++step) {
+                const int t = dir ? T - 1 - step : step;
+                for (int half = 0; half < 2; ++half, ++it) {
+                    const int s = it % NXS;
+                    mbar_wait(&x_empty[s], ((it / NXS) & 1) ^ 1);
+                    const uint32_t lbar = leader_full0 + s * 8;
+                    if (rank == 0) mbar_expect_tx_addr(smem_u32(&x_full[s]), 2 * TILE);
+                    else mbar_arrive_remote(lbar);
+                    tma_load_4d_pair(smem + SM_X + s * TILE, &tmX, lbar, half * 64, c1(t, seq0), c2(t, seq0), outer);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================= MMA issuer (leader CTA only): A(t), B(t), A(t+1), ... =================
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+            const uint32_t aW = smem_u32(smem + SM_W), aH = smem_u32(smem + SM_H), aX = smem_u32(smem + SM_X);
+            auto mma_kb = [&](int j, int nh, int kb, uint32_t a_tile, bool first) {
+                const uint32_t b_tile = aW + (nh * 4 + kb) * TILE;
+                const uint32_t d = tmem + (uint32_t)(j * 2 + nh) * 128;
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk)
+                    umma_bf16<2>(d, umma_desc_sw128(a_tile + j * HALF_ROWS + kk * 32), umma_desc_sw128(b_tile + kk * 32),
+                                 idesc, (first && kk == 0) ? 0u : 1u);
+            };
+            int it = 0;
+            for (int step = 0; step < T; ++step, it += 2) {
+                const int s0 = it % NXS, s1 = (it + 1) % NXS;
+                mbar_wait_cluster(&x_full[s0], (it / NXS) & 1);
+                mbar_wait_cluster(&x_full[s1], ((it + 1) / NXS) & 1);
+                tc_fence_after();
+                const uint32_t x0 = aX + s0 * TILE, x1 = aX + s1 * TILE;
+                for (int j = 0; j < 2; ++j) {
+                    if (step == 0) {                              // h_0 = 0: only the input projection
+                        mma_kb(j, 0, 0, x0, true);  mma_kb(j, 0, 1, x1, false);
+                        mma_kb(j, 1, 0, x0, true);  mma_kb(j, 1, 1, x1, false);
+                        umma_commit_2cta(&h_free[j], 3);
+                        umma_commit_2cta(&d_full[j * 2 + 0], 3); umma_commit_2cta(&d_full[j * 2 + 1], 3);
+                        continue;
+                    }
+                    const uint32_t par = (step - 1) & 1;
+                    mbar_wait_cluster(&h_done[j * 2 + 0], par);   // D[j][0] drained, units 0..63 of h_{t-1} written
+                    tc_fence_after();
+                    mma_kb(j, 0, 0, x0, true);  mma_kb(j, 0, 1, x1, false);
+                    mma_kb(j, 0, 2, aH, false);
+                    mbar_wait_cluster(&h_done[j * 2 + 1], par);   // D[j][1] drained, h_{t-1} complete
+                    tc_fence_after();
+                    mma_kb(j, 0, 3, aH + TILE, false);
+                    umma_commit_2cta(&d_full[j * 2 + 0], 3);
+                    mma_kb(j, 1, 2, aH, true);   mma_kb(j, 1, 3, aH + TILE, false);
+                    umma_commit_2cta(&h_free[j], 3);
+                    mma_kb(j, 1, 0, x0, false);  mma_kb(j, 1, 1, x1, false);
+                    umma_commit_2cta(&d_full[j * 2 + 1], 3);
+                }
+                umma_commit_2cta(&x_empty[s0], 3); umma_commit_2cta(&x_empty[s1], 3);
+            }
+        }
+    } else if (warp >= 4) {
+        // ================= epilogue: warps 4..7 = half-job A, 8..11 = half-job B =================
+        const int e = warp - 4, j = e >> 2, q = e & 3;        // q = TMEM lane quadrant = warp % 4
+        const int L = q * 32 + lane;                           // TMEM lane: rows 0..63 twice (2x2 layout)
+        const int rih = L & 63, ub = L >> 6;                   // row inside the half-job, 32-unit block inside the unit half
+        const int row = j * 64 + rih;                          // row inside the CTA's 128-sequence tile
+        const uint32_t tlane = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(j * 2) * 128;
+        const uint32_t leader_hdone = map_to_cta(smem_u32(&h_done[j * 2]), 0);
+        float c0[32], c1s[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { c0[i] = 0.f; c1s[i] = 0.f; }
+        const bool storer = ((e & 3) == 0 && lane == 0);
+        const int bar_a = 1 + 2 * j, bar_b = 2 + 2 * j;
+        const int sq = seq0 + j * 64;
+
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? T - 1 - step : step;
+            const uint32_t par = step & 1;
+            // ---------------- unit half 0
+            mbar_wait(&d_full[j * 2 + 0], par);
+            tc_fence_after();
+            uint32_t pk[4][4];
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                lstm_cell8<kFastAct, false, 32>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g]);
+            tc_fence_before();
+            mbar_wait(&h_free[j], par);                // the MMAs that read this half-job's h_{t-1} have completed
+            if (storer) bulk_wait_read0();             // ... and so has last step's TMA store of its h rows
+            named_bar(bar_a, 128);
+            {
+                uint8_t* sH = smem + SM_H;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(sH + sw128_offset(row, ub * 4 + g)) = make_uint4(pk[g][0], pk[g][1], pk[g][2], pk[g][3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(leader_hdone);
+            // ---------------- unit half 1
+            mbar_wait(&d_full[j * 2 + 1], par);
+            tc_fence_after();
+#pragma unroll
+            for (int g = 0; g < 4; ++g)
+                lstm_cell8<kFastAct, false, 32>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g, pk[g]);
+            tc_fence_before();
+            {
+                uint8_t* sH = smem + SM_H + TILE;
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(sH + sw128_offset(row, ub * 4 + g)) = make_uint4(pk[g][0], pk[g][1], pk[g][2], pk[g][3]);
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(leader_hdone + 8);
+            named_bar(bar_b, 128);
+            if (storer) {
+                tma_store_4d(&tmH64, smem + SM_H + j * HALF_ROWS, dir * 128, c1(t, sq), c2(t, sq), outer);
+                tma_store_4d(&tmH64, smem + SM_H + TILE + j * HALF_ROWS, dir * 128 + 64, c1(t, sq), c2(t, sq), outer);
+                bulk_commit();
+            }
+        }
+        if (storer) bulk_wait0();
+    }
+    __syncwarp();
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc<2>(tmem, 512);
+}
+
+}  // namespace dprnn
+
+using namespace dprnn;
+
+// Same arguments and results as dprnn_lstm_layer_bf16, except the weight packing: w_packed rows for direction d, CTA
+// rank r and MMA nh are {[W_ih | W_hh][gate*H + 64*nh + 32*r + u] : gate = 0..3, u < 32} (Engine._pack_lstm_tc(half_jobs=True)).
+extern "C" int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B,
+                                        int S, int K, int inter, int hidden, int ndir, int fast_act, void* stream) {
+    DPRNN_CHECK_ARG(x && w_packed && bias_perm && hout && B > 0 && S > 0 && K > 0);
+    DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2));
+    DPRNN_CHECK_ARG(((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)hout) % 16 == 0);
+    CUtensorMap tmX, tmW, tmH;
+    const uint64_t ldx = 128 * 2, ldh = (uint64_t)ndir * 128 * 2;
+    LstmTcParams p{};
+    p.ndir = ndir;
+    uint64_t dX[4], sX[4], dH[4], sH[4];
+    uint32_t box[4] = {64, 1, 1, 1}, boxh[4] = {64, 1, 1, 1};
+    long njobs;
+    if (!inter) {
+        dX[0] = 128; dX[1] = K; dX[2] = (uint64_t)B * S; dX[3] = 1;
+        sX[0] = 2; sX[1] = ldx; sX[2] = (uint64_t)K * ldx; sX[3] = (uint64_t)B * S * K * ldx;
+        sH[0] = 2; sH[1] = ldh; sH[2] = (uint64_t)K * ldh; sH[3] = (uint64_t)B * S * K * ldh;
+        box[2] = 128; boxh[2] = 64;
+        p.T = K; p.seq_dim = 2; p.tiles_per_outer = (int)(((long)B * S + 255) / 256);
+        njobs = (long)p.tiles_per_outer * ndir;
+    } else {
+        dX[0] = 128; dX[1] = K; dX[2] = S; dX[3] = B;
+        sX[0] = 2; sX[1] = ldx; sX[2] = (uint64_t)K * ldx; sX[3] = (uint64_t)S * K * ldx;
+        sH[0] = 2; sH[1] = ldh; sH[2] = (uint64_t)K * ldh; sH[3] = (uint64_t)S * K * ldh;
+        box[1] = 128; boxh[1] = 64;
+        p.T = S; p.seq_dim = 1; p.tiles_per_outer = (K + 255) / 256;
+        njobs = (long)p.tiles_per_outer * B * ndir;
+    }
+    for (int i = 0; i < 4; ++i) dH[i] = dX[i];
+    dH[0] = (uint64_t)ndir * 128;
+    if (make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dX, sX, box)) return 1;
+    if (make_tmap(&tmH, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, hout, dH, sH, boxh)) return 1;
+    const uint64_t dW[2] = {256, (uint64_t)ndir * 512}, sW[2] = {2, 512};
+    const uint32_t bW[2] = {64, 128};
+    if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dW, sW, bW)) return 1;
+    auto kern = fast_act ? lstm_tc_pp_kernel<true> : lstm_tc_pp_kernel<false>;
+    DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP_SM_TOTAL));
+    DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
+    kern<<<(unsigned)(njobs * 2), 384, PP_SM_TOTAL, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}

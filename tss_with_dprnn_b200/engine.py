@@ -29,6 +29,7 @@ class Engine(RaggedMixin):
         self.precision = 'fp32'
         self.lstm_slices = 1           # > 1: time-sliced persistent LSTM kernel (bf16 mode, uniform batches)
         self.lstm_pairs = 0            # > 0: cap on the CTA pairs that kernel keeps resident (0 = all SM pairs)
+        self.lstm_pingpong = True      # half-job ping-pong LSTM kernel (bf16 mode, uniform batches; bit-identical results)
         self.fast_act = True       # bf16 mode: tanh.approx-based gate activations (1 MUFU op each)
         self.n_streams = 1         # >1: the batch is split into that many utterance groups on concurrent streams
         self.fused_tail = False    # bf16 mode: Linear + norm + residual as one persistent kernel (linear_norm.cu)
@@ -79,9 +80,10 @@ class Engine(RaggedMixin):
                                   for s in sfx], 0)
                 whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach().t() for s in sfx], 0)  # [nd, H, 4H]
                 wp, bp = self._pack_lstm_tc(rnn, sfx)
+                wp2, _ = self._pack_lstm_tc(rnn, sfx, half_jobs=True)
                 halves.append(dict(wih_t=wih.t().contiguous(), bias=bias.contiguous(), whh_t=whh.contiguous(),
                                    ndir=len(sfx), lin_t=_t(lin.weight), lin_b=lin.bias.detach(),
-                                   tc_w=wp, tc_bias=bp, lin_bf16=lin.weight.detach().to(torch.bfloat16).contiguous()))
+                                   tc_w=wp, tc_w2=wp2, tc_bias=bp, lin_bf16=lin.weight.detach().to(torch.bfloat16).contiguous()))
             blocks.append(halves)
         W['blocks'] = blocks
         cw = sep.conv2d.weight.detach().reshape(2 * F, F)
@@ -115,16 +117,21 @@ class Engine(RaggedMixin):
     _lstm_perm_cache = {}
 
     @staticmethod
-    def _pack_lstm_tc(rnn, sfx):
+    def _pack_lstm_tc(rnn, sfx, half_jobs=False):
         """Weight layout of dprnn_lstm_layer_bf16 (include/dprnn_b200.h): for direction d, CTA rank r and MMA
-        instruction nh, the 128 rows {[W_ih | W_hh][q*H + 64*nh + j] : q in (2r, 2r+1), j < 64}; bias likewise."""
+        instruction nh, the 128 rows {[W_ih | W_hh][q*H + 64*nh + j] : q in (2r, 2r+1), j < 64}; bias likewise.
+        half_jobs: the layout of dprnn_lstm_layer_bf16_pp - rows {[..][gate*H + 64*nh + 32*r + u] : gate < 4, u < 32}."""
         H = rnn.hidden_size
         dev = rnn.weight_ih_l0.device
-        key = (H, str(dev))
+        key = (H, str(dev), bool(half_jobs))
         cache = Engine._lstm_perm_cache
         if key not in cache:        # row permutations and the 1/2 pre-scale are fixed: built once per device
             j = torch.arange(64)
-            wrows = torch.cat([torch.cat([q * H + 64 * nh + j for q in (2 * r, 2 * r + 1)]) for r in range(2) for nh in range(2)])
+            if half_jobs:
+                u = torch.arange(32)
+                wrows = torch.cat([torch.cat([g * H + 64 * nh + 32 * r + u for g in range(4)]) for r in range(2) for nh in range(2)])
+            else:
+                wrows = torch.cat([torch.cat([q * H + 64 * nh + j for q in (2 * r, 2 * r + 1)]) for r in range(2) for nh in range(2)])
             brows = torch.cat([q * H + 64 * nh + j for nh in range(2) for q in range(4)])
             half = torch.ones(4 * H)
             half[:2 * H] = 0.5      # i, f, o rows pre-scaled by 1/2 (exact): the kernel evaluates sigmoid(x) as
@@ -407,6 +414,12 @@ class Engine(RaggedMixin):
     def _half_lstm(self, s, bi, which):
         """bf16 mode: one nn.LSTM layer (intra: which=0, inter: which=1) as the fused tcgen05 kernel -> s['hb']."""
         hw = self.packed()['blocks'][bi][which]
+        if self.lstm_pingpong:
+            # two half-jobs per CTA pair in ping-pong (lstm_tc_pp.cu): bit-identical results, the hand-off of one half-job
+            # hidden under the cell update of the other
+            lib().call('dprnn_lstm_layer_bf16_pp', s['xb'], hw['tc_w2'], hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'],
+                       which, s['H'], hw['ndir'], int(self.fast_act), self._stream())
+            return
         if self.lstm_slices > 1:
             # persistent CTA pairs over time-sliced jobs (lstm_tc_sliced.cu): bit-identical results, fewer idle SMs when
             # the layer has more pair-jobs than the GPU has SM pairs
@@ -515,7 +528,7 @@ class Engine(RaggedMixin):
         if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
         key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
-               self.fast_act, self.fused_tail, self.lstm_slices, self.lstm_pairs, self._weights_key())
+               self.fast_act, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self._weights_key())
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = 'seen'
