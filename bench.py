@@ -564,7 +564,7 @@ def run_ours(args):
     peak_tf = peaks.get('bf16_tflops_sustained', 1400.0)     # kernel timed inside a long step -> sustained figure
     roofline = None
     lstm_names = [n for n in per_kernel if n in (dominant, 'dprnn_lstm_inter_bf16_ragged', 'dprnn_lstm_layer_bf16_pp',
-                                                 'dprnn_lstm_layer_bf16_sliced')]
+                                                 'dprnn_lstm_layer_bf16_sliced', 'dprnn_lstm_inter_bf16_ragged_pp')]
     if args.workload == 'cfg5':
         lstm_names = [n for n in per_kernel if n in ('dprnn_lstm_recurrence_f32_train', 'dprnn_lstm_bptt_f32', 'dprnn_lstm_layer_bf16_train', 'dprnn_lstm_bptt_tc')]
     if lstm_names:

@@ -276,6 +276,9 @@ int dprnn_gemm_tc_ragged(const void* A, int a_is_bf16, const void* W, const floa
  * (same 1/2 pre-scale of the i, f, o rows); bias_perm as dprnn_lstm_layer_bf16. */
 int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
                              int inter, int hidden, int ndir, int fast_act, void* stream);
+int dprnn_lstm_inter_bf16_ragged_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout,
+                                    long total_chunks, int K, const void* utt_jobs, int n_utt, int hidden, int ndir,
+                                    int fast_act, void* stream);
 /* dprnn_lstm_layer_bf16 as a persistent kernel over time-sliced jobs (csrc/lstm_tc_sliced.cu): every (tile, direction) job
  * is cut into nslices slices handed out by an atomic ticket to <= #SM/2 resident CTA pairs, which turns ceil(jobs/74)
  * waves into ceil(nslices*jobs/74)/nslices.  Same arguments and results (bit for bit) as dprnn_lstm_layer_bf16;

@@ -11,7 +11,7 @@
 // exactly those of the one-job kernel; the x tiles (128 rows) serve both half-jobs.
 // Warps 4..7 run half-job A's cell updates, warps 8..11 half-job B's, each with its own barriers; the MMA thread
 // alternates A(t), B(t), A(t+1), ...: while it waits for A's h_t, B's MMAs are in flight and B's epilogue keeps the MUFU
-// pipe busy, and vice versa.  Inference, uniform batches.
+// pipe busy, and vice versa.  Inference; uniform batches and the ragged inter-chunk layer (one pair-job per utterance).
 #include "lstm_tc_common.cuh"
 
 namespace dprnn {
@@ -42,9 +42,13 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int job = blockIdx.x >> 1;
     const int dir = job % p.ndir;
     const int jt = job / p.ndir;
-    const int outer = jt / p.tiles_per_outer;
+    int outer = jt / p.tiles_per_outer;
     const int seq0 = (jt % p.tiles_per_outer) * 256 + (int)rank * 128;
-    const int T = p.T;
+    int T = p.T, t_base = 0;
+    if (p.jobs) {          // ragged inter-chunk layer: one pair-job per utterance (its chunks start at t_base)
+        const int2 jb = p.jobs[jt];
+        t_base = jb.x; T = jb.y; outer = 0;
+    }
 
     if (threadIdx.x == 0) {
         if (smem_u32(smem) & 1023u) {
@@ -76,7 +80,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const uint32_t tmem = *tmem_slot;
 
     auto c1 = [&](int t, int sq) { return p.seq_dim == 2 ? t : sq; };
-    auto c2 = [&](int t, int sq) { return p.seq_dim == 2 ? sq : t; };
+    auto c2 = [&](int t, int sq) { return p.seq_dim == 2 ? sq : t_base + t; };
 
     if (warp == 0) {
         // ================= TMA producer: x_t K-halves (128 rows: both half-jobs) into the ring =================
@@ -216,8 +220,8 @@ using namespace dprnn;
 
 // Same arguments and results as dprnn_lstm_layer_bf16, except the weight packing: w_packed rows for direction d, CTA
 // rank r and MMA nh are {[W_ih | W_hh][gate*H + 64*nh + 32*r + u] : gate = 0..3, u < 32} (Engine._pack_lstm_tc(half_jobs=True)).
-extern "C" int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B,
-                                        int S, int K, int inter, int hidden, int ndir, int fast_act, void* stream) {
+static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
+                        int inter, int hidden, int ndir, int fast_act, const int2* jobs, int n_jobs, void* stream) {
     DPRNN_CHECK_ARG(x && w_packed && bias_perm && hout && B > 0 && S > 0 && K > 0);
     DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2));
     DPRNN_CHECK_ARG(((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)hout) % 16 == 0);
@@ -242,7 +246,12 @@ extern "C" int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, con
         box[1] = 128; boxh[1] = 64;
         p.T = S; p.seq_dim = 1; p.tiles_per_outer = (K + 255) / 256;
         njobs = (long)p.tiles_per_outer * B * ndir;
+        if (jobs) {        // ragged: B == 1, S = total chunks of the packed batch, one pair-job per utterance and direction
+            DPRNN_CHECK_ARG(B == 1 && K <= 256 && n_jobs > 0);
+            njobs = (long)n_jobs * ndir;
+        }
     }
+    p.jobs = jobs;
     for (int i = 0; i < 4; ++i) dH[i] = dX[i];
     dH[0] = (uint64_t)ndir * 128;
     if (make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dX, sX, box)) return 1;
@@ -256,4 +265,18 @@ extern "C" int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, con
     kern<<<(unsigned)(njobs * 2), 384, PP_SM_TOTAL, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);
     DPRNN_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B,
+                                        int S, int K, int inter, int hidden, int ndir, int fast_act, void* stream) {
+    return lstm_pp_impl(x, w_packed, bias_perm, hout, B, S, K, inter, hidden, ndir, fast_act, nullptr, 0, stream);
+}
+
+// dprnn_lstm_inter_bf16_ragged with the half-job kernel (same arguments; half-job weight packing).
+extern "C" int dprnn_lstm_inter_bf16_ragged_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout,
+                                               long total_chunks, int K, const void* utt_jobs, int n_utt, int hidden,
+                                               int ndir, int fast_act, void* stream) {
+    DPRNN_CHECK_ARG(utt_jobs && n_utt > 0 && total_chunks > 0 && total_chunks < (1L << 31));
+    return lstm_pp_impl(x, w_packed, bias_perm, hout, 1, (int)total_chunks, K, 1, hidden, ndir, fast_act,
+                        (const int2*)utt_jobs, n_utt, stream);
 }

@@ -272,11 +272,13 @@ class RaggedMixin:
                 mr2 = torch.empty((B, 2), device=dev)
                 if bf16:
                     hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
+                    pp = '_pp' if self.lstm_pingpong else ''          # half-job ping-pong kernels (bit-identical)
+                    wk = hw['tc_w2'] if self.lstm_pingpong else hw['tc_w']
                     if which == 0:      # every chunk is one length-K sequence: the packed chunk space is a uniform batch
-                        L_.call('dprnn_lstm_layer_bf16', xb, hw['tc_w'], hw['tc_bias'], hb, 1, TC, K, 0, H, nd,
+                        L_.call('dprnn_lstm_layer_bf16' + pp, xb, wk, hw['tc_bias'], hb, 1, TC, K, 0, H, nd,
                                 int(self.fast_act), st)
                     else:               # one pair-job per utterance and direction, S_b steps each
-                        L_.call('dprnn_lstm_inter_bf16_ragged', xb, hw['tc_w'], hw['tc_bias'], hb, TC, K, lay.jobs, B,
+                        L_.call('dprnn_lstm_inter_bf16_ragged' + pp, xb, wk, hw['tc_bias'], hb, TC, K, lay.jobs, B,
                                 H, nd, int(self.fast_act), st)
                     ybuf = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
                     part = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', rows), device=dev, dtype=torch.uint8)
