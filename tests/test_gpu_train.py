@@ -290,3 +290,33 @@ def test_pit_assignment_and_bss_train_step():
     worst = max(float((dict(model.named_parameters())[n].detach().cpu().double() - leaf.detach()).abs().max())
                 for n, leaf in zip(names, leaves))
     assert worst < 1e-4, worst
+
+
+def test_eval_after_train_step_uses_the_updated_weights():
+    """The fused clip + Adam kernel writes the parameters through raw pointers; the engine's cached weight packs and CUDA
+    graphs must not survive it: an eval forward after a step equals a fresh model loaded from the updated state_dict."""
+    from tss_with_dprnn_b200.train import SpeTrainStep
+    kw = dict(KW)
+    torch.manual_seed(61)
+    model = P.DPRNNSpeTasNet(**kw, fusion_type='film').cuda()
+    g = torch.Generator().manual_seed(62)
+    B, T = 2, 1501
+    mix, ref, tgt = (0.05 * torch.randn(B, T, generator=g).cuda() for _ in range(3))
+    spk = torch.randint(0, 251, (B,), generator=g).cuda()
+    rl = torch.tensor(float(T))
+    model.eval()
+    with torch.no_grad():
+        for _ in range(3):                       # warm the pack cache and capture the graph
+            before, _ = model(mix, ref, rl)
+    stepper = SpeTrainStep(model)
+    for _ in range(2):
+        stepper.step(mix, ref, tgt, spk, ref_len=T)
+    model.eval()
+    with torch.no_grad():
+        after, _ = model(mix, ref, rl)
+    fresh = P.DPRNNSpeTasNet(**kw, fusion_type='film').cuda().eval()
+    fresh.load_state_dict(model.state_dict())
+    with torch.no_grad():
+        want, _ = fresh(mix, ref, rl)
+    assert not torch.equal(after, before)
+    assert torch.equal(after, want)

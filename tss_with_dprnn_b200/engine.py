@@ -48,6 +48,13 @@ class Engine(RaggedMixin):
         self.precision = mode
 
     # ------------------------------------------------------------------ weights
+    def invalidate(self):
+        """Forget the kernel-layout weight copies and the captured graphs: for updates that write the parameters through
+        raw pointers (the fused clip + Adam kernel), which do not bump the tensors' version counters."""
+        self._packed = None
+        self._packed_key = None
+        self._graphs = {}
+
     def _weights_key(self):
         return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
 

@@ -722,6 +722,7 @@ class SpeTrainStep:
         loss3 = self.loss_and_grads(mix, ref, target, spk_idx, ref_len)
         allreduce_mean(self.fp.grad, self.group)
         self.opt.step()
+        self.model._engine.invalidate()       # the update went through raw pointers: cached weight packs are stale
         return loss3
 
     # ---- checkpoints in the reference's format (src/trainers/trainer.py:294-306: {'epoch', 'optimizer', 'model'})
@@ -743,6 +744,7 @@ class SpeTrainStep:
                 raise KeyError(f'checkpoint lacks {sorted(missing)[:3]}...')
             for k, v in own.items():
                 v.copy_(cpt['model'][k])
+        self.model._engine.invalidate()
         self.opt.load_state_dict(cpt['optimizer'])
         return cpt['epoch']
 
