@@ -398,6 +398,9 @@ int dprnn_lstm_recurrence_f32_train(const float* gx, const float* whhT, float* h
 int dprnn_lstm_layer_bf16_train(const void* x, const void* w_packed, const float* bias_perm, void* hout_bf16, void* gates_packed,
                                 float* cstate, float* hout_f32, int B, int S, int K, int inter, int hidden, int ndir,
                                 int fast_act, void* stream);
+int dprnn_lstm_layer_bf16_train_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout_bf16,
+                                   void* gates_packed, float* cstate, float* hout_f32, int B, int S, int K, int inter,
+                                   int hidden, int ndir, int fast_act, void* stream);   /* half-job kernel + packing */
 /* BPTT: dh_out [rows, ndir*H] = gradient of the layer output; whh [ndir][4H][H] (PyTorch layout);
  * dgates [rows, ndir*4H] = gradient of the gate pre-activations of every step (same sequence geometry as forward). */
 int dprnn_lstm_bptt_f32(const float* dh_out, const float* gates, const float* cstate, const float* whh, float* dgates,

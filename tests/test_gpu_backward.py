@@ -173,8 +173,11 @@ def test_lstm_tensor_core_train_forward_saves_what_bptt_needs(inter):
     hb = torch.empty(rows, nd * H, device=DEV, dtype=torch.bfloat16)
     h1, c1 = (torch.full((rows + 1, n), 7.0, device=DEV) for n in (nd * H, nd * H))
     g1p = torch.full((rows + 1, nd * 4 * H), 7.0, device=DEV, dtype=torch.bfloat16)
-    for fast in (0, 1):
-        L.call('dprnn_lstm_layer_bf16_train', xb, wp, bp, hb, g1p, c1, h1, B, S, K, inter, H, nd, fast, st())
+    wp2, _ = Engine._pack_lstm_tc(rnn, sfx, half_jobs=True)
+    for fast, fn, w in ((0, 'dprnn_lstm_layer_bf16_train', wp), (1, 'dprnn_lstm_layer_bf16_train', wp),
+                        (1, 'dprnn_lstm_layer_bf16_train_pp', wp2)):
+        g1p.fill_(7.0); c1.fill_(7.0); h1.fill_(7.0)
+        L.call(fn, xb, w, bp, hb, g1p, c1, h1, B, S, K, inter, H, nd, fast, st())
         g1 = unpack_gates(g1p, nd)
         assert float((g1[:rows] - g0).abs().max()) < 3e-2
         assert float((c1[:rows] - c0).abs().max()) < 5e-2

@@ -22,7 +22,7 @@ constexpr uint32_t PP_SM_TOTAL = SM_BAR + PP_BAR_BYTES;
 static_assert(PP_SM_TOTAL <= 232448, "shared memory budget of one SM (227 KiB)");
 constexpr uint32_t HALF_ROWS = 64 * 128;      // byte offset of rows 64..127 inside a [128 x 128 B] tile
 
-template <bool kFastAct>
+template <bool kFastAct, bool kTrain>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmH64, const float* __restrict__ bias_perm, const LstmTcParams p) {
@@ -158,17 +158,30 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const bool storer = ((e & 3) == 0 && lane == 0);
         const int bar_a = 1 + 2 * j, bar_b = 2 + 2 * j;
         const int sq = seq0 + j * 64;
+        const long seq = (long)seq0 + row;
+        const bool live = kTrain && seq < p.seq_limit;
 
         for (int step = 0; step < T; ++step) {
             const int t = dir ? T - 1 - step : step;
             const uint32_t par = step & 1;
+            uint32_t* gd = nullptr;               // training: gates (packed bf16), c, h (fp32) of this row's 32 + 32 units
+            float *cd = nullptr, *hd = nullptr;
+            if constexpr (kTrain) {
+                if (live) {
+                    const long lr = p.seq_dim == 2 ? seq * p.K + t : ((long)outer * p.S + t) * p.K + seq;
+                    gd = p.gates + (lr * p.ndir + dir) * 256 + ub * 64;       // uint32 units: 16 per 8-unit chunk
+                    cd = p.cst + (lr * p.ndir + dir) * 128 + ub * 32;
+                    hd = p.hf + (lr * p.ndir + dir) * 128 + ub * 32;
+                }
+            }
             // ---------------- unit half 0
             mbar_wait(&d_full[j * 2 + 0], par);
             tc_fence_after();
             uint32_t pk[4][4];
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-                lstm_cell8<kFastAct, false, 32>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g]);
+                lstm_cell8<kFastAct, kTrain, 32>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g],
+                                                 gd ? gd + 16 * g : nullptr, cd + 8 * g, hd + 8 * g);
             tc_fence_before();
             mbar_wait(&h_free[j], par);                // the MMAs that read this half-job's h_{t-1} have completed
             if (storer) bulk_wait_read0();             // ... and so has last step's TMA store of its h rows
@@ -187,7 +200,8 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             tc_fence_after();
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-                lstm_cell8<kFastAct, false, 32>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g, pk[g]);
+                lstm_cell8<kFastAct, kTrain, 32>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g, pk[g],
+                                                 gd ? gd + 128 + 16 * g : nullptr, cd + 64 + 8 * g, hd + 64 + 8 * g);
             tc_fence_before();
             {
                 uint8_t* sH = smem + SM_H + TILE;
@@ -221,7 +235,8 @@ using namespace dprnn;
 // Same arguments and results as dprnn_lstm_layer_bf16, except the weight packing: w_packed rows for direction d, CTA
 // rank r and MMA nh are {[W_ih | W_hh][gate*H + 64*nh + 32*r + u] : gate = 0..3, u < 32} (Engine._pack_lstm_tc(half_jobs=True)).
 static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
-                        int inter, int hidden, int ndir, int fast_act, const int2* jobs, int n_jobs, void* stream) {
+                        int inter, int hidden, int ndir, int fast_act, const int2* jobs, int n_jobs, void* stream,
+                        void* gates = nullptr, float* cstate = nullptr, float* hout_f32 = nullptr) {
     DPRNN_CHECK_ARG(x && w_packed && bias_perm && hout && B > 0 && S > 0 && K > 0);
     DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2));
     DPRNN_CHECK_ARG(((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)hout) % 16 == 0);
@@ -252,6 +267,9 @@ static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_p
         }
     }
     p.jobs = jobs;
+    p.gates = (uint32_t*)gates; p.cst = cstate; p.hf = hout_f32;
+    p.K = K; p.S = S;
+    p.seq_limit = inter ? K : (long)B * S;
     for (int i = 0; i < 4; ++i) dH[i] = dX[i];
     dH[0] = (uint64_t)ndir * 128;
     if (make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dX, sX, box)) return 1;
@@ -259,7 +277,8 @@ static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_p
     const uint64_t dW[2] = {256, (uint64_t)ndir * 512}, sW[2] = {2, 512};
     const uint32_t bW[2] = {64, 128};
     if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dW, sW, bW)) return 1;
-    auto kern = fast_act ? lstm_tc_pp_kernel<true> : lstm_tc_pp_kernel<false>;
+    auto kern = gates ? (fast_act ? lstm_tc_pp_kernel<true, true> : lstm_tc_pp_kernel<false, true>)
+                      : (fast_act ? lstm_tc_pp_kernel<true, false> : lstm_tc_pp_kernel<false, false>);
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP_SM_TOTAL));
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
     kern<<<(unsigned)(njobs * 2), 384, PP_SM_TOTAL, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);
@@ -279,4 +298,14 @@ extern "C" int dprnn_lstm_inter_bf16_ragged_pp(const void* x, const void* w_pack
     DPRNN_CHECK_ARG(utt_jobs && n_utt > 0 && total_chunks > 0 && total_chunks < (1L << 31));
     return lstm_pp_impl(x, w_packed, bias_perm, hout, 1, (int)total_chunks, K, 1, hidden, ndir, fast_act,
                         (const int2*)utt_jobs, n_utt, stream);
+}
+
+// dprnn_lstm_layer_bf16_train with the half-job kernel (half-job weight packing; same saved-state layouts).
+extern "C" int dprnn_lstm_layer_bf16_train_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout_bf16,
+                                              void* gates_packed, float* cstate, float* hout_f32, int B, int S, int K,
+                                              int inter, int hidden, int ndir, int fast_act, void* stream) {
+    DPRNN_CHECK_ARG(gates_packed && cstate && hout_f32);
+    DPRNN_CHECK_ARG(((uintptr_t)gates_packed | (uintptr_t)cstate | (uintptr_t)hout_f32) % 32 == 0);
+    return lstm_pp_impl(x, w_packed, bias_perm, hout_bf16, B, S, K, inter, hidden, ndir, fast_act, nullptr, 0, stream,
+                        gates_packed, cstate, hout_f32);
 }

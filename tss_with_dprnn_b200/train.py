@@ -273,10 +273,11 @@ def forward_train(model, mix, ref=None, div=None):
                 from .engine import Engine
                 xb = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
                 L_.call('dprnn_cast_bf16', xs, xb, rows * F, st)
-                wp, bp = Engine._pack_lstm_tc(rnn, sfx)
+                pp = model._engine.lstm_pingpong                      # half-job ping-pong kernel (same results)
+                wp, bp = Engine._pack_lstm_tc(rnn, sfx, half_jobs=pp)
                 hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
-                L_.call('dprnn_lstm_layer_bf16_train', xb, wp, bp, hb, gates, cst, hout, B, S, K, which, H, nd,
-                        int(model._engine.fast_act), st)
+                L_.call('dprnn_lstm_layer_bf16_train_pp' if pp else 'dprnn_lstm_layer_bf16_train', xb, wp, bp, hb, gates,
+                        cst, hout, B, S, K, which, H, nd, int(model._engine.fast_act), st)
                 del xb, hb
             else:
                 gx = ops.mm(xs, wih, rows, nd * 4 * H, F, bias=b)
