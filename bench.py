@@ -496,6 +496,7 @@ def run_ours(args):
     model.n_streams = args.streams
     model._engine.lstm_slices = args.lstm_slices
     model._engine.lstm_pairs = args.lstm_pairs
+    model._engine.residual_bf16 = bool(args.residual_bf16)
     model._engine.lstm_pingpong = bool(args.lstm_pingpong)
     if args.fused_tail is not None:
         model._engine.fused_tail = bool(args.fused_tail)
@@ -662,6 +663,8 @@ def main():
                     help='time slices per LSTM job of the persistent kernel (1 = one job per CTA pair)')
     ap.add_argument('--lstm-pingpong', type=int, default=int(os.environ.get('DPRNN_LSTM_PINGPONG', '1')),
                     help='1 (default): half-job ping-pong LSTM kernel; 0: one job per CTA pair')
+    ap.add_argument('--residual-bf16', type=int, default=1,
+                    help='bf16 mode: 1 (default) residual stream in bf16 only; 0: fp32 master copy of the residual stream')
     ap.add_argument('--lstm-pairs', type=int, default=int(os.environ.get('DPRNN_LSTM_PAIRS', '0')),
                     help='cap on the resident CTA pairs of the persistent LSTM kernel (0 = all)')
     ap.add_argument('--fused-tail', type=int, default=None, help='1: Linear+norm+residual as one persistent kernel')

@@ -57,6 +57,11 @@ int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const 
 /* Same with y stored in bf16 (the output of dprnn_linear_bf16out_stats); C a multiple of 8. */
 int dprnn_norm_residual_ybf16(const void* y_bf16, float* x, const float* mean_rstd, const float* gamma, const float* beta,
                               int B, long rows_per_utt, int C, void* x_bf16, void* stream);
+/* Opt-in variant with the residual stream kept in bf16 only: x_bf16 <- bf16(float(x_bf16) + norm(y)); when x_f32_out is
+ * given (last half-block) the fp32 result is written there instead, for the fold.  Halves the HBM traffic of the stage at
+ * the price of a bf16 rounding of the residual per half-block (Engine.residual_bf16, off by default). */
+int dprnn_norm_residual_bf16res(const void* y_bf16, void* x_bf16, float* x_f32_out, const float* mean_rstd,
+                                const float* gamma, const float* beta, int B, long rows_per_utt, int C, void* stream);
 
 /* DPRNN._segmentation, src/models/dprnn.py:189-201 (F.unfold, kernel K, pad K, stride P):
  * y [B,L,F] -> x [B,S,K,F], x[b,s,k,:] = y[b, s*P+k-K, :] or 0. S = dprnn_num_chunks(L,K,P). Bit-exact. */
@@ -240,6 +245,9 @@ int dprnn_row_stats_finalize_ragged(const void* stats_partial, const long* row_o
 int dprnn_norm_residual_ragged(const void* y, int y_is_bf16, float* x, const float* mean_rstd, const float* gamma,
                                const float* beta, const int* chunk_utt, long total_chunks, int K, int C, void* x_bf16,
                                void* stream);
+int dprnn_norm_residual_ragged_bf16res(const void* y_bf16, void* x_bf16, float* x_f32_out, const float* mean_rstd,
+                                       const float* gamma, const float* beta, const int* chunk_utt, long total_chunks,
+                                       int K, int C, void* stream);     /* dprnn_norm_residual_bf16res, packed chunk space */
 /* dprnn_unfold / dprnn_fold_prelu between the packed frame and chunk spaces (integer maps bit-exact per utterance). */
 int dprnn_unfold_ragged(const float* y, float* x, const int* chunk_utt, const long* chunk_off, const long* frame_off,
                         const long* L, long total_chunks, int K, int P, int F, void* stream);

@@ -8,8 +8,9 @@ for case in ('spe_cat_r6_3s', 'tasnet_r6_3s', 'spe_att_r2_eval', 'ira_cat_r2_eva
     model = build_from_meta(meta).eval().cuda()
     mix, ref = torch.from_numpy(arr['mix']).cuda(), torch.from_numpy(arr['ref']).cuda()
     want = torch.from_numpy(arr['est'])
-    for prec in ('fp32', 'bf16'):
-        model.precision = prec
+    for prec in ('fp32', 'bf16', 'bf16+residual_bf16'):
+        model.precision = prec.split('+')[0]
+        model._engine.residual_bf16 = prec.endswith('residual_bf16')
         with torch.no_grad():
             est = model(mix) if meta['cls'].endswith('DPRNNTasNet') else model(mix, ref, torch.tensor(float(meta['Tr'])))[0]
         e = est.cpu()

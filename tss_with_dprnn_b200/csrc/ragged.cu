@@ -129,6 +129,38 @@ __global__ void norm_residual_ragged_kernel(const void* __restrict__ yv, float* 
     }
 }
 
+// bf16-residual variant (Engine.residual_bf16; the uniform twin is norm_residual_bf16res_kernel in pointwise.cu - the
+// per-element arithmetic is the same expression, so a packed batch stays bit-identical to per-utterance calls)
+__global__ void norm_residual_ragged_bf16res_kernel(const uint2* __restrict__ y, uint2* __restrict__ xb,
+                                                    float* __restrict__ x_f32, const float* __restrict__ mean_rstd,
+                                                    const float* __restrict__ gamma, const float* __restrict__ beta,
+                                                    const int* __restrict__ chunk_utt, long total4, long chunk4, int c4n) {
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
+        const int b = __ldg(chunk_utt + idx / chunk4);
+        const int c4 = (int)(idx % c4n);
+        const float mean = __ldg(mean_rstd + 2 * b), rstd = __ldg(mean_rstd + 2 * b + 1);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+        const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+        const uint2 yr = __ldg(y + idx);
+        const uint2 xr = xb[idx];
+        const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yr.x));
+        const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yr.y));
+        const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.x));
+        const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.y));
+        float4 r;
+        r.x = x01.x + ((y01.x - mean) * rstd * g.x + be.x);
+        r.y = x01.y + ((y01.y - mean) * rstd * g.y + be.y);
+        r.z = x23.x + ((y23.x - mean) * rstd * g.z + be.z);
+        r.w = x23.y + ((y23.y - mean) * rstd * g.w + be.w);
+        if (x_f32) {
+            reinterpret_cast<float4*>(x_f32)[idx] = r;
+        } else {
+            __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+            xb[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        }
+    }
+}
+
 // ---------------------------------------------------------------- unfold / fold between frame and chunk space
 __global__ void unfold_ragged_kernel(const float* __restrict__ y, float* __restrict__ out,
                                      const int* __restrict__ chunk_utt, const long* __restrict__ chunk_off,
@@ -396,6 +428,17 @@ int dprnn_norm_residual_ragged(const void* y, int y_is_bf16, float* x, const flo
     else
         norm_residual_ragged_kernel<false><<<rgrid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
             y, x, mean_rstd, gamma, beta, chunk_utt, total4, chunk4, C / 4, (uint2*)x_bf16);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_norm_residual_ragged_bf16res(const void* y_bf16, void* x_bf16, float* x_f32_out, const float* mean_rstd,
+                                       const float* gamma, const float* beta, const int* chunk_utt, long total_chunks,
+                                       int K, int C, void* stream) {
+    DPRNN_CHECK_ARG(y_bf16 && x_bf16 && mean_rstd && gamma && beta && chunk_utt && total_chunks > 0 && K > 0 && C % 4 == 0);
+    const long chunk4 = (long)K * (C / 4), total4 = total_chunks * chunk4;
+    norm_residual_ragged_bf16res_kernel<<<rgrid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint2*)y_bf16, (uint2*)x_bf16, x_f32_out, mean_rstd, gamma, beta, chunk_utt, total4, chunk4, C / 4);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

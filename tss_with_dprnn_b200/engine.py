@@ -10,6 +10,8 @@ row stride - see DESIGN.md.
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from ._lib import lib
@@ -29,6 +31,9 @@ class Engine(RaggedMixin):
         self.precision = 'fp32'
         self.lstm_slices = 1           # > 1: time-sliced persistent LSTM kernel (bf16 mode, uniform batches)
         self.lstm_pairs = 0            # > 0: cap on the CTA pairs that kernel keeps resident (0 = all SM pairs)
+        # bf16 mode: the residual stream between the half-blocks lives in bf16 only (what the LSTM consumes anyway); the
+        # fp32 master copy (False / env DPRNN_RESIDUAL_BF16=0) is ~1 dB closer to the reference and ~9 % slower
+        self.residual_bf16 = os.environ.get('DPRNN_RESIDUAL_BF16', '1') == '1'
         self.lstm_pingpong = True      # half-job ping-pong LSTM kernel (bf16 mode, uniform batches; bit-identical results)
         self.fast_act = True       # bf16 mode: tanh.approx-based gate activations (1 MUFU op each)
         self.n_streams = 1         # >1: the batch is split into that many utterance groups on concurrent streams
@@ -469,6 +474,10 @@ class Engine(RaggedMixin):
         blk = self.model.separation.dprnn_blocks[bi]
         g_, b_, _ = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
         last = bi == len(self.model.separation.dprnn_blocks) - 1 and which == 1     # nothing reads the bf16 shadow then
+        if self.residual_bf16:      # opt-in: residual stream in bf16 only; the last half-block writes the fp32 x for the fold
+            lib().call('dprnn_norm_residual_bf16res', s['ybuf'], s['xb'], s['x'] if last else None, s['mr2'], g_, b_,
+                       s['B'], s['S'] * s['K'], s['F'], self._stream())
+            return
         lib().call('dprnn_norm_residual_ybf16', s['ybuf'], s['x'], s['mr2'], g_, b_, s['B'], s['S'] * s['K'], s['F'],
                    None if last else s['xb'], self._stream())
 
@@ -535,7 +544,7 @@ class Engine(RaggedMixin):
         if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
         key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
-               self.fast_act, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self._weights_key())
+               self.fast_act, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self._weights_key())
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = 'seen'

@@ -283,7 +283,12 @@ class RaggedMixin:
                     ybuf = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
                     part = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', rows), device=dev, dtype=torch.uint8)
                     self._linear_stats_ragged(hb, hw, ybuf, rows, nd * H, part, lay, eps, mr2)
-                    L_.call('dprnn_norm_residual_ragged', ybuf, 1, x, mr2, g_, b_, lay.chunk_utt, TC, K, F, xb, st)
+                    if self.residual_bf16:      # opt-in bf16 residual stream (same arithmetic as the uniform path)
+                        last = blk is sep.dprnn_blocks[len(sep.dprnn_blocks) - 1] and which == 1
+                        L_.call('dprnn_norm_residual_ragged_bf16res', ybuf, xb, x if last else None, mr2, g_, b_,
+                                lay.chunk_utt, TC, K, F, st)
+                    else:
+                        L_.call('dprnn_norm_residual_ragged', ybuf, 1, x, mr2, g_, b_, lay.chunk_utt, TC, K, F, xb, st)
                     del hb, ybuf
                     continue
                 gx = self.gemm(x, hw['wih_t'], rows, nd * 4 * H, F, bias=hw['bias'])
