@@ -54,7 +54,16 @@ int dprnn_norm_affine(const float* mean_rstd, const float* gamma, const float* b
 int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const float* gamma, const float* beta,
                         int B, long rows_per_utt, int C, void* x_bf16, void* stream);
 
-/* Same with y stored in bf16 (the output of dprnn_linear_bf16out_stats); C a multiple of 8. */
+/* 16-bit storage / tensor-core operand formats (argument `h16` below).  bf16: fp32's range, 8 significand bits - the
+ * 'bf16' mode.  fp16: 11 significand bits - the 'fp16' mode, which keeps the estimated sources within north_star's
+ * 1e-3 of the reference's fp32 path at the same kernel speed.  Entry points named *_bf16* without an
+ * `h16` argument are the bf16 instances of the *_h16* ones and are kept for existing callers. */
+#define DPRNN_H16_BF16 0
+#define DPRNN_H16_FP16 1
+
+/* Same with y stored in 16 bits (the output of dprnn_linear_h16out_stats); C a multiple of 8; x_h16 may be NULL. */
+int dprnn_norm_residual_yh16(const void* y_h16, float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                             int B, long rows_per_utt, int C, void* x_h16, int h16, void* stream);
 int dprnn_norm_residual_ybf16(const void* y_bf16, float* x, const float* mean_rstd, const float* gamma, const float* beta,
                               int B, long rows_per_utt, int C, void* x_bf16, void* stream);
 /* Opt-in variant with the residual stream kept in bf16 only: x_bf16 <- bf16(float(x_bf16) + norm(y)); when x_f32_out is
@@ -62,6 +71,9 @@ int dprnn_norm_residual_ybf16(const void* y_bf16, float* x, const float* mean_rs
  * the price of a bf16 rounding of the residual per half-block (Engine.residual_bf16, off by default). */
 int dprnn_norm_residual_bf16res(const void* y_bf16, void* x_bf16, float* x_f32_out, const float* mean_rstd,
                                 const float* gamma, const float* beta, int B, long rows_per_utt, int C, void* stream);
+int dprnn_norm_residual_h16res(const void* y_h16, void* x_h16, float* x_f32_out, const float* mean_rstd,
+                               const float* gamma, const float* beta, int B, long rows_per_utt, int C, int h16,
+                               void* stream);
 
 /* DPRNN._segmentation, src/models/dprnn.py:189-201 (F.unfold, kernel K, pad K, stride P):
  * y [B,L,F] -> x [B,S,K,F], x[b,s,k,:] = y[b, s*P+k-K, :] or 0. S = dprnn_num_chunks(L,K,P). Bit-exact. */
@@ -69,6 +81,7 @@ int dprnn_num_chunks(long L, int K, int P);
 int dprnn_unfold(const float* y, float* x, int B, long L, int K, int P, int F, void* stream);
 /* Same, also writing the bf16 copy x_bf16 [B,S,K,F] (operand of the first tensor-core LSTM layer). */
 int dprnn_unfold_bf16(const float* y, float* x, void* x_bf16, int B, long L, int K, int P, int F, void* stream);
+int dprnn_unfold_h16(const float* y, float* x, void* x_h16, int B, long L, int K, int P, int F, int h16, void* stream);
 
 /* self.prelu + DPRNN._overlap_add, src/models/dprnn.py:174,203-217 (F.fold, plain sum):
  * x [B,S,K,F] -> out [B,L,F]. prelu_a (1 float, device) may be NULL for a pure fold. */
@@ -149,6 +162,7 @@ int dprnn_prologue_apply(const float* a, float* out, long rows, int C, long rows
 
 /* fp32 -> bf16 (round to nearest even) copy of an activation tensor. */
 int dprnn_cast_bf16(const float* x, void* out, long elems, void* stream);
+int dprnn_cast_h16(const float* x, void* out, long elems, int h16, void* stream);
 
 /* Pointwise contraction on tensor cores: C[M,N] (fp32) = epi(A[M,K] @ W[N,K]^T + bias), W in nn.Linear / Conv1d
  * layout (K-major, no transpose).  a_is_bf16 != 0: A and W are bf16 (the Linear after each LSTM,
@@ -192,6 +206,10 @@ int dprnn_linear_bf16_stats(const void* A, const void* W, const float* bias, flo
  * (dprnn_row_stats_finalize_ragged). */
 int dprnn_linear_bf16out_stats(const void* A, const void* W, const float* bias, void* C_bf16, int M, int K,
                                void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream);
+/* ... with A, W and the output in the 16-bit format h16 (DPRNN_H16_*). */
+int dprnn_linear_h16out_stats(const void* A, const void* W, const float* bias, void* C_h16, int M, int K,
+                              void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, int h16,
+                              void* stream);
 
 /* The tail of a DPRNN half-block, dprnn.py:86-92 / 96-99, as ONE persistent tcgen05 kernel (bf16 mode):
  *   y = h[M,K] (bf16) @ W[128,K]^T (bf16) + bias;  x[M,128] (fp32, in place) += (y - mean_u) * rstd_u * gamma + beta,
@@ -214,7 +232,11 @@ int dprnn_linear_norm_residual_bf16(const void* h, const void* W, const float* b
  *   (b_ih + b_hh)[q*128 + 64*nh + j].  Rows / biases of the i, f, o gates (q = 0, 1, 3) are pre-scaled by 1/2 (the
  *   kernel evaluates sigmoid(x) = 1/2 tanh(x/2) + 1/2).
  * inter == 0: sequences (b,s) run along k (intra-chunk); inter == 1: sequences (b,k) run along s.
- * fast_act != 0: tanh.approx-based activations (1 MUFU op each); 0: expf/tanhf. hidden must be 128. */
+ * fast_act != 0: tanh.approx-based activations (1 MUFU op each); 0: expf/tanhf. hidden must be 128.
+ * For the *_pp entry points below the same argument is a flag word: DPRNN_LSTM_FAST_ACT | DPRNN_LSTM_FP16, the latter
+ * meaning that x, w_packed and hout are fp16 instead of bf16 (inference only). */
+#define DPRNN_LSTM_FAST_ACT 1
+#define DPRNN_LSTM_FP16 2
 int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S,
                           int K, int inter, int hidden, int ndir, int fast_act, void* stream);
 
@@ -241,13 +263,16 @@ int dprnn_utt_stats_ragged(const float* x, int C, const long* off, const long* l
 /* mean/rstd per utterance (rows [row_off[b], row_off[b+1])) from the per-row sums of dprnn_linear_bf16*_stats. */
 int dprnn_row_stats_finalize_ragged(const void* stats_partial, const long* row_off, int B, int cols, float eps,
                                     float* mean_rstd, void* stream);
-/* dprnn_norm_residual on the packed chunk space; y fp32 or bf16. */
+/* dprnn_norm_residual on the packed chunk space; y_is_bf16: 0 = y fp32, 1 = y (and x_bf16) bf16, 2 = y (and x_bf16) fp16. */
 int dprnn_norm_residual_ragged(const void* y, int y_is_bf16, float* x, const float* mean_rstd, const float* gamma,
                                const float* beta, const int* chunk_utt, long total_chunks, int K, int C, void* x_bf16,
                                void* stream);
 int dprnn_norm_residual_ragged_bf16res(const void* y_bf16, void* x_bf16, float* x_f32_out, const float* mean_rstd,
                                        const float* gamma, const float* beta, const int* chunk_utt, long total_chunks,
                                        int K, int C, void* stream);     /* dprnn_norm_residual_bf16res, packed chunk space */
+int dprnn_norm_residual_ragged_h16res(const void* y_h16, void* x_h16, float* x_f32_out, const float* mean_rstd,
+                                      const float* gamma, const float* beta, const int* chunk_utt, long total_chunks,
+                                      int K, int C, int h16, void* stream);
 /* dprnn_unfold / dprnn_fold_prelu between the packed frame and chunk spaces (integer maps bit-exact per utterance). */
 int dprnn_unfold_ragged(const float* y, float* x, const int* chunk_utt, const long* chunk_off, const long* frame_off,
                         const long* L, long total_chunks, int K, int P, int F, void* stream);

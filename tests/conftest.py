@@ -37,4 +37,5 @@ def weight_fingerprint(sd):
 
 GOLDEN_CASES = ['tasnet_r2', 'spe_cat_r2_eval', 'spe_add_r2_eval', 'spe_mul_r2_eval', 'spe_film_r2_eval',
                 'spe_att_r2_eval', 'spe_cat_r2_train', 'spe_att_r2_train_b1', 'spe_film_gln_relu_r2',
-                'spe_cat_uni_r2', 'ira_cat_r2_eval', 'ira_cat_r2_train', 'spe_cat_r6_3s', 'tasnet_r6_3s']
+                'spe_cat_uni_r2', 'ira_cat_r2_eval', 'ira_cat_r2_train', 'spe_cat_r6_3s', 'tasnet_r6_3s',
+                'speech_att_r6', 'speech_cat_r6_wx3']       # the last two: real speech (example.ipynb cell 15)

@@ -128,10 +128,12 @@ def test_rejects_cpu_tensors_and_grad_training():
 # (a) SI-SDR of our bf16 output against the reference fp32 output, (b) the change of SI-SDR towards a synthetic target
 # placed so that the fp32 output scores ~13 dB (the published operating point).
 # ---------------------------------------------------------------------------------------------------------
-def _bf16_vs_fp32(case, fast_act=True):
+def _bf16_vs_fp32(case, fast_act=True, precision='bf16', residual16=None):
     meta, arr = load_golden(case)
     model = build_from_meta(meta).cuda()
-    model.precision = 'bf16'
+    model.precision = precision
+    if residual16 is not None:
+        model._engine.residual_bf16 = residual16
     model._engine.fast_act = fast_act
     mix, ref = torch.from_numpy(arr['mix']).cuda(), torch.from_numpy(arr['ref']).cuda()
     with torch.no_grad():
@@ -143,14 +145,22 @@ def _bf16_vs_fp32(case, fast_act=True):
     return est, want
 
 
-@pytest.mark.parametrize('case', ['spe_cat_r6_3s', 'tasnet_r6_3s', 'spe_att_r2_eval', 'ira_cat_r2_eval', 'spe_cat_uni_r2'])
+@pytest.mark.parametrize('case', ['spe_cat_r6_3s', 'tasnet_r6_3s', 'spe_att_r2_eval', 'ira_cat_r2_eval', 'spe_cat_uni_r2',
+                                  'speech_att_r6', 'speech_cat_r6_wx3'])
 @pytest.mark.parametrize('fast_act', [True, False])
 def test_bf16_mode_sisdr(case, fast_act):
     est, want = _bf16_vs_fp32(case, fast_act)
     assert torch.isfinite(est).all()
     sdr_vs_ref = O.si_sdr_db(est, want)
-    assert sdr_vs_ref.min() > 35.0, sdr_vs_ref                 # bf16 output within -35 dB of the fp32 reference output
-    assert O.peak_rel_err(est, want) < 3e-2
+    if case in SATURATED:       # gates in saturation: emulated 39.5 dB / 1.4e-2 (tools/emulate_precision.py --wscale 3)
+        assert sdr_vs_ref.min() > 33.0, sdr_vs_ref
+        assert O.peak_rel_err(est, want) < 4e-2
+        return
+    # measured (profiles/r1_accuracy_report.txt): 51-53 dB / 3.2e-3 on the full-depth fixtures, 67-68 dB / 8e-4 on the
+    # 2-block ones; thresholds = measured - 5 dB (a regression of the operand handling shows up as >= 6 dB)
+    deep = '_r6' in case
+    assert sdr_vs_ref.min() > (46.0 if deep else 60.0), sdr_vs_ref
+    assert O.peak_rel_err(est, want) < (6e-3 if deep else 2e-3)
     g = torch.Generator().manual_seed(77)
     noise = torch.randn(want.shape, generator=g)
     noise = noise * (want.pow(2).sum(-1, keepdim=True) / noise.pow(2).sum(-1, keepdim=True) / 10 ** 1.3).sqrt()
@@ -159,7 +169,66 @@ def test_bf16_mode_sisdr(case, fast_act):
     assert delta.max() < 0.05, delta
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+SATURATED = {'speech_cat_r6_wx3'}
+TOL_NORTH_STAR = 1e-3     # north_star: estimated sources within a max relative (peak-normalised) error of 1e-3
+
+
+@pytest.mark.parametrize('case', GOLDEN_CASES)
+@pytest.mark.parametrize('fast_act', [True, False])
+def test_fp16_mode_meets_1e3(case, fast_act):
+    """The tensor-core mode that meets north_star's floating-point tolerance: fp16 operands (11 significand bits) on the
+    same tcgen05 kernels as the bf16 mode, 16-bit residual stream included.  Every reference fixture (both full-depth
+    3-s ones, every 2-block one, train-mode BatchNorm ones) must be within 1e-3 peak-normalised."""
+    est, want = _bf16_vs_fp32(case, fast_act, precision='fp16')
+    assert torch.isfinite(est).all()
+    err = O.peak_rel_err(est, want)
+    if case in SATURATED:
+        # LSTM weights x3 (gates in saturation): the network amplifies ANY perturbation ~6x more than at its default
+        # init - TF32 1x1 convs alone give 1.4e-3, tanh.approx alone 9e-4 (tools/emulate_precision.py --wscale 3) - so
+        # only the exact fp32 mode holds 1e-3 there (test_cuda_matches_reference_fixture); fp16 is held to its emulated
+        # 2.6e-3 + margin, bf16 lands at 1.4e-2
+        assert err < 5e-3, err
+        assert O.si_sdr_db(est, want).min() > 50.0
+        return
+    assert err < TOL_NORTH_STAR, err
+    assert O.si_sdr_db(est, want).min() > 60.0
+
+
+@pytest.mark.parametrize('case', ['spe_cat_r6_3s', 'tasnet_r6_3s'])
+def test_fp16_mode_fp32_master(case):
+    """fp16 operands with the fp32 master copy of the residual stream (Engine.residual_bf16 = False)."""
+    est, want = _bf16_vs_fp32(case, True, precision='fp16', residual16=False)
+    assert O.peak_rel_err(est, want) < TOL_NORTH_STAR
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+def test_cfg2_batch64_streams_graph_equals_b1(precision):
+    """Parity AT the benchmarked configuration: B = 64 x 3 s, full depth, 3 utterance groups on concurrent streams,
+    CUDA-graph replay - every utterance must equal its own B = 1 forward bit for bit, and utterance 0 (the fixture's
+    mixture / reference) must agree with the reference fixture as the B = 1 tests require."""
+    meta, arr = load_golden('spe_cat_r6_3s')
+    model = build_from_meta(meta).eval().cuda()
+    model.precision = precision
+    g = torch.Generator().manual_seed(64)
+    mix, ref = 0.05 * torch.randn(64, 24000, generator=g), 0.05 * torch.randn(64, 24000, generator=g)
+    mix[0], ref[0] = torch.from_numpy(arr['mix'][0]), torch.from_numpy(arr['ref'][0])
+    mix, ref, rl = mix.cuda(), ref.cuda(), torch.tensor(24000.)
+    with torch.no_grad():
+        model.n_streams = 3
+        outs = [model(mix, ref, rl) for _ in range(3)]        # eager, capture, replay
+        torch.cuda.synchronize()
+        for e, l in outs[1:]:
+            assert torch.equal(e, outs[0][0]) and torch.equal(l, outs[0][1])
+        est, logits = outs[2]
+        model.n_streams = 1
+        for b in (0, 1, 21, 22, 42, 63):                      # first / last utterances of every stream group
+            e1, l1 = model(mix[b:b + 1], ref[b:b + 1], rl)
+            assert torch.equal(e1[0], est[b]) and torch.equal(l1[0], logits[b]), b
+    err = O.peak_rel_err(est[:1].cpu(), torch.from_numpy(arr['est']))
+    assert err < (TOL_NORTH_STAR if precision == 'fp16' else 6e-3), err
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'fp16'])
 def test_stream_groups_bit_exact(precision):
     """Splitting the batch over concurrent streams inside forward must not change a single bit."""
     torch.manual_seed(6)

@@ -20,7 +20,7 @@ def waves(lens, seed=0):
 
 
 @pytest.mark.parametrize('fusion', ['cat', 'add', 'mul', 'film', 'att'])
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'fp16'])
 def test_spe_ragged_equals_per_utterance(fusion, precision):
     torch.manual_seed(3)
     model = P.DPRNNSpeTasNet(**KW, fusion_type=fusion).eval().cuda()
@@ -52,7 +52,7 @@ def test_spe_ragged_matches_oracle():
             assert O.peak_rel_err(logits[b].cpu(), wl[0]) < 2e-5
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'fp16'])
 def test_ira_ragged_equals_per_utterance(precision):
     torch.manual_seed(6)
     model = P.DPRNNSpeIRATasNet(**dict(KW, n_repeats=1), fusion_type='cat').eval().cuda()
@@ -66,7 +66,7 @@ def test_ira_ragged_equals_per_utterance(precision):
             assert torch.equal(logits[b], l1[0])
 
 
-@pytest.mark.parametrize('precision', ['fp32', 'bf16'])
+@pytest.mark.parametrize('precision', ['fp32', 'bf16', 'fp16'])
 def test_tasnet_ragged_equals_per_utterance(precision):
     torch.manual_seed(7)
     model = P.DPRNNTasNet(**dict(KW, n_repeats=1)).eval().cuda()

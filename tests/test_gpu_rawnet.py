@@ -29,15 +29,21 @@ def test_rawnet_matches_reference_fixture_fp32():
     assert O.peak_rel_err(logits.cpu(), torch.from_numpy(arr['logits'])) < 2e-4
 
 
-def test_rawnet_bf16_mode_close():
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+def test_rawnet_bf16_mode_close(precision):
     meta, arr = load_golden('rawnet_att_r1_eval')
     model = build(meta).cuda()
-    model.precision = 'bf16'
+    model.precision = precision
     mix, ref = torch.from_numpy(arr['mix']).cuda(), torch.from_numpy(arr['ref']).cuda()
     with torch.no_grad():
         est, _ = model(mix, ref)
     want = torch.from_numpy(arr['est'])
-    assert O.si_sdr_db(est.cpu(), want).min() > 30.0
+    sdr = float(O.si_sdr_db(est.cpu(), want).min())
+    print(f'rawnet {precision}: SI-SDR vs reference fixture {sdr:.1f} dB, peak-normalised {O.peak_rel_err(est.cpu(), want):.2e}')
+    assert sdr > RAWNET_SDR_FLOOR[precision]
+
+
+RAWNET_SDR_FLOOR = {'bf16': 30.0, 'fp16': 30.0}      # measured - 5 dB (see profiles/r2_accuracy_report.txt)
 
 
 def test_rawnet_rejects_cpu_and_train():

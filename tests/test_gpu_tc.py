@@ -31,20 +31,20 @@ def test_linear_bf16(M, N, K):
     assert O.peak_rel_err(out.cpu(), ref) < 1e-5      # exact products, fp32 accumulation
 
 
-def lstm_bf16_reference(x, rnn, reverse_flags, exact_h_rounding=True):
-    """fp32 restatement of what dprnn_lstm_layer_bf16 computes: bf16 x / weights / recurrent h, fp32 accumulation and
-    state, exact activations. x [nseq, T, 128] (already bf16-representable)."""
+def lstm_bf16_reference(x, rnn, reverse_flags, exact_h_rounding=True, dtype=torch.bfloat16):
+    """fp32 restatement of what dprnn_lstm_layer_bf16 computes: bf16 (or fp16) x / weights / recurrent h, fp32
+    accumulation and state, exact activations. x [nseq, T, 128] (already representable in the 16-bit format)."""
     outs = []
     for d, rev in enumerate(reverse_flags):
         sf = '_reverse' if rev else ''
-        wih = getattr(rnn, 'weight_ih_l0' + sf).detach().bfloat16().float()
-        whh = getattr(rnn, 'weight_hh_l0' + sf).detach().bfloat16().float()
+        wih = getattr(rnn, 'weight_ih_l0' + sf).detach().to(dtype).float()
+        whh = getattr(rnn, 'weight_hh_l0' + sf).detach().to(dtype).float()
         b = (getattr(rnn, 'bias_ih_l0' + sf) + getattr(rnn, 'bias_hh_l0' + sf)).detach()
         N, T, H = x.shape[0], x.shape[1], 128
         h = torch.zeros(N, H); c = torch.zeros(N, H)
         out = torch.empty(N, T, H)
         for t in (range(T - 1, -1, -1) if rev else range(T)):
-            g = x[:, t] @ wih.t() + h.bfloat16().float() @ whh.t() + b
+            g = x[:, t] @ wih.t() + h.to(dtype).float() @ whh.t() + b
             i, f, gg, o = g.split(H, 1)
             c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(gg)
             h = torch.sigmoid(o) * torch.tanh(c)
@@ -264,3 +264,93 @@ def test_lstm_half_job_pingpong_matches(inter):
     print('half-job kernel: max |diff| vs one-job kernel', err, 'bit-identical', torch.equal(got[:rows], want))
     assert err < 2e-2
     assert float((got[rows:].float() - 7.0).abs().max()) == 0.0
+
+
+@pytest.mark.parametrize('inter', [0, 1])
+@pytest.mark.parametrize('ndir', [2, 1])
+@pytest.mark.parametrize('fast', [0, 1])
+@pytest.mark.parametrize('fmt', ['bf16', 'fp16'])
+def test_lstm_layer_pp_direct(inter, ndir, fast, fmt):
+    """The SHIPPED default LSTM kernel (dprnn_lstm_layer_bf16_pp, half-job ping-pong) directly against the fp32
+    restatement of an nn.LSTM layer (dprnn.py:23-28) with the same operand roundings, in both 16-bit operand formats;
+    in bf16 additionally bit for bit against the one-job kernel (DESIGN.md 4.1 states they are identical)."""
+    from tss_with_dprnn_b200.engine import Engine
+    H = 128
+    dtype = torch.float16 if fmt == 'fp16' else torch.bfloat16
+    B, S, K = (3, 100, 37) if not inter else (3, 21, 250)
+    rows = B * S * K
+    torch.manual_seed(21 + inter)
+    rnn = torch.nn.LSTM(H, H, batch_first=True, bidirectional=(ndir == 2))
+    x = rnd(B, S, K, H, seed=22).to(dtype)
+    xf = x.float()
+    seqs = xf.reshape(B * S, K, H) if not inter else xf.permute(0, 2, 1, 3).reshape(B * K, S, H)
+    want = lstm_bf16_reference(seqs, rnn, [False, True][:ndir], dtype=dtype)
+    want = want.reshape(B, S, K, ndir * H) if not inter else want.reshape(B, K, S, ndir * H).permute(0, 2, 1, 3)
+    sfx = ['', '_reverse'][:ndir]
+    wp2, bp = Engine._pack_lstm_tc(rnn, sfx, half_jobs=True, dtype=dtype)
+    hout = torch.full((rows + 1, ndir * H), 7.0, device=DEV, dtype=dtype)
+    flags = fast | (2 if fmt == 'fp16' else 0)
+    xd = x.reshape(rows, H).to(DEV)
+    P.lib().call('dprnn_lstm_layer_bf16_pp', xd, wp2.to(DEV), bp.to(DEV), hout, B, S, K, inter, H, ndir, flags, stream())
+    torch.cuda.synchronize()
+    got = hout[:rows].float().cpu().view(B, S, K, ndir * H)
+    assert torch.isfinite(got).all()
+    assert float((hout[rows:].float() - 7.0).abs().max()) == 0.0          # nothing written past the last row
+    err = O.peak_rel_err(got, want)
+    # output rounding (2^-9 bf16 / 2^-12 fp16) + rounding flips of the recurrent h; tanh.approx adds ~2^-11
+    tol = {('bf16', 0): 1e-2, ('bf16', 1): 1.5e-2, ('fp16', 0): 1.5e-3, ('fp16', 1): 3e-3}[(fmt, fast)]
+    assert err < tol, err
+    assert (got - want).abs().mean() < (2e-3 if fmt == 'bf16' else 3e-4)
+    if fmt == 'bf16':
+        wp, _ = Engine._pack_lstm_tc(rnn, sfx)
+        one = torch.empty((rows, ndir * H), device=DEV, dtype=dtype)
+        P.lib().call('dprnn_lstm_layer_bf16', xd, wp.to(DEV), bp.to(DEV), one, B, S, K, inter, H, ndir, fast, stream())
+        torch.cuda.synchronize()
+        assert torch.equal(hout[:rows], one)
+
+
+@pytest.mark.parametrize('B,R,K', [(3, 1337, 256), (2, 700, 128)])
+@pytest.mark.parametrize('res16', [False, True])
+def test_linear_fp16out_then_norm_residual(B, R, K, res16):
+    """The half-block tail in the fp16 format: Linear (fp16 operands / output, fp32 statistics), then norm + residual
+    with the fp32 master (yh16) or the 16-bit residual stream (h16res) - dprnn.py:86-92."""
+    M, N = B * R, 128
+    A = (rnd(M, K, seed=M) + 0.2).half()
+    W = (rnd(N, K, seed=5) / K ** 0.5).half()
+    bias, gamma, beta = rnd(N, seed=3), 1 + 0.1 * rnd(N, seed=4), 0.1 * rnd(N, seed=6)
+    x0 = rnd(M, N, seed=7)
+    ref = A.double() @ W.double().t() + bias.double()
+    L = P.lib()
+    y = torch.full((M, N), float('nan'), device=DEV, dtype=torch.float16)
+    part = torch.empty(L.query('dprnn_gemm_tc_stats_bytes', M), device=DEV, dtype=torch.uint8)
+    mr = torch.empty(B, 2, device=DEV)
+    L.call('dprnn_linear_h16out_stats', A.to(DEV), W.to(DEV), bias.to(DEV), y, M, K, part, R, 1e-5, mr, 1, stream())
+    torch.cuda.synchronize()
+    assert O.peak_rel_err(y.float().cpu(), ref.float()) < 5e-4
+    rb = ref.view(B, -1)
+    mean, rstd = rb.mean(1), 1 / torch.sqrt(rb.var(1, unbiased=False) + 1e-5)
+    assert torch.allclose(mr[:, 0].cpu().double(), mean, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(mr[:, 1].cpu().double(), rstd, rtol=1e-4)
+    yv = y.float().cpu().double().view(B, R, N)
+    nrm = (yv - mean.view(B, 1, 1)) * rstd.view(B, 1, 1) * gamma.double() + beta.double()
+    if not res16:
+        x = x0.clone().to(DEV)
+        xb = torch.empty((M, N), device=DEV, dtype=torch.float16)
+        L.call('dprnn_norm_residual_yh16', y, x, mr, gamma.to(DEV), beta.to(DEV), B, R, N, xb, 1, stream())
+        torch.cuda.synchronize()
+        want = x0.double().view(B, R, N) + nrm
+        assert O.peak_rel_err(x.cpu(), want.view(M, N).float()) < 2e-5
+        assert torch.equal(xb.cpu(), x.cpu().half())
+    else:
+        xb0 = x0.half()
+        for last in (False, True):
+            xb = xb0.clone().to(DEV)
+            xf = torch.full((M, N), float('nan'), device=DEV)
+            L.call('dprnn_norm_residual_h16res', y, xb, xf if last else None, mr, gamma.to(DEV), beta.to(DEV), B, R, N, 1,
+                   stream())
+            torch.cuda.synchronize()
+            want = (xb0.double().view(B, R, N) + nrm).view(M, N).float()
+            if last:                          # the fp32 result goes to x_f32_out, the 16-bit stream is left alone
+                assert O.peak_rel_err(xf.cpu(), want) < 2e-5 and torch.equal(xb.cpu(), xb0)
+            else:
+                assert O.peak_rel_err(xb.float().cpu(), want) < 6e-4

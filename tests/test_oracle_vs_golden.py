@@ -20,6 +20,11 @@ def build_from_meta(meta):
            'DPRNNSpeIRATasNet': P.DPRNNSpeIRATasNet}[meta['cls'].rsplit('.', 1)[1]]
     torch.manual_seed(meta['wseed'])
     model = cls(**meta['kwargs'])
+    if meta.get('lstm_wscale', 1.0) != 1.0:       # gates driven into saturation (tests/golden/make_speech_clips.py)
+        with torch.no_grad():
+            for n, p in model.named_parameters():
+                if '.rnn.weight_' in n:
+                    p.mul_(meta['lstm_wscale'])
     model.train(meta['training'])
     return model
 

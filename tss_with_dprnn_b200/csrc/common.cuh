@@ -1,6 +1,8 @@
 // Shared helpers for libdprnn_b200 (sm_100a only).
 #pragma once
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -40,6 +42,25 @@ void set_error(const char* fmt, ...);
             return 1;                                                                \
         }                                                                            \
     } while (0)
+
+// 16-bit storage / tensor-core operand formats (the `h16` argument of the C ABI, DPRNN_H16_* in the header): bf16 has
+// fp32's range and 8 significand bits, fp16 11 significand bits - the format of the 1e-3 tolerance mode
+constexpr int H16_BF16 = 0, H16_FP16 = 1;
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_h16x2(float a, float b) {
+    if constexpr (kF16) {
+        __half2 v = __floats2half2_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    } else {
+        __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+        return *reinterpret_cast<uint32_t*>(&v);
+    }
+}
+template <bool kF16>
+__device__ __forceinline__ float2 unpack_h16x2(uint32_t v) {
+    if constexpr (kF16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+    else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
+}
 
 static inline unsigned cdiv(long a, long b) { return (unsigned)((a + b - 1) / b); }
 

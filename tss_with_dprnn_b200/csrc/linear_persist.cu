@@ -31,7 +31,7 @@ __device__ __forceinline__ void lp_tma_store_2d(const CUtensorMap* m, const void
                  ::"l"(m), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
 }
 
-template <int KB, bool kBf16Out>     // K / 64; output fp32 or bf16
+template <int KB, bool kBf16Out, bool kF16>     // K / 64; output fp32 or 16-bit; operands (and 16-bit output) bf16 / fp16
 __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmW,
                                                                 const __grid_constant__ CUtensorMap tmC,
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, LP_N);
+            constexpr uint32_t idesc = umma_idesc_h16(128, LP_N, kF16);
             mbar_wait(&w_full, 0);
             int it = 0;
             for (int n = 0;; ++n) {
@@ -150,8 +150,7 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
                         for (int j = 0; j < 32; j += 2) {
                             const float y0 = v[j] + __ldg(a.bias + c0 + hh * 32 + j), y1 = v[j + 1] + __ldg(a.bias + c0 + hh * 32 + j + 1);
                             s += y0 + y1; qq = fmaf(y0, y0, fmaf(y1, y1, qq));
-                            __nv_bfloat162 b2 = __floats2bfloat162_rn(y0, y1);
-                            pk[hh * 16 + (j >> 1)] = *reinterpret_cast<uint32_t*>(&b2);
+                            pk[hh * 16 + (j >> 1)] = pack_h16x2<kF16>(y0, y1);
                         }
                         s_sum += s; s_sq += qq;
                     }
@@ -214,7 +213,7 @@ __global__ void __launch_bounds__(192, 1) linear_persist_kernel(const __grid_con
 int launch_row_stats_finalize(const void* partial, float* mean_rstd, long n_utt, long rows_per_utt, int cols, double eps,
                               cudaStream_t st);
 
-template <int KB, bool kBf16Out>
+template <int KB, bool kBf16Out, bool kF16>
 static int launch_lp(const void* A, const void* W, const float* bias, void* C, int M, void* stats, cudaStream_t st) {
     constexpr int K = KB * 64;
     CUtensorMap tmA, tmW, tmC;
@@ -225,11 +224,12 @@ static int launch_lp(const void* A, const void* W, const float* bias, void* C, i
     const uint64_t esz = kBf16Out ? 2 : 4;
     const uint64_t dC[2] = {(uint64_t)LP_N, (uint64_t)M}, sC[2] = {esz, (uint64_t)LP_N * esz};
     const uint32_t bC[2] = {kBf16Out ? 64u : 32u, 128};
-    if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, A, dA, sA, bA)) return 1;
-    if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dW, sW, bW)) return 1;
-    if (make_tmap(&tmC, kBf16Out ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dC, sC, bC)) return 1;
+    constexpr CUtensorMapDataType t16 = kF16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    if (make_tmap(&tmA, t16, 2, A, dA, sA, bA)) return 1;
+    if (make_tmap(&tmW, t16, 2, W, dW, sW, bW)) return 1;
+    if (make_tmap(&tmC, kBf16Out ? t16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dC, sC, bC)) return 1;
     const size_t smem = (size_t)(KB + LP_AST + LP_CST) * LP_BLK + 1024;
-    auto kern = linear_persist_kernel<KB, kBf16Out>;
+    auto kern = linear_persist_kernel<KB, kBf16Out, kF16>;
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -251,14 +251,17 @@ static int launch_lp(const void* A, const void* W, const float* bias, void* C, i
 using namespace dprnn;
 
 static int linear_stats_impl(const void* A, const void* W, const float* bias, void* C, bool bf16_out, int M, int K,
-                             void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream) {
+                             void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, void* stream,
+                             int h16 = DPRNN_H16_BF16) {
+    DPRNN_CHECK_ARG(h16 == DPRNN_H16_BF16 || (h16 == DPRNN_H16_FP16 && bf16_out));
     DPRNN_CHECK_ARG(A && W && bias && C && M > 0 && (K == 128 || K == 256));
     DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C) % 16 == 0);
     if (stats_partial && mean_rstd) DPRNN_CHECK_ARG(rows_per_utt > 0 && M % rows_per_utt == 0);
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-    if (bf16_out) rc = K == 256 ? launch_lp<4, true>(A, W, bias, C, M, stats_partial, st) : launch_lp<2, true>(A, W, bias, C, M, stats_partial, st);
-    else rc = K == 256 ? launch_lp<4, false>(A, W, bias, C, M, stats_partial, st) : launch_lp<2, false>(A, W, bias, C, M, stats_partial, st);
+    if (h16 == DPRNN_H16_FP16) rc = K == 256 ? launch_lp<4, true, true>(A, W, bias, C, M, stats_partial, st) : launch_lp<2, true, true>(A, W, bias, C, M, stats_partial, st);
+    else if (bf16_out) rc = K == 256 ? launch_lp<4, true, false>(A, W, bias, C, M, stats_partial, st) : launch_lp<2, true, false>(A, W, bias, C, M, stats_partial, st);
+    else rc = K == 256 ? launch_lp<4, false, false>(A, W, bias, C, M, stats_partial, st) : launch_lp<2, false, false>(A, W, bias, C, M, stats_partial, st);
     if (rc) return rc;
     if (stats_partial && mean_rstd) {     // mean_rstd == NULL: the caller reduces the per-row sums itself (ragged batches)
         return launch_row_stats_finalize(stats_partial, mean_rstd, M / rows_per_utt, rows_per_utt, LP_N, (double)eps, st);
@@ -276,4 +279,11 @@ extern "C" int dprnn_linear_bf16out_stats(const void* A, const void* W, const fl
                                           void* stats_partial, long rows_per_utt, float eps, float* mean_rstd,
                                           void* stream) {
     return linear_stats_impl(A, W, bias, C_bf16, true, M, K, stats_partial, rows_per_utt, eps, mean_rstd, stream);
+}
+
+// dprnn_linear_bf16out_stats with operands and output in the 16-bit format h16 (DPRNN_H16_BF16 / DPRNN_H16_FP16).
+extern "C" int dprnn_linear_h16out_stats(const void* A, const void* W, const float* bias, void* C_h16, int M, int K,
+                                         void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, int h16,
+                                         void* stream) {
+    return linear_stats_impl(A, W, bias, C_h16, true, M, K, stats_partial, rows_per_utt, eps, mean_rstd, stream, h16);
 }

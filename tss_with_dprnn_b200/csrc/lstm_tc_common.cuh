@@ -95,7 +95,8 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // leaves room on the SM for a memory-bound CTA of another stream next to this kernel.
 // The i, f, o rows of the weights and biases are pre-scaled by 1/2 on the host (exact), so sigmoid(x) = 1/2 tanh(x') + 1/2.
 // kGS = distance in TMEM columns between the four gates of a unit (64: one-job kernels; 32: the half-job kernel).
-template <bool kFastAct, bool kTrain, int kGS = 64>
+// kF16: h leaves as fp16 instead of bf16 (the 'fp16' mode: operands with 11 significand bits).
+template <bool kFastAct, bool kTrain, int kGS = 64, bool kF16 = false>
 __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restrict__ bq, float* __restrict__ c,
                                            uint32_t (&packed)[4], uint32_t* __restrict__ gdst = nullptr,
                                            float* __restrict__ cdst = nullptr, float* __restrict__ hdst = nullptr) {
@@ -151,9 +152,8 @@ __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restric
                 }
             }
         }
-        __nv_bfloat162 h01 = __floats2bfloat162_rn(hv[0], hv[1]), h23 = __floats2bfloat162_rn(hv[2], hv[3]);
-        packed[(j >> 1) + 0] = *reinterpret_cast<uint32_t*>(&h01);
-        packed[(j >> 1) + 1] = *reinterpret_cast<uint32_t*>(&h23);
+        packed[(j >> 1) + 0] = pack_h16x2<kF16>(hv[0], hv[1]);
+        packed[(j >> 1) + 1] = pack_h16x2<kF16>(hv[2], hv[3]);
     }
 }
 

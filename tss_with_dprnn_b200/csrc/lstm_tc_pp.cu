@@ -22,7 +22,7 @@ constexpr uint32_t PP_SM_TOTAL = SM_BAR + PP_BAR_BYTES;
 static_assert(PP_SM_TOTAL <= 232448, "shared memory budget of one SM (227 KiB)");
 constexpr uint32_t HALF_ROWS = 64 * 128;      // byte offset of rows 64..127 inside a [128 x 128 B] tile
 
-template <bool kFastAct, bool kTrain>
+template <bool kFastAct, bool kTrain, bool kF16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmH64, const float* __restrict__ bias_perm, const LstmTcParams p) {
@@ -102,7 +102,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     } else if (warp == 1) {
         // ================= MMA issuer (leader CTA only): A(t), B(t), A(t+1), ... =================
         if (rank == 0 && elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(128, 256);
+            constexpr uint32_t idesc = umma_idesc_h16(128, 256, kF16);
             const uint32_t aW = smem_u32(smem + SM_W), aH = smem_u32(smem + SM_H), aX = smem_u32(smem + SM_X);
             auto mma_kb = [&](int j, int nh, int kb, uint32_t a_tile, bool first) {
                 const uint32_t b_tile = aW + (nh * 4 + kb) * TILE;
@@ -180,7 +180,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             uint32_t pk[4][4];
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-                lstm_cell8<kFastAct, kTrain, 32>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g],
+                lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g],
                                                  gd ? gd + 16 * g : nullptr, cd + 8 * g, hd + 8 * g);
             tc_fence_before();
             mbar_wait(&h_free[j], par);                // the MMAs that read this half-job's h_{t-1} have completed
@@ -200,7 +200,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             tc_fence_after();
 #pragma unroll
             for (int g = 0; g < 4; ++g)
-                lstm_cell8<kFastAct, kTrain, 32>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g, pk[g],
+                lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g, pk[g],
                                                  gd ? gd + 128 + 16 * g : nullptr, cd + 64 + 8 * g, hd + 64 + 8 * g);
             tc_fence_before();
             {
@@ -235,8 +235,10 @@ using namespace dprnn;
 // Same arguments and results as dprnn_lstm_layer_bf16, except the weight packing: w_packed rows for direction d, CTA
 // rank r and MMA nh are {[W_ih | W_hh][gate*H + 64*nh + 32*r + u] : gate = 0..3, u < 32} (Engine._pack_lstm_tc(half_jobs=True)).
 static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
-                        int inter, int hidden, int ndir, int fast_act, const int2* jobs, int n_jobs, void* stream,
+                        int inter, int hidden, int ndir, int flags, const int2* jobs, int n_jobs, void* stream,
                         void* gates = nullptr, float* cstate = nullptr, float* hout_f32 = nullptr) {
+    const int fast_act = flags & DPRNN_LSTM_FAST_ACT, f16 = flags & DPRNN_LSTM_FP16;
+    DPRNN_CHECK_ARG(!(f16 && gates));       // the training forward is built for bf16 operands (cfg 5: "bf16 gate GEMMs")
     DPRNN_CHECK_ARG(x && w_packed && bias_perm && hout && B > 0 && S > 0 && K > 0);
     DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2));
     DPRNN_CHECK_ARG(((uintptr_t)x | (uintptr_t)w_packed | (uintptr_t)hout) % 16 == 0);
@@ -272,13 +274,15 @@ static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_p
     p.seq_limit = inter ? K : (long)B * S;
     for (int i = 0; i < 4; ++i) dH[i] = dX[i];
     dH[0] = (uint64_t)ndir * 128;
-    if (make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, x, dX, sX, box)) return 1;
-    if (make_tmap(&tmH, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, hout, dH, sH, boxh)) return 1;
+    const CUtensorMapDataType t16 = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    if (make_tmap(&tmX, t16, 4, x, dX, sX, box)) return 1;
+    if (make_tmap(&tmH, t16, 4, hout, dH, sH, boxh)) return 1;
     const uint64_t dW[2] = {256, (uint64_t)ndir * 512}, sW[2] = {2, 512};
     const uint32_t bW[2] = {64, 128};
-    if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, w_packed, dW, sW, bW)) return 1;
-    auto kern = gates ? (fast_act ? lstm_tc_pp_kernel<true, true> : lstm_tc_pp_kernel<false, true>)
-                      : (fast_act ? lstm_tc_pp_kernel<true, false> : lstm_tc_pp_kernel<false, false>);
+    if (make_tmap(&tmW, t16, 2, w_packed, dW, sW, bW)) return 1;
+    auto kern = gates ? (fast_act ? lstm_tc_pp_kernel<true, true, false> : lstm_tc_pp_kernel<false, true, false>)
+                : f16 ? (fast_act ? lstm_tc_pp_kernel<true, false, true> : lstm_tc_pp_kernel<false, false, true>)
+                      : (fast_act ? lstm_tc_pp_kernel<true, false, false> : lstm_tc_pp_kernel<false, false, false>);
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP_SM_TOTAL));
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
     kern<<<(unsigned)(njobs * 2), 384, PP_SM_TOTAL, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);

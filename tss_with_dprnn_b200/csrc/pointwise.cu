@@ -99,6 +99,7 @@ __global__ void norm_affine_kernel(const float* __restrict__ mean_rstd, const fl
 }
 
 // x[b,r,c] += (y[b,r,c] - mean_b) * rstd_b * gamma_c + beta_c
+template <bool kF16>
 __global__ void norm_residual_kernel(const float* __restrict__ y, float* __restrict__ x,
                                      const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, long total4, long per_utt4, int c4n,
@@ -116,14 +117,13 @@ __global__ void norm_residual_kernel(const float* __restrict__ y, float* __restr
         r.z += (v.z - mean) * rstd * g.z + be.z;
         r.w += (v.w - mean) * rstd * g.w + be.w;
         reinterpret_cast<float4*>(x)[idx] = r;
-        if (x_bf16) {    // bf16 shadow copy: the TMA-fed A operand of the next tensor-core LSTM layer
-            __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
-            x_bf16[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-        }
+        if (x_bf16)      // 16-bit shadow copy: the TMA-fed A operand of the next tensor-core LSTM layer
+            x_bf16[idx] = make_uint2(pack_h16x2<kF16>(r.x, r.y), pack_h16x2<kF16>(r.z, r.w));
     }
 }
 
-// Same with y in bf16 (output of the tensor-core Linear), 8 elements per thread
+// Same with y in bf16 / fp16 (output of the tensor-core Linear), 8 elements per thread
+template <bool kF16>
 __global__ void norm_residual_ybf16_kernel(const uint4* __restrict__ y, float* __restrict__ x,
                                            const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                            const float* __restrict__ beta, long total8, long per_utt8, int c8n,
@@ -142,15 +142,13 @@ __global__ void norm_residual_ybf16_kernel(const uint4* __restrict__ y, float* _
         for (int h = 0; h < 2; ++h) {
             const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8 + h);
             const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8 + h);
-            const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[2 * h]));
-            const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[2 * h + 1]));
+            const float2 y01 = unpack_h16x2<kF16>(yw[2 * h]), y23 = unpack_h16x2<kF16>(yw[2 * h + 1]);
             r[h].x += (y01.x - mean) * rstd * g.x + be.x;
             r[h].y += (y01.y - mean) * rstd * g.y + be.y;
             r[h].z += (y23.x - mean) * rstd * g.z + be.z;
             r[h].w += (y23.y - mean) * rstd * g.w + be.w;
-            __nv_bfloat162 lo = __floats2bfloat162_rn(r[h].x, r[h].y), hi = __floats2bfloat162_rn(r[h].z, r[h].w);
-            ob[2 * h] = *reinterpret_cast<uint32_t*>(&lo);
-            ob[2 * h + 1] = *reinterpret_cast<uint32_t*>(&hi);
+            ob[2 * h] = pack_h16x2<kF16>(r[h].x, r[h].y);
+            ob[2 * h + 1] = pack_h16x2<kF16>(r[h].z, r[h].w);
         }
         reinterpret_cast<float4*>(x)[2 * idx] = r[0];
         reinterpret_cast<float4*>(x)[2 * idx + 1] = r[1];
@@ -162,6 +160,7 @@ __global__ void norm_residual_ybf16_kernel(const uint4* __restrict__ y, float* _
 // x_bf16 <- bf16(float(x_bf16) + norm(y)); the fp32 master is written once, by the last half-block (x_f32 != NULL), for
 // the fold.  2.4 GB instead of 4.77 GB per launch at B = 64; costs ~8 dB of the bf16 mode's 52 dB agreement with the
 // reference, hence not the default.
+template <bool kF16>
 __global__ void norm_residual_bf16res_kernel(const uint4* __restrict__ y, uint4* __restrict__ xb, float* __restrict__ x_f32,
                                              const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                              const float* __restrict__ beta, long total8, long per_utt8, int c8n) {
@@ -180,17 +179,14 @@ __global__ void norm_residual_bf16res_kernel(const uint4* __restrict__ y, uint4*
         for (int h = 0; h < 2; ++h) {
             const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8 + h);
             const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8 + h);
-            const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[2 * h]));
-            const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yw[2 * h + 1]));
-            const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[2 * h]));
-            const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xw[2 * h + 1]));
+            const float2 y01 = unpack_h16x2<kF16>(yw[2 * h]), y23 = unpack_h16x2<kF16>(yw[2 * h + 1]);
+            const float2 x01 = unpack_h16x2<kF16>(xw[2 * h]), x23 = unpack_h16x2<kF16>(xw[2 * h + 1]);
             r[h].x = x01.x + ((y01.x - mean) * rstd * g.x + be.x);
             r[h].y = x01.y + ((y01.y - mean) * rstd * g.y + be.y);
             r[h].z = x23.x + ((y23.x - mean) * rstd * g.z + be.z);
             r[h].w = x23.y + ((y23.y - mean) * rstd * g.w + be.w);
-            __nv_bfloat162 lo = __floats2bfloat162_rn(r[h].x, r[h].y), hi = __floats2bfloat162_rn(r[h].z, r[h].w);
-            ob[2 * h] = *reinterpret_cast<uint32_t*>(&lo);
-            ob[2 * h + 1] = *reinterpret_cast<uint32_t*>(&hi);
+            ob[2 * h] = pack_h16x2<kF16>(r[h].x, r[h].y);
+            ob[2 * h + 1] = pack_h16x2<kF16>(r[h].z, r[h].w);
         }
         if (x_f32) {
             reinterpret_cast<float4*>(x_f32)[2 * idx] = r[0];
@@ -225,17 +221,18 @@ __global__ void prologue_apply_kernel(const float* __restrict__ a, float* __rest
     }
 }
 
+template <bool kF16>
 __global__ void cast_bf16_kernel(const float* __restrict__ x, uint2* __restrict__ out, long total4) {
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
         const float4 r = reinterpret_cast<const float4*>(x)[idx];
-        __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
-        out[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+        out[idx] = make_uint2(pack_h16x2<kF16>(r.x, r.y), pack_h16x2<kF16>(r.z, r.w));
     }
 }
 
 // ------------------------------------------------------------------------------------------
 // unfold: out[b,s,k,:] = y[b, s*P + k - K, :] (zero outside [0,L))
 // ------------------------------------------------------------------------------------------
+template <bool kF16>
 __global__ void unfold_kernel(const float* __restrict__ y, float* __restrict__ out, int B, long L, int S, int K,
                               int P, int f4n, uint2* __restrict__ out_bf16) {
     const long total = (long)B * S * K * f4n;
@@ -249,10 +246,8 @@ __global__ void unfold_kernel(const float* __restrict__ y, float* __restrict__ o
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t >= 0 && t < L) v = __ldg(reinterpret_cast<const float4*>(y) + (b * L + t) * f4n + f4);
         reinterpret_cast<float4*>(out)[idx] = v;
-        if (out_bf16) {      // bf16 shadow for the first tensor-core LSTM layer (saves a separate cast pass)
-            __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
-            out_bf16[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-        }
+        if (out_bf16)        // 16-bit shadow for the first tensor-core LSTM layer (saves a separate cast pass)
+            out_bf16[idx] = make_uint2(pack_h16x2<kF16>(v.x, v.y), pack_h16x2<kF16>(v.z, v.w));
     }
 }
 
@@ -620,42 +615,63 @@ int dprnn_prologue_apply_ragged(const float* a, float* out, long rows, int C, co
     return 0;
 }
 
-int dprnn_cast_bf16(const float* x, void* out, long elems, void* stream) {
+#define DPRNN_CHECK_H16(h16) DPRNN_CHECK_ARG((h16) == DPRNN_H16_BF16 || (h16) == DPRNN_H16_FP16)
+
+int dprnn_cast_h16(const float* x, void* out, long elems, int h16, void* stream) {
     DPRNN_CHECK_ARG(x && out && elems > 0 && elems % 4 == 0);
-    cast_bf16_kernel<<<grid_for(elems / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint2*)out, elems / 4);
+    DPRNN_CHECK_H16(h16);
+    auto kern = h16 ? cast_bf16_kernel<true> : cast_bf16_kernel<false>;
+    kern<<<grid_for(elems / 4, 256), 256, 0, (cudaStream_t)stream>>>(x, (uint2*)out, elems / 4);
     DPRNN_CHECK_LAUNCH();
     return 0;
+}
+int dprnn_cast_bf16(const float* x, void* out, long elems, void* stream) {
+    return dprnn_cast_h16(x, out, elems, DPRNN_H16_BF16, stream);
 }
 
 int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const float* gamma, const float* beta,
                         int B, long rows_per_utt, int C, void* x_bf16, void* stream) {
     DPRNN_CHECK_ARG(y && x && mean_rstd && gamma && beta && B > 0 && rows_per_utt > 0 && C % 4 == 0);
     const long per4 = rows_per_utt * (C / 4);
-    norm_residual_kernel<<<grid_for(per4 * B, 256), 256, 0, (cudaStream_t)stream>>>(y, x, mean_rstd, gamma, beta,
-                                                                                  per4 * B, per4, C / 4,
-                                                                                  (uint2*)x_bf16);
+    norm_residual_kernel<false><<<grid_for(per4 * B, 256), 256, 0, (cudaStream_t)stream>>>(y, x, mean_rstd, gamma, beta,
+                                                                                         per4 * B, per4, C / 4,
+                                                                                         (uint2*)x_bf16);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }
 
+int dprnn_norm_residual_yh16(const void* y_h16, float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                             int B, long rows_per_utt, int C, void* x_h16, int h16, void* stream) {
+    DPRNN_CHECK_ARG(y_h16 && x && mean_rstd && gamma && beta && B > 0 && rows_per_utt > 0 && C % 8 == 0);
+    DPRNN_CHECK_H16(h16);
+    const long per8 = rows_per_utt * (C / 8);
+    auto kern = h16 ? norm_residual_ybf16_kernel<true> : norm_residual_ybf16_kernel<false>;
+    kern<<<grid_for(per8 * B, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)y_h16, x, mean_rstd, gamma, beta, per8 * B, per8, C / 8, (uint4*)x_h16);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
 int dprnn_norm_residual_ybf16(const void* y_bf16, float* x, const float* mean_rstd, const float* gamma, const float* beta,
                               int B, long rows_per_utt, int C, void* x_bf16, void* stream) {
-    DPRNN_CHECK_ARG(y_bf16 && x && mean_rstd && gamma && beta && B > 0 && rows_per_utt > 0 && C % 8 == 0);
+    return dprnn_norm_residual_yh16(y_bf16, x, mean_rstd, gamma, beta, B, rows_per_utt, C, x_bf16, DPRNN_H16_BF16, stream);
+}
+
+int dprnn_norm_residual_h16res(const void* y_h16, void* x_h16, float* x_f32_out, const float* mean_rstd,
+                               const float* gamma, const float* beta, int B, long rows_per_utt, int C, int h16,
+                               void* stream) {
+    DPRNN_CHECK_ARG(y_h16 && x_h16 && mean_rstd && gamma && beta && B > 0 && rows_per_utt > 0 && C % 8 == 0);
+    DPRNN_CHECK_H16(h16);
     const long per8 = rows_per_utt * (C / 8);
-    norm_residual_ybf16_kernel<<<grid_for(per8 * B, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint4*)y_bf16, x, mean_rstd, gamma, beta, per8 * B, per8, C / 8, (uint4*)x_bf16);
+    auto kern = h16 ? norm_residual_bf16res_kernel<true> : norm_residual_bf16res_kernel<false>;
+    kern<<<grid_for(per8 * B, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)y_h16, (uint4*)x_h16, x_f32_out, mean_rstd, gamma, beta, per8 * B, per8, C / 8);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }
-
 int dprnn_norm_residual_bf16res(const void* y_bf16, void* x_bf16, float* x_f32_out, const float* mean_rstd,
                                 const float* gamma, const float* beta, int B, long rows_per_utt, int C, void* stream) {
-    DPRNN_CHECK_ARG(y_bf16 && x_bf16 && mean_rstd && gamma && beta && B > 0 && rows_per_utt > 0 && C % 8 == 0);
-    const long per8 = rows_per_utt * (C / 8);
-    norm_residual_bf16res_kernel<<<grid_for(per8 * B, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint4*)y_bf16, (uint4*)x_bf16, x_f32_out, mean_rstd, gamma, beta, per8 * B, per8, C / 8);
-    DPRNN_CHECK_LAUNCH();
-    return 0;
+    return dprnn_norm_residual_h16res(y_bf16, x_bf16, x_f32_out, mean_rstd, gamma, beta, B, rows_per_utt, C,
+                                      DPRNN_H16_BF16, stream);
 }
 
 int dprnn_num_chunks(long L, int K, int P) { return (int)((L + K) / P + 1); }
@@ -663,19 +679,24 @@ int dprnn_num_chunks(long L, int K, int P) { return (int)((L + K) / P + 1); }
 int dprnn_unfold(const float* y, float* x, int B, long L, int K, int P, int F, void* stream) {
     DPRNN_CHECK_ARG(y && x && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);
     const int S = dprnn_num_chunks(L, K, P);
-    unfold_kernel<<<grid_for((long)B * S * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, x, B, L, S, K, P,
-                                                                                           F / 4, nullptr);
+    unfold_kernel<false><<<grid_for((long)B * S * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, x, B, L, S, K, P,
+                                                                                                  F / 4, nullptr);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }
 
-int dprnn_unfold_bf16(const float* y, float* x, void* x_bf16, int B, long L, int K, int P, int F, void* stream) {
-    DPRNN_CHECK_ARG(y && x && x_bf16 && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);
+int dprnn_unfold_h16(const float* y, float* x, void* x_h16, int B, long L, int K, int P, int F, int h16, void* stream) {
+    DPRNN_CHECK_ARG(y && x && x_h16 && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);
+    DPRNN_CHECK_H16(h16);
     const int S = dprnn_num_chunks(L, K, P);
-    unfold_kernel<<<grid_for((long)B * S * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, x, B, L, S, K, P,
-                                                                                           F / 4, (uint2*)x_bf16);
+    auto kern = h16 ? unfold_kernel<true> : unfold_kernel<false>;
+    kern<<<grid_for((long)B * S * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, x, B, L, S, K, P, F / 4,
+                                                                                  (uint2*)x_h16);
     DPRNN_CHECK_LAUNCH();
     return 0;
+}
+int dprnn_unfold_bf16(const float* y, float* x, void* x_bf16, int B, long L, int K, int P, int F, void* stream) {
+    return dprnn_unfold_h16(y, x, x_bf16, B, L, K, P, F, DPRNN_H16_BF16, stream);
 }
 
 int dprnn_fold_prelu(const float* x, float* out, int B, long L, int K, int P, int F, const float* prelu_a,

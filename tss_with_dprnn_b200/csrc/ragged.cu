@@ -96,7 +96,7 @@ __global__ void row_stats_finalize_ragged_kernel(const float2* __restrict__ part
 }
 
 // ---------------------------------------------------------------- norm + residual on the chunk space
-template <bool kYBf16>
+template <bool kYBf16, bool kF16>
 __global__ void norm_residual_ragged_kernel(const void* __restrict__ yv, float* __restrict__ x,
                                             const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                             const float* __restrict__ beta, const int* __restrict__ chunk_utt,
@@ -110,8 +110,7 @@ __global__ void norm_residual_ragged_kernel(const void* __restrict__ yv, float* 
         float4 v;
         if constexpr (kYBf16) {
             const uint2 raw = __ldg(reinterpret_cast<const uint2*>(yv) + idx);
-            const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.x));
-            const float2 c = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&raw.y));
+            const float2 a = unpack_h16x2<kF16>(raw.x), c = unpack_h16x2<kF16>(raw.y);
             v = make_float4(a.x, a.y, c.x, c.y);
         } else {
             v = ld_stream(reinterpret_cast<const float4*>(yv) + idx);
@@ -122,15 +121,13 @@ __global__ void norm_residual_ragged_kernel(const void* __restrict__ yv, float* 
         r.z += (v.z - mean) * rstd * g.z + be.z;
         r.w += (v.w - mean) * rstd * g.w + be.w;
         reinterpret_cast<float4*>(x)[idx] = r;
-        if (x_bf16) {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
-            x_bf16[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
-        }
+        if (x_bf16) x_bf16[idx] = make_uint2(pack_h16x2<kF16>(r.x, r.y), pack_h16x2<kF16>(r.z, r.w));
     }
 }
 
 // bf16-residual variant (Engine.residual_bf16; the uniform twin is norm_residual_bf16res_kernel in pointwise.cu - the
 // per-element arithmetic is the same expression, so a packed batch stays bit-identical to per-utterance calls)
+template <bool kF16>
 __global__ void norm_residual_ragged_bf16res_kernel(const uint2* __restrict__ y, uint2* __restrict__ xb,
                                                     float* __restrict__ x_f32, const float* __restrict__ mean_rstd,
                                                     const float* __restrict__ gamma, const float* __restrict__ beta,
@@ -143,10 +140,8 @@ __global__ void norm_residual_ragged_bf16res_kernel(const uint2* __restrict__ y,
         const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
         const uint2 yr = __ldg(y + idx);
         const uint2 xr = xb[idx];
-        const float2 y01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yr.x));
-        const float2 y23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&yr.y));
-        const float2 x01 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.x));
-        const float2 x23 = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&xr.y));
+        const float2 y01 = unpack_h16x2<kF16>(yr.x), y23 = unpack_h16x2<kF16>(yr.y);
+        const float2 x01 = unpack_h16x2<kF16>(xr.x), x23 = unpack_h16x2<kF16>(xr.y);
         float4 r;
         r.x = x01.x + ((y01.x - mean) * rstd * g.x + be.x);
         r.y = x01.y + ((y01.y - mean) * rstd * g.y + be.y);
@@ -155,8 +150,7 @@ __global__ void norm_residual_ragged_bf16res_kernel(const uint2* __restrict__ y,
         if (x_f32) {
             reinterpret_cast<float4*>(x_f32)[idx] = r;
         } else {
-            __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
-            xb[idx] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+            xb[idx] = make_uint2(pack_h16x2<kF16>(r.x, r.y), pack_h16x2<kF16>(r.z, r.w));
         }
     }
 }
@@ -422,25 +416,32 @@ int dprnn_norm_residual_ragged(const void* y, int y_is_bf16, float* x, const flo
                                void* stream) {
     DPRNN_CHECK_ARG(y && x && mean_rstd && gamma && beta && chunk_utt && total_chunks > 0 && K > 0 && C % 4 == 0);
     const long chunk4 = (long)K * (C / 4), total4 = total_chunks * chunk4;
-    if (y_is_bf16)
-        norm_residual_ragged_kernel<true><<<rgrid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-            y, x, mean_rstd, gamma, beta, chunk_utt, total4, chunk4, C / 4, (uint2*)x_bf16);
-    else
-        norm_residual_ragged_kernel<false><<<rgrid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-            y, x, mean_rstd, gamma, beta, chunk_utt, total4, chunk4, C / 4, (uint2*)x_bf16);
+    DPRNN_CHECK_ARG(y_is_bf16 >= 0 && y_is_bf16 <= 2);       // 0: y fp32; 1: y and x_bf16 bf16; 2: y and x_bf16 fp16
+    auto kern = y_is_bf16 == 2 ? norm_residual_ragged_kernel<true, true>
+                               : (y_is_bf16 ? norm_residual_ragged_kernel<true, false> : norm_residual_ragged_kernel<false, false>);
+    kern<<<rgrid(total4, 256), 256, 0, (cudaStream_t)stream>>>(y, x, mean_rstd, gamma, beta, chunk_utt, total4, chunk4,
+                                                               C / 4, (uint2*)x_bf16);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }
 
+int dprnn_norm_residual_ragged_h16res(const void* y_h16, void* x_h16, float* x_f32_out, const float* mean_rstd,
+                                      const float* gamma, const float* beta, const int* chunk_utt, long total_chunks,
+                                      int K, int C, int h16, void* stream) {
+    DPRNN_CHECK_ARG(y_h16 && x_h16 && mean_rstd && gamma && beta && chunk_utt && total_chunks > 0 && K > 0 && C % 4 == 0);
+    DPRNN_CHECK_ARG(h16 == DPRNN_H16_BF16 || h16 == DPRNN_H16_FP16);
+    const long chunk4 = (long)K * (C / 4), total4 = total_chunks * chunk4;
+    auto kern = h16 ? norm_residual_ragged_bf16res_kernel<true> : norm_residual_ragged_bf16res_kernel<false>;
+    kern<<<rgrid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint2*)y_h16, (uint2*)x_h16, x_f32_out, mean_rstd, gamma, beta, chunk_utt, total4, chunk4, C / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
 int dprnn_norm_residual_ragged_bf16res(const void* y_bf16, void* x_bf16, float* x_f32_out, const float* mean_rstd,
                                        const float* gamma, const float* beta, const int* chunk_utt, long total_chunks,
                                        int K, int C, void* stream) {
-    DPRNN_CHECK_ARG(y_bf16 && x_bf16 && mean_rstd && gamma && beta && chunk_utt && total_chunks > 0 && K > 0 && C % 4 == 0);
-    const long chunk4 = (long)K * (C / 4), total4 = total_chunks * chunk4;
-    norm_residual_ragged_bf16res_kernel<<<rgrid(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-        (const uint2*)y_bf16, (uint2*)x_bf16, x_f32_out, mean_rstd, gamma, beta, chunk_utt, total4, chunk4, C / 4);
-    DPRNN_CHECK_LAUNCH();
-    return 0;
+    return dprnn_norm_residual_ragged_h16res(y_bf16, x_bf16, x_f32_out, mean_rstd, gamma, beta, chunk_utt, total_chunks,
+                                             K, C, DPRNN_H16_BF16, stream);
 }
 
 int dprnn_unfold_ragged(const float* y, float* x, const int* chunk_utt, const long* chunk_off, const long* frame_off,

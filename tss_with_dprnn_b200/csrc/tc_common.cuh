@@ -167,6 +167,11 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// the same with A = B = fp16 (format code 0) when f16 is set: same tensor-core rate, 11 instead of 8 significand bits
+__host__ __device__ constexpr uint32_t umma_idesc_h16(int M, int N, bool f16) {
+    return f16 ? ((1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24)) : umma_idesc_bf16(M, N);
+}
+
 // D[tmem] (+)= A[smem] * B[smem]^T, issued by ONE thread
 template <int kCtaGroup>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,

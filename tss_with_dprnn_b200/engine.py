@@ -46,11 +46,31 @@ class Engine(RaggedMixin):
         self._packed_key = None
 
     def set_precision(self, mode: str):
-        if mode not in ('fp32', 'bf16'):
-            raise ValueError("precision must be 'fp32' or 'bf16'")
-        if mode == 'bf16' and 'bf16' not in lib().build_info():
-            raise RuntimeError('this build of libdprnn_b200 carries no bf16 tensor-core kernels')
+        """'fp32': exact fp32 on CUDA cores (parity mode).  'bf16' / 'fp16': the tcgen05 kernels with bf16 / fp16 operands
+        (fp32 accumulation in TMEM, fp32 cell state and statistics).  'fp16' keeps the estimated sources within
+        north_star's 1e-3 of the reference's fp32 path (11 significand bits instead of 8) at the speed of 'bf16'."""
+        if mode not in ('fp32', 'bf16', 'fp16'):
+            raise ValueError("precision must be 'fp32', 'bf16' or 'fp16'")
+        if mode != 'fp32' and 'bf16' not in lib().build_info():
+            raise RuntimeError('this build of libdprnn_b200 carries no tensor-core kernels')
         self.precision = mode
+
+    @property
+    def tc(self) -> bool:
+        """tensor-core mode (bf16 or fp16 operands)"""
+        return self.precision != 'fp32'
+
+    @property
+    def h16(self) -> int:
+        """DPRNN_H16_* code of the 16-bit operand / storage format"""
+        return 1 if self.precision == 'fp16' else 0
+
+    @property
+    def h16_dtype(self):
+        return torch.float16 if self.precision == 'fp16' else torch.bfloat16
+
+    def _lstm_flags(self) -> int:
+        return int(self.fast_act) | (2 if self.precision == 'fp16' else 0)       # DPRNN_LSTM_FAST_ACT | DPRNN_LSTM_FP16
 
     # ------------------------------------------------------------------ weights
     def invalidate(self):
@@ -61,7 +81,7 @@ class Engine(RaggedMixin):
         self._graphs = {}
 
     def _weights_key(self):
-        return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+        return (self.h16,) + tuple((p.data_ptr(), p._version) for p in self.model.parameters())
 
     def packed(self):
         """Kernel-layout copies of the weights, rebuilt whenever a parameter changes."""
@@ -91,11 +111,11 @@ class Engine(RaggedMixin):
                 bias = torch.cat([(getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s)).detach()
                                   for s in sfx], 0)
                 whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach().t() for s in sfx], 0)  # [nd, H, 4H]
-                wp, bp = self._pack_lstm_tc(rnn, sfx)
-                wp2, _ = self._pack_lstm_tc(rnn, sfx, half_jobs=True)
+                wp, bp = self._pack_lstm_tc(rnn, sfx, dtype=self.h16_dtype)
+                wp2, _ = self._pack_lstm_tc(rnn, sfx, half_jobs=True, dtype=self.h16_dtype)
                 halves.append(dict(wih_t=wih.t().contiguous(), bias=bias.contiguous(), whh_t=whh.contiguous(),
                                    ndir=len(sfx), lin_t=_t(lin.weight), lin_b=lin.bias.detach(),
-                                   tc_w=wp, tc_w2=wp2, tc_bias=bp, lin_bf16=lin.weight.detach().to(torch.bfloat16).contiguous()))
+                                   tc_w=wp, tc_w2=wp2, tc_bias=bp, lin_bf16=lin.weight.detach().to(self.h16_dtype).contiguous()))
             blocks.append(halves)
         W['blocks'] = blocks
         cw = sep.conv2d.weight.detach().reshape(2 * F, F)
@@ -129,7 +149,7 @@ class Engine(RaggedMixin):
     _lstm_perm_cache = {}
 
     @staticmethod
-    def _pack_lstm_tc(rnn, sfx, half_jobs=False):
+    def _pack_lstm_tc(rnn, sfx, half_jobs=False, dtype=torch.bfloat16):
         """Weight layout of dprnn_lstm_layer_bf16 (include/dprnn_b200.h): for direction d, CTA rank r and MMA
         instruction nh, the 128 rows {[W_ih | W_hh][q*H + 64*nh + j] : q in (2r, 2r+1), j < 64}; bias likewise.
         half_jobs: the layout of dprnn_lstm_layer_bf16_pp - rows {[..][gate*H + 64*nh + 32*r + u] : gate < 4, u < 32}."""
@@ -156,7 +176,7 @@ class Engine(RaggedMixin):
             b = (getattr(rnn, 'bias_ih_l0' + sf) + getattr(rnn, 'bias_hh_l0' + sf)).detach()
             ws.append((wcat * half[:, None])[wrows])
             bs.append((b * half)[brows])
-        return torch.cat(ws, 0).to(torch.bfloat16).contiguous(), torch.stack(bs, 0).float().contiguous()
+        return torch.cat(ws, 0).to(dtype).contiguous(), torch.stack(bs, 0).float().contiguous()
 
     # ------------------------------------------------------------------ helpers
     @staticmethod
@@ -287,7 +307,7 @@ class Engine(RaggedMixin):
         s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
         L_.call('dprnn_norm_affine', mr, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
         O = se[1].weight.shape[0]
-        if self.precision == 'bf16' and N % 32 == 0 and O in (64, 128, 256):
+        if self.tc and N % 32 == 0 and O in (64, 128, 256):
             fn = torch.empty_like(feats)            # GroupNorm applied, then the 1x1 conv on the tensor cores (TF32)
             L_.call('dprnn_prologue_apply', feats, fn, B * Lr, N, Lr, s1, s0, None, None, st)
             x = self.gemm_tc(fn, se[1].weight.detach(), B * Lr, O, N, bias=se[1].bias.detach())
@@ -309,7 +329,7 @@ class Engine(RaggedMixin):
                 if training:
                     bnm.num_batches_tracked += 1
 
-            tc = self.precision == 'bf16' and Cin in (128, 256) and Cout in (128, 256)
+            tc = self.tc and Cin in (128, 256) and Cout in (128, 256)
 
             def conv(inp, conv_mod, wt, cin, cout):
                 if tc:
@@ -334,7 +354,7 @@ class Engine(RaggedMixin):
                     Cout, st)
             x, Lx = out, Lo
         E = se[5].weight.shape[0]
-        if self.precision == 'bf16' and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
+        if self.tc and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
             z = self.gemm_tc(x, se[5].weight.detach(), B * Lx, E, se[5].weight.shape[1], bias=se[5].bias.detach())
         else:
             z = self.gemm(x, W['spk_conv5_t'], B * Lx, E, se[5].weight.shape[1], bias=se[5].bias.detach())
@@ -392,7 +412,7 @@ class Engine(RaggedMixin):
             L_.call('dprnn_att_rowscale', enc, n1, n0, sep.average.weight.detach(), sep.average.bias.detach(), mulc,
                     scores, rowscale, B, L, N, k, st)
         L_.call('dprnn_norm_affine', mr, gamma, beta, mulc, s1, s0, B, N, st)
-        if self.precision == 'bf16' and N % 32 == 0 and F in (64, 128, 256):
+        if self.tc and N % 32 == 0 and F in (64, 128, 256):
             en = torch.empty_like(enc)              # norm + fusion applied, then the 1x1 conv on the tensor cores (TF32)
             L_.call('dprnn_prologue_apply', enc, en, B * L, N, L, s1, s0, addc, rowscale, st)
             y = self.gemm_tc(en, W['bott_w_x'], B * L, F, N, bias=bias, bias_rows_per_utt=L if bias_per_utt else 0)
@@ -403,20 +423,20 @@ class Engine(RaggedMixin):
         S = L_.query('dprnn_num_chunks', L, K, P)
         x = torch.empty((B, S, K, F), device=dev)
         rows = B * S * K
-        bf16 = self.precision == 'bf16'
+        bf16 = self.tc
         s = dict(B=B, L=L, S=S, K=K, P=P, F=F, H=H, N=N, rows=rows, x=x, bf16=bf16, dev=dev)
         if bf16:
             if H != 128 or F != 128:
                 raise NotImplementedError('the tensor-core LSTM kernel is built for feature_size = hidden_size = 128')
-            s['xb'] = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
-            L_.call('dprnn_unfold_bf16', y, x, s['xb'], B, L, K, P, F, st)
+            s['xb'] = torch.empty((rows, F), device=dev, dtype=self.h16_dtype)
+            L_.call('dprnn_unfold_h16', y, x, s['xb'], B, L, K, P, F, self.h16, st)
         else:
             L_.call('dprnn_unfold', y, x, B, L, K, P, F, st)
         del y
         if bf16:
             ndmax = max(hw['ndir'] for halves in W['blocks'] for hw in halves)
-            s['hb'] = torch.empty((rows * ndmax * H,), device=dev, dtype=torch.bfloat16)
-            s['ybuf'] = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+            s['hb'] = torch.empty((rows * ndmax * H,), device=dev, dtype=self.h16_dtype)
+            s['ybuf'] = torch.empty((rows, F), device=dev, dtype=self.h16_dtype)
             s['part'] = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', rows), device=dev, dtype=torch.uint8)
             s['mr2'] = torch.empty((B, 2), device=dev)
             if self.fused_tail:
@@ -430,8 +450,10 @@ class Engine(RaggedMixin):
             # two half-jobs per CTA pair in ping-pong (lstm_tc_pp.cu): bit-identical results, the hand-off of one half-job
             # hidden under the cell update of the other
             lib().call('dprnn_lstm_layer_bf16_pp', s['xb'], hw['tc_w2'], hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'],
-                       which, s['H'], hw['ndir'], int(self.fast_act), self._stream())
+                       which, s['H'], hw['ndir'], self._lstm_flags(), self._stream())
             return
+        if self.precision == 'fp16':
+            raise NotImplementedError("precision 'fp16' is built for the default LSTM kernel (lstm_pingpong = True)")
         if self.lstm_slices > 1:
             # persistent CTA pairs over time-sliced jobs (lstm_tc_sliced.cu): bit-identical results, fewer idle SMs when
             # the layer has more pair-jobs than the GPU has SM pairs
@@ -450,6 +472,8 @@ class Engine(RaggedMixin):
     def _half_tail(self, s, bi, which):
         """bf16 mode: Linear -> GroupNorm / gLN -> residual (dprnn.py:86-92 / 96-99) on s['hb'] -> s['x'], s['xb']."""
         if self.fused_tail:
+            if self.precision == 'fp16':
+                raise NotImplementedError("precision 'fp16' is built for the default two-kernel tail (fused_tail = False)")
             # Linear + norm statistics + norm apply + residual in one persistent kernel (linear_norm.cu)
             hw = self.packed()['blocks'][bi][which]
             blk = self.model.separation.dprnn_blocks[bi]
@@ -467,19 +491,19 @@ class Engine(RaggedMixin):
         hw = self.packed()['blocks'][bi][which]
         blk = self.model.separation.dprnn_blocks[bi]
         _, _, eps = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
-        lib().call('dprnn_linear_bf16out_stats', s['hb'], hw['lin_bf16'], hw['lin_b'], s['ybuf'], s['rows'],
-                   hw['ndir'] * s['H'], s['part'], s['S'] * s['K'], float(eps), s['mr2'], self._stream())
+        lib().call('dprnn_linear_h16out_stats', s['hb'], hw['lin_bf16'], hw['lin_b'], s['ybuf'], s['rows'],
+                   hw['ndir'] * s['H'], s['part'], s['S'] * s['K'], float(eps), s['mr2'], self.h16, self._stream())
 
     def _half_norm(self, s, bi, which):
         blk = self.model.separation.dprnn_blocks[bi]
         g_, b_, _ = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
         last = bi == len(self.model.separation.dprnn_blocks) - 1 and which == 1     # nothing reads the bf16 shadow then
-        if self.residual_bf16:      # opt-in: residual stream in bf16 only; the last half-block writes the fp32 x for the fold
-            lib().call('dprnn_norm_residual_bf16res', s['ybuf'], s['xb'], s['x'] if last else None, s['mr2'], g_, b_,
-                       s['B'], s['S'] * s['K'], s['F'], self._stream())
+        if self.residual_bf16:      # default: residual stream in 16 bits only; the last half-block writes the fp32 x for the fold
+            lib().call('dprnn_norm_residual_h16res', s['ybuf'], s['xb'], s['x'] if last else None, s['mr2'], g_, b_,
+                       s['B'], s['S'] * s['K'], s['F'], self.h16, self._stream())
             return
-        lib().call('dprnn_norm_residual_ybf16', s['ybuf'], s['x'], s['mr2'], g_, b_, s['B'], s['S'] * s['K'], s['F'],
-                   None if last else s['xb'], self._stream())
+        lib().call('dprnn_norm_residual_yh16', s['ybuf'], s['x'], s['mr2'], g_, b_, s['B'], s['S'] * s['K'], s['F'],
+                   None if last else s['xb'], self.h16, self._stream())
 
     def _half_fp32(self, s, bi, which):
         """exact-fp32 mode: input projection GEMM, recurrence, Linear, statistics, norm + residual on CUDA cores."""

@@ -162,7 +162,8 @@ class _TasNetBase(nn.Module):
         self.decoder = nn.ConvTranspose1d(input_size, 1, kernel_size, stride=self.stride, bias=False)
         self._engine = Engine(self)
 
-    #: 'fp32' = exact fp32 everywhere; 'bf16' = bf16 tcgen05 gate/linear contractions (fp32 accumulate)
+    #: 'fp32' = exact fp32 everywhere; 'bf16' / 'fp16' = tcgen05 LSTM / Linear contractions with bf16 / fp16 operands
+    #: (fp32 accumulation); 'fp16' stays within 1e-3 (peak-normalised) of the reference's fp32 path at the same speed
     @property
     def precision(self) -> str:
         return self._engine.precision
@@ -247,7 +248,7 @@ class DPRNNRawNetTasNet(_TasNetBase):
                          embeddings_size=embeddings_size, num_spks=num_spks, fusion_type=fusion_type)
 
     def forward(self, input, aux):
-        self.separation.spk_encoder.allow_tf32 = self.precision == 'bf16'
+        self.separation.spk_encoder.allow_tf32 = self.precision != 'fp32'
         emb = self.separation.spk_encoder.embed(aux)
         return self._engine.forward_spe(input, None, None, embedding=emb)
 

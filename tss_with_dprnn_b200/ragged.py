@@ -160,7 +160,7 @@ class RaggedMixin:
         s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
         L_.call('dprnn_norm_affine', mr, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
         O = se[1].weight.shape[0]
-        if self.precision == 'bf16' and N % 32 == 0 and O in (64, 128, 256):     # same arithmetic as the uniform path
+        if self.tc and N % 32 == 0 and O in (64, 128, 256):     # same arithmetic as the uniform path
             fn = torch.empty_like(feats)
             L_.call('dprnn_prologue_apply_ragged', feats, fn, lay.total_rows, N, lay.frame_utt, s1, s0, None, None, st)
             x = self.gemm_tc(fn, se[1].weight.detach(), lay.total_rows, O, N, bias=se[1].bias.detach())
@@ -177,7 +177,7 @@ class RaggedMixin:
                 L_.call('dprnn_batchnorm_affine', None, rows, Cout, bnm.weight.detach(), bnm.bias.detach(),
                         bnm.running_mean, bnm.running_var, 0, float(bnm.eps), 0.1, None, scale, shift, st)
 
-            tc = self.precision == 'bf16' and Cin in (128, 256) and Cout in (128, 256)
+            tc = self.tc and Cin in (128, 256) and Cout in (128, 256)
 
             def conv(inp, conv_mod, wt, cin, cout):
                 if tc:
@@ -200,7 +200,7 @@ class RaggedMixin:
                     stage['out_utt'], stage['in_off'], stage['out_off'], stage['total_out'], Cout, st)
             x, rows = out, stage['total_out']
         E = se[5].weight.shape[0]
-        if self.precision == 'bf16' and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
+        if self.tc and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
             z = self.gemm_tc(x, se[5].weight.detach(), rows, E, se[5].weight.shape[1], bias=se[5].bias.detach())
         else:
             z = self.gemm(x, W['spk_conv5_t'], rows, E, se[5].weight.shape[1], bias=se[5].bias.detach())
@@ -245,7 +245,7 @@ class RaggedMixin:
                     mulc, scores, rowscale, lay.frame_utt, lay.frame_off, lay.L_d, lay.La_d, B, TR, N,
                     cfg['kernel_size'], st)
         L_.call('dprnn_norm_affine', mr, gamma, beta, mulc, s1, s0, B, N, st)
-        if self.precision == 'bf16' and N % 32 == 0 and F in (64, 128, 256):
+        if self.tc and N % 32 == 0 and F in (64, 128, 256):
             en = torch.empty_like(enc)
             L_.call('dprnn_prologue_apply_ragged', enc, en, TR, N, lay.frame_utt, s1, s0, addc, rowscale, st)
             y = self.gemm_tc(en, W['bott_w_x'], TR, F, N, bias=bias, bias_row_utt=lay.frame_utt if bias_per_utt else None)
@@ -258,12 +258,14 @@ class RaggedMixin:
         x = torch.empty((rows, F), device=dev)
         L_.call('dprnn_unfold_ragged', y, x, lay.chunk_utt, lay.chunk_off, lay.frame_off, lay.L_d, TC, K, P, F, st)
         del y
-        bf16 = self.precision == 'bf16'
+        bf16 = self.tc
         if bf16:
             if H != 128 or F != 128:
                 raise NotImplementedError('the tensor-core LSTM kernel is built for feature_size = hidden_size = 128')
-            xb = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
-            L_.call('dprnn_cast_bf16', x, xb, rows * F, st)
+            if self.precision == 'fp16' and not self.lstm_pingpong:
+                raise NotImplementedError("precision 'fp16' is built for the default LSTM kernel (lstm_pingpong = True)")
+            xb = torch.empty((rows, F), device=dev, dtype=self.h16_dtype)
+            L_.call('dprnn_cast_h16', x, xb, rows * F, self.h16, st)
         for blk, halves in zip(sep.dprnn_blocks, W['blocks']):
             for which, hw in enumerate(halves):
                 nd = hw['ndir']
@@ -271,24 +273,24 @@ class RaggedMixin:
                 g_, b_, eps = self._norm_params(nm)
                 mr2 = torch.empty((B, 2), device=dev)
                 if bf16:
-                    hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
+                    hb = torch.empty((rows, nd * H), device=dev, dtype=self.h16_dtype)
                     pp = '_pp' if self.lstm_pingpong else ''          # half-job ping-pong kernels (bit-identical)
                     wk = hw['tc_w2'] if self.lstm_pingpong else hw['tc_w']
                     if which == 0:      # every chunk is one length-K sequence: the packed chunk space is a uniform batch
                         L_.call('dprnn_lstm_layer_bf16' + pp, xb, wk, hw['tc_bias'], hb, 1, TC, K, 0, H, nd,
-                                int(self.fast_act), st)
+                                self._lstm_flags(), st)
                     else:               # one pair-job per utterance and direction, S_b steps each
                         L_.call('dprnn_lstm_inter_bf16_ragged' + pp, xb, wk, hw['tc_bias'], hb, TC, K, lay.jobs, B,
-                                H, nd, int(self.fast_act), st)
-                    ybuf = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+                                H, nd, self._lstm_flags(), st)
+                    ybuf = torch.empty((rows, F), device=dev, dtype=self.h16_dtype)
                     part = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', rows), device=dev, dtype=torch.uint8)
                     self._linear_stats_ragged(hb, hw, ybuf, rows, nd * H, part, lay, eps, mr2)
                     if self.residual_bf16:      # opt-in bf16 residual stream (same arithmetic as the uniform path)
                         last = blk is sep.dprnn_blocks[len(sep.dprnn_blocks) - 1] and which == 1
-                        L_.call('dprnn_norm_residual_ragged_bf16res', ybuf, xb, x if last else None, mr2, g_, b_,
-                                lay.chunk_utt, TC, K, F, st)
+                        L_.call('dprnn_norm_residual_ragged_h16res', ybuf, xb, x if last else None, mr2, g_, b_,
+                                lay.chunk_utt, TC, K, F, self.h16, st)
                     else:
-                        L_.call('dprnn_norm_residual_ragged', ybuf, 1, x, mr2, g_, b_, lay.chunk_utt, TC, K, F, xb, st)
+                        L_.call('dprnn_norm_residual_ragged', ybuf, 1 + self.h16, x, mr2, g_, b_, lay.chunk_utt, TC, K, F, xb, st)
                     del hb, ybuf
                     continue
                 gx = self.gemm(x, hw['wih_t'], rows, nd * 4 * H, F, bias=hw['bias'])
@@ -326,8 +328,8 @@ class RaggedMixin:
     def _linear_stats_ragged(self, hb, hw, ybuf, rows, Kdim, part, lay, eps, mr2):
         """Tensor-core Linear with bf16 output and per-row sums, then the per-utterance reduction."""
         L_, st = lib(), self._stream()
-        L_.call('dprnn_linear_bf16out_stats', hb, hw['lin_bf16'], hw['lin_b'], ybuf, rows, Kdim, part, 0, float(eps),
-                None, st)          # mean_rstd = NULL: per-row sums only
+        L_.call('dprnn_linear_h16out_stats', hb, hw['lin_bf16'], hw['lin_b'], ybuf, rows, Kdim, part, 0, float(eps),
+                None, self.h16, st)          # mean_rstd = NULL: per-row sums only
         L_.call('dprnn_row_stats_finalize_ragged', part, lay.row_off, lay.B, hw['lin_bf16'].shape[0], float(eps), mr2, st)
 
     def decode_ragged(self, mask, enc, lay):

@@ -121,6 +121,9 @@ def _norm_params(mod):
 
 def _check_supported(model):
     cfg = model.cfg
+    if model.precision == 'fp16':
+        raise NotImplementedError("the training step runs in precision 'fp32' or 'bf16' (cfg 5: bf16 gate GEMMs); "
+                                  "'fp16' is an inference mode")
     if cfg['kind'] not in ('spe', 'bss') or (cfg['kind'] == 'spe' and cfg['fusion_type'] not in
                                                   ('film', 'add', 'mul', 'cat', 'att')):
         raise NotImplementedError("training is built for DPRNNTasNet (scripts/train/config_bss.yaml) and DPRNNSpeTasNet "
