@@ -288,6 +288,18 @@ def time_cpu(args, steps, warmup):
     return kind, cores, times, batch * T / SR, desc
 
 
+def reference_config(args, desc):
+    """The workload is the repo arm's (same `workload` string); every other key says what THIS arm ran: the reference's
+    CPU code has one precision (fp32), no streams, and is timed on a bounded sample of the batch (CPU throughput is
+    flat in the batch size: cpu_baseline.b8)."""
+    cfg = workload_config(args)
+    cfg.update({'precision': 'fp32 (the reference has no other)', 'streams': 'n/a (CPU)', 'l2': 'n/a (CPU)',
+                'parallelism': f'{os.cpu_count()} host threads, rank 0 only', 'batch_per_forward': cpu_sample(args)[0],
+                'sample': desc})
+    cfg.pop('batch_per_gpu', None)
+    return cfg
+
+
 def run_reference(args):
     rank = int(os.environ.get('RANK', 0))
     if rank != 0:
@@ -303,7 +315,7 @@ def run_reference(args):
         'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': 'audio-s/s', 'n_gpus': args.gpus,
         'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * total / len(times),
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': workload_config(args),
+        'config': reference_config(args, desc),
         'cpu_baseline': {'value': value, 'unit': 'audio-s/s', 'cores': cores, 'kind': kind, 'sample': desc},
         'e2e': {'value': value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -476,6 +488,107 @@ class Cfg3:
         return (sum(s['Ts']) + sum(s['Trs'])) * 4, sum(s['Ts']) * 4
 
 
+# ----------------------------------------------------------------------------------------------------------
+# side measurements of the default (cfg 2) line: other precision modes, the reference's modules on this GPU,
+# a short cfg-5 training step (the only path with a collective)
+# ----------------------------------------------------------------------------------------------------------
+def fixture_error(model, dev):
+    """Peak-normalised error of the CUDA path against the reference's own fp32 output: fixture spe_cat_r6_3s
+    (tests/golden, written by the live reference for torch.manual_seed(0) weights of exactly the bench model)."""
+    import numpy as np
+    try:
+        z = np.load(os.path.join(ROOT, 'tests', 'golden', 'spe_cat_r6_3s.npz'), allow_pickle=False)
+    except OSError:
+        return None
+    mix, ref = torch.from_numpy(z['mix']).to(dev), torch.from_numpy(z['ref']).to(dev)
+    want = torch.from_numpy(z['est']).to(dev).double()
+    with torch.no_grad():
+        est, _ = model(mix, ref, torch.tensor(float(ref.shape[1])))
+    return float((est.double() - want).abs().max() / want.abs().max())
+
+
+def gpu_reference(args, dev):
+    """SURVEY.md 8d 'informative extra row': the UNMODIFIED reference classes (baseline/_ref) on this GPU through stock
+    PyTorch (cuDNN LSTM, ATen GroupNorm / unfold / fold), same batch, outside the repo arm's timed region."""
+    ref_root = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isdir(os.path.join(ref_root, 'src', 'models')):
+        return {'unavailable': 'baseline/_ref absent'}
+    out = {}
+    try:
+        sys.path.insert(0, ref_root)
+        from src.models.dprnn_spe import DPRNNSpeTasNet as RefModel
+        torch.manual_seed(0)
+        model = RefModel(**KW).eval().to(dev)
+        mix, ref = synth(args.batch, args.samples, 0, dev)
+        rl = torch.tensor(float(args.samples))
+        old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+        for name, tf32 in (('fp32', False), ('tf32_allowed', True)):
+            torch.backends.cuda.matmul.allow_tf32 = tf32
+            torch.backends.cudnn.allow_tf32 = tf32
+            with torch.no_grad():
+                for _ in range(2):
+                    model(mix, ref, rl)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(3):
+                    model(mix, ref, rl)
+                e1.record()
+                torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / 3
+            out[name] = {'ms_per_step': ms, 'value': args.batch * args.samples / SR / (ms / 1e3), 'unit': 'audio-s/s'}
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+        out['what'] = (f'baseline/_ref DPRNNSpeTasNet (cat).cuda().eval(), batch {args.batch} x {args.samples / SR:g} s, torch '
+                       f'{torch.__version__} / cuDNN {torch.backends.cudnn.version()}, 2 warm-up + 3 timed forwards, CUDA events')
+        del model
+    except Exception as e:          # an informative row must not take the bench line down
+        out['unavailable'] = f'{type(e).__name__}: {e}'[:200]
+    torch.cuda.empty_cache()
+    return out
+
+
+def cfg5_sub(args, P, rank, world, dev, barrier, reduce_timing):
+    """A short cfg-5 measurement (DPRNN-Spe FiLM training step, 16 x 3 s per GPU, bf16 tensor-core mode) so that the
+    driver's 1 -> 8 GPU runs of the DEFAULT command also exercise the one collective of the project: the NCCL
+    all-reduce of the flat gradient buffer.  Ranks are seeded DIFFERENTLY on purpose: the stepper has to broadcast rank
+    0's parameters, and replica_param_checksum_spread must come out 0."""
+    import torch.distributed as dist
+    a5 = argparse.Namespace(batch=16, samples=24000)
+    torch.manual_seed(100 + rank)
+    model = P.DPRNNSpeTasNet(**KW5).train().to(dev)
+    model.precision = 'bf16'
+    wl = Cfg5(a5, model, rank, dev)
+    wl.stepper.allreduce_events = []
+    steps, warm = 3, 2
+    for i in range(warm):
+        wl.resident(i)
+    barrier()
+    wl.stepper.allreduce_events = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        wl.resident(i)
+    e1.record()
+    barrier()
+    ms_local = e0.elapsed_time(e1)
+    ms, audio = reduce_timing(ms_local, steps * wl.audio(0), dev)
+    ar = [a.elapsed_time(b) for a, b in wl.stepper.allreduce_events]
+    chk = wl.stepper.fp.flat.double().sum().reshape(1)
+    spread = 0.0
+    if world > 1:
+        allc = [torch.zeros_like(chk) for _ in range(world)]
+        dist.all_gather(allc, chk)
+        spread = float(max(float(c) for c in allc) - min(float(c) for c in allc))
+    out = {'workload': 'cfg5: DPRNN-Spe (FiLM) training step, 16 x 3 s per GPU, bf16 tensor-core mode; 2 warm-up + 3 timed '
+                       'steps; ranks start from different seeds (parameters broadcast from rank 0)',
+           'ms_per_step': ms / steps, 'samples_per_s': 16 * world * steps / (ms / 1e3), 'audio_s_per_s': audio / (ms / 1e3),
+           'allreduce_ms': (sum(ar) / len(ar)) if ar else 0.0, 'allreduce_bytes': int(wl.stepper.fp.size * 4),
+           'replica_param_checksum_spread': spread, 'n_gpus': world}
+    del wl, model
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_ours(args):
     import torch.distributed as dist
     import tss_with_dprnn_b200 as P
@@ -547,7 +660,8 @@ def run_ours(args):
 
     # --- per-kernel pass (separate from the timed region, one stream so that launches do not overlap): CUDA events
     # around every launch of step 0
-    dominant = 'dprnn_lstm_layer_bf16' if args.precision == 'bf16' else 'dprnn_lstm_recurrence_f32'
+    tcmode = args.precision != 'fp32'
+    dominant = 'dprnn_lstm_layer_bf16' if tcmode else 'dprnn_lstm_recurrence_f32'
     names = list(L.protos.keys())
     model.n_streams = 1
     L.timing = {n: [] for n in names}
@@ -577,13 +691,13 @@ def run_ours(args):
         n_launch = sum(per_kernel[n]['launches'] for n in lstm_names)
         # one launch = one RNN layer (both directions) over every chunk position of the step; the fused bf16 kernel
         # also does the input projection: 2 * 2 * 128 * 512 flop per position and direction (else 2 * 128 * 512)
-        flop_per_pos = 2 * (2 if args.precision == 'bf16' and args.workload != 'cfg5' else 1) * 2 * 128 * 512
+        flop_per_pos = 2 * (2 if tcmode and args.workload != 'cfg5' else 1) * 2 * 128 * 512
         flop_per_launch = flop_per_pos * wl.positions(0) / (2 if args.workload == 'cfg3' else 1)
         achieved = flop_per_launch * n_launch / (ms_lstm * 1e-3) / 1e12
         roofline = {'kernel': '+'.join(lstm_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                     'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
                     'traffic': (ncu_traffic_per_launch('lstm_tc_') if args.workload == 'cfg2' and args.batch == 64
-                                and args.precision == 'bf16' else None),
+                                and tcmode else None),
                     'traffic_note': 'DRAM read+write bytes per launch, ncu --set full (profiles/r1_top3_ncu_full.txt); '
                                     'algorithmic: read xb 2 x 0.79 GB + write hb 1.59 GB = 3.18 GB',
                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (B200_PROFILING.md)',
@@ -591,7 +705,7 @@ def run_ours(args):
                     'share_of_step_single_stream': ms_lstm / sum(k['ms_total'] for k in per_kernel.values()),
                     'note': ('algorithmic flops = [x_t|h_{t-1}] [W_ih|W_hh]^T, 2*256*512 per chunk position and direction; '
                              'launches timed one by one on a single stream'
-                             if args.precision == 'bf16' and args.workload != 'cfg5' else
+                             if tcmode and args.workload != 'cfg5' else
                              'algorithmic flops = h W_hh^T only (2*128*512 per position and direction); the fp32 mode '
                              'runs this on CUDA cores, so its fraction of the bf16 tensor peak is small by construction')}
 
@@ -615,12 +729,47 @@ def run_ours(args):
                             'element-wise cell backward between the MMAs is issue/latency-bound (ncu: 27 % issue slots, top '
                             'stall = first use of the streamed loads): DESIGN.md section 5.2'}
 
+    modes = gpu_ref = cfg5 = None
+    if args.workload == 'cfg2':
+        if args.modes and world == 1:
+            # the other precision modes on the same batch: throughput, and the error of each against the reference's own
+            # fp32 output (fixture of the same seeded weights); tol_1e-3 names the fastest mode inside north_star's tolerance
+            modes = {args.precision: {'value': value, 'ms_per_step': ms_total / args.steps,
+                                      'err': fixture_error(model, dev)}}
+            for mode in ('fp16', 'bf16', 'fp32'):
+                if mode in modes:
+                    continue
+                model.precision = mode
+                k, w = (1, 1) if mode == 'fp32' else (3, 3)
+                ms_m, _ = timed(wl.resident, k, w)
+                modes[mode] = {'value': k * wl.audio(0) / (ms_m / 1e3), 'ms_per_step': ms_m / k, 'err': fixture_error(model, dev)}
+            model.precision = args.precision
+            ok = [m for m, v in modes.items() if v['err'] is not None and v['err'] <= 1e-3]
+            modes['tol_1e-3'] = dict(modes[max(ok, key=lambda m: modes[m]['value'])], mode=max(ok, key=lambda m: modes[m]['value'])) if ok else None
+            modes['err_metric'] = ('max|est - ref| / max|ref| against tests/golden/spe_cat_r6_3s.npz (the live reference, fp32, '
+                                   'same seeded weights), B = 1')
+        model._engine.invalidate()          # drop the captured graphs (they pin their forward's buffers)
+        torch.cuda.empty_cache()
+        if args.gpu_reference and world == 1:
+            gpu_ref = gpu_reference(args, dev)
+        if args.cfg5:
+            del wl
+            torch.cuda.empty_cache()
+            cfg5 = cfg5_sub(args, P, rank, world, dev, barrier, reduce_timing)
+
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        kind, cores, times, audio, desc = time_cpu(args, 2, 1)
-        cpu = {'value': audio * len(times) / sum(times), 'unit': 'audio-s/s', 'cores': cores, 'kind': kind,
-               'sample': desc + (', 1 warm-up + 2 timed training iterations, fp32, train()' if args.workload == 'cfg5'
-                                  else ', 1 warm-up + 2 timed forwards, fp32, eval()')}
+        # SURVEY.md section 8d protocol: 1 warm-up + 3 timed, best-of and mean, at B = 1 and (cfg 2) B = 8
+        kind, cores, times, audio, desc = time_cpu(args, 3, 1)
+        cpu = {'value': audio * len(times) / sum(times), 'best': audio / min(times), 'unit': 'audio-s/s', 'cores': cores,
+               'kind': kind,
+               'sample': desc + (', 1 warm-up + 3 timed training iterations, fp32, train()' if args.workload == 'cfg5'
+                                  else ', 1 warm-up + 3 timed forwards, fp32, eval()')}
+        if args.workload == 'cfg2' and args.cpu_b8:
+            a8 = argparse.Namespace(**vars(args))
+            a8.cpu_batch = 8
+            _, _, t8, audio8, desc8 = time_cpu(a8, 3, 1)
+            cpu['b8'] = {'value': audio8 * len(t8) / sum(t8), 'best': audio8 / min(t8), 'sample': desc8 + ', 1 warm-up + 3 timed'}
 
     replica_spread = None
     if args.workload == 'cfg5':
@@ -636,12 +785,18 @@ def run_ours(args):
         line = {
             'metric': METRIC, 'value': value, 'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-            'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'bf16 LSTM gate contractions (fwd + BPTT), tf32 linear / weight-gradient contractions, f32 accumulate+state' if args.workload == 'cfg5' else 'bf16 gate/linear contractions, f32 accumulate+state',
+            'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'bf16 LSTM gate contractions (fwd + BPTT), tf32 linear / weight-gradient contractions, f32 accumulate+state' if args.workload == 'cfg5' else f'{args.precision} gate/linear contractions (tcgen05), tf32 1x1 convs, f32 accumulate+state',
             'data': 'synthetic', 'config': workload_config(args), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'kernels': per_kernel,
             'build': L.build_info(),
         }
+        if modes is not None:
+            line['modes'] = modes
+        if gpu_ref is not None:
+            line['gpu_reference'] = gpu_ref
+        if cfg5 is not None:
+            line['cfg5'] = cfg5
         if args.workload == 'cfg5':
             line['train'] = {'samples_per_s': args.batch * world * args.steps / (ms_total / 1e3),
                              'replica_param_checksum_spread': replica_spread,
@@ -660,7 +815,8 @@ def main():
     ap.add_argument('--workload', default='cfg2', choices=['cfg1', 'cfg2', 'cfg3', 'cfg4', 'cfg5'],
                     help='cfg1: DPRNN-TasNet B=1; cfg2 (headline): DPRNN-Spe cat, 3-s batch 64; cfg3: DPRNN-Spe-IRA on the ragged test-set lengths; '
                          'cfg4: DPRNN-RawNet3 att, batch 16 per GPU; cfg5: DPRNN-Spe FiLM training step, batch 16 per GPU')
-    ap.add_argument('--precision', default=os.environ.get('DPRNN_PRECISION', 'bf16'), choices=['fp32', 'bf16'])
+    ap.add_argument('--precision', default=None, choices=['fp32', 'bf16', 'fp16'],
+                    help="default: fp16 (tensor-core mode inside north_star's 1e-3 tolerance); cfg5: bf16")
     ap.add_argument('--streams', type=int, default=int(os.environ.get('DPRNN_STREAMS', '3')),
                     help='concurrent CUDA streams the batch is split over inside one forward (cfg2)')
     ap.add_argument('--lstm-slices', type=int, default=int(os.environ.get('DPRNN_LSTM_SLICES', '1')),
@@ -668,7 +824,7 @@ def main():
     ap.add_argument('--lstm-pingpong', type=int, default=int(os.environ.get('DPRNN_LSTM_PINGPONG', '1')),
                     help='1 (default): half-job ping-pong LSTM kernel; 0: one job per CTA pair')
     ap.add_argument('--residual-bf16', type=int, default=1,
-                    help='bf16 mode: 1 (default) residual stream in bf16 only; 0: fp32 master copy of the residual stream')
+                    help='tensor-core modes: 1 (default) residual stream in 16 bits only; 0: fp32 master copy of the residual stream')
     ap.add_argument('--lstm-pairs', type=int, default=int(os.environ.get('DPRNN_LSTM_PAIRS', '0')),
                     help='cap on the resident CTA pairs of the persistent LSTM kernel (0 = all)')
     ap.add_argument('--fused-tail', type=int, default=None, help='1: Linear+norm+residual as one persistent kernel')
@@ -676,9 +832,18 @@ def main():
     ap.add_argument('--samples', type=int, default=24000, help='samples per utterance (3 s @ 8 kHz)')
     ap.add_argument('--cpu-batch', type=int, default=1, help='utterances per CPU-baseline forward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-b8', type=int, default=1, help='cfg2: also time the CPU baseline at B = 8 (SURVEY.md 8d protocol)')
+    ap.add_argument('--modes', type=int, default=1,
+                    help='cfg2: also measure the other precision modes (throughput + error against the reference fixture)')
+    ap.add_argument('--gpu-reference', type=int, default=1,
+                    help='cfg2, 1 GPU: also time the unmodified reference classes on this GPU through stock PyTorch / cuDNN')
+    ap.add_argument('--cfg5', type=int, default=1,
+                    help='cfg2: append a short cfg-5 (training step, all-reduce) sub-measurement to the line')
     args = ap.parse_args()
     if args.batch is None:
         args.batch = {'cfg1': 1, 'cfg4': 16, 'cfg5': 16}.get(args.workload, 64)
+    if args.precision is None:
+        args.precision = os.environ.get('DPRNN_PRECISION', 'bf16' if args.workload == 'cfg5' else 'fp16')
     if args.workload in ('cfg1', 'cfg5'):
         args.streams = 1
     if args.warmup < 3 and args.impl == 'ours':

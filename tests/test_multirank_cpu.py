@@ -103,3 +103,50 @@ def test_flat_gradient_allreduce_two_ranks():
         assert numel == 8 * 16 + 16 + 16 * 4 + 4             # PReLU weight excluded
         assert lo == hi == 1.5                               # mean of 1 and 2 on both ranks
         assert aliased                                       # parameters are views of the flat buffer
+
+
+def _bcast_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    sys.path.insert(0, ROOT)
+    from tss_with_dprnn_b200.dp import FlatParams, allreduce_mean, average_buffers, broadcast_state
+    torch.manual_seed(100 + rank)                            # replicas built from DIFFERENT seeds
+    net = torch.nn.Sequential(torch.nn.Linear(8, 16), torch.nn.BatchNorm1d(16), torch.nn.Linear(16, 4))
+    net[1].running_mean.fill_(float(rank))
+    fp = FlatParams(net)
+    before = float(fp.flat.double().sum())
+    moments = torch.full_like(fp.flat, float(rank))
+    broadcast_state([fp.flat, moments] + list(net.buffers()))
+    after = float(fp.flat.double().sum())
+    # one data-parallel SGD step on rank-dependent gradients: the replicas must stay identical
+    for _, p in fp.named:
+        p.grad.fill_(float(rank + 1))
+    allreduce_mean(fp.grad)
+    fp.flat.add_(fp.grad, alpha=-0.1)
+    net[1].running_var.fill_(1.0 + rank)                     # rank-local statistics of the step
+    average_buffers([b for b in net.buffers() if b.dtype.is_floating_point])
+    q.put((rank, before, after, float(moments.max()), float(net[1].running_mean.max()), float(fp.flat.double().sum()),
+           float(net[0].weight.double().sum()), float(net[1].running_var.mean())))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_replicas_start_identical_from_different_seeds():
+    """SpeTrainStep broadcasts rank 0's parameters, Adam moments and BatchNorm buffers at construction (and
+    after load_checkpoint); here the plumbing it uses (dp.broadcast_state / average_buffers) on gloo, world size 2."""
+    world, port = 2, 29657
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bcast_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=100) for _ in range(world))
+    for p in procs:
+        p.join(timeout=30)
+        assert p.exitcode == 0
+    (_, b0, a0, m0, rm0, s0, w0, rv0), (_, b1, a1, m1, rm1, s1, w1, rv1) = res
+    assert b0 != b1                                           # different seeds really gave different replicas
+    assert a0 == a1 == b0                                     # both now hold rank 0's parameters
+    assert m0 == m1 == 0.0 and rm0 == rm1 == 0.0              # moments / BatchNorm buffers likewise
+    assert s0 == s1 and w0 == w1                              # still identical after an all-reduced update
+    assert rv0 == rv1 == 1.5                                  # BatchNorm statistics averaged for the checkpoint

@@ -4,8 +4,9 @@ NVLink - followed by gradient clipping and Adam as one fused kernel over the sam
 (src/trainers/trainer.py:42-43,115-116; scripts/train/config_tss.yaml:36-39,59).
 
 The reference has no distributed code (single process, single GPU); this is new functionality next to the path.  The
-backward kernels that fill the gradient buffer are NOT built yet, so cfg 5 cannot run end to end; this module and its
-tests cover the exchange step and the optimiser so that the backward can be dropped in.
+backward that fills the gradient buffer is train.py (DPRNN-TasNet and every DPRNN-Spe fusion); SpeTrainStep there drives
+one iteration with the pieces of this module: FlatParams, broadcast_state (replicas start identical), allreduce_mean (the
+exchange step) and ClipAdam.
 """
 from __future__ import annotations
 
@@ -55,6 +56,32 @@ def allreduce_mean(flat_grad: torch.Tensor, group=None) -> torch.Tensor:
         dist.all_reduce(flat_grad, op=dist.ReduceOp.SUM, group=group)
         flat_grad.div_(dist.get_world_size(group))
     return flat_grad
+
+
+def _world(group=None) -> int:
+    import torch.distributed as dist
+    return dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+
+
+def broadcast_state(tensors, group=None, src: int = 0):
+    """In-place broadcast of rank `src`'s tensors (parameters, optimiser moments, BatchNorm buffers) to every replica;
+    no-op without a process group.  Integer buffers (num_batches_tracked) are broadcast as they are."""
+    import torch.distributed as dist
+    if _world(group) > 1:
+        for t in tensors:
+            dist.broadcast(t, src=src, group=group)
+    return tensors
+
+
+def average_buffers(tensors, group=None):
+    """In-place mean over the ranks (the BatchNorm running statistics before a rank-0 checkpoint)."""
+    import torch.distributed as dist
+    w = _world(group)
+    if w > 1:
+        for t in tensors:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+            t.div_(w)
+    return tensors
 
 
 class ClipAdam:

@@ -81,7 +81,14 @@ class Engine(RaggedMixin):
         self._graphs = {}
 
     def _weights_key(self):
+        """Key of the kernel-layout weight copies: a re-seated or in-place-updated parameter changes it.  Writes torch
+        cannot see (p.data, raw pointers) need model.invalidate()."""
         return (self.h16,) + tuple((p.data_ptr(), p._version) for p in self.model.parameters())
+
+    def _graph_key(self):
+        """Captured graphs additionally bake in the addresses (and, in eval mode, rely on the values) of the buffers -
+        the BatchNorm running statistics."""
+        return self._weights_key() + tuple((b.data_ptr(), b._version) for b in self.model.buffers())
 
     def packed(self):
         """Kernel-layout copies of the weights, rebuilt whenever a parameter changes."""
@@ -568,7 +575,7 @@ class Engine(RaggedMixin):
         if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
         key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
-               self.fast_act, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self._weights_key())
+               self.fast_act, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self._graph_key())
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = 'seen'

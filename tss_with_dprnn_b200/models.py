@@ -172,6 +172,25 @@ class _TasNetBase(nn.Module):
     def precision(self, mode: str):
         self._engine.set_precision(mode)
 
+    def invalidate(self):
+        """Forget the kernel-layout weight copies and the captured CUDA graphs.  Needed only after writing parameters or
+        buffers in a way torch cannot see: through ``p.data`` (EMA, weight clipping, ``p.data.copy_``) or raw pointers -
+        neither bumps the tensors' version counters the caches are keyed on.  ``load_state_dict``, ``.to()`` / ``.cuda()``
+        / ``.half()`` (``_apply``) and the fused optimiser step of ``SpeTrainStep`` call it themselves."""
+        self._engine.invalidate()
+
+    def _apply(self, fn, *a, **kw):
+        out = super()._apply(fn, *a, **kw)
+        eng = self.__dict__.get('_engine')
+        if eng is not None:
+            eng.invalidate()
+        return out
+
+    def load_state_dict(self, *a, **kw):
+        out = super().load_state_dict(*a, **kw)
+        self._engine.invalidate()
+        return out
+
     #: number of concurrent CUDA streams the batch is split over inside forward (results do not depend on it)
     @property
     def n_streams(self) -> int:

@@ -691,6 +691,24 @@ class SpeTrainStep:
         self.G = {n: p.grad for n, p in self.fp.named}
         dev = self.fp.flat.device
         self.loss3 = torch.zeros(3, device=dev)
+        self.allreduce_events = None
+        self.sync_replicas()
+
+    def sync_replicas(self):
+        """Data-parallel replicas must start from the same state (torch DDP does this at construction): broadcast rank
+        0's parameters, Adam moments / step count and the speaker encoder's BatchNorm buffers.  The reference has no
+        SyncBN, so the running statistics then evolve per rank on its own shard; average_bn_stats() (called by
+        checkpoint()) puts the mean over the ranks into the file instead of rank 0's private copy."""
+        from .dp import broadcast_state
+        step = torch.tensor([float(self.opt.step_count)], device=self.fp.flat.device)
+        broadcast_state([self.fp.flat, self.opt.exp_avg, self.opt.exp_avg_sq, step] + list(self.model.buffers()),
+                        self.group)
+        self.opt.step_count = int(step.item())
+        self.model._engine.invalidate()
+
+    def average_bn_stats(self):
+        from .dp import average_buffers
+        average_buffers([b for b in self.model.buffers() if b.dtype.is_floating_point], self.group)
 
     def loss_and_grads(self, mix, ref=None, target=None, spk_idx=None, ref_len=None):
         """forward + loss + backward into the flat gradient buffer (no exchange, no update).  -> loss3 (device tensor:
@@ -724,13 +742,23 @@ class SpeTrainStep:
     def step(self, mix, ref=None, target=None, spk_idx=None, ref_len=None):
         from .dp import allreduce_mean
         loss3 = self.loss_and_grads(mix, ref, target, spk_idx, ref_len)
+        if self.allreduce_events is not None:       # optional device timing of the exchange step (bench.py)
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
         allreduce_mean(self.fp.grad, self.group)
+        if self.allreduce_events is not None:
+            ev[1].record()
+            self.allreduce_events.append(ev)
         self.opt.step()
         self.model._engine.invalidate()       # the update went through raw pointers: cached weight packs are stale
         return loss3
 
     # ---- checkpoints in the reference's format (src/trainers/trainer.py:294-306: {'epoch', 'optimizer', 'model'})
-    def checkpoint(self, epoch: int):
+    def checkpoint(self, epoch: int, average_bn: bool = False):
+        """average_bn=True (a collective: call it on EVERY rank) stores the mean over the ranks of the BatchNorm
+        running statistics instead of this rank's private ones."""
+        if average_bn:
+            self.average_bn_stats()
         return {'epoch': int(epoch), 'optimizer': self.opt.state_dict(),
                 'model': {k: v.detach().clone() for k, v in self.model.state_dict().items()}}
 
@@ -750,6 +778,7 @@ class SpeTrainStep:
                 v.copy_(cpt['model'][k])
         self.model._engine.invalidate()
         self.opt.load_state_dict(cpt['optimizer'])
+        self.sync_replicas()          # ranks that resumed from different files continue from rank 0's
         return cpt['epoch']
 
 
