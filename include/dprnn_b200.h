@@ -183,9 +183,16 @@ int dprnn_gemm_tc(const void* A, int a_is_bf16, const void* W, const float* bias
  * bias: [N], or per utterance [*, N] selected by row / bias_rows_per_utt (> 0) or bias_row_utt[row] (ragged);
  * DPRNN_EPI_AFFINE_PRELU: prelu(acc * post_scale[n] + post_shift[n]).  dprnn_gemm_persist_supported() tells whether
  * (operand type, N, K, epilogue) is built; workspace: dprnn_gemm_persist_workspace_bytes() bytes (scheduler ticket). */
+/* a_kind: DPRNN_GEMM_TF32 - A, W fp32 read (truncated) as TF32; DPRNN_GEMM_BF16 - A, W bf16; DPRNN_GEMM_F32X2 - A fp32,
+ * split in shared memory into bf16 pairs hi + lo (16 significand bits), W packed by the caller as [N, 2K] bf16 holding,
+ * for every 32 consecutive k, hi(32) then lo(32) (hi = bf16(w), lo = bf16(w - hi)); three MMAs per K slice.  The tolerance
+ * ('fp16') mode uses F32X2 for every 1x1 convolution: TF32 truncation was its dominant error. */
+#define DPRNN_GEMM_TF32 0
+#define DPRNN_GEMM_BF16 1
+#define DPRNN_GEMM_F32X2 2
 size_t dprnn_gemm_persist_workspace_bytes(void);
-int dprnn_gemm_persist_supported(int a_is_bf16, int N, int K, int epilogue);
-int dprnn_gemm_persist(const void* A, int a_is_bf16, const void* W, const float* bias, long bias_rows_per_utt,
+int dprnn_gemm_persist_supported(int a_kind, int N, int K, int epilogue);
+int dprnn_gemm_persist(const void* A, int a_kind, const void* W, const float* bias, long bias_rows_per_utt,
                        const int* bias_row_utt, const float* post_scale, const float* post_shift, const float* prelu_a,
                        float* C, long ldc, int M, int N, int K, int epilogue, void* workspace, void* stream);
 

@@ -354,3 +354,42 @@ def test_linear_fp16out_then_norm_residual(B, R, K, res16):
                 assert O.peak_rel_err(xf.cpu(), want) < 2e-5 and torch.equal(xb.cpu(), xb0)
             else:
                 assert O.peak_rel_err(xb.float().cpu(), want) < 6e-4
+
+
+@pytest.mark.parametrize('M,N,K,epi', [(777, 128, 128, 0), (1000, 256, 128, 0), (513, 256, 256, 0), (129, 128, 256, 0),
+                                       (70000, 128, 64, 0), (640, 64, 128, 2), (900, 256, 128, 3), (5, 128, 128, 1),
+                                       (3000, 128, 64, 4), (2048, 256, 256, 4)])
+def test_gemm_f32x2_split(M, N, K, epi):
+    """DPRNN_GEMM_F32X2: fp32 operands as bf16 pairs (in-kernel split of A, host-packed W, 3 MMAs): within 3e-5 of the
+    fp64 product of the UNROUNDED operands, where the TF32 form (truncation) sits at ~1e-3.  N = K = 256 goes through
+    the two-halves path of Engine.gemm_tc."""
+    from tss_with_dprnn_b200.engine import Engine
+    A = rnd(M, K, seed=M) + 0.25
+    W = rnd(N, K, seed=N + 1) / K ** 0.5
+    bias = rnd(N, seed=3)
+    ref = A.double() @ W.double().t() + bias.double()
+    eng = Engine.__new__(Engine)
+    eng.conv_kind, eng.precision = 'f32x2', 'fp16'
+    kw = dict(bias=bias.to(DEV), epi=epi)
+    if epi == 1:
+        ref = torch.relu(ref)
+    elif epi == 2:
+        ref = torch.sigmoid(ref)
+    elif epi == 3:
+        ref = torch.tanh(ref[:, :N // 2]) * torch.sigmoid(ref[:, N // 2:])
+    elif epi == 4:
+        sc, sh, pa = 1 + 0.1 * rnd(N, seed=5), 0.1 * rnd(N, seed=6), torch.tensor([0.25])
+        ref = (A.double() @ W.double().t()) * sc.double() + sh.double()
+        ref = torch.where(ref >= 0, ref, 0.25 * ref)
+        kw = dict(post=(sc.to(DEV), sh.to(DEV), pa.to(DEV)))
+    n0 = P.lib().launches
+    out = Engine.gemm_tc(eng, A.to(DEV), W.to(DEV), M, N, K, **kw)
+    torch.cuda.synchronize()
+    assert P.lib().launches - n0 == (2 if N == 256 and K == 256 else 1)
+    assert torch.isfinite(out).all()
+    err = O.peak_rel_err(out.cpu(), ref.float())
+    assert err < (3e-5 if epi in (0, 1, 4) else 1e-3), err           # tanh.approx in the sigmoid / gated epilogues
+    eng.conv_kind = 'tf32'
+    out_t = Engine.gemm_tc(eng, A.to(DEV), W.to(DEV), M, N, K, **kw)
+    if epi == 0:
+        assert O.peak_rel_err(out_t.cpu(), ref.float()) > 3 * err    # what the split buys

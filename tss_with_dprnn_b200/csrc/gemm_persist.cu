@@ -8,6 +8,15 @@
 // The non-persistent gemm_tc_kernel (one CTA per tile, W reloaded per CTA, direct stores) reached 23-52 % of the
 // measured HBM bandwidth on these shapes; it remains for the statistics-emitting variant and as the small-M path.
 // Warps: 0 = ticket scheduler + TMA producer, 1 = MMA issuer, 2..5 = epilogue (TMEM lane quadrant = warp % 4).
+//
+// Operand kinds (argument a_is_bf16 of the C ABI): 0 = fp32 read by the tensor core as TF32, i.e. TRUNCATED to 10
+// mantissa bits - a coherent shrink of ~3.5e-4 per operand that measured as the dominant error of the fp16 mode (9.6e-4
+// against the reference with TF32 convs, 3.9e-4 with exact ones; tools/accuracy_matrix.py); 1 = bf16;
+// 2 = DPRNN_GEMM_F32X2: fp32 operands as PAIRS of bf16 (hi = bf16(a), lo = bf16(a - hi): 16 significand bits) and three
+// kind::f16 MMAs per K slice (hi*hi + lo*hi + hi*lo).  A still arrives as fp32 through TMA; warps 6..9 rewrite every
+// 128-byte row of a landed K-block IN PLACE as [hi(32) | lo(32)] bf16 (the bytes and the swizzle of the tile do not
+// change), W is packed that way once on the host ([N, 2K] bf16).  1.5x the MMA instructions of the TF32 form on a kernel
+// that waits for HBM anyway, and the convolutions then sit at 1e-5 instead of 1e-3.
 #include "tc_common.cuh"
 #include "../../include/dprnn_b200.h"
 
@@ -54,9 +63,33 @@ __device__ __forceinline__ void gp_tma_store_2d(const CUtensorMap* m, const void
                  ::"l"(m), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
 }
 
-// KB = number of 128-byte K-blocks (K * kElem / 128); AST = A ring stages
-template <int kElem, int KB, int N, int EPI, int AST>
-__global__ void __launch_bounds__(192, 1) gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
+// one thread = one row of a [128 x 32 fp32] SWIZZLE_128B K-block: fp32 -> [hi(32) | lo(32)] bf16, in place
+__device__ __forceinline__ void gp_split_row(uint8_t* tile, int r) {
+    float v[32];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const float4 t = *reinterpret_cast<const float4*>(tile + sw128_offset(r, c));
+        v[4 * c] = t.x; v[4 * c + 1] = t.y; v[4 * c + 2] = t.z; v[4 * c + 3] = t.w;
+    }
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+        const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+        const float2 hf = __bfloat1622float2(h);
+        const __nv_bfloat162 l = __floats2bfloat162_rn(v[2 * j] - hf.x, v[2 * j + 1] - hf.y);
+        hi[j] = *reinterpret_cast<const uint32_t*>(&h);
+        lo[j] = *reinterpret_cast<const uint32_t*>(&l);
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        *reinterpret_cast<uint4*>(tile + sw128_offset(r, c)) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+        *reinterpret_cast<uint4*>(tile + sw128_offset(r, 4 + c)) = make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+    }
+}
+
+// KB = number of 128-byte K-blocks (K * kElem / 128); AST = A ring stages; kSplit: DPRNN_GEMM_F32X2 (kElem == 4)
+template <int kElem, int KB, int N, int EPI, int AST, bool kSplit>
+__global__ void __launch_bounds__(kSplit ? 320 : 192, 1) gemm_persist_kernel(const __grid_constant__ CUtensorMap tmA,
                                                               const __grid_constant__ CUtensorMap tmW,
                                                               const __grid_constant__ CUtensorMap tmC,
                                                               const GemmPersistArgs a) {
@@ -67,18 +100,18 @@ __global__ void __launch_bounds__(192, 1) gemm_persist_kernel(const __grid_const
     uint8_t* sW = smem;                                 // KB blocks of [N rows x 128 B]
     uint8_t* sA = sW + KB * W_BLK;                      // AST blocks of [128 rows x 128 B]
     uint8_t* sC = sA + AST * GP_BLK;                    // GP_CST staging blocks [128 rows x 32 fp32]
-    __shared__ __align__(8) uint64_t a_full[AST], a_empty[AST], w_full, acc_full[2], acc_empty[2], tq_full[GP_TQ],
-        tq_empty[GP_TQ];
+    __shared__ __align__(8) uint64_t a_full[AST], a_empty[AST], a_conv[AST], w_full, acc_full[2], acc_empty[2],
+        tq_full[GP_TQ], tq_empty[GP_TQ];
     __shared__ int tile_q[GP_TQ];
     __shared__ uint32_t tmem_base_s;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if (threadIdx.x == 0) {
         prefetch_tmap(&tmA); prefetch_tmap(&tmW); prefetch_tmap(&tmC);
-        for (int s = 0; s < AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); }
+        for (int s = 0; s < AST; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 1); mbar_init(&a_conv[s], 4); }
         mbar_init(&w_full, 1);
         for (int s = 0; s < 2; ++s) { mbar_init(&acc_full[s], 1); mbar_init(&acc_empty[s], 4); }
-        for (int s = 0; s < GP_TQ; ++s) { mbar_init(&tq_full[s], 1); mbar_init(&tq_empty[s], 5); }
+        for (int s = 0; s < GP_TQ; ++s) { mbar_init(&tq_full[s], 1); mbar_init(&tq_empty[s], kSplit ? 9 : 5); }
         fence_barrier_init();
     }
     constexpr uint32_t TMEM_COLS = 2 * N <= 32 ? 32 : 2 * N <= 64 ? 64 : 2 * N <= 128 ? 128 : 2 * N <= 256 ? 256 : 512;
@@ -91,7 +124,7 @@ __global__ void __launch_bounds__(192, 1) gemm_persist_kernel(const __grid_const
     if (warp == 0) {
         if (elect_one()) {
             mbar_expect_tx(&w_full, KB * W_BLK);
-            for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * W_BLK, &tmW, &w_full, kb * (128 / kElem), 0);
+            for (int kb = 0; kb < KB; ++kb) tma_load_2d(sW + kb * W_BLK, &tmW, &w_full, kb * (kSplit ? 64 : 128 / kElem), 0);
             int it = 0;
             for (int n = 0;; ++n) {
                 int tile = (int)atomicAdd(a.ticket, 1u);
@@ -112,7 +145,7 @@ __global__ void __launch_bounds__(192, 1) gemm_persist_kernel(const __grid_const
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            constexpr uint32_t idesc = gp_idesc(kElem, 128, N);
+            constexpr uint32_t idesc = gp_idesc(kSplit ? 2 : kElem, 128, N);
             mbar_wait(&w_full, 0);
             int it = 0;
             for (int n = 0;; ++n) {
@@ -126,19 +159,51 @@ __global__ void __launch_bounds__(192, 1) gemm_persist_kernel(const __grid_const
                 tc_fence_after();
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % AST;
-                    mbar_wait(&a_full[s], (it / AST) & 1);
+                    mbar_wait(kSplit ? &a_conv[s] : &a_full[s], (it / AST) & 1);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(sA + s * GP_BLK), sb = smem_u32(sW + kb * W_BLK);
+                    if constexpr (kSplit) {
+                        // row = [hi(k..k+31) | lo(k..k+31)] bf16 in both operands: hi*hi + lo*hi + hi*lo per 16-k slice
 #pragma unroll
-                    for (int kk = 0; kk < 4; ++kk)
-                        gp_umma<kElem>(tmem + acc * N, umma_desc_sw128(sa + kk * 32), umma_desc_sw128(sb + kk * 32), idesc,
-                                       (kb | kk) ? 1u : 0u);
+                        for (int kk = 0; kk < 2; ++kk) {
+                            const uint64_t ah = umma_desc_sw128(sa + kk * 32), al = umma_desc_sw128(sa + 64 + kk * 32);
+                            const uint64_t wh = umma_desc_sw128(sb + kk * 32), wl = umma_desc_sw128(sb + 64 + kk * 32);
+                            gp_umma<2>(tmem + acc * N, ah, wh, idesc, (kb | kk) ? 1u : 0u);
+                            gp_umma<2>(tmem + acc * N, al, wh, idesc, 1u);
+                            gp_umma<2>(tmem + acc * N, ah, wl, idesc, 1u);
+                        }
+                    } else {
+#pragma unroll
+                        for (int kk = 0; kk < 4; ++kk)
+                            gp_umma<kElem>(tmem + acc * N, umma_desc_sw128(sa + kk * 32), umma_desc_sw128(sb + kk * 32), idesc,
+                                           (kb | kk) ? 1u : 0u);
+                    }
                     umma_commit(&a_empty[s]);
                 }
                 umma_commit(&acc_full[acc]);
             }
         }
         __syncwarp();
+    } else if (kSplit && warp >= 6) {
+        // ================= converter: every landed fp32 K-block of A becomes [hi | lo] bf16 in place =================
+        const int r = (warp - 6) * 32 + lane;
+        int it = 0;
+        for (int n = 0;; ++n) {
+            const int qs = n % GP_TQ;
+            mbar_wait(&tq_full[qs], (n / GP_TQ) & 1);
+            const int tile = tile_q[qs];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tq_empty[qs]);
+            if (tile < 0) break;
+            for (int kb = 0; kb < KB; ++kb, ++it) {
+                const int s = it % AST;
+                mbar_wait(&a_full[s], (it / AST) & 1);
+                gp_split_row(sA + s * GP_BLK, r);
+                fence_async_smem();              // generic-proxy writes -> visible to the tensor core (async proxy)
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&a_conv[s]);
+            }
+        }
     } else {
         const int q = warp & 3;
         const int r_in_tile = q * 32 + lane;
@@ -210,7 +275,7 @@ __global__ void __launch_bounds__(192, 1) gemm_persist_kernel(const __grid_const
     if (warp == 1) tmem_dealloc<1>(tmem, TMEM_COLS);
 }
 
-template <int kElem, int KB, int N, int EPI>
+template <int kElem, int KB, int N, int EPI, bool kSplit = false>
 static int launch_gp(const void* A, const void* W, float* C, long ldc, const GemmPersistArgs& args0, cudaStream_t st) {
     constexpr int K = KB * 128 / kElem;
     constexpr int N_OUT = EPI == DPRNN_EPI_GATED ? N / 2 : N;
@@ -229,10 +294,14 @@ static int launch_gp(const void* A, const void* W, float* C, long ldc, const Gem
     const uint32_t bC[2] = {32, 128};
     const CUtensorMapDataType dt = kElem == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     if (make_tmap(&tmA, dt, 2, A, dA, sA, bA)) return 1;
-    if (make_tmap(&tmW, dt, 2, W, dW, sW, bW)) return 1;
+    if constexpr (kSplit) {        // W packed on the host as [N, 2K] bf16: per 32 k, [hi(32) | lo(32)]
+        const uint64_t dW2[2] = {(uint64_t)2 * K, (uint64_t)N}, sW2[2] = {2, (uint64_t)K * 4};
+        const uint32_t bW2[2] = {64, (uint32_t)N};
+        if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, W, dW2, sW2, bW2)) return 1;
+    } else if (make_tmap(&tmW, dt, 2, W, dW, sW, bW)) return 1;
     if (make_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dC, sC, bC)) return 1;
     const size_t smem = (size_t)W_BYTES + (size_t)(AST + GP_CST) * GP_BLK + 1024;
-    auto kern = gemm_persist_kernel<kElem, KB, N, EPI, AST>;
+    auto kern = gemm_persist_kernel<kElem, KB, N, EPI, AST, kSplit>;
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
@@ -240,34 +309,34 @@ static int launch_gp(const void* A, const void* W, float* C, long ldc, const Gem
     GemmPersistArgs args = args0;
     args.tiles = (int)cdiv(M, 128);
     DPRNN_CUDA(cudaMemsetAsync(args.ticket, 0, sizeof(unsigned), st));
-    kern<<<args.tiles < sms ? args.tiles : sms, 192, smem, st>>>(tmA, tmW, tmC, args);
+    kern<<<args.tiles < sms ? args.tiles : sms, kSplit ? 320 : 192, smem, st>>>(tmA, tmW, tmC, args);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }
 
-template <int kElem, int KB, int N>
+template <int kElem, int KB, int N, bool kSplit>
 static int gp_dispatch_epi(const void* A, const void* W, float* C, long ldc, const GemmPersistArgs& args, int epi,
                            cudaStream_t st) {
     switch (epi) {
-        case DPRNN_EPI_NONE: return launch_gp<kElem, KB, N, DPRNN_EPI_NONE>(A, W, C, ldc, args, st);
-        case DPRNN_EPI_RELU: return launch_gp<kElem, KB, N, DPRNN_EPI_RELU>(A, W, C, ldc, args, st);
-        case DPRNN_EPI_SIGMOID: return launch_gp<kElem, KB, N, DPRNN_EPI_SIGMOID>(A, W, C, ldc, args, st);
-        case DPRNN_EPI_AFFINE_PRELU: return launch_gp<kElem, KB, N, DPRNN_EPI_AFFINE_PRELU>(A, W, C, ldc, args, st);
+        case DPRNN_EPI_NONE: return launch_gp<kElem, KB, N, DPRNN_EPI_NONE, kSplit>(A, W, C, ldc, args, st);
+        case DPRNN_EPI_RELU: return launch_gp<kElem, KB, N, DPRNN_EPI_RELU, kSplit>(A, W, C, ldc, args, st);
+        case DPRNN_EPI_SIGMOID: return launch_gp<kElem, KB, N, DPRNN_EPI_SIGMOID, kSplit>(A, W, C, ldc, args, st);
+        case DPRNN_EPI_AFFINE_PRELU: return launch_gp<kElem, KB, N, DPRNN_EPI_AFFINE_PRELU, kSplit>(A, W, C, ldc, args, st);
         case DPRNN_EPI_GATED:
-            if constexpr (N == 256) return launch_gp<kElem, KB, N, DPRNN_EPI_GATED>(A, W, C, ldc, args, st);
+            if constexpr (N == 256) return launch_gp<kElem, KB, N, DPRNN_EPI_GATED, kSplit>(A, W, C, ldc, args, st);
             break;
         default: break;
     }
     return -1;
 }
 
-template <int kElem, int KB>
+template <int kElem, int KB, bool kSplit = false>
 static int gp_dispatch_n(const void* A, const void* W, float* C, long ldc, const GemmPersistArgs& args, int N, int epi,
                          cudaStream_t st) {
-    if (N == 64) return gp_dispatch_epi<kElem, KB, 64>(A, W, C, ldc, args, epi, st);
-    if (N == 128) return gp_dispatch_epi<kElem, KB, 128>(A, W, C, ldc, args, epi, st);
+    if (N == 64) return gp_dispatch_epi<kElem, KB, 64, kSplit>(A, W, C, ldc, args, epi, st);
+    if (N == 128) return gp_dispatch_epi<kElem, KB, 128, kSplit>(A, W, C, ldc, args, epi, st);
     if (N == 256) {
-        if constexpr (KB <= 4) return gp_dispatch_epi<kElem, KB, 256>(A, W, C, ldc, args, epi, st);
+        if constexpr (KB <= 4) return gp_dispatch_epi<kElem, KB, 256, kSplit>(A, W, C, ldc, args, epi, st);
     }
     return -1;
 }
@@ -279,7 +348,9 @@ using namespace dprnn;
 extern "C" size_t dprnn_gemm_persist_workspace_bytes(void) { return 256; }
 
 // 1 if (elem, N, K, epilogue) is built for the persistent kernel
-extern "C" int dprnn_gemm_persist_supported(int a_is_bf16, int N, int K, int epilogue) {
+extern "C" int dprnn_gemm_persist_supported(int a_kind, int N, int K, int epilogue) {
+    if (a_kind < 0 || a_kind > DPRNN_GEMM_F32X2) return 0;
+    const int a_is_bf16 = a_kind == DPRNN_GEMM_BF16;
     const int kb = K * (a_is_bf16 ? 2 : 4) / 128;
     if ((K * (a_is_bf16 ? 2 : 4)) % 128) return 0;
     if (a_is_bf16 ? !(kb == 1 || kb == 2 || kb == 4) : !(kb == 2 || kb == 4 || kb == 8)) return 0;
@@ -289,13 +360,14 @@ extern "C" int dprnn_gemm_persist_supported(int a_is_bf16, int N, int K, int epi
     return epilogue >= DPRNN_EPI_NONE && epilogue <= DPRNN_EPI_AFFINE_PRELU;
 }
 
-extern "C" int dprnn_gemm_persist(const void* A, int a_is_bf16, const void* W, const float* bias, long bias_rows_per_utt,
+extern "C" int dprnn_gemm_persist(const void* A, int a_kind, const void* W, const float* bias, long bias_rows_per_utt,
                                   const int* bias_row_utt, const float* post_scale, const float* post_shift,
                                   const float* prelu_a, float* C, long ldc, int M, int N, int K, int epilogue,
                                   void* workspace, void* stream) {
     DPRNN_CHECK_ARG(A && W && C && workspace && M > 0 && ldc % 4 == 0);
     DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C | (uintptr_t)workspace) % 16 == 0);
-    DPRNN_CHECK_ARG(dprnn_gemm_persist_supported(a_is_bf16, N, K, epilogue));
+    DPRNN_CHECK_ARG(dprnn_gemm_persist_supported(a_kind, N, K, epilogue));
+    const int a_is_bf16 = a_kind == DPRNN_GEMM_BF16;
     DPRNN_CHECK_ARG(epilogue != DPRNN_EPI_GATED || bias);
     DPRNN_CHECK_ARG(epilogue != DPRNN_EPI_AFFINE_PRELU || (post_scale && post_shift && prelu_a));
     if (bias_rows_per_utt > 0) DPRNN_CHECK_ARG(bias && M % bias_rows_per_utt == 0 && epilogue != DPRNN_EPI_GATED);
@@ -308,13 +380,17 @@ extern "C" int dprnn_gemm_persist(const void* A, int a_is_bf16, const void* W, c
         if (kb == 1) rc = gp_dispatch_n<2, 1>(A, W, C, ldc, args, N, epilogue, st);
         else if (kb == 2) rc = gp_dispatch_n<2, 2>(A, W, C, ldc, args, N, epilogue, st);
         else if (kb == 4) rc = gp_dispatch_n<2, 4>(A, W, C, ldc, args, N, epilogue, st);
+    } else if (a_kind == DPRNN_GEMM_F32X2) {
+        if (kb == 2) rc = gp_dispatch_n<4, 2, true>(A, W, C, ldc, args, N, epilogue, st);
+        else if (kb == 4) rc = gp_dispatch_n<4, 4, true>(A, W, C, ldc, args, N, epilogue, st);
+        else if (kb == 8) rc = gp_dispatch_n<4, 8, true>(A, W, C, ldc, args, N, epilogue, st);
     } else {
         if (kb == 2) rc = gp_dispatch_n<4, 2>(A, W, C, ldc, args, N, epilogue, st);
         else if (kb == 4) rc = gp_dispatch_n<4, 4>(A, W, C, ldc, args, N, epilogue, st);
         else if (kb == 8) rc = gp_dispatch_n<4, 8>(A, W, C, ldc, args, N, epilogue, st);
     }
     if (rc == -1) {
-        set_error("dprnn_gemm_persist: (bf16=%d, N=%d, K=%d, epilogue=%d) is not built", a_is_bf16, N, K, epilogue);
+        set_error("dprnn_gemm_persist: (kind=%d, N=%d, K=%d, epilogue=%d) is not built", a_kind, N, K, epilogue);
         return 2;
     }
     return rc;

@@ -35,7 +35,11 @@ class Engine(RaggedMixin):
         # fp32 master copy (False / env DPRNN_RESIDUAL_BF16=0) is ~1 dB closer to the reference and ~9 % slower
         self.residual_bf16 = os.environ.get('DPRNN_RESIDUAL_BF16', '1') == '1'
         self.lstm_pingpong = True      # half-job ping-pong LSTM kernel (bf16 mode, uniform batches; bit-identical results)
-        self.fast_act = True       # bf16 mode: tanh.approx-based gate activations (1 MUFU op each)
+        self.fast_act = True       # tensor-core modes: tanh.approx-based gate activations (1 MUFU op each)
+        # tensor-core modes, the 1x1 convolutions: None = by precision ('fp16' -> 'f32x2', 'bf16' -> 'tf32'); 'tf32' = fp32
+        # operands truncated to TF32 by the tensor core; 'f32x2' = fp32 operands as bf16 pairs, 3 MMAs (16 significand bits:
+        # TF32 truncation was the dominant error of the fp16 mode); 'fp32' = exact CUDA-core GEMM (diagnosis)
+        self.conv_kind = None
         self.n_streams = 1         # >1: the batch is split into that many utterance groups on concurrent streams
         self.fused_tail = False    # bf16 mode: Linear + norm + residual as one persistent kernel (linear_norm.cu)
         self._row_off = {}
@@ -61,6 +65,30 @@ class Engine(RaggedMixin):
         return self.precision != 'fp32'
 
     @property
+    def conv_mode(self) -> str:
+        return getattr(self, 'conv_kind', None) or ('f32x2' if getattr(self, 'precision', 'bf16') == 'fp16' else 'tf32')
+
+    @property
+    def tc_conv(self) -> bool:
+        return self.tc and self.conv_mode != 'fp32'
+
+    @property
+    def conv_tf32(self) -> bool:          # name kept for the call sites: "the convolutions run on the tensor cores"
+        return self.conv_mode != 'fp32'
+
+    def _w_x2(self, W):
+        """[N, K] fp32 weight -> [N, 2K] bf16 for DPRNN_GEMM_F32X2: per 32 consecutive k, hi(32) then lo(32)."""
+        cache = self.__dict__.setdefault('_x2', {})          # dropped by invalidate() together with the other packs
+        key = (W.data_ptr(), tuple(W.shape))
+        if key not in cache:
+            N, K = W.shape
+            w = W.detach().float().reshape(N, K // 32, 32)
+            hi = w.to(torch.bfloat16)
+            lo = (w - hi.float()).to(torch.bfloat16)
+            cache[key] = (torch.cat([hi, lo], -1).reshape(N, 2 * K).contiguous(), W)     # W kept alive: its address is the key
+        return cache[key][0]
+
+    @property
     def h16(self) -> int:
         """DPRNN_H16_* code of the 16-bit operand / storage format"""
         return 1 if self.precision == 'fp16' else 0
@@ -79,6 +107,7 @@ class Engine(RaggedMixin):
         self._packed = None
         self._packed_key = None
         self._graphs = {}
+        self._x2 = {}
 
     def _weights_key(self):
         """Key of the kernel-layout weight copies: a re-seated or in-place-updated parameter changes it.  Writes torch
@@ -94,6 +123,7 @@ class Engine(RaggedMixin):
         """Kernel-layout copies of the weights, rebuilt whenever a parameter changes."""
         key = self._weights_key()
         if self._packed is None or key != self._packed_key:
+            self._x2 = {}
             self._packed = self._pack()
             self._packed_key = key
         return self._packed
@@ -190,12 +220,17 @@ class Engine(RaggedMixin):
     def _stream():
         return torch.cuda.current_stream().cuda_stream
 
-    @staticmethod
-    def _check_input(x, name):
+    def _check_input(self, x, name):
         if not isinstance(x, torch.Tensor) or not x.is_cuda:
             raise RuntimeError(f'{name} must be a CUDA tensor: tss_with_dprnn_b200 has no CPU path')
         if x.dtype != torch.float32:
             raise TypeError(f'{name} must be float32')
+        # every C-ABI call launches on the calling thread's CURRENT device and stream: a tensor or model on another
+        # device would hand kernels of GPU a pointers of GPU b
+        pdev = next(self.model.parameters()).device
+        if x.device != pdev or x.device.index != torch.cuda.current_device():
+            raise RuntimeError(f'{name} is on {x.device}, the model on {pdev}, the current CUDA device is '
+                               f'cuda:{torch.cuda.current_device()}: run the call under torch.cuda.device(model device)')
         return x.contiguous()
 
     def _row_offsets(self, B, R, dev):
@@ -241,9 +276,22 @@ class Engine(RaggedMixin):
         if out is None:
             out = torch.empty((M, n_out), device=A.device, dtype=torch.float32)
         is_bf16 = int(A.dtype == torch.bfloat16)
+        ps, psh, pa = post if post is not None else (None, None, None)
+        if stats is None and A.dtype == torch.float32 and self.conv_mode == 'f32x2' and K % 32 == 0 and W.numel() == N * K:
+            # fp32 operands as bf16 pairs (DPRNN_GEMM_F32X2); a weight too large to stay resident (N = K = 256: the last
+            # ResBlock of the speaker encoder) is cut into two 128-row halves writing the two column halves of C
+            parts = [(0, N)] if L_.query('dprnn_gemm_persist_supported', 2, N, K, epi) else \
+                [(0, N // 2), (N // 2, N // 2)] if epi != EPI_GATED and L_.query('dprnn_gemm_persist_supported', 2, N // 2, K, epi) else []
+            if parts and (len(parts) == 1 or not (bias_rows_per_utt or bias_row_utt is not None)):
+                ws = torch.empty(L_.query('dprnn_gemm_persist_workspace_bytes'), device=A.device, dtype=torch.uint8)
+                Wc = W.detach().reshape(N, K)          # a view: parameters and packed weights are contiguous
+                for n0, nn in parts:
+                    L_.call('dprnn_gemm_persist', A, 2, self._w_x2(Wc[n0:n0 + nn]), None if bias is None else bias[..., n0:] if bias.dim() == 1 else bias,
+                            int(bias_rows_per_utt), bias_row_utt, None if ps is None else ps[n0:], None if psh is None else psh[n0:],
+                            pa, out[:, n0:] if len(parts) > 1 else out, n_out, M, nn, K, epi, ws, self._stream())
+                return out
         if stats is None and L_.query('dprnn_gemm_persist_supported', is_bf16, N, K, epi):
             ws = torch.empty(L_.query('dprnn_gemm_persist_workspace_bytes'), device=A.device, dtype=torch.uint8)
-            ps, psh, pa = post if post is not None else (None, None, None)
             L_.call('dprnn_gemm_persist', A, is_bf16, W, bias, int(bias_rows_per_utt), bias_row_utt, ps, psh, pa, out,
                     n_out, M, N, K, epi, ws, self._stream())
             return out
@@ -314,7 +362,7 @@ class Engine(RaggedMixin):
         s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
         L_.call('dprnn_norm_affine', mr, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
         O = se[1].weight.shape[0]
-        if self.tc and N % 32 == 0 and O in (64, 128, 256):
+        if self.tc_conv and N % 32 == 0 and O in (64, 128, 256):
             fn = torch.empty_like(feats)            # GroupNorm applied, then the 1x1 conv on the tensor cores (TF32)
             L_.call('dprnn_prologue_apply', feats, fn, B * Lr, N, Lr, s1, s0, None, None, st)
             x = self.gemm_tc(fn, se[1].weight.detach(), B * Lr, O, N, bias=se[1].bias.detach())
@@ -336,7 +384,7 @@ class Engine(RaggedMixin):
                 if training:
                     bnm.num_batches_tracked += 1
 
-            tc = self.tc and Cin in (128, 256) and Cout in (128, 256)
+            tc = self.tc_conv and Cin in (128, 256) and Cout in (128, 256)
 
             def conv(inp, conv_mod, wt, cin, cout):
                 if tc:
@@ -361,7 +409,7 @@ class Engine(RaggedMixin):
                     Cout, st)
             x, Lx = out, Lo
         E = se[5].weight.shape[0]
-        if self.tc and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
+        if self.tc_conv and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
             z = self.gemm_tc(x, se[5].weight.detach(), B * Lx, E, se[5].weight.shape[1], bias=se[5].bias.detach())
         else:
             z = self.gemm(x, W['spk_conv5_t'], B * Lx, E, se[5].weight.shape[1], bias=se[5].bias.detach())
@@ -419,7 +467,7 @@ class Engine(RaggedMixin):
             L_.call('dprnn_att_rowscale', enc, n1, n0, sep.average.weight.detach(), sep.average.bias.detach(), mulc,
                     scores, rowscale, B, L, N, k, st)
         L_.call('dprnn_norm_affine', mr, gamma, beta, mulc, s1, s0, B, N, st)
-        if self.tc and N % 32 == 0 and F in (64, 128, 256):
+        if self.tc_conv and N % 32 == 0 and F in (64, 128, 256):
             en = torch.empty_like(enc)              # norm + fusion applied, then the 1x1 conv on the tensor cores (TF32)
             L_.call('dprnn_prologue_apply', enc, en, B * L, N, L, s1, s0, addc, rowscale, st)
             y = self.gemm_tc(en, W['bott_w_x'], B * L, F, N, bias=bias, bias_rows_per_utt=L if bias_per_utt else 0)
@@ -548,7 +596,7 @@ class Engine(RaggedMixin):
             if cov is None:
                 raise NotImplementedError('hop_length must be chunk_length/2 (every shipped config)')
             out = None if outs is None else outs[len(masks)].view(B * L, N)
-            if bf16 and F == 128 and N == 64:
+            if bf16 and self.conv_tf32 and F == 128 and N == 64:
                 u = self.gemm_tc(z, W['conv2d_w'][spk], B * L, F, F, bias=W['conv2d_b2'][spk])
                 g = self.gemm_tc(u, W['og_w'], B * L, 2 * F, F, bias=W['og_bias'], epi=EPI_GATED)
                 masks.append(self.gemm_tc(g, W['end_w'], B * L, N, F, epi=act, out=out).view(B, L, N))
@@ -575,7 +623,7 @@ class Engine(RaggedMixin):
         if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
         key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
-               self.fast_act, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self._graph_key())
+               self.fast_act, self.conv_mode, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self._graph_key())
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = 'seen'

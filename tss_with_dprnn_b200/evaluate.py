@@ -85,7 +85,12 @@ def evaluate(model, mixtures, references=None, targets=None, bucket: int = 64, r
         for j in range(len(mine)):
             cur = nxt
             nxt = stage(buckets[mine[j + 1]]) if j + 1 < len(mine) else None
-            torch.cuda.current_stream().wait_event(cur['ready'])
+            main = torch.cuda.current_stream()
+            main.wait_event(cur['ready'])
+            for v in cur.values():          # allocated on the copy stream, consumed on this one: keep the caching allocator
+                t = v.data if isinstance(v, _Pcm) else v        # from re-using the blocks before this stream is done
+                if isinstance(t, torch.Tensor) and t.is_cuda:
+                    t.record_stream(main)
             if tss:
                 est, logits = model.forward_ragged((cur['mix'], cur['Ts']), (cur['ref'], cur['Trs']))
             else:

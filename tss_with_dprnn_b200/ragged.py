@@ -160,7 +160,7 @@ class RaggedMixin:
         s1 = torch.empty((B, N), device=dev); s0 = torch.empty_like(s1)
         L_.call('dprnn_norm_affine', mr, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
         O = se[1].weight.shape[0]
-        if self.tc and N % 32 == 0 and O in (64, 128, 256):     # same arithmetic as the uniform path
+        if self.tc_conv and N % 32 == 0 and O in (64, 128, 256):     # same arithmetic as the uniform path
             fn = torch.empty_like(feats)
             L_.call('dprnn_prologue_apply_ragged', feats, fn, lay.total_rows, N, lay.frame_utt, s1, s0, None, None, st)
             x = self.gemm_tc(fn, se[1].weight.detach(), lay.total_rows, O, N, bias=se[1].bias.detach())
@@ -177,7 +177,7 @@ class RaggedMixin:
                 L_.call('dprnn_batchnorm_affine', None, rows, Cout, bnm.weight.detach(), bnm.bias.detach(),
                         bnm.running_mean, bnm.running_var, 0, float(bnm.eps), 0.1, None, scale, shift, st)
 
-            tc = self.tc and Cin in (128, 256) and Cout in (128, 256)
+            tc = self.tc_conv and Cin in (128, 256) and Cout in (128, 256)
 
             def conv(inp, conv_mod, wt, cin, cout):
                 if tc:
@@ -200,7 +200,7 @@ class RaggedMixin:
                     stage['out_utt'], stage['in_off'], stage['out_off'], stage['total_out'], Cout, st)
             x, rows = out, stage['total_out']
         E = se[5].weight.shape[0]
-        if self.tc and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
+        if self.tc_conv and E in (64, 128, 256) and se[5].weight.shape[1] % 32 == 0:
             z = self.gemm_tc(x, se[5].weight.detach(), rows, E, se[5].weight.shape[1], bias=se[5].bias.detach())
         else:
             z = self.gemm(x, W['spk_conv5_t'], rows, E, se[5].weight.shape[1], bias=se[5].bias.detach())
@@ -245,7 +245,7 @@ class RaggedMixin:
                     mulc, scores, rowscale, lay.frame_utt, lay.frame_off, lay.L_d, lay.La_d, B, TR, N,
                     cfg['kernel_size'], st)
         L_.call('dprnn_norm_affine', mr, gamma, beta, mulc, s1, s0, B, N, st)
-        if self.tc and N % 32 == 0 and F in (64, 128, 256):
+        if self.tc_conv and N % 32 == 0 and F in (64, 128, 256):
             en = torch.empty_like(enc)
             L_.call('dprnn_prologue_apply_ragged', enc, en, TR, N, lay.frame_utt, s1, s0, addc, rowscale, st)
             y = self.gemm_tc(en, W['bott_w_x'], TR, F, N, bias=bias, bias_row_utt=lay.frame_utt if bias_per_utt else None)
@@ -315,7 +315,7 @@ class RaggedMixin:
         act = EPI_SIGMOID if cfg['activation_type'] == 'sigmoid' else EPI_RELU
         masks = []
         for spk in speakers:
-            if bf16 and F == 128 and N == 64:
+            if bf16 and self.conv_tf32 and F == 128 and N == 64:
                 u = self.gemm_tc(z, W['conv2d_w'][spk], TR, F, F, bias=W['conv2d_b2'][spk])
                 g = self.gemm_tc(u, W['og_w'], TR, 2 * F, F, bias=W['og_bias'], epi=EPI_GATED)
                 masks.append(self.gemm_tc(g, W['end_w'], TR, N, F, epi=act))

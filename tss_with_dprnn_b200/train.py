@@ -1,16 +1,20 @@
-"""Training step of the separation path (cfg 5: DPRNN-Spe, src/trainers/trainer_spe.py:14-72): forward in train mode
-(BatchNorm batch statistics, running-stat updates) that keeps what the backward needs, and the hand-written backward
-(csrc/backward.cu, csrc/lstm_simt.cu) - exact fp32 on CUDA cores, correctness first.  The loss lives in the caller
-(asteroid's PIT / SI-SDR wrapper + CrossEntropyLoss in the reference trainer), so the model is exposed to autograd as ONE
-``torch.autograd.Function``: forward -> (est, logits), backward(d_est, d_logits) -> parameter gradients.
+"""Training step of the separation path (cfg 5: DPRNN-Spe, src/trainers/trainer_spe.py:14-72; DPRNN-TasNet:
+src/trainers/trainer.py:100-118): forward in train mode (BatchNorm batch statistics, running-stat updates) that keeps
+what the backward needs, and the hand-written backward (csrc/backward.cu, csrc/lstm_simt.cu, csrc/lstm_bptt_tc.cu,
+csrc/atb_tc.cu).  precision 'fp32': exact fp32 on CUDA cores; 'bf16': LSTM forward / BPTT contractions on tcgen05 with
+bf16 operands, Linear / dX / weight-gradient contractions in TF32 (cfg 5: "bf16 gate GEMMs").  The loss lives in the
+caller (asteroid's PIT / SI-SDR wrapper + CrossEntropyLoss in the reference trainer), so the model is exposed to autograd
+as ONE ``torch.autograd.Function``: forward -> (est, logits), backward(d_est, d_logits) -> parameter gradients;
+``SpeTrainStep`` runs the whole iteration (loss kernel, all-reduce, fused clip + Adam) as device work.
 
 Memory: per half-block the forward keeps the LSTM gates / cell state / output and the Linear output (13 A, A = one
 [B,S,K,128] fp32 tensor = 0.40 GB at B = 16); the block inputs are NOT kept - the residual stream is reversible
-(x_in = x_out - norm(y)), so the backward walks it back while it walks the blocks in reverse.
+(x_in = x_out - norm(y)), so the backward walks it back while it walks the blocks in reverse (which is also why a forward
+can be differentiated only once).
 
-Supported: DPRNNSpeTasNet with fusion_type in {film, add, mul, cat}, 'ln' / 'gLN' norms, sigmoid / relu mask activation,
-kernel_size 2 / stride 1, feature_size = hidden_size = 128.  The attention fusion, the IRA model and DPRNN-TasNet keep
-raising NotImplementedError in train mode.
+Supported: DPRNNTasNet and DPRNNSpeTasNet with fusion_type in {film, add, mul, cat, att}, 'ln' / 'gLN' norms, sigmoid /
+relu mask activation, uni- or bidirectional inter-RNN, kernel_size 2 / stride 1, feature_size = hidden_size = 128; frozen
+parameters are skipped.  DPRNN-Spe-IRA and DPRNN-RawNet raise NotImplementedError in train mode with autograd on.
 """
 from __future__ import annotations
 
@@ -340,8 +344,18 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
     enc, feats, emb, div = ctx['enc'], ctx['feats'], ctx['emb'], ctx['div']
     is_spe = cfg['kind'] == 'spe'
     E = emb.shape[1] if is_spe else 0
+    if ctx.get('consumed'):
+        raise RuntimeError('this forward has already been differentiated: the hand-written backward walks the saved '
+                           'activations back in place (retain_graph / a second backward is not supported)')
+    ctx['consumed'] = True
     if G is None:
         G = {n: torch.zeros_like(p) for n, p in model.named_parameters() if p.requires_grad}
+    # frozen parameters (fine-tuning with e.g. a frozen speaker encoder; the reference optimises filter(requires_grad),
+    # src/trainers/trainer.py:42-43): their gradients are computed into scratch and dropped
+    G = dict(G)
+    for n, p in model.named_parameters():
+        if n not in G:
+            G[n] = torch.zeros_like(p)
     d_est = d_est.contiguous().float()
     if is_spe:
         d_logits = d_logits.contiguous().float()
