@@ -520,7 +520,7 @@ def gpu_reference(args, dev):
         torch.manual_seed(0)
         model = RefModel(**KW).eval().to(dev)
         mix, ref = synth(args.batch, args.samples, 0, dev)
-        rl = torch.tensor(float(args.samples))
+        rl = torch.tensor(float(args.samples), device=dev)      # dprnn_spe.py:159-161 divides a device tensor by it
         old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
         for name, tf32 in (('fp32', False), ('tf32_allowed', True)):
             torch.backends.cuda.matmul.allow_tf32 = tf32

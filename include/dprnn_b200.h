@@ -319,15 +319,16 @@ int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, const float* b
 int dprnn_lstm_inter_bf16_ragged_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout,
                                     long total_chunks, int K, const void* utt_jobs, int n_utt, int hidden, int ndir,
                                     int fast_act, void* stream);
-/* dprnn_lstm_layer_bf16 as a persistent kernel over time-sliced jobs (csrc/lstm_tc_sliced.cu): every (tile, direction) job
- * is cut into nslices slices handed out by an atomic ticket to <= #SM/2 resident CTA pairs, which turns ceil(jobs/74)
- * waves into ceil(nslices*jobs/74)/nslices.  Same arguments and results (bit for bit) as dprnn_lstm_layer_bf16;
- * workspace (dprnn_lstm_sliced_workspace_bytes) holds the ticket, per-job completion counters and the cell-state
- * hand-off; it is re-armed by every call.  max_pairs > 0 caps the number of resident CTA pairs (the SMs left over serve
- * the memory-bound kernels of concurrent streams). */
+/* dprnn_lstm_layer_bf16_pp as a PERSISTENT kernel over time-sliced jobs (csrc/lstm_tc_sliced.cu): every (tile, direction)
+ * job is cut into nslices slices of ceil(T / nslices) steps which <= 74 resident CTA pairs draw by atomic ticket, turning
+ * ceil(jobs / 74) waves into ceil(nslices * jobs / 74) / nslices.  Same arguments (flags: DPRNN_LSTM_*), weight packing and
+ * results (bit for bit) as dprnn_lstm_layer_bf16_pp; nslices <= 0: chosen by dprnn_lstm_sliced_auto; max_pairs > 0 caps
+ * the resident pairs; workspace: dprnn_lstm_sliced_workspace_bytes(...) bytes, 256-byte aligned, private to the call while
+ * it runs (scheduler ticket, per-job completion counters, the cell-state hand-off scratch). */
 size_t dprnn_lstm_sliced_workspace_bytes(int B, int S, int K, int inter, int ndir);
+int dprnn_lstm_sliced_auto(int B, int S, int K, int inter, int ndir, int pairs, int kmax);
 int dprnn_lstm_layer_bf16_sliced(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
-                                 int inter, int hidden, int ndir, int fast_act, int nslices, int max_pairs, void* workspace,
+                                 int inter, int hidden, int ndir, int flags, int nslices, int max_pairs, void* workspace,
                                  void* stream);
 /* Inter-chunk layer of dprnn_lstm_layer_bf16 on the packed chunk space: utt_jobs = n_utt x {int32 first chunk, int32
  * number of chunks}, in the order the pair-jobs should be scheduled (longest first). */

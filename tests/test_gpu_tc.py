@@ -215,29 +215,44 @@ def test_linear_bf16out_then_norm_residual(B, R, K):
 
 
 @pytest.mark.parametrize('inter', [0, 1])
-@pytest.mark.parametrize('nslices', [1, 2, 3, 7])
-def test_lstm_sliced_persistent_is_bit_identical(inter, nslices):
-    """The persistent, time-sliced LSTM kernel (cell state through a global scratch, h re-read from the stored rows)
-    returns bit for bit what the one-job-per-pair kernel returns."""
+@pytest.mark.parametrize('nslices', [0, 1, 2, 3, 7])
+@pytest.mark.parametrize('fmt', ['bf16', 'fp16'])
+def test_lstm_sliced_persistent_is_bit_identical(inter, nslices, fmt):
+    """The persistent, time-sliced half-job LSTM kernel (cell state through a global scratch, h re-read from the stored
+    rows, weights re-loaded when the drawn item changes direction) returns bit for bit what the one-job-per-pair half-job
+    kernel returns; nslices = 0 lets the launcher choose; 3 resident pairs force many items per pair."""
     from tss_with_dprnn_b200.engine import Engine
     L = P.lib()
     B, S, K, H, nd = 5, 30, 250, 128, 2                      # intra: 150 sequences; inter: 5 tiles x 2 dirs, T = 30
+    dtype = torch.float16 if fmt == 'fp16' else torch.bfloat16
+    flags = 1 | (2 if fmt == 'fp16' else 0)
     torch.manual_seed(3 + inter)
     rnn = torch.nn.LSTM(H, H, 1, batch_first=True, bidirectional=True).cuda()
     rows = B * S * K
-    xb = (0.5 * torch.randn(rows, H, generator=torch.Generator().manual_seed(4))).cuda().to(torch.bfloat16)
-    wp, bp = Engine._pack_lstm_tc(rnn, ['', '_reverse'])
+    xb = (0.5 * torch.randn(rows, H, generator=torch.Generator().manual_seed(4))).cuda().to(dtype)
+    wp2, bp = Engine._pack_lstm_tc(rnn, ['', '_reverse'], half_jobs=True, dtype=dtype)
     st = torch.cuda.current_stream().cuda_stream
-    want = torch.empty(rows, nd * H, device='cuda', dtype=torch.bfloat16)
-    L.call('dprnn_lstm_layer_bf16', xb, wp, bp, want, B, S, K, inter, H, nd, 1, st)
-    got = torch.full((rows + 1, nd * H), 7.0, device='cuda', dtype=torch.bfloat16)
+    want = torch.empty(rows, nd * H, device='cuda', dtype=dtype)
+    L.call('dprnn_lstm_layer_bf16_pp', xb, wp2, bp, want, B, S, K, inter, H, nd, flags, st)
+    got = torch.full((rows + 1, nd * H), 7.0, device='cuda', dtype=dtype)
     ws = torch.empty(L.query('dprnn_lstm_sliced_workspace_bytes', B, S, K, inter, nd), device='cuda', dtype=torch.uint8)
     for _ in range(2):                                       # the workspace is re-armed by every call
-        L.call('dprnn_lstm_layer_bf16_sliced', xb, wp, bp, got, B, S, K, inter, H, nd, 1, nslices, 3 if nslices == 3 else 0,
-               ws, st)
+        L.call('dprnn_lstm_layer_bf16_sliced', xb, wp2, bp, got, B, S, K, inter, H, nd, flags, nslices,
+               3 if nslices in (0, 3) else 0, ws, st)
         torch.cuda.synchronize()
         assert torch.equal(got[:rows], want)
         assert float((got[rows:].float() - 7.0).abs().max()) == 0.0
+
+
+def test_lstm_sliced_auto_picks_the_packing_slices():
+    """dprnn_lstm_sliced_auto minimises ceil(k J / pairs) * ceil(T / k): the headline layers (B = 64, 3 s) on 74 pairs."""
+    L = P.lib()
+    assert L.query('dprnn_lstm_sliced_auto', 64, 194, 250, 0, 2, 74, 8) == 3      # intra: J = 98, 294 items = 3.97 rounds
+    k_inter = L.query('dprnn_lstm_sliced_auto', 64, 194, 250, 1, 2, 74, 8)        # inter: J = 128
+    import math
+    cost = lambda k, J, T: math.ceil(k * J / 74) * math.ceil(T / k)
+    assert cost(k_inter, 128, 194) == min(cost(k, 128, 194) for k in range(1, 9))
+    assert L.query('dprnn_lstm_sliced_auto', 1, 194, 250, 0, 2, 74, 8) == 1       # one wave already: no slicing
 
 
 @pytest.mark.parametrize('inter', [0, 1])

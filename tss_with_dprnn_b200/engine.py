@@ -29,7 +29,7 @@ class Engine(RaggedMixin):
     def __init__(self, model):
         self.model = model
         self.precision = 'fp32'
-        self.lstm_slices = 1           # > 1: time-sliced persistent LSTM kernel (bf16 mode, uniform batches)
+        self.lstm_slices = 1           # time-sliced persistent LSTM kernel (uniform batches): 1 = off, k > 1 slices, 0 = auto
         self.lstm_pairs = 0            # > 0: cap on the CTA pairs that kernel keeps resident (0 = all SM pairs)
         # bf16 mode: the residual stream between the half-blocks lives in bf16 only (what the LSTM consumes anyway); the
         # fp32 master copy (False / env DPRNN_RESIDUAL_BF16=0) is ~1 dB closer to the reference and ~9 % slower
@@ -501,6 +501,18 @@ class Engine(RaggedMixin):
     def _half_lstm(self, s, bi, which):
         """bf16 mode: one nn.LSTM layer (intra: which=0, inter: which=1) as the fused tcgen05 kernel -> s['hb']."""
         hw = self.packed()['blocks'][bi][which]
+        if self.lstm_pingpong and self.lstm_slices != 1:
+            # persistent CTA pairs over time-sliced jobs (lstm_tc_sliced.cu): the half-job ping-pong step, bit-identical
+            # results, no part-empty last wave when the layer has more pair-jobs than the GPU has SM pairs
+            key = ('lstm_ws', s['B'], s['S'], s['K'], which, hw['ndir'], torch.cuda.current_stream().cuda_stream)
+            ws = s.get(key)
+            if ws is None:
+                ws = s[key] = torch.empty(lib().query('dprnn_lstm_sliced_workspace_bytes', s['B'], s['S'], s['K'], which,
+                                                      hw['ndir']), device=s['dev'], dtype=torch.uint8)
+            lib().call('dprnn_lstm_layer_bf16_sliced', s['xb'], hw['tc_w2'], hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'],
+                       which, s['H'], hw['ndir'], self._lstm_flags(), int(self.lstm_slices), int(self.lstm_pairs), ws,
+                       self._stream())
+            return
         if self.lstm_pingpong:
             # two half-jobs per CTA pair in ping-pong (lstm_tc_pp.cu): bit-identical results, the hand-off of one half-job
             # hidden under the cell update of the other
@@ -509,18 +521,6 @@ class Engine(RaggedMixin):
             return
         if self.precision == 'fp16':
             raise NotImplementedError("precision 'fp16' is built for the default LSTM kernel (lstm_pingpong = True)")
-        if self.lstm_slices > 1:
-            # persistent CTA pairs over time-sliced jobs (lstm_tc_sliced.cu): bit-identical results, fewer idle SMs when
-            # the layer has more pair-jobs than the GPU has SM pairs
-            key = ('lstm_ws', s['B'], s['S'], s['K'], which, hw['ndir'], torch.cuda.current_stream().cuda_stream)
-            ws = s.get(key)
-            if ws is None:
-                ws = s[key] = torch.empty(lib().query('dprnn_lstm_sliced_workspace_bytes', s['B'], s['S'], s['K'], which,
-                                                      hw['ndir']), device=s['dev'], dtype=torch.uint8)
-            lib().call('dprnn_lstm_layer_bf16_sliced', s['xb'], hw['tc_w'], hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'],
-                       which, s['H'], hw['ndir'], int(self.fast_act), int(self.lstm_slices), int(self.lstm_pairs), ws,
-                       self._stream())
-            return
         lib().call('dprnn_lstm_layer_bf16', s['xb'], hw['tc_w'], hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'], which,
                    s['H'], hw['ndir'], int(self.fast_act), self._stream())
 
