@@ -156,11 +156,12 @@ def test_bf16_mode_sisdr(case, fast_act):
         assert sdr_vs_ref.min() > 33.0, sdr_vs_ref
         assert O.peak_rel_err(est, want) < 4e-2
         return
-    # measured (profiles/r1_accuracy_report.txt): 51-53 dB / 3.2e-3 on the full-depth fixtures, 67-68 dB / 8e-4 on the
-    # 2-block ones; thresholds = measured - 5 dB (a regression of the operand handling shows up as >= 6 dB)
-    deep = '_r6' in case
-    assert sdr_vs_ref.min() > (46.0 if deep else 60.0), sdr_vs_ref
-    assert O.peak_rel_err(est, want) < (6e-3 if deep else 2e-3)
+    # measured (profiles/r2_accuracy_report.txt): 51-53 dB / 3.2e-3 on the full-depth synthetic fixtures, 48.1 dB / 7.1e-3
+    # on the real-speech one, 67-68 dB / 8e-4 on the 2-block ones; thresholds = measured - 5 dB / x1.7 (a regression of
+    # the operand handling shows up as >= 6 dB)
+    floor_db, ceil_err = (43.0, 1.2e-2) if case.startswith('speech') else (46.0, 6e-3) if '_r6' in case else (60.0, 2e-3)
+    assert sdr_vs_ref.min() > floor_db, sdr_vs_ref
+    assert O.peak_rel_err(est, want) < ceil_err
     g = torch.Generator().manual_seed(77)
     noise = torch.randn(want.shape, generator=g)
     noise = noise * (want.pow(2).sum(-1, keepdim=True) / noise.pow(2).sum(-1, keepdim=True) / 10 ** 1.3).sqrt()
