@@ -316,6 +316,14 @@ int dprnn_gemm_tc_ragged(const void* A, int a_is_bf16, const void* W, const floa
  * (same 1/2 pre-scale of the i, f, o rows); bias_perm as dprnn_lstm_layer_bf16. */
 int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
                              int inter, int hidden, int ndir, int fast_act, void* stream);
+/* ... on the input x_in + norm(y): the norm + residual that ends the previous half-block (src/models/dprnn.py:90-92,
+ * 98-99; mean_rstd [B,2] per utterance, gamma / beta [128]) is applied to every input tile in shared memory before the
+ * tensor core reads it, and x_out [rows,128] (16-bit, NOT x_in) receives the updated residual stream.  Results are bit for
+ * bit those of dprnn_norm_residual_h16res followed by dprnn_lstm_layer_bf16_pp; the stand-alone norm pass (2.4 GB per
+ * half-block at B = 64) disappears.  Uniform batches, inference. */
+int dprnn_lstm_layer_bf16_pp_fused(const void* x_in, const void* y, const float* mean_rstd, const float* gamma,
+                                   const float* beta, void* x_out, const void* w_packed, const float* bias_perm, void* hout,
+                                   int B, int S, int K, int inter, int hidden, int ndir, int flags, void* stream);
 int dprnn_lstm_inter_bf16_ragged_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout,
                                     long total_chunks, int K, const void* utt_jobs, int n_utt, int hidden, int ndir,
                                     int fast_act, void* stream);

@@ -244,3 +244,27 @@ def test_stream_groups_bit_exact(precision):
         e3, l3 = model(mix, ref, torch.tensor(6000.))
         torch.cuda.synchronize()
     assert torch.equal(e1, e3) and torch.equal(l1, l3)
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+@pytest.mark.parametrize('cls', ['spe', 'ira', 'bss'])
+def test_fused_input_norm_whole_model_bit_identical(precision, cls):
+    """Engine.fuse_norm (default): the half-block's norm + residual moved into the next LSTM kernel changes no bit."""
+    torch.manual_seed(9)
+    kw = dict(KW, n_repeats=2)
+    model = {'spe': lambda: P.DPRNNSpeTasNet(**kw, fusion_type='film'), 'ira': lambda: P.DPRNNSpeIRATasNet(**kw, fusion_type='cat'),
+             'bss': lambda: P.DPRNNTasNet(**kw)}[cls]().eval().cuda()
+    model.precision = precision
+    g = torch.Generator().manual_seed(10)
+    mix, ref = (0.05 * torch.randn(3, 5000, generator=g)).cuda(), (0.05 * torch.randn(3, 4000, generator=g)).cuda()
+    args = (mix,) if cls == 'bss' else (mix, ref, torch.tensor(4000.))
+    outs = []
+    with torch.no_grad():
+        for fuse in (True, False):
+            model._engine.fuse_norm = fuse
+            n0 = P.lib().launches
+            o = model(*args)
+            outs.append(((o,) if cls == 'bss' else o, P.lib().launches - n0))
+    (a, na), (b, nb) = outs
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert nb - na == (3 if cls != 'ira' else 6)          # one norm launch less per half-block but the last (2 blocks)

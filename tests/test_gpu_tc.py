@@ -408,3 +408,40 @@ def test_gemm_f32x2_split(M, N, K, epi):
     out_t = Engine.gemm_tc(eng, A.to(DEV), W.to(DEV), M, N, K, **kw)
     if epi == 0:
         assert O.peak_rel_err(out_t.cpu(), ref.float()) > 3 * err    # what the split buys
+
+
+@pytest.mark.parametrize('inter', [0, 1])
+@pytest.mark.parametrize('ndir', [2, 1])
+@pytest.mark.parametrize('fmt', ['bf16', 'fp16'])
+def test_lstm_fused_input_norm_is_bit_identical(inter, ndir, fmt):
+    """dprnn_lstm_layer_bf16_pp_fused (the previous half-block's norm + residual applied while the LSTM kernel loads its
+    input) == dprnn_norm_residual_h16res followed by dprnn_lstm_layer_bf16_pp, bit for bit, for both the LSTM output and
+    the updated residual stream; tiles that straddle utterances and a ragged last tile included."""
+    from tss_with_dprnn_b200.engine import Engine
+    L = P.lib()
+    H = 128
+    dtype = torch.float16 if fmt == 'fp16' else torch.bfloat16
+    h16 = 1 if fmt == 'fp16' else 0
+    flags = 1 | (2 if fmt == 'fp16' else 0)
+    B, S, K = (5, 60, 37) if not inter else (3, 21, 250)       # intra: 300 sequences, 60 per utterance
+    rows = B * S * K
+    torch.manual_seed(31 + inter)
+    rnn = torch.nn.LSTM(H, H, batch_first=True, bidirectional=(ndir == 2)).cuda()
+    wp2, bp = Engine._pack_lstm_tc(rnn, ['', '_reverse'][:ndir], half_jobs=True, dtype=dtype)
+    x0 = rnd(rows, H, seed=1).to(dtype).cuda()
+    y = (2 * rnd(rows, H, seed=2) + 0.3).to(dtype).cuda()
+    mr = torch.stack([0.3 + 0.1 * rnd(B, seed=3), 0.5 + 0.1 * rnd(B, seed=4).abs()], 1).cuda().contiguous()
+    gamma, beta = (1 + 0.1 * rnd(H, seed=5)).cuda(), (0.1 * rnd(H, seed=6)).cuda()
+    st = stream()
+    xa = x0.clone()
+    L.call('dprnn_norm_residual_h16res', y, xa, None, mr, gamma, beta, B, S * K, H, h16, st)
+    want = torch.empty(rows, ndir * H, device=DEV, dtype=dtype)
+    L.call('dprnn_lstm_layer_bf16_pp', xa, wp2, bp, want, B, S, K, inter, H, ndir, flags, st)
+    got = torch.full((rows + 1, ndir * H), 7.0, device=DEV, dtype=dtype)
+    xout = torch.full((rows + 1, H), 7.0, device=DEV, dtype=dtype)
+    for _ in range(2):
+        L.call('dprnn_lstm_layer_bf16_pp_fused', x0, y, mr, gamma, beta, xout, wp2, bp, got, B, S, K, inter, H, ndir, flags, st)
+        torch.cuda.synchronize()
+        assert torch.equal(xout[:rows], xa)
+        assert torch.equal(got[:rows], want)
+        assert float((got[rows:].float() - 7.0).abs().max()) == 0.0 and float((xout[rows:].float() - 7.0).abs().max()) == 0.0

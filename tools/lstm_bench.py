@@ -36,8 +36,16 @@ for inter in (0, 1):
     lo, med = bench(lambda: L.call('dprnn_lstm_layer_bf16_pp', xb, wp2, bp, hb, B, S, K, inter, H, nd, 1, st))
     print(f"{'inter' if inter else 'intra'} J={J} T={T}  pp (one job per pair): min {lo:.3f} median {med:.3f} ms   "
           f"ideal packing x{J / 74 / -(-J // 74):.3f}", flush=True)
+    y = torch.randn(rows, H, device='cuda').to(torch.bfloat16)
+    mr = torch.stack([torch.zeros(B), torch.ones(B)], 1).cuda().contiguous()
+    gamma, beta = torch.ones(H, device='cuda'), torch.zeros(H, device='cuda')
+    xo = torch.empty_like(xb)
+    lo, med = bench(lambda: L.call('dprnn_lstm_layer_bf16_pp_fused', xb, y, mr, gamma, beta, xo, wp2, bp, hb, B, S, K, inter, H, nd, 1, st))
+    print(f"   pp + fused input norm: min {lo:.3f} median {med:.3f} ms   (stand-alone norm pass: ", end='')
+    lo, med = bench(lambda: L.call('dprnn_norm_residual_h16res', y, xo, None, mr, gamma, beta, B, S * K, H, 0, st))
+    print(f"min {lo:.3f} median {med:.3f} ms)", flush=True)
     ws = torch.empty(L.query('dprnn_lstm_sliced_workspace_bytes', B, S, K, inter, nd), device='cuda', dtype=torch.uint8)
-    for k in (1, 2, 3, 4, 5, 6, 8):
+    for k in (3, 4):
         lo, med = bench(lambda: L.call('dprnn_lstm_layer_bf16_sliced', xb, wp2, bp, hb, B, S, K, inter, H, nd, 1, k, 0, ws, st))
         rounds = -(-k * J // 74)
         print(f"   sliced k={k}: min {lo:.3f} median {med:.3f} ms   ({rounds} rounds x {-(-T // k)} steps = {rounds * -(-T // k)} step-times)", flush=True)

@@ -62,6 +62,13 @@ __device__ __forceinline__ float2 unpack_h16x2(uint32_t v) {
     else return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v));
 }
 
+// x + norm(y) of one element of a half-block tail (dprnn.py:90-92,98-99).  ONE definition shared by the stand-alone norm
+// kernels and the LSTM kernel that applies the pending norm while it loads its input (lstm_tc_pp.cu, kFuse), so that both
+// round identically.
+__device__ __forceinline__ float norm_res1(float x, float y, float mean, float rstd, float g, float be) {
+    return x + ((y - mean) * rstd * g + be);
+}
+
 static inline unsigned cdiv(long a, long b) { return (unsigned)((a + b - 1) / b); }
 
 __device__ __forceinline__ float sigmoid_acc(float x) { return 1.0f / (1.0f + expf(-x)); }

@@ -12,6 +12,14 @@
 // Warps 4..7 run half-job A's cell updates, warps 8..11 half-job B's, each with its own barriers; the MMA thread
 // alternates A(t), B(t), A(t+1), ...: while it waits for A's h_t, B's MMAs are in flight and B's epilogue keeps the MUFU
 // pipe busy, and vice versa.  Inference; uniform batches and the ragged inter-chunk layer (one pair-job per utterance).
+//
+// kFuse (uniform batches, inference): the norm + residual that ends the PREVIOUS half-block (dprnn.py:90-92 / 98-99) is
+// applied here, while the layer's input is loaded, instead of by a pass of its own over the residual stream (2.4 GB and
+// 0.44 ms per half-block at B = 64, 13 % of the step, on a kernel that leaves 70 % of the HBM bandwidth unused).  Each CTA's
+// TMA lands the OLD residual tile in the x ring; warps 2 and 3 - idle in the plain kernel - read the matching rows of y
+// (the Linear output, straight from global memory, issued before the tile arrives), rewrite the tile in place as
+// x + norm(y) with the arithmetic of norm_residual_bf16res_kernel (bit-identical), publish it to the tensor core, and the
+// direction-0 job also stores it as the new residual stream (a second buffer: the other direction still reads the old one).
 #include "lstm_tc_common.cuh"
 
 namespace dprnn {
@@ -22,7 +30,7 @@ constexpr uint32_t PP_SM_TOTAL = SM_BAR + PP_BAR_BYTES;
 static_assert(PP_SM_TOTAL <= 232448, "shared memory budget of one SM (227 KiB)");
 constexpr uint32_t HALF_ROWS = 64 * 128;      // byte offset of rows 64..127 inside a [128 x 128 B] tile
 
-template <bool kFastAct, bool kTrain, bool kF16>
+template <bool kFastAct, bool kTrain, bool kF16, bool kFuse = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmH64, const float* __restrict__ bias_perm, const LstmTcParams p) {
@@ -35,6 +43,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint64_t* h_free = bars + 2 * NXS + 5;    // [2]
     uint64_t* h_done = bars + 2 * NXS + 7;    // [2][2]  (leader's copy)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NXS + 11);
+    uint64_t* x_raw = bars + 2 * NXS + 12;    // [NXS]  kFuse: the old residual tile has landed (this CTA's own copy)
     float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -56,7 +65,8 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             __trap();
         }
         prefetch_tmap(&tmX); prefetch_tmap(&tmW); prefetch_tmap(&tmH64);
-        for (int s = 0; s < NXS; ++s) { mbar_init(&x_full[s], 2); mbar_init(&x_empty[s], 1); }
+        // x_full: plain = the two CTAs' TMA halves; kFuse = the two converter warps of both CTAs
+        for (int s = 0; s < NXS; ++s) { mbar_init(&x_full[s], kFuse ? 4 : 2); mbar_init(&x_empty[s], 1); mbar_init(&x_raw[s], 1); }
         mbar_init(w_full, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&h_done[i], 8); }   // 4 warps x 2 CTAs
         mbar_init(&h_free[0], 1); mbar_init(&h_free[1], 1);
@@ -92,6 +102,11 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 for (int half = 0; half < 2; ++half, ++it) {
                     const int s = it % NXS;
                     mbar_wait(&x_empty[s], ((it / NXS) & 1) ^ 1);
+                    if constexpr (kFuse) {     // lands in this CTA only; the converter warps publish it to the leader
+                        mbar_expect_tx(&x_raw[s], TILE);
+                        tma_load_4d(smem + SM_X + s * TILE, &tmX, &x_raw[s], half * 64, c1(t, seq0), c2(t, seq0), outer);
+                        continue;
+                    }
                     const uint32_t lbar = leader_full0 + s * 8;
                     if (rank == 0) mbar_expect_tx_addr(smem_u32(&x_full[s]), 2 * TILE);
                     else mbar_arrive_remote(lbar);
@@ -142,6 +157,74 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     umma_commit_2cta(&d_full[j * 2 + 1], 3);
                 }
                 umma_commit_2cta(&x_empty[s0], 3); umma_commit_2cta(&x_empty[s1], 3);
+            }
+        }
+    } else if (kFuse && (warp == 2 || warp == 3)) {
+        // ================= converter: x tile <- x + norm(y) in place (kFuse) =================
+        const int ci = (warp - 2) * 32 + lane;                 // 64 threads: 16-byte chunk c of rows r0 + 8 k, k < 16
+        const int c = ci & 7, r0 = ci >> 3;
+        const uint32_t leader_full0 = map_to_cta(smem_u32(&x_full[0]), 0);
+        // per job, 32-bit: row of (sequence seq0 + r0 + 8 k, time t) in the [rows, 128] buffers = base0 + k * kstride + t * tstride
+        const bool intra = p.seq_dim == 2;
+        const int kstride = intra ? 8 * p.K : 8, tstride = intra ? 1 : p.K;
+        const int base0 = intra ? (seq0 + r0) * p.K : outer * p.S * p.K + seq0 + r0;
+        const long left = p.seq_limit - seq0 - r0;             // valid rows: k < kmax
+        const int kmax = left <= 0 ? 0 : (int)((left + 7) / 8 < 16 ? (left + 7) / 8 : 16);
+        // utterance of every row as an offset from the first one, 4 bits each (a 128-row tile spans <= 16 utterances for
+        // S >= 9; shorter utterances take the slow path below)
+        const int b0 = intra ? (seq0 + r0) / p.S : outer;
+        uint64_t boff = 0;
+        bool wide = false;
+        if (intra) {
+            for (int k = 0; k < 16; ++k) {
+                const int d = (seq0 + r0 + 8 * k) / p.S - b0;
+                wide |= d > 15;
+                boff |= (uint64_t)(d & 15) << (4 * k);
+            }
+        }
+        int it = 0;
+        for (int step = 0; step < T; ++step) {
+            const int t = dir ? T - 1 - step : step;
+#pragma unroll
+            for (int half = 0; half < 2; ++half, ++it) {
+                const int s = it % NXS;
+                const int rbase = base0 + t * tstride;
+                uint4 yv[16];
+#pragma unroll
+                for (int k = 0; k < 16; ++k)                   // y rows first: in flight while the tile lands
+                    if (k < kmax) yv[k] = __ldg(p.fy + (long)(rbase + k * kstride) * 16 + half * 8 + c);
+                float g[8], be[8];                             // affine of the thread's 8 channels of this K-half (L1 hits)
+                {
+                    const float4 g0 = __ldg(reinterpret_cast<const float4*>(p.fgamma + half * 64 + c * 8)), g1 = __ldg(reinterpret_cast<const float4*>(p.fgamma + half * 64 + c * 8 + 4));
+                    const float4 e0 = __ldg(reinterpret_cast<const float4*>(p.fbeta + half * 64 + c * 8)), e1 = __ldg(reinterpret_cast<const float4*>(p.fbeta + half * 64 + c * 8 + 4));
+                    g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+                    be[0] = e0.x; be[1] = e0.y; be[2] = e0.z; be[3] = e0.w; be[4] = e1.x; be[5] = e1.y; be[6] = e1.z; be[7] = e1.w;
+                }
+                mbar_wait(&x_raw[s], (it / NXS) & 1);
+                uint8_t* tile = smem + SM_X + s * TILE;
+#pragma unroll
+                for (int k = 0; k < 16; ++k) {
+                    if (k >= kmax) continue;                   // padding rows of the last tile stay zero
+                    const int row = r0 + 8 * k;
+                    const int b = wide ? (seq0 + row) / p.S : b0 + (int)((boff >> (4 * k)) & 15);
+                    const float2 st = __ldg(p.fmr + b);
+                    uint4* px = reinterpret_cast<uint4*>(tile + sw128_offset(row, c));
+                    const uint4 xv = *px;
+                    const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, yw[4] = {yv[k].x, yv[k].y, yv[k].z, yv[k].w};
+                    uint32_t ob[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const float2 xf = unpack_h16x2<kF16>(xw[q]), yf = unpack_h16x2<kF16>(yw[q]);
+                        ob[q] = pack_h16x2<kF16>(norm_res1(xf.x, yf.x, st.x, st.y, g[2 * q], be[2 * q]),
+                                                 norm_res1(xf.y, yf.y, st.x, st.y, g[2 * q + 1], be[2 * q + 1]));
+                    }
+                    const uint4 o = make_uint4(ob[0], ob[1], ob[2], ob[3]);
+                    *px = o;
+                    if (dir == 0) p.fxout[(long)(rbase + k * kstride) * 16 + half * 8 + c] = o;
+                }
+                fence_async_smem();                            // generic-proxy writes -> visible to the tensor core
+                __syncwarp();
+                if (lane == 0) mbar_arrive_remote(leader_full0 + s * 8);
             }
         }
     } else if (warp >= 4) {
@@ -236,7 +319,9 @@ using namespace dprnn;
 // rank r and MMA nh are {[W_ih | W_hh][gate*H + 64*nh + 32*r + u] : gate = 0..3, u < 32} (Engine._pack_lstm_tc(half_jobs=True)).
 static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S, int K,
                         int inter, int hidden, int ndir, int flags, const int2* jobs, int n_jobs, void* stream,
-                        void* gates = nullptr, float* cstate = nullptr, float* hout_f32 = nullptr) {
+                        void* gates = nullptr, float* cstate = nullptr, float* hout_f32 = nullptr,
+                        const void* fy = nullptr, const float* fmr = nullptr, const float* fgamma = nullptr,
+                        const float* fbeta = nullptr, void* fxout = nullptr) {
     const int fast_act = flags & DPRNN_LSTM_FAST_ACT, f16 = flags & DPRNN_LSTM_FP16;
     DPRNN_CHECK_ARG(!(f16 && gates));       // the training forward is built for bf16 operands (cfg 5: "bf16 gate GEMMs")
     DPRNN_CHECK_ARG(x && w_packed && bias_perm && hout && B > 0 && S > 0 && K > 0);
@@ -270,6 +355,8 @@ static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_p
     }
     p.jobs = jobs;
     p.gates = (uint32_t*)gates; p.cst = cstate; p.hf = hout_f32;
+    p.fy = (const uint4*)fy; p.fmr = (const float2*)fmr; p.fgamma = fgamma; p.fbeta = fbeta; p.fxout = (uint4*)fxout;
+    DPRNN_CHECK_ARG(!fy || (!gates && !jobs && fmr && fgamma && fbeta && fxout && fxout != x && (long)B * S * K < (1L << 27)));
     p.K = K; p.S = S;
     p.seq_limit = inter ? K : (long)B * S;
     for (int i = 0; i < 4; ++i) dH[i] = dX[i];
@@ -281,6 +368,8 @@ static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_p
     const uint32_t bW[2] = {64, 128};
     if (make_tmap(&tmW, t16, 2, w_packed, dW, sW, bW)) return 1;
     auto kern = gates ? (fast_act ? lstm_tc_pp_kernel<true, true, false> : lstm_tc_pp_kernel<false, true, false>)
+                : fy  ? (f16 ? (fast_act ? lstm_tc_pp_kernel<true, false, true, true> : lstm_tc_pp_kernel<false, false, true, true>)
+                             : (fast_act ? lstm_tc_pp_kernel<true, false, false, true> : lstm_tc_pp_kernel<false, false, false, true>))
                 : f16 ? (fast_act ? lstm_tc_pp_kernel<true, false, true> : lstm_tc_pp_kernel<false, false, true>)
                       : (fast_act ? lstm_tc_pp_kernel<true, false, false> : lstm_tc_pp_kernel<false, false, false>);
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP_SM_TOTAL));
@@ -293,6 +382,20 @@ static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_p
 extern "C" int dprnn_lstm_layer_bf16_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B,
                                         int S, int K, int inter, int hidden, int ndir, int fast_act, void* stream) {
     return lstm_pp_impl(x, w_packed, bias_perm, hout, B, S, K, inter, hidden, ndir, fast_act, nullptr, 0, stream);
+}
+
+// dprnn_lstm_layer_bf16_pp on the input x_in + norm(y) (GroupNorm(1,128) / gLN with per-utterance mean_rstd [B,2] and the
+// affine gamma / beta [128]): the previous half-block's norm + residual applied while the input is loaded; x_out (a
+// buffer other than x_in) receives the updated residual stream.  Bit-identical to dprnn_norm_residual_h16res followed by
+// dprnn_lstm_layer_bf16_pp.
+extern "C" int dprnn_lstm_layer_bf16_pp_fused(const void* x_in, const void* y, const float* mean_rstd, const float* gamma,
+                                              const float* beta, void* x_out, const void* w_packed, const float* bias_perm,
+                                              void* hout, int B, int S, int K, int inter, int hidden, int ndir, int flags,
+                                              void* stream) {
+    DPRNN_CHECK_ARG(y && mean_rstd && gamma && beta && x_out);
+    DPRNN_CHECK_ARG(((uintptr_t)y | (uintptr_t)x_out) % 16 == 0);
+    return lstm_pp_impl(x_in, w_packed, bias_perm, hout, B, S, K, inter, hidden, ndir, flags, nullptr, 0, stream, nullptr,
+                        nullptr, nullptr, y, mean_rstd, gamma, beta, x_out);
 }
 
 // dprnn_lstm_inter_bf16_ragged with the half-job kernel (same arguments; half-job weight packing).

@@ -181,10 +181,10 @@ __global__ void norm_residual_bf16res_kernel(const uint4* __restrict__ y, uint4*
             const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8 + h);
             const float2 y01 = unpack_h16x2<kF16>(yw[2 * h]), y23 = unpack_h16x2<kF16>(yw[2 * h + 1]);
             const float2 x01 = unpack_h16x2<kF16>(xw[2 * h]), x23 = unpack_h16x2<kF16>(xw[2 * h + 1]);
-            r[h].x = x01.x + ((y01.x - mean) * rstd * g.x + be.x);
-            r[h].y = x01.y + ((y01.y - mean) * rstd * g.y + be.y);
-            r[h].z = x23.x + ((y23.x - mean) * rstd * g.z + be.z);
-            r[h].w = x23.y + ((y23.y - mean) * rstd * g.w + be.w);
+            r[h].x = norm_res1(x01.x, y01.x, mean, rstd, g.x, be.x);
+            r[h].y = norm_res1(x01.y, y01.y, mean, rstd, g.y, be.y);
+            r[h].z = norm_res1(x23.x, y23.x, mean, rstd, g.z, be.z);
+            r[h].w = norm_res1(x23.y, y23.y, mean, rstd, g.w, be.w);
             ob[2 * h] = pack_h16x2<kF16>(r[h].x, r[h].y);
             ob[2 * h + 1] = pack_h16x2<kF16>(r[h].z, r[h].w);
         }

@@ -42,6 +42,11 @@ class Engine(RaggedMixin):
         self.conv_kind = None
         self.n_streams = 1         # >1: the batch is split into that many utterance groups on concurrent streams
         self.fused_tail = False    # bf16 mode: Linear + norm + residual as one persistent kernel (linear_norm.cu)
+        # opt-in (tensor-core modes, 16-bit residual stream): the norm + residual of a half-block applied by the NEXT
+        # half-block's LSTM kernel while it loads its input (lstm_tc_pp.cu, kFuse).  Bit-identical and one HBM pass less,
+        # but measured SLOWER (intra 1.82 -> 4.04 ms per layer against a 0.40 ms norm pass saved: the two converter warps sit
+        # on schedulers whose issue slots and MUFU pipe the cell updates already fill) - DESIGN.md section 4.2
+        self.fuse_norm = os.environ.get('DPRNN_FUSE_NORM', '0') == '1'
         self._row_off = {}
         self._streams = []
         self.use_graphs = True     # eval forwards of a repeated shape are captured into a CUDA graph and replayed
@@ -494,6 +499,8 @@ class Engine(RaggedMixin):
             s['ybuf'] = torch.empty((rows, F), device=dev, dtype=self.h16_dtype)
             s['part'] = torch.empty(L_.query('dprnn_gemm_tc_stats_bytes', rows), device=dev, dtype=torch.uint8)
             s['mr2'] = torch.empty((B, 2), device=dev)
+            if self._fuses_norm():
+                s['xb2'] = torch.empty_like(s['xb'])       # the residual stream ping-pongs between two 16-bit buffers
             if self.fused_tail:
                 s['ws'] = torch.empty(L_.query('dprnn_linear_norm_workspace_bytes', rows, B), device=dev, dtype=torch.uint8)
         return s
@@ -501,6 +508,16 @@ class Engine(RaggedMixin):
     def _half_lstm(self, s, bi, which):
         """bf16 mode: one nn.LSTM layer (intra: which=0, inter: which=1) as the fused tcgen05 kernel -> s['hb']."""
         hw = self.packed()['blocks'][bi][which]
+        pend = s.pop('pending_norm', None)
+        if pend is not None:
+            # the previous half-block left its norm + residual to this kernel: input = xb + norm(ybuf), applied while the
+            # tiles are loaded; the updated residual stream lands in the other 16-bit buffer (lstm_tc_pp.cu, kFuse)
+            g_, b_ = pend
+            lib().call('dprnn_lstm_layer_bf16_pp_fused', s['xb'], s['ybuf'], s['mr2'], g_, b_, s['xb2'], hw['tc_w2'],
+                       hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'], which, s['H'], hw['ndir'], self._lstm_flags(),
+                       self._stream())
+            s['xb'], s['xb2'] = s['xb2'], s['xb']
+            return
         if self.lstm_pingpong and self.lstm_slices != 1:
             # persistent CTA pairs over time-sliced jobs (lstm_tc_sliced.cu): the half-job ping-pong step, bit-identical
             # results, no part-empty last wave when the layer has more pair-jobs than the GPU has SM pairs
@@ -541,6 +558,10 @@ class Engine(RaggedMixin):
         self._half_linear(s, bi, which)
         self._half_norm(s, bi, which)
 
+    def _fuses_norm(self) -> bool:
+        return (self.fuse_norm and self.tc and self.residual_bf16 and self.lstm_pingpong and self.lstm_slices == 1
+                and not self.fused_tail)
+
     def _half_linear(self, s, bi, which):
         """Linear with bf16 output; per-utterance mean / rstd of the following norm from the fp32 accumulators."""
         hw = self.packed()['blocks'][bi][which]
@@ -553,6 +574,9 @@ class Engine(RaggedMixin):
         blk = self.model.separation.dprnn_blocks[bi]
         g_, b_, _ = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
         last = bi == len(self.model.separation.dprnn_blocks) - 1 and which == 1     # nothing reads the bf16 shadow then
+        if self._fuses_norm() and not last:
+            s['pending_norm'] = (g_, b_)        # applied by the next half-block's LSTM kernel
+            return
         if self.residual_bf16:      # default: residual stream in 16 bits only; the last half-block writes the fp32 x for the fold
             lib().call('dprnn_norm_residual_h16res', s['ybuf'], s['xb'], s['x'] if last else None, s['mr2'], g_, b_,
                        s['B'], s['S'] * s['K'], s['F'], self.h16, self._stream())
@@ -623,7 +647,7 @@ class Engine(RaggedMixin):
         if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
         key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
-               self.fast_act, self.conv_mode, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self._graph_key())
+               self.fast_act, self.conv_mode, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self.fuse_norm, self._graph_key())
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = 'seen'
