@@ -453,7 +453,8 @@ class Cfg3:
 
     def __init__(self, args, model, rank, world, dev, n_steps):
         self.model, self.dev = model, dev
-        buckets = pick_steps(cfg3_buckets(world, args.batch)[rank], n_steps)
+        mine = cfg3_buckets(world, args.batch)[rank]
+        buckets = mine if n_steps is None else pick_steps(mine, n_steps)       # None: the rank's whole share of the test set
         self.n_steps = len(buckets)
         self.steps = []
         g = torch.Generator().manual_seed(4321 + rank)
@@ -619,7 +620,7 @@ def run_ours(args):
         model._engine.fused_tail = bool(args.fused_tail)
     L = P.lib()
     if args.workload == 'cfg3':
-        wl = Cfg3(args, model, rank, world, dev, args.steps)
+        wl = Cfg3(args, model, rank, world, dev, None if args.full else args.steps)
     elif args.workload == 'cfg4':
         wl = Cfg4(args, model, rank, dev)
     elif args.workload == 'cfg1':
@@ -645,18 +646,27 @@ def run_ours(args):
         return ms, L.launches - n0
 
     from tss_with_dprnn_b200.sharding import reduce_timing
-    audio_local = sum(wl.audio(i) for i in range(args.steps))
+    # cfg3 --full: every rank runs ALL the buckets the LPT rule gave it (the whole 3 000-utterance test set across the
+    # job), so the per-rank step counts differ and the max-over-ranks time shows the real imbalance
+    steps_local = wl.n_steps if (args.workload == 'cfg3' and args.full) else args.steps
+    audio_local = sum(wl.audio(i) for i in range(steps_local))
     with ClockSampler(local) as clk:
         # every distinct step is warmed up at least once (ragged layouts, tensor maps, allocator pools)
-        ms_local, launches = timed(wl.resident, args.steps, max(args.warmup, wl.n_steps))
+        ms_local, launches = timed(wl.resident, steps_local, max(args.warmup, wl.n_steps))
     clocks = clk.summary()
     ms_total, audio_steps = reduce_timing(ms_local, audio_local, dev)     # max over ranks of device time, whole-job audio
-    ms_local_e2e, _ = timed(wl.e2e, args.steps, max(1, wl.n_steps))
+    ms_local_e2e, _ = timed(wl.e2e, steps_local, max(1, wl.n_steps))
     ms_e2e, _ = reduce_timing(ms_local_e2e, audio_local, dev)
     value = audio_steps / (ms_total / 1e3)
     e2e_value = audio_steps / (ms_e2e / 1e3)
-    h2d = sum(wl.bytes(i)[0] for i in range(args.steps)) / args.steps
-    d2h = sum(wl.bytes(i)[1] for i in range(args.steps)) / args.steps
+    h2d = sum(wl.bytes(i)[0] for i in range(steps_local)) / steps_local
+    d2h = sum(wl.bytes(i)[1] for i in range(steps_local)) / steps_local
+    rank_ms = [ms_local]
+    if world > 1:
+        t = torch.tensor([ms_local], dtype=torch.float64, device=dev)
+        allt = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        rank_ms = [float(x) for x in allt]
 
     # --- per-kernel pass (separate from the timed region, one stream so that launches do not overlap): CUDA events
     # around every launch of step 0
@@ -783,12 +793,14 @@ def run_ours(args):
             replica_spread = 0.0
     if rank == 0:
         line = {
-            'metric': METRIC, 'value': value, 'unit': 'audio-s/s', 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms_total / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'metric': METRIC, 'value': value, 'unit': 'audio-s/s', 'n_gpus': world, 'steps': steps_local,
+            'warmup': args.warmup, 'ms_per_step': ms_total / steps_local, 'higher_is_better': True, 'scaling': 'weak',
             'vs_baseline': None, 'dtype': 'f32' if args.precision == 'fp32' else 'bf16 LSTM gate contractions (fwd + BPTT), tf32 linear / weight-gradient contractions, f32 accumulate+state' if args.workload == 'cfg5' else f'{args.precision} gate/linear contractions (tcgen05), tf32 1x1 convs, f32 accumulate+state',
             'data': 'synthetic', 'config': workload_config(args), 'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'audio-s/s', 'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h)},
             'gpu_launches': launches, 'roofline': roofline, 'cpu_baseline': cpu, 'kernels': per_kernel,
+            'ranks': {'ms': rank_ms, 'imbalance_max_over_mean': max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
+                      'steps_rank0': steps_local},
             'build': L.build_info(),
         }
         if modes is not None:
@@ -832,6 +844,8 @@ def main():
     ap.add_argument('--samples', type=int, default=24000, help='samples per utterance (3 s @ 8 kHz)')
     ap.add_argument('--cpu-batch', type=int, default=1, help='utterances per CPU-baseline forward')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--full', action='store_true',
+                    help='cfg3: every rank runs its whole LPT share of the 3 000-utterance test set (steps = its bucket count)')
     ap.add_argument('--cpu-b8', type=int, default=1, help='cfg2: also time the CPU baseline at B = 8 (SURVEY.md 8d protocol)')
     ap.add_argument('--modes', type=int, default=1,
                     help='cfg2: also measure the other precision modes (throughput + error against the reference fixture)')

@@ -112,14 +112,13 @@ def test_rejects_cpu_tensors_and_grad_training():
     with pytest.raises(RuntimeError, match='no CPU path'):
         with torch.no_grad():
             model(torch.zeros(1, 4000), torch.zeros(1, 4000), torch.tensor(4000.))
-    # train() + autograd: DPRNN-Spe / DPRNN-TasNet return tensors attached to the hand-written backward (train.py);
-    # the models without one (IRA, RawNet) refuse instead of silently dropping the graph
+    # train() + autograd: every model class returns tensors attached to the hand-written backward (train.py)
     model.train()
     est, logits = model(0.1 * torch.randn(2, 4000).cuda(), 0.1 * torch.randn(2, 4000).cuda(), torch.tensor(4000.))
     assert est.requires_grad and logits.requires_grad
     ira = P.DPRNNSpeIRATasNet(**dict(KW, n_repeats=1)).cuda().train()
-    with pytest.raises(NotImplementedError):
-        ira(torch.zeros(1, 4000).cuda(), torch.zeros(1, 4000).cuda(), torch.tensor(4000.))
+    est, logits = ira(0.1 * torch.randn(2, 4000).cuda(), 0.1 * torch.randn(2, 4000).cuda(), torch.tensor(4000.))
+    assert est.requires_grad and logits.requires_grad
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -52,8 +52,33 @@ def test_rawnet_rejects_cpu_and_train():
     model = P.DPRNNRawNetTasNet(**meta['kwargs'])
     with pytest.raises(RuntimeError, match='no CPU path'):
         model.eval()(torch.zeros(1, 4000), torch.zeros(1, 8000))
-    with pytest.raises(NotImplementedError):
-        model.train().cuda()(torch.zeros(1, 4000).cuda(), torch.zeros(1, 8000).cuda())
+
+
+def test_rawnet_training_path():
+    """TrainerRawNet's step (src/trainers/trainer_rawnet.py:31-56): RawNet3 as library ops under torch autograd
+    (embed_autograd), masker + decoder as the hand-written autograd node.  (a) the torch-op restatement equals the
+    hand-written kernels in eval mode; (b) a train-mode step gives finite, non-zero gradients to RawNet3, the fusion and
+    the masker, and updates the BatchNorm running statistics."""
+    meta, arr = load_golden('rawnet_att_r1_eval')
+    model = build(meta).cuda()
+    mix, ref = torch.from_numpy(arr['mix']).cuda(), torch.from_numpy(arr['ref']).cuda()
+    se = model.separation.spk_encoder
+    with torch.no_grad():
+        a, b = se.embed(ref), se.embed_autograd(ref)               # eval mode: kernels vs library ops
+    assert O.peak_rel_err(b.cpu(), a.cpu()) < 2e-4
+    model.train()
+    rv0 = se.layer1.bn1.running_var.clone()
+    est, logits = model(mix, ref)
+    assert est.requires_grad and logits.requires_grad
+    g = torch.Generator().manual_seed(1)
+    loss = (est * torch.randn(est.shape, generator=g).cuda()).sum() + logits.square().sum()
+    loss.backward()
+    assert not torch.equal(se.layer1.bn1.running_var, rv0)
+    for name in ('separation.spk_encoder.fc6.weight', 'separation.spk_encoder.layer1.conv1.weight',
+                 'separation.spk_encoder.conv1.filterbank.low_hz_', 'separation.fusion_linear.weight',
+                 'separation.dprnn_blocks.0.intra_rnn.rnn.weight_hh_l0', 'encoder.conv1d.weight', 'decoder.weight'):
+        p = dict(model.named_parameters())[name]
+        assert p.grad is not None and torch.isfinite(p.grad).all() and float(p.grad.abs().max()) > 0, name
 
 
 def test_rawnet_frontend_kernels_match_oracle():

@@ -255,9 +255,7 @@ class Engine(RaggedMixin):
 
     def _guard_autograd(self):
         if torch.is_grad_enabled() and self.model.training and any(p.requires_grad for p in self.model.parameters()):
-            raise NotImplementedError(
-                'the backward of this model / fusion is not built (train.py covers DPRNNTasNet and DPRNNSpeTasNet with '
-                "fusion film | add | mul | cat | att): call under torch.no_grad() or model.eval()")
+            raise NotImplementedError('this entry point has no backward: call under torch.no_grad() or model.eval()')
 
     def gemm(self, A, Wt, M, N, K, out=None, bias=None, bias_per_utt=False, bias_scale=1.0, rows_per_utt=0,
              p_scale=None, p_shift=None, p_add=None, rowscale=None, epi=EPI_NONE):
@@ -732,9 +730,12 @@ class Engine(RaggedMixin):
             return self._graphed('bss', (mix,), lambda m: self._run_groups(m.shape[0], lambda b0, b1: group_of(m, b0, b1)))[0]
 
     def forward_spe(self, mix, ref, ref_len, embedding=None):
-        if embedding is not None:
-            self._guard_autograd()
         mix = self._check_input(mix, 'input')
+        if embedding is not None and self._wants_grad():
+            # DPRNN-RawNet training: the speaker encoder ran outside (torch autograd); masker + decoder as one autograd node
+            # that also returns the gradient of the embedding
+            from .train import forward_with_grad
+            return forward_with_grad(self.model, mix, embedding=self._check_input(embedding, 'embedding'))
         sep, cfg = self.model.separation, self.model.cfg
         N = cfg['input_size']
 
@@ -773,9 +774,13 @@ class Engine(RaggedMixin):
                 B, lambda b0, b1: group(m, None, None, e, b0, b1)))
 
     def forward_ira(self, mix, ref, ref_len):
-        self._guard_autograd()
         mix = self._check_input(mix, 'input')
         ref = self._check_input(ref, 'aux')
+        if self._wants_grad():
+            # training (dprnn_spe_ira.py:53-115 under TrainerSpe): both masker passes and both speaker-encoder passes as
+            # one autograd node over the hand-written forward / backward
+            from .train import forward_with_grad
+            return forward_with_grad(self.model, mix, ref, self._aux_div(ref_len, mix.shape[0], mix.device))
         sep, cfg = self.model.separation, self.model.cfg
         N, E = cfg['input_size'], cfg['embeddings_size']
 

@@ -267,8 +267,14 @@ class DPRNNRawNetTasNet(_TasNetBase):
                          embeddings_size=embeddings_size, num_spks=num_spks, fusion_type=fusion_type)
 
     def forward(self, input, aux):
-        self.separation.spk_encoder.allow_tf32 = self.precision != 'fp32'
-        emb = self.separation.spk_encoder.embed(aux)
+        se = self.separation.spk_encoder
+        se.allow_tf32 = self.precision != 'fp32'
+        if self.training and torch.is_grad_enabled():
+            # TrainerRawNet (src/trainers/trainer_rawnet.py:31-56): RawNet3 as library ops under torch autograd, the masker
+            # + decoder as the hand-written autograd node that also returns d loss / d embedding (train.EmbTrainFunction)
+            emb = se.embed_autograd(aux)
+        else:
+            emb = se.embed(aux)
         return self._engine.forward_spe(input, None, None, embedding=emb)
 
     def forward_with_embedding(self, input, embedding):

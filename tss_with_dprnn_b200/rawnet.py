@@ -8,7 +8,9 @@ parameterised sinc filterbank, log-abs, mean normalisation: csrc/rawnet.cu), the
 kernel-3 dilated convolutions as tensor-core contractions with fused bias / ReLU / BatchNorm / residual epilogues -
 TF32 in bf16 mode, exact fp32 on CUDA cores in fp32 mode - max-pooling, AFMS), layer4, and the attentive statistics
 pooling.  Channels-last [B*T, C] activations like the rest of the path; torch is only used for buffers and one-off weight
-re-layout.  Eval mode only (InferencerRawNet calls model.eval()).  There is no CPU path: the tensors must be CUDA tensors.
+re-layout.  That is the eval() path (InferencerRawNet calls model.eval()); in train() mode - BatchNorm batch statistics, and
+the backward TrainerRawNet needs - the branch runs as stock torch ops under autograd (embed_autograd) and only the masker it
+feeds is hand-written.  There is no CPU path: the tensors must be CUDA tensors.
 
 The sinc front-end restates ``asteroid_filterbanks==0.4.0`` ``ParamSincFB`` / ``Encoder`` (third-party, not vendored in
 the reference, not installable here): parity for that part is UNPINNED.
@@ -284,12 +286,58 @@ class RawNet3(nn.Module):
                 B, nOut, 2 * C4, 0, st)
         return emb
 
+    # ------------------------------------------------------------------ training path (library ops + torch autograd)
+    def _block_autograd(self, x, blk):
+        """Bottle2neck.forward + AFMS (RawNetBasicBlock.py:48-55,111-142) with the module's own Conv1d / BatchNorm1d objects
+        (BatchNorm honours self.training: batch statistics and running-stat updates in train mode). x [B,C,T]."""
+        F = torch.nn.functional
+        residual = blk.residual(x)
+        out = blk.bn1(torch.relu(blk.conv1(x)))
+        spx = torch.split(out, blk.width, 1)
+        outs, sp = [], None
+        for i in range(blk.nums):
+            sp = spx[i] if i == 0 else sp + spx[i]
+            sp = blk.bns[i](torch.relu(blk.convs[i](sp)))
+            outs.append(sp)
+        outs.append(spx[blk.nums])
+        out = blk.bn3(torch.relu(blk.conv3(torch.cat(outs, 1)))) + residual
+        if blk.pool:
+            out = F.max_pool1d(out, blk.pool)
+        y = torch.sigmoid(blk.afms.fc(out.mean(-1)))
+        return (out + blk.afms.alpha) * y.unsqueeze(-1)
+
+    def embed_autograd(self, x):
+        """RawNet3.forward (RawNet3.py:72-136) as stock torch ops, differentiable and with train-mode BatchNorm - the
+        TRAINING path of the speaker branch of DPRNN-RawNet (trainer_rawnet.py:31-56).  RawNet3 is ~8 % of the model's
+        arithmetic; its hand-written kernels (embed) cover inference, and a hand-written
+        backward for it is not built: here the branch runs on library kernels under torch autograd and hands its embedding
+        to the hand-written masker forward / backward (train.EmbTrainFunction), which returns d loss / d embedding to it."""
+        F = torch.nn.functional
+        if not x.is_cuda:
+            raise RuntimeError('aux must be a CUDA tensor: tss_with_dprnn_b200 has no CPU path')
+        fb = self.conv1.filterbank
+        xi = F.conv1d(F.pad(x.unsqueeze(1), (1, 0), 'reflect'), self.preprocess[0].flipped_filter)      # PreEmphasis
+        xi = self.preprocess[1](xi)                                                                       # InstanceNorm1d
+        f = torch.log(torch.abs(F.conv1d(xi, fb.filters(), stride=fb.stride)) + 1e-6)                     # RawNet3.py:79-81
+        f = f - f.mean(-1, keepdim=True)                                                                  # :83
+        x1 = self._block_autograd(f, self.layer1)
+        x2 = self._block_autograd(x1, self.layer2)
+        x1p = F.max_pool1d(x1, 3)
+        x3 = self._block_autograd(x1p + x2, self.layer3)                                                  # summed (:93)
+        h = torch.relu(self.layer4(torch.cat((x1p, x2, x3), 1)))
+        t = h.shape[-1]
+        g = torch.cat((h, h.mean(2, keepdim=True).repeat(1, 1, t),
+                       torch.sqrt(h.var(2, keepdim=True).clamp(min=1e-4, max=1e4)).repeat(1, 1, t)), 1)  # :105-117
+        w = self.attention(g)
+        mu = torch.sum(h * w, 2)
+        sg = torch.sqrt((torch.sum(h ** 2 * w, 2) - mu ** 2).clamp(min=1e-4, max=1e4))
+        return self.fc6(self.bn5(torch.cat((mu, sg), 1)))                                                 # out_bn=False
+
     @torch.no_grad()
     def embed(self, x):
         """RawNet3.forward (RawNet3.py:72-136), eval mode, on the GPU.  x [B, T] raw 16 kHz reference -> [B, nOut]."""
         if not x.is_cuda:
             raise RuntimeError('aux must be a CUDA tensor: tss_with_dprnn_b200 has no CPU path')
         if self.training:
-            raise NotImplementedError('the RawNet3 speaker encoder runs in eval() mode (InferencerRawNet calls '
-                                      'model.eval(), src/inferencers/inferencer_rawnet.py:29)')
+            return self.embed_autograd(x)          # train-mode BatchNorm (batch statistics, running-stat updates): library ops
         return self._embed_kernels(x)

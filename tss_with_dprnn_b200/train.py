@@ -128,112 +128,101 @@ def _check_supported(model):
     if model.precision == 'fp16':
         raise NotImplementedError("the training step runs in precision 'fp32' or 'bf16' (cfg 5: bf16 gate GEMMs); "
                                   "'fp16' is an inference mode")
-    if cfg['kind'] not in ('spe', 'bss') or (cfg['kind'] == 'spe' and cfg['fusion_type'] not in
-                                                  ('film', 'add', 'mul', 'cat', 'att')):
-        raise NotImplementedError("training is built for DPRNNTasNet (scripts/train/config_bss.yaml) and DPRNNSpeTasNet "
-                                  "with fusion_type in {'film','add','mul','cat','att'} (cfg 5: film; "
-                                  "scripts/train/config_tss.yaml: att); other models keep their forward-only path")
+    if cfg['kind'] not in ('spe', 'bss', 'ira', 'rawnet') or \
+            (cfg['kind'] != 'bss' and cfg['fusion_type'] not in ('film', 'add', 'mul', 'cat', 'att')):
+        raise NotImplementedError("training is built for DPRNNTasNet (scripts/train/config_bss.yaml), DPRNNSpeTasNet / "
+                                  "DPRNNSpeIRATasNet / DPRNNRawNetTasNet with fusion_type in {'film','add','mul','cat','att'}")
     if cfg['kernel_size'] != 2 or cfg['stride'] != 1 or cfg['feature_size'] != 128 or cfg['hidden_size'] != 128 \
             or cfg['chunk_length'] != 2 * cfg['hop_length'] or cfg['input_size'] not in (32, 64, 128):
         raise NotImplementedError('training is built for the shipped geometry (kernel 2, stride 1, F = H = 128, hop = K/2)')
 
 
 # --------------------------------------------------------------------------------------------------------------
-# forward (train mode)
+# forward (train mode), in the pieces the model variants are composed of
 # --------------------------------------------------------------------------------------------------------------
-def forward_train(model, mix, ref=None, div=None):
-    """DPRNNSpeTasNet: -> est [B,T], logits [B,num_spks], ctx (everything the backward needs).
-    DPRNNTasNet (ref = div = None): -> est [B,2,T], None, ctx."""
-    _check_supported(model)
-    L_, cfg, sep = lib(), model.cfg, model.separation
-    dev = mix.device
-    ops = _Ops(dev, tf32=model.precision == 'bf16')
-    st = _st()
+def _spk_fwd(model, ops, feats, B, Lr, div):
+    """Speaker encoder + time mean (dprnn_spe.py:115-122,156-163), BatchNorm in train mode: feats [B,Lr,N] -> emb [B,E] and
+    what its backward needs.  Its contractions stay exact fp32 in both modes: the train-mode BatchNorm chain and the scalar
+    PReLU slope gradients are cancellation-heavy (TF32 there moved one slope gradient by 40 %) and the branch is < 3 % of
+    the step."""
+    L_, sep, st, dev = lib(), model.separation, _st(), feats.device
+    N = model.cfg['input_size']
+    se = sep.spk_encoder
+    mr_s = ops.utt_stats(feats, B, Lr * N, se[0].eps)
+    s1 = ops.empty(B, N); s0 = ops.empty(B, N)
+    L_.call('dprnn_norm_affine', mr_s, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
+    gnf = torch.empty_like(feats)                                  # GroupNorm(feats): kept for dW of conv0
+    L_.call('dprnn_prologue_apply', feats, gnf, B * Lr, N, Lr, s1, s0, None, None, st)
+    O = se[1].weight.shape[0]
+    x = ops.gemm(gnf, se[1].weight.detach().reshape(O, N).t().contiguous(), B * Lr, O, N, bias=se[1].bias.detach())
+    res, Lx = [], Lr
+    for rb in (se[2], se[3], se[4]):
+        Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
+        rows = B * Lx
+        rc = dict(x=x, Lx=Lx, Cin=Cin, Cout=Cout)
+        ws = torch.empty(L_.query('dprnn_bn_workspace_bytes', Cout), device=dev, dtype=torch.uint8)
+
+        def bn(y, bnm):
+            scale, shift = ops.empty(Cout), ops.empty(Cout)
+            L_.call('dprnn_batchnorm_affine', y, rows, Cout, bnm.weight.detach(), bnm.bias.detach(), bnm.running_mean,
+                    bnm.running_var, 1, float(bnm.eps), float(bnm.momentum if bnm.momentum is not None else 0.1), ws,
+                    scale, shift, st)
+            bnm.num_batches_tracked += 1
+            return scale, shift
+
+        y1 = ops.gemm(x, rb.conv1.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
+        sc1, sh1 = bn(y1, rb.batch_norm1)
+        a1 = ops.empty(rows, Cout)
+        L_.call('dprnn_affine_prelu', y1, sc1, sh1, rb.prelu1.weight.detach(), a1, rows, Cout, st)
+        y2 = ops.gemm(a1, rb.conv2.weight.detach().reshape(Cout, Cout).t().contiguous(), rows, Cout, Cout)
+        sc2, sh2 = bn(y2, rb.batch_norm2)
+        if hasattr(rb, 'conv_downsample'):
+            skip = ops.gemm(x, rb.conv_downsample.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
+        else:
+            skip = x
+        Lo = Lx // 3
+        out = ops.empty(B, Lo, Cout)
+        L_.call('dprnn_affine_add_prelu_pool3', y2, sc2, sh2, skip, rb.prelu2.weight.detach(), out, B, Lx, Cout, st)
+        rc.update(y1=y1, sc1=sc1, sh1=sh1, a1=a1, y2=y2, sc2=sc2, sh2=sh2, skip=skip)
+        res.append(rc)
+        x, Lx = out.view(B * Lo, Cout), Lo
+    E = se[5].weight.shape[0]
+    C5 = se[5].weight.shape[1]
+    z5 = ops.gemm(x, se[5].weight.detach().reshape(E, C5).t().contiguous(), B * Lx, E, C5, bias=se[5].bias.detach())
+    emb = ops.empty(B, E)
+    L_.call('dprnn_time_sum', z5, emb, B, Lx, E, div, st)
+    return emb, dict(feats=feats, mr_s=mr_s, gnf=gnf, res=res, x3=x, L3=Lx, Lr=Lr, div=div, B=B)
+
+
+def _emb_linear(ops, emb, m, w_off=0, K=None):
+    """m(emb[:, :K]) with the weight columns [w_off, w_off + K) of the nn.Linear m."""
+    B, E = emb.shape
+    Kin = m.weight.shape[1]
+    K = E if K is None else K
+    out = ops.empty(B, m.weight.shape[0])
+    lib().call('dprnn_small_linear', emb, E, m.weight.detach().data_ptr() + 4 * w_off, Kin,
+               m.bias.detach() if w_off == 0 else None, out, out.shape[1], B, out.shape[1], K, 0, _st())
+    return out
+
+
+def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
+    """Bottleneck norm + fusion + 1x1 conv, segmentation, the DPRNN blocks, PReLU, overlap-add, conv2d, gated head, end
+    conv + activation (dprnn.py:166-187 / dprnn_spe.py:125-154,231-248): enc [B,Lm,N] (+ emb [B,E]) -> one mask [B*Lm,N]
+    per requested speaker, and everything the backward needs."""
+    L_, cfg, sep, st, dev = lib(), model.cfg, model.separation, _st(), enc.device
     N, F, H, K, P = cfg['input_size'], cfg['feature_size'], cfg['hidden_size'], cfg['chunk_length'], cfg['hop_length']
-    B, T = mix.shape
-    is_spe = cfg['kind'] == 'spe'
-    Lm, Lr = T - 1, (ref.shape[1] - 1 if is_spe else 0)
-    ctx = dict(B=B, T=T, L=Lm, Lr=Lr, mix=mix, ref=ref, div=div, tf32=ops.tf32)
-    w_enc = model.encoder.conv1d.weight.detach().reshape(N, 2).contiguous()
-    enc = ops.empty(B, Lm, N)
-    L_.call('dprnn_encoder_fwd', mix, w_enc, enc, B, T, N, 2, 1, st)
-    feats = emb = None
-    E = 0
-    if is_spe:
-        feats = ops.empty(B, Lr, N)
-        L_.call('dprnn_encoder_fwd', ref, w_enc, feats, B, ref.shape[1], N, 2, 1, st)
-    ctx.update(enc=enc, feats=feats, emb=None)
-
-    if is_spe:
-        # ---- speaker encoder (dprnn_spe.py:115-122,156-163), BatchNorm in train mode.  Its contractions stay exact fp32 in
-    # both modes: the train-mode BatchNorm chain and the scalar PReLU slope gradients are cancellation-heavy (TF32 there
-    # moved one slope gradient by 40 %) and the branch is < 3 % of the step
-        se = sep.spk_encoder
-        mr_s = ops.utt_stats(feats, B, Lr * N, se[0].eps)
-        s1 = ops.empty(B, N); s0 = ops.empty(B, N)
-        L_.call('dprnn_norm_affine', mr_s, se[0].weight.detach(), se[0].bias.detach(), None, s1, s0, B, N, st)
-        gnf = torch.empty_like(feats)                                  # GroupNorm(feats): kept for dW of conv0
-        L_.call('dprnn_prologue_apply', feats, gnf, B * Lr, N, Lr, s1, s0, None, None, st)
-        O = se[1].weight.shape[0]
-        x = ops.gemm(gnf, se[1].weight.detach().reshape(O, N).t().contiguous(), B * Lr, O, N, bias=se[1].bias.detach())
-        ctx.update(mr_s=mr_s, gnf=gnf)
-        res, Lx = [], Lr
-        for rb in (se[2], se[3], se[4]):
-            Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
-            rows = B * Lx
-            rc = dict(x=x, Lx=Lx, Cin=Cin, Cout=Cout)
-            ws = torch.empty(L_.query('dprnn_bn_workspace_bytes', Cout), device=dev, dtype=torch.uint8)
-
-            def bn(y, bnm):
-                scale, shift = ops.empty(Cout), ops.empty(Cout)
-                L_.call('dprnn_batchnorm_affine', y, rows, Cout, bnm.weight.detach(), bnm.bias.detach(), bnm.running_mean,
-                        bnm.running_var, 1, float(bnm.eps), float(bnm.momentum if bnm.momentum is not None else 0.1), ws,
-                        scale, shift, st)
-                bnm.num_batches_tracked += 1
-                return scale, shift
-
-            y1 = ops.gemm(x, rb.conv1.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
-            sc1, sh1 = bn(y1, rb.batch_norm1)
-            a1 = ops.empty(rows, Cout)
-            L_.call('dprnn_affine_prelu', y1, sc1, sh1, rb.prelu1.weight.detach(), a1, rows, Cout, st)
-            y2 = ops.gemm(a1, rb.conv2.weight.detach().reshape(Cout, Cout).t().contiguous(), rows, Cout, Cout)
-            sc2, sh2 = bn(y2, rb.batch_norm2)
-            if hasattr(rb, 'conv_downsample'):
-                skip = ops.gemm(x, rb.conv_downsample.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
-            else:
-                skip = x
-            Lo = Lx // 3
-            out = ops.empty(B, Lo, Cout)
-            L_.call('dprnn_affine_add_prelu_pool3', y2, sc2, sh2, skip, rb.prelu2.weight.detach(), out, B, Lx, Cout, st)
-            rc.update(y1=y1, sc1=sc1, sh1=sh1, a1=a1, y2=y2, sc2=sc2, sh2=sh2, skip=skip)
-            res.append(rc)
-            x, Lx = out.view(B * Lo, Cout), Lo
-        E = se[5].weight.shape[0]
-        C5 = se[5].weight.shape[1]
-        z5 = ops.gemm(x, se[5].weight.detach().reshape(E, C5).t().contiguous(), B * Lx, E, C5, bias=se[5].bias.detach())
-        emb = ops.empty(B, E)
-        L_.call('dprnn_time_sum', z5, emb, B, Lx, E, div, st)
-        ctx.update(res=res, x3=x, L3=Lx, emb=emb)
-
-    # ---- bottleneck norm + fusion + 1x1 conv (dprnn_spe.py:136-143)
-    gamma, beta, eps = _norm_params(sep.bottleneck[0])
-    mr_e = ops.utt_stats(enc, B, Lm * N, eps)
-    ft = cfg['fusion_type'] if is_spe else None
-
-    def lin(m):
-        out = ops.empty(B, m.weight.shape[0])
-        L_.call('dprnn_small_linear', emb, E, m.weight.detach(), E, m.bias.detach(), out, out.shape[1], B, out.shape[1], E, 0, st)
-        return out
-
+    gamma, beta, _ = _norm_params(sep.bottleneck[0])
+    ft = cfg['fusion_type'] if emb is not None else None
+    E = emb.shape[1] if emb is not None else 0
     mulc = addc = None
     bw = sep.bottleneck[1].weight.detach().reshape(F, -1)
     bias, bias_per_utt = sep.bottleneck[1].bias.detach(), False
     if ft == 'film':
-        mulc, addc = lin(sep.fusion_linear_1), lin(sep.fusion_linear_2)
+        mulc, addc = _emb_linear(ops, emb, sep.fusion_linear_1), _emb_linear(ops, emb, sep.fusion_linear_2)
     elif ft == 'add':
-        addc = lin(sep.fusion_linear)
+        addc = _emb_linear(ops, emb, sep.fusion_linear)
     elif ft == 'mul':
-        mulc = lin(sep.fusion_linear)
+        mulc = _emb_linear(ops, emb, sep.fusion_linear)
     elif ft == 'cat':
         bias = ops.empty(B, F)
         L_.call('dprnn_small_linear', emb, E, bw.data_ptr() + 4 * N, N + E, sep.bottleneck[1].bias.detach(), bias, F, B, F, E, 0, st)
@@ -241,7 +230,7 @@ def forward_train(model, mix, ref=None, div=None):
     rowscale = att_a = None
     if ft == 'att':                                                 # dprnn_spe.py:177-183,217-225
         ksz = cfg['kernel_size']
-        mulc = lin(sep.fusion_linear)
+        mulc = _emb_linear(ops, emb, sep.fusion_linear)
         n1, n0 = ops.empty(B, N), ops.empty(B, N)
         L_.call('dprnn_norm_affine', mr_e, gamma.detach(), beta.detach(), None, n1, n0, B, N, st)
         att_a = ops.empty(B, (Lm - ksz) // ksz + 1)                 # softmax over the averaged frames (kept for the backward)
@@ -258,7 +247,7 @@ def forward_train(model, mix, ref=None, div=None):
     L_.call('dprnn_unfold', y, xs, B, Lm, K, P, F, st)
     del y
     rows = B * S * K
-    ctx.update(mr_e=mr_e, mulc=mulc, addc=addc, fused=fused, S=S, rows=rows, rowscale=rowscale, att_a=att_a)
+    c = dict(B=B, Lm=Lm, emb=emb, mulc=mulc, addc=addc, fused=fused, S=S, rows=rows, rowscale=rowscale, att_a=att_a)
 
     # ---- DPRNN blocks (dprnn.py:79-99)
     halves = []
@@ -296,9 +285,9 @@ def forward_train(model, mix, ref=None, div=None):
             L_.call('dprnn_norm_residual', yl, xs, mr, g_.detach(), b_.detach(), B, S * K, F, None, st)
             halves.append(dict(nd=nd, geo=geo, hout=hout, gates=gates, cst=cst, yl=yl, mr=mr, wih=wih, whh=whh,
                                rnn=rnn, lin=linm, norm=nm, sfx=sfx))
-    ctx.update(halves=halves, xs=xs)
+    c.update(halves=halves, xs=xs)
 
-    # ---- PReLU, overlap-add, conv2d (speaker 0), gated head, end conv, mask, decoder (dprnn_spe.py:231-248,323-325)
+    # ---- PReLU, overlap-add, conv2d, gated head, end conv + activation (dprnn_spe.py:231-248)
     z = ops.empty(B, Lm, F)
     L_.call('dprnn_fold_prelu', xs, z, B, Lm, K, P, F, sep.prelu.weight.detach(), st)
     cw = sep.conv2d.weight.detach().reshape(2 * F, F)
@@ -306,82 +295,176 @@ def forward_train(model, mix, ref=None, div=None):
     wog = torch.cat([sep.out[0].weight.detach().reshape(F, F), sep.gate[0].weight.detach().reshape(F, F)], 0)   # [2F,F]
     bog = torch.cat([sep.out[0].bias.detach(), sep.gate[0].bias.detach()], 0)
     act = EPI_SIGMOID if cfg['activation_type'] == 'sigmoid' else EPI_RELU
-    w_dec = model.decoder.weight.detach().reshape(N, 2).contiguous()
-    # DPRNN-Spe keeps speaker 0 only (dprnn_spe.py:325); DPRNN-TasNet decodes both (dprnn.py:277-281)
-    spks = (0,) if is_spe else (0, 1)
-    est = ops.empty(B, T) if is_spe else ops.empty(B, 2, T)
     heads = []
     for sp in spks:
         u = ops.mm(z, cw[sp * F:(sp + 1) * F], B * Lm, F, F,
-                     bias=(2.0 * cb[sp * F:(sp + 1) * F]).contiguous())       # overlap-add sums two chunks: bias twice
+                   bias=(2.0 * cb[sp * F:(sp + 1) * F]).contiguous())         # overlap-add sums two chunks: bias twice
         pre = ops.mm(u, wog, B * Lm, 2 * F, F, bias=bog)
         g = ops.empty(B * Lm, F)
         L_.call('dprnn_gated_fwd', pre, g, B * Lm, F, st)
         m = ops.mm(g, sep.end_conv1x1.weight.detach().reshape(N, F), B * Lm, N, F, epi=act)
+        heads.append(dict(sp=sp, u=u, pre=pre, g=g, m=m))
+    c.update(z=z, heads=heads, wog=wog, cw=cw)
+    return [hd['m'] for hd in heads], c
+
+
+def forward_train(model, mix, ref=None, div=None, embedding=None):
+    """-> est, logits, ctx (everything the backward needs).
+    DPRNNTasNet (ref = div = None): est [B,2,T], logits None.  DPRNNSpeTasNet: est [B,T], logits [B,num_spks].
+    DPRNNSpeIRATasNet: the two masker passes of dprnn_spe_ira.py:53-115.  embedding [B,E] (DPRNNRawNetTasNet, whose speaker
+    encoder runs outside): replaces the speaker encoder; the backward then also returns its gradient."""
+    _check_supported(model)
+    L_, cfg, sep = lib(), model.cfg, model.separation
+    dev = mix.device
+    ops = _Ops(dev, tf32=model.precision == 'bf16')
+    st = _st()
+    N = cfg['input_size']
+    B, T = mix.shape
+    kind = cfg['kind']
+    tss = kind != 'bss'
+    Lm = T - 1
+    w_enc = model.encoder.conv1d.weight.detach().reshape(N, 2).contiguous()
+    w_dec = model.decoder.weight.detach().reshape(N, 2).contiguous()
+    enc = ops.empty(B, Lm, N)
+    L_.call('dprnn_encoder_fwd', mix, w_enc, enc, B, T, N, 2, 1, st)
+    ctx = dict(B=B, T=T, L=Lm, mix=mix, ref=ref, enc=enc, tf32=ops.tf32, kind=kind, ext_emb=embedding is not None)
+    emb = embedding
+    if tss and embedding is None:
+        Lr = ref.shape[1] - 1
+        feats = ops.empty(B, Lr, N)
+        L_.call('dprnn_encoder_fwd', ref, w_enc, feats, B, ref.shape[1], N, 2, 1, st)
+        emb, ctx['spk0'] = _spk_fwd(model, ops, feats, B, Lr, div)
+    _, _, eps = _norm_params(sep.bottleneck[0])
+    mr_e = ops.utt_stats(enc, B, Lm * N, eps)
+    ctx['mr_e'] = mr_e
+    if kind == 'ira':
+        # first pass, d0 = mask * enc, re-embedding (still divided by the REFERENCE's length, :84), aux_linear(cat(v0, v1))
+        (m0,), ctx['core0'] = _core_fwd(model, ops, enc, mr_e, emb, B, Lm, (0,))
+        d0 = ops.empty(B, Lm, N)
+        L_.call('dprnn_mask_apply', m0, enc, d0, B * Lm * N, st)
+        v1p, ctx['spk1'] = _spk_fwd(model, ops, d0, B, Lm, div)
+        E = emb.shape[1]
+        v = _emb_linear(ops, emb, sep.aux_linear, 0, E)                       # W[:, :E] v0 + b
+        L_.call('dprnn_small_linear', v1p, E, sep.aux_linear.weight.detach().data_ptr() + 4 * E, 2 * E, None, v, E, B, E, E,
+                1, st)                                                        # + W[:, E:] v1
+        ctx.update(v0=emb, v1p=v1p)
+        emb = v
+    spks = (0,) if tss else (0, 1)
+    masks, ctx['core'] = _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks)
+    est = ops.empty(B, T) if tss else ops.empty(B, 2, T)
+    for sp, m in zip(spks, masks):
+        # DPRNN-Spe keeps speaker 0 only (dprnn_spe.py:325); DPRNN-TasNet decodes both (dprnn.py:277-281)
         L_.call('dprnn_mask_decode', m, Lm * N, enc, w_dec, est.data_ptr() + 4 * sp * T, len(spks) * T, B, Lm, N, 2, 1, st)
-        heads.append(dict(u=u, pre=pre, g=g, m=m))
     logits = None
-    if is_spe:
-        logits = ops.empty(B, sep.pred_linear.weight.shape[0])
-        L_.call('dprnn_small_linear', emb, E, sep.pred_linear.weight.detach(), E, sep.pred_linear.bias.detach(), logits,
-                logits.shape[1], B, logits.shape[1], E, 0, st)
-    ctx.update(z=z, heads=heads, wog=wog, cw=cw)
+    if tss:
+        logits = _emb_linear(ops, emb, sep.pred_linear)
+    ctx['emb'] = emb
     return est, logits, ctx
 
 
 # --------------------------------------------------------------------------------------------------------------
 # backward
 # --------------------------------------------------------------------------------------------------------------
-def backward_train(model, ctx, d_est, d_logits, G=None):
-    """-> {parameter name: gradient tensor} for every trainable parameter of the model.  ``G`` may be given (zeroed
-    views into a flat gradient buffer, dp.FlatParams); every kernel accumulates into it."""
-    L_, cfg, sep = lib(), model.cfg, model.separation
-    dev = d_est.device
-    ops = _Ops(dev, tf32=ctx['tf32'])
-    st = _st()
-    N, F, H, K, P = cfg['input_size'], cfg['feature_size'], cfg['hidden_size'], cfg['chunk_length'], cfg['hop_length']
-    B, T, Lm, Lr, S, rows = ctx['B'], ctx['T'], ctx['L'], ctx['Lr'], ctx['S'], ctx['rows']
-    enc, feats, emb, div = ctx['enc'], ctx['feats'], ctx['emb'], ctx['div']
-    is_spe = cfg['kind'] == 'spe'
-    E = emb.shape[1] if is_spe else 0
-    if ctx.get('consumed'):
-        raise RuntimeError('this forward has already been differentiated: the hand-written backward walks the saved '
-                           'activations back in place (retain_graph / a second backward is not supported)')
-    ctx['consumed'] = True
-    if G is None:
-        G = {n: torch.zeros_like(p) for n, p in model.named_parameters() if p.requires_grad}
-    # frozen parameters (fine-tuning with e.g. a frozen speaker encoder; the reference optimises filter(requires_grad),
-    # src/trainers/trainer.py:42-43): their gradients are computed into scratch and dropped
-    G = dict(G)
-    for n, p in model.named_parameters():
-        if n not in G:
-            G[n] = torch.zeros_like(p)
-    d_est = d_est.contiguous().float()
-    if is_spe:
-        d_logits = d_logits.contiguous().float()
-    ML = B * Lm
+def _emb_linear_bwd(ops, mod, name, emb, dv, demb, G, w_off=0, K=None):
+    """dv [B, out]: gradient of mod(emb) (weight columns [w_off, w_off + K)) -> weight / bias gradients, demb += dv @ W"""
+    B, E = emb.shape
+    Kin = mod.weight.shape[1]
+    K = E if K is None else K
+    out = dv.shape[1]
+    ops.atb(dv, emb, B, out, K, G[name + '.weight'].data_ptr() + 4 * w_off, ldb=E, ldc=Kin)
+    if w_off == 0:
+        ops.colsum(dv, B, out, G[name + '.bias'])
+    wt = mod.weight.detach()[:, w_off:w_off + K].t().contiguous()       # [K, out]: demb[b,e] += sum_j dv[b,j] W[j,e]
+    lib().call('dprnn_small_linear', dv, out, wt, out, None, demb, demb.shape[1], B, K, out, 1, _st())
 
-    # ---- decoder, mask, end conv, gated head, conv2d (per decoded speaker)
-    z = ctx['z']
-    w_dec = model.decoder.weight.detach().reshape(N, 2).contiguous()
-    wsw = torch.empty(L_.query('dprnn_convw2_workspace_bytes', N), device=dev, dtype=torch.uint8)
+
+def _spk_bwd(model, ops, sc, demb, G):
+    """Adjoint of _spk_fwd: demb [B,E] -> gradient of its input features [B*Lr,N]; parameter gradients into G."""
+    L_, sep, st, dev = lib(), model.separation, _st(), demb.device
+    N = model.cfg['input_size']
+    se = sep.spk_encoder
+    B, Lr, L3, x3, div, feats = sc['B'], sc['Lr'], sc['L3'], sc['x3'], sc['div'], sc['feats']
+    E = demb.shape[1]
+    C5 = se[5].weight.shape[1]
+    dscaled = torch.empty_like(demb)
+    L_.call('dprnn_bcast_mul', (1.0 / div).contiguous().view(B, 1).expand(B, E).contiguous(), demb, dscaled, B, 1, E, 0, st)
+    dz5 = ops.empty(B * L3, E)
+    L_.call('dprnn_bcast_mul', dscaled, None, dz5, B, L3, E, 0, st)
+    ops.atb(dz5, x3, B * L3, E, C5, G['separation.spk_encoder.5.weight'])
+    ops.colsum(dz5, B * L3, E, G['separation.spk_encoder.5.bias'])
+    dout = ops.gemm(dz5, se[5].weight.detach().reshape(E, C5).contiguous(), B * L3, C5, E)
+    del dz5
+    for bi, (rb, rc) in reversed(list(enumerate(zip((se[2], se[3], se[4]), sc['res'])))):
+        pre_n = f'separation.spk_encoder.{bi + 2}'
+        Cin, Cout, Lx, x = rc['Cin'], rc['Cout'], rc['Lx'], rc['x']
+        rws = B * Lx
+        # recompute v2 = BN2(y2) + skip and p2 = prelu(v2)
+        v2 = ops.empty(rws, Cout)
+        one = torch.ones(1, device=dev)
+        L_.call('dprnn_affine_prelu', rc['y2'], rc['sc2'], rc['sh2'], one, v2, rws, Cout, st)      # slope 1 = identity
+        ops.axpy(rc['skip'], v2)
+        p2 = ops.empty(rws, Cout)
+        ident_s, ident_b = torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev)
+        L_.call('dprnn_affine_prelu', v2, ident_s, ident_b, rb.prelu2.weight.detach(), p2, rws, Cout, st)
+        dp2 = ops.empty(rws, Cout)
+        L_.call('dprnn_pool3_bwd', dout, p2, dp2, B, Lx, Cout, st)
+        dv2 = ops.prelu_bwd(dp2, v2, rb.prelu2.weight.detach(), G[pre_n + '.prelu2.weight'])
+        del p2, dp2, v2
+
+        def bn_bwd(dv, y, scale, shift, bnm, name):
+            gmm = bnm.weight.detach()
+            rstd = (scale / gmm).contiguous()
+            mean = ((bnm.bias.detach() - shift) / scale).contiguous()
+            s_d, s_dy = ops.empty(Cout), ops.empty(Cout)
+            ops.colsum(dv, rws, Cout, s_d, accumulate=False)
+            ops.colsum(dv, rws, Cout, s_dy, Y=y, accumulate=False)
+            s_dyh = (rstd * (s_dy - mean * s_d)).contiguous()        # sum dv * yhat
+            G[name + '.weight'] += s_dyh
+            G[name + '.bias'] += s_d
+            dy = ops.empty(rws, Cout)
+            L_.call('dprnn_bn_bwd_apply', dv, y, mean, rstd, gmm, (s_d / rws).contiguous(), (s_dyh / rws).contiguous(), dy,
+                    rws, Cout, st)
+            return dy
+
+        dy2 = bn_bwd(dv2, rc['y2'], rc['sc2'], rc['sh2'], rb.batch_norm2, pre_n + '.batch_norm2')
+        ops.atb(dy2, rc['a1'], rws, Cout, Cout, G[pre_n + '.conv2.weight'])
+        da1 = ops.gemm(dy2, rb.conv2.weight.detach().reshape(Cout, Cout).contiguous(), rws, Cout, Cout)
+        v1 = ops.empty(rws, Cout)
+        L_.call('dprnn_affine_prelu', rc['y1'], rc['sc1'], rc['sh1'], one, v1, rws, Cout, st)
+        dv1 = ops.prelu_bwd(da1, v1, rb.prelu1.weight.detach(), G[pre_n + '.prelu1.weight'])
+        dy1 = bn_bwd(dv1, rc['y1'], rc['sc1'], rc['sh1'], rb.batch_norm1, pre_n + '.batch_norm1')
+        ops.atb(dy1, x, rws, Cout, Cin, G[pre_n + '.conv1.weight'])
+        dxr = ops.gemm(dy1, rb.conv1.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
+        if hasattr(rb, 'conv_downsample'):
+            ops.atb(dv2, x, rws, Cout, Cin, G[pre_n + '.conv_downsample.weight'])
+            t = ops.gemm(dv2, rb.conv_downsample.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
+            ops.axpy(t, dxr)
+        else:
+            ops.axpy(dv2, dxr)
+        dout = dxr
+        del dy1, dy2, da1, dv1, dv2, v1
+    O = se[1].weight.shape[0]
+    ops.atb(dout, sc['gnf'], B * Lr, O, N, G['separation.spk_encoder.1.weight'])
+    ops.colsum(dout, B * Lr, O, G['separation.spk_encoder.1.bias'])
+    dgnf = ops.gemm(dout, se[1].weight.detach().reshape(O, N).contiguous(), B * Lr, N, O)
+    return ops.gn_bwd(dgnf, feats, sc['mr_s'], se[0].weight.detach(), B, Lr, N, G['separation.spk_encoder.0.weight'],
+                      G['separation.spk_encoder.0.bias'])
+
+
+def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
+    """Adjoint of _core_fwd.  dms: gradient of every mask it returned ([B*Lm,N] each); denc [B*Lm,N] receives (+=) the
+    gradient reaching enc through the bottleneck norm; demb [B,E] (+=) the one reaching the embedding through the fusion."""
+    L_, cfg, sep, st, dev = lib(), model.cfg, model.separation, _st(), enc.device
+    N, F, H, K, P = cfg['input_size'], cfg['feature_size'], cfg['hidden_size'], cfg['chunk_length'], cfg['hop_length']
+    B, Lm, S, rows, emb = c['B'], c['Lm'], c['S'], c['rows'], c['emb']
+    E = emb.shape[1] if emb is not None else 0
+    ML = B * Lm
+    z = c['z']
     gout, ggate = G['separation.out.0.weight'], G['separation.gate.0.weight']
     gcw, gcb = G['separation.conv2d.weight'], G['separation.conv2d.bias']       # [2F,F,1,1]: rows of the decoded speakers
-    denc = dz = None
-    for sp, hd in enumerate(ctx['heads']):
-        m, g, pre, u = hd['m'], hd['g'], hd['pre'], hd['u']
-        de = d_est if is_spe else d_est[:, sp].contiguous()
-        dze = ops.empty(B, Lm, N)
-        L_.call('dprnn_decoder_bwd', de, w_dec, dze, B, Lm, N, st)
-        me = ops.mul(m, enc.view(ML, N))
-        L_.call('dprnn_convw2_grad', me, de, B, Lm, N, G['decoder.weight'], 1, wsw, st)
-        del me
-        dm = ops.mul(dze.view(ML, N), enc.view(ML, N))
-        t = ops.mul(dze.view(ML, N), m)                             # gradient reaching enc through the mask product
-        if denc is None:
-            denc = t
-        else:
-            ops.axpy(t, denc)
+    dz = None
+    for hd, dm in zip(c['heads'], dms):
+        sp, m, g, pre, u = hd['sp'], hd['m'], hd['g'], hd['pre'], hd['u']
         dpm = torch.empty_like(dm)
         L_.call('dprnn_act_bwd', dm, m, dpm, dm.numel(), 2 if cfg['activation_type'] == 'sigmoid' else 1, st)
         ops.atb(dpm, g, ML, N, F, G['separation.end_conv1x1.weight'])
@@ -392,20 +475,20 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
         ops.atb(dpre.data_ptr() + 4 * F, u, ML, F, F, ggate, lda=2 * F)
         ops.colsum(dpre, ML, F, G['separation.out.0.bias'], ldx=2 * F)
         ops.colsum(dpre.data_ptr() + 4 * F, ML, F, G['separation.gate.0.bias'], ldx=2 * F)
-        du = ops.mm(dpre, ctx['wog'].t().contiguous(), ML, F, 2 * F)
+        du = ops.mm(dpre, c['wog'].t().contiguous(), ML, F, 2 * F)
         ops.atb(du, z, ML, F, F, gcw.data_ptr() + 4 * sp * F * F)
         dbc = ops.empty(F)
         ops.colsum(du, ML, F, dbc, accumulate=False)
         L_.call('dprnn_axpy', dbc, 2.0, gcb.data_ptr() + 4 * sp * F, F, 1, st)    # the folded conv adds the bias twice
-        t = ops.mm(du, ctx['cw'][sp * F:(sp + 1) * F].t().contiguous(), ML, F, F)
+        t = ops.mm(du, c['cw'][sp * F:(sp + 1) * F].t().contiguous(), ML, F, F)
         if dz is None:
             dz = t
         else:
             ops.axpy(t, dz)
-        del du, dpre, dg, dpm, dm, dze, t
+        del du, dpre, dg, dpm, t
         hd.clear()
     # fold adjoint = unfold; then the PReLU adjoint on the final residual stream
-    xs = ctx['xs']
+    xs = c['xs']
     dxp = ops.empty(B, S, K, F)
     L_.call('dprnn_unfold', dz, dxp, B, Lm, K, P, F, st)
     dx = ops.prelu_bwd(dxp, xs, sep.prelu.weight.detach(), G['separation.prelu.weight'])
@@ -434,7 +517,7 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
         for t_ in tensors:
             t_.record_stream(side)
 
-    for hv in reversed(ctx['halves']):
+    for hv in reversed(c['halves']):
         nd, geo, yl, mr = hv['nd'], hv['geo'], hv['yl'], hv['mr']
         g_, b_, _ = _norm_params(hv['norm'])
         pn = names[id(hv['norm'])]
@@ -489,26 +572,21 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
     dyb = ops.empty(B, Lm, F)
     L_.call('dprnn_fold_prelu', dx, dyb, B, Lm, K, P, F, None, st)
     del dx
-    fused, mulc, addc, mr_e = ctx['fused'], ctx['mulc'], ctx['addc'], ctx['mr_e']
+    fused, mulc, addc = c['fused'], c['mulc'], c['addc']
     gbw = G['separation.bottleneck.1.weight']                       # [F, N(+E), 1]
     ldw = gbw.shape[1]
     ops.atb(dyb, fused, ML, F, N, gbw, ldc=ldw)
     ops.colsum(dyb, ML, F, G['separation.bottleneck.1.bias'])
     bw = sep.bottleneck[1].weight.detach().reshape(F, -1)
     dfused = ops.mm(dyb, bw[:, :N].t().contiguous(), ML, N, F)                    # first N input channels of the conv
-    demb = torch.zeros_like(emb) if is_spe else None
-    ft = cfg['fusion_type'] if is_spe else None
+    ft = cfg['fusion_type'] if emb is not None else None
     gamma, beta, _ = _norm_params(sep.bottleneck[0])
     bn0 = 'separation.bottleneck.0'
     gname = bn0 + ('.gamma' if hasattr(sep.bottleneck[0], 'gamma') else '.weight')
     bname = bn0 + ('.beta' if hasattr(sep.bottleneck[0], 'gamma') else '.bias')
 
     def lin_bwd(mod, name, dv):
-        """dv [B, out]: gradient of mod(emb) -> weight / bias gradients, demb += dv @ W"""
-        ops.atb(dv, emb, B, dv.shape[1], E, G[name + '.weight'])
-        ops.colsum(dv, B, dv.shape[1], G[name + '.bias'])
-        wt = mod.weight.detach().t().contiguous()                   # [E, out]: demb[b,e] += sum_j dv[b,j] W[j,e]
-        L_.call('dprnn_small_linear', dv, dv.shape[1], wt, dv.shape[1], None, demb, E, B, E, dv.shape[1], 1, st)
+        _emb_linear_bwd(ops, mod, name, emb, dv, demb, G)
 
     if ft == 'cat':
         # constant channels: y += W_e e per utterance -> de = sum_t dy @ W_e ; dW_e = (sum_t dy)^T e
@@ -526,10 +604,10 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
         L_.call('dprnn_prologue_apply', enc, gn, ML, N, Lm, s1, s0, None, None, st)
         dr = ops.empty(B, Lm)
         L_.call('dprnn_row_dot3', dfused, gn, mulc, ML, Lm, N, dr, st)
-        w2, ds = ops.empty(B, Lm), torch.empty_like(ctx['att_a'])
-        L_.call('dprnn_att_softmax_bwd', dr, ctx['att_a'], B, Lm, ksz, w2, ds, st)
+        w2, ds = ops.empty(B, Lm), torch.empty_like(c['att_a'])
+        L_.call('dprnn_att_softmax_bwd', dr, c['att_a'], B, Lm, ksz, w2, ds, st)
         dgn, tdv = torch.empty_like(dfused), torch.empty_like(dfused)
-        L_.call('dprnn_att_bwd_apply', dfused, gn, mulc, ctx['rowscale'], w2, sep.average.weight.detach(), B, Lm, N, ksz,
+        L_.call('dprnn_att_bwd_apply', dfused, gn, mulc, c['rowscale'], w2, sep.average.weight.detach(), B, Lm, N, ksz,
                 dgn, tdv, st)
         lin_bwd(sep.fusion_linear, 'separation.fusion_linear', ops.utt_colsum(tdv, None, B, Lm, N))
         del gn, tdv, dr, w2
@@ -555,82 +633,87 @@ def backward_train(model, ctx, d_est, d_logits, G=None):
             dgn = dfused
     # GroupNorm(enc) adjoint, accumulated onto the gradient that reached enc through the mask product
     ops.gn_bwd(dgn, enc, mr_e, gamma.detach(), B, Lm, N, G[gname], G[bname], dy=denc, accumulate_dy=True)
-    del dgn, dfused, dyb
 
-    if is_spe:
-        # ---- pred_linear, then the speaker encoder
-        lin_bwd(sep.pred_linear, 'separation.pred_linear', d_logits)
-        se = sep.spk_encoder
-        L3, x3 = ctx['L3'], ctx['x3']
-        C5 = se[5].weight.shape[1]
-        dscaled = torch.empty_like(demb)
-        L_.call('dprnn_bcast_mul', (1.0 / div).contiguous().view(B, 1).expand(B, E).contiguous(), demb, dscaled, B, 1, E, 0, st)
-        dz5 = ops.empty(B * L3, E)
-        L_.call('dprnn_bcast_mul', dscaled, None, dz5, B, L3, E, 0, st)
-        ops.atb(dz5, x3, B * L3, E, C5, G['separation.spk_encoder.5.weight'])
-        ops.colsum(dz5, B * L3, E, G['separation.spk_encoder.5.bias'])
-        dout = ops.gemm(dz5, se[5].weight.detach().reshape(E, C5).contiguous(), B * L3, C5, E)
-        del dz5
-        for bi, (rb, rc) in reversed(list(enumerate(zip((se[2], se[3], se[4]), ctx['res'])))):
-            pre_n = f'separation.spk_encoder.{bi + 2}'
-            Cin, Cout, Lx, x = rc['Cin'], rc['Cout'], rc['Lx'], rc['x']
-            rws = B * Lx
-            # recompute v2 = BN2(y2) + skip and p2 = prelu(v2)
-            v2 = ops.empty(rws, Cout)
-            one = torch.ones(1, device=dev)
-            L_.call('dprnn_affine_prelu', rc['y2'], rc['sc2'], rc['sh2'], one, v2, rws, Cout, st)      # slope 1 = identity
-            ops.axpy(rc['skip'], v2)
-            p2 = ops.empty(rws, Cout)
-            ident_s, ident_b = torch.ones(Cout, device=dev), torch.zeros(Cout, device=dev)
-            L_.call('dprnn_affine_prelu', v2, ident_s, ident_b, rb.prelu2.weight.detach(), p2, rws, Cout, st)
-            dp2 = ops.empty(rws, Cout)
-            L_.call('dprnn_pool3_bwd', dout, p2, dp2, B, Lx, Cout, st)
-            dv2 = ops.prelu_bwd(dp2, v2, rb.prelu2.weight.detach(), G[pre_n + '.prelu2.weight'])
-            del p2, dp2, v2
 
-            def bn_bwd(dv, y, scale, shift, bnm, name):
-                gmm = bnm.weight.detach()
-                rstd = (scale / gmm).contiguous()
-                mean = ((bnm.bias.detach() - shift) / scale).contiguous()
-                s_d, s_dy = ops.empty(Cout), ops.empty(Cout)
-                ops.colsum(dv, rws, Cout, s_d, accumulate=False)
-                ops.colsum(dv, rws, Cout, s_dy, Y=y, accumulate=False)
-                s_dyh = (rstd * (s_dy - mean * s_d)).contiguous()        # sum dv * yhat
-                G[name + '.weight'] += s_dyh
-                G[name + '.bias'] += s_d
-                dy = ops.empty(rws, Cout)
-                L_.call('dprnn_bn_bwd_apply', dv, y, mean, rstd, gmm, (s_d / rws).contiguous(), (s_dyh / rws).contiguous(), dy,
-                        rws, Cout, st)
-                return dy
+def backward_train(model, ctx, d_est, d_logits, G=None):
+    """-> {parameter name: gradient tensor} for every trainable parameter of the model.  ``G`` may be given (zeroed
+    views into a flat gradient buffer, dp.FlatParams); every kernel accumulates into it.  With an external embedding
+    (forward_train(embedding=...)) the gradient of that embedding is left in ctx['d_embedding']."""
+    L_, cfg, sep = lib(), model.cfg, model.separation
+    dev = d_est.device
+    ops = _Ops(dev, tf32=ctx['tf32'])
+    st = _st()
+    N = cfg['input_size']
+    B, T, Lm, enc, mr_e, kind = ctx['B'], ctx['T'], ctx['L'], ctx['enc'], ctx['mr_e'], ctx['kind']
+    tss = kind != 'bss'
+    if ctx.get('consumed'):
+        raise RuntimeError('this forward has already been differentiated: the hand-written backward walks the saved '
+                           'activations back in place (retain_graph / a second backward is not supported)')
+    ctx['consumed'] = True
+    if G is None:
+        G = {n: torch.zeros_like(p) for n, p in model.named_parameters() if p.requires_grad}
+    # frozen parameters (fine-tuning with e.g. a frozen speaker encoder; the reference optimises filter(requires_grad),
+    # src/trainers/trainer.py:42-43): their gradients are computed into scratch and dropped
+    G = dict(G)
+    for n, p in model.named_parameters():
+        if n not in G:
+            G[n] = torch.zeros_like(p)
+    d_est = d_est.contiguous().float()
+    ML = B * Lm
+    w_dec = model.decoder.weight.detach().reshape(N, 2).contiguous()
+    wsw = torch.empty(L_.query('dprnn_convw2_workspace_bytes', N), device=dev, dtype=torch.uint8)
+    encv = enc.view(ML, N)
 
-            dy2 = bn_bwd(dv2, rc['y2'], rc['sc2'], rc['sh2'], rb.batch_norm2, pre_n + '.batch_norm2')
-            ops.atb(dy2, rc['a1'], rws, Cout, Cout, G[pre_n + '.conv2.weight'])
-            da1 = ops.gemm(dy2, rb.conv2.weight.detach().reshape(Cout, Cout).contiguous(), rws, Cout, Cout)
-            v1 = ops.empty(rws, Cout)
-            L_.call('dprnn_affine_prelu', rc['y1'], rc['sc1'], rc['sh1'], one, v1, rws, Cout, st)
-            dv1 = ops.prelu_bwd(da1, v1, rb.prelu1.weight.detach(), G[pre_n + '.prelu1.weight'])
-            dy1 = bn_bwd(dv1, rc['y1'], rc['sc1'], rc['sh1'], rb.batch_norm1, pre_n + '.batch_norm1')
-            ops.atb(dy1, x, rws, Cout, Cin, G[pre_n + '.conv1.weight'])
-            dxr = ops.gemm(dy1, rb.conv1.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
-            if hasattr(rb, 'conv_downsample'):
-                ops.atb(dv2, x, rws, Cout, Cin, G[pre_n + '.conv_downsample.weight'])
-                t = ops.gemm(dv2, rb.conv_downsample.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
-                ops.axpy(t, dxr)
-            else:
-                ops.axpy(dv2, dxr)
-            dout = dxr
-            del dy1, dy2, da1, dv1, dv2, v1
-        O = se[1].weight.shape[0]
-        ops.atb(dout, ctx['gnf'], B * Lr, O, N, G['separation.spk_encoder.1.weight'])
-        ops.colsum(dout, B * Lr, O, G['separation.spk_encoder.1.bias'])
-        dgnf = ops.gemm(dout, se[1].weight.detach().reshape(O, N).contiguous(), B * Lr, N, O)
-        dfeats = ops.gn_bwd(dgnf, feats, ctx['mr_s'], se[0].weight.detach(), B, Lr, N, G['separation.spk_encoder.0.weight'],
-                            G['separation.spk_encoder.0.bias'])
-        del dgnf, dout
+    # ---- decoder and the mask product (per decoded speaker): dm = dz * enc, denc = sum dz * m
+    core = ctx['core']
+    denc, dms = None, []
+    for hd in core['heads']:
+        m = hd['m']
+        de = d_est if tss else d_est[:, hd['sp']].contiguous()
+        dze = ops.empty(B, Lm, N)
+        L_.call('dprnn_decoder_bwd', de, w_dec, dze, B, Lm, N, st)
+        me = ops.mul(m, encv)
+        L_.call('dprnn_convw2_grad', me, de, B, Lm, N, G['decoder.weight'], 1, wsw, st)
+        del me
+        dms.append(ops.mul(dze.view(ML, N), encv))
+        t = ops.mul(dze.view(ML, N), m)                             # gradient reaching enc through the mask product
+        if denc is None:
+            denc = t
+        else:
+            ops.axpy(t, denc)
+        del dze
+    emb = ctx['emb']
+    demb = torch.zeros_like(emb) if tss else None
+    _core_bwd(model, ops, core, dms, enc, mr_e, denc, demb, G)
+    del dms
+    dfeats = None
+    if tss:
+        _emb_linear_bwd(ops, sep.pred_linear, 'separation.pred_linear', emb, d_logits.contiguous().float(), demb, G)
+    if kind == 'ira':
+        # emb = aux_linear(cat(v0, v1')): gradients of both halves; v1' = speaker encoder of d0 = mask0 * enc
+        v0, v1p, core0 = ctx['v0'], ctx['v1p'], ctx['core0']
+        E = v0.shape[1]
+        dv0, dv1p = torch.zeros_like(v0), torch.zeros_like(v1p)
+        _emb_linear_bwd(ops, sep.aux_linear, 'separation.aux_linear', v0, demb, dv0, G, 0, E)
+        _emb_linear_bwd(ops, sep.aux_linear, 'separation.aux_linear', v1p, demb, dv1p, G, E, E)
+        dd0 = _spk_bwd(model, ops, ctx['spk1'], dv1p, G)             # [B*Lm, N]
+        m0 = core0['heads'][0]['m']
+        ops.axpy(ops.mul(dd0, m0), denc)
+        dm0 = ops.mul(dd0, encv)
+        del dd0
+        _core_bwd(model, ops, core0, [dm0], enc, mr_e, denc, dv0, G)
+        demb = dv0
+    if tss and not ctx['ext_emb']:
+        dfeats = _spk_bwd(model, ops, ctx['spk0'], demb, G)
+    elif tss:
+        ctx['d_embedding'] = demb
 
     # ---- encoder (shared by the mixture and the reference)
     genc = G['encoder.conv1d.weight']
-    for d_, e_, sig in (((denc, enc, ctx['mix']), (dfeats, feats, ctx['ref'])) if is_spe else ((denc, enc, ctx['mix']),)):
+    pairs = [(denc, enc, ctx['mix'])]
+    if dfeats is not None:
+        pairs.append((dfeats, ctx['spk0']['feats'], ctx['ref']))
+    for d_, e_, sig in pairs:
         dpe = torch.empty_like(d_)
         L_.call('dprnn_act_bwd', d_, e_, dpe, d_.numel(), 1, st)
         L_.call('dprnn_convw2_grad', dpe, sig, B, e_.shape[1], N, genc, 1, wsw, st)
@@ -675,11 +758,41 @@ class SpeTrainFunction(torch.autograd.Function):
         return (None, None, None, None) + tuple(G[n] for n in fctx.names)
 
 
-def forward_with_grad(model, mix, ref=None, div=None):
+class EmbTrainFunction(torch.autograd.Function):
+    """Masker + decoder with an EXTERNAL speaker embedding (DPRNN-RawNet: RawNet3 runs outside, dprnn_rawnet.py:72-105) as
+    one autograd node over the embedding and the model's trainable parameters other than the speaker encoder's."""
+
+    @staticmethod
+    def forward(fctx, model, mix, emb, *params):
+        est, logits, ctx = forward_train(model, mix, embedding=emb.detach().contiguous().float())
+        fctx.model, fctx.saved = model, ctx
+        fctx.names = _core_param_names(model)
+        return est, logits
+
+    @staticmethod
+    def backward(fctx, d_est, d_logits):
+        if d_logits is None:
+            d_logits = torch.zeros((fctx.saved['B'], fctx.model.separation.pred_linear.weight.shape[0]), device=d_est.device)
+        if d_est is None:
+            d_est = torch.zeros((fctx.saved['B'], fctx.saved['T']), device=d_logits.device)
+        ctx = fctx.saved
+        G = backward_train(fctx.model, ctx, d_est, d_logits)
+        fctx.saved = None
+        return (None, None, ctx['d_embedding']) + tuple(G[n] for n in fctx.names)
+
+
+def _core_param_names(model):
+    return [n for n, p in model.named_parameters() if p.requires_grad and not n.startswith('separation.spk_encoder.')]
+
+
+def forward_with_grad(model, mix, ref=None, div=None, embedding=None):
+    if embedding is not None:
+        named = dict(model.named_parameters())
+        return EmbTrainFunction.apply(model, mix, embedding, *[named[n] for n in _core_param_names(model)])
     params = [p for _, p in model.named_parameters() if p.requires_grad]
     if model.cfg['kind'] == 'bss':
         return TasNetTrainFunction.apply(model, mix, *params)
-    return SpeTrainFunction.apply(model, mix, ref, div, *params)
+    return SpeTrainFunction.apply(model, mix, ref, div, *params)          # DPRNN-Spe and DPRNN-Spe-IRA
 
 
 class SpeTrainStep:
@@ -696,6 +809,9 @@ class SpeTrainStep:
                  group=None):
         from .dp import FlatParams, ClipAdam
         _check_supported(model)
+        if model.cfg['kind'] == 'rawnet':
+            raise NotImplementedError('DPRNN-RawNet trains through torch autograd (RawNet3 runs as library ops): use '
+                                      'model(mix, ref16k) / loss.backward() with a torch optimiser, as TrainerRawNet does')
         if next(model.parameters()).device.type != 'cuda':
             raise RuntimeError('SpeTrainStep runs on the GPU (no CPU path)')
         model.train()
