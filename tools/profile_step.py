@@ -22,7 +22,8 @@ def main():
     ap.add_argument('--batch', type=int, default=64)
     ap.add_argument('--samples', type=int, default=24000)
     ap.add_argument('--fusion', default='cat')
-    ap.add_argument('--precision', default='bf16')
+    ap.add_argument('--precision', default='fp16')
+    ap.add_argument('--lstm-slices', type=int, default=1, help='0 = auto: the persistent time-sliced LSTM kernel')
     ap.add_argument('--repeats', type=int, default=1)
     ap.add_argument('--passes', type=int, default=1)
     a = ap.parse_args()
@@ -32,6 +33,7 @@ def main():
     torch.manual_seed(0)
     model = P.DPRNNSpeTasNet(**kw).eval().cuda()
     model.precision = a.precision
+    model._engine.lstm_slices = a.lstm_slices
     g = torch.Generator().manual_seed(1234)
     mix = (0.05 * torch.randn(a.batch, a.samples, generator=g)).cuda()
     ref = (0.05 * torch.randn(a.batch, a.samples, generator=g)).cuda()
