@@ -445,3 +445,17 @@ def test_lstm_fused_input_norm_is_bit_identical(inter, ndir, fmt):
         assert torch.equal(xout[:rows], xa)
         assert torch.equal(got[:rows], want)
         assert float((got[rows:].float() - 7.0).abs().max()) == 0.0 and float((xout[rows:].float() - 7.0).abs().max()) == 0.0
+
+
+def test_fp16_storage_saturates_instead_of_overflowing():
+    """fp16 has 5 exponent bits: the 16-bit stores of the fp16 mode clamp at +-65504 (cvt.rn.satfinite) instead of writing
+    inf, and round to nearest even like torch everywhere else; bf16 is untouched."""
+    x = torch.tensor([1e6, -1e6, 65504.0, 70000.0, 1.0009765625, 3.14159, -0.0, 6e-8] * 64, device=DEV)
+    for h16, dtype in ((1, torch.float16), (0, torch.bfloat16)):
+        out = torch.empty(x.numel(), device=DEV, dtype=dtype)
+        P.lib().call('dprnn_cast_h16', x, out, x.numel(), h16, stream())
+        torch.cuda.synchronize()
+        want = x.to(dtype)
+        if h16:
+            want = torch.where(torch.isinf(want), torch.sign(want) * 65504.0, want)
+        assert torch.equal(out, want), (h16, out[:8], want[:8])

@@ -49,8 +49,11 @@ constexpr int H16_BF16 = 0, H16_FP16 = 1;
 template <bool kF16>
 __device__ __forceinline__ uint32_t pack_h16x2(float a, float b) {
     if constexpr (kF16) {
-        __half2 v = __floats2half2_rn(a, b);
-        return *reinterpret_cast<uint32_t*>(&v);
+        // fp16 has 5 exponent bits: a value beyond +-65504 saturates instead of becoming inf (one F2FP either way), so an
+        // outlier activation degrades one element instead of poisoning the recurrence with inf - inf
+        uint32_t v;
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(v) : "f"(b), "f"(a));
+        return v;
     } else {
         __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
         return *reinterpret_cast<uint32_t*>(&v);

@@ -671,14 +671,17 @@ class Engine(RaggedMixin):
         L_.launches += n_launch
         return tuple(o.clone() for o in out)
 
-    def _run_groups(self, B, fn, couples_batch=False):
-        """Run fn(b0, b1) -> tuple of [b1-b0, ...] tensors for utterance groups on concurrent streams and concatenate.
+    def _run_groups(self, B, fn, couples_batch=False, alloc=None):
+        """Run fn(b0, b1, outs) for utterance groups on concurrent streams.  alloc() -> the full-batch result tensors; every
+        group writes its rows outs[i][b0:b1] in place (no concatenation pass afterwards).
         Utterances are independent (unless train-mode BatchNorm couples them), so the results do not depend on the
         grouping; side by side, one group's memory-bound and GEMM kernels (encoders, speaker ResNet, head) fill the
         SMs that another group's LSTM kernel leaves idle in its partial second wave."""
         n = 1 if couples_batch else max(1, min(self.n_streams, B))
+        outs = alloc()
         if n == 1:
-            return fn(0, B)
+            fn(0, B, outs)
+            return outs
         dev = torch.cuda.current_device()
         while len(self._streams) < n:
             self._streams.append(torch.cuda.Stream(device=dev))
@@ -686,22 +689,21 @@ class Engine(RaggedMixin):
         ready = torch.cuda.Event()
         ready.record(main)
         base, extra = divmod(B, n)
-        b0, parts = 0, []
+        b0 = 0
         for i in range(n):
             b1 = b0 + base + (1 if i < extra else 0)
             st = self._streams[i]
             st.wait_event(ready)
             with torch.cuda.stream(st):
-                out = fn(b0, b1)
+                fn(b0, b1, tuple(o[b0:b1] for o in outs))
                 done = torch.cuda.Event()
                 done.record(st)
             main.wait_event(done)
             if not torch.cuda.is_current_stream_capturing():
-                for t in out:
-                    t.record_stream(main)
-            parts.append(out)
+                for t in outs:
+                    t.record_stream(st)
             b0 = b1
-        return tuple(torch.cat([p[j] for p in parts], 0) for j in range(len(parts[0])))
+        return outs
 
     def forward_bss(self, mix):
         mix = self._check_input(mix, 'input')
@@ -713,21 +715,25 @@ class Engine(RaggedMixin):
         self._guard_autograd()
         N = cfg['input_size']
 
-        def group_of(mixs, b0, b1):
+        k, st_ = cfg['kernel_size'], cfg['stride']
+        Tout = ((mix.shape[1] - k) // st_) * st_ + k
+
+        def group_of(mixs, b0, b1, outs):
             m = mixs[b0:b1]
             B = b1 - b0
             enc, L = self.encode(m)
             _, _, eps = self._norm_params(self.model.separation.bottleneck[0])
             mr = self.utt_stats(enc, B, L * N, eps)
             masks = self.masker(enc, mr, B, L, None, (0, 1))
-            Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
-            out = torch.empty((B, 2, Tout), device=mix.device)
             for s in (0, 1):
-                self.decode(masks[s], enc, out[:, s], B, L, 2 * Tout)
-            return (out,)
+                self.decode(masks[s], enc, outs[0][:, s], B, L, 2 * Tout)
+
+        def alloc():
+            return (torch.empty((mix.shape[0], 2, Tout), device=mix.device),)
 
         with torch.no_grad():
-            return self._graphed('bss', (mix,), lambda m: self._run_groups(m.shape[0], lambda b0, b1: group_of(m, b0, b1)))[0]
+            return self._graphed('bss', (mix,), lambda m: self._run_groups(
+                m.shape[0], lambda b0, b1, outs: group_of(m, b0, b1, outs), alloc=alloc))[0]
 
     def forward_spe(self, mix, ref, ref_len, embedding=None):
         mix = self._check_input(mix, 'input')
@@ -739,7 +745,11 @@ class Engine(RaggedMixin):
         sep, cfg = self.model.separation, self.model.cfg
         N = cfg['input_size']
 
-        def group(m, r, d, e, b0, b1):
+        k, st_ = cfg['kernel_size'], cfg['stride']
+        Tout = ((mix.shape[1] - k) // st_) * st_ + k
+        n_spk = sep.pred_linear.weight.shape[0]
+
+        def group(m, r, d, e, b0, b1, outs):
             B = b1 - b0
             enc, L = self.encode(m[b0:b1])
             if e is None:
@@ -751,10 +761,11 @@ class Engine(RaggedMixin):
             _, _, eps = self._norm_params(sep.bottleneck[0])
             mr = self.utt_stats(enc, B, L * N, eps)
             mask = self.masker(enc, mr, B, L, emb, (0,))[0]
-            Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
-            est = torch.empty((B, Tout), device=m.device)
-            self.decode(mask, enc, est, B, L, Tout)
-            return est, self.small_linear(emb, sep.pred_linear, B)
+            self.decode(mask, enc, outs[0], B, L, Tout)
+            self.small_linear(emb, sep.pred_linear, B, out=outs[1])
+
+        def alloc():
+            return (torch.empty((mix.shape[0], Tout), device=mix.device), torch.empty((mix.shape[0], n_spk), device=mix.device))
 
         if embedding is None and self._wants_grad():
             # training step (cfg 5): forward that keeps what the hand-written backward needs, as one autograd node
@@ -768,10 +779,11 @@ class Engine(RaggedMixin):
                 div = self._aux_div(ref_len, B, mix.device)
                 # train-mode BatchNorm statistics run over the whole batch (dprnn_spe.py:20-21): no grouping then
                 return self._graphed('spe', (mix, ref, div), lambda m, r, d: self._run_groups(
-                    B, lambda b0, b1: group(m, r, d, None, b0, b1), couples_batch=self.model.training))
+                    B, lambda b0, b1, outs: group(m, r, d, None, b0, b1, outs), couples_batch=self.model.training,
+                    alloc=alloc))
             embedding = self._check_input(embedding, 'embedding')
             return self._graphed('spe_emb', (mix, embedding), lambda m, e: self._run_groups(
-                B, lambda b0, b1: group(m, None, None, e, b0, b1)))
+                B, lambda b0, b1, outs: group(m, None, None, e, b0, b1, outs), alloc=alloc))
 
     def forward_ira(self, mix, ref, ref_len):
         mix = self._check_input(mix, 'input')
@@ -784,7 +796,11 @@ class Engine(RaggedMixin):
         sep, cfg = self.model.separation, self.model.cfg
         N, E = cfg['input_size'], cfg['embeddings_size']
 
-        def group(m, r, d, b0, b1):
+        k, st_ = cfg['kernel_size'], cfg['stride']
+        Tout = ((mix.shape[1] - k) // st_) * st_ + k
+        n_spk = sep.pred_linear.weight.shape[0]
+
+        def group(m, r, d, b0, b1, outs):
             B = b1 - b0
             div = d[b0:b1]
             enc, L = self.encode(m[b0:b1])
@@ -801,13 +817,14 @@ class Engine(RaggedMixin):
             v = self.small_linear(v0, sep.aux_linear, B, K=E)                                  # W[:, :E] v0 + b
             self.small_linear(v1, sep.aux_linear, B, out=v, accumulate=True, w_off=E, bias=False)   # + W[:, E:] v1
             mask = self.masker(enc, mr, B, L, v, (0,))[0]
-            Tout = (L - 1) * cfg['stride'] + cfg['kernel_size']
-            est = torch.empty((B, Tout), device=m.device)
-            self.decode(mask, enc, est, B, L, Tout)
-            return est, self.small_linear(v, sep.pred_linear, B)
+            self.decode(mask, enc, outs[0], B, L, Tout)
+            self.small_linear(v, sep.pred_linear, B, out=outs[1])
+
+        def alloc():
+            return (torch.empty((mix.shape[0], Tout), device=mix.device), torch.empty((mix.shape[0], n_spk), device=mix.device))
 
         with torch.no_grad():
             B = mix.shape[0]
             div_all = self._aux_div(ref_len, B, mix.device)
             return self._graphed('ira', (mix, ref, div_all), lambda m, r, d: self._run_groups(
-                B, lambda b0, b1: group(m, r, d, b0, b1), couples_batch=self.model.training))
+                B, lambda b0, b1, outs: group(m, r, d, b0, b1, outs), couples_batch=self.model.training, alloc=alloc))
