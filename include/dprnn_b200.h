@@ -218,6 +218,17 @@ int dprnn_linear_h16out_stats(const void* A, const void* W, const float* bias, v
                               void* stats_partial, long rows_per_utt, float eps, float* mean_rstd, int h16,
                               void* stream);
 
+/* Linear + norm + residual of a half-block (dprnn.py:86-92 / 96-99) as ONE launch that keeps the Linear output in L2
+ * (csrc/linear_normres.cu): x_h16[M,128] (16-bit, in place) += norm_u(h[M,K] @ W[128,K]^T + bias), statistics per utterance
+ * of rows_per_utt (>= 128) rows.  y_scratch [M,128] 16-bit and stats_partial (dprnn_gemm_tc_stats_bytes(M) bytes) are
+ * scratch, mean_rstd [M / rows_per_utt, 2] an output, workspace dprnn_linear_normres_workspace_bytes(n_utt) bytes (zeroed
+ * by the call).  discard_y != 0: y's cache lines are discarded from L2 after their single use instead of being written
+ * back.  Bit for bit the results of dprnn_linear_h16out_stats followed by dprnn_norm_residual_h16res. */
+size_t dprnn_linear_normres_workspace_bytes(int n_utt);
+int dprnn_linear_normres_h16(const void* h, const void* W, const float* bias, void* y_scratch, void* x_h16,
+                             const float* gamma, const float* beta, int M, int K, void* stats_partial, long rows_per_utt,
+                             float eps, float* mean_rstd, void* workspace, int discard_y, int h16, void* stream);
+
 /* The tail of a DPRNN half-block, dprnn.py:86-92 / 96-99, as ONE persistent tcgen05 kernel (bf16 mode):
  *   y = h[M,K] (bf16) @ W[128,K]^T (bf16) + bias;  x[M,128] (fp32, in place) += (y - mean_u) * rstd_u * gamma + beta,
  * mean_u / rstd_u (biased variance, eps) over all rows x 128 columns of utterance u = rows [row_off[u], row_off[u+1])
@@ -244,6 +255,8 @@ int dprnn_linear_norm_residual_bf16(const void* h, const void* W, const float* b
  * meaning that x, w_packed and hout are fp16 instead of bf16 (inference only). */
 #define DPRNN_LSTM_FAST_ACT 1
 #define DPRNN_LSTM_FP16 2
+#define DPRNN_LSTM_HALF_TILES 4     /* *_pp: force 128-sequence pair tiles (default: chosen when they fit one wave) */
+#define DPRNN_LSTM_FULL_TILES 8     /* *_pp: force 256-sequence pair tiles */
 int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S,
                           int K, int inter, int hidden, int ndir, int fast_act, void* stream);
 
@@ -476,6 +489,13 @@ int dprnn_gemm_atb_tc_supported(int N1, int N2, long lda, long ldb);
 size_t dprnn_gemm_atb_tc_workspace_bytes(int N1, int N2);
 int dprnn_gemm_atb_tc(const float* A, long lda, const float* B, long ldb, float* C, long ldc, long M, int N1, int N2,
                       int accumulate, void* workspace, void* stream);
+/* dprnn_gemm_atb_tc for N2 = 128 with the column sums of A in the same pass: C[N1,128] (+)= A^T B, colsum[N1] (+)= sum_m
+ * A[m,:] (dW_ih = dgates^T x with db = sum dgates): a 32-column group of ones extends B in shared memory, so the bias
+ * gradient costs no pass of its own over A.  workspace: dprnn_gemm_atb_tc_colsum_workspace_bytes(N1) bytes. */
+int dprnn_gemm_atb_tc_colsum_supported(int N1, int N2, long lda, long ldb);
+size_t dprnn_gemm_atb_tc_colsum_workspace_bytes(int N1);
+int dprnn_gemm_atb_tc_colsum(const float* A, long lda, const float* B, long ldb, float* C, long ldc, float* colsum, long M,
+                             int N1, int N2, int accumulate, int accumulate_colsum, void* workspace, void* stream);
 /* out[n] (+)= sum_m X[m,n] (* Y[m,n] if Y): bias gradients, BatchNorm reductions. */
 size_t dprnn_col_sum_workspace_bytes(int N);
 int dprnn_col_sum(const float* X, long ldx, const float* Y, long ldy, long M, int N, float* out, int accumulate,

@@ -185,3 +185,32 @@ def test_lstm_tensor_core_train_forward_saves_what_bptt_needs(inter):
         assert float((hb.float() - h1[:rows]).abs().max()) < 1e-2          # the bf16 copy of the same h
         for t_ in (g1, c1, h1):
             assert float((t_[rows:] - 7.0).abs().max()) == 0.0             # nothing written past the real rows
+
+
+@pytest.mark.parametrize('M,N1,lda', [(48500 * 4, 512, 1024), (20001, 128, 128), (776000, 512, 1024), (4100, 256, 256)])
+def test_gemm_atb_tc_colsum(M, N1, lda):
+    """dW = A^T B with the column sums of A (the bias gradient) from the SAME pass: a 32-column group of ones extends B in
+    shared memory.  TF32 operands (truncated) against the fp64 product; strided A (one direction of a [rows, ndir*4H]
+    d-gates tensor); accumulate into C, overwrite the column sums; deterministic."""
+    L = P.lib()
+    g = torch.Generator().manual_seed(M % 977)
+    Afull = torch.randn(M, lda, generator=g)
+    B = torch.randn(M, 128, generator=g)
+    A = Afull[:, lda - N1:]                                      # the last N1 columns: a strided view
+    tr = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    want = tr(A).t() @ tr(B)
+    want_cs = tr(A).sum(0)
+    Ad, Bd = Afull.to(DEV), B.to(DEV)
+    aptr = Ad.data_ptr() + 4 * (lda - N1)
+    ws = torch.empty(L.query('dprnn_gemm_atb_tc_colsum_workspace_bytes', N1), device=DEV, dtype=torch.uint8)
+    outs = []
+    for _ in range(2):
+        C = torch.full((N1, 128), 3.0, device=DEV)
+        cs = torch.full((N1,), 7.0, device=DEV)
+        L.call('dprnn_gemm_atb_tc_colsum', aptr, lda, Bd, 128, C, 128, cs, M, N1, 128, 1, 0, ws, st())
+        torch.cuda.synchronize()
+        outs.append((C.cpu(), cs.cpu()))
+    C, cs = outs[0]
+    assert rel(C - 3.0, want) < 2e-5
+    assert float((cs.double() - want_cs).abs().max() / want_cs.abs().max()) < 2e-5
+    assert torch.equal(outs[1][0], C) and torch.equal(outs[1][1], cs)

@@ -459,3 +459,34 @@ def test_fp16_storage_saturates_instead_of_overflowing():
         if h16:
             want = torch.where(torch.isinf(want), torch.sign(want) * 65504.0, want)
         assert torch.equal(out, want), (h16, out[:8], want[:8])
+
+
+@pytest.mark.parametrize('B,R,K', [(3, 1337, 256), (2, 48500, 256), (5, 700, 128), (64, 300, 256)])
+@pytest.mark.parametrize('fmt', ['bf16', 'fp16'])
+@pytest.mark.parametrize('discard', [0, 1])
+def test_linear_normres_one_launch_is_bit_identical(B, R, K, fmt, discard):
+    """Linear + norm + residual as ONE launch whose Linear output only lives in L2 (linear_normres.cu) == the Linear kernel
+    followed by the norm kernel, bit for bit (statistics included); tiles straddle utterances, many / few utterances."""
+    L = P.lib()
+    M, N = B * R, 128
+    dtype = torch.float16 if fmt == 'fp16' else torch.bfloat16
+    h16 = 1 if fmt == 'fp16' else 0
+    A = (rnd(M, K, seed=M % 1000) + 0.2).to(dtype).to(DEV)
+    W = (rnd(N, K, seed=5) / K ** 0.5).to(dtype).to(DEV)
+    bias, gamma, beta = rnd(N, seed=3).to(DEV), (1 + 0.1 * rnd(N, seed=4)).to(DEV), (0.1 * rnd(N, seed=6)).to(DEV)
+    x0 = rnd(M, N, seed=7).to(dtype).to(DEV)
+    part = torch.empty(L.query('dprnn_gemm_tc_stats_bytes', M), device=DEV, dtype=torch.uint8)
+    y = torch.empty((M, N), device=DEV, dtype=dtype)
+    mr = torch.empty(B, 2, device=DEV)
+    L.call('dprnn_linear_h16out_stats', A, W, bias, y, M, K, part, R, 1e-5, mr, h16, stream())
+    want = x0.clone()
+    L.call('dprnn_norm_residual_h16res', y, want, None, mr, gamma, beta, B, R, N, h16, stream())
+    ws = torch.empty(L.query('dprnn_linear_normres_workspace_bytes', B), device=DEV, dtype=torch.uint8)
+    for _ in range(2):
+        got = x0.clone()
+        y2 = torch.full((M, N), float('nan'), device=DEV, dtype=dtype)
+        mr2 = torch.full((B, 2), float('nan'), device=DEV)
+        L.call('dprnn_linear_normres_h16', A, W, bias, y2, got, gamma, beta, M, K, part, R, 1e-5, mr2, ws, discard, h16, stream())
+        torch.cuda.synchronize()
+        assert torch.equal(mr2, mr)
+        assert torch.equal(got, want)

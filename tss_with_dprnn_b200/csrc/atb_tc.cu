@@ -134,6 +134,134 @@ __global__ void atb_tc_reduce_kernel(const float* __restrict__ partial, int spli
     *dst = accumulate ? *dst + s : s;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// The same contraction with the COLUMN SUMS of A for free:  C[N1,128] (+)= A[M,N1]^T B[M,128],  colsum[N1] (+)= sum_m A[m,:]
+// (dW_ih = dgates^T x together with db = sum dgates, backward of src/models/dprnn.py:23-28).  Here a 128-column tile of A
+// takes the MMA's M role and B the N role, extended by one 32-column group of ONES that lives in shared memory (written
+// once per stage slot, never touched by TMA): D[a-column, 128 + 0] = sum_m A[m, a-column] * 1.  The bias gradient then costs
+// no pass of its own over the 3.2 GB d-gates tensor (it was a separate 0.6 ms reduction per half-block).
+// grid = (N1 / 128 tiles, row splits); partial[split][tile][160][128].
+constexpr int AB_YG = 5;         // B's four 32-column groups + the ones group
+
+__global__ void __launch_bounds__(192) atb_tc_colsum_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                            const __grid_constant__ CUtensorMap tmY, long M,
+                                                            long rows_per_split, int tiles, float* __restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[AB_NST], bar_empty[AB_NST], bar_done;
+    __shared__ uint32_t tmem_base_s;
+    constexpr uint32_t X_BYTES = 4 * AB_GROUP, Y_BYTES = AB_YG * AB_GROUP, STAGE = X_BYTES + Y_BYTES, Y_TMA = 4 * AB_GROUP;
+    constexpr int NY = 32 * AB_YG;                     // 160 accumulator columns
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const long r0 = (long)split * rows_per_split;
+    const long r1 = r0 + rows_per_split < M ? r0 + rows_per_split : M;
+    const int num_kb = r1 > r0 ? (int)((r1 - r0 + AB_KB - 1) / AB_KB) : 0;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmX);
+        prefetch_tmap(&tmY);
+        for (int s = 0; s < AB_NST; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_done, 1);
+        fence_barrier_init();
+    }
+    // the ones group of every stage slot (rows past M count too: TMA zero-fills A's out-of-range rows, 0 * 1 = 0)
+    for (int i = threadIdx.x; i < AB_NST * (int)(AB_GROUP / 4); i += blockDim.x) {
+        const int s = i / (int)(AB_GROUP / 4), j = i % (int)(AB_GROUP / 4);
+        reinterpret_cast<float*>(smem + s * STAGE + X_BYTES + Y_TMA)[j] = 1.0f;
+    }
+    fence_async_smem();
+    if (warp == 1) tmem_alloc<1>(&tmem_base_s, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % AB_NST;
+                mbar_wait(&bar_empty[s], ((kb / AB_NST) & 1) ^ 1);
+                mbar_expect_tx(&bar_full[s], X_BYTES + Y_TMA);
+                const int row = (int)(r0 + (long)kb * AB_KB);
+                tma_load_3d(smem + s * STAGE, &tmX, &bar_full[s], 0, row, tile * 4);
+                tma_load_3d(smem + s * STAGE + X_BYTES, &tmY, &bar_full[s], 0, row, 0);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc = umma_idesc_tf32_mn(128, NY);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % AB_NST;
+                mbar_wait(&bar_full[s], (kb / AB_NST) & 1);
+                tc_fence_after();
+                const uint32_t sx = smem_u32(smem + s * STAGE), sy = sx + X_BYTES;
+#pragma unroll
+                for (int kk = 0; kk < AB_KB / 8; ++kk) {
+                    const uint32_t acc = (kb | kk) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem), "l"(umma_desc_sw128_mn(sx + kk * 1024)), "l"(umma_desc_sw128_mn(sy + kk * 1024)),
+                          "r"(idesc), "r"(acc) : "memory");
+                }
+                umma_commit(&bar_empty[s]);
+            }
+            umma_commit(&bar_done);
+        }
+        __syncwarp();
+    } else {
+        // epilogue warps 2..5 -> TMEM lane quadrant warp % 4; lane = column of the A tile, TMEM column = column of [B | 1]
+        const int q = warp & 3;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+        float* dst = partial + (((long)split * tiles + tile) * NY) * 128 + q * 32 + lane;
+        if (num_kb > 0) {
+            mbar_wait(&bar_done, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < NY; c0 += 32) {
+            float v[32];
+            if (num_kb > 0) {
+                tmem_ld32(taddr + c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if (c0 < 128) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[(long)(c0 + j) * 128] = v[j];
+            } else {
+                dst[(long)128 * 128] = v[0];            // the ones group: 32 identical columns, one is enough
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<1>(tmem, 256);
+}
+
+// C[a, b] (+)= sum over splits, colsum[a] (+)= likewise (fixed order: deterministic)
+__global__ void atb_tc_colsum_reduce_kernel(const float* __restrict__ partial, int splits, int tiles, float* __restrict__ C,
+                                            long ldc, float* __restrict__ colsum, int accumulate, int accumulate_colsum) {
+    constexpr int NY = 32 * AB_YG;
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long per_tile = 129L * 128;                   // 128 columns of B + the column-sum row
+    if (e >= (long)tiles * per_tile) return;
+    const int tile = (int)(e / per_tile), r = (int)(e % per_tile), y = r >> 7, x = r & 127;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(((long)k * tiles + tile) * NY + y) * 128 + x];
+    const long a = (long)tile * 128 + x;
+    if (y < 128) {
+        float* dst = C + a * ldc + y;
+        *dst = accumulate ? *dst + s : s;
+    } else {
+        colsum[a] = accumulate_colsum ? colsum[a] + s : s;
+    }
+}
+
 static void atb_tc_plan(long M, int ycols, int* nyt, int* tiles, int* splits, long* rows_per_split) {
     *nyt = ycols % 256 == 0 ? 256 : 128;
     *tiles = ycols / *nyt;
@@ -189,6 +317,48 @@ extern "C" int dprnn_gemm_atb_tc(const float* A, long lda, const float* B, long 
     const long total = (long)ycols * 128;
     atb_tc_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, splits, ycols, C, ldc,
                                                                         x_is_b ? 0 : 1, accumulate);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+// C[N1,128] (+)= A[M,N1]^T B[M,128] and colsum[N1] (+)= column sums of A, in one pass over A (see atb_tc_colsum_kernel).
+extern "C" int dprnn_gemm_atb_tc_colsum_supported(int N1, int N2, long lda, long ldb) {
+    return N2 == 128 && N1 % 128 == 0 && N1 > 0 && N1 <= 4096 && lda % 4 == 0 && ldb % 4 == 0;
+}
+
+extern "C" size_t dprnn_gemm_atb_tc_colsum_workspace_bytes(int N1) {
+    return (size_t)(148 + N1 / 128) * (size_t)(32 * AB_YG) * 128 * sizeof(float);     // splits * tiles <= 148 (+ rounding)
+}
+
+extern "C" int dprnn_gemm_atb_tc_colsum(const float* A, long lda, const float* B, long ldb, float* C, long ldc, float* colsum,
+                                        long M, int N1, int N2, int accumulate, int accumulate_colsum, void* workspace,
+                                        void* stream) {
+    DPRNN_CHECK_ARG(A && B && C && colsum && workspace && M > 0 && M < (1L << 31));
+    DPRNN_CHECK_ARG(dprnn_gemm_atb_tc_colsum_supported(N1, N2, lda, ldb));
+    DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)B) % 16 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tiles = N1 / 128;
+    long sp = 148 / tiles;
+    const long max_sp = (M + 4 * AB_KB - 1) / (4 * AB_KB);
+    if (sp > max_sp) sp = max_sp;
+    if (sp < 1) sp = 1;
+    long rps = (M + sp - 1) / sp;
+    rps = (rps + AB_KB - 1) / AB_KB * AB_KB;
+    const int splits = (int)((M + rps - 1) / rps);
+    CUtensorMap tmX, tmY;
+    const uint64_t dX[3] = {32, (uint64_t)M, (uint64_t)(N1 / 32)}, sX[3] = {4, (uint64_t)lda * 4, 128};
+    const uint32_t bX[3] = {32, AB_KB, 4};
+    const uint64_t dY[3] = {32, (uint64_t)M, 4}, sY[3] = {4, (uint64_t)ldb * 4, 128};
+    const uint32_t bY[3] = {32, AB_KB, 4};
+    if (make_tmap(&tmX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, A, dX, sX, bX, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    if (make_tmap(&tmY, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, B, dY, sY, bY, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B)) return 1;
+    const size_t smem = (size_t)AB_NST * (4 + AB_YG) * AB_GROUP + 1024;
+    DPRNN_CUDA(cudaFuncSetAttribute(atb_tc_colsum_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    atb_tc_colsum_kernel<<<dim3(tiles, splits), 192, smem, st>>>(tmX, tmY, M, rps, tiles, (float*)workspace);
+    DPRNN_CHECK_LAUNCH();
+    const long total = (long)tiles * 129 * 128;
+    atb_tc_colsum_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, splits, tiles, C, ldc,
+                                                                               colsum, accumulate, accumulate_colsum);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

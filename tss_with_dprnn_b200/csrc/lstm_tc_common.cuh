@@ -27,6 +27,7 @@ struct LstmTcParams {
     float* hf;             // [rows, ndir*H]  h in fp32 (operand of the weight-gradient contractions)
     int K, S;              // chunk length / chunks per utterance (linear row of (sequence, t))
     long seq_limit;        // number of real sequences along the sequence coordinate (tiles are padded to 256)
+    int half_tiles;        // lstm_tc_pp_kernel: 128-sequence pair tiles = half-job A only (small batches: twice the pairs busy)
     // fused input norm (lstm_tc_pp_kernel<kFuse>): the layer's input is x_in + norm(y) of the PREVIOUS half-block's tail,
     // applied to every x tile in shared memory before the tensor core reads it; direction 0 also writes it to x_out
     const uint4* fy;       // [rows, 128] 16-bit: Linear output of the previous half-block

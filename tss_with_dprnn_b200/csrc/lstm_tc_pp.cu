@@ -13,6 +13,11 @@
 // alternates A(t), B(t), A(t+1), ...: while it waits for A's h_t, B's MMAs are in flight and B's epilogue keeps the MUFU
 // pipe busy, and vice versa.  Inference; uniform batches and the ragged inter-chunk layer (one pair-job per utterance).
 //
+// half_tiles (small batches): when the layer has so few sequences that 256-sequence tiles would leave more than half of the
+// CTA pairs without a job, the tiles shrink to 128 sequences and every pair runs half-job A only - twice as many SMs work,
+// and a step without a ping-pong partner is shorter than a step with one (a half-job's MMAs and cell update instead of two
+// interleaved): cfg 4 (16 utterances per GPU), cfg 1 (B = 1) and the training forward at B = 16.
+//
 // kFuse (uniform batches, inference): the norm + residual that ends the PREVIOUS half-block (dprnn.py:90-92 / 98-99) is
 // applied here, while the layer's input is loaded, instead of by a pass of its own over the residual stream (2.4 GB and
 // 0.44 ms per half-block at B = 64, 13 % of the step, on a kernel that leaves 70 % of the HBM bandwidth unused).  Each CTA's
@@ -52,7 +57,9 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int dir = job % p.ndir;
     const int jt = job / p.ndir;
     int outer = jt / p.tiles_per_outer;
-    const int seq0 = (jt % p.tiles_per_outer) * 256 + (int)rank * 128;
+    const int nj = p.half_tiles ? 1 : 2;                       // half-jobs this pair runs
+    const int seq0 = (jt % p.tiles_per_outer) * (128 * nj) + (int)rank * (64 * nj);
+    const uint32_t xbytes = TILE / 2 * nj;                     // one K-half of this CTA's rows
     int T = p.T, t_base = 0;
     if (p.jobs) {          // ragged inter-chunk layer: one pair-job per utterance (its chunks start at t_base)
         const int2 jb = p.jobs[jt];
@@ -108,7 +115,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                         continue;
                     }
                     const uint32_t lbar = leader_full0 + s * 8;
-                    if (rank == 0) mbar_expect_tx_addr(smem_u32(&x_full[s]), 2 * TILE);
+                    if (rank == 0) mbar_expect_tx_addr(smem_u32(&x_full[s]), 2 * xbytes);
                     else mbar_arrive_remote(lbar);
                     tma_load_4d_pair(smem + SM_X + s * TILE, &tmX, lbar, half * 64, c1(t, seq0), c2(t, seq0), outer);
                 }
@@ -134,7 +141,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 mbar_wait_cluster(&x_full[s1], ((it + 1) / NXS) & 1);
                 tc_fence_after();
                 const uint32_t x0 = aX + s0 * TILE, x1 = aX + s1 * TILE;
-                for (int j = 0; j < 2; ++j) {
+                for (int j = 0; j < nj; ++j) {
                     if (step == 0) {                              // h_0 = 0: only the input projection
                         mma_kb(j, 0, 0, x0, true);  mma_kb(j, 0, 1, x1, false);
                         mma_kb(j, 1, 0, x0, true);  mma_kb(j, 1, 1, x1, false);
@@ -230,6 +237,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     } else if (warp >= 4) {
         // ================= epilogue: warps 4..7 = half-job A, 8..11 = half-job B =================
         const int e = warp - 4, j = e >> 2, q = e & 3;        // q = TMEM lane quadrant = warp % 4
+        if (j < nj) {
         const int L = q * 32 + lane;                           // TMEM lane: rows 0..63 twice (2x2 layout)
         const int rih = L & 63, ub = L >> 6;                   // row inside the half-job, 32-unit block inside the unit half
         const int row = j * 64 + rih;                          // row inside the CTA's 128-sequence tile
@@ -303,6 +311,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
         }
         if (storer) bulk_wait0();
+        }
     }
     __syncwarp();
 
@@ -351,6 +360,21 @@ static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_p
         if (jobs) {        // ragged: B == 1, S = total chunks of the packed batch, one pair-job per utterance and direction
             DPRNN_CHECK_ARG(B == 1 && K <= 256 && n_jobs > 0);
             njobs = (long)n_jobs * ndir;
+        }
+    }
+    // small batches: 128-sequence tiles (half-job A only) when that still fits the CTA pairs in one wave
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    {
+        const long nseq = inter ? K : (long)B * S;
+        const long tiles128 = (nseq + 127) / 128, jobs128 = (inter ? tiles128 * B : tiles128) * ndir;
+        const bool want = (flags & DPRNN_LSTM_HALF_TILES) || (!(flags & DPRNN_LSTM_FULL_TILES) && jobs128 <= sms / 2);
+        if (want && !jobs && !fy) {
+            p.half_tiles = 1;
+            p.tiles_per_outer = (int)tiles128;
+            njobs = jobs128;
+            (inter ? box[1] : box[2]) = 64;
         }
     }
     p.jobs = jobs;

@@ -47,6 +47,9 @@ class Engine(RaggedMixin):
         # but measured SLOWER (intra 1.82 -> 4.04 ms per layer against a 0.40 ms norm pass saved: the two converter warps sit
         # on schedulers whose issue slots and MUFU pipe the cell updates already fill) - DESIGN.md section 4.2
         self.fuse_norm = os.environ.get('DPRNN_FUSE_NORM', '0') == '1'
+        # tensor-core modes, 16-bit residual stream: Linear + norm + residual of a half-block as ONE launch whose Linear output
+        # only lives in L2 (linear_normres.cu; bit-identical to the two kernels); 2 = also discard y from L2 after its use
+        self.tail_l2 = int(os.environ.get('DPRNN_TAIL_L2', '0'))
         self._row_off = {}
         self._streams = []
         self.use_graphs = True     # eval forwards of a repeated shape are captured into a CUDA graph and replayed
@@ -553,6 +556,18 @@ class Engine(RaggedMixin):
                        float(eps), self._row_offsets(s['B'], R, s['dev']), s['B'], R, s['rows'], hw['ndir'] * s['H'],
                        s['ws'], self._stream())
             return
+        last = bi == len(self.model.separation.dprnn_blocks) - 1 and which == 1
+        if self.tail_l2 and self.residual_bf16 and not last and not self._fuses_norm() and s['S'] * s['K'] >= 128:
+            hw = self.packed()['blocks'][bi][which]
+            blk = self.model.separation.dprnn_blocks[bi]
+            g_, b_, eps = self._norm_params(blk.intra_norm if which == 0 else blk.inter_norm)
+            if 'lnr_ws' not in s:
+                s['lnr_ws'] = torch.empty(lib().query('dprnn_linear_normres_workspace_bytes', s['B']), device=s['dev'],
+                                          dtype=torch.uint8)
+            lib().call('dprnn_linear_normres_h16', s['hb'], hw['lin_bf16'], hw['lin_b'], s['ybuf'], s['xb'], g_, b_, s['rows'],
+                       hw['ndir'] * s['H'], s['part'], s['S'] * s['K'], float(eps), s['mr2'], s['lnr_ws'],
+                       int(self.tail_l2 == 2), self.h16, self._stream())
+            return
         self._half_linear(s, bi, which)
         self._half_norm(s, bi, which)
 
@@ -645,7 +660,7 @@ class Engine(RaggedMixin):
         if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
         key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
-               self.fast_act, self.conv_mode, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self.fuse_norm, self._graph_key())
+               self.fast_act, self.conv_mode, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self.fuse_norm, self.tail_l2, self._graph_key())
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = 'seen'

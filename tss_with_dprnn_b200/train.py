@@ -68,6 +68,15 @@ class _Ops:
         ws = torch.empty(self.L.query('dprnn_gemm_atb_workspace_bytes', M, N1, N2), device=self.dev, dtype=torch.uint8)
         self.L.call('dprnn_gemm_atb', A, lda or N1, B, ldb or N2, out, ldc or N2, M, N1, N2, int(accumulate), ws, _st())
 
+    def atb_colsum(self, A, B, M, N1, N2, out, colsum, lda=None, ldb=None):
+        """out[N1,N2] += A^T B and colsum[N1] = column sums of A in ONE pass over A (tensor-core mode, N2 = 128); returns
+        False when that kernel does not apply (the caller then runs atb + colsum)."""
+        if not (self.tf32 and M >= 4096 and self.L.query('dprnn_gemm_atb_tc_colsum_supported', N1, N2, lda or N1, ldb or N2)):
+            return False
+        ws = torch.empty(self.L.query('dprnn_gemm_atb_tc_colsum_workspace_bytes', N1), device=self.dev, dtype=torch.uint8)
+        self.L.call('dprnn_gemm_atb_tc_colsum', A, lda or N1, B, ldb or N2, out, N2, colsum, M, N1, N2, 1, 0, ws, _st())
+        return True
+
     def colsum(self, X, M, N, out, Y=None, ldx=None, accumulate=True):
         ws = torch.empty(self.L.query('dprnn_col_sum_workspace_bytes', N), device=self.dev, dtype=torch.uint8)
         self.L.call('dprnn_col_sum', X, ldx or N, Y, ldx or N, M, N, out, int(accumulate), ws, _st())
@@ -549,16 +558,26 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
         xs_read = torch.cuda.Event()
 
         def rnn_grads(dgates=dgates, hout=hout, rn=rn, nd=nd, geo=geo, sfx=hv['sfx'], xs_read=xs_read):
+            dbs = []
             for d, sf in enumerate(sfx):                             # the reads of xs first: the chain waits for them
-                ops.atb(dgates.data_ptr() + 4 * d * 4 * H, xs, rows, 4 * H, F, G[f'{rn}.weight_ih_l0{sf}'], lda=nd * 4 * H)
+                # dW_ih = dgates^T x; in tensor-core mode the same pass also yields db = column sums of dgates
+                db = ops.empty(4 * H)
+                if ops.atb_colsum(dgates.data_ptr() + 4 * d * 4 * H, xs, rows, 4 * H, F, G[f'{rn}.weight_ih_l0{sf}'], db,
+                                  lda=nd * 4 * H):
+                    dbs.append(db)
+                else:
+                    ops.atb(dgates.data_ptr() + 4 * d * 4 * H, xs, rows, 4 * H, F, G[f'{rn}.weight_ih_l0{sf}'], lda=nd * 4 * H)
+                    dbs.append(None)
             xs_read.record(torch.cuda.current_stream())
             hprev = ops.empty(rows, nd * H)
             L_.call('dprnn_shift_rows', hout, hprev, *geo, H, nd, _st())
             for d, sf in enumerate(sfx):
                 dgd = dgates.data_ptr() + 4 * d * 4 * H
                 ops.atb(dgd, hprev.data_ptr() + 4 * d * H, rows, 4 * H, H, G[f'{rn}.weight_hh_l0{sf}'], lda=nd * 4 * H, ldb=nd * H)
-                db = ops.empty(4 * H)                                # b_ih and b_hh enter as a sum: one reduction, two adds
-                ops.colsum(dgd, rows, 4 * H, db, ldx=nd * 4 * H, accumulate=False)
+                db = dbs[d]                                          # b_ih and b_hh enter as a sum: one reduction, two adds
+                if db is None:
+                    db = ops.empty(4 * H)
+                    ops.colsum(dgd, rows, 4 * H, db, ldx=nd * 4 * H, accumulate=False)
                 ops.axpy(db, G[f'{rn}.bias_ih_l0{sf}'])
                 ops.axpy(db, G[f'{rn}.bias_hh_l0{sf}'])
         on_side(rnn_grads, dgates, hout)
