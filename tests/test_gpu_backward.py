@@ -211,6 +211,7 @@ def test_gemm_atb_tc_colsum(M, N1, lda):
         torch.cuda.synchronize()
         outs.append((C.cpu(), cs.cpu()))
     C, cs = outs[0]
-    assert rel(C - 3.0, want) < 2e-5
-    assert float((cs.double() - want_cs).abs().max() / want_cs.abs().max()) < 2e-5
+    tol = 2e-5 if M < 300000 else 1e-4           # fp32 accumulation over M rows (a split holds ~M / 37 of them)
+    assert rel(C - 3.0, want) < tol
+    assert float((cs.double() - want_cs).abs().max() / want_cs.abs().max()) < tol
     assert torch.equal(outs[1][0], C) and torch.equal(outs[1][1], cs)

@@ -8,11 +8,11 @@
 //   * warps 0..5 are linear_persist_kernel unchanged (TMA ring for hb with an evict_first hint, W resident, two TMEM
 //     accumulators, swizzled staging + TMA stores of y, per-row {sum, sumsq}); tiles are drawn by ticket in row order, i.e.
 //     utterance by utterance; the storer publishes a tile's rows in a per-utterance counter once its stores have landed;
-//   * warps 6..13 (256 threads) draw pass-1 items by a second ticket, also in utterance order: item (u, 0) waits for the
-//     counter of u to reach its row count, reduces the per-row sums exactly as row_stats_finalize_kernel does (256 threads
-//     strided, fp64, the same tree: results are bit-identical to the two-kernel path and to the ragged path), publishes
-//     mean / rstd and a flag; items (u, c > 0) wait for that flag and apply norm + residual to 128 rows with the arithmetic
-//     of norm_residual_bf16res_kernel (norm_res1).  y is read ~one utterance after it was written - an L2 hit - and, with
+//   * warps 6..13 are 8 independent pass-1 workers drawing items by a second ticket, also in utterance order: item (u, 0)
+//     waits for the counter of u to reach its row count, reduces the per-row sums with the arithmetic of
+//     row_stats_finalize_kernel (one warp playing its 256 threads: results are bit-identical to the two-kernel path and to
+//     the ragged path), publishes mean / rstd and a flag; items (u, c > 0) wait for that flag and apply norm + residual to
+//     128 rows with the arithmetic of norm_residual_bf16res_kernel (norm_res1).  y is read ~one utterance after it was written - an L2 hit - and, with
 //     `discard`, dropped from L2 afterwards (discard.global.L2) so that it is never written back to HBM either.
 // A pass-1 item only ever waits for work with smaller tickets, owned by resident CTAs: no deadlock, whatever else runs.
 // HBM traffic: read hb 1.59 + read xb 0.79 + write xb 0.79 = 3.18 GB (+ 0.79 if y's dirty lines are written back).
@@ -37,6 +37,8 @@ struct LnrArgs {
     unsigned* ticket1;         // pass-1 item ticket            }
     unsigned* rows_done;       // [n_utt] rows of the utterance whose y / sums are in global memory
     unsigned* flag;            // [n_utt] 1 once mean_rstd[u] is published
+    unsigned* parts_done;      // [n_utt] statistics parts finished
+    double* part8;             // [n_utt][16] the 8 warp results of {sum, sumsq}
     float* mean_rstd;          // [n_utt, 2]
     const uint4* y;            // [M, 128] 16-bit (the buffer the TMA stores of pass 0 fill)
     uint4* xb;                 // [M, 128] 16-bit residual stream, updated in place
@@ -69,17 +71,6 @@ __device__ __forceinline__ unsigned lr_ld_acquire(const unsigned* p) {
 __device__ __forceinline__ void lr_st_release(unsigned* p, unsigned v) {
     asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-// block_sum of common.cuh for the 256 norm threads (named barrier 3): the same operation order, hence the same bits
-__device__ __forceinline__ double lr_group_sum(double v, double* scratch, int t) {
-    const int lane = t & 31, wid = t >> 5;
-    v = warp_sum(v);
-    asm volatile("bar.sync 3, 256;" ::: "memory");
-    if (lane == 0) scratch[wid] = v;
-    asm volatile("bar.sync 3, 256;" ::: "memory");
-    double r = (lane < 8) ? scratch[lane] : 0.0;
-    return warp_sum(r);
-}
-
 template <int KB, bool kF16>     // K / 64; 16-bit format of operands, y and the residual stream
 __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                       const __grid_constant__ CUtensorMap tmW,
@@ -94,8 +85,6 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
         tq_empty[LR_TQ];
     __shared__ int tile_q[LR_TQ];
     __shared__ uint32_t tmem_base_s;
-    __shared__ unsigned item_s;
-    __shared__ double red_s[32];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -172,7 +161,10 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
         const int r_in_tile = q * 32 + lane;
         const bool storer = (warp == 2 && lane == 0);
         const uint64_t pol_y = lr_policy_evict_last();     // y is read again one utterance later: keep it in L2 until then
-        int chunk_it = 0, prev_tile = -1;
+        constexpr int LAG = 3;                             // a tile is published once LAG younger tiles have been committed
+        int chunk_it = 0, hist[LAG], nhist = 0;            // the storer's ring of committed, not yet published tiles
+#pragma unroll
+        for (int i = 0; i < LAG; ++i) hist[i] = -1;
         auto publish = [&](int tile) {                  // rows of `tile` -> the counter(s) of the utterance(s) it covers
             const long r0 = (long)tile * 128, r1 = r0 + 128 < a.M ? r0 + 128 : (long)a.M;
             const long u0 = r0 / R, split = (u0 + 1) * R < r1 ? (u0 + 1) * R : r1;
@@ -217,9 +209,16 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
                 }
                 uint8_t* stage = sC + (chunk_it % LR_CST) * LR_BLK;
                 if (storer) {
-                    // <= 1 store group pending: the staging buffer is free, and every group but the newest has LANDED
-                    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(LR_CST - 1) : "memory");
-                    if (c0 == 64 && prev_tile >= 0) publish(prev_tile);     // both groups of the previous tile are complete
+                    // the staging buffer has been READ by the TMA engine (cheap); a tile is published only when its stores
+                    // have LANDED, which is waited for LAG tiles later so that it never stalls the store pipeline
+                    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(LR_CST - 1) : "memory");
+                    if (c0 == 0 && nhist == LAG) {
+                        asm volatile("cp.async.bulk.wait_group %0;" ::"n"(2 * (LAG - 1)) : "memory");   // all but the newest LAG-1 tiles
+                        publish(hist[0]);
+#pragma unroll
+                        for (int i = 0; i + 1 < LAG; ++i) hist[i] = hist[i + 1];
+                        --nhist;
+                    }
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");
 #pragma unroll
@@ -233,84 +232,125 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                 }
             }
+            // (the storer passes a CTA barrier after these stores and fences at GPU scope before it publishes the tile)
             if (row < a.M) a.stats[row] = make_float2(s_sum, s_sq);
-            __threadfence();                               // this tile's sums before the barrier the storer passes next
-            prev_tile = tile;
+            if (storer) hist[nhist++] = tile;
         }
         asm volatile("bar.sync 1, 128;" ::: "memory");     // every epilogue thread's last sums are fenced
         if (storer) {
             asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
-            if (prev_tile >= 0) publish(prev_tile);
+            for (int i = 0; i < nhist; ++i) publish(hist[i]);
         }
     } else {
         // ================= pass 1: statistics of an utterance, then norm + residual on its rows =================
-        const int t = threadIdx.x - 192;                   // 0..255
-        const int c8 = t & 15;                             // 8 channels per thread, fixed: 256 threads x 8 = 16 rows x 128
+        // Every one of the 8 warps is an independent worker with its own tickets: an item costs several dependent round
+        // trips (ticket, flag, statistics, the loads), which only other warps' items can hide - one CTA-wide worker
+        // measured 12 us per 128-row item against the 2.2 us the HBM share of an SM allows.
+        const int c8 = lane & 15;                          // 8 channels per lane, fixed: 32 lanes x 8 = 2 rows x 128
         const unsigned nch = (unsigned)((R + LR_CH - 1) / LR_CH);
-        const unsigned total = (unsigned)a.n_utt * (nch + 1);
+        const unsigned per_utt = nch + 8;                  // 8 statistics parts, then the chunks
+        const unsigned total = (unsigned)a.n_utt * per_utt;
         const uint64_t pol_s = lr_policy_evict_first();    // the residual stream passes through once: do not let it displace y
         float g[8], be[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { g[j] = __ldg(a.gamma + c8 * 8 + j); be[j] = __ldg(a.beta + c8 * 8 + j); }
+        long ready_u = -1;                                 // utterances <= ready_u are known to be published
+        float mean = 0.f, rstd = 0.f;
+        long mr_u = -1;
         for (;;) {
-            if (t == 0) item_s = atomicAdd(a.ticket1, 1u);
-            asm volatile("bar.sync 3, 256;" ::: "memory");
-            const unsigned item = item_s;
-            asm volatile("bar.sync 3, 256;" ::: "memory");     // everyone has read item_s before thread 0 overwrites it
+            unsigned item = 0;
+            if (lane == 0) item = atomicAdd(a.ticket1, 1u);
+            item = __shfl_sync(0xffffffffu, item, 0);
             if (item >= total) break;
-            const unsigned u = item / (nch + 1), c = item % (nch + 1);
-            if (c == 0) {
-                if (t == 0) while (lr_ld_acquire(a.rows_done + u) < (unsigned)R) __nanosleep(200);
-                asm volatile("bar.sync 3, 256;" ::: "memory");
+            const unsigned u = item / per_utt, c = item % per_utt;
+            if (c < 8) {
+                // statistics of utterance u with the arithmetic of row_stats_finalize_kernel (256 threads strided over the rows,
+                // fp64, a tree per warp, then a tree over the 8 warp results): this item plays warp w = c of that block -
+                // 8 items per utterance on 8 different warps, ~10 us each - and the one that finishes last combines the 8
+                // results, so every partial sum and every tree has the same operands in the same order
+                if (lane == 0) while (lr_ld_acquire(a.rows_done + u) < (unsigned)R) __nanosleep(200);
+                __syncwarp();
                 const float2* p = a.stats + (long)u * R;
                 double s = 0.0, qd = 0.0;
-                for (long r = t; r < R; r += 256) {
-                    const float2 v = __ldcg(p + r);            // written by other SMs: L2
-                    s += (double)v.x; qd += (double)v.y;
+                for (long rb = c * 32 + lane; rb < R; rb += 16 * 256) {       // 16 independent L2 loads in flight per lane
+                    float2 v[16];
+#pragma unroll
+                    for (int k = 0; k < 16; ++k) v[k] = rb + k * 256 < R ? __ldcg(p + rb + k * 256) : make_float2(0.f, 0.f);
+#pragma unroll
+                    for (int k = 0; k < 16; ++k)
+                        if (rb + k * 256 < R) { s += (double)v[k].x; qd += (double)v[k].y; }
                 }
-                s = lr_group_sum(s, red_s, t);
-                qd = lr_group_sum(qd, red_s, t);
-                if (t == 0) {
-                    const double cnt = (double)R * LR_N;
-                    const double mean = s / cnt;
-                    double var = qd / cnt - mean * mean;
-                    if (var < 0.0) var = 0.0;
-                    a.mean_rstd[2 * u] = (float)mean;
-                    a.mean_rstd[2 * u + 1] = (float)(1.0 / sqrt(var + a.eps));
+                s = warp_sum(s); qd = warp_sum(qd);
+                unsigned prior = 0;
+                if (lane == 0) {
+                    a.part8[(long)u * 16 + c] = s;
+                    a.part8[(long)u * 16 + 8 + c] = qd;
                     __threadfence();
-                    lr_st_release(a.flag + u, 1u);
+                    prior = atomicAdd(a.parts_done + u, 1u);
+                }
+                prior = __shfl_sync(0xffffffffu, prior, 0);
+                if (prior == 7) {                                              // all 8 warp results are in: the final tree
+                    __threadfence();
+                    double rs = lane < 8 ? __ldcg(a.part8 + (long)u * 16 + lane) : 0.0;
+                    double rq = lane < 8 ? __ldcg(a.part8 + (long)u * 16 + 8 + lane) : 0.0;
+                    rs = warp_sum(rs); rq = warp_sum(rq);
+                    if (lane == 0) {
+                        const double cnt = (double)R * LR_N;
+                        const double m = rs / cnt;
+                        double var = rq / cnt - m * m;
+                        if (var < 0.0) var = 0.0;
+                        a.mean_rstd[2 * u] = (float)m;
+                        a.mean_rstd[2 * u + 1] = (float)(1.0 / sqrt(var + a.eps));
+                        __threadfence();
+                        lr_st_release(a.flag + u, 1u);
+                    }
                 }
                 continue;
             }
-            if (t == 0) while (lr_ld_acquire(a.flag + u) == 0u) __nanosleep(100);
-            asm volatile("bar.sync 3, 256;" ::: "memory");
-            const float mean = __ldcg(a.mean_rstd + 2 * u), rstd = __ldcg(a.mean_rstd + 2 * u + 1);
-            const long r0 = (long)u * R + (long)(c - 1) * LR_CH;
+            if ((long)u > ready_u) {
+                if (lane == 0) while (lr_ld_acquire(a.flag + u) == 0u) __nanosleep(100);
+                __syncwarp();
+                ready_u = u;
+            }
+            if ((long)u != mr_u) { mean = __ldcg(a.mean_rstd + 2 * u); rstd = __ldcg(a.mean_rstd + 2 * u + 1); mr_u = u; }
+            const long r0 = (long)u * R + (long)(c - 8) * LR_CH;
             const long r1 = r0 + LR_CH < (long)(u + 1) * R ? r0 + LR_CH : (long)(u + 1) * R;
-            for (long base = r0 * 16; base < r1 * 16; base += 256) {           // 16 uint4 per row; (base + t) % 16 == c8 always
-                const long idx = base + t;
-                const bool ok = idx < r1 * 16;                                  // uniform per 16-lane row group
-                if (ok) {
-                    uint4 yv;
-                    asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"        // L2 (written by another SM through TMA)
-                                 : "=r"(yv.x), "=r"(yv.y), "=r"(yv.z), "=r"(yv.w) : "l"(a.y + idx));
-                    uint4 xv;
-                    asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
-                                 : "=r"(xv.x), "=r"(xv.y), "=r"(xv.z), "=r"(xv.w) : "l"(a.xb + idx), "l"(pol_s));
-                    const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, xw[4] = {xv.x, xv.y, xv.z, xv.w};
-                    uint32_t ob[4];
+            const long end = r1 * 16;
+            for (long base = r0 * 16; base < end; base += 256) {       // 16 rows = 256 uint4 per pass of the warp: 8 per lane
+                uint4 yv[8], xv[8];
 #pragma unroll
-                    for (int h = 0; h < 4; ++h) {
-                        const float2 yf = unpack_h16x2<kF16>(yw[h]), xf = unpack_h16x2<kF16>(xw[h]);
-                        ob[h] = pack_h16x2<kF16>(norm_res1(xf.x, yf.x, mean, rstd, g[2 * h], be[2 * h]),
-                                                 norm_res1(xf.y, yf.y, mean, rstd, g[2 * h + 1], be[2 * h + 1]));
+                for (int i = 0; i < 8; ++i) {                  // all 16 loads of a lane are in flight before the first use
+                    const long idx = base + i * 32 + lane;     // idx % 16 == c8 always (16 uint4 per row)
+                    if (idx < end) {
+                        asm volatile("ld.global.cg.v4.u32 {%0,%1,%2,%3}, [%4];"        // L2 (written by another SM through TMA)
+                                     : "=r"(yv[i].x), "=r"(yv[i].y), "=r"(yv[i].z), "=r"(yv[i].w) : "l"(a.y + idx));
+                        asm volatile("ld.global.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                                     : "=r"(xv[i].x), "=r"(xv[i].y), "=r"(xv[i].z), "=r"(xv[i].w) : "l"(a.xb + idx), "l"(pol_s));
                     }
-                    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
-                                 ::"l"(a.xb + idx), "r"(ob[0]), "r"(ob[1]), "r"(ob[2]), "r"(ob[3]), "l"(pol_s) : "memory");
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const long idx = base + i * 32 + lane;
+                    if (idx < end) {
+                        const uint32_t yw[4] = {yv[i].x, yv[i].y, yv[i].z, yv[i].w}, xw[4] = {xv[i].x, xv[i].y, xv[i].z, xv[i].w};
+                        uint32_t ob[4];
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float2 yf = unpack_h16x2<kF16>(yw[h]), xf = unpack_h16x2<kF16>(xw[h]);
+                            ob[h] = pack_h16x2<kF16>(norm_res1(xf.x, yf.x, mean, rstd, g[2 * h], be[2 * h]),
+                                                     norm_res1(xf.y, yf.y, mean, rstd, g[2 * h + 1], be[2 * h + 1]));
+                        }
+                        asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;"
+                                     ::"l"(a.xb + idx), "r"(ob[0]), "r"(ob[1]), "r"(ob[2]), "r"(ob[3]), "l"(pol_s) : "memory");
+                    }
                 }
                 if (a.discard) {
-                    __syncwarp();                              // the 8 lanes that share a 128-byte line of y have loaded it
-                    if (ok && (t & 7) == 0) asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.y + idx) : "memory");
+                    __syncwarp();                              // the 8 lanes that share a 128-byte line of y have used it
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const long idx = base + i * 32 + lane;
+                        if (idx < end && (lane & 7) == 0) asm volatile("discard.global.L2 [%0], 128;" ::"l"(a.y + idx) : "memory");
+                    }
                 }
             }
         }
@@ -351,7 +391,9 @@ static int launch_lnr(const void* A, const void* W, void* C, LnrArgs args, cudaS
 
 using namespace dprnn;
 
-extern "C" size_t dprnn_linear_normres_workspace_bytes(int n_utt) { return 256 + (size_t)n_utt * 2 * sizeof(unsigned); }
+extern "C" size_t dprnn_linear_normres_workspace_bytes(int n_utt) {
+    return 256 + (size_t)n_utt * 4 * sizeof(unsigned) + (size_t)n_utt * 16 * sizeof(double);
+}
 
 // xb[M,128] (16-bit, in place) += norm_u(h[M,K] @ W[128,K]^T + bias): Linear + GroupNorm(1,128) / gLN + residual of a
 // half-block as ONE launch (see the header of this file).  y_scratch [M,128] 16-bit and stats_partial
@@ -368,13 +410,14 @@ extern "C" int dprnn_linear_normres_h16(const void* h, const void* W, const floa
     cudaStream_t st = (cudaStream_t)stream;
     const int n_utt = (int)(M / rows_per_utt);
     uint8_t* ws = (uint8_t*)workspace;
-    DPRNN_CUDA(cudaMemsetAsync(ws, 0, dprnn_linear_normres_workspace_bytes(n_utt), st));
+    DPRNN_CUDA(cudaMemsetAsync(ws, 0, 256 + (size_t)n_utt * 4 * sizeof(unsigned), st));
     LnrArgs a{};
     a.bias = bias; a.gamma = gamma; a.beta = beta;
     a.stats = (float2*)stats_partial;
     a.M = M; a.n_utt = n_utt; a.discard = discard_y; a.rows_per_utt = rows_per_utt; a.eps = (double)eps;
     a.ticket = (unsigned*)ws; a.ticket1 = (unsigned*)(ws + 128);
-    a.rows_done = (unsigned*)(ws + 256); a.flag = a.rows_done + n_utt;
+    a.rows_done = (unsigned*)(ws + 256); a.flag = a.rows_done + n_utt; a.parts_done = a.flag + n_utt;
+    a.part8 = (double*)(ws + 256 + (size_t)n_utt * 4 * sizeof(unsigned));
     a.mean_rstd = mean_rstd;
     a.y = (const uint4*)y_scratch; a.xb = (uint4*)x_h16;
     if (h16 == DPRNN_H16_FP16)
