@@ -105,8 +105,16 @@ class Engine(RaggedMixin):
     def h16_dtype(self):
         return torch.float16 if self.precision == 'fp16' else torch.bfloat16
 
-    def _lstm_flags(self) -> int:
-        return int(self.fast_act) | (2 if self.precision == 'fp16' else 0)       # DPRNN_LSTM_FAST_ACT | DPRNN_LSTM_FP16
+    def _lstm_flags(self, s=None, which=0, ndir=2) -> int:
+        """DPRNN_LSTM_FAST_ACT | DPRNN_LSTM_FP16 | tile size.  The launcher's own rule for 128-sequence tiles looks at ONE
+        launch; with utterance groups on concurrent streams the layer of the whole batch is what shares the 74 CTA pairs,
+        so the choice is made here from the batch of the forward (half tiles iff all its 128-sequence jobs fit one wave)."""
+        f = int(self.fast_act) | (2 if self.precision == 'fp16' else 0)
+        if s is not None:
+            B = getattr(self, '_batch_total', None) or s['B']
+            tiles = B * ((s['K'] + 127) // 128) if which else (B * s['S'] + 127) // 128
+            f |= 4 if tiles * ndir <= 74 else 8          # DPRNN_LSTM_HALF_TILES / DPRNN_LSTM_FULL_TILES
+        return f
 
     # ------------------------------------------------------------------ weights
     def invalidate(self):
@@ -535,7 +543,7 @@ class Engine(RaggedMixin):
             # two half-jobs per CTA pair in ping-pong (lstm_tc_pp.cu): bit-identical results, the hand-off of one half-job
             # hidden under the cell update of the other
             lib().call('dprnn_lstm_layer_bf16_pp', s['xb'], hw['tc_w2'], hw['tc_bias'], s['hb'], s['B'], s['S'], s['K'],
-                       which, s['H'], hw['ndir'], self._lstm_flags(), self._stream())
+                       which, s['H'], hw['ndir'], self._lstm_flags(s, which, hw['ndir']), self._stream())
             return
         if self.precision == 'fp16':
             raise NotImplementedError("precision 'fp16' is built for the default LSTM kernel (lstm_pingpong = True)")
@@ -694,6 +702,7 @@ class Engine(RaggedMixin):
         SMs that another group's LSTM kernel leaves idle in its partial second wave."""
         n = 1 if couples_batch else max(1, min(self.n_streams, B))
         outs = alloc()
+        self._batch_total = B
         if n == 1:
             fn(0, B, outs)
             return outs
