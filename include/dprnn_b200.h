@@ -222,8 +222,10 @@ int dprnn_linear_h16out_stats(const void* A, const void* W, const float* bias, v
  * (csrc/linear_normres.cu): x_h16[M,128] (16-bit, in place) += norm_u(h[M,K] @ W[128,K]^T + bias), statistics per utterance
  * of rows_per_utt (>= 128) rows.  y_scratch [M,128] 16-bit and stats_partial (dprnn_gemm_tc_stats_bytes(M) bytes) are
  * scratch, mean_rstd [M / rows_per_utt, 2] an output, workspace dprnn_linear_normres_workspace_bytes(n_utt) bytes (zeroed
- * by the call).  discard_y != 0: y's cache lines are discarded from L2 after their single use instead of being written
- * back.  Bit for bit the results of dprnn_linear_h16out_stats followed by dprnn_norm_residual_h16res. */
+ * by the call).  discard_y is a flag word: bit 0 - y's cache lines are discarded from L2 after their single use instead of
+ * being written back; bits 8.. - lead: the Linear pass never runs more than that many utterances ahead of the norm pass
+ * (0 = unbounded), which is what keeps y inside the 126 MB L2.  Bit for bit the results of dprnn_linear_h16out_stats
+ * followed by dprnn_norm_residual_h16res. */
 size_t dprnn_linear_normres_workspace_bytes(int n_utt);
 int dprnn_linear_normres_h16(const void* h, const void* W, const float* bias, void* y_scratch, void* x_h16,
                              const float* gamma, const float* beta, int M, int K, void* stats_partial, long rows_per_utt,

@@ -463,7 +463,7 @@ def test_fp16_storage_saturates_instead_of_overflowing():
 
 @pytest.mark.parametrize('B,R,K', [(3, 1337, 256), (2, 48500, 256), (5, 700, 128), (64, 300, 256)])
 @pytest.mark.parametrize('fmt', ['bf16', 'fp16'])
-@pytest.mark.parametrize('discard', [0, 1])
+@pytest.mark.parametrize('discard', [0, 1, 1 | (1 << 8), 2 << 8])
 def test_linear_normres_one_launch_is_bit_identical(B, R, K, fmt, discard):
     """Linear + norm + residual as ONE launch whose Linear output only lives in L2 (linear_normres.cu) == the Linear kernel
     followed by the norm kernel, bit for bit (statistics included); tiles straddle utterances, many / few utterances."""

@@ -43,6 +43,8 @@ gb = lambda ms, gbytes: gbytes / ms
 print(f'B={B}: rows {M}; algorithmic HBM bytes: two kernels {4.76 * B / 64:.2f} GB, one launch {3.18 * B / 64:.2f} GB (+{0.79 * B / 64:.2f} if y is written back)')
 lo, med = bench(two)
 print(f'Linear kernel + norm kernel : min {lo:.3f} median {med:.3f} ms')
-for d in (0, 1):
-    lo, med = bench(lambda: L.call('dprnn_linear_normres_h16', hb, W, bias, y, xb, gamma, beta, M, nd * H, part, R, 1e-5, mr, ws, d, 0, st))
-    print(f'one launch, discard_y = {d}   : min {lo:.3f} median {med:.3f} ms')
+for lead in (0, 1, 2, 3, 4, 6):
+    for d in (0, 1):
+        lo, med = bench(lambda: L.call('dprnn_linear_normres_h16', hb, W, bias, y, xb, gamma, beta, M, nd * H, part, R, 1e-5, mr, ws,
+                                       d | (lead << 8), 0, st))
+        print(f'one launch, lead = {lead}, discard_y = {d}   : min {lo:.3f} median {med:.3f} ms', flush=True)

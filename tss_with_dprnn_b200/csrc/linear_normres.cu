@@ -30,7 +30,7 @@ constexpr int LR_THREADS = 192 + 256;
 struct LnrArgs {
     const float *bias, *gamma, *beta;
     float2* stats;             // [M] per-row {sum, sumsq}
-    int M, tiles, n_utt, discard;
+    int M, tiles, n_utt, discard, lead;    // lead > 0: pass 0 never runs more than `lead` utterances ahead of pass 1
     long rows_per_utt;
     double eps;
     unsigned* ticket;          // pass-0 tile ticket           } workspace, zeroed before the launch
@@ -39,6 +39,7 @@ struct LnrArgs {
     unsigned* flag;            // [n_utt] 1 once mean_rstd[u] is published
     unsigned* parts_done;      // [n_utt] statistics parts finished
     double* part8;             // [n_utt][16] the 8 warp results of {sum, sumsq}
+    unsigned* chunks_done;     // [n_utt] pass-1 chunks finished (flow control only)
     float* mean_rstd;          // [n_utt, 2]
     const uint4* y;            // [M, 128] 16-bit (the buffer the TMA stores of pass 0 fill)
     uint4* xb;                 // [M, 128] 16-bit residual stream, updated in place
@@ -102,6 +103,7 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
     tc_fence_after();
     const uint32_t tmem = tmem_base_s;
     const long R = a.rows_per_utt;
+    const unsigned nch_all = (unsigned)((R + LR_CH - 1) / LR_CH);      // pass-1 chunks per utterance
 
     if (warp == 0) {
         if (elect_one()) {
@@ -112,6 +114,20 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
             for (int n = 0;; ++n) {
                 int tile = (int)atomicAdd(a.ticket, 1u);
                 if (tile >= a.tiles) tile = -1;
+                if (tile >= 0 && a.lead > 0) {
+                    // flow control: y of at most lead + 1 utterances is alive at any time, so that it stays in L2 until pass 1
+                    // has used it.  Before waiting, a flush entry makes the epilogue publish the tiles it still holds back
+                    // (their rows may be what pass 1 of the awaited utterance is waiting for).
+                    const long u = ((long)tile * 128) / R - a.lead;
+                    if (u >= 0 && lr_ld_acquire(a.chunks_done + u) < nch_all) {
+                        const int qf = n % LR_TQ;
+                        mbar_wait(&tq_empty[qf], ((n / LR_TQ) & 1) ^ 1);
+                        tile_q[qf] = -2;
+                        mbar_arrive(&tq_full[qf]);
+                        ++n;
+                        while (lr_ld_acquire(a.chunks_done + u) < nch_all) __nanosleep(200);
+                    }
+                }
                 const int qs = n % LR_TQ;
                 mbar_wait(&tq_empty[qs], ((n / LR_TQ) & 1) ^ 1);
                 tile_q[qs] = tile;
@@ -130,15 +146,17 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
         if (elect_one()) {
             constexpr uint32_t idesc = umma_idesc_h16(128, LR_N, kF16);
             mbar_wait(&w_full, 0);
-            int it = 0;
+            int it = 0, m = 0;                                       // m counts real tiles (the accumulators alternate on it)
             for (int n = 0;; ++n) {
                 const int qs = n % LR_TQ;
                 mbar_wait(&tq_full[qs], (n / LR_TQ) & 1);
                 const int tile = tile_q[qs];
                 mbar_arrive(&tq_empty[qs]);
+                if (tile == -2) continue;                            // flush entry: nothing to multiply
                 if (tile < 0) break;
-                const int acc = n & 1;
-                mbar_wait(&acc_empty[acc], ((n >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                const int acc = m & 1;
+                mbar_wait(&acc_empty[acc], ((m >> 1) & 1) ^ 1);      // epilogue has drained this accumulator
+                ++m;
                 tc_fence_after();
                 for (int kb = 0; kb < KB; ++kb, ++it) {
                     const int s = it % LR_AST;
@@ -162,7 +180,7 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
         const bool storer = (warp == 2 && lane == 0);
         const uint64_t pol_y = lr_policy_evict_last();     // y is read again one utterance later: keep it in L2 until then
         constexpr int LAG = 3;                             // a tile is published once LAG younger tiles have been committed
-        int chunk_it = 0, hist[LAG], nhist = 0;            // the storer's ring of committed, not yet published tiles
+        int chunk_it = 0, m = 0, hist[LAG], nhist = 0;     // m: real tiles; the storer's ring of committed, unpublished tiles
 #pragma unroll
         for (int i = 0; i < LAG; ++i) hist[i] = -1;
         auto publish = [&](int tile) {                  // rows of `tile` -> the counter(s) of the utterance(s) it covers
@@ -179,10 +197,20 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
             const int tile = tile_q[qs];
             __syncwarp();
             if (lane == 0) mbar_arrive(&tq_empty[qs]);
+            if (tile == -2) {                               // flush entry: publish every tile still held back
+                asm volatile("bar.sync 1, 128;" ::: "memory");     // every epilogue thread's sums of those tiles are written
+                if (storer) {
+                    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+                    for (int i = 0; i < nhist; ++i) publish(hist[i]);
+                    nhist = 0;
+                }
+                continue;
+            }
             if (tile < 0) break;
-            const int acc = n & 1;
+            const int acc = m & 1;
             const long row = (long)tile * 128 + r_in_tile;
-            mbar_wait(&acc_full[acc], (n >> 1) & 1);
+            mbar_wait(&acc_full[acc], (m >> 1) & 1);
+            ++m;
             tc_fence_after();
             const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + acc * LR_N;
             float s_sum = 0.f, s_sq = 0.f;
@@ -353,6 +381,10 @@ __global__ void __launch_bounds__(LR_THREADS, 1) linear_normres_kernel(const __g
                     }
                 }
             }
+            if (a.lead > 0) {
+                __syncwarp();
+                if (lane == 0) atomicAdd(a.chunks_done + u, 1u);       // flow control only: no data hangs on it
+            }
         }
     }
     tc_fence_before();
@@ -392,7 +424,7 @@ static int launch_lnr(const void* A, const void* W, void* C, LnrArgs args, cudaS
 using namespace dprnn;
 
 extern "C" size_t dprnn_linear_normres_workspace_bytes(int n_utt) {
-    return 256 + (size_t)n_utt * 4 * sizeof(unsigned) + (size_t)n_utt * 16 * sizeof(double);
+    return 256 + (size_t)n_utt * 4 * sizeof(unsigned) + (size_t)n_utt * 16 * sizeof(double);     // chunks_done = 4th counter row
 }
 
 // xb[M,128] (16-bit, in place) += norm_u(h[M,K] @ W[128,K]^T + bias): Linear + GroupNorm(1,128) / gLN + residual of a
@@ -414,9 +446,11 @@ extern "C" int dprnn_linear_normres_h16(const void* h, const void* W, const floa
     LnrArgs a{};
     a.bias = bias; a.gamma = gamma; a.beta = beta;
     a.stats = (float2*)stats_partial;
-    a.M = M; a.n_utt = n_utt; a.discard = discard_y; a.rows_per_utt = rows_per_utt; a.eps = (double)eps;
+    a.M = M; a.n_utt = n_utt; a.discard = discard_y & 1; a.rows_per_utt = rows_per_utt; a.eps = (double)eps;
     a.ticket = (unsigned*)ws; a.ticket1 = (unsigned*)(ws + 128);
     a.rows_done = (unsigned*)(ws + 256); a.flag = a.rows_done + n_utt; a.parts_done = a.flag + n_utt;
+    a.chunks_done = a.parts_done + n_utt;
+    a.lead = discard_y >> 8;                       // bits 8.. of the flag word: utterances pass 0 may run ahead (0 = unbounded)
     a.part8 = (double*)(ws + 256 + (size_t)n_utt * 4 * sizeof(unsigned));
     a.mean_rstd = mean_rstd;
     a.y = (const uint4*)y_scratch; a.xb = (uint4*)x_h16;

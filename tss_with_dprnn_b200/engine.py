@@ -50,6 +50,7 @@ class Engine(RaggedMixin):
         # tensor-core modes, 16-bit residual stream: Linear + norm + residual of a half-block as ONE launch whose Linear output
         # only lives in L2 (linear_normres.cu; bit-identical to the two kernels); 2 = also discard y from L2 after its use
         self.tail_l2 = int(os.environ.get('DPRNN_TAIL_L2', '0'))
+        self.tail_lead = int(os.environ.get('DPRNN_TAIL_LEAD', '2'))    # utterances its Linear pass may run ahead of its norm pass
         self._row_off = {}
         self._streams = []
         self.use_graphs = True     # eval forwards of a repeated shape are captured into a CUDA graph and replayed
@@ -574,7 +575,7 @@ class Engine(RaggedMixin):
                                           dtype=torch.uint8)
             lib().call('dprnn_linear_normres_h16', s['hb'], hw['lin_bf16'], hw['lin_b'], s['ybuf'], s['xb'], g_, b_, s['rows'],
                        hw['ndir'] * s['H'], s['part'], s['S'] * s['K'], float(eps), s['mr2'], s['lnr_ws'],
-                       int(self.tail_l2 == 2), self.h16, self._stream())
+                       int(self.tail_l2 == 2) | (int(self.tail_lead) << 8), self.h16, self._stream())
             return
         self._half_linear(s, bi, which)
         self._half_norm(s, bi, which)
@@ -668,7 +669,7 @@ class Engine(RaggedMixin):
         if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
         key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
-               self.fast_act, self.conv_mode, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self.fuse_norm, self.tail_l2, self._graph_key())
+               self.fast_act, self.conv_mode, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self.fuse_norm, self.tail_l2, self.tail_lead, self._graph_key())
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = 'seen'
