@@ -90,11 +90,14 @@ class ClockSampler:
 # ----------------------------------------------------------------------------------------------------------
 # workloads
 # ----------------------------------------------------------------------------------------------------------
+NCU_FULL_CAPTURE = 'r2_top_ncu_full.txt'
+
+
 def ncu_traffic_per_launch(kernel_substr):
     """dram__bytes_read.sum + dram__bytes_write.sum per launch of a kernel, from the committed `ncu --set full` capture
-    (profiles/r1_top3_ncu_full.txt; B = 64 cfg-2 shape) - None if the file or the kernel is missing."""
+    (profiles/r2_top_ncu_full.txt; B = 64 cfg-2 shape, fp16 mode) - None if the file or the kernel is missing."""
     try:
-        text = open(os.path.join(ROOT, 'profiles', 'r1_top3_ncu_full.txt')).read()
+        text = open(os.path.join(ROOT, 'profiles', NCU_FULL_CAPTURE)).read()
     except OSError:
         return None
     unit = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
@@ -706,9 +709,10 @@ def run_ours(args):
         achieved = flop_per_launch * n_launch / (ms_lstm * 1e-3) / 1e12
         roofline = {'kernel': '+'.join(lstm_names), 'bound': 'tensor', 'achieved': achieved, 'peak': peak_tf,
                     'unit': 'TFLOP/s', 'frac': achieved / peak_tf,
-                    'traffic': (ncu_traffic_per_launch('lstm_tc_') if args.workload == 'cfg2' and args.batch == 64
-                                and tcmode else None),
-                    'traffic_note': 'DRAM read+write bytes per launch, ncu --set full (profiles/r1_top3_ncu_full.txt); '
+                    'traffic': (ncu_traffic_per_launch('lstm_tc_sliced' if 'dprnn_lstm_layer_bf16_sliced' in lstm_names
+                                                       else 'lstm_tc_pp')
+                                if args.workload == 'cfg2' and args.batch == 64 and tcmode else None),
+                    'traffic_note': f'DRAM read+write bytes per launch, ncu --set full (profiles/{NCU_FULL_CAPTURE}); '
                                     'algorithmic: read xb 2 x 0.79 GB + write hb 1.59 GB = 3.18 GB',
                     'peak_source': 'MEASURED_PEAKS.json bf16_tflops_sustained' if peaks else 'fallback 1400 (B200_PROFILING.md)',
                     'launch_ms_avg': ms_lstm / n_launch,

@@ -53,6 +53,10 @@ int dprnn_norm_affine(const float* mean_rstd, const float* gamma, const float* b
  * the TMA-fed input of the next tensor-core LSTM layer. */
 int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const float* gamma, const float* beta,
                         int B, long rows_per_utt, int C, void* x_bf16, void* stream);
+/* Out of place: x_out = x + norm(y), x untouched (the training backward walks the reversible residual stream back with
+ * negated gamma / beta while a side stream still reads the layer's x_out: no wait between the two). */
+int dprnn_norm_residual_to(const float* y, const float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                           int B, long rows_per_utt, int C, float* x_out, void* x_bf16, void* stream);
 
 /* 16-bit storage / tensor-core operand formats (argument `h16` below).  bf16: fp32's range, 8 significand bits - the
  * 'bf16' mode.  fp16: 11 significand bits - the 'fp16' mode, which keeps the estimated sources within north_star's
@@ -196,6 +200,29 @@ int dprnn_gemm_persist(const void* A, int a_kind, const void* W, const float* bi
                        const int* bias_row_utt, const float* post_scale, const float* post_shift, const float* prelu_a,
                        float* C, long ldc, int M, int N, int K, int epilogue, void* workspace, void* stream);
 
+/* Both weight gradients and the bias gradient of one LSTM direction from ONE pass over its d gates (backward of
+ * src/models/dprnn.py:23-28):  C1[N1,128] (+)= A^T B1,  C2[N1,128] (+)= A^T shift_t(B2),  colsum[N1] (+)= column sums of A.
+ * A [rows, lda] (pointer at the direction's first column, N1 % 128 == 0 columns used), B1 [rows, ldb1] and B2 [rows, ldb2]
+ * (128 columns each); rows are the chunk positions of a [B, S, K] batch, row = (b*S + s)*K + k.  inter = 0: time runs
+ * along k (intra-chunk layer), 1: along s.  shift in {-1, 0, +1}: B2 is read at time t + shift and is zero outside the
+ * sequence (h_{t-1} for the forward direction, h_{t+1} for the reverse one: no shifted copy of h).  shift = 0 with
+ * B1 | B2 = the two halves of h gives the Linear's dW = dy^T h and db.  lda, ldb1, ldb2 in floats, multiples of 32.
+ * TF32 operands, fp32 accumulation, fixed reduction order.  workspace: dprnn_gemm_atb_dual_workspace_bytes(N1). */
+int dprnn_gemm_atb_dual_supported(int N1, long lda, long ldb1, long ldb2);
+size_t dprnn_gemm_atb_dual_workspace_bytes(int N1);
+int dprnn_gemm_atb_dual(const float* A, long lda, int N1, const float* B1, long ldb1, const float* B2, long ldb2, int B,
+                        int S, int K, int inter, int shift, float* C1, long ldc1, float* C2, long ldc2, float* colsum,
+                        int accumulate, int accumulate_colsum, void* workspace, void* stream);
+
+/* Deep-K contraction of the training step's backward (d x = d gates @ W_ih: src/models/dprnn.py:51-70 differentiated):
+ * C[M,128] (+)= A[M,K] @ W[128,K]^T, fp32 operands read as TF32, K % 32 == 0 (any depth: W streams with A, 256-row tiles
+ * share every W block).  accumulate != 0 adds into C through TMA reduce-add (each element of C is touched once:
+ * deterministic).  lda / ldc in floats.  workspace: dprnn_gemm_kdeep_workspace_bytes() bytes (scheduler ticket). */
+size_t dprnn_gemm_kdeep_workspace_bytes(void);
+int dprnn_gemm_kdeep_supported(int N, int K, long lda, long ldc);
+int dprnn_gemm_kdeep(const float* A, long lda, const float* W, float* C, long ldc, int M, int N, int K, int accumulate,
+                     void* workspace, void* stream);
+
 /* 1x1 conv -> BatchNorm1d (eval: per-channel scale/shift from dprnn_batchnorm_affine) -> PReLU in one pass
  * (ResBlock, src/models/dprnn_spe.py:32-34): C[M,N] = prelu(A @ W^T * scale[n] + shift[n]); fp32 (TF32) operands,
  * N in {128,256}. */
@@ -259,6 +286,8 @@ int dprnn_linear_norm_residual_bf16(const void* h, const void* W, const float* b
 #define DPRNN_LSTM_FP16 2
 #define DPRNN_LSTM_HALF_TILES 4     /* *_pp: force 128-sequence pair tiles (default: chosen when they fit one wave) */
 #define DPRNN_LSTM_FULL_TILES 8     /* *_pp: force 256-sequence pair tiles */
+#define DPRNN_LSTM_DIRECT_SAVE 16   /* *_train_pp on 128-sequence tiles: the saved gates / c / h are stored from the registers
+                                     * (as the 256-sequence tiles do) instead of through staging buffers + TMA (A/B knob) */
 int dprnn_lstm_layer_bf16(const void* x, const void* w_packed, const float* bias_perm, void* hout, int B, int S,
                           int K, int inter, int hidden, int ndir, int fast_act, void* stream);
 
@@ -473,7 +502,9 @@ int dprnn_lstm_bptt_f32(const float* dh_out, const float* gates, const float* cs
 /* dprnn_lstm_bptt_f32 with the recurrent contraction d h_{t-1} = d gates_t @ W_hh on the tensor cores (tcgen05, CTA pair,
  * bf16 operands, fp32 accumulation in TMEM; everything element-wise and the d gates output stay fp32).
  * gates_packed: the bf16 layout dprnn_lstm_layer_bf16_train writes.  whhT_bf16: [ndir][H][4H] bf16 = W_hh^T per
- * direction.  fast_act: tanh.approx for tanh(c_t), as the forward kernel. */
+ * direction.  fast_act: bit DPRNN_LSTM_FAST_ACT = tanh.approx for tanh(c_t), as the forward kernel; tiles of 128 sequences
+ * per CTA pair (64 rows per CTA, cta_group::2 M = 128) are chosen when they still fit the SMs in one wave (small
+ * batches), DPRNN_LSTM_HALF_TILES / DPRNN_LSTM_FULL_TILES force that choice. */
 int dprnn_lstm_bptt_tc(const float* dh_out, const void* gates_packed, const float* cstate, const void* whhT_bf16, float* dgates,
                        long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride, long step_stride,
                        int hidden, int ndir, int fast_act, void* stream);

@@ -129,11 +129,18 @@ def test_lstm_train_forward_and_bptt(inter, ndir, big=False):
     dg2 = torch.full((rows + 1, ndir * 4 * H), 7.0, device=DEV)
     whhT = whh.transpose(1, 2).contiguous().to(torch.bfloat16).to(DEV)
     gates_p = pack_gates(gates, ndir)
-    for fast in (0, 1):
+    # flags: tanh.approx (1) | 64 rows per CTA (4) | 128 rows per CTA (8); 0 / 1 leave the tile size to the library
+    got = {}
+    for flags in (0, 1, 4, 5, 8, 9):
+        dg2[:rows].zero_()
         L.call('dprnn_lstm_bptt_tc', dout.float().reshape(rows, -1).contiguous().to(DEV), gates_p, cst, whhT, dg2, *geo, H,
-               ndir, fast, st())
-        assert float((dg2[:rows] - dg).abs().max()) < 2e-2 * float(dg.abs().max())
+               ndir, flags, st())
+        assert float((dg2[:rows] - dg).abs().max()) < 2e-2 * float(dg.abs().max()), flags
         assert float((dg2[rows:] - 7.0).abs().max()) == 0.0
+        got[flags] = dg2[:rows].clone()
+    # both tile sizes run the same arithmetic per row (M = 128 and M = 256 MMAs accumulate the K = 512 in the same order)
+    assert torch.equal(got[4], got[8]) and torch.equal(got[5], got[9])
+    assert torch.equal(got[0], got[4]) or torch.equal(got[0], got[8])
     # dx = dgates @ W_ih ; dW_ih = dgates^T x ; db = colsum(dgates)
     dx = dgc @ wih.double()
     assert rel(dx, x.grad.reshape(rows, H)) < 1e-4
@@ -174,17 +181,27 @@ def test_lstm_tensor_core_train_forward_saves_what_bptt_needs(inter):
     h1, c1 = (torch.full((rows + 1, n), 7.0, device=DEV) for n in (nd * H, nd * H))
     g1p = torch.full((rows + 1, nd * 4 * H), 7.0, device=DEV, dtype=torch.bfloat16)
     wp2, _ = Engine._pack_lstm_tc(rnn, sfx, half_jobs=True)
+    # flag word of the half-job kernel: 1 tanh.approx | 4 / 8 = 128- / 256-sequence tiles | 16 = the 128-sequence tiles store
+    # the saved values from the registers instead of through staging buffers + TMA
+    saved = {}
     for fast, fn, w in ((0, 'dprnn_lstm_layer_bf16_train', wp), (1, 'dprnn_lstm_layer_bf16_train', wp),
-                        (1, 'dprnn_lstm_layer_bf16_train_pp', wp2)):
+                        (1, 'dprnn_lstm_layer_bf16_train_pp', wp2), (1 | 4, 'dprnn_lstm_layer_bf16_train_pp', wp2),
+                        (1 | 4 | 16, 'dprnn_lstm_layer_bf16_train_pp', wp2), (1 | 8, 'dprnn_lstm_layer_bf16_train_pp', wp2),
+                        (4, 'dprnn_lstm_layer_bf16_train_pp', wp2), (4 | 16, 'dprnn_lstm_layer_bf16_train_pp', wp2)):
         g1p.fill_(7.0); c1.fill_(7.0); h1.fill_(7.0)
         L.call(fn, xb, w, bp, hb, g1p, c1, h1, B, S, K, inter, H, nd, fast, st())
         g1 = unpack_gates(g1p, nd)
-        assert float((g1[:rows] - g0).abs().max()) < 3e-2
-        assert float((c1[:rows] - c0).abs().max()) < 5e-2
-        assert float((h1[:rows] - h0).abs().max()) < 3e-2
+        assert float((g1[:rows] - g0).abs().max()) < 3e-2, (fast, fn)
+        assert float((c1[:rows] - c0).abs().max()) < 5e-2, (fast, fn)
+        assert float((h1[:rows] - h0).abs().max()) < 3e-2, (fast, fn)
         assert float((hb.float() - h1[:rows]).abs().max()) < 1e-2          # the bf16 copy of the same h
         for t_ in (g1, c1, h1):
             assert float((t_[rows:] - 7.0).abs().max()) == 0.0             # nothing written past the real rows
+        if fn.endswith('_pp'):
+            saved[fast] = (g1p.clone(), c1.clone(), h1.clone(), hb.clone())
+    # the staged epilogue stores exactly what the direct one stores; tile size does not change a row's arithmetic
+    for a, b_ in ((1 | 4, 1 | 4 | 16), (1 | 4, 1 | 8), (4, 4 | 16)):
+        assert all(torch.equal(x_, y_) for x_, y_ in zip(saved[a], saved[b_])), (a, b_)
 
 
 @pytest.mark.parametrize('M,N1,lda', [(48500 * 4, 512, 1024), (20001, 128, 128), (776000, 512, 1024), (4100, 256, 256)])
@@ -215,3 +232,82 @@ def test_gemm_atb_tc_colsum(M, N1, lda):
     assert rel(C - 3.0, want) < tol
     assert float((cs.double() - want_cs).abs().max() / want_cs.abs().max()) < tol
     assert torch.equal(outs[1][0], C) and torch.equal(outs[1][1], cs)
+
+
+@pytest.mark.parametrize('M,K,lda', [(48500 * 4, 1024, 1024), (1000, 512, 512), (257, 1024, 1536), (776000, 1024, 1024), (300, 32, 32)])
+def test_gemm_kdeep(M, K, lda):
+    """C[M,128] (+)= A[M,K] W[128,K]^T with W streamed next to A (256-row tiles, TMA reduce-add into C): TF32 operands
+    (truncated) against the fp64 product; strided A, a ragged last tile, rows past M untouched, deterministic."""
+    L = P.lib()
+    g = torch.Generator().manual_seed(M % 977 + K)
+    tr = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    Afull = torch.randn(M, lda, generator=g)
+    W = torch.randn(128, K, generator=g) / K ** 0.5
+    C0 = torch.randn(M + 3, 128, generator=g)
+    A = Afull[:, lda - K:]
+    want = tr(A) @ tr(W).t()
+    Ad, Wd = Afull.to(DEV), W.to(DEV)
+    aptr = Ad.data_ptr() + 4 * (lda - K)
+    ws = torch.empty(L.query('dprnn_gemm_kdeep_workspace_bytes'), device=DEV, dtype=torch.uint8)
+    assert L.query('dprnn_gemm_kdeep_supported', 128, K, lda, 128) == 1
+    outs = []
+    for acc in (0, 1, 1):
+        C = C0.to(DEV)
+        L.call('dprnn_gemm_kdeep', aptr, lda, Wd, C, 128, M, 128, K, acc, ws, st())
+        torch.cuda.synchronize()
+        ref = want + (C0[:M].double() if acc else 0.0)
+        err = float((C[:M].cpu().double() - ref).abs().max()) / float(ref.abs().max())
+        assert err < 1e-4, (acc, err)
+        assert torch.equal(C[M:].cpu(), C0[M:])                         # rows past M are not touched
+        outs.append(C.clone())
+    assert torch.equal(outs[1], outs[2])
+    assert L.query('dprnn_gemm_kdeep_supported', 64, K, lda, 128) == 0
+
+
+@pytest.mark.parametrize('B,S,K,inter,N1,shift', [(2, 37, 50, 0, 512, -1), (2, 37, 50, 0, 512, 1), (3, 41, 70, 1, 512, -1),
+                                                  (3, 41, 70, 1, 512, 1), (2, 33, 250, 0, 128, 0), (16, 97, 250, 1, 512, -1)])
+def test_gemm_atb_dual(B, S, K, inter, N1, shift):
+    """dW_ih, dW_hh and db of one LSTM direction from one pass over its d gates: C1 += A^T B1, C2 += A^T shift_t(B2),
+    colsum = sum A, with B2 read one time step earlier / later through the tensor map (zero outside the sequence).  TF32
+    operands (truncated) against the fp64 products; strided operands; accumulate into C, overwrite the sums."""
+    L = P.lib()
+    rows = B * S * K
+    g = torch.Generator().manual_seed(rows % 977 + N1 + shift)
+    tr = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    lda, ldb2 = 2 * N1, 256
+    Afull = torch.randn(rows, lda, generator=g)
+    B1 = torch.randn(rows, 128, generator=g)
+    B2full = torch.randn(rows, ldb2, generator=g)
+    A, B2 = Afull[:, N1:], B2full[:, 128:]
+    # the time shift in the [B, S, K] layout: intra -> along K, inter -> along S
+    h = B2.reshape(B, S, K, 128)
+    hs = torch.zeros_like(h)
+    if shift == 0:
+        hs = h
+    elif inter == 0:
+        if shift < 0: hs[:, :, 1:] = h[:, :, :-1]
+        else: hs[:, :, :-1] = h[:, :, 1:]
+    else:
+        if shift < 0: hs[:, 1:] = h[:, :-1]
+        else: hs[:, :-1] = h[:, 1:]
+    want1 = tr(A).t() @ tr(B1)
+    want2 = tr(A).t() @ tr(hs.reshape(rows, 128))
+    want_cs = tr(A).sum(0)
+    Ad, B1d, B2d = Afull.to(DEV), B1.to(DEV), B2full.to(DEV)
+    assert L.query('dprnn_gemm_atb_dual_supported', N1, lda, 128, ldb2) == 1
+    ws = torch.empty(L.query('dprnn_gemm_atb_dual_workspace_bytes', N1), device=DEV, dtype=torch.uint8)
+    outs = []
+    for _ in range(2):
+        C1 = torch.full((N1, 128), 3.0, device=DEV)
+        C2 = torch.full((N1, 256), -2.0, device=DEV)              # written at columns 128.. with ldc = 256
+        cs = torch.full((N1,), 9.0, device=DEV)
+        L.call('dprnn_gemm_atb_dual', Ad.data_ptr() + 4 * N1, lda, N1, B1d, 128, B2d.data_ptr() + 4 * 128, ldb2, B, S, K, inter,
+               shift, C1, 128, C2.data_ptr() + 4 * 128, 256, cs, 1, 0, ws, st())
+        torch.cuda.synchronize()
+        tol = 1e-4 * float(want1.abs().max())
+        assert float((C1.cpu().double() - 3.0 - want1).abs().max()) < tol
+        assert float((C2[:, 128:].cpu().double() + 2.0 - want2).abs().max()) < tol
+        assert float((C2[:, :128] + 2.0).abs().max()) == 0.0
+        assert float((cs.cpu().double() - want_cs).abs().max()) < 1e-4 * float(want_cs.abs().max()) + 1e-3
+        outs.append((C1.clone(), C2.clone(), cs.clone()))
+    assert all(torch.equal(a, b) for a, b in zip(*outs))

@@ -71,6 +71,8 @@ class _Lib:
 
     def call(self, name: str, *args):
         """Invoke an int-returning entry point; tensors are passed as device pointers, None as NULL."""
+        if name not in self.protos:      # an undeclared symbol would be called with ctypes' default (32-bit int) arguments
+            raise AttributeError(f'{name} is not declared in include/dprnn_b200.h')
         conv = []
         for a in args:
             if isinstance(a, torch.Tensor):
@@ -92,6 +94,8 @@ class _Lib:
             self.launches += 1     # training mode adds the batch-statistics kernel
 
     def query(self, name: str, *args):
+        if name not in self.protos:
+            raise AttributeError(f'{name} is not declared in include/dprnn_b200.h')
         return getattr(self.cdll, name)(*args)
 
 

@@ -262,6 +262,165 @@ __global__ void atb_tc_colsum_reduce_kernel(const float* __restrict__ partial, i
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Both weight gradients of an LSTM direction and its bias gradient from ONE pass over d gates:
+//     C1[N1,128] (+)= A^T B1,   C2[N1,128] (+)= A^T shift_t(B2),   colsum[N1] (+)= sum_rows A
+// with A = d gates of the direction (N1 = 512), B1 = x (dW_ih), B2 = the layer's fp32 output h read ONE TIME STEP EARLIER
+// (dW_hh = sum_t dgates_t^T h_{t-1}; the reverse direction reads one step LATER) - backward of src/models/dprnn.py:23-28.
+// The training step is bound by its aggregate HBM traffic (the weight-gradient passes run on a side stream next to the
+// BPTT chain: taking them out shortens the step from 107 to 81 ms), and d gates is its largest tensor: 3.2 GB per
+// half-block at 16 utterances.  The separate passes read it twice (dW_ih + bias, dW_hh) and needed a shifted COPY of h
+// (dprnn_shift_rows: 0.8 GB read + 0.8 GB written).  Here the rows are addressed as (time, sequence) through 5-D tensor
+// maps {32 columns, d1, d2, d3, column groups} - intra-chunk layer: d1 = time, d2 = sequence; inter-chunk: d1 = position in
+// the chunk, d2 = time, d3 = utterance - and a contraction block is 32 consecutive d1 indices of one (d2, d3).  B2's box is
+// fetched at time coordinate t -/+ 1: the step before the first (after the last) is out of bounds, which TMA fills with
+// zeros - exactly h_{-1} = 0.  The same kernel with shift 0 and B1 | B2 = the two halves of h gives the Linear's
+// dW = dy^T h and db = sum dy in one pass over dy.
+// B operand in shared memory = [B1 (4 groups) | B2 (4 groups) | ones (1 group)]: one N = 256 and one N = 32 MMA per K slice.
+constexpr int AD_YG = 9;
+constexpr int AD_ROWS = 257;     // rows of a partial: 256 columns of [B1 | B2] + the column-sum row
+
+struct AtbDualGeo {
+    int n1chunks, D2;            // 32-index blocks along d1; extent of d2
+    int sh1, sh2;                // B2's coordinate offset along d1 / d2 (the time shift)
+    long total_chunks, chunks_per_split;
+};
+
+__device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, uint64_t* bar, int c0, int c1, int c2, int c3,
+                                            int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(smem_u32(smem)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+
+__global__ void __launch_bounds__(192) atb_dual_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                       const __grid_constant__ CUtensorMap tmB1,
+                                                       const __grid_constant__ CUtensorMap tmB2, const AtbDualGeo g,
+                                                       int tiles, float* __restrict__ partial) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    __shared__ __align__(8) uint64_t bar_full[AB_NST], bar_empty[AB_NST], bar_done;
+    __shared__ uint32_t tmem_base_s;
+    constexpr uint32_t X_BYTES = 4 * AB_GROUP, STAGE = X_BYTES + AD_YG * AB_GROUP, TMA_BYTES = 12 * AB_GROUP;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tile = blockIdx.x, split = blockIdx.y;
+    const long k0 = (long)split * g.chunks_per_split;
+    const long k1 = k0 + g.chunks_per_split < g.total_chunks ? k0 + g.chunks_per_split : g.total_chunks;
+    const int num_kb = k1 > k0 ? (int)(k1 - k0) : 0;
+
+    if (threadIdx.x == 0) {
+        prefetch_tmap(&tmA); prefetch_tmap(&tmB1); prefetch_tmap(&tmB2);
+        for (int s = 0; s < AB_NST; ++s) { mbar_init(&bar_full[s], 1); mbar_init(&bar_empty[s], 1); }
+        mbar_init(&bar_done, 1);
+        fence_barrier_init();
+    }
+    // the ones group of every stage slot (A's out-of-range rows are zero-filled by TMA: 0 * 1 = 0)
+    for (int i = threadIdx.x; i < AB_NST * (int)(AB_GROUP / 4); i += blockDim.x) {
+        const int s = i / (int)(AB_GROUP / 4), j = i % (int)(AB_GROUP / 4);
+        reinterpret_cast<float*>(smem + s * STAGE + TMA_BYTES)[j] = 1.0f;
+    }
+    fence_async_smem();
+    if (warp == 1) tmem_alloc<1>(&tmem_base_s, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmem_base_s;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // chunk -> (d1 block, d2, d3), kept incrementally
+            long rest = k0 / g.n1chunks;
+            int i1 = (int)(k0 % g.n1chunks), i2 = (int)(rest % g.D2), i3 = (int)(rest / g.D2);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % AB_NST;
+                mbar_wait(&bar_empty[s], ((kb / AB_NST) & 1) ^ 1);
+                mbar_expect_tx(&bar_full[s], TMA_BYTES);
+                uint8_t* st = smem + s * STAGE;
+                tma_load_5d(st, &tmA, &bar_full[s], 0, i1 * 32, i2, i3, tile * 4);
+                tma_load_5d(st + X_BYTES, &tmB1, &bar_full[s], 0, i1 * 32, i2, i3, 0);
+                tma_load_5d(st + X_BYTES + 4 * AB_GROUP, &tmB2, &bar_full[s], 0, i1 * 32 + g.sh1, i2 + g.sh2, i3, 0);
+                if (++i1 == g.n1chunks) { i1 = 0; if (++i2 == g.D2) { i2 = 0; ++i3; } }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (elect_one()) {
+            const uint32_t idesc256 = umma_idesc_tf32_mn(128, 256), idesc32 = umma_idesc_tf32_mn(128, 32);
+            for (int kb = 0; kb < num_kb; ++kb) {
+                const int s = kb % AB_NST;
+                mbar_wait(&bar_full[s], (kb / AB_NST) & 1);
+                tc_fence_after();
+                const uint32_t sx = smem_u32(smem + s * STAGE), sy = sx + X_BYTES, so = sy + 8 * AB_GROUP;
+#pragma unroll
+                for (int kk = 0; kk < AB_KB / 8; ++kk) {
+                    const uint32_t acc = (kb | kk) ? 1u : 0u;
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem), "l"(umma_desc_sw128_mn(sx + kk * 1024)), "l"(umma_desc_sw128_mn(sy + kk * 1024)),
+                          "r"(idesc256), "r"(acc) : "memory");
+                    asm volatile(
+                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                        ::"r"(tmem + 256), "l"(umma_desc_sw128_mn(sx + kk * 1024)), "l"(umma_desc_sw128_mn(so + kk * 1024)),
+                          "r"(idesc32), "r"(acc) : "memory");
+                }
+                umma_commit(&bar_empty[s]);
+            }
+            umma_commit(&bar_done);
+        }
+        __syncwarp();
+    } else {
+        // epilogue warps 2..5 -> TMEM lane quadrant warp % 4; lane = column of the A tile, TMEM column = column of [B1 | B2 | 1]
+        const int q = warp & 3;
+        const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16);
+        float* dst = partial + (((long)split * tiles + tile) * AD_ROWS) * 128 + q * 32 + lane;
+        if (num_kb > 0) {
+            mbar_wait(&bar_done, 0);
+            tc_fence_after();
+        }
+#pragma unroll 1
+        for (int c0 = 0; c0 < 288; c0 += 32) {
+            float v[32];
+            if (num_kb > 0) {
+                tmem_ld32(taddr + c0, v);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = 0.f;
+            }
+            if (c0 < 256) {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) dst[(long)(c0 + j) * 128] = v[j];
+            } else {
+                dst[(long)256 * 128] = v[0];            // the ones group: 32 identical columns, one is enough
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc<1>(tmem, 512);
+}
+
+// C1 / C2 / colsum (+)= sum over splits (fixed order: deterministic)
+__global__ void atb_dual_reduce_kernel(const float* __restrict__ partial, int splits, int tiles, float* __restrict__ C1,
+                                       long ldc1, float* __restrict__ C2, long ldc2, float* __restrict__ colsum,
+                                       int accumulate, int accumulate_colsum) {
+    const long e = blockIdx.x * (long)blockDim.x + threadIdx.x;
+    const long per_tile = (long)AD_ROWS * 128;
+    if (e >= (long)tiles * per_tile) return;
+    const int tile = (int)(e / per_tile), r = (int)(e % per_tile), y = r >> 7, x = r & 127;
+    float s = 0.f;
+    for (int k = 0; k < splits; ++k) s += partial[(((long)k * tiles + tile) * AD_ROWS + y) * 128 + x];
+    const long a = (long)tile * 128 + x;
+    if (y < 256) {
+        float* dst = y < 128 ? C1 + a * ldc1 + y : C2 + a * ldc2 + (y - 128);
+        *dst = accumulate ? *dst + s : s;
+    } else {
+        colsum[a] = accumulate_colsum ? colsum[a] + s : s;
+    }
+}
+
 static void atb_tc_plan(long M, int ycols, int* nyt, int* tiles, int* splits, long* rows_per_split) {
     *nyt = ycols % 256 == 0 ? 256 : 128;
     *tiles = ycols / *nyt;
@@ -359,6 +518,59 @@ extern "C" int dprnn_gemm_atb_tc_colsum(const float* A, long lda, const float* B
     const long total = (long)tiles * 129 * 128;
     atb_tc_colsum_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, splits, tiles, C, ldc,
                                                                                colsum, accumulate, accumulate_colsum);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+// One pass over A for C1 (+)= A^T B1, C2 (+)= A^T shift_t(B2), colsum (+)= column sums of A (see atb_dual_kernel).
+// Rows are the chunk positions of a [B, S, K] batch: row = (b*S + s)*K + k.  inter = 0: sequences run along k (the intra-
+// chunk layer, time = k); inter = 1: along s (time = s).  shift in {-1, 0, +1}: B2 is read at time t + shift, zero outside.
+extern "C" int dprnn_gemm_atb_dual_supported(int N1, long lda, long ldb1, long ldb2) {
+    return N1 > 0 && N1 % 128 == 0 && N1 <= 4096 && lda % 32 == 0 && ldb1 % 32 == 0 && ldb2 % 32 == 0 && lda >= N1 &&
+           ldb1 >= 128 && ldb2 >= 128;
+}
+
+extern "C" size_t dprnn_gemm_atb_dual_workspace_bytes(int N1) {
+    return (size_t)(148 + N1 / 128) * (size_t)AD_ROWS * 128 * sizeof(float);      // splits * tiles <= 148 (+ rounding)
+}
+
+extern "C" int dprnn_gemm_atb_dual(const float* A, long lda, int N1, const float* B1, long ldb1, const float* B2, long ldb2,
+                                   int B, int S, int K, int inter, int shift, float* C1, long ldc1, float* C2, long ldc2,
+                                   float* colsum, int accumulate, int accumulate_colsum, void* workspace, void* stream) {
+    DPRNN_CHECK_ARG(A && B1 && B2 && C1 && C2 && colsum && workspace && B > 0 && S > 0 && K > 0);
+    DPRNN_CHECK_ARG(dprnn_gemm_atb_dual_supported(N1, lda, ldb1, ldb2) && shift >= -1 && shift <= 1);
+    DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)B1 | (uintptr_t)B2) % 16 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tiles = N1 / 128;
+    // d1 = k (unit row stride) in both layouts; intra: d2 = (b, s) flattened, time = d1; inter: d2 = s = time, d3 = b
+    const uint64_t D1 = (uint64_t)K, D2 = inter ? (uint64_t)S : (uint64_t)B * S, D3 = inter ? (uint64_t)B : 1;
+    AtbDualGeo g;
+    g.n1chunks = (int)((D1 + 31) / 32);
+    g.D2 = (int)D2;
+    g.sh1 = inter ? 0 : shift;
+    g.sh2 = inter ? shift : 0;
+    g.total_chunks = (long)g.n1chunks * (long)D2 * (long)D3;
+    long sp = 148 / tiles;
+    const long max_sp = (g.total_chunks + 3) / 4;                 // at least 4 stages of rows per split
+    if (sp > max_sp) sp = max_sp;
+    if (sp < 1) sp = 1;
+    g.chunks_per_split = (g.total_chunks + sp - 1) / sp;
+    const int splits = (int)((g.total_chunks + g.chunks_per_split - 1) / g.chunks_per_split);
+    auto make = [&](CUtensorMap* m, const float* base, long ld, int groups) {
+        const uint64_t d[5] = {32, D1, D2, D3, (uint64_t)groups};
+        const uint64_t sb[5] = {4, (uint64_t)ld * 4, (uint64_t)K * ld * 4, (uint64_t)S * K * ld * 4, 128};
+        const uint32_t bx[5] = {32, AB_KB, 1, 1, 4};
+        return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, d, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    };
+    CUtensorMap tmA, tmB1, tmB2;
+    if (make(&tmA, A, lda, N1 / 32) || make(&tmB1, B1, ldb1, 4) || make(&tmB2, B2, ldb2, 4)) return 1;
+    const size_t smem = (size_t)AB_NST * (4 + AD_YG) * AB_GROUP + 1024;
+    DPRNN_CUDA(cudaFuncSetAttribute(atb_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    atb_dual_kernel<<<dim3(tiles, splits), 192, smem, st>>>(tmA, tmB1, tmB2, g, tiles, (float*)workspace);
+    DPRNN_CHECK_LAUNCH();
+    const long total = (long)tiles * AD_ROWS * 128;
+    atb_dual_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, splits, tiles, C1, ldc1,
+                                                                          C2, ldc2, colsum, accumulate, accumulate_colsum);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

@@ -160,21 +160,39 @@ __global__ void __launch_bounds__(256) gn_bwd_reduce_kernel(const float* __restr
     }
 }
 
-__global__ void gn_bwd_finalize_kernel(const double* __restrict__ utt_part, const float* __restrict__ ch_part, int B,
-                                       int nparts, int C, double count, float* __restrict__ s12,
-                                       float* __restrict__ dgamma, float* __restrict__ dbeta) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < B) {
-        double s1 = 0.0, s2 = 0.0;
-        for (int p = 0; p < nparts; ++p) { s1 += utt_part[((long)idx * nparts + p) * 2]; s2 += utt_part[((long)idx * nparts + p) * 2 + 1]; }
-        s12[2 * idx] = (float)(s1 / count);
-        s12[2 * idx + 1] = (float)(s2 / count);
-    }
-    if (idx < C) {
+// Kernel 2: one warp per channel (blocks 0 .. C/4-1) and one warp per utterance (the blocks after them) add the partials
+// in a fixed order - lane l takes every 32nd partial, then a shuffle tree - so the result does not depend on scheduling.
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(128) gn_bwd_finalize_kernel(const double* __restrict__ utt_part,
+                                                              const float* __restrict__ ch_part, int B, int nparts, int C,
+                                                              double count, float* __restrict__ s12,
+                                                              float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cblocks = (C + 3) / 4;
+    if ((int)blockIdx.x < cblocks) {
+        const int c = blockIdx.x * 4 + warp;
+        if (c >= C) return;
         double dg = 0.0, db = 0.0;
-        for (long bp = 0; bp < (long)B * nparts; ++bp) { dg += ch_part[(bp * C + idx) * 2]; db += ch_part[(bp * C + idx) * 2 + 1]; }
-        dgamma[idx] += (float)dg;
-        dbeta[idx] += (float)db;
+        for (long bp = lane; bp < (long)B * nparts; bp += 32) {
+            const float2 v = *reinterpret_cast<const float2*>(ch_part + (bp * C + c) * 2);
+            dg += v.x; db += v.y;
+        }
+        dg = warp_sum_f64(dg); db = warp_sum_f64(db);
+        if (lane == 0) { dgamma[c] += (float)dg; dbeta[c] += (float)db; }
+    } else {
+        const int b = ((int)blockIdx.x - cblocks) * 4 + warp;
+        if (b >= B) return;
+        double s1 = 0.0, s2 = 0.0;
+        for (int p = lane; p < nparts; p += 32) {
+            s1 += utt_part[((long)b * nparts + p) * 2];
+            s2 += utt_part[((long)b * nparts + p) * 2 + 1];
+        }
+        s1 = warp_sum_f64(s1); s2 = warp_sum_f64(s2);
+        if (lane == 0) { s12[2 * b] = (float)(s1 / count); s12[2 * b + 1] = (float)(s2 / count); }
     }
 }
 
@@ -530,9 +548,8 @@ int dprnn_groupnorm_bwd(const float* dz, const float* y, const float* mean_rstd,
     dim3 grid(nparts, B);
     gn_bwd_reduce_kernel<<<grid, 256, 0, st>>>(dz, y, mean_rstd, gamma, rows_per_utt, C, utt_part, ch_part);
     DPRNN_CHECK_LAUNCH();
-    const int n = B > C ? B : C;
-    gn_bwd_finalize_kernel<<<cdiv(n, 128), 128, 0, st>>>(utt_part, ch_part, B, nparts, C, (double)rows_per_utt * C, s12,
-                                                        dgamma, dbeta);
+    gn_bwd_finalize_kernel<<<cdiv(C, 4) + cdiv(B, 4), 128, 0, st>>>(utt_part, ch_part, B, nparts, C,
+                                                                   (double)rows_per_utt * C, s12, dgamma, dbeta);
     DPRNN_CHECK_LAUNCH();
     const long per4 = rows_per_utt * (C / 4);
     gn_bwd_apply_kernel<<<bgrid(per4 * B, 256), 256, 0, st>>>(dz, y, mean_rstd, gamma, s12, dy, per4 * B, per4, C / 4,

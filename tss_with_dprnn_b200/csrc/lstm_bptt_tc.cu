@@ -17,6 +17,13 @@
 //     d gates -> global (fp32) and -> the A tile (bf16, 128B-swizzled K-major); publish -> the MMA warp issues the K-blocks of
 //     that unit-half (the MMAs of half 0 overlap the element-wise work of half 1) | commit -> D[cur]   (TMEM ping-pong)
 // K index = gate*128 + unit, i.e. K-block kb = 2*gate + unit_half: W_hh^T needs no permutation.
+//
+// kRows = 64 (small batches: at 16 utterances per GPU the 256-sequence tiles give 52..64 CTAs for 148 SMs, and the step is
+// bound by the latency of the streamed loads, not by their bandwidth): the pair owns 128 sequences, 64 per CTA, and the
+// MMA is the cta_group::2 M = 128 shape.  Its accumulator has the "2x2" layout - TMEM lanes 0..63 hold units 0..63 of the
+// CTA's 64 rows, lanes 64..127 hold units 64..127 of the SAME rows (64 columns per buffer) - so the lane quadrant a warp
+// may read fixes both its rows and its unit-half: every warp differentiates one unit-half of 8 rows per step instead of
+// both halves, twice as many SMs work, and c_{t-1} of a step is kept in registers as c_t of the next one.
 #include "tc_common.cuh"
 #include "../../include/dprnn_b200.h"
 
@@ -25,7 +32,7 @@ using namespace tc;
 
 namespace bptt {
 constexpr int H = 128, G4 = 512;
-constexpr uint32_t A_TILE = 128 * 128;        // [128 rows x 128 B]
+constexpr uint32_t A_TILE = 128 * 128;        // [128 rows x 128 B] (kRows = 64: the first half of each tile is used)
 constexpr uint32_t W_TILE = 64 * 128;         // [64 rows x 128 B]
 constexpr int NEW = 16;                       // element-wise warps (issue-bound part: more warps hide its latencies)
 constexpr int ITS = 128 / NEW / 2;            // row pairs per warp and unit-half
@@ -77,10 +84,14 @@ __device__ __forceinline__ void bptt_arrive_remote(uint32_t cluster_addr) {
 }
 __device__ __forceinline__ void bptt_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <bool kFastAct>
+template <bool kFastAct, int kRows>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * bptt::NEW, 1)
 lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcParams p) {
     using namespace bptt;
+    static_assert(kRows == 128 || kRows == 64, "rows per CTA");
+    constexpr int NPH = kRows == 128 ? 2 : 1;          // unit-halves a warp differentiates
+    constexpr uint32_t DCOLS = kRows == 128 ? 128 : 64; // TMEM columns of one accumulator buffer
+    constexpr bool kKeepC = kRows == 64;               // c_{t-1} stays in registers for the next step
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
     uint64_t* w_full = bars;
@@ -93,7 +104,7 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
     const uint32_t rank = bptt_cluster_ctarank();
     const int job = blockIdx.x >> 1;
     const int dir = job % p.ndir;
-    const long n0 = (long)(job / p.ndir) * 256 + (long)rank * 128;
+    const long n0 = (long)(job / p.ndir) * (2 * kRows) + (long)rank * kRows;
     const int T = p.T;
 
     if (threadIdx.x == 0) {
@@ -104,7 +115,8 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
         prefetch_tmap(&tmW);
         mbar_init(w_full, 1);
         mbar_init(d_full, 1);
-        mbar_init(&a_ready[0], 2 * NEW); mbar_init(&a_ready[1], 2 * NEW);     // one elected lane per element-wise warp, both CTAs
+        // one elected lane per element-wise warp that writes the unit-half, both CTAs
+        mbar_init(&a_ready[0], 2 * NEW / (3 - NPH)); mbar_init(&a_ready[1], 2 * NEW / (3 - NPH));
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<2>(tmem_slot, 256);
@@ -124,10 +136,10 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
     if (warp == 1) {
         // ================= MMA issuer (leader CTA only) =================
         if (rank == 0 && elect_one()) {
-            constexpr uint32_t idesc = umma_idesc_bf16(256, 128);
+            constexpr uint32_t idesc = umma_idesc_bf16(2 * kRows, 128);
             const uint32_t aW = smem_u32(smem + SM_W), aA = smem_u32(smem + SM_A);
             for (int s = 0; s + 1 < T; ++s) {
-                const uint32_t d = tmem + (uint32_t)(s & 1) * 128;
+                const uint32_t d = tmem + (uint32_t)(s & 1) * DCOLS;
                 for (int half = 0; half < 2; ++half) {
                     mbar_wait_cluster(&a_ready[half], s & 1);
                     tc_fence_after();
@@ -151,6 +163,8 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
         // the rows a warp differentiates are rows whose recurrent d h it can fetch itself, so staging is warp-private
         const int e = warp - 4, q = e & 3, wq = e >> 2;
         const int hw = lane >> 4, l16 = lane & 15;           // coalesced role: half-warp = row, 4 units per lane
+        const int rq = (kRows == 128 ? q : (q & 1)) * 32 + wq * (2 * ITS);    // first of this warp's rows inside the CTA's tile
+        const int ph0 = kRows == 128 ? 0 : (q >> 1);         // first (kRows = 64: only) unit-half of this warp
         const int ldg = p.ndir * G4, ldh = p.ndir * H;
         const uint32_t leader_ready = bptt_map_to_cta(smem_u32(&a_ready[0]), 0);
         float* stgw = stg + e * (2 * ITS) * STG_LD;          // this warp's staging rows
@@ -158,13 +172,14 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
         bool ok[ITS];
 #pragma unroll
         for (int it = 0; it < ITS; ++it) {
-            const long n = n0 + q * 32 + wq * (2 * ITS) + it * 2 + hw;
+            const long n = n0 + rq + it * 2 + hw;
             ok[it] = n < p.nseq;
             base[it] = ok[it] ? (int)((n / p.seq_div) * p.seq_outer + (n % p.seq_div) * p.seq_inner) : 0;
         }
-        float dc[2][ITS][4];
+        float dc[NPH][ITS][4];
+        float4 ckeep[kKeepC ? ITS : 1];                      // kKeepC: c_{t-1} of this step = c_t of the next
 #pragma unroll
-        for (int a = 0; a < 2; ++a)
+        for (int a = 0; a < NPH; ++a)
 #pragma unroll
             for (int b = 0; b < ITS; ++b)
 #pragma unroll
@@ -186,7 +201,7 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                 // chunk = u0 / 8 (8 uint2 each: 2 per gate), 4-unit half (u0 / 4) & 1 inside it
                 const uint2* g = p.gates + ((rowi * p.ndir + dir) * 16 + (u0 >> 3)) * 8 + ((u0 >> 2) & 1);
                 L.gi = __ldg(g); L.gf = __ldg(g + 2); L.gg = __ldg(g + 4); L.go = __ldg(g + 6);
-                L.cv = *reinterpret_cast<const float4*>(p.cstate + rowi * ldh + dir * H + u0);
+                if (!kKeepC || s_ == 0) L.cv = *reinterpret_cast<const float4*>(p.cstate + rowi * ldh + dir * H + u0);
                 if (fs > 0)
                     L.cp = *reinterpret_cast<const float4*>(p.cstate + ((long)base_ + (long)tp * p.step_stride) * ldh + dir * H + u0);
                 L.dho = ld_stream(reinterpret_cast<const float4*>(p.dh_out + rowi * ldh + dir * H + u0));
@@ -204,8 +219,8 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                 if (!ok[it]) continue;
                 const long rowi = (long)base[it] + (long)t_ * p.step_stride;
 #pragma unroll
-                for (int ph_ = 0; ph_ < 2; ++ph_) {
-                    const int u0 = ph_ * 64 + l16 * 4;
+                for (int pi_ = 0; pi_ < NPH; ++pi_) {
+                    const int u0 = (ph0 + pi_) * 64 + l16 * 4;
                     // packed gates: 512 B = 4 lines per (row, direction, unit-half); lanes 0 and 8 of the half-warp fetch two
                     // consecutive lines each (chunks 0-3 / 4-7)
                     const uint2* g = p.gates + ((rowi * p.ndir + dir) * 16 + (u0 >> 3)) * 8;
@@ -218,7 +233,7 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
             }
         };
         Ld cur, nxt;
-        issue(0, 0, ok[0], base[0], cur);
+        issue(0, ph0, ok[0], base[0], cur);
 
         for (int s = 0; s < T; ++s) {
             const int fstep = T - 1 - s;                      // forward step being differentiated
@@ -229,7 +244,8 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                 tc_fence_after();
             }
 #pragma unroll
-            for (int ph = 0; ph < 2; ++ph) {
+            for (int pi = 0; pi < NPH; ++pi) {
+                const int ph = ph0 + pi;
                 if (s > 0) {                                  // recurrent d h of units 64ph..64ph+63: TMEM -> staging
                     __syncwarp();                             // the previous unit-half's reads of the staging rows are done
                     const bool mine = lane >= wq * (2 * ITS) && lane < (wq + 1) * (2 * ITS);
@@ -237,7 +253,7 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
 #pragma unroll
                     for (int cq = 0; cq < 4; ++cq) {
                         float v[16];
-                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((s - 1) & 1) * 128 + ph * 64 + cq * 16, v);
+                        tmem_ld16(tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)((s - 1) & 1) * DCOLS + pi * 64 + cq * 16, v);
                         if (mine) {
 #pragma unroll
                             for (int j = 0; j < 16; j += 4)
@@ -252,9 +268,13 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                 for (int it = 0; it < ITS; ++it) {
                     // next in the order (step, unit-half, row pair)
                     if (it < ITS - 1) issue(s, ph, ok[it + 1], base[it + 1], nxt);
-                    else if (ph == 0) issue(s, 1, ok[0], base[0], nxt);
-                    else issue(s + 1, 0, ok[0], base[0], nxt);
-                    const int row = q * 32 + wq * (2 * ITS) + it * 2 + hw;
+                    else if (pi < NPH - 1) issue(s, 1, ok[0], base[0], nxt);
+                    else issue(s + 1, ph0, ok[0], base[0], nxt);
+                    if constexpr (kKeepC) {
+                        if (s > 0) cur.cv = ckeep[it];
+                        ckeep[it] = cur.cp;
+                    }
+                    const int row = rq + it * 2 + hw;
                     const long rowi = (long)base[it] + (long)t * p.step_stride;
                     float4 dhr = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (s > 0) dhr = *reinterpret_cast<const float4*>(stgw + (it * 2 + hw) * STG_LD + l16 * 4);
@@ -272,12 +292,12 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                     for (int u = 0; u < 4; ++u) {
                         const float dh = da[u];
                         const float tcv = bptt_tanh(ca[u], kFastAct);
-                        const float dct = dc[ph][it][u] + dh * oa[u] * (1.f - tcv * tcv);
+                        const float dct = dc[pi][it][u] + dh * oa[u] * (1.f - tcv * tcv);
                         dpo[u] = dh * tcv * oa[u] * (1.f - oa[u]);
                         dpi[u] = dct * ga[u] * ia[u] * (1.f - ia[u]);
                         dpf[u] = dct * pa[u] * fa[u] * (1.f - fa[u]);
                         dpg[u] = dct * ia[u] * (1.f - ga[u] * ga[u]);
-                        dc[ph][it][u] = dct * fa[u];
+                        dc[pi][it][u] = dct * fa[u];
                     }
                     if (ok[it]) {
                         float* o = p.dgates + rowi * ldg + dir * G4 + u0;
@@ -336,9 +356,18 @@ extern "C" int dprnn_lstm_bptt_tc(const float* dh_out, const void* gates, const 
     const uint32_t bW[2] = {64, 64};
     if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, whhT_bf16, dW, sW, bW)) return 1;
     LstmBpttTcParams p{dh_out, (const uint2*)gates, cstate, dgates, nseq, T, (int)seq_div, seq_outer_stride, seq_inner_stride, step_stride, ndir};
-    const long njobs = (nseq + 255) / 256 * ndir;
+    // small batches: 64 rows per CTA when the 128-sequence pair tiles still fit the CTA pairs in one wave (the rule of the
+    // forward kernel, lstm_tc_pp.cu); DPRNN_LSTM_HALF_TILES / DPRNN_LSTM_FULL_TILES in `fast_act` force the choice
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const long jobs128 = (nseq + 127) / 128 * ndir;
+    const bool half = (fast_act & DPRNN_LSTM_HALF_TILES) || (!(fast_act & DPRNN_LSTM_FULL_TILES) && jobs128 <= sms / 2);
+    const long njobs = half ? jobs128 : (nseq + 255) / 256 * ndir;
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
-    auto kern = fast_act ? lstm_bptt_tc_kernel<true> : lstm_bptt_tc_kernel<false>;
+    const bool fa = fast_act & DPRNN_LSTM_FAST_ACT;
+    auto kern = half ? (fa ? lstm_bptt_tc_kernel<true, 64> : lstm_bptt_tc_kernel<false, 64>)
+                     : (fa ? lstm_bptt_tc_kernel<true, 128> : lstm_bptt_tc_kernel<false, 128>);
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bptt::SM_TOTAL));
     kern<<<(unsigned)(njobs * 2), 128 + 32 * bptt::NEW, bptt::SM_TOTAL, (cudaStream_t)stream>>>(tmW, p);
     DPRNN_CHECK_LAUNCH();

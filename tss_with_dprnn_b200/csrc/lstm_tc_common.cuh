@@ -70,6 +70,7 @@ __device__ __forceinline__ void tma_store_4d(const CUtensorMap* m, const void* s
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 // Remote arrive with the default (.release.cta) semantics, as CUTLASS' ClusterBarrier::arrive does: the data the
@@ -103,10 +104,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
 // The i, f, o rows of the weights and biases are pre-scaled by 1/2 on the host (exact), so sigmoid(x) = 1/2 tanh(x') + 1/2.
 // kGS = distance in TMEM columns between the four gates of a unit (64: one-job kernels; 32: the half-job kernel).
 // kF16: h leaves as fp16 instead of bf16 (the 'fp16' mode: operands with 11 significand bits).
-template <bool kFastAct, bool kTrain, int kGS = 64, bool kF16 = false>
+// kStage (training, 128-sequence tiles): the saved values do not go to global memory from the registers (32 rows x 32 B
+// per store instruction = 32 L1 wavefronts of a quarter line each; the step was bound by exactly that) but into a
+// warp-private staging buffer `stg` laid out as three TMA boxes - gates [32 rows x 64 B] SWIZZLE_64B at 0, c and h
+// [32 rows x 32 B] SWIZZLE_32B at 2048 / 3072 - which the caller stores with three bulk tensor copies.
+template <bool kFastAct, bool kTrain, int kGS = 64, bool kF16 = false, bool kStage = false>
 __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restrict__ bq, float* __restrict__ c,
                                            uint32_t (&packed)[4], uint32_t* __restrict__ gdst = nullptr,
-                                           float* __restrict__ cdst = nullptr, float* __restrict__ hdst = nullptr) {
+                                           float* __restrict__ cdst = nullptr, float* __restrict__ hdst = nullptr,
+                                           uint8_t* __restrict__ stg = nullptr, int lane = 0) {
     uint32_t ri[8], rf[8], rg[8], ro[8];
     tmem_ld8_issue(tcol + 0 * kGS, ri);
     tmem_ld8_issue(tcol + 1 * kGS, rf);
@@ -139,7 +145,24 @@ __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restric
             hv[u] = og * (kFastAct ? tanh_fast(cn) : tanhf(cn));
             if constexpr (kTrain) { sv[0][u] = ig; sv[1][u] = fg; sv[2][u] = gg; sv[3][u] = og; sv[4][u] = cn; }
         }
-        if constexpr (kTrain) {
+        if constexpr (kTrain && kStage) {
+#pragma unroll
+            for (int g = 0; g < 4; ++g) {
+                gk[g][(j >> 1) + 0] = pack_bf16x2(sv[g][0], sv[g][1]);
+                gk[g][(j >> 1) + 1] = pack_bf16x2(sv[g][2], sv[g][3]);
+            }
+            // c / h: 16-byte chunk j/4 of the row's 32 bytes, SWIZZLE_32B (chunk ^= bit 7 of the byte offset = bit 2 of the row)
+            const uint32_t o32 = (uint32_t)lane * 32 + (uint32_t)(((j >> 2) ^ ((lane >> 2) & 1)) << 4);
+            *reinterpret_cast<float4*>(stg + 2048 + o32) = make_float4(sv[4][0], sv[4][1], sv[4][2], sv[4][3]);
+            *reinterpret_cast<float4*>(stg + 3072 + o32) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            if (j == 4) {
+                // gates: chunk g (8 units of gate g) of the row's 64 bytes, SWIZZLE_64B (chunk ^= bits 7..8 = bits 1..2 of the row)
+#pragma unroll
+                for (int g = 0; g < 4; ++g)
+                    *reinterpret_cast<uint4*>(stg + (uint32_t)lane * 64 + (uint32_t)((g ^ ((lane >> 1) & 3)) << 4)) =
+                        make_uint4(gk[g][0], gk[g][1], gk[g][2], gk[g][3]);
+            }
+        } else if constexpr (kTrain) {
             if (gdst) {
                 // the 8 units of the call leave as 64 contiguous bytes of bf16 gates [i8 | f8 | g8 | o8] (two 32-byte
                 // stores) plus one 32-byte store each for c and h (fp32): 4 full-sector stores per thread and call

@@ -30,15 +30,20 @@
 namespace dprnn {
 using namespace tc;
 
-constexpr uint32_t PP_BAR_BYTES = 256;
+constexpr uint32_t PP_BAR_BYTES = 384;
 constexpr uint32_t PP_SM_TOTAL = SM_BAR + PP_BAR_BYTES;
 static_assert(PP_SM_TOTAL <= 232448, "shared memory budget of one SM (227 KiB)");
 constexpr uint32_t HALF_ROWS = 64 * 128;      // byte offset of rows 64..127 inside a [128 x 128 B] tile
 
-template <bool kFastAct, bool kTrain, bool kF16, bool kFuse = false>
+// The three tensor maps of the staged training epilogue (kStage): gates / cell state / fp32 h with the geometry of tmH64.
+struct LstmSaveMaps { CUtensorMap g, c, h; };
+
+template <bool kFastAct, bool kTrain, bool kF16, bool kFuse = false, bool kStage = false>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
-                  const __grid_constant__ CUtensorMap tmH64, const float* __restrict__ bias_perm, const LstmTcParams p) {
+                  const __grid_constant__ CUtensorMap tmH64, const float* __restrict__ bias_perm, const LstmTcParams p,
+                  const __grid_constant__ LstmSaveMaps sm) {
+    static_assert(!kStage || kTrain, "the staged epilogue belongs to the training forward");
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + SM_BAR);
     uint64_t* x_full = bars;                  // [NXS]  (leader's copy is the live one)
@@ -49,6 +54,8 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     uint64_t* h_done = bars + 2 * NXS + 7;    // [2][2]  (leader's copy)
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * NXS + 11);
     uint64_t* x_raw = bars + 2 * NXS + 12;    // [NXS]  kFuse: the old residual tile has landed (this CTA's own copy)
+    uint64_t* sv_full = bars + 3 * NXS + 12;  // [4 warps][2 buffers]  kStage: a call's saved values are in the staging buffer
+    uint64_t* sv_free = sv_full + 8;          // [4][2]  ... and its bulk stores have read them
     float* sbias = reinterpret_cast<float*>(smem + SM_BIAS);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -72,11 +79,13 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             __trap();
         }
         prefetch_tmap(&tmX); prefetch_tmap(&tmW); prefetch_tmap(&tmH64);
+        if constexpr (kStage) { prefetch_tmap(&sm.g); prefetch_tmap(&sm.c); prefetch_tmap(&sm.h); }
         // x_full: plain = the two CTAs' TMA halves; kFuse = the two converter warps of both CTAs
         for (int s = 0; s < NXS; ++s) { mbar_init(&x_full[s], kFuse ? 4 : 2); mbar_init(&x_empty[s], 1); mbar_init(&x_raw[s], 1); }
         mbar_init(w_full, 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&d_full[i], 1); mbar_init(&h_done[i], 8); }   // 4 warps x 2 CTAs
         mbar_init(&h_free[0], 1); mbar_init(&h_free[1], 1);
+        if constexpr (kStage) for (int i = 0; i < 16; ++i) mbar_init(&sv_full[i], 1);
         fence_barrier_init();
     }
     for (int i = threadIdx.x; i < 512; i += blockDim.x) sbias[i] = bias_perm[dir * 512 + i];
@@ -250,8 +259,23 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         const int bar_a = 1 + 2 * j, bar_b = 2 + 2 * j;
         const int sq = seq0 + j * 64;
         const long seq = (long)seq0 + row;
-        const bool live = kTrain && seq < p.seq_limit;
-
+        const bool live = kTrain && !kStage && seq < p.seq_limit;
+        // kStage (half tiles only: half-job B's halves of the h tiles and of the x ring stages are unused, and so are its
+        // epilogue warps): warp q owns the second 8 KiB of one of those tiles as two 4 KiB staging buffers and hands every
+        // call's boxes to warp q + 4, which issues the bulk stores - the cell-update warps, the step's critical path, only
+        // write shared memory
+        uint8_t* stg_base = smem + (q < 2 ? SM_H + q * TILE : SM_X + (q - 2) * TILE) + HALF_ROWS;
+        int ncall = 0;
+        auto stage_buf = [&]() {                          // the buffer of two calls ago has been read by its bulk stores
+            const int n = ncall++;
+            if (n >= 2) mbar_wait(&sv_free[q * 2 + (n & 1)], ((n >> 1) - 1) & 1);
+            return stg_base + (n & 1) * 4096;
+        };
+        auto stage_done = [&]() {                         // after the call's writes: publish to the async proxy, hand over
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sv_full[q * 2 + ((ncall - 1) & 1)]);
+        };
         for (int step = 0; step < T; ++step) {
             const int t = dir ? T - 1 - step : step;
             const uint32_t par = step & 1;
@@ -270,9 +294,17 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             tc_fence_after();
             uint32_t pk[4][4];
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g],
-                                                 gd ? gd + 16 * g : nullptr, cd + 8 * g, hd + 8 * g);
+            for (int g = 0; g < 4; ++g) {
+                if constexpr (kStage) {
+                    uint8_t* buf = stage_buf();
+                    lstm_cell8<kFastAct, kTrain, 32, kF16, true>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g],
+                                                                 nullptr, nullptr, nullptr, buf, lane);
+                    stage_done();
+                } else {
+                    lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g],
+                                                           gd ? gd + 16 * g : nullptr, cd + 8 * g, hd + 8 * g);
+                }
+            }
             tc_fence_before();
             mbar_wait(&h_free[j], par);                // the MMAs that read this half-job's h_{t-1} have completed
             if (storer) bulk_wait_read0();             // ... and so has last step's TMA store of its h rows
@@ -290,9 +322,17 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             mbar_wait(&d_full[j * 2 + 1], par);
             tc_fence_after();
 #pragma unroll
-            for (int g = 0; g < 4; ++g)
-                lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g, pk[g],
-                                                 gd ? gd + 128 + 16 * g : nullptr, cd + 64 + 8 * g, hd + 64 + 8 * g);
+            for (int g = 0; g < 4; ++g) {
+                if constexpr (kStage) {
+                    uint8_t* buf = stage_buf();
+                    lstm_cell8<kFastAct, kTrain, 32, kF16, true>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g,
+                                                                 pk[g], nullptr, nullptr, nullptr, buf, lane);
+                    stage_done();
+                } else {
+                    lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g, pk[g],
+                                                           gd ? gd + 128 + 16 * g : nullptr, cd + 64 + 8 * g, hd + 64 + 8 * g);
+                }
+            }
             tc_fence_before();
             {
                 uint8_t* sH = smem + SM_H + TILE;
@@ -311,6 +351,32 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             }
         }
         if (storer) bulk_wait0();
+        } else if constexpr (kStage) {
+            // ================= kStage: warps 8..11 store what warps 4..7 staged (same order of calls) =================
+            if (lane == 0) {
+                const int sq_w = seq0 + (q & 1) * 32, ub = q >> 1;
+                const uint8_t* stg_base = smem + (q < 2 ? SM_H + q * TILE : SM_X + (q - 2) * TILE) + HALF_ROWS;
+                int n = 0;
+                for (int step = 0; step < T; ++step) {
+                    const int t = dir ? T - 1 - step : step;
+                    const int k1 = c1(t, sq_w), k2 = c2(t, sq_w);
+                    for (int nh = 0; nh < 2; ++nh)
+                        for (int g = 0; g < 4; ++g, ++n) {
+                            const int unit0 = nh * 64 + ub * 32 + 8 * g;
+                            const uint8_t* buf = stg_base + (n & 1) * 4096;
+                            mbar_wait(&sv_full[q * 2 + (n & 1)], (n >> 1) & 1);
+                            tma_store_4d(&sm.g, buf, dir * 256 + unit0 * 2, k1, k2, outer);
+                            tma_store_4d(&sm.c, buf + 2048, dir * 128 + unit0, k1, k2, outer);
+                            tma_store_4d(&sm.h, buf + 3072, dir * 128 + unit0, k1, k2, outer);
+                            bulk_commit();
+                            if (n >= 1) {                  // the stores of the call before have read their buffer
+                                bulk_wait_read1();
+                                mbar_arrive(&sv_free[q * 2 + ((n - 1) & 1)]);
+                            }
+                        }
+                }
+                bulk_wait0();
+            }
         }
     }
     __syncwarp();
@@ -391,14 +457,30 @@ static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_p
     const uint64_t dW[2] = {256, (uint64_t)ndir * 512}, sW[2] = {2, 512};
     const uint32_t bW[2] = {64, 128};
     if (make_tmap(&tmW, t16, 2, w_packed, dW, sW, bW)) return 1;
-    auto kern = gates ? (fast_act ? lstm_tc_pp_kernel<true, true, false> : lstm_tc_pp_kernel<false, true, false>)
+    // training forward on 128-sequence tiles: the saved gates / c / h leave through staging buffers and TMA (kStage)
+    LstmSaveMaps sm{};
+    const bool stage = gates && p.half_tiles && !(flags & DPRNN_LSTM_DIRECT_SAVE);
+    if (stage) {
+        uint64_t dS[4], sS[4];
+        uint32_t bS[4] = {16, 1, 1, 1};
+        bS[inter ? 1 : 2] = 32;
+        for (int i = 0; i < 4; ++i) dS[i] = dX[i];
+        auto scale = [&](uint64_t row_bytes) { sS[0] = 4; for (int i = 1; i < 4; ++i) sS[i] = sX[i] / ldx * row_bytes; };
+        dS[0] = (uint64_t)ndir * 256; scale((uint64_t)ndir * 1024);
+        if (make_tmap(&sm.g, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, gates, dS, sS, bS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
+        dS[0] = (uint64_t)ndir * 128; scale((uint64_t)ndir * 512); bS[0] = 8;
+        if (make_tmap(&sm.c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cstate, dS, sS, bS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+        if (make_tmap(&sm.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hout_f32, dS, sS, bS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+    }
+    auto kern = stage ? (fast_act ? lstm_tc_pp_kernel<true, true, false, false, true> : lstm_tc_pp_kernel<false, true, false, false, true>)
+                : gates ? (fast_act ? lstm_tc_pp_kernel<true, true, false> : lstm_tc_pp_kernel<false, true, false>)
                 : fy  ? (f16 ? (fast_act ? lstm_tc_pp_kernel<true, false, true, true> : lstm_tc_pp_kernel<false, false, true, true>)
                              : (fast_act ? lstm_tc_pp_kernel<true, false, false, true> : lstm_tc_pp_kernel<false, false, false, true>))
                 : f16 ? (fast_act ? lstm_tc_pp_kernel<true, false, true> : lstm_tc_pp_kernel<false, false, true>)
                       : (fast_act ? lstm_tc_pp_kernel<true, false, false> : lstm_tc_pp_kernel<false, false, false>);
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PP_SM_TOTAL));
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
-    kern<<<(unsigned)(njobs * 2), 384, PP_SM_TOTAL, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p);
+    kern<<<(unsigned)(njobs * 2), 384, PP_SM_TOTAL, (cudaStream_t)stream>>>(tmX, tmW, tmH, bias_perm, p, sm);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

@@ -103,7 +103,7 @@ template <bool kF16>
 __global__ void norm_residual_kernel(const float* __restrict__ y, float* __restrict__ x,
                                      const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                      const float* __restrict__ beta, long total4, long per_utt4, int c4n,
-                                     uint2* __restrict__ x_bf16) {
+                                     uint2* __restrict__ x_bf16, float* __restrict__ x_out = nullptr) {
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
         const long b = idx / per_utt4;
         const int c4 = (int)(idx % c4n);
@@ -116,7 +116,7 @@ __global__ void norm_residual_kernel(const float* __restrict__ y, float* __restr
         r.y += (v.y - mean) * rstd * g.y + be.y;
         r.z += (v.z - mean) * rstd * g.z + be.z;
         r.w += (v.w - mean) * rstd * g.w + be.w;
-        reinterpret_cast<float4*>(x)[idx] = r;
+        reinterpret_cast<float4*>(x_out ? x_out : x)[idx] = r;      // x_out: out of place (x is left as it was)
         if (x_bf16)      // 16-bit shadow copy: the TMA-fed A operand of the next tensor-core LSTM layer
             x_bf16[idx] = make_uint2(pack_h16x2<kF16>(r.x, r.y), pack_h16x2<kF16>(r.z, r.w));
     }
@@ -636,6 +636,16 @@ int dprnn_norm_residual(const float* y, float* x, const float* mean_rstd, const 
     norm_residual_kernel<false><<<grid_for(per4 * B, 256), 256, 0, (cudaStream_t)stream>>>(y, x, mean_rstd, gamma, beta,
                                                                                          per4 * B, per4, C / 4,
                                                                                          (uint2*)x_bf16);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_norm_residual_to(const float* y, const float* x, const float* mean_rstd, const float* gamma, const float* beta,
+                           int B, long rows_per_utt, int C, float* x_out, void* x_bf16, void* stream) {
+    DPRNN_CHECK_ARG(y && x && x_out && x_out != x && mean_rstd && gamma && beta && B > 0 && rows_per_utt > 0 && C % 4 == 0);
+    const long per4 = rows_per_utt * (C / 4);
+    norm_residual_kernel<false><<<grid_for(per4 * B, 256), 256, 0, (cudaStream_t)stream>>>(
+        y, const_cast<float*>(x), mean_rstd, gamma, beta, per4 * B, per4, C / 4, (uint2*)x_bf16, x_out);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

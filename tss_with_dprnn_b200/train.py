@@ -14,15 +14,26 @@ can be differentiated only once).
 
 Supported: DPRNNTasNet and DPRNNSpeTasNet with fusion_type in {film, add, mul, cat, att}, 'ln' / 'gLN' norms, sigmoid /
 relu mask activation, uni- or bidirectional inter-RNN, kernel_size 2 / stride 1, feature_size = hidden_size = 128; frozen
-parameters are skipped.  DPRNN-Spe-IRA and DPRNN-RawNet raise NotImplementedError in train mode with autograd on.
+parameters are skipped.  DPRNN-Spe-IRA (the refinement iterations share the core's weights: their gradients accumulate)
+and an external speaker embedding (EmbTrainFunction: DPRNN-RawNet, whose RawNet3 encoder differentiates through library
+ops in rawnet.py) use the same pieces.
 """
 from __future__ import annotations
+
+import os
 
 import torch
 
 from ._lib import lib
 
 EPI_NONE, EPI_RELU, EPI_SIGMOID, EPI_GATED = 0, 1, 2, 3
+
+
+# experiments: 4 / 8 force 64 / 128 rows per CTA in the BPTT kernel (include/dprnn_b200.h: DPRNN_LSTM_HALF_TILES / _FULL_TILES)
+_BPTT_FLAGS = int(os.environ.get('DPRNN_BPTT_FLAGS', '0')) & 12
+# 4 / 8 likewise for the training forward, 16 = DPRNN_LSTM_DIRECT_SAVE (saved activations stored from the registers)
+_SKIP_SIDE = os.environ.get('DPRNN_TRAIN_SKIP_SIDE', '0') == '1'
+_FWD_FLAGS = int(os.environ.get('DPRNN_TRAIN_LSTM_FLAGS', '0')) & 28
 
 
 def _st():
@@ -36,6 +47,10 @@ class _Ops:
         self.dev = dev
         self.L = lib()
         self.tf32 = tf32                # big contractions on the tensor cores (TF32 operands, fp32 accumulation)
+        self.persist = os.environ.get('DPRNN_TRAIN_PERSIST', '1') != '0'     # resident-weight GEMM where it applies
+        self._gp_ws = {}                # its ticket word, one per stream (launches of two streams may overlap)
+        self.dual = os.environ.get('DPRNN_TRAIN_DUAL', '1') != '0'           # dW_ih, dW_hh, db from one pass over d gates
+        self.kdeep = os.environ.get('DPRNN_TRAIN_KDEEP', '1') != '0'         # d x = d gates @ W_ih accumulated in place
 
     def empty(self, *shape):
         return torch.empty(shape, device=self.dev, dtype=torch.float32)
@@ -54,10 +69,33 @@ class _Ops:
             return self.gemm(A, W.t().contiguous(), M, N, K, bias=bias, epi=epi)
         out = self.empty(M, N)
         step = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 64)
+        if step == 256 and K > 128:
+            step = 128                                   # the persistent kernel keeps [step, K] of W resident
         for n0 in range(0, N, step):
-            self.L.call('dprnn_gemm_tc', A, 0, W[n0:n0 + step], None if bias is None else bias[n0:n0 + step],
-                        out.data_ptr() + 4 * n0, N, M, step, K, epi, None, 0, 0.0, None, _st())
+            bn = None if bias is None else bias[n0:n0 + step]
+            if self.persist and self.L.query('dprnn_gemm_persist_supported', 0, step, K, epi):
+                # one CTA per SM with the weight resident and a TMA ring over the rows (csrc/gemm_persist.cu)
+                ws = self._gp_ws.get(_st())
+                if ws is None:
+                    ws = self._gp_ws[_st()] = torch.empty(self.L.query('dprnn_gemm_persist_workspace_bytes'), device=self.dev,
+                                                          dtype=torch.uint8)
+                self.L.call('dprnn_gemm_persist', A, 0, W[n0:n0 + step], bn, 0, None, None, None, None,
+                            out.data_ptr() + 4 * n0, N, M, step, K, epi, ws, _st())
+            else:
+                self.L.call('dprnn_gemm_tc', A, 0, W[n0:n0 + step], bn, out.data_ptr() + 4 * n0, N, M, step, K, epi,
+                            None, 0, 0.0, None, _st())
         return out
+
+    def mm_acc(self, A, W, M, N, K, out):
+        """out[M,N] += A[M,K] @ W[N,K]^T in one pass (deep-K kernel, csrc/gemm_kdeep.cu); False when it does not apply."""
+        if not (self.tf32 and self.kdeep and M >= 256 and self.L.query('dprnn_gemm_kdeep_supported', N, K, K, N)):
+            return False
+        ws = self._gp_ws.get(('kd', _st()))
+        if ws is None:
+            ws = self._gp_ws[('kd', _st())] = torch.empty(self.L.query('dprnn_gemm_kdeep_workspace_bytes'), device=self.dev,
+                                                          dtype=torch.uint8)
+        self.L.call('dprnn_gemm_kdeep', A, K, W, out, N, M, N, K, 1, ws, _st())
+        return True
 
     def atb(self, A, B, M, N1, N2, out, lda=None, ldb=None, ldc=None, accumulate=True):
         """out[N1,N2] (+)= A[M,N1]^T B[M,N2]"""
@@ -75,6 +113,18 @@ class _Ops:
             return False
         ws = torch.empty(self.L.query('dprnn_gemm_atb_tc_colsum_workspace_bytes', N1), device=self.dev, dtype=torch.uint8)
         self.L.call('dprnn_gemm_atb_tc_colsum', A, lda or N1, B, ldb or N2, out, N2, colsum, M, N1, N2, 1, 0, ws, _st())
+        return True
+
+    def atb_dual(self, A, lda, N1, B1, ldb1, B2, ldb2, B, S, K, inter, shift, C1, ldc1, C2, ldc2, colsum):
+        """C1[N1,128] += A^T B1, C2[N1,128] += A^T shift_t(B2) and colsum[N1] = column sums of A in ONE pass over A
+        (csrc/atb_tc.cu: atb_dual_kernel; rows addressed as (time, sequence), so the time shift costs no copy); False
+        when the kernel does not apply."""
+        if not (self.tf32 and self.dual and B * S * K >= 4096
+                and self.L.query('dprnn_gemm_atb_dual_supported', N1, lda, ldb1, ldb2)):
+            return False
+        ws = torch.empty(self.L.query('dprnn_gemm_atb_dual_workspace_bytes', N1), device=self.dev, dtype=torch.uint8)
+        self.L.call('dprnn_gemm_atb_dual', A, lda, N1, B1, ldb1, B2, ldb2, B, S, K, int(inter), int(shift), C1, ldc1, C2, ldc2,
+                    colsum, 1, 0, ws, _st())
         return True
 
     def colsum(self, X, M, N, out, Y=None, ldx=None, accumulate=True):
@@ -260,6 +310,7 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
 
     # ---- DPRNN blocks (dprnn.py:79-99)
     halves = []
+    xb_next, n_half = None, 0
     for blk in sep.dprnn_blocks:
         for which, (rnn, linm, nm) in enumerate(((blk.intra_rnn.rnn, blk.intra_linear, blk.intra_norm),
                                                  (blk.inter_rnn.rnn, blk.inter_linear, blk.inter_norm))):
@@ -276,13 +327,15 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
                 # tensor-core recurrence (bf16 operands, fp32 accumulation and cell state), input projection fused:
                 # the kernel of the inference path, whose epilogue also stores what BPTT needs
                 from .engine import Engine
-                xb = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
-                L_.call('dprnn_cast_bf16', xs, xb, rows * F, st)
+                xb = xb_next                                          # written by the previous half-block's norm + residual
+                if xb is None:
+                    xb = torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+                    L_.call('dprnn_cast_bf16', xs, xb, rows * F, st)
                 pp = model._engine.lstm_pingpong                      # half-job ping-pong kernel (same results)
                 wp, bp = Engine._pack_lstm_tc(rnn, sfx, half_jobs=pp)
                 hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
                 L_.call('dprnn_lstm_layer_bf16_train_pp' if pp else 'dprnn_lstm_layer_bf16_train', xb, wp, bp, hb, gates,
-                        cst, hout, B, S, K, which, H, nd, int(model._engine.fast_act), st)
+                        cst, hout, B, S, K, which, H, nd, int(model._engine.fast_act) | (_FWD_FLAGS if pp else 0), st)
                 del xb, hb
             else:
                 gx = ops.mm(xs, wih, rows, nd * 4 * H, F, bias=b)
@@ -291,9 +344,12 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
             yl = ops.mm(hout, linm.weight.detach(), rows, F, nd * H, bias=linm.bias.detach())
             g_, b_, eps_ = _norm_params(nm)
             mr = ops.utt_stats(yl, B, S * K * F, eps_)
-            L_.call('dprnn_norm_residual', yl, xs, mr, g_.detach(), b_.detach(), B, S * K, F, None, st)
+            n_half += 1
+            xb_next = (torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
+                       if ops.tf32 and n_half < 2 * len(sep.dprnn_blocks) else None)      # the next LSTM's bf16 operand
+            L_.call('dprnn_norm_residual', yl, xs, mr, g_.detach(), b_.detach(), B, S * K, F, xb_next, st)
             halves.append(dict(nd=nd, geo=geo, hout=hout, gates=gates, cst=cst, yl=yl, mr=mr, wih=wih, whh=whh,
-                               rnn=rnn, lin=linm, norm=nm, sfx=sfx))
+                               rnn=rnn, lin=linm, norm=nm, sfx=sfx, which=which))
     c.update(halves=halves, xs=xs)
 
     # ---- PReLU, overlap-add, conv2d, gated head, end conv + activation (dprnn_spe.py:231-248)
@@ -509,15 +565,16 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
         names[id(mod)] = n_
     # The gradient CHAIN (norm adjoint -> d h -> BPTT -> d x) runs on the caller's stream; the weight / bias gradients of each
     # half-block hang off it and run on a side stream, where they overlap the next half-block's BPTT (which occupies only
-    # the SMs its 256-sequence tiles land on).  xs is rewritten in place at the top of every iteration, so the chain waits
-    # for the side stream's reads of xs (xs_read) before doing that; buffers handed to the side stream are
+    # the SMs its tiles land on).  The residual stream is walked back OUT OF PLACE (x_in of a half-block goes to a new buffer),
+    # so the chain never waits for the side stream's reads of the layer inputs; buffers handed to the side stream are
     # record_stream()-ed so that the caching allocator does not recycle them early.
     main = torch.cuda.current_stream()
     side = _side_stream(dev)
     side.wait_stream(main)
-    xs_read = None
 
     def on_side(fn, *tensors):
+        if _SKIP_SIDE:             # timing experiment only (tools/ab_cfg5.sh): the weight gradients are NOT computed
+            return
         ev = torch.cuda.Event()
         ev.record(main)
         side.wait_event(ev)
@@ -532,15 +589,22 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
         pn = names[id(hv['norm'])]
         gname = pn + ('.gamma' if hasattr(hv['norm'], 'gamma') else '.weight')
         bname = pn + ('.beta' if hasattr(hv['norm'], 'gamma') else '.bias')
-        if xs_read is not None:
-            main.wait_event(xs_read)
-        L_.call('dprnn_norm_residual', yl, xs, mr, (-g_.detach()).contiguous(), (-b_.detach()).contiguous(), B, S * K, F,
-                None, st)                                            # xs: x_out -> x_in
+        xs_out, xs = xs, torch.empty_like(xs)
+        L_.call('dprnn_norm_residual_to', yl, xs_out, mr, (-g_.detach()).contiguous(), (-b_.detach()).contiguous(), B, S * K,
+                F, xs, None, st)                                     # xs: x_in = x_out - norm(y)
+        del xs_out
         dy = ops.gn_bwd(dx, yl, mr, g_.detach(), B, S * K, F, G[gname], G[bname])
         ln = names[id(hv['lin'])]
         hout = hv['hout']
 
         def lin_grads(dy=dy, hout=hout, ln=ln, nd=nd):
+            if nd == 2 and F == 128:       # dW = dy^T [h_fwd | h_bwd] and db = sum dy from one pass over dy
+                db = ops.empty(F)
+                gw = G[ln + '.weight']
+                if ops.atb_dual(dy, F, F, hout, nd * H, hout.data_ptr() + 4 * H, nd * H, B, S, K, 0, 0,
+                                gw, nd * H, gw.data_ptr() + 4 * H, nd * H, db):
+                    ops.axpy(db, G[ln + '.bias'])
+                    return
             ops.atb(dy, hout, rows, F, nd * H, G[ln + '.weight'])
             ops.colsum(dy, rows, F, G[ln + '.bias'])
         on_side(lin_grads, dy, hout)
@@ -550,14 +614,28 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
         if ops.tf32:
             whhT = hv['whh'].transpose(1, 2).contiguous().to(torch.bfloat16)              # [nd, H, 4H]
             L_.call('dprnn_lstm_bptt_tc', dh, hv['gates'], hv['cst'], whhT, dgates, *geo, H, nd,
-                    int(model._engine.fast_act), st)
+                    int(model._engine.fast_act) | _BPTT_FLAGS, st)
         else:
             L_.call('dprnn_lstm_bptt_f32', dh, hv['gates'], hv['cst'], hv['whh'], dgates, *geo, H, nd, st)
         del dh
         rn = names[id(hv['rnn'])]
-        xs_read = torch.cuda.Event()
 
-        def rnn_grads(dgates=dgates, hout=hout, rn=rn, nd=nd, geo=geo, sfx=hv['sfx'], xs_read=xs_read):
+        def rnn_grads(dgates=dgates, hout=hout, rn=rn, nd=nd, geo=geo, sfx=hv['sfx'], xs=xs, which=hv['which']):
+            if F == 128 and ops.tf32 and ops.dual:
+                # per direction ONE pass over its d gates: dW_ih = dg^T x, dW_hh = dg^T h_{t-1} (h read one time step earlier
+                # - later for the reverse direction - through the tensor map: no shifted copy), db = sum dg
+                done = True
+                for d, sf in enumerate(sfx):
+                    db = ops.empty(4 * H)
+                    done = done and ops.atb_dual(dgates.data_ptr() + 4 * d * 4 * H, nd * 4 * H, 4 * H, xs, F,
+                                                 hout.data_ptr() + 4 * d * H, nd * H, B, S, K, which, 1 if d else -1,
+                                                 G[f'{rn}.weight_ih_l0{sf}'], F, G[f'{rn}.weight_hh_l0{sf}'], H, db)
+                    if not done:
+                        break
+                    ops.axpy(db, G[f'{rn}.bias_ih_l0{sf}'])
+                    ops.axpy(db, G[f'{rn}.bias_hh_l0{sf}'])
+                if done:
+                    return
             dbs = []
             for d, sf in enumerate(sfx):                             # the reads of xs first: the chain waits for them
                 # dW_ih = dgates^T x; in tensor-core mode the same pass also yields db = column sums of dgates
@@ -568,7 +646,6 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
                 else:
                     ops.atb(dgates.data_ptr() + 4 * d * 4 * H, xs, rows, 4 * H, F, G[f'{rn}.weight_ih_l0{sf}'], lda=nd * 4 * H)
                     dbs.append(None)
-            xs_read.record(torch.cuda.current_stream())
             hprev = ops.empty(rows, nd * H)
             L_.call('dprnn_shift_rows', hout, hprev, *geo, H, nd, _st())
             for d, sf in enumerate(sfx):
@@ -580,10 +657,13 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
                     ops.colsum(dgd, rows, 4 * H, db, ldx=nd * 4 * H, accumulate=False)
                 ops.axpy(db, G[f'{rn}.bias_ih_l0{sf}'])
                 ops.axpy(db, G[f'{rn}.bias_hh_l0{sf}'])
-        on_side(rnn_grads, dgates, hout)
-        dxl = ops.mm(dgates, hv['wih'].t().contiguous(), rows, F, nd * 4 * H)
-        ops.axpy(dxl, dx)                                            # dx (gradient of x_in) = dx_out + LSTM-branch gradient
-        del dgates, dxl, hout
+        on_side(rnn_grads, dgates, hout, xs)
+        # dx (gradient of x_in) = dx_out + LSTM-branch gradient
+        if not ops.mm_acc(dgates, hv['wih'].t().contiguous(), rows, F, nd * 4 * H, dx):
+            dxl = ops.mm(dgates, hv['wih'].t().contiguous(), rows, F, nd * 4 * H)
+            ops.axpy(dxl, dx)
+            del dxl
+        del dgates, hout
         hv['hout'] = hv['gates'] = hv['cst'] = hv['yl'] = None       # free as we go
     main.wait_stream(side)
 
