@@ -206,22 +206,25 @@ int dprnn_gemm_persist(const void* A, int a_kind, const void* W, const float* bi
  * (128 columns each); rows are the chunk positions of a [B, S, K] batch, row = (b*S + s)*K + k.  inter = 0: time runs
  * along k (intra-chunk layer), 1: along s.  shift in {-1, 0, +1}: B2 is read at time t + shift and is zero outside the
  * sequence (h_{t-1} for the forward direction, h_{t+1} for the reverse one: no shifted copy of h).  shift = 0 with
- * B1 | B2 = the two halves of h gives the Linear's dW = dy^T h and db.  lda, ldb1, ldb2 in floats, multiples of 32.
- * TF32 operands, fp32 accumulation, fixed reduction order.  workspace: dprnn_gemm_atb_dual_workspace_bytes(N1). */
-int dprnn_gemm_atb_dual_supported(int N1, long lda, long ldb1, long ldb2);
+ * B1 | B2 = the two halves of h gives the Linear's dW = dy^T h and db.
+ * is_bf16 = 0: fp32 operands read as TF32 (leading dimensions in floats, multiples of 32); 1: all three operands bf16
+ * (d gates from dprnn_lstm_bptt_tc_bf16out, x and h as the bf16 operands of the tensor-core forward; leading dimensions in
+ * elements, multiples of 64).  fp32 accumulation, fixed reduction order.  workspace: dprnn_gemm_atb_dual_workspace_bytes(N1). */
+int dprnn_gemm_atb_dual_supported(int is_bf16, int N1, long lda, long ldb1, long ldb2);
 size_t dprnn_gemm_atb_dual_workspace_bytes(int N1);
-int dprnn_gemm_atb_dual(const float* A, long lda, int N1, const float* B1, long ldb1, const float* B2, long ldb2, int B,
-                        int S, int K, int inter, int shift, float* C1, long ldc1, float* C2, long ldc2, float* colsum,
+int dprnn_gemm_atb_dual(const void* A, int is_bf16, long lda, int N1, const void* B1, long ldb1, const void* B2, long ldb2,
+                        int B, int S, int K, int inter, int shift, float* C1, long ldc1, float* C2, long ldc2, float* colsum,
                         int accumulate, int accumulate_colsum, void* workspace, void* stream);
 
 /* Deep-K contraction of the training step's backward (d x = d gates @ W_ih: src/models/dprnn.py:51-70 differentiated):
- * C[M,128] (+)= A[M,K] @ W[128,K]^T, fp32 operands read as TF32, K % 32 == 0 (any depth: W streams with A, 256-row tiles
- * share every W block).  accumulate != 0 adds into C through TMA reduce-add (each element of C is touched once:
- * deterministic).  lda / ldc in floats.  workspace: dprnn_gemm_kdeep_workspace_bytes() bytes (scheduler ticket). */
+ * C[M,128] (+)= A[M,K] @ W[128,K]^T; a_is_bf16 = 0: fp32 operands read as TF32, K % 32 == 0; 1: bf16 operands (the d gates
+ * dprnn_lstm_bptt_tc_bf16out writes), K % 64 == 0.  Any depth: W streams with A, 256-row tiles share every W block.
+ * accumulate != 0 adds into C through TMA reduce-add (each element of C is touched once: deterministic).  lda in
+ * elements, ldc in floats.  workspace: dprnn_gemm_kdeep_workspace_bytes() bytes (scheduler ticket). */
 size_t dprnn_gemm_kdeep_workspace_bytes(void);
-int dprnn_gemm_kdeep_supported(int N, int K, long lda, long ldc);
-int dprnn_gemm_kdeep(const float* A, long lda, const float* W, float* C, long ldc, int M, int N, int K, int accumulate,
-                     void* workspace, void* stream);
+int dprnn_gemm_kdeep_supported(int a_is_bf16, int N, int K, long lda, long ldc);
+int dprnn_gemm_kdeep(const void* A, int a_is_bf16, long lda, const void* W, float* C, long ldc, int M, int N, int K,
+                     int accumulate, void* workspace, void* stream);
 
 /* 1x1 conv -> BatchNorm1d (eval: per-channel scale/shift from dprnn_batchnorm_affine) -> PReLU in one pass
  * (ResBlock, src/models/dprnn_spe.py:32-34): C[M,N] = prelu(A @ W^T * scale[n] + shift[n]); fp32 (TF32) operands,
@@ -508,6 +511,11 @@ int dprnn_lstm_bptt_f32(const float* dh_out, const float* gates, const float* cs
 int dprnn_lstm_bptt_tc(const float* dh_out, const void* gates_packed, const float* cstate, const void* whhT_bf16, float* dgates,
                        long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride, long step_stride,
                        int hidden, int ndir, int fast_act, void* stream);
+/* The same with d gates written as bf16 [rows, ndir*4H] (TMA stores of the operand tile the tensor core has just read):
+ * the input format of dprnn_gemm_kdeep (a_is_bf16 = 1) and dprnn_gemm_atb_dual (is_bf16 = 1); nseq % seq_div == 0. */
+int dprnn_lstm_bptt_tc_bf16out(const float* dh_out, const void* gates_packed, const float* cstate, const void* whhT_bf16,
+                               void* dgates_bf16, long nseq, int T, long seq_div, long seq_outer_stride,
+                               long seq_inner_stride, long step_stride, int hidden, int ndir, int fast_act, void* stream);
 /* h_prev for the W_hh gradient: out[row(n,t)] = h[row(n, previous step of the direction)], 0 at the first step. */
 int dprnn_shift_rows(const float* h, float* out, long nseq, int T, long seq_div, long seq_outer_stride,
                      long seq_inner_stride, long step_stride, int hidden, int ndir, void* stream);

@@ -141,6 +141,13 @@ def test_lstm_train_forward_and_bptt(inter, ndir, big=False):
     # both tile sizes run the same arithmetic per row (M = 128 and M = 256 MMAs accumulate the K = 512 in the same order)
     assert torch.equal(got[4], got[8]) and torch.equal(got[5], got[9])
     assert torch.equal(got[0], got[4]) or torch.equal(got[0], got[8])
+    # bf16 output (TMA stores of the tensor core's operand tile): the bf16 rounding of the fp32 output, bit for bit
+    for flags in (5, 9):
+        dgb = torch.full((rows + 1, ndir * 4 * H), 7.0, device=DEV, dtype=torch.bfloat16)
+        L.call('dprnn_lstm_bptt_tc_bf16out', dout.float().reshape(rows, -1).contiguous().to(DEV), gates_p, cst, whhT, dgb, *geo,
+               H, ndir, flags, st())
+        assert torch.equal(dgb[:rows], got[flags].to(torch.bfloat16)), flags
+        assert float((dgb[rows:].float() - 7.0).abs().max()) == 0.0
     # dx = dgates @ W_ih ; dW_ih = dgates^T x ; db = colsum(dgates)
     dx = dgc @ wih.double()
     assert rel(dx, x.grad.reshape(rows, H)) < 1e-4
@@ -234,26 +241,33 @@ def test_gemm_atb_tc_colsum(M, N1, lda):
     assert torch.equal(outs[1][0], C) and torch.equal(outs[1][1], cs)
 
 
-@pytest.mark.parametrize('M,K,lda', [(48500 * 4, 1024, 1024), (1000, 512, 512), (257, 1024, 1536), (776000, 1024, 1024), (300, 32, 32)])
-def test_gemm_kdeep(M, K, lda):
+@pytest.mark.parametrize('bf', [0, 1])
+@pytest.mark.parametrize('M,K,lda', [(48500 * 4, 1024, 1024), (1000, 512, 512), (257, 1024, 1536), (776000, 1024, 1024), (300, 64, 64)])
+def test_gemm_kdeep(M, K, lda, bf):
     """C[M,128] (+)= A[M,K] W[128,K]^T with W streamed next to A (256-row tiles, TMA reduce-add into C): TF32 operands
-    (truncated) against the fp64 product; strided A, a ragged last tile, rows past M untouched, deterministic."""
+    (truncated) or bf16 operands against the fp64 product of the same operands; strided A, a ragged last tile, rows past M
+    untouched, deterministic."""
     L = P.lib()
     g = torch.Generator().manual_seed(M % 977 + K)
-    tr = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    if bf:
+        tr = lambda t: t.to(torch.bfloat16).double()
+        dt, el = torch.bfloat16, 2
+    else:
+        tr = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+        dt, el = torch.float32, 4
     Afull = torch.randn(M, lda, generator=g)
     W = torch.randn(128, K, generator=g) / K ** 0.5
     C0 = torch.randn(M + 3, 128, generator=g)
     A = Afull[:, lda - K:]
     want = tr(A) @ tr(W).t()
-    Ad, Wd = Afull.to(DEV), W.to(DEV)
-    aptr = Ad.data_ptr() + 4 * (lda - K)
+    Ad, Wd = Afull.to(dt).to(DEV), W.to(dt).to(DEV)
+    aptr = Ad.data_ptr() + el * (lda - K)
     ws = torch.empty(L.query('dprnn_gemm_kdeep_workspace_bytes'), device=DEV, dtype=torch.uint8)
-    assert L.query('dprnn_gemm_kdeep_supported', 128, K, lda, 128) == 1
+    assert L.query('dprnn_gemm_kdeep_supported', bf, 128, K, lda, 128) == 1
     outs = []
     for acc in (0, 1, 1):
         C = C0.to(DEV)
-        L.call('dprnn_gemm_kdeep', aptr, lda, Wd, C, 128, M, 128, K, acc, ws, st())
+        L.call('dprnn_gemm_kdeep', aptr, bf, lda, Wd, C, 128, M, 128, K, acc, ws, st())
         torch.cuda.synchronize()
         ref = want + (C0[:M].double() if acc else 0.0)
         err = float((C[:M].cpu().double() - ref).abs().max()) / float(ref.abs().max())
@@ -261,19 +275,26 @@ def test_gemm_kdeep(M, K, lda):
         assert torch.equal(C[M:].cpu(), C0[M:])                         # rows past M are not touched
         outs.append(C.clone())
     assert torch.equal(outs[1], outs[2])
-    assert L.query('dprnn_gemm_kdeep_supported', 64, K, lda, 128) == 0
+    assert L.query('dprnn_gemm_kdeep_supported', bf, 64, K, lda, 128) == 0
 
 
+@pytest.mark.parametrize('bf', [0, 1])
 @pytest.mark.parametrize('B,S,K,inter,N1,shift', [(2, 37, 50, 0, 512, -1), (2, 37, 50, 0, 512, 1), (3, 41, 70, 1, 512, -1),
                                                   (3, 41, 70, 1, 512, 1), (2, 33, 250, 0, 128, 0), (16, 97, 250, 1, 512, -1)])
-def test_gemm_atb_dual(B, S, K, inter, N1, shift):
+def test_gemm_atb_dual(B, S, K, inter, N1, shift, bf):
     """dW_ih, dW_hh and db of one LSTM direction from one pass over its d gates: C1 += A^T B1, C2 += A^T shift_t(B2),
     colsum = sum A, with B2 read one time step earlier / later through the tensor map (zero outside the sequence).  TF32
-    operands (truncated) against the fp64 products; strided operands; accumulate into C, overwrite the sums."""
+    (truncated) or bf16 operands against the fp64 products of the same operands; strided operands; accumulate into C,
+    overwrite the sums."""
     L = P.lib()
     rows = B * S * K
     g = torch.Generator().manual_seed(rows % 977 + N1 + shift)
-    tr = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+    if bf:
+        tr = lambda t: t.to(torch.bfloat16).double()
+        dt, el = torch.bfloat16, 2
+    else:
+        tr = lambda t: (t.contiguous().view(torch.int32) & ~0x1FFF).view(torch.float32).double()
+        dt, el = torch.float32, 4
     lda, ldb2 = 2 * N1, 256
     Afull = torch.randn(rows, lda, generator=g)
     B1 = torch.randn(rows, 128, generator=g)
@@ -293,16 +314,16 @@ def test_gemm_atb_dual(B, S, K, inter, N1, shift):
     want1 = tr(A).t() @ tr(B1)
     want2 = tr(A).t() @ tr(hs.reshape(rows, 128))
     want_cs = tr(A).sum(0)
-    Ad, B1d, B2d = Afull.to(DEV), B1.to(DEV), B2full.to(DEV)
-    assert L.query('dprnn_gemm_atb_dual_supported', N1, lda, 128, ldb2) == 1
+    Ad, B1d, B2d = Afull.to(dt).to(DEV), B1.to(dt).to(DEV), B2full.to(dt).to(DEV)
+    assert L.query('dprnn_gemm_atb_dual_supported', bf, N1, lda, 128, ldb2) == 1
     ws = torch.empty(L.query('dprnn_gemm_atb_dual_workspace_bytes', N1), device=DEV, dtype=torch.uint8)
     outs = []
     for _ in range(2):
         C1 = torch.full((N1, 128), 3.0, device=DEV)
         C2 = torch.full((N1, 256), -2.0, device=DEV)              # written at columns 128.. with ldc = 256
         cs = torch.full((N1,), 9.0, device=DEV)
-        L.call('dprnn_gemm_atb_dual', Ad.data_ptr() + 4 * N1, lda, N1, B1d, 128, B2d.data_ptr() + 4 * 128, ldb2, B, S, K, inter,
-               shift, C1, 128, C2.data_ptr() + 4 * 128, 256, cs, 1, 0, ws, st())
+        L.call('dprnn_gemm_atb_dual', Ad.data_ptr() + el * N1, bf, lda, N1, B1d, 128, B2d.data_ptr() + el * 128, ldb2, B, S, K,
+               inter, shift, C1, 128, C2.data_ptr() + 4 * 128, 256, cs, 1, 0, ws, st())
         torch.cuda.synchronize()
         tol = 1e-4 * float(want1.abs().max())
         assert float((C1.cpu().double() - 3.0 - want1).abs().max()) < tol

@@ -16,6 +16,5 @@ except Exception as e:
 PY
 }
 run default X=1
-run no_dual DPRNN_TRAIN_DUAL=0
+run no_dg16 DPRNN_TRAIN_DG16=0
 run default2 X=1
-run no_dual2 DPRNN_TRAIN_DUAL=0

@@ -277,11 +277,13 @@ __global__ void atb_tc_colsum_reduce_kernel(const float* __restrict__ partial, i
 // zeros - exactly h_{-1} = 0.  The same kernel with shift 0 and B1 | B2 = the two halves of h gives the Linear's
 // dW = dy^T h and db = sum dy in one pass over dy.
 // B operand in shared memory = [B1 (4 groups) | B2 (4 groups) | ones (1 group)]: one N = 256 and one N = 32 MMA per K slice.
-constexpr int AD_YG = 9;
+// kElem = 2: bf16 operands (d gates as dprnn_lstm_bptt_tc_bf16out writes it, x and h as the bf16 copies the tensor-core
+// forward works on) - half the bytes of the fp32 form.  16-bit MN-major operands use the plain SWIZZLE_128B layout: a group
+// is 64 columns (128 bytes) wide, 8 contraction rows form the 1024-byte swizzle atom, an MMA consumes K = 16 rows.
 constexpr int AD_ROWS = 257;     // rows of a partial: 256 columns of [B1 | B2] + the column-sum row
 
 struct AtbDualGeo {
-    int n1chunks, D2;            // 32-index blocks along d1; extent of d2
+    int n1chunks, D2;            // blocks of KB indices along d1; extent of d2
     int sh1, sh2;                // B2's coordinate offset along d1 / d2 (the time shift)
     long total_chunks, chunks_per_split;
 };
@@ -293,15 +295,53 @@ __device__ __forceinline__ void tma_load_5d(void* smem, const CUtensorMap* m, ui
         ::"r"(smem_u32(smem)), "l"(m), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 
+template <int kElem>
+struct AdCfg {
+    static constexpr int KB = kElem == 2 ? 64 : 32;                 // contraction rows per stage
+    static constexpr int G128 = kElem == 2 ? 2 : 4;                 // column groups (128 bytes wide) per 128 columns
+    static constexpr uint32_t GROUP = KB * 128;                     // bytes of one column group of a stage = LBO
+    static constexpr uint32_t STAGE = (3 * G128 + 1) * GROUP;       // A | B1 | B2 | ones
+    static constexpr uint32_t TMA_BYTES = 3 * G128 * GROUP;
+    static constexpr uint32_t KSTEP = kElem == 2 ? 2048 : 1024;     // bytes of the rows one MMA consumes (K = 16 / 8)
+    static constexpr size_t SMEM = (size_t)AB_NST * STAGE + 1024;
+};
+static_assert(AdCfg<2>::SMEM <= 232448 && AdCfg<4>::SMEM <= 232448, "shared memory budget of one SM (227 KiB)");
+
+template <int kElem>
+__device__ __forceinline__ uint64_t ad_desc_mn(uint32_t smem_addr) {
+    if constexpr (kElem == 2)       // SWIZZLE_128B (2): LBO = distance between 64-column groups, SBO = between 8-row atoms
+        return (uint64_t)((smem_addr & 0x3FFFF) >> 4) | ((uint64_t)(AdCfg<2>::GROUP >> 4) << 16) | ((uint64_t)(1024 >> 4) << 32) |
+               ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+    else
+        return umma_desc_sw128_mn(smem_addr);
+}
+template <int kElem>
+__device__ __forceinline__ void ad_umma(uint32_t tmem_d, uint64_t da, uint64_t db, int n, uint32_t acc) {
+    if constexpr (kElem == 2) {
+        // kind::f16, D = f32, A = B = bf16, both MN-major (bits 15, 16)
+        const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | (1u << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        const uint32_t idesc = umma_idesc_tf32_mn(128, n);
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    }
+}
+
+template <int kElem>
 __global__ void __launch_bounds__(192) atb_dual_kernel(const __grid_constant__ CUtensorMap tmA,
                                                        const __grid_constant__ CUtensorMap tmB1,
                                                        const __grid_constant__ CUtensorMap tmB2, const AtbDualGeo g,
                                                        int tiles, float* __restrict__ partial) {
+    using Cf = AdCfg<kElem>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     __shared__ __align__(8) uint64_t bar_full[AB_NST], bar_empty[AB_NST], bar_done;
     __shared__ uint32_t tmem_base_s;
-    constexpr uint32_t X_BYTES = 4 * AB_GROUP, STAGE = X_BYTES + AD_YG * AB_GROUP, TMA_BYTES = 12 * AB_GROUP;
+    constexpr uint32_t X_BYTES = Cf::G128 * Cf::GROUP, STAGE = Cf::STAGE, TMA_BYTES = Cf::TMA_BYTES;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tile = blockIdx.x, split = blockIdx.y;
@@ -316,9 +356,9 @@ __global__ void __launch_bounds__(192) atb_dual_kernel(const __grid_constant__ C
         fence_barrier_init();
     }
     // the ones group of every stage slot (A's out-of-range rows are zero-filled by TMA: 0 * 1 = 0)
-    for (int i = threadIdx.x; i < AB_NST * (int)(AB_GROUP / 4); i += blockDim.x) {
-        const int s = i / (int)(AB_GROUP / 4), j = i % (int)(AB_GROUP / 4);
-        reinterpret_cast<float*>(smem + s * STAGE + TMA_BYTES)[j] = 1.0f;
+    for (int i = threadIdx.x; i < AB_NST * (int)(Cf::GROUP / 4); i += blockDim.x) {
+        const int s = i / (int)(Cf::GROUP / 4), j = i % (int)(Cf::GROUP / 4);
+        reinterpret_cast<uint32_t*>(smem + s * STAGE + TMA_BYTES)[j] = kElem == 2 ? 0x3F803F80u : 0x3F800000u;
     }
     fence_async_smem();
     if (warp == 1) tmem_alloc<1>(&tmem_base_s, 512);
@@ -337,34 +377,25 @@ __global__ void __launch_bounds__(192) atb_dual_kernel(const __grid_constant__ C
                 mbar_wait(&bar_empty[s], ((kb / AB_NST) & 1) ^ 1);
                 mbar_expect_tx(&bar_full[s], TMA_BYTES);
                 uint8_t* st = smem + s * STAGE;
-                tma_load_5d(st, &tmA, &bar_full[s], 0, i1 * 32, i2, i3, tile * 4);
-                tma_load_5d(st + X_BYTES, &tmB1, &bar_full[s], 0, i1 * 32, i2, i3, 0);
-                tma_load_5d(st + X_BYTES + 4 * AB_GROUP, &tmB2, &bar_full[s], 0, i1 * 32 + g.sh1, i2 + g.sh2, i3, 0);
+                tma_load_5d(st, &tmA, &bar_full[s], 0, i1 * Cf::KB, i2, i3, tile * Cf::G128);
+                tma_load_5d(st + X_BYTES, &tmB1, &bar_full[s], 0, i1 * Cf::KB, i2, i3, 0);
+                tma_load_5d(st + 2 * X_BYTES, &tmB2, &bar_full[s], 0, i1 * Cf::KB + g.sh1, i2 + g.sh2, i3, 0);
                 if (++i1 == g.n1chunks) { i1 = 0; if (++i2 == g.D2) { i2 = 0; ++i3; } }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            const uint32_t idesc256 = umma_idesc_tf32_mn(128, 256), idesc32 = umma_idesc_tf32_mn(128, 32);
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = kb % AB_NST;
                 mbar_wait(&bar_full[s], (kb / AB_NST) & 1);
                 tc_fence_after();
-                const uint32_t sx = smem_u32(smem + s * STAGE), sy = sx + X_BYTES, so = sy + 8 * AB_GROUP;
+                const uint32_t sx = smem_u32(smem + s * STAGE), sy = sx + X_BYTES, so = sx + TMA_BYTES;
 #pragma unroll
-                for (int kk = 0; kk < AB_KB / 8; ++kk) {
+                for (int kk = 0; kk < 4; ++kk) {
                     const uint32_t acc = (kb | kk) ? 1u : 0u;
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem), "l"(umma_desc_sw128_mn(sx + kk * 1024)), "l"(umma_desc_sw128_mn(sy + kk * 1024)),
-                          "r"(idesc256), "r"(acc) : "memory");
-                    asm volatile(
-                        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                        ::"r"(tmem + 256), "l"(umma_desc_sw128_mn(sx + kk * 1024)), "l"(umma_desc_sw128_mn(so + kk * 1024)),
-                          "r"(idesc32), "r"(acc) : "memory");
+                    ad_umma<kElem>(tmem, ad_desc_mn<kElem>(sx + kk * Cf::KSTEP), ad_desc_mn<kElem>(sy + kk * Cf::KSTEP), 256, acc);
+                    ad_umma<kElem>(tmem + 256, ad_desc_mn<kElem>(sx + kk * Cf::KSTEP), ad_desc_mn<kElem>(so + kk * Cf::KSTEP), 32, acc);
                 }
                 umma_commit(&bar_empty[s]);
             }
@@ -525,8 +556,10 @@ extern "C" int dprnn_gemm_atb_tc_colsum(const float* A, long lda, const float* B
 // One pass over A for C1 (+)= A^T B1, C2 (+)= A^T shift_t(B2), colsum (+)= column sums of A (see atb_dual_kernel).
 // Rows are the chunk positions of a [B, S, K] batch: row = (b*S + s)*K + k.  inter = 0: sequences run along k (the intra-
 // chunk layer, time = k); inter = 1: along s (time = s).  shift in {-1, 0, +1}: B2 is read at time t + shift, zero outside.
-extern "C" int dprnn_gemm_atb_dual_supported(int N1, long lda, long ldb1, long ldb2) {
-    return N1 > 0 && N1 % 128 == 0 && N1 <= 4096 && lda % 32 == 0 && ldb1 % 32 == 0 && ldb2 % 32 == 0 && lda >= N1 &&
+// is_bf16: all three operands bf16 (leading dimensions in elements, multiples of 64), else fp32 read as TF32.
+extern "C" int dprnn_gemm_atb_dual_supported(int is_bf16, int N1, long lda, long ldb1, long ldb2) {
+    const int gc = is_bf16 ? 64 : 32;
+    return N1 > 0 && N1 % 128 == 0 && N1 <= 4096 && lda % gc == 0 && ldb1 % gc == 0 && ldb2 % gc == 0 && lda >= N1 &&
            ldb1 >= 128 && ldb2 >= 128;
 }
 
@@ -534,18 +567,21 @@ extern "C" size_t dprnn_gemm_atb_dual_workspace_bytes(int N1) {
     return (size_t)(148 + N1 / 128) * (size_t)AD_ROWS * 128 * sizeof(float);      // splits * tiles <= 148 (+ rounding)
 }
 
-extern "C" int dprnn_gemm_atb_dual(const float* A, long lda, int N1, const float* B1, long ldb1, const float* B2, long ldb2,
-                                   int B, int S, int K, int inter, int shift, float* C1, long ldc1, float* C2, long ldc2,
-                                   float* colsum, int accumulate, int accumulate_colsum, void* workspace, void* stream) {
+extern "C" int dprnn_gemm_atb_dual(const void* A, int is_bf16, long lda, int N1, const void* B1, long ldb1, const void* B2,
+                                   long ldb2, int B, int S, int K, int inter, int shift, float* C1, long ldc1, float* C2,
+                                   long ldc2, float* colsum, int accumulate, int accumulate_colsum, void* workspace,
+                                   void* stream) {
     DPRNN_CHECK_ARG(A && B1 && B2 && C1 && C2 && colsum && workspace && B > 0 && S > 0 && K > 0);
-    DPRNN_CHECK_ARG(dprnn_gemm_atb_dual_supported(N1, lda, ldb1, ldb2) && shift >= -1 && shift <= 1);
+    DPRNN_CHECK_ARG(dprnn_gemm_atb_dual_supported(is_bf16, N1, lda, ldb1, ldb2) && shift >= -1 && shift <= 1);
     DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)B1 | (uintptr_t)B2) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
     const int tiles = N1 / 128;
+    const int kb_rows = is_bf16 ? AdCfg<2>::KB : AdCfg<4>::KB, gcols = is_bf16 ? 64 : 32, g128 = is_bf16 ? 2 : 4;
+    const uint64_t el = is_bf16 ? 2 : 4;
     // d1 = k (unit row stride) in both layouts; intra: d2 = (b, s) flattened, time = d1; inter: d2 = s = time, d3 = b
     const uint64_t D1 = (uint64_t)K, D2 = inter ? (uint64_t)S : (uint64_t)B * S, D3 = inter ? (uint64_t)B : 1;
     AtbDualGeo g;
-    g.n1chunks = (int)((D1 + 31) / 32);
+    g.n1chunks = (int)((D1 + kb_rows - 1) / kb_rows);
     g.D2 = (int)D2;
     g.sh1 = inter ? 0 : shift;
     g.sh2 = inter ? shift : 0;
@@ -556,17 +592,19 @@ extern "C" int dprnn_gemm_atb_dual(const float* A, long lda, int N1, const float
     if (sp < 1) sp = 1;
     g.chunks_per_split = (g.total_chunks + sp - 1) / sp;
     const int splits = (int)((g.total_chunks + g.chunks_per_split - 1) / g.chunks_per_split);
-    auto make = [&](CUtensorMap* m, const float* base, long ld, int groups) {
-        const uint64_t d[5] = {32, D1, D2, D3, (uint64_t)groups};
-        const uint64_t sb[5] = {4, (uint64_t)ld * 4, (uint64_t)K * ld * 4, (uint64_t)S * K * ld * 4, 128};
-        const uint32_t bx[5] = {32, AB_KB, 1, 1, 4};
-        return make_tmap(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, d, sb, bx, CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
+    auto make = [&](CUtensorMap* m, const void* base, long ld, int groups) {
+        const uint64_t d[5] = {(uint64_t)gcols, D1, D2, D3, (uint64_t)groups};
+        const uint64_t sb[5] = {el, (uint64_t)ld * el, (uint64_t)K * ld * el, (uint64_t)S * K * ld * el, 128};
+        const uint32_t bx[5] = {(uint32_t)gcols, (uint32_t)kb_rows, 1, 1, (uint32_t)g128};
+        return make_tmap(m, is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, base, d, sb, bx,
+                         is_bf16 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B);
     };
     CUtensorMap tmA, tmB1, tmB2;
-    if (make(&tmA, A, lda, N1 / 32) || make(&tmB1, B1, ldb1, 4) || make(&tmB2, B2, ldb2, 4)) return 1;
-    const size_t smem = (size_t)AB_NST * (4 + AD_YG) * AB_GROUP + 1024;
-    DPRNN_CUDA(cudaFuncSetAttribute(atb_dual_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    atb_dual_kernel<<<dim3(tiles, splits), 192, smem, st>>>(tmA, tmB1, tmB2, g, tiles, (float*)workspace);
+    if (make(&tmA, A, lda, N1 / gcols) || make(&tmB1, B1, ldb1, g128) || make(&tmB2, B2, ldb2, g128)) return 1;
+    const size_t smem = is_bf16 ? AdCfg<2>::SMEM : AdCfg<4>::SMEM;
+    auto kern = is_bf16 ? atb_dual_kernel<2> : atb_dual_kernel<4>;
+    DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<dim3(tiles, splits), 192, smem, st>>>(tmA, tmB1, tmB2, g, tiles, (float*)workspace);
     DPRNN_CHECK_LAUNCH();
     const long total = (long)tiles * AD_ROWS * 128;
     atb_dual_reduce_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const float*)workspace, splits, tiles, C1, ldc1,

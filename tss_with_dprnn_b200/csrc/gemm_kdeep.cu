@@ -1,5 +1,5 @@
 // Deep-K tensor-core contraction of the training step's backward (cfg 5):
-//     C[M, 128] (+)= A[M, K] @ W[128, K]^T          A, W fp32 read as TF32, K a multiple of 32 (K = ndir * 4H = 1024)
+//     C[M, 128] (+)= A[M, K] @ W[128, K]^T          A, W fp32 read as TF32 (K % 32 == 0) or bf16 (K % 64 == 0); K = ndir * 4H = 1024
 // i.e. d x = d gates @ W_ih, the input gradient of an LSTM layer (backward of src/models/dprnn.py:51-70), accumulated
 // straight into the gradient of the residual stream.
 //
@@ -31,10 +31,17 @@ struct GemmKdeepArgs {
     unsigned* ticket;
 };
 
-__device__ __forceinline__ void kd_umma_tf32(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
-    asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                 "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
-                 ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+template <int kElem>
+__device__ __forceinline__ void kd_umma(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc, uint32_t acc) {
+    if constexpr (kElem == 2) {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    } else {
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+                     ::"r"(tmem_d), "l"(da), "l"(db), "r"(idesc), "r"(acc) : "memory");
+    }
 }
 __device__ __forceinline__ void kd_tma_store_2d(const CUtensorMap* m, const void* smem, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
@@ -45,6 +52,7 @@ __device__ __forceinline__ void kd_tma_reduce_add_2d(const CUtensorMap* m, const
                  ::"l"(m), "r"(smem_u32(smem)), "r"(c0), "r"(c1) : "memory");
 }
 
+template <int kElem>      // 4: fp32 operands read as TF32, 2: bf16
 __global__ void __launch_bounds__(192, 1) gemm_kdeep_kernel(const __grid_constant__ CUtensorMap tmA,
                                                             const __grid_constant__ CUtensorMap tmW,
                                                             const __grid_constant__ CUtensorMap tmC,
@@ -86,16 +94,17 @@ __global__ void __launch_bounds__(192, 1) gemm_kdeep_kernel(const __grid_constan
                     const int s = it % NST;
                     mbar_wait(&empty[s], ((it / NST) & 1) ^ 1);
                     mbar_expect_tx(&full[s], STAGE);
-                    tma_load_2d(smem + s * STAGE, &tmA, &full[s], kb * 32, tile * 256);         // [256 rows x 32 k]
-                    tma_load_2d(smem + s * STAGE + 2 * BLK, &tmW, &full[s], kb * 32, 0);        // [128 rows x 32 k]
+                    tma_load_2d(smem + s * STAGE, &tmA, &full[s], kb * (128 / kElem), tile * 256);         // [256 rows x 128 B]
+                    tma_load_2d(smem + s * STAGE + 2 * BLK, &tmW, &full[s], kb * (128 / kElem), 0);        // [128 rows x 128 B]
                 }
             }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
-            // kind::tf32, fp32 accumulation, both operands K-major, M = 128, N = 128
-            constexpr uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+            // fp32 accumulation, both operands K-major, M = 128, N = 128; operand format TF32 = 2, BF16 = 1
+            constexpr uint32_t fmt = kElem == 2 ? 1u : 2u;
+            constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
             int it = 0;
             for (int n = 0;; ++n) {
                 const int qs = n % TQ;
@@ -115,7 +124,7 @@ __global__ void __launch_bounds__(192, 1) gemm_kdeep_kernel(const __grid_constan
                     for (int sub = 0; sub < 2; ++sub)
 #pragma unroll
                         for (int kk = 0; kk < 4; ++kk)
-                            kd_umma_tf32(tmem + (uint32_t)(acc * 2 + sub) * N, umma_desc_sw128(sa + sub * BLK + kk * 32),
+                            kd_umma<kElem>(tmem + (uint32_t)(acc * 2 + sub) * N, umma_desc_sw128(sa + sub * BLK + kk * 32),
                                          umma_desc_sw128(sb + kk * 32), idesc, (kb | kk) ? 1u : 0u);
                     umma_commit(&empty[s]);
                 }
@@ -178,32 +187,37 @@ using namespace dprnn;
 
 extern "C" size_t dprnn_gemm_kdeep_workspace_bytes(void) { return 256; }
 
-extern "C" int dprnn_gemm_kdeep_supported(int N, int K, long lda, long ldc) {
-    return N == 128 && K >= 32 && K % 32 == 0 && lda % 4 == 0 && lda >= K && ldc % 4 == 0 && ldc >= N;
+extern "C" int dprnn_gemm_kdeep_supported(int a_is_bf16, int N, int K, long lda, long ldc) {
+    const int kblk = a_is_bf16 ? 64 : 32;
+    return N == 128 && K >= kblk && K % kblk == 0 && lda % (a_is_bf16 ? 8 : 4) == 0 && lda >= K && ldc % 4 == 0 && ldc >= N;
 }
 
-extern "C" int dprnn_gemm_kdeep(const float* A, long lda, const float* W, float* C, long ldc, int M, int N, int K,
-                                int accumulate, void* workspace, void* stream) {
-    DPRNN_CHECK_ARG(A && W && C && workspace && M > 0 && dprnn_gemm_kdeep_supported(N, K, lda, ldc));
+extern "C" int dprnn_gemm_kdeep(const void* A, int a_is_bf16, long lda, const void* W, float* C, long ldc, int M, int N,
+                                int K, int accumulate, void* workspace, void* stream) {
+    DPRNN_CHECK_ARG(A && W && C && workspace && M > 0 && dprnn_gemm_kdeep_supported(a_is_bf16, N, K, lda, ldc));
     DPRNN_CHECK_ARG(((uintptr_t)A | (uintptr_t)W | (uintptr_t)C | (uintptr_t)workspace) % 16 == 0);
     cudaStream_t st = (cudaStream_t)stream;
+    const uint64_t el = a_is_bf16 ? 2 : 4;
+    const uint32_t kblk = a_is_bf16 ? 64 : 32;
+    const CUtensorMapDataType dt = a_is_bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
     CUtensorMap tmA, tmW, tmC;
-    const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {4, (uint64_t)lda * 4};
-    const uint32_t bA[2] = {32, 256};
-    const uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}, sW[2] = {4, (uint64_t)K * 4};
-    const uint32_t bW[2] = {32, (uint32_t)N};
+    const uint64_t dA[2] = {(uint64_t)K, (uint64_t)M}, sA[2] = {el, (uint64_t)lda * el};
+    const uint32_t bA[2] = {kblk, 256};
+    const uint64_t dW[2] = {(uint64_t)K, (uint64_t)N}, sW[2] = {el, (uint64_t)K * el};
+    const uint32_t bW[2] = {kblk, (uint32_t)N};
     const uint64_t dC[2] = {(uint64_t)N, (uint64_t)M}, sC[2] = {4, (uint64_t)ldc * 4};
     const uint32_t bC[2] = {32, 128};
-    if (make_tmap(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, A, dA, sA, bA)) return 1;
-    if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, W, dW, sW, bW)) return 1;
+    if (make_tmap(&tmA, dt, 2, A, dA, sA, bA)) return 1;
+    if (make_tmap(&tmW, dt, 2, W, dW, sW, bW)) return 1;
     if (make_tmap(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, C, dC, sC, bC)) return 1;
-    DPRNN_CUDA(cudaFuncSetAttribute(gemm_kdeep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kd::SMEM));
+    auto kern = a_is_bf16 ? gemm_kdeep_kernel<2> : gemm_kdeep_kernel<4>;
+    DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kd::SMEM));
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    GemmKdeepArgs args{M, (int)cdiv(M, 256), K / 32, accumulate ? 1 : 0, (unsigned*)workspace};
+    GemmKdeepArgs args{M, (int)cdiv(M, 256), K / (int)kblk, accumulate ? 1 : 0, (unsigned*)workspace};
     DPRNN_CUDA(cudaMemsetAsync(args.ticket, 0, sizeof(unsigned), st));
-    gemm_kdeep_kernel<<<args.tiles < sms ? args.tiles : sms, 192, kd::SMEM, st>>>(tmA, tmW, tmC, args);
+    kern<<<args.tiles < sms ? args.tiles : sms, 192, kd::SMEM, st>>>(tmA, tmW, tmC, args);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

@@ -18,6 +18,11 @@
 //     that unit-half (the MMAs of half 0 overlap the element-wise work of half 1) | commit -> D[cur]   (TMEM ping-pong)
 // K index = gate*128 + unit, i.e. K-block kb = 2*gate + unit_half: W_hh^T needs no permutation.
 //
+// kOutBf16: d gates leaves as bf16 [rows, ndir*4H] - exactly the A tile the step has just built for the tensor core: one
+// warp stores its 8 K-blocks with TMA (box = [rows of the tile x 64 columns], rows past the last sequence are clipped)
+// instead of sixteen warps issuing fp32 vector stores.  Half the bytes for this kernel and for the three passes that read
+// d gates afterwards (d x and the weight gradients, which consume bf16 operands: gemm_kdeep.cu, atb_tc.cu).
+//
 // kRows = 64 (small batches: at 16 utterances per GPU the 256-sequence tiles give 52..64 CTAs for 148 SMs, and the step is
 // bound by the latency of the streamed loads, not by their bandwidth): the pair owns 128 sequences, 64 per CTA, and the
 // MMA is the cta_group::2 M = 128 shape.  Its accumulator has the "2x2" layout - TMEM lanes 0..63 hold units 0..63 of the
@@ -47,9 +52,13 @@ struct LstmBpttTcParams {
     const uint2* gates;    // activations i,f,g,o as bf16, packed [rows][ndir][16 chunks of 8 units][4 gates][8] (the
                            // layout dprnn_lstm_layer_bf16_train writes); one uint2 = 4 units of one gate
     const float* cstate;   // [rows, ndir*H]
-    float* dgates;         // [rows, ndir*4H]
-    long nseq; int T;
-    int seq_div; long seq_outer, seq_inner, step_stride;
+    float* dgates;         // [rows, ndir*4H] fp32 (kOutBf16: unused - the bf16 output leaves through the tensor map)
+    int T;
+    // sequences are tiled per OUTER index (intra-chunk layer: one outer, the B*S sequences; inter-chunk: one outer per
+    // utterance, its K sequences), so that a tile's rows are one box of the output tensor map; row of (outer, n, t) =
+    // outer * seq_outer + n * seq_inner + t * step_stride
+    int limit, tiles_per_outer;
+    long seq_outer, seq_inner, step_stride;
     int ndir;
 };
 
@@ -82,11 +91,16 @@ __device__ __forceinline__ uint32_t bptt_map_to_cta(uint32_t addr, uint32_t cta)
 __device__ __forceinline__ void bptt_arrive_remote(uint32_t cluster_addr) {
     asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+__device__ __forceinline__ void bptt_tma_store_4d(const CUtensorMap* m, const void* smem, int c0, int c1, int c2, int c3) {
+    asm volatile("cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5}], [%1];"
+                 ::"l"(m), "r"(smem_u32(smem)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
 __device__ __forceinline__ void bptt_named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
-template <bool kFastAct, int kRows>
+template <bool kFastAct, int kRows, bool kOutBf16>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + 32 * bptt::NEW, 1)
-lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcParams p) {
+lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmDG,
+                    const LstmBpttTcParams p) {
     using namespace bptt;
     static_assert(kRows == 128 || kRows == 64, "rows per CTA");
     constexpr int NPH = kRows == 128 ? 2 : 1;          // unit-halves a warp differentiates
@@ -98,13 +112,17 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
     uint64_t* d_full = bars + 1;              // MMAs of the step complete (multicast commit, both CTAs)
     uint64_t* a_ready = bars + 2;             // [2] (leader's copy) A K-blocks of unit-half p written by both CTAs
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+    uint64_t* a_local = bars + 5;             // [2] kOutBf16: this CTA's warps have written unit-half p of the A tile
+    uint64_t* a_free = bars + 7;              // kOutBf16: the bulk stores of the step have read the A tile
     float* stg = reinterpret_cast<float*>(smem + SM_STG);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = bptt_cluster_ctarank();
     const int job = blockIdx.x >> 1;
     const int dir = job % p.ndir;
-    const long n0 = (long)(job / p.ndir) * (2 * kRows) + (long)rank * kRows;
+    const int jt = job / p.ndir;
+    const int outer = jt / p.tiles_per_outer;
+    const int n0 = (jt % p.tiles_per_outer) * (2 * kRows) + (int)rank * kRows;      // first sequence of this CTA inside `outer`
     const int T = p.T;
 
     if (threadIdx.x == 0) {
@@ -117,6 +135,9 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
         mbar_init(d_full, 1);
         // one elected lane per element-wise warp that writes the unit-half, both CTAs
         mbar_init(&a_ready[0], 2 * NEW / (3 - NPH)); mbar_init(&a_ready[1], 2 * NEW / (3 - NPH));
+        mbar_init(&a_local[0], NEW / (3 - NPH)); mbar_init(&a_local[1], NEW / (3 - NPH));
+        mbar_init(a_free, 1);
+        if constexpr (kOutBf16) prefetch_tmap(&tmDG);
         fence_barrier_init();
     }
     if (warp == 2) tmem_alloc<2>(tmem_slot, 256);
@@ -157,6 +178,27 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
             }
         }
         __syncwarp();
+    } else if (kOutBf16 && warp == 3) {
+        // ================= d gates of the step: the A tile, as it is, to global memory (bf16) =================
+        if (elect_one()) {
+            for (int s = 0; s < T; ++s) {
+                const int fstep = T - 1 - s;
+                const int t = dir ? T - 1 - fstep : fstep;
+                for (int half = 0; half < 2; ++half) {
+                    mbar_wait(&a_local[half], s & 1);
+#pragma unroll
+                    for (int q4 = 0; q4 < 4; ++q4) {
+                        const int kb = q4 * 2 + half;
+                        bptt_tma_store_4d(&tmDG, smem + SM_A + kb * A_TILE, dir * G4 + kb * 64, n0, t, outer);
+                    }
+                }
+                asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                mbar_arrive(a_free);
+            }
+            asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+        }
+        __syncwarp();
     } else if (warp >= 4) {
         // ================= element-wise backward of the cell =================
         // warp -> TMEM lane quadrant q (= warp % 4, the only lanes it may read) and the wq-th group of 2*ITS rows inside it:
@@ -172,9 +214,9 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
         bool ok[ITS];
 #pragma unroll
         for (int it = 0; it < ITS; ++it) {
-            const long n = n0 + rq + it * 2 + hw;
-            ok[it] = n < p.nseq;
-            base[it] = ok[it] ? (int)((n / p.seq_div) * p.seq_outer + (n % p.seq_div) * p.seq_inner) : 0;
+            const int n = n0 + rq + it * 2 + hw;
+            ok[it] = n < p.limit;
+            base[it] = ok[it] ? (int)((long)outer * p.seq_outer + (long)n * p.seq_inner) : 0;
         }
         float dc[NPH][ITS][4];
         float4 ckeep[kKeepC ? ITS : 1];                      // kKeepC: c_{t-1} of this step = c_t of the next
@@ -242,6 +284,7 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
             if (s > 0) {
                 mbar_wait(d_full, (s - 1) & 1);
                 tc_fence_after();
+                if constexpr (kOutBf16) mbar_wait(a_free, (s - 1) & 1);      // ... and its bulk stores have read the A tile
             }
 #pragma unroll
             for (int pi = 0; pi < NPH; ++pi) {
@@ -299,14 +342,14 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                         dpg[u] = dct * ia[u] * (1.f - ga[u] * ga[u]);
                         dc[pi][it][u] = dct * fa[u];
                     }
-                    if (ok[it]) {
+                    if (!kOutBf16 && ok[it]) {
                         float* o = p.dgates + rowi * ldg + dir * G4 + u0;
                         st_stream4(o, dpi[0], dpi[1], dpi[2], dpi[3]);
                         st_stream4(o + H, dpf[0], dpf[1], dpf[2], dpf[3]);
                         st_stream4(o + 2 * H, dpg[0], dpg[1], dpg[2], dpg[3]);
                         st_stream4(o + 3 * H, dpo[0], dpo[1], dpo[2], dpo[3]);
                     }
-                    if (fstep > 0) {
+                    if (kOutBf16 || fstep > 0) {
                         // A operand: K-block kb = 2*gate + ph, column (unit % 64) -> 16-byte chunk l16/2, byte (l16&1)*8
                         const uint32_t off = sw128_offset((uint32_t)row, (uint32_t)(l16 >> 1)) + (uint32_t)(l16 & 1) * 8;
                         uint8_t* at = smem + SM_A + ph * A_TILE + off;
@@ -321,10 +364,13 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
                     }
                     cur = nxt;
                 }
-                if (fstep > 0) {
-                    fence_async_smem();                       // generic-proxy writes of the A tile -> visible to tcgen05.mma
+                if (kOutBf16 || fstep > 0) {
+                    fence_async_smem();                       // generic-proxy writes of the A tile -> visible to tcgen05.mma / TMA
                     __syncwarp();
-                    if (lane == 0) bptt_arrive_remote(leader_ready + ph * 8);
+                    if (lane == 0) {
+                        if (fstep > 0) bptt_arrive_remote(leader_ready + ph * 8);
+                        if constexpr (kOutBf16) mbar_arrive(&a_local[ph]);
+                    }
                 }
             }
         }
@@ -340,36 +386,72 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const LstmBpttTcPar
 using namespace dprnn;
 
 // whhT_bf16: [ndir][H = 128 output columns j][4H = 512 gate rows k] bf16 = W_hh^T per direction (k = gate*128 + unit)
-extern "C" int dprnn_lstm_bptt_tc(const float* dh_out, const void* gates, const float* cstate, const void* whhT_bf16,
-                                  float* dgates, long nseq, int T, long seq_div, long seq_outer_stride,
-                                  long seq_inner_stride, long step_stride, int hidden, int ndir, int fast_act,
-                                  void* stream) {
-    DPRNN_CHECK_ARG(dh_out && gates && cstate && whhT_bf16 && dgates && nseq > 0 && T > 0 && seq_div > 0);
-    DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2) && seq_div < (1L << 31));
-    DPRNN_CHECK_ARG(((uintptr_t)dh_out | (uintptr_t)gates | (uintptr_t)cstate | (uintptr_t)whhT_bf16 | (uintptr_t)dgates) % 16 == 0);
+static int bptt_tc_impl(const float* dh_out, const void* gates, const float* cstate, const void* whhT_bf16, float* dgates,
+                        void* dgates_bf16, long nseq, int T, long seq_div, long seq_outer_stride, long seq_inner_stride,
+                        long step_stride, int hidden, int ndir, int fast_act, void* stream) {
+    DPRNN_CHECK_ARG(dh_out && gates && cstate && whhT_bf16 && (dgates || dgates_bf16) && nseq > 0 && T > 0 && seq_div > 0);
+    DPRNN_CHECK_ARG(hidden == 128 && (ndir == 1 || ndir == 2) && seq_div < (1L << 31) && nseq < (1L << 31));
+    DPRNN_CHECK_ARG(((uintptr_t)dh_out | (uintptr_t)gates | (uintptr_t)cstate | (uintptr_t)whhT_bf16 | (uintptr_t)dgates |
+                     (uintptr_t)dgates_bf16) % 16 == 0);
     // row indices are kept as int32 inside the kernel
     const long max_row = ((nseq - 1) / seq_div) * seq_outer_stride + ((nseq - 1) % seq_div) * seq_inner_stride +
                          (long)(T - 1) * step_stride;
     DPRNN_CHECK_ARG(max_row < (1L << 31));
-    CUtensorMap tmW;
+    // tiles per outer index: seq_div == 1 -> one outer holding all sequences (row = n * seq_outer_stride + t * step_stride),
+    // else nseq / seq_div outers of seq_div sequences each
+    DPRNN_CHECK_ARG(nseq % seq_div == 0);
+    const long limit = seq_div == 1 ? nseq : seq_div, n_outer = seq_div == 1 ? 1 : nseq / seq_div;
+    const long sn = seq_div == 1 ? seq_outer_stride : seq_inner_stride, so = seq_div == 1 ? 0 : seq_outer_stride;
+    CUtensorMap tmW, tmDG;
     const uint64_t dW[2] = {512, (uint64_t)ndir * 128}, sW[2] = {2, 1024};
     const uint32_t bW[2] = {64, 64};
     if (make_tmap(&tmW, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, whhT_bf16, dW, sW, bW)) return 1;
-    LstmBpttTcParams p{dh_out, (const uint2*)gates, cstate, dgates, nseq, T, (int)seq_div, seq_outer_stride, seq_inner_stride, step_stride, ndir};
     // small batches: 64 rows per CTA when the 128-sequence pair tiles still fit the CTA pairs in one wave (the rule of the
     // forward kernel, lstm_tc_pp.cu); DPRNN_LSTM_HALF_TILES / DPRNN_LSTM_FULL_TILES in `fast_act` force the choice
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long jobs128 = (nseq + 127) / 128 * ndir;
+    const long jobs128 = (limit + 127) / 128 * n_outer * ndir;
     const bool half = (fast_act & DPRNN_LSTM_HALF_TILES) || (!(fast_act & DPRNN_LSTM_FULL_TILES) && jobs128 <= sms / 2);
-    const long njobs = half ? jobs128 : (nseq + 255) / 256 * ndir;
+    const int tile = half ? 128 : 256;
+    const long tpo = (limit + tile - 1) / tile, njobs = tpo * n_outer * ndir;
     DPRNN_CHECK_ARG(njobs * 2 < (1L << 31));
-    const bool fa = fast_act & DPRNN_LSTM_FAST_ACT;
-    auto kern = half ? (fa ? lstm_bptt_tc_kernel<true, 64> : lstm_bptt_tc_kernel<false, 64>)
-                     : (fa ? lstm_bptt_tc_kernel<true, 128> : lstm_bptt_tc_kernel<false, 128>);
+    tmDG = tmW;
+    if (dgates_bf16) {      // [rows, ndir*512] bf16 addressed as (column, sequence inside the outer, time, outer)
+        const uint64_t ld = (uint64_t)ndir * 512 * 2;
+        const uint64_t dG[4] = {(uint64_t)ndir * 512, (uint64_t)limit, (uint64_t)T, (uint64_t)n_outer};
+        const uint64_t sG[4] = {2, (uint64_t)sn * ld, (uint64_t)step_stride * ld, (uint64_t)(so ? so : 1) * ld};
+        const uint32_t bG[4] = {64, (uint32_t)(tile / 2), 1, 1};
+        if (make_tmap(&tmDG, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, dgates_bf16, dG, sG, bG)) return 1;
+    }
+    LstmBpttTcParams p{dh_out, (const uint2*)gates, cstate, dgates, T, (int)limit, (int)tpo, so, sn, step_stride, ndir};
+    const bool fa = fast_act & DPRNN_LSTM_FAST_ACT, ob = dgates_bf16 != nullptr;
+    auto kern = half ? (ob ? (fa ? lstm_bptt_tc_kernel<true, 64, true> : lstm_bptt_tc_kernel<false, 64, true>)
+                           : (fa ? lstm_bptt_tc_kernel<true, 64, false> : lstm_bptt_tc_kernel<false, 64, false>))
+                     : (ob ? (fa ? lstm_bptt_tc_kernel<true, 128, true> : lstm_bptt_tc_kernel<false, 128, true>)
+                           : (fa ? lstm_bptt_tc_kernel<true, 128, false> : lstm_bptt_tc_kernel<false, 128, false>));
     DPRNN_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bptt::SM_TOTAL));
-    kern<<<(unsigned)(njobs * 2), 128 + 32 * bptt::NEW, bptt::SM_TOTAL, (cudaStream_t)stream>>>(tmW, p);
+    kern<<<(unsigned)(njobs * 2), 128 + 32 * bptt::NEW, bptt::SM_TOTAL, (cudaStream_t)stream>>>(tmW, tmDG, p);
     DPRNN_CHECK_LAUNCH();
     return 0;
+}
+
+extern "C" int dprnn_lstm_bptt_tc(const float* dh_out, const void* gates, const float* cstate, const void* whhT_bf16,
+                                  float* dgates, long nseq, int T, long seq_div, long seq_outer_stride,
+                                  long seq_inner_stride, long step_stride, int hidden, int ndir, int fast_act,
+                                  void* stream) {
+    DPRNN_CHECK_ARG(dgates);
+    return bptt_tc_impl(dh_out, gates, cstate, whhT_bf16, dgates, nullptr, nseq, T, seq_div, seq_outer_stride,
+                        seq_inner_stride, step_stride, hidden, ndir, fast_act, stream);
+}
+
+// d gates as bf16 [rows, ndir*4H] (stored by TMA from the tile the tensor core reads): the operand format of
+// dprnn_gemm_kdeep (d x) and dprnn_gemm_atb_dual (weight gradients) in their bf16 forms
+extern "C" int dprnn_lstm_bptt_tc_bf16out(const float* dh_out, const void* gates, const float* cstate, const void* whhT_bf16,
+                                          void* dgates_bf16, long nseq, int T, long seq_div, long seq_outer_stride,
+                                          long seq_inner_stride, long step_stride, int hidden, int ndir, int fast_act,
+                                          void* stream) {
+    DPRNN_CHECK_ARG(dgates_bf16);
+    return bptt_tc_impl(dh_out, gates, cstate, whhT_bf16, nullptr, dgates_bf16, nseq, T, seq_div, seq_outer_stride,
+                        seq_inner_stride, step_stride, hidden, ndir, fast_act, stream);
 }

@@ -7,10 +7,11 @@ caller (asteroid's PIT / SI-SDR wrapper + CrossEntropyLoss in the reference trai
 as ONE ``torch.autograd.Function``: forward -> (est, logits), backward(d_est, d_logits) -> parameter gradients;
 ``SpeTrainStep`` runs the whole iteration (loss kernel, all-reduce, fused clip + Adam) as device work.
 
-Memory: per half-block the forward keeps the LSTM gates / cell state / output and the Linear output (13 A, A = one
-[B,S,K,128] fp32 tensor = 0.40 GB at B = 16); the block inputs are NOT kept - the residual stream is reversible
-(x_in = x_out - norm(y)), so the backward walks it back while it walks the blocks in reverse (which is also why a forward
-can be differentiated only once).
+Memory: per half-block the forward keeps the LSTM gates / cell state / output, the Linear output and the half-block's
+input (14 A, A = one [B,S,K,128] fp32 tensor = 0.40 GB at B = 16).  With DPRNN_TRAIN_KEEP_INPUTS=0 the inputs are not kept:
+the residual stream is reversible (x_in = x_out - norm(y)), and the backward walks it back while it walks the blocks in
+reverse, at the price of one more pass over it per half-block.  Either way a forward can be differentiated only once
+(the saved activations are freed as the backward consumes them).
 
 Supported: DPRNNTasNet and DPRNNSpeTasNet with fusion_type in {film, add, mul, cat, att}, 'ln' / 'gLN' norms, sigmoid /
 relu mask activation, uni- or bidirectional inter-RNN, kernel_size 2 / stride 1, feature_size = hidden_size = 128; frozen
@@ -32,6 +33,9 @@ EPI_NONE, EPI_RELU, EPI_SIGMOID, EPI_GATED = 0, 1, 2, 3
 # experiments: 4 / 8 force 64 / 128 rows per CTA in the BPTT kernel (include/dprnn_b200.h: DPRNN_LSTM_HALF_TILES / _FULL_TILES)
 _BPTT_FLAGS = int(os.environ.get('DPRNN_BPTT_FLAGS', '0')) & 12
 # 4 / 8 likewise for the training forward, 16 = DPRNN_LSTM_DIRECT_SAVE (saved activations stored from the registers)
+# 1 (default): the forward keeps every half-block's input (0.4 GB each at 16 x 3 s; 12 of them) and the backward reads it;
+# 0: the forward updates the residual stream in place and the backward recomputes x_in = x_out - norm(y) (one more pass)
+_KEEP_INPUTS = os.environ.get('DPRNN_TRAIN_KEEP_INPUTS', '1') != '0'
 _SKIP_SIDE = os.environ.get('DPRNN_TRAIN_SKIP_SIDE', '0') == '1'
 _FWD_FLAGS = int(os.environ.get('DPRNN_TRAIN_LSTM_FLAGS', '0')) & 28
 
@@ -51,6 +55,8 @@ class _Ops:
         self._gp_ws = {}                # its ticket word, one per stream (launches of two streams may overlap)
         self.dual = os.environ.get('DPRNN_TRAIN_DUAL', '1') != '0'           # dW_ih, dW_hh, db from one pass over d gates
         self.kdeep = os.environ.get('DPRNN_TRAIN_KDEEP', '1') != '0'         # d x = d gates @ W_ih accumulated in place
+        # d gates in bf16 (what the BPTT's tensor-core tile holds anyway): d x and the weight gradients read bf16 operands
+        self.dg16 = tf32 and self.dual and self.kdeep and os.environ.get('DPRNN_TRAIN_DG16', '1') != '0'
 
     def empty(self, *shape):
         return torch.empty(shape, device=self.dev, dtype=torch.float32)
@@ -87,14 +93,16 @@ class _Ops:
         return out
 
     def mm_acc(self, A, W, M, N, K, out):
-        """out[M,N] += A[M,K] @ W[N,K]^T in one pass (deep-K kernel, csrc/gemm_kdeep.cu); False when it does not apply."""
-        if not (self.tf32 and self.kdeep and M >= 256 and self.L.query('dprnn_gemm_kdeep_supported', N, K, K, N)):
+        """out[M,N] += A[M,K] @ W[N,K]^T in one pass (deep-K kernel, csrc/gemm_kdeep.cu); A and W fp32 (TF32) or both bf16;
+        False when it does not apply."""
+        bf = int(A.dtype == torch.bfloat16)
+        if not (self.tf32 and self.kdeep and M >= 256 and self.L.query('dprnn_gemm_kdeep_supported', bf, N, K, K, N)):
             return False
         ws = self._gp_ws.get(('kd', _st()))
         if ws is None:
             ws = self._gp_ws[('kd', _st())] = torch.empty(self.L.query('dprnn_gemm_kdeep_workspace_bytes'), device=self.dev,
                                                           dtype=torch.uint8)
-        self.L.call('dprnn_gemm_kdeep', A, K, W, out, N, M, N, K, 1, ws, _st())
+        self.L.call('dprnn_gemm_kdeep', A, bf, K, W, out, N, M, N, K, 1, ws, _st())
         return True
 
     def atb(self, A, B, M, N1, N2, out, lda=None, ldb=None, ldc=None, accumulate=True):
@@ -115,16 +123,16 @@ class _Ops:
         self.L.call('dprnn_gemm_atb_tc_colsum', A, lda or N1, B, ldb or N2, out, N2, colsum, M, N1, N2, 1, 0, ws, _st())
         return True
 
-    def atb_dual(self, A, lda, N1, B1, ldb1, B2, ldb2, B, S, K, inter, shift, C1, ldc1, C2, ldc2, colsum):
+    def atb_dual(self, A, lda, N1, B1, ldb1, B2, ldb2, B, S, K, inter, shift, C1, ldc1, C2, ldc2, colsum, bf16=False):
         """C1[N1,128] += A^T B1, C2[N1,128] += A^T shift_t(B2) and colsum[N1] = column sums of A in ONE pass over A
-        (csrc/atb_tc.cu: atb_dual_kernel; rows addressed as (time, sequence), so the time shift costs no copy); False
-        when the kernel does not apply."""
+        (csrc/atb_tc.cu: atb_dual_kernel; rows addressed as (time, sequence), so the time shift costs no copy); operands
+        fp32 (TF32) or all bf16; False when the kernel does not apply."""
         if not (self.tf32 and self.dual and B * S * K >= 4096
-                and self.L.query('dprnn_gemm_atb_dual_supported', N1, lda, ldb1, ldb2)):
+                and self.L.query('dprnn_gemm_atb_dual_supported', int(bf16), N1, lda, ldb1, ldb2)):
             return False
         ws = torch.empty(self.L.query('dprnn_gemm_atb_dual_workspace_bytes', N1), device=self.dev, dtype=torch.uint8)
-        self.L.call('dprnn_gemm_atb_dual', A, lda, N1, B1, ldb1, B2, ldb2, B, S, K, int(inter), int(shift), C1, ldc1, C2, ldc2,
-                    colsum, 1, 0, ws, _st())
+        self.L.call('dprnn_gemm_atb_dual', A, int(bf16), lda, N1, B1, ldb1, B2, ldb2, B, S, K, int(inter), int(shift), C1, ldc1,
+                    C2, ldc2, colsum, 1, 0, ws, _st())
         return True
 
     def colsum(self, X, M, N, out, Y=None, ldx=None, accumulate=True):
@@ -311,6 +319,10 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
     # ---- DPRNN blocks (dprnn.py:79-99)
     halves = []
     xb_next, n_half = None, 0
+    # bf16 d gates in the backward: its weight-gradient pass reads the bf16 x and h this forward works on (kept), and the
+    # half-block inputs need neither be kept in fp32 nor be recomputed
+    dg16 = ops.dg16 and F == 128 and H == 128 and rows >= 4096
+    xb = hb = None
     for blk in sep.dprnn_blocks:
         for which, (rnn, linm, nm) in enumerate(((blk.intra_rnn.rnn, blk.intra_linear, blk.intra_norm),
                                                  (blk.inter_rnn.rnn, blk.inter_linear, blk.inter_norm))):
@@ -336,7 +348,8 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
                 hb = torch.empty((rows, nd * H), device=dev, dtype=torch.bfloat16)
                 L_.call('dprnn_lstm_layer_bf16_train_pp' if pp else 'dprnn_lstm_layer_bf16_train', xb, wp, bp, hb, gates,
                         cst, hout, B, S, K, which, H, nd, int(model._engine.fast_act) | (_FWD_FLAGS if pp else 0), st)
-                del xb, hb
+                if not dg16:
+                    xb = hb = None
             else:
                 gx = ops.mm(xs, wih, rows, nd * 4 * H, F, bias=b)
                 L_.call('dprnn_lstm_recurrence_f32_train', gx, whh.transpose(1, 2).contiguous(), hout, gates, cst, *geo, H, nd, st)
@@ -347,10 +360,16 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
             n_half += 1
             xb_next = (torch.empty((rows, F), device=dev, dtype=torch.bfloat16)
                        if ops.tf32 and n_half < 2 * len(sep.dprnn_blocks) else None)      # the next LSTM's bf16 operand
-            L_.call('dprnn_norm_residual', yl, xs, mr, g_.detach(), b_.detach(), B, S * K, F, xb_next, st)
+            x_in = None
+            if _KEEP_INPUTS and not dg16:       # x_out goes to a new buffer and the half-block's input stays for the backward (dW_ih)
+                x_in, xs = xs, torch.empty_like(xs)
+                L_.call('dprnn_norm_residual_to', yl, x_in, mr, g_.detach(), b_.detach(), B, S * K, F, xs, xb_next, st)
+            else:                  # in place: the backward walks the (reversible) residual stream back, x_in = x_out - norm(y)
+                L_.call('dprnn_norm_residual', yl, xs, mr, g_.detach(), b_.detach(), B, S * K, F, xb_next, st)
             halves.append(dict(nd=nd, geo=geo, hout=hout, gates=gates, cst=cst, yl=yl, mr=mr, wih=wih, whh=whh,
-                               rnn=rnn, lin=linm, norm=nm, sfx=sfx, which=which))
-    c.update(halves=halves, xs=xs)
+                               rnn=rnn, lin=linm, norm=nm, sfx=sfx, which=which, x_in=x_in,
+                               xb=xb if dg16 else None, hb=hb if dg16 else None))
+    c.update(halves=halves, xs=xs, dg16=dg16)
 
     # ---- PReLU, overlap-add, conv2d, gated head, end conv + activation (dprnn_spe.py:231-248)
     z = ops.empty(B, Lm, F)
@@ -589,10 +608,16 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
         pn = names[id(hv['norm'])]
         gname = pn + ('.gamma' if hasattr(hv['norm'], 'gamma') else '.weight')
         bname = pn + ('.beta' if hasattr(hv['norm'], 'gamma') else '.bias')
-        xs_out, xs = xs, torch.empty_like(xs)
-        L_.call('dprnn_norm_residual_to', yl, xs_out, mr, (-g_.detach()).contiguous(), (-b_.detach()).contiguous(), B, S * K,
-                F, xs, None, st)                                     # xs: x_in = x_out - norm(y)
-        del xs_out
+        dg16 = c['dg16']
+        if dg16:
+            pass                                                     # the weight gradients read the kept bf16 input
+        elif hv['x_in'] is not None:
+            xs, hv['x_in'] = hv['x_in'], None                        # the half-block's input, kept by the forward
+        else:
+            xs_out, xs = xs, torch.empty_like(xs)
+            L_.call('dprnn_norm_residual_to', yl, xs_out, mr, (-g_.detach()).contiguous(), (-b_.detach()).contiguous(), B,
+                    S * K, F, xs, None, st)                          # xs: x_in = x_out - norm(y)
+            del xs_out
         dy = ops.gn_bwd(dx, yl, mr, g_.detach(), B, S * K, F, G[gname], G[bname])
         ln = names[id(hv['lin'])]
         hout = hv['hout']
@@ -610,17 +635,29 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
         on_side(lin_grads, dy, hout)
         dh = ops.mm(dy, hv['lin'].weight.detach().t().contiguous(), rows, nd * H, F)
         del dy
-        dgates = ops.empty(rows, nd * 4 * H)
+        dgates = torch.empty((rows, nd * 4 * H), device=dev, dtype=torch.bfloat16 if dg16 else torch.float32)
         if ops.tf32:
             whhT = hv['whh'].transpose(1, 2).contiguous().to(torch.bfloat16)              # [nd, H, 4H]
-            L_.call('dprnn_lstm_bptt_tc', dh, hv['gates'], hv['cst'], whhT, dgates, *geo, H, nd,
-                    int(model._engine.fast_act) | _BPTT_FLAGS, st)
+            L_.call('dprnn_lstm_bptt_tc_bf16out' if dg16 else 'dprnn_lstm_bptt_tc', dh, hv['gates'], hv['cst'], whhT, dgates,
+                    *geo, H, nd, int(model._engine.fast_act) | _BPTT_FLAGS, st)
         else:
             L_.call('dprnn_lstm_bptt_f32', dh, hv['gates'], hv['cst'], hv['whh'], dgates, *geo, H, nd, st)
         del dh
         rn = names[id(hv['rnn'])]
 
-        def rnn_grads(dgates=dgates, hout=hout, rn=rn, nd=nd, geo=geo, sfx=hv['sfx'], xs=xs, which=hv['which']):
+        def rnn_grads(dgates=dgates, hout=hout, rn=rn, nd=nd, geo=geo, sfx=hv['sfx'], xs=xs, which=hv['which'],
+                      xb=hv['xb'], hb=hv['hb']):
+            if dg16:
+                # bf16 operands: d gates as the BPTT's tensor-core tile held it, x and h as the forward's tensor cores read them
+                for d, sf in enumerate(sfx):
+                    db = ops.empty(4 * H)
+                    if not ops.atb_dual(dgates.data_ptr() + 2 * d * 4 * H, nd * 4 * H, 4 * H, xb, F,
+                                        hb.data_ptr() + 2 * d * H, nd * H, B, S, K, which, 1 if d else -1,
+                                        G[f'{rn}.weight_ih_l0{sf}'], F, G[f'{rn}.weight_hh_l0{sf}'], H, db, bf16=True):
+                        raise RuntimeError('dprnn_gemm_atb_dual (bf16) does not apply to this shape')
+                    ops.axpy(db, G[f'{rn}.bias_ih_l0{sf}'])
+                    ops.axpy(db, G[f'{rn}.bias_hh_l0{sf}'])
+                return
             if F == 128 and ops.tf32 and ops.dual:
                 # per direction ONE pass over its d gates: dW_ih = dg^T x, dW_hh = dg^T h_{t-1} (h read one time step earlier
                 # - later for the reverse direction - through the tensor map: no shifted copy), db = sum dg
@@ -657,14 +694,18 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
                     ops.colsum(dgd, rows, 4 * H, db, ldx=nd * 4 * H, accumulate=False)
                 ops.axpy(db, G[f'{rn}.bias_ih_l0{sf}'])
                 ops.axpy(db, G[f'{rn}.bias_hh_l0{sf}'])
-        on_side(rnn_grads, dgates, hout, xs)
+        on_side(rnn_grads, dgates, hout, *((hv['xb'], hv['hb']) if dg16 else (xs,)))
         # dx (gradient of x_in) = dx_out + LSTM-branch gradient
-        if not ops.mm_acc(dgates, hv['wih'].t().contiguous(), rows, F, nd * 4 * H, dx):
-            dxl = ops.mm(dgates, hv['wih'].t().contiguous(), rows, F, nd * 4 * H)
+        wihT = hv['wih'].t().contiguous()
+        if dg16:
+            if not ops.mm_acc(dgates, wihT.to(torch.bfloat16), rows, F, nd * 4 * H, dx):
+                raise RuntimeError('dprnn_gemm_kdeep (bf16) does not apply to this shape')
+        elif not ops.mm_acc(dgates, wihT, rows, F, nd * 4 * H, dx):
+            dxl = ops.mm(dgates, wihT, rows, F, nd * 4 * H)
             ops.axpy(dxl, dx)
             del dxl
         del dgates, hout
-        hv['hout'] = hv['gates'] = hv['cst'] = hv['yl'] = None       # free as we go
+        hv['hout'] = hv['gates'] = hv['cst'] = hv['yl'] = hv['xb'] = hv['hb'] = None       # free as we go
     main.wait_stream(side)
 
     # ---- unfold adjoint = fold; bottleneck conv; fusion; bottleneck norm
