@@ -50,7 +50,8 @@ def test_gemm_atb(M, N1, N2):
 
 @pytest.mark.parametrize('M,N1,N2,lda,ldb', [(50017, 512, 128, 1024, 256), (48500, 128, 256, 128, 256),
                                              (20000, 128, 128, 128, 128), (4100, 256, 128, 256, 128),
-                                             (100, 512, 128, 512, 128)])
+                                             (100, 512, 128, 512, 128), (30011, 64, 128, 64, 128),
+                                             (30011, 128, 64, 128, 64)])
 def test_gemm_atb_tensor_core(M, N1, N2, lda, ldb):
     """The MN-major TF32 weight-gradient contraction against fp64 (operands are column slices of wider row-major
     tensors, as the per-direction slices of dgates / h_prev are)."""

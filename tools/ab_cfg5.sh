@@ -16,5 +16,3 @@ except Exception as e:
 PY
 }
 run default X=1
-run no_dg16 DPRNN_TRAIN_DG16=0
-run default2 X=1

@@ -453,7 +453,7 @@ __global__ void atb_dual_reduce_kernel(const float* __restrict__ partial, int sp
 }
 
 static void atb_tc_plan(long M, int ycols, int* nyt, int* tiles, int* splits, long* rows_per_split) {
-    *nyt = ycols % 256 == 0 ? 256 : 128;
+    *nyt = ycols % 256 == 0 ? 256 : ycols % 128 == 0 ? 128 : 64;       // 64: the N = 64 operand (input_size) as one tile
     *tiles = ycols / *nyt;
     long sp = 148 / *tiles;
     const long max_sp = (M + 4 * AB_KB - 1) / (4 * AB_KB);       // at least 4 stages of rows per split
@@ -470,7 +470,8 @@ static void atb_tc_plan(long M, int ycols, int* nyt, int* tiles, int* splits, lo
 using namespace dprnn;
 
 extern "C" int dprnn_gemm_atb_tc_supported(int N1, int N2, long lda, long ldb) {
-    const bool shape = (N1 == 128 && N2 % 128 == 0 && N2 <= 4096) || (N2 == 128 && N1 % 128 == 0 && N1 <= 4096);
+    const bool shape = (N1 == 128 && (N2 % 128 == 0 || N2 == 64) && N2 <= 4096) ||
+                       (N2 == 128 && (N1 % 128 == 0 || N1 == 64) && N1 <= 4096);
     return shape && lda % 4 == 0 && ldb % 4 == 0 && N1 > 0 && N2 > 0;
 }
 

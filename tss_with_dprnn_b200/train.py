@@ -69,27 +69,45 @@ class _Ops:
                     pro.get('p_shift'), pro.get('p_add'), None, epi, _st())
         return out
 
-    def mm(self, A, W, M, N, K, bias=None, epi=EPI_NONE):
-        """C[M,N] = epi(A[M,K] @ W[N,K]^T + bias) with W in nn.Linear layout; tensor cores in tf32 mode."""
+    def mm(self, A, W, M, N, K, bias=None, epi=EPI_NONE, rows_per_utt=0, x2=False):
+        """C[M,N] = epi(A[M,K] @ W[N,K]^T + bias) with W in nn.Linear layout; tensor cores in tf32 mode.
+        rows_per_utt > 0: bias is per utterance, [M / rows_per_utt, N].  x2: fp32 operands as bf16 PAIRS (DPRNN_GEMM_F32X2,
+        16 significand bits, three MMAs per K slice) instead of truncated TF32 - for the speaker encoder, whose scalar PReLU
+        gradients are sums with heavy cancellation that the coherent TF32 truncation error does not survive."""
         if not (self.tf32 and K % 32 == 0 and N % 64 == 0 and M >= 128):
-            return self.gemm(A, W.t().contiguous(), M, N, K, bias=bias, epi=epi)
+            return self.gemm(A, W.t().contiguous(), M, N, K, bias=bias, epi=epi, bias_per_utt=rows_per_utt > 0,
+                             rows_per_utt=rows_per_utt)
         out = self.empty(M, N)
         step = 256 if N % 256 == 0 else (128 if N % 128 == 0 else 64)
         if step == 256 and K > 128:
             step = 128                                   # the persistent kernel keeps [step, K] of W resident
+        kind = 2 if x2 and self.persist and self.L.query('dprnn_gemm_persist_supported', 2, step, K, epi) else 0
+        if x2 and not kind:
+            return self.gemm(A, W.t().contiguous(), M, N, K, bias=bias, epi=epi, bias_per_utt=rows_per_utt > 0,
+                             rows_per_utt=rows_per_utt)
         for n0 in range(0, N, step):
-            bn = None if bias is None else bias[n0:n0 + step]
-            if self.persist and self.L.query('dprnn_gemm_persist_supported', 0, step, K, epi):
+            if bias is None:
+                bn = None
+            elif rows_per_utt:                           # [utterances, N] -> this column block's [utterances, step]
+                bn = bias if N == step else bias[:, n0:n0 + step].contiguous()
+            else:
+                bn = bias[n0:n0 + step]
+            Wn = W[n0:n0 + step]
+            if kind == 2:                                # per 32 consecutive k: hi(32) then lo(32), as bf16
+                w3 = Wn.detach().float().reshape(step, K // 32, 32)
+                hi = w3.to(torch.bfloat16)
+                Wn = torch.cat([hi, (w3 - hi.float()).to(torch.bfloat16)], -1).reshape(step, 2 * K).contiguous()
+            if self.persist and self.L.query('dprnn_gemm_persist_supported', kind, step, K, epi):
                 # one CTA per SM with the weight resident and a TMA ring over the rows (csrc/gemm_persist.cu)
                 ws = self._gp_ws.get(_st())
                 if ws is None:
                     ws = self._gp_ws[_st()] = torch.empty(self.L.query('dprnn_gemm_persist_workspace_bytes'), device=self.dev,
                                                           dtype=torch.uint8)
-                self.L.call('dprnn_gemm_persist', A, 0, W[n0:n0 + step], bn, 0, None, None, None, None,
+                self.L.call('dprnn_gemm_persist', A, kind, Wn, bn, int(rows_per_utt), None, None, None, None,
                             out.data_ptr() + 4 * n0, N, M, step, K, epi, ws, _st())
             else:
-                self.L.call('dprnn_gemm_tc', A, 0, W[n0:n0 + step], bn, out.data_ptr() + 4 * n0, N, M, step, K, epi,
-                            None, 0, 0.0, None, _st())
+                self.L.call('dprnn_gemm_tc', A, 0, Wn, bn, out.data_ptr() + 4 * n0, N, M, step, K, epi,
+                            None, int(rows_per_utt), 0.0, None, _st())
         return out
 
     def mm_acc(self, A, W, M, N, K, out):
@@ -107,6 +125,13 @@ class _Ops:
 
     def atb(self, A, B, M, N1, N2, out, lda=None, ldb=None, ldc=None, accumulate=True):
         """out[N1,N2] (+)= A[M,N1]^T B[M,N2]"""
+        if (self.tf32 and M >= 4096 and N1 == 256 and N2 == 256 and isinstance(A, torch.Tensor) and isinstance(out, torch.Tensor)
+                and lda is None and ldc is None):
+            # neither operand is the 128-column one the tensor-core kernel wants: two row halves of `out`
+            for h in (0, 1):
+                self.atb(A.data_ptr() + 4 * 128 * h, B, M, 128, N2, out.data_ptr() + 4 * 128 * h * N2, lda=N1, ldb=ldb,
+                         ldc=N2, accumulate=accumulate)
+            return
         if self.tf32 and M >= 4096 and self.L.query('dprnn_gemm_atb_tc_supported', N1, N2, lda or N1, ldb or N2):
             ws = torch.empty(self.L.query('dprnn_gemm_atb_tc_workspace_bytes', N1, N2), device=self.dev, dtype=torch.uint8)
             self.L.call('dprnn_gemm_atb_tc', A, lda or N1, B, ldb or N2, out, ldc or N2, M, N1, N2, int(accumulate), ws, _st())
@@ -221,7 +246,7 @@ def _spk_fwd(model, ops, feats, B, Lr, div):
     gnf = torch.empty_like(feats)                                  # GroupNorm(feats): kept for dW of conv0
     L_.call('dprnn_prologue_apply', feats, gnf, B * Lr, N, Lr, s1, s0, None, None, st)
     O = se[1].weight.shape[0]
-    x = ops.gemm(gnf, se[1].weight.detach().reshape(O, N).t().contiguous(), B * Lr, O, N, bias=se[1].bias.detach())
+    x = ops.mm(gnf, se[1].weight.detach().reshape(O, N), B * Lr, O, N, bias=se[1].bias.detach(), x2=True)
     res, Lx = [], Lr
     for rb in (se[2], se[3], se[4]):
         Cin, Cout = rb.conv1.weight.shape[1], rb.conv1.weight.shape[0]
@@ -237,14 +262,14 @@ def _spk_fwd(model, ops, feats, B, Lr, div):
             bnm.num_batches_tracked += 1
             return scale, shift
 
-        y1 = ops.gemm(x, rb.conv1.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
+        y1 = ops.mm(x, rb.conv1.weight.detach().reshape(Cout, Cin), rows, Cout, Cin, x2=True)
         sc1, sh1 = bn(y1, rb.batch_norm1)
         a1 = ops.empty(rows, Cout)
         L_.call('dprnn_affine_prelu', y1, sc1, sh1, rb.prelu1.weight.detach(), a1, rows, Cout, st)
-        y2 = ops.gemm(a1, rb.conv2.weight.detach().reshape(Cout, Cout).t().contiguous(), rows, Cout, Cout)
+        y2 = ops.mm(a1, rb.conv2.weight.detach().reshape(Cout, Cout), rows, Cout, Cout, x2=True)
         sc2, sh2 = bn(y2, rb.batch_norm2)
         if hasattr(rb, 'conv_downsample'):
-            skip = ops.gemm(x, rb.conv_downsample.weight.detach().reshape(Cout, Cin).t().contiguous(), rows, Cout, Cin)
+            skip = ops.mm(x, rb.conv_downsample.weight.detach().reshape(Cout, Cin), rows, Cout, Cin, x2=True)
         else:
             skip = x
         Lo = Lx // 3
@@ -255,7 +280,7 @@ def _spk_fwd(model, ops, feats, B, Lr, div):
         x, Lx = out.view(B * Lo, Cout), Lo
     E = se[5].weight.shape[0]
     C5 = se[5].weight.shape[1]
-    z5 = ops.gemm(x, se[5].weight.detach().reshape(E, C5).t().contiguous(), B * Lx, E, C5, bias=se[5].bias.detach())
+    z5 = ops.mm(x, se[5].weight.detach().reshape(E, C5), B * Lx, E, C5, bias=se[5].bias.detach(), x2=True)
     emb = ops.empty(B, E)
     L_.call('dprnn_time_sum', z5, emb, B, Lx, E, div, st)
     return emb, dict(feats=feats, mr_s=mr_s, gnf=gnf, res=res, x3=x, L3=Lx, Lr=Lr, div=div, B=B)
@@ -308,7 +333,7 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
     L_.call('dprnn_norm_affine', mr_e, gamma.detach(), beta.detach(), mulc, s1e, s0e, B, N, st)
     fused = torch.empty_like(enc)                                   # fusion(GroupNorm(enc)): kept for dW of the 1x1 conv
     L_.call('dprnn_prologue_apply', enc, fused, B * Lm, N, Lm, s1e, s0e, addc, rowscale, st)
-    y = ops.gemm(fused, bw[:, :N].t().contiguous(), B * Lm, F, N, bias=bias, bias_per_utt=bias_per_utt, rows_per_utt=Lm)
+    y = ops.mm(fused, bw[:, :N].contiguous(), B * Lm, F, N, bias=bias, rows_per_utt=Lm if bias_per_utt else 0)
     S = L_.query('dprnn_num_chunks', Lm, K, P)
     xs = ops.empty(B, S, K, F)
     L_.call('dprnn_unfold', y, xs, B, Lm, K, P, F, st)
@@ -476,7 +501,7 @@ def _spk_bwd(model, ops, sc, demb, G):
     L_.call('dprnn_bcast_mul', dscaled, None, dz5, B, L3, E, 0, st)
     ops.atb(dz5, x3, B * L3, E, C5, G['separation.spk_encoder.5.weight'])
     ops.colsum(dz5, B * L3, E, G['separation.spk_encoder.5.bias'])
-    dout = ops.gemm(dz5, se[5].weight.detach().reshape(E, C5).contiguous(), B * L3, C5, E)
+    dout = ops.mm(dz5, se[5].weight.detach().reshape(E, C5).t().contiguous(), B * L3, C5, E, x2=True)
     del dz5
     for bi, (rb, rc) in reversed(list(enumerate(zip((se[2], se[3], se[4]), sc['res'])))):
         pre_n = f'separation.spk_encoder.{bi + 2}'
@@ -512,16 +537,16 @@ def _spk_bwd(model, ops, sc, demb, G):
 
         dy2 = bn_bwd(dv2, rc['y2'], rc['sc2'], rc['sh2'], rb.batch_norm2, pre_n + '.batch_norm2')
         ops.atb(dy2, rc['a1'], rws, Cout, Cout, G[pre_n + '.conv2.weight'])
-        da1 = ops.gemm(dy2, rb.conv2.weight.detach().reshape(Cout, Cout).contiguous(), rws, Cout, Cout)
+        da1 = ops.mm(dy2, rb.conv2.weight.detach().reshape(Cout, Cout).t().contiguous(), rws, Cout, Cout, x2=True)
         v1 = ops.empty(rws, Cout)
         L_.call('dprnn_affine_prelu', rc['y1'], rc['sc1'], rc['sh1'], one, v1, rws, Cout, st)
         dv1 = ops.prelu_bwd(da1, v1, rb.prelu1.weight.detach(), G[pre_n + '.prelu1.weight'])
         dy1 = bn_bwd(dv1, rc['y1'], rc['sc1'], rc['sh1'], rb.batch_norm1, pre_n + '.batch_norm1')
         ops.atb(dy1, x, rws, Cout, Cin, G[pre_n + '.conv1.weight'])
-        dxr = ops.gemm(dy1, rb.conv1.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
+        dxr = ops.mm(dy1, rb.conv1.weight.detach().reshape(Cout, Cin).t().contiguous(), rws, Cin, Cout, x2=True)
         if hasattr(rb, 'conv_downsample'):
             ops.atb(dv2, x, rws, Cout, Cin, G[pre_n + '.conv_downsample.weight'])
-            t = ops.gemm(dv2, rb.conv_downsample.weight.detach().reshape(Cout, Cin).contiguous(), rws, Cin, Cout)
+            t = ops.mm(dv2, rb.conv_downsample.weight.detach().reshape(Cout, Cin).t().contiguous(), rws, Cin, Cout, x2=True)
             ops.axpy(t, dxr)
         else:
             ops.axpy(dv2, dxr)
@@ -530,7 +555,7 @@ def _spk_bwd(model, ops, sc, demb, G):
     O = se[1].weight.shape[0]
     ops.atb(dout, sc['gnf'], B * Lr, O, N, G['separation.spk_encoder.1.weight'])
     ops.colsum(dout, B * Lr, O, G['separation.spk_encoder.1.bias'])
-    dgnf = ops.gemm(dout, se[1].weight.detach().reshape(O, N).contiguous(), B * Lr, N, O)
+    dgnf = ops.mm(dout, se[1].weight.detach().reshape(O, N).t().contiguous(), B * Lr, N, O, x2=True)
     return ops.gn_bwd(dgnf, feats, sc['mr_s'], se[0].weight.detach(), B, Lr, N, G['separation.spk_encoder.0.weight'],
                       G['separation.spk_encoder.0.bias'])
 
