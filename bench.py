@@ -698,7 +698,7 @@ def run_ours(args):
     lstm_names = [n for n in per_kernel if n in (dominant, 'dprnn_lstm_inter_bf16_ragged', 'dprnn_lstm_layer_bf16_pp',
                                                  'dprnn_lstm_layer_bf16_sliced', 'dprnn_lstm_inter_bf16_ragged_pp')]
     if args.workload == 'cfg5':
-        lstm_names = [n for n in per_kernel if n in ('dprnn_lstm_recurrence_f32_train', 'dprnn_lstm_bptt_f32', 'dprnn_lstm_layer_bf16_train', 'dprnn_lstm_bptt_tc')]
+        lstm_names = [n for n in per_kernel if n in ('dprnn_lstm_recurrence_f32_train', 'dprnn_lstm_bptt_f32', 'dprnn_lstm_layer_bf16_train', 'dprnn_lstm_bptt_tc', 'dprnn_lstm_bptt_tc_bf16out')]
     if lstm_names:
         ms_lstm = sum(per_kernel[n]['ms_total'] for n in lstm_names)
         n_launch = sum(per_kernel[n]['launches'] for n in lstm_names)
@@ -723,25 +723,34 @@ def run_ours(args):
                              'algorithmic flops = h W_hh^T only (2*128*512 per position and direction); the fp32 mode '
                              'runs this on CUDA cores, so its fraction of the bf16 tensor peak is small by construction')}
 
-    bptt_name = 'dprnn_lstm_bptt_tc' if 'dprnn_lstm_bptt_tc' in per_kernel else 'dprnn_lstm_bptt_f32'
+    bptt_name = next((n for n in ('dprnn_lstm_bptt_tc_bf16out', 'dprnn_lstm_bptt_tc', 'dprnn_lstm_bptt_f32') if n in per_kernel),
+                     'dprnn_lstm_bptt_f32')
     if args.workload == 'cfg5' and bptt_name in per_kernel:
-        # dominant kernel of the training step: the fp32 BPTT recurrence.  It streams the saved gate activations, two
-        # cell states and d h_out and writes d gates: 4H + 2H + H + 4H floats per chunk position and direction.
+        # dominant kernel of the training step: the BPTT recurrence.  Per chunk position and direction it streams the saved
+        # gate activations (4 H), the cell state (H; c_{t-1} of a step is c_t of the next one) and d h_out (H) and writes
+        # d gates (4 H).
         k = per_kernel[bptt_name]
         peak_bw = peaks.get('hbm_gbs', 6400.0)
-        gate_bytes = 4 * 128 * (2 if bptt_name == 'dprnn_lstm_bptt_tc' else 4)     # saved gates: packed bf16 / fp32
-        bytes_per_launch = wl.positions(0) * 2 * (gate_bytes + (2 * 128 + 128 + 4 * 128) * 4)
+        H_ = 128
+        gate_bytes = 4 * H_ * (4 if bptt_name == 'dprnn_lstm_bptt_f32' else 2)           # saved gates: fp32 / packed bf16
+        dg_bytes = 4 * H_ * (2 if bptt_name == 'dprnn_lstm_bptt_tc_bf16out' else 4)      # d gates out: bf16 / fp32
+        c_bytes = H_ * 4 * (1 if bptt_name == 'dprnn_lstm_bptt_tc_bf16out' else 2)       # older forms load c_t and c_{t-1}
+        bytes_per_launch = wl.positions(0) * 2 * (gate_bytes + c_bytes + H_ * 4 + dg_bytes)
         achieved = bytes_per_launch / (k['ms_avg'] * 1e-3) / 1e9
         roofline = {'kernel': bptt_name, 'bound': 'hbm', 'achieved': achieved, 'peak': peak_bw, 'unit': 'GB/s',
                     'frac': achieved / peak_bw, 'traffic': None,
                     'peak_source': 'MEASURED_PEAKS.json hbm_gbs' if peaks else 'fallback 6400 (B200_PROFILING.md)',
                     'launch_ms_avg': k['ms_avg'],
                     'share_of_step_single_stream': k['ms_total'] / sum(v['ms_total'] for v in per_kernel.values()),
-                    'note': 'dominant kernel of the training step (BPTT).  Algorithmic bytes per chunk position and direction: 4 H '
-                            'saved gate activations (bf16 in tensor-core mode), c_t, c_{t-1}, dh (3 H fp32) in; dgates (4 H fp32) out.  Tensor-core mode: d h_{t-1} = d gates_t '
-                            'W_hh on tcgen05 (CTA pair); at 16 utterances per GPU only 64..98 of 148 SMs hold a CTA and the '
-                            'element-wise cell backward between the MMAs is issue/latency-bound (ncu: 27 % issue slots, top '
-                            'stall = first use of the streamed loads): DESIGN.md section 5.2'}
+                    'bytes_per_position_and_direction': gate_bytes + c_bytes + H_ * 4 + dg_bytes,
+                    'note': 'dominant kernel of the training step (BPTT).  Algorithmic bytes per chunk position and direction: '
+                            '4 H saved gate activations (bf16 in tensor-core mode), c_t and d h_out (fp32) in; d gates out (4 H; '
+                            'bf16 when the weight-gradient and d x kernels take bf16 operands).  d h_{t-1} = d gates_t W_hh on '
+                            'tcgen05 (CTA pair, 64 rows per CTA at 16 utterances per GPU: 100-128 of 148 SMs hold a CTA); the '
+                            'element-wise cell backward between the MMAs is issue- and latency-bound (ncu: 47 % issue slots, top '
+                            'stalls = first use of the streamed loads and the wait for the step\'s MMA).  The launch is timed while '
+                            'the weight-gradient kernels of the previous half-block run on the side stream and share the HBM '
+                            'bandwidth with it: DESIGN.md section 5.2'}
 
     modes = gpu_ref = cfg5 = None
     if args.workload == 'cfg2':

@@ -547,6 +547,10 @@ size_t dprnn_gn_bwd_workspace_bytes(int B, int C);
 int dprnn_groupnorm_bwd(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
                         long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
                         void* workspace, void* stream);
+/* The same, also writing a bf16 copy of dy (the operand of the Linear's bf16 weight-gradient pass). */
+int dprnn_groupnorm_bwd_h16(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
+                            long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
+                            void* workspace, void* dy_bf16, void* stream);
 /* PReLU adjoint: dx = dy * (x > 0 ? 1 : a); da[0] += sum dy*x*[x <= 0]; workspace: 148*16 doubles. */
 int dprnn_prelu_bwd(const float* dy, const float* x, const float* prelu_a, float* dx, long n, float* da, void* workspace,
                     void* stream);

@@ -207,6 +207,11 @@ def test_lstm_tensor_core_train_forward_saves_what_bptt_needs(inter):
             assert float((t_[rows:] - 7.0).abs().max()) == 0.0             # nothing written past the real rows
         if fn.endswith('_pp'):
             saved[fast] = (g1p.clone(), c1.clone(), h1.clone(), hb.clone())
+    # without the fp32 copy of h (hout_f32 = NULL: h is kept as bf16 only) the other outputs do not change
+    for fl in (1 | 4, 1 | 4 | 16, 1 | 8):
+        g1p.fill_(7.0); c1.fill_(7.0); hb.fill_(7.0)
+        L.call('dprnn_lstm_layer_bf16_train_pp', xb, wp2, bp, hb, g1p, c1, None, B, S, K, inter, H, nd, fl, st())
+        assert all(torch.equal(x_, y_) for x_, y_ in zip((g1p, c1, hb), (saved[fl][0], saved[fl][1], saved[fl][3]))), fl
     # the staged epilogue stores exactly what the direct one stores; tile size does not change a row's arithmetic
     for a, b_ in ((1 | 4, 1 | 4 | 16), (1 | 4, 1 | 8), (4, 4 | 16)):
         assert all(torch.equal(x_, y_) for x_, y_ in zip(saved[a], saved[b_])), (a, b_)

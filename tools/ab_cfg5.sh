@@ -16,3 +16,4 @@ except Exception as e:
 PY
 }
 run default X=1
+run with_hf DPRNN_TRAIN_NO_HF=0

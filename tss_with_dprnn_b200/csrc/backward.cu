@@ -199,7 +199,7 @@ __global__ void __launch_bounds__(128) gn_bwd_finalize_kernel(const double* __re
 __global__ void gn_bwd_apply_kernel(const float* __restrict__ dz, const float* __restrict__ y,
                                     const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
                                     const float* __restrict__ s12, float* __restrict__ dy, long total4, long per_utt4,
-                                    int c4n, int accumulate) {
+                                    int c4n, int accumulate, uint2* __restrict__ dy_bf16 = nullptr) {
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total4; idx += (long)gridDim.x * blockDim.x) {
         const long b = idx / per_utt4;
         const int c4 = (int)(idx % c4n);
@@ -217,6 +217,10 @@ __global__ void gn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
             o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
         reinterpret_cast<float4*>(dy)[idx] = o;
+        if (dy_bf16) {          // bf16 copy: the operand of the Linear's weight-gradient pass (dprnn_gemm_atb_dual, bf16 form)
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            dy_bf16[idx] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
+        }
     }
 }
 
@@ -535,9 +539,9 @@ int dprnn_col_sum(const float* X, long ldx, const float* Y, long ldy, long M, in
 
 size_t dprnn_gn_bwd_workspace_bytes(int B, int C) { return (size_t)B * 64 * (2 * sizeof(double) + 2 * C * sizeof(float)) + (size_t)B * 2 * sizeof(float); }
 
-int dprnn_groupnorm_bwd(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
-                        long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
-                        void* workspace, void* stream) {
+static int gn_bwd_impl(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
+                       long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
+                       void* workspace, void* dy_bf16, void* stream) {
     DPRNN_CHECK_ARG(dz && y && mean_rstd && gamma && dy && dgamma && dbeta && workspace && B > 0 && B <= 65535);
     DPRNN_CHECK_ARG(rows_per_utt > 0 && C % 4 == 0 && 256 % C == 0);
     cudaStream_t st = (cudaStream_t)stream;
@@ -553,9 +557,22 @@ int dprnn_groupnorm_bwd(const float* dz, const float* y, const float* mean_rstd,
     DPRNN_CHECK_LAUNCH();
     const long per4 = rows_per_utt * (C / 4);
     gn_bwd_apply_kernel<<<bgrid(per4 * B, 256), 256, 0, st>>>(dz, y, mean_rstd, gamma, s12, dy, per4 * B, per4, C / 4,
-                                                             accumulate_dy);
+                                                             accumulate_dy, (uint2*)dy_bf16);
     DPRNN_CHECK_LAUNCH();
     return 0;
+}
+
+int dprnn_groupnorm_bwd(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
+                        long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
+                        void* workspace, void* stream) {
+    return gn_bwd_impl(dz, y, mean_rstd, gamma, B, rows_per_utt, C, dy, accumulate_dy, dgamma, dbeta, workspace, nullptr, stream);
+}
+
+int dprnn_groupnorm_bwd_h16(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
+                            long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
+                            void* workspace, void* dy_bf16, void* stream) {
+    DPRNN_CHECK_ARG(dy_bf16 && (uintptr_t)dy_bf16 % 16 == 0);
+    return gn_bwd_impl(dz, y, mean_rstd, gamma, B, rows_per_utt, C, dy, accumulate_dy, dgamma, dbeta, workspace, dy_bf16, stream);
 }
 
 int dprnn_prelu_bwd(const float* dy, const float* x, const float* prelu_a, float* dx, long n, float* da, void* workspace,

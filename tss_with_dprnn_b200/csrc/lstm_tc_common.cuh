@@ -178,7 +178,7 @@ __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restric
                     st_global_v8u(gdst, gk[0], gk[1]);
                     st_global_v8u(gdst + 8, gk[2], gk[3]);
                     st_global_v8(cdst, keep[0], sv[4]);
-                    st_global_v8(hdst, keep[1], hv);
+                    if (hdst) st_global_v8(hdst, keep[1], hv);
                 }
             }
         }

@@ -286,7 +286,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     const long lr = p.seq_dim == 2 ? seq * p.K + t : ((long)outer * p.S + t) * p.K + seq;
                     gd = p.gates + (lr * p.ndir + dir) * 256 + ub * 64;       // uint32 units: 16 per 8-unit chunk
                     cd = p.cst + (lr * p.ndir + dir) * 128 + ub * 32;
-                    hd = p.hf + (lr * p.ndir + dir) * 128 + ub * 32;
+                    hd = p.hf ? p.hf + (lr * p.ndir + dir) * 128 + ub * 32 : nullptr;
                 }
             }
             // ---------------- unit half 0
@@ -302,7 +302,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     stage_done();
                 } else {
                     lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g],
-                                                           gd ? gd + 16 * g : nullptr, cd + 8 * g, hd + 8 * g);
+                                                           gd ? gd + 16 * g : nullptr, cd + 8 * g, hd ? hd + 8 * g : nullptr);
                 }
             }
             tc_fence_before();
@@ -330,7 +330,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                     stage_done();
                 } else {
                     lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g, pk[g],
-                                                           gd ? gd + 128 + 16 * g : nullptr, cd + 64 + 8 * g, hd + 64 + 8 * g);
+                                                           gd ? gd + 128 + 16 * g : nullptr, cd + 64 + 8 * g, hd ? hd + 64 + 8 * g : nullptr);
                 }
             }
             tc_fence_before();
@@ -367,7 +367,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                             mbar_wait(&sv_full[q * 2 + (n & 1)], (n >> 1) & 1);
                             tma_store_4d(&sm.g, buf, dir * 256 + unit0 * 2, k1, k2, outer);
                             tma_store_4d(&sm.c, buf + 2048, dir * 128 + unit0, k1, k2, outer);
-                            tma_store_4d(&sm.h, buf + 3072, dir * 128 + unit0, k1, k2, outer);
+                            if (p.hf) tma_store_4d(&sm.h, buf + 3072, dir * 128 + unit0, k1, k2, outer);
                             bulk_commit();
                             if (n >= 1) {                  // the stores of the call before have read their buffer
                                 bulk_wait_read1();
@@ -470,7 +470,8 @@ static int lstm_pp_impl(const void* x, const void* w_packed, const float* bias_p
         if (make_tmap(&sm.g, CU_TENSOR_MAP_DATA_TYPE_UINT32, 4, gates, dS, sS, bS, CU_TENSOR_MAP_SWIZZLE_64B)) return 1;
         dS[0] = (uint64_t)ndir * 128; scale((uint64_t)ndir * 512); bS[0] = 8;
         if (make_tmap(&sm.c, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, cstate, dS, sS, bS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
-        if (make_tmap(&sm.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hout_f32, dS, sS, bS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
+        sm.h = sm.c;
+        if (hout_f32 && make_tmap(&sm.h, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, hout_f32, dS, sS, bS, CU_TENSOR_MAP_SWIZZLE_32B)) return 1;
     }
     auto kern = stage ? (fast_act ? lstm_tc_pp_kernel<true, true, false, false, true> : lstm_tc_pp_kernel<false, true, false, false, true>)
                 : gates ? (fast_act ? lstm_tc_pp_kernel<true, true, false> : lstm_tc_pp_kernel<false, true, false>)
@@ -517,7 +518,7 @@ extern "C" int dprnn_lstm_inter_bf16_ragged_pp(const void* x, const void* w_pack
 extern "C" int dprnn_lstm_layer_bf16_train_pp(const void* x, const void* w_packed, const float* bias_perm, void* hout_bf16,
                                               void* gates_packed, float* cstate, float* hout_f32, int B, int S, int K,
                                               int inter, int hidden, int ndir, int fast_act, void* stream) {
-    DPRNN_CHECK_ARG(gates_packed && cstate && hout_f32);
+    DPRNN_CHECK_ARG(gates_packed && cstate);        // hout_f32 may be NULL: h is then kept as bf16 (hout_bf16) only
     DPRNN_CHECK_ARG(((uintptr_t)gates_packed | (uintptr_t)cstate | (uintptr_t)hout_f32) % 32 == 0);
     return lstm_pp_impl(x, w_packed, bias_perm, hout_bf16, B, S, K, inter, hidden, ndir, fast_act, nullptr, 0, stream,
                         gates_packed, cstate, hout_f32);

@@ -36,6 +36,8 @@ _BPTT_FLAGS = int(os.environ.get('DPRNN_BPTT_FLAGS', '0')) & 12
 # 1 (default): the forward keeps every half-block's input (0.4 GB each at 16 x 3 s; 12 of them) and the backward reads it;
 # 0: the forward updates the residual stream in place and the backward recomputes x_in = x_out - norm(y) (one more pass)
 _KEEP_INPUTS = os.environ.get('DPRNN_TRAIN_KEEP_INPUTS', '1') != '0'
+# 1 (default): in the bf16-d-gates mode the LSTM output is kept as bf16 only (no fp32 copy)
+_NO_HF = os.environ.get('DPRNN_TRAIN_NO_HF', '1') != '0'
 _SKIP_SIDE = os.environ.get('DPRNN_TRAIN_SKIP_SIDE', '0') == '1'
 _FWD_FLAGS = int(os.environ.get('DPRNN_TRAIN_LSTM_FLAGS', '0')) & 28
 
@@ -177,12 +179,28 @@ class _Ops:
         self.L.call('dprnn_utt_stats', x, B, elems, float(eps), ws, mr, _st())
         return mr
 
-    def gn_bwd(self, dz, y, mr, gamma, B, rows_per_utt, C, dgamma, dbeta, dy=None, accumulate_dy=False):
+    def gn_bwd(self, dz, y, mr, gamma, B, rows_per_utt, C, dgamma, dbeta, dy=None, accumulate_dy=False, dy16=None):
         ws = torch.empty(self.L.query('dprnn_gn_bwd_workspace_bytes', B, C), device=self.dev, dtype=torch.uint8)
         if dy is None:
             dy = self.empty(B * rows_per_utt, C)
-        self.L.call('dprnn_groupnorm_bwd', dz, y, mr, gamma, B, rows_per_utt, C, dy, int(accumulate_dy), dgamma, dbeta, ws, _st())
+        if dy16 is not None:       # also a bf16 copy of dy
+            self.L.call('dprnn_groupnorm_bwd_h16', dz, y, mr, gamma, B, rows_per_utt, C, dy, int(accumulate_dy), dgamma, dbeta,
+                        ws, dy16, _st())
+        else:
+            self.L.call('dprnn_groupnorm_bwd', dz, y, mr, gamma, B, rows_per_utt, C, dy, int(accumulate_dy), dgamma, dbeta, ws,
+                        _st())
         return dy
+
+    def mm16(self, A16, W, M, N, K, bias=None):
+        """C[M,N] (fp32) = A16[M,K] @ bf16(W[N,K])^T + bias with bf16 operands on the persistent tensor-core kernel."""
+        out = self.empty(M, N)
+        ws = self._gp_ws.get(_st())
+        if ws is None:
+            ws = self._gp_ws[_st()] = torch.empty(self.L.query('dprnn_gemm_persist_workspace_bytes'), device=self.dev,
+                                                  dtype=torch.uint8)
+        self.L.call('dprnn_gemm_persist', A16, 1, W.detach().to(torch.bfloat16).contiguous(), bias, 0, None, None, None, None,
+                    out, N, M, N, K, EPI_NONE, ws, _st())
+        return out
 
     def prelu_bwd(self, dy, x, a, da):
         dx = torch.empty_like(x)
@@ -347,6 +365,9 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
     # bf16 d gates in the backward: its weight-gradient pass reads the bf16 x and h this forward works on (kept), and the
     # half-block inputs need neither be kept in fp32 nor be recomputed
     dg16 = ops.dg16 and F == 128 and H == 128 and rows >= 4096
+    # ... and with every layer bidirectional h is kept as bf16 only: the Linear and its weight gradient read that copy
+    nohf = (dg16 and _NO_HF and model._engine.lstm_pingpong and all(blk.intra_rnn.rnn.bidirectional and blk.inter_rnn.rnn.bidirectional for blk in sep.dprnn_blocks)
+            and bool(ops.L.query('dprnn_gemm_persist_supported', 1, F, 2 * H, EPI_NONE)))
     xb = hb = None
     for blk in sep.dprnn_blocks:
         for which, (rnn, linm, nm) in enumerate(((blk.intra_rnn.rnn, blk.intra_linear, blk.intra_norm),
@@ -357,7 +378,7 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
             b = torch.cat([(getattr(rnn, 'bias_ih_l0' + s) + getattr(rnn, 'bias_hh_l0' + s)).detach() for s in sfx], 0)
             whh = torch.stack([getattr(rnn, 'weight_hh_l0' + s).detach() for s in sfx], 0).contiguous()   # [nd,4H,H]
             geo = (B * S, K, 1, K, 0, 1) if which == 0 else (B * K, S, K, S * K, 1, K)
-            hout, cst = ops.empty(rows, nd * H), ops.empty(rows, nd * H)
+            hout, cst = (None if nohf else ops.empty(rows, nd * H)), ops.empty(rows, nd * H)
             # saved gate activations: fp32 row-major in the exact mode, bf16 packed per 8-unit chunk in the tensor-core mode
             gates = torch.empty((rows, nd * 4 * H), device=dev, dtype=torch.bfloat16 if ops.tf32 else torch.float32)
             if ops.tf32:
@@ -379,7 +400,10 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
                 gx = ops.mm(xs, wih, rows, nd * 4 * H, F, bias=b)
                 L_.call('dprnn_lstm_recurrence_f32_train', gx, whh.transpose(1, 2).contiguous(), hout, gates, cst, *geo, H, nd, st)
                 del gx
-            yl = ops.mm(hout, linm.weight.detach(), rows, F, nd * H, bias=linm.bias.detach())
+            if nohf:
+                yl = ops.mm16(hb, linm.weight, rows, F, nd * H, bias=linm.bias.detach())
+            else:
+                yl = ops.mm(hout, linm.weight.detach(), rows, F, nd * H, bias=linm.bias.detach())
             g_, b_, eps_ = _norm_params(nm)
             mr = ops.utt_stats(yl, B, S * K * F, eps_)
             n_half += 1
@@ -394,7 +418,7 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
             halves.append(dict(nd=nd, geo=geo, hout=hout, gates=gates, cst=cst, yl=yl, mr=mr, wih=wih, whh=whh,
                                rnn=rnn, lin=linm, norm=nm, sfx=sfx, which=which, x_in=x_in,
                                xb=xb if dg16 else None, hb=hb if dg16 else None))
-    c.update(halves=halves, xs=xs, dg16=dg16)
+    c.update(halves=halves, xs=xs, dg16=dg16, nohf=nohf)
 
     # ---- PReLU, overlap-add, conv2d, gated head, end conv + activation (dprnn_spe.py:231-248)
     z = ops.empty(B, Lm, F)
@@ -643,11 +667,21 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
             L_.call('dprnn_norm_residual_to', yl, xs_out, mr, (-g_.detach()).contiguous(), (-b_.detach()).contiguous(), B,
                     S * K, F, xs, None, st)                          # xs: x_in = x_out - norm(y)
             del xs_out
-        dy = ops.gn_bwd(dx, yl, mr, g_.detach(), B, S * K, F, G[gname], G[bname])
+        nohf = c['nohf']
+        dy16 = torch.empty((rows, F), device=dev, dtype=torch.bfloat16) if nohf else None
+        dy = ops.gn_bwd(dx, yl, mr, g_.detach(), B, S * K, F, G[gname], G[bname], dy16=dy16)
         ln = names[id(hv['lin'])]
         hout = hv['hout']
 
-        def lin_grads(dy=dy, hout=hout, ln=ln, nd=nd):
+        def lin_grads(dy=dy, hout=hout, ln=ln, nd=nd, dy16=dy16, hb=hv['hb']):
+            if nohf:                       # bf16 operands: dW = dy^T [h_fwd | h_bwd], db = sum dy
+                db = ops.empty(F)
+                gw = G[ln + '.weight']
+                if not ops.atb_dual(dy16, F, F, hb, nd * H, hb.data_ptr() + 2 * H, nd * H, B, S, K, 0, 0,
+                                    gw, nd * H, gw.data_ptr() + 4 * H, nd * H, db, bf16=True):
+                    raise RuntimeError('dprnn_gemm_atb_dual (bf16) does not apply to this shape')
+                ops.axpy(db, G[ln + '.bias'])
+                return
             if nd == 2 and F == 128:       # dW = dy^T [h_fwd | h_bwd] and db = sum dy from one pass over dy
                 db = ops.empty(F)
                 gw = G[ln + '.weight']
@@ -657,7 +691,7 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
                     return
             ops.atb(dy, hout, rows, F, nd * H, G[ln + '.weight'])
             ops.colsum(dy, rows, F, G[ln + '.bias'])
-        on_side(lin_grads, dy, hout)
+        on_side(lin_grads, *((dy16, hv['hb']) if nohf else (dy, hout)))
         dh = ops.mm(dy, hv['lin'].weight.detach().t().contiguous(), rows, nd * H, F)
         del dy
         dgates = torch.empty((rows, nd * 4 * H), device=dev, dtype=torch.bfloat16 if dg16 else torch.float32)
@@ -719,7 +753,7 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
                     ops.colsum(dgd, rows, 4 * H, db, ldx=nd * 4 * H, accumulate=False)
                 ops.axpy(db, G[f'{rn}.bias_ih_l0{sf}'])
                 ops.axpy(db, G[f'{rn}.bias_hh_l0{sf}'])
-        on_side(rnn_grads, dgates, hout, *((hv['xb'], hv['hb']) if dg16 else (xs,)))
+        on_side(rnn_grads, dgates, *((hv['xb'], hv['hb']) if dg16 else (xs, hout)))
         # dx (gradient of x_in) = dx_out + LSTM-branch gradient
         wihT = hv['wih'].t().contiguous()
         if dg16:
