@@ -338,3 +338,27 @@ def test_gemm_atb_dual(B, S, K, inter, N1, shift, bf):
         assert float((cs.cpu().double() - want_cs).abs().max()) < 1e-4 * float(want_cs.abs().max()) + 1e-3
         outs.append((C1.clone(), C2.clone(), cs.clone()))
     assert all(torch.equal(a, b) for a, b in zip(*outs))
+
+
+@pytest.mark.parametrize('rows,C', [(2 * 1300 - 1, 128), (384001, 256), (7, 64), (100003, 64)])
+def test_batchnorm_training_statistics(rows, C):
+    """dprnn_batchnorm_affine in training mode: per-channel batch statistics (float4 loads, fp32 over 16 rows then fp64,
+    fixed partition) -> scale / shift and the running-statistics update of nn.BatchNorm1d."""
+    L = P.lib()
+    g = torch.Generator().manual_seed(rows + C)
+    y = (torch.randn(rows, C, generator=g) * 1.7 + 0.3 * torch.arange(C)).float()
+    bn = torch.nn.BatchNorm1d(C).double()
+    with torch.no_grad():
+        bn.weight.copy_(torch.randn(C, generator=g)); bn.bias.copy_(torch.randn(C, generator=g))
+        bn.running_mean.copy_(torch.randn(C, generator=g)); bn.running_var.copy_(torch.rand(C, generator=g) + 0.5)
+    rm, rv = bn.running_mean.clone().float().to(DEV), bn.running_var.clone().float().to(DEV)
+    want = bn.train()(y.double().t().unsqueeze(0)).squeeze(0).t().detach()         # [rows, C]
+    ws = torch.empty(L.query('dprnn_bn_workspace_bytes', C), device=DEV, dtype=torch.uint8)
+    scale, shift = torch.empty(C, device=DEV), torch.empty(C, device=DEV)
+    yd = y.to(DEV)
+    L.call('dprnn_batchnorm_affine', yd, rows, C, bn.weight.detach().float().to(DEV), bn.bias.detach().float().to(DEV), rm, rv, 1,
+           float(bn.eps), float(bn.momentum), ws, scale, shift, st())
+    got = yd.double() * scale.double() + shift.double()
+    assert float((got.cpu() - want).abs().max()) < 2e-5 * float(want.abs().max())
+    assert float((rm.cpu().double() - bn.running_mean).abs().max()) < 1e-6 * float(bn.running_mean.abs().max()) + 1e-6
+    assert float((rv.cpu().double() - bn.running_var).abs().max()) < 1e-5 * float(bn.running_var.abs().max())

@@ -11,8 +11,8 @@ KW = dict(input_size=64, feature_size=128, hidden_size=128, chunk_length=250, ke
           n_repeats=1, bidirectional=True, norm_type='ln', activation_type='sigmoid', dropout=0)
 
 
-def oracle_grads(model, kw, fusion, mix, ref, Tr, w_est, w_log):
-    sd = {k: v.detach().clone().double() for k, v in model.state_dict().items()}
+def oracle_grads(model, kw, fusion, mix, ref, Tr, w_est, w_log, dtype=torch.float64):
+    sd = {k: v.detach().clone().to(dtype) if v.is_floating_point() else v.detach().clone() for k, v in model.state_dict().items()}
     leaves = {}
     for n, p in model.named_parameters():
         if p.requires_grad:
@@ -21,9 +21,9 @@ def oracle_grads(model, kw, fusion, mix, ref, Tr, w_est, w_log):
     cfg = O.Config(**{k: kw[k] for k in ('input_size', 'feature_size', 'hidden_size', 'chunk_length', 'kernel_size',
                                          'hop_length', 'n_repeats', 'bidirectional', 'norm_type', 'activation_type')},
                    fusion_type=fusion)
-    est, logits = O.spe_forward(mix.double(), ref.double(), torch.tensor(float(Tr)), sd, cfg, training=True, new_stats={},
+    est, logits = O.spe_forward(mix.to(dtype), ref.to(dtype), torch.tensor(float(Tr)), sd, cfg, training=True, new_stats={},
                                 fast=False)
-    loss = (est * w_est.double()).sum() + (logits * w_log.double()).sum()
+    loss = (est * w_est.to(dtype)).sum() + (logits * w_log.to(dtype)).sum()
     loss.backward()
     return est.detach(), logits.detach(), {n: v.grad for n, v in leaves.items()}
 
@@ -41,13 +41,16 @@ def test_backward_matches_oracle_autograd(fusion, extra):
     mix, ref = 0.05 * torch.randn(B, T, generator=g), 0.05 * torch.randn(B, Tr, generator=g)
     w_est, w_log = torch.randn(B, T, generator=g), torch.randn(B, 251, generator=g)
     est_o, log_o, grads_o = oracle_grads(model, kw, fusion, mix, ref, Tr, w_est, w_log)
+    # the fp32 noise floor of each parameter's gradient: torch's own fp32 autograd through the oracle against the fp64 one
+    # (train-mode BatchNorm biases of the speaker encoder sit at ~3e-4: sums with cancellation)
+    _, _, floor = oracle_grads(model, kw, fusion, mix, ref, Tr, w_est, w_log, dtype=torch.float32)
     model = model.cuda()
     est, logits = model(mix.cuda(), ref.cuda(), torch.tensor(float(Tr)))
     assert est.requires_grad and logits.requires_grad
     assert O.peak_rel_err(est.detach().cpu(), est_o.float()) < 2e-5
     loss = (est * w_est.cuda()).sum() + (logits * w_log.cuda()).sum()
     loss.backward()
-    worst = ('', 0.0)
+    worst = ('', 0.0, 0.0)
     for n, p in model.named_parameters():
         if not p.requires_grad:
             continue
@@ -55,10 +58,11 @@ def test_backward_matches_oracle_autograd(fusion, extra):
         want = grads_o[n].float()
         denom = max(float(want.abs().max()), 1e-6 * max(float(v.abs().max()) for v in grads_o.values()))
         err = float((p.grad.cpu() - want).abs().max()) / denom
+        fl = float((floor[n].float() - want).abs().max()) / denom
         if err > worst[1]:
-            worst = (n, err)
-        assert err < 2e-3, (n, err)
-    print('worst gradient error', worst)
+            worst = (n, err, fl)
+        assert err < max(2e-3, 6 * fl), (n, err, fl)          # 2e-3, or 6x the parameter's fp32 noise floor where that is larger
+    print('worst gradient error (parameter, error, fp32 noise floor of torch autograd)', worst)
 
 
 def test_backward_tensor_core_mode():

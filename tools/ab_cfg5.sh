@@ -9,11 +9,10 @@ import json
 try:
     d = json.load(open('$O/ab_cfg5_$name.json'))
     pk = d.get('kernels', {})
-    top = sorted(pk.items(), key=lambda kv: -kv[1]['ms_total'])[:7]
+    top = sorted(pk.items(), key=lambda kv: -kv[1]['ms_total'])[:14]
     print('$name', round(d['ms_per_step'], 2), 'ms/step', [(k.replace('dprnn_', ''), round(v['ms_avg'], 3), v['launches']) for k, v in top])
 except Exception as e:
     print('$name', 'no line', e)
 PY
 }
 run default X=1
-run with_hf DPRNN_TRAIN_NO_HF=0

@@ -327,7 +327,18 @@ __global__ void __launch_bounds__(256) convw2_partial_kernel(const float* __rest
     const long rows = (long)B * L, per = (rows + gridDim.x - 1) / gridDim.x;
     const long r0 = (long)blockIdx.x * per, r1 = min(r0 + per, rows);
     float a0 = 0.f, a1 = 0.f;
-    for (long r = r0 + rl; r < r1; r += lanes) {
+    long r = r0 + rl;
+    for (; r + 3L * lanes < r1; r += 4L * lanes) {          // four independent loads in flight
+        float zv[4], s0[4], s1[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long rr = r + (long)u * lanes, b = rr / L, l = rr % L;
+            zv[u] = z[rr * N + c]; s0[u] = __ldg(sig + b * T + l); s1[u] = __ldg(sig + b * T + l + 1);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { a0 = fmaf(zv[u], s0[u], a0); a1 = fmaf(zv[u], s1[u], a1); }
+    }
+    for (; r < r1; r += lanes) {
         const long b = r / L, l = r % L;
         const float zv = z[r * N + c];
         a0 = fmaf(zv, sig[b * T + l], a0);
@@ -635,16 +646,17 @@ int dprnn_decoder_bwd(const float* dest, const float* wdec, float* dz, int B, lo
     return 0;
 }
 
-size_t dprnn_convw2_workspace_bytes(int N) { return (size_t)128 * N * 2 * sizeof(float); }
+constexpr int kConvwParts = 592;      // 4 blocks per SM
+size_t dprnn_convw2_workspace_bytes(int N) { return (size_t)kConvwParts * N * 2 * sizeof(float); }
 
 /* dw[c, j] (+)= sum_{b,l} z[b,l,c] * sig[b, l + j], j in {0,1}: the weight gradient of the kernel-2 stride-1 decoder
  * (z = mask*enc, sig = d est) and encoder (z = d enc * [enc > 0], sig = waveform). */
 int dprnn_convw2_grad(const float* z, const float* sig, int B, long L, int N, float* dw, int accumulate, void* workspace,
                       void* stream) {
     DPRNN_CHECK_ARG(z && sig && dw && workspace && B > 0 && L > 0 && N > 0 && 256 % N == 0);
-    convw2_partial_kernel<<<128, 256, 0, (cudaStream_t)stream>>>(z, sig, B, L, L + 1, N, (float*)workspace);
+    convw2_partial_kernel<<<kConvwParts, 256, 0, (cudaStream_t)stream>>>(z, sig, B, L, L + 1, N, (float*)workspace);
     DPRNN_CHECK_LAUNCH();
-    chunk_reduce_kernel<<<bgrid(2L * N, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, 128, 2L * N, dw, 2L * N,
+    chunk_reduce_kernel<<<bgrid(2L * N, 256), 256, 0, (cudaStream_t)stream>>>((const float*)workspace, kConvwParts, 2L * N, dw, 2L * N,
                                                                               2 * N, accumulate);
     DPRNN_CHECK_LAUNCH();
     return 0;

@@ -408,30 +408,48 @@ __global__ void att_rowscale_kernel(const float* __restrict__ sm, float* __restr
 // ------------------------------------------------------------------------------------------
 // speaker ResNet pieces
 // ------------------------------------------------------------------------------------------
-// per-channel partial sums over rows: partial[p][c] = {sum, sumsq}; blockDim = 256, C in {64,128,256}
+// per-channel partial sums over rows: partial[p][c] = {sum, sumsq}; blockDim = 256, C in {64,128,256}.  Thread = 4
+// consecutive channels (float4 loads), four independent loads in flight, fp32 over 16 rows then fp64; kBnParts blocks
+// (4 per SM: the 128-block scalar form of round 1 reached 0.4 TB/s).
+constexpr int kBnParts = 592;
 __global__ void __launch_bounds__(256) channel_stats_kernel(const float* __restrict__ y, double* __restrict__ partial,
                                                             long rows, int C) {
-    __shared__ double sh[2][256];
-    const int lanes = 256 / C;
-    const int c = threadIdx.x % C, rl = threadIdx.x / C;
+    __shared__ double sh[8][256];
+    const int c4n = C / 4, lanes = 256 / c4n;
+    const int c4 = threadIdx.x % c4n, rl = threadIdx.x / c4n;
     const long per = (rows + gridDim.x - 1) / gridDim.x;
     const long beg = blockIdx.x * per, end = min(beg + per, rows);
-    double ds = 0.0, dq = 0.0;
+    const float4* y4 = reinterpret_cast<const float4*>(y);
+    double ds[4] = {0.0, 0.0, 0.0, 0.0}, dq[4] = {0.0, 0.0, 0.0, 0.0};
     long r = beg + rl;
     while (r < end) {
-        float s = 0.f, q = 0.f;
-        for (int u = 0; u < 32 && r < end; ++u, r += lanes) {
-            const float v = y[r * C + c];
-            s += v; q = fmaf(v, v, q);
+        float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+        auto acc = [&](const float4 v) {
+            s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+            q.x = fmaf(v.x, v.x, q.x); q.y = fmaf(v.y, v.y, q.y); q.z = fmaf(v.z, v.z, q.z); q.w = fmaf(v.w, v.w, q.w);
+        };
+        int u = 0;
+        for (; u < 4 && r + 3L * lanes < end; ++u, r += 4L * lanes) {
+            const float4 v0 = ld_stream(y4 + r * c4n + c4), v1 = ld_stream(y4 + (r + lanes) * c4n + c4);
+            const float4 v2 = ld_stream(y4 + (r + 2L * lanes) * c4n + c4), v3 = ld_stream(y4 + (r + 3L * lanes) * c4n + c4);
+            acc(v0); acc(v1); acc(v2); acc(v3);
         }
-        ds += (double)s; dq += (double)q;
+        if (u < 4)
+            for (; r < end; r += lanes) acc(ld_stream(y4 + r * c4n + c4));
+        ds[0] += (double)s.x; ds[1] += (double)s.y; ds[2] += (double)s.z; ds[3] += (double)s.w;
+        dq[0] += (double)q.x; dq[1] += (double)q.y; dq[2] += (double)q.z; dq[3] += (double)q.w;
     }
-    sh[0][threadIdx.x] = ds; sh[1][threadIdx.x] = dq;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { sh[k][threadIdx.x] = ds[k]; sh[4 + k][threadIdx.x] = dq[k]; }
     __syncthreads();
     if (rl == 0) {
-        for (int i = 1; i < lanes; ++i) { ds += sh[0][i * C + c]; dq += sh[1][i * C + c]; }
-        partial[((long)blockIdx.x * C + c) * 2 + 0] = ds;
-        partial[((long)blockIdx.x * C + c) * 2 + 1] = dq;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            double a = ds[k], b2 = dq[k];
+            for (int i = 1; i < lanes; ++i) { a += sh[k][i * c4n + c4]; b2 += sh[4 + k][i * c4n + c4]; }
+            partial[((long)blockIdx.x * C + c4 * 4 + k) * 2 + 0] = a;
+            partial[((long)blockIdx.x * C + c4 * 4 + k) * 2 + 1] = b2;
+        }
     }
 }
 
@@ -760,7 +778,7 @@ int dprnn_att_rowscale(const float* enc, const float* s1, const float* s0, const
     return 0;
 }
 
-size_t dprnn_bn_workspace_bytes(int C) { return (size_t)kStatParts * C * 2 * sizeof(double); }
+size_t dprnn_bn_workspace_bytes(int C) { return (size_t)kBnParts * C * 2 * sizeof(double); }
 
 int dprnn_batchnorm_affine(const float* y, long rows, int C, const float* weight, const float* bias,
                            float* running_mean, float* running_var, int training, float eps, float momentum,
@@ -768,12 +786,13 @@ int dprnn_batchnorm_affine(const float* y, long rows, int C, const float* weight
     DPRNN_CHECK_ARG(weight && bias && scale && shift && C > 0 && 256 % C == 0);
     if (training) {
         DPRNN_CHECK_ARG(y && workspace && rows > 0);
-        channel_stats_kernel<<<kStatParts, 256, 0, (cudaStream_t)stream>>>(y, (double*)workspace, rows, C);
+        DPRNN_CHECK_ARG(C % 4 == 0 && (uintptr_t)y % 16 == 0);
+        channel_stats_kernel<<<kBnParts, 256, 0, (cudaStream_t)stream>>>(y, (double*)workspace, rows, C);
         DPRNN_CHECK_LAUNCH();
     } else {
         DPRNN_CHECK_ARG(running_mean && running_var);
     }
-    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>((const double*)workspace, kStatParts,
+    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>((const double*)workspace, kBnParts,
                                                                      (double)rows, weight, bias, running_mean,
                                                                      running_var, scale, shift, C, training, eps,
                                                                      momentum);
