@@ -460,15 +460,22 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partial, int npart
                                    float* __restrict__ running_mean, float* __restrict__ running_var,
                                    float* __restrict__ scale, float* __restrict__ shift, int C, int training,
                                    float eps, float momentum) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    // one warp per channel: lane l adds every 32nd partial, then a shuffle tree (fixed order: deterministic)
+    const int c = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     if (c >= C) return;
     float mean, var;
     if (training) {
         double s = 0.0, q = 0.0;
-        for (int p = 0; p < nparts; ++p) {
+        for (int p = lane; p < nparts; p += 32) {
             s += partial[((long)p * C + c) * 2 + 0];
             q += partial[((long)p * C + c) * 2 + 1];
         }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (lane != 0) return;
         const double m = s / count;
         double v = q / count - m * m;
         if (v < 0.0) v = 0.0;
@@ -479,6 +486,7 @@ __global__ void bn_finalize_kernel(const double* __restrict__ partial, int npart
             running_var[c] = (1.f - momentum) * running_var[c] + momentum * (float)unb;
         }
     } else {
+        if (lane != 0) return;
         mean = running_mean[c]; var = running_var[c];
     }
     const float sc = weight[c] / sqrtf(var + eps);
@@ -792,7 +800,7 @@ int dprnn_batchnorm_affine(const float* y, long rows, int C, const float* weight
     } else {
         DPRNN_CHECK_ARG(running_mean && running_var);
     }
-    bn_finalize_kernel<<<cdiv(C, 128), 128, 0, (cudaStream_t)stream>>>((const double*)workspace, kBnParts,
+    bn_finalize_kernel<<<cdiv(C, 4), 128, 0, (cudaStream_t)stream>>>((const double*)workspace, kBnParts,
                                                                      (double)rows, weight, bias, running_mean,
                                                                      running_var, scale, shift, C, training, eps,
                                                                      momentum);
