@@ -437,3 +437,50 @@ def test_ira_train_step_runs_and_learns():
     losses = [float(step.step(mix, ref, tgt.cuda(), spk, ref_len=T)[0]) for _ in range(8)]
     assert all(torch.isfinite(torch.tensor(losses)))
     assert losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize('kind,extra', [('ira', dict(fusion_type='cat')), ('spe', dict(fusion_type='att', bidirectional=False, norm_type='gLN')),
+                                        ('spe', dict(fusion_type='mul')), ('tasnet', {})])
+def test_tensor_core_training_variants(kind, extra):
+    """The tensor-core training mode (bf16 d gates, bf16-only h, one-pass weight gradients, ...) on the other model
+    classes and options - DPRNN-Spe-IRA (two core passes sharing weights), a unidirectional inter-RNN with gLN (keeps an
+    fp32 h), DPRNN-TasNet - against the exact fp32 mode of the same model on the same batch: gradient cosine > 0.999 over
+    all parameters, every parameter within 10 % peak-normalised (the mixed-precision tolerance of
+    test_backward_tensor_core_mode)."""
+    kw = dict(KW, **extra)
+    torch.manual_seed(51)
+    cls = {'ira': P.DPRNNSpeIRATasNet, 'spe': P.DPRNNSpeTasNet, 'tasnet': P.DPRNNTasNet}[kind]
+    model = cls(**kw).cuda().train()
+    g = torch.Generator().manual_seed(52)
+    B, T, Tr = 2, 4001, 3000                                        # 2 x 33 x 250 = 16 500 chunk positions
+    mix, ref = (0.05 * torch.randn(B, T, generator=g)).cuda(), (0.05 * torch.randn(B, Tr, generator=g)).cuda()
+    w_est, w_log = torch.randn(B, 2, T, generator=g).cuda(), torch.randn(B, 251, generator=g).cuda()
+
+    def run(precision):
+        model.precision = precision
+        model.zero_grad(set_to_none=True)
+        torch.manual_seed(53)
+        if kind == 'tasnet':
+            est = model(mix)
+            loss = (est * w_est).sum()
+        else:
+            est, logits = model(mix, ref, torch.tensor(float(Tr)))
+            loss = (est * w_est[:, 0]).sum() + (logits * w_log).sum()
+        loss.backward()
+        return est.detach().clone(), {n: p.grad.detach().clone() for n, p in model.named_parameters() if p.requires_grad}
+
+    # BatchNorm running statistics advance with every forward; the batch statistics used in train mode do not depend on them
+    est32, g32 = run('fp32')
+    est16, g16 = run('bf16')
+    assert float((est16 - est32).abs().max()) < 1e-2 * float(est32.abs().max())
+    dot = na = nb = 0.0
+    worst = ('', 0.0)
+    scale = max(float(v.abs().max()) for v in g32.values())
+    for n, want in g32.items():
+        got = g16[n]
+        err = float((got - want).abs().max()) / max(float(want.abs().max()), 1e-6 * scale)
+        worst = max(worst, (n, err), key=lambda t: t[1])
+        dot += float((got.double() * want.double()).sum()); na += float(got.double().pow(2).sum()); nb += float(want.double().pow(2).sum())
+    print('tensor-core vs fp32 mode', kind, extra, 'worst', worst, 'cosine', dot / (na * nb) ** 0.5)
+    assert dot / (na * nb) ** 0.5 > 0.999
+    assert worst[1] < 0.10, worst
