@@ -230,47 +230,48 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
         // The step streams 7 float4 per (row, lane) through registers; with only 8 warps per SM the loads of the NEXT
         // (row pair | unit-half | step) are issued before the current one is computed (software double buffering).
         struct Ld { uint2 gi, gf, gg, go; float4 cv, cp, dho; };
+        // Row indices fit 32 bits (checked by the launcher): every address is base + (u32 row) * (u32 stride) + constant,
+        // one IMAD.WIDE each instead of 64-bit multiply chains (address arithmetic was 37 % of the executed instructions).
+        const int sstep = (int)p.step_stride;
+        const unsigned gstride = (unsigned)p.ndir * 128u, hstride = (unsigned)ldh;      // uint2 units / floats per row
+        auto gate_off = [&](int ph_) { const int u0 = ph_ * 64 + l16 * 4; return (unsigned)(dir * 128 + (u0 >> 3) * 8 + ((u0 >> 2) & 1)); };
+        auto ch_off = [&](int ph_) { return (unsigned)(dir * H + ph_ * 64 + l16 * 4); };
         auto issue = [&](int s_, int ph_, bool valid, int base_, Ld& L) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             const uint2 zu = make_uint2(0u, 0u);
             L.gi = zu; L.gf = zu; L.gg = zu; L.go = zu; L.cv = z; L.cp = z; L.dho = z;
             if (s_ < T && valid) {
-                const int fs = T - 1 - s_;
-                const int t_ = dir ? T - 1 - fs : fs;
-                const int tp = dir ? t_ + 1 : t_ - 1;
-                const long rowi = (long)base_ + (long)t_ * p.step_stride;
-                const int u0 = ph_ * 64 + l16 * 4;
+                const int t_ = dir ? s_ : T - 1 - s_;          // time of the forward step T-1-s_ in this direction's order
+                const unsigned R = (unsigned)(base_ + t_ * sstep), Rp = dir ? R + (unsigned)sstep : R - (unsigned)sstep;
                 // chunk = u0 / 8 (8 uint2 each: 2 per gate), 4-unit half (u0 / 4) & 1 inside it
-                const uint2* g = p.gates + ((rowi * p.ndir + dir) * 16 + (u0 >> 3)) * 8 + ((u0 >> 2) & 1);
+                const uint2* g = p.gates + (size_t)R * gstride + gate_off(ph_);
                 L.gi = __ldg(g); L.gf = __ldg(g + 2); L.gg = __ldg(g + 4); L.go = __ldg(g + 6);
-                if (!kKeepC || s_ == 0) L.cv = *reinterpret_cast<const float4*>(p.cstate + rowi * ldh + dir * H + u0);
-                if (fs > 0)
-                    L.cp = *reinterpret_cast<const float4*>(p.cstate + ((long)base_ + (long)tp * p.step_stride) * ldh + dir * H + u0);
-                L.dho = ld_stream(reinterpret_cast<const float4*>(p.dh_out + rowi * ldh + dir * H + u0));
+                const unsigned co = ch_off(ph_);
+                if (!kKeepC || s_ == 0) L.cv = *reinterpret_cast<const float4*>(p.cstate + (size_t)R * hstride + co);
+                if (s_ < T - 1) L.cp = *reinterpret_cast<const float4*>(p.cstate + (size_t)Rp * hstride + co);
+                L.dho = ld_stream(reinterpret_cast<const float4*>(p.dh_out + (size_t)R * hstride + co));
             }
         };
         // L2 prefetch of the step after the next one's register prefetch can reach: the addresses of every step are known up
         // front, so DRAM latency is taken off the recurrence's critical path (two lanes per half-warp cover its two lines)
         auto prefetch_step = [&](int s_) {
             if (s_ >= T || (l16 & 7) != 0) return;
-            const int fs = T - 1 - s_;
-            const int t_ = dir ? T - 1 - fs : fs;
-            const int tp = dir ? t_ + 1 : t_ - 1;
+            const int t_ = dir ? s_ : T - 1 - s_;
 #pragma unroll
             for (int it = 0; it < ITS; ++it) {
                 if (!ok[it]) continue;
-                const long rowi = (long)base[it] + (long)t_ * p.step_stride;
+                const unsigned R = (unsigned)(base[it] + t_ * sstep), Rp = dir ? R + (unsigned)sstep : R - (unsigned)sstep;
 #pragma unroll
                 for (int pi_ = 0; pi_ < NPH; ++pi_) {
-                    const int u0 = (ph0 + pi_) * 64 + l16 * 4;
                     // packed gates: 512 B = 4 lines per (row, direction, unit-half); lanes 0 and 8 of the half-warp fetch two
                     // consecutive lines each (chunks 0-3 / 4-7)
-                    const uint2* g = p.gates + ((rowi * p.ndir + dir) * 16 + (u0 >> 3)) * 8;
+                    const uint2* g = p.gates + (size_t)R * gstride + (gate_off(ph0 + pi_) & ~7u);
+                    const unsigned co = ch_off(ph0 + pi_);
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(g));
                     asm volatile("prefetch.global.L2 [%0];" ::"l"(g + 16));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dh_out + rowi * ldh + dir * H + u0));
-                    if (fs > 0)     // c_{t-1} of that step (it is c_t of the step after it)
-                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cstate + ((long)base[it] + (long)tp * p.step_stride) * ldh + dir * H + u0));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dh_out + (size_t)R * hstride + co));
+                    if (s_ < T - 1)     // c_{t-1} of that step (it is c_t of the step after it)
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.cstate + (size_t)Rp * hstride + co));
                 }
             }
         };
@@ -318,7 +319,7 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                         ckeep[it] = cur.cp;
                     }
                     const int row = rq + it * 2 + hw;
-                    const long rowi = (long)base[it] + (long)t * p.step_stride;
+                    const unsigned rowi = (unsigned)(base[it] + t * sstep);
                     float4 dhr = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (s > 0) dhr = *reinterpret_cast<const float4*>(stgw + (it * 2 + hw) * STG_LD + l16 * 4);
                     auto unpack = [](uint2 v, float (&o)[4]) {
@@ -343,7 +344,7 @@ lstm_bptt_tc_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_consta
                         dc[pi][it][u] = dct * fa[u];
                     }
                     if (!kOutBf16 && ok[it]) {
-                        float* o = p.dgates + rowi * ldg + dir * G4 + u0;
+                        float* o = p.dgates + (size_t)rowi * (unsigned)ldg + (unsigned)(dir * G4 + u0);
                         st_stream4(o, dpi[0], dpi[1], dpi[2], dpi[3]);
                         st_stream4(o + H, dpf[0], dpf[1], dpf[2], dpf[3]);
                         st_stream4(o + 2 * H, dpg[0], dpg[1], dpg[2], dpg[3]);

@@ -154,7 +154,7 @@ __device__ __forceinline__ void lstm_cell8(uint32_t tcol, const float* __restric
             // c / h: 16-byte chunk j/4 of the row's 32 bytes, SWIZZLE_32B (chunk ^= bit 7 of the byte offset = bit 2 of the row)
             const uint32_t o32 = (uint32_t)lane * 32 + (uint32_t)(((j >> 2) ^ ((lane >> 2) & 1)) << 4);
             *reinterpret_cast<float4*>(stg + 2048 + o32) = make_float4(sv[4][0], sv[4][1], sv[4][2], sv[4][3]);
-            *reinterpret_cast<float4*>(stg + 3072 + o32) = make_float4(hv[0], hv[1], hv[2], hv[3]);
+            if (hdst) *reinterpret_cast<float4*>(stg + 3072 + o32) = make_float4(hv[0], hv[1], hv[2], hv[3]);   // hdst: only "h wanted"
             if (j == 4) {
                 // gates: chunk g (8 units of gate g) of the row's 64 bytes, SWIZZLE_64B (chunk ^= bits 7..8 = bits 1..2 of the row)
 #pragma unroll

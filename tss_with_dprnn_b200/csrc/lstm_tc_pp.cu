@@ -298,7 +298,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 if constexpr (kStage) {
                     uint8_t* buf = stage_buf();
                     lstm_cell8<kFastAct, kTrain, 32, kF16, true>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g],
-                                                                 nullptr, nullptr, nullptr, buf, lane);
+                                                                 nullptr, nullptr, p.hf, buf, lane);
                     stage_done();
                 } else {
                     lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 8 * g, sbias + ub * 32 + 8 * g, c0 + 8 * g, pk[g],
@@ -326,7 +326,7 @@ lstm_tc_pp_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
                 if constexpr (kStage) {
                     uint8_t* buf = stage_buf();
                     lstm_cell8<kFastAct, kTrain, 32, kF16, true>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g,
-                                                                 pk[g], nullptr, nullptr, nullptr, buf, lane);
+                                                                 pk[g], nullptr, nullptr, p.hf, buf, lane);
                     stage_done();
                 } else {
                     lstm_cell8<kFastAct, kTrain, 32, kF16>(tlane + 128 + 8 * g, sbias + 256 + ub * 32 + 8 * g, c1s + 8 * g, pk[g],
