@@ -547,7 +547,8 @@ size_t dprnn_gn_bwd_workspace_bytes(int B, int C);
 int dprnn_groupnorm_bwd(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
                         long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
                         void* workspace, void* stream);
-/* The same, also writing a bf16 copy of dy (the operand of the Linear's bf16 weight-gradient pass). */
+/* The same, also writing a bf16 copy of dy (the operand of the Linear's bf16 weight-gradient pass and of d h = dy W);
+ * dy may then be NULL (accumulate_dy = 0): only the bf16 copy is written. */
 int dprnn_groupnorm_bwd_h16(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
                             long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
                             void* workspace, void* dy_bf16, void* stream);

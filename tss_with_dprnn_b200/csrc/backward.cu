@@ -216,7 +216,7 @@ __global__ void gn_bwd_apply_kernel(const float* __restrict__ dz, const float* _
             const float4 a = reinterpret_cast<const float4*>(dy)[idx];
             o.x += a.x; o.y += a.y; o.z += a.z; o.w += a.w;
         }
-        reinterpret_cast<float4*>(dy)[idx] = o;
+        if (dy) reinterpret_cast<float4*>(dy)[idx] = o;          // dy == NULL: only the bf16 copy is wanted
         if (dy_bf16) {          // bf16 copy: the operand of the Linear's weight-gradient pass (dprnn_gemm_atb_dual, bf16 form)
             const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
             dy_bf16[idx] = make_uint2(*reinterpret_cast<const uint32_t*>(&lo), *reinterpret_cast<const uint32_t*>(&hi));
@@ -553,7 +553,8 @@ size_t dprnn_gn_bwd_workspace_bytes(int B, int C) { return (size_t)B * 64 * (2 *
 static int gn_bwd_impl(const float* dz, const float* y, const float* mean_rstd, const float* gamma, int B,
                        long rows_per_utt, int C, float* dy, int accumulate_dy, float* dgamma, float* dbeta,
                        void* workspace, void* dy_bf16, void* stream) {
-    DPRNN_CHECK_ARG(dz && y && mean_rstd && gamma && dy && dgamma && dbeta && workspace && B > 0 && B <= 65535);
+    DPRNN_CHECK_ARG(dz && y && mean_rstd && gamma && (dy || (dy_bf16 && !accumulate_dy)) && dgamma && dbeta && workspace && B > 0 &&
+                    B <= 65535);
     DPRNN_CHECK_ARG(rows_per_utt > 0 && C % 4 == 0 && 256 % C == 0);
     cudaStream_t st = (cudaStream_t)stream;
     const int nparts = 64;

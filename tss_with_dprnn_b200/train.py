@@ -179,11 +179,11 @@ class _Ops:
         self.L.call('dprnn_utt_stats', x, B, elems, float(eps), ws, mr, _st())
         return mr
 
-    def gn_bwd(self, dz, y, mr, gamma, B, rows_per_utt, C, dgamma, dbeta, dy=None, accumulate_dy=False, dy16=None):
+    def gn_bwd(self, dz, y, mr, gamma, B, rows_per_utt, C, dgamma, dbeta, dy=None, accumulate_dy=False, dy16=None, only16=False):
         ws = torch.empty(self.L.query('dprnn_gn_bwd_workspace_bytes', B, C), device=self.dev, dtype=torch.uint8)
-        if dy is None:
+        if dy is None and not only16:
             dy = self.empty(B * rows_per_utt, C)
-        if dy16 is not None:       # also a bf16 copy of dy
+        if dy16 is not None:       # also (only16: only) a bf16 copy of dy
             self.L.call('dprnn_groupnorm_bwd_h16', dz, y, mr, gamma, B, rows_per_utt, C, dy, int(accumulate_dy), dgamma, dbeta,
                         ws, dy16, _st())
         else:
@@ -367,7 +367,8 @@ def _core_fwd(model, ops, enc, mr_e, emb, B, Lm, spks):
     dg16 = ops.dg16 and F == 128 and H == 128 and rows >= 4096
     # ... and with every layer bidirectional h is kept as bf16 only: the Linear and its weight gradient read that copy
     nohf = (dg16 and _NO_HF and model._engine.lstm_pingpong and all(blk.intra_rnn.rnn.bidirectional and blk.inter_rnn.rnn.bidirectional for blk in sep.dprnn_blocks)
-            and bool(ops.L.query('dprnn_gemm_persist_supported', 1, F, 2 * H, EPI_NONE)))
+            and bool(ops.L.query('dprnn_gemm_persist_supported', 1, F, 2 * H, EPI_NONE))
+            and bool(ops.L.query('dprnn_gemm_persist_supported', 1, 2 * H, F, EPI_NONE)))
     xb = hb = None
     for blk in sep.dprnn_blocks:
         for which, (rnn, linm, nm) in enumerate(((blk.intra_rnn.rnn, blk.intra_linear, blk.intra_norm),
@@ -669,7 +670,7 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
             del xs_out
         nohf = c['nohf']
         dy16 = torch.empty((rows, F), device=dev, dtype=torch.bfloat16) if nohf else None
-        dy = ops.gn_bwd(dx, yl, mr, g_.detach(), B, S * K, F, G[gname], G[bname], dy16=dy16)
+        dy = ops.gn_bwd(dx, yl, mr, g_.detach(), B, S * K, F, G[gname], G[bname], dy16=dy16, only16=nohf)
         ln = names[id(hv['lin'])]
         hout = hv['hout']
 
@@ -692,7 +693,10 @@ def _core_bwd(model, ops, c, dms, enc, mr_e, denc, demb, G):
             ops.atb(dy, hout, rows, F, nd * H, G[ln + '.weight'])
             ops.colsum(dy, rows, F, G[ln + '.bias'])
         on_side(lin_grads, *((dy16, hv['hb']) if nohf else (dy, hout)))
-        dh = ops.mm(dy, hv['lin'].weight.detach().t().contiguous(), rows, nd * H, F)
+        if nohf:       # d h = dy W_lin with bf16 operands (dy exists as bf16 only)
+            dh = ops.mm16(dy16, hv['lin'].weight.detach().t().contiguous(), rows, nd * H, F)
+        else:
+            dh = ops.mm(dy, hv['lin'].weight.detach().t().contiguous(), rows, nd * H, F)
         del dy
         dgates = torch.empty((rows, nd * 4 * H), device=dev, dtype=torch.bfloat16 if dg16 else torch.float32)
         if ops.tf32:
