@@ -639,13 +639,16 @@ def run_ours(args):
                 fn(i)
             barrier()
             ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            marks = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]     # end of every step: median / best
             n0 = L.launches
             ev0.record()
             for i in range(steps):
                 fn(i)
+                marks[i].record()
             ev1.record()
             barrier()
             ms = ev0.elapsed_time(ev1)
+            timed.per_step = [a.elapsed_time(b) for a, b in zip([ev0] + marks[:-1], marks)]
         return ms, L.launches - n0
 
     from tss_with_dprnn_b200.sharding import reduce_timing
@@ -657,6 +660,7 @@ def run_ours(args):
         # every distinct step is warmed up at least once (ragged layouts, tensor maps, allocator pools)
         ms_local, launches = timed(wl.resident, steps_local, max(args.warmup, wl.n_steps))
     clocks = clk.summary()
+    step_ms = sorted(timed.per_step)          # this rank's steps of the timed region (median and best)
     ms_total, audio_steps = reduce_timing(ms_local, audio_local, dev)     # max over ranks of device time, whole-job audio
     ms_local_e2e, _ = timed(wl.e2e, steps_local, max(1, wl.n_steps))
     ms_e2e, _ = reduce_timing(ms_local_e2e, audio_local, dev)
@@ -815,6 +819,8 @@ def run_ours(args):
             'ranks': {'ms': rank_ms, 'imbalance_max_over_mean': max(rank_ms) / (sum(rank_ms) / len(rank_ms)),
                       'steps_rank0': steps_local},
             'build': L.build_info(),
+            # rank 0's own steps inside the timed region (events at the end of every step on the launching stream)
+            'step_ms': {'median': step_ms[len(step_ms) // 2], 'best': step_ms[0], 'worst': step_ms[-1]},
         }
         if modes is not None:
             line['modes'] = modes

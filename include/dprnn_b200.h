@@ -83,9 +83,19 @@ int dprnn_norm_residual_h16res(const void* y_h16, void* x_h16, float* x_f32_out,
  * y [B,L,F] -> x [B,S,K,F], x[b,s,k,:] = y[b, s*P+k-K, :] or 0. S = dprnn_num_chunks(L,K,P). Bit-exact. */
 int dprnn_num_chunks(long L, int K, int P);
 int dprnn_unfold(const float* y, float* x, int B, long L, int K, int P, int F, void* stream);
-/* Same, also writing the bf16 copy x_bf16 [B,S,K,F] (operand of the first tensor-core LSTM layer). */
+/* Same, also writing the bf16 copy x_bf16 [B,S,K,F] (operand of the first tensor-core LSTM layer); x may be NULL when the
+ * residual stream is kept in 16 bits only (nothing reads the fp32 copy before the last half-block rewrites it). */
 int dprnn_unfold_bf16(const float* y, float* x, void* x_bf16, int B, long L, int K, int P, int F, void* stream);
 int dprnn_unfold_h16(const float* y, float* x, void* x_h16, int B, long L, int K, int P, int F, int h16, void* stream);
+
+/* The last half-block's norm + residual (src/models/dprnn.py:98-99) + self.prelu + DPRNN._overlap_add (:174,203-217) in
+ * one pass over the 16-bit residual stream: out[b,t,:] = sum over the (at most two) chunks s covering t of
+ * prelu(float(x_h16[b,s,k,:]) + norm_b(float(y_h16[b,s,k,:]))), k = t + K - s*P.  y_h16 / x_h16 [B,S,K,F] in the format
+ * h16, mean_rstd [B,2], out [B,L,F] fp32, F a multiple of 8.  Bit for bit dprnn_norm_residual_h16res (fp32 output) followed
+ * by dprnn_fold_prelu, without the fp32 [B,S,K,F] tensor between them. */
+int dprnn_norm_residual_fold_prelu_h16(const void* y_h16, const void* x_h16, const float* mean_rstd, const float* gamma,
+                                       const float* beta, float* out, int B, long L, int K, int P, int F,
+                                       const float* prelu_a, int h16, void* stream);
 
 /* self.prelu + DPRNN._overlap_add, src/models/dprnn.py:174,203-217 (F.fold, plain sum):
  * x [B,S,K,F] -> out [B,L,F]. prelu_a (1 float, device) may be NULL for a pure fold. */

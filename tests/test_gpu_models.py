@@ -267,3 +267,28 @@ def test_fused_input_norm_whole_model_bit_identical(precision, cls):
     (a, na), (b, nb) = outs
     assert all(torch.equal(x, y) for x, y in zip(a, b))
     assert nb - na == (3 if cls != 'ira' else 6)          # one norm launch less per half-block but the last (2 blocks)
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+@pytest.mark.parametrize('cls', ['spe', 'ira', 'bss'])
+def test_fold_fused_whole_model_bit_identical(precision, cls):
+    """Engine.fold_fused (default): the last half-block's norm + residual applied by the fold, no fp32 [B,S,K,F] tensor -
+    no bit changes against the separate kernels, two launches become one per masker pass."""
+    torch.manual_seed(11)
+    kw = dict(KW, n_repeats=2)
+    model = {'spe': lambda: P.DPRNNSpeTasNet(**kw, fusion_type='att'), 'ira': lambda: P.DPRNNSpeIRATasNet(**kw, fusion_type='cat'),
+             'bss': lambda: P.DPRNNTasNet(**kw)}[cls]().eval().cuda()
+    model.precision = precision
+    g = torch.Generator().manual_seed(12)
+    mix, ref = (0.05 * torch.randn(3, 5001, generator=g)).cuda(), (0.05 * torch.randn(3, 4000, generator=g)).cuda()
+    args = (mix,) if cls == 'bss' else (mix, ref, torch.tensor(4000.))
+    outs = []
+    with torch.no_grad():
+        for fused in (True, False):
+            model._engine.fold_fused = fused
+            n0 = P.lib().launches
+            o = model(*args)
+            outs.append(((o,) if cls == 'bss' else o, P.lib().launches - n0))
+    (a, na), (b, nb) = outs
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert nb - na == (1 if cls != 'ira' else 2)

@@ -490,3 +490,35 @@ def test_linear_normres_one_launch_is_bit_identical(B, R, K, fmt, discard):
         torch.cuda.synchronize()
         assert torch.equal(mr2, mr)
         assert torch.equal(got, want)
+
+
+@pytest.mark.parametrize('B,L,K,P_', [(2, 1337, 100, 50), (1, 23999, 250, 125), (3, 249, 250, 125), (2, 1, 20, 10)])
+@pytest.mark.parametrize('fmt', ['bf16', 'fp16'])
+def test_last_norm_residual_fold_prelu_one_pass_is_bit_identical(B, L, K, P_, fmt):
+    """dprnn_norm_residual_fold_prelu_h16 (last half-block's norm + residual + PReLU + overlap-add in one pass over the
+    16-bit tensors, dprnn.py:98-99,174,203-217) against the two kernels it replaces and against F.fold in fp64."""
+    F = 128
+    lib = P.lib()
+    h16 = 1 if fmt == 'fp16' else 0
+    dt = torch.float16 if h16 else torch.bfloat16
+    S = lib.query('dprnn_num_chunks', L, K, P_)
+    rows = B * S * K
+    y = rnd(rows, F, seed=L).to(dt).to(DEV)
+    xb = (0.5 * rnd(rows, F, seed=L + 1)).to(dt).to(DEV)
+    mr = torch.stack([0.1 * rnd(B, seed=2), 1 + 0.2 * rnd(B, seed=3).abs()], 1).contiguous().to(DEV)
+    gamma, beta = (1 + 0.1 * rnd(F, seed=4)).to(DEV), (0.1 * rnd(F, seed=6)).to(DEV)
+    a = torch.tensor([0.25], device=DEV)
+    xf = torch.full((rows, F), float('nan'), device=DEV)
+    lib.call('dprnn_norm_residual_h16res', y, xb.clone(), xf, mr, gamma, beta, B, S * K, F, h16, stream())
+    want = torch.full((B, L, F), float('nan'), device=DEV)
+    lib.call('dprnn_fold_prelu', xf, want, B, L, K, P_, F, a, stream())
+    got = torch.full((B, L, F), float('nan'), device=DEV)
+    lib.call('dprnn_norm_residual_fold_prelu_h16', y, xb, mr, gamma, beta, got, B, L, K, P_, F, a, h16, stream())
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    # ... and the composition itself against torch in fp64
+    v = xb.double().cpu() + ((y.double().cpu().view(B, -1) - mr[:, :1].double().cpu()) * mr[:, 1:].double().cpu()).view(rows, F) \
+        * gamma.double().cpu() + beta.double().cpu()
+    v = torch.where(v >= 0, v, 0.25 * v).view(B, S, K, F).permute(0, 3, 2, 1).reshape(B, F * K, S)
+    ref = torch.nn.functional.fold(v, ((S - 1) * P_ + K, 1), kernel_size=(K, 1), stride=(P_, 1))[:, :, K:K + L, 0]
+    assert O.peak_rel_err(got.cpu().double().transpose(1, 2), ref) < 1e-6

@@ -245,7 +245,7 @@ __global__ void unfold_kernel(const float* __restrict__ y, float* __restrict__ o
         const long t = (long)s * P + k - K;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t >= 0 && t < L) v = __ldg(reinterpret_cast<const float4*>(y) + (b * L + t) * f4n + f4);
-        reinterpret_cast<float4*>(out)[idx] = v;
+        if (out) reinterpret_cast<float4*>(out)[idx] = v;      // out == NULL: only the 16-bit copy is wanted
         if (out_bf16)        // 16-bit shadow for the first tensor-core LSTM layer (saves a separate cast pass)
             out_bf16[idx] = make_uint2(pack_h16x2<kF16>(v.x, v.y), pack_h16x2<kF16>(v.z, v.w));
     }
@@ -273,6 +273,58 @@ __global__ void fold_prelu_kernel(const float* __restrict__ x, float* __restrict
             acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
         }
         reinterpret_cast<float4*>(out)[idx] = acc;
+    }
+}
+
+// The last half-block's norm + residual (16-bit residual stream), the PReLU and the fold in ONE pass: every (s, k) position
+// of the last Linear output feeds exactly one output frame, so x + norm(y) never has to exist as an fp32 [B,S,K,F] tensor
+// (written by norm_residual_bf16res_kernel and read back by fold_prelu_kernel: 2 x 1.59 GB at B = 64).  Same arithmetic
+// in the same order as those two kernels (norm_res1, predicated multiply, sum over s ascending): bit-identical.
+template <bool kF16>
+__global__ void norm_residual_fold_prelu_kernel(const uint4* __restrict__ y, const uint4* __restrict__ xb,
+                                                const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                                const float* __restrict__ beta, float* __restrict__ out, int B, long L,
+                                                int S, int K, int P, int c8n, const float* __restrict__ prelu_a) {
+    const long total = (long)B * L * c8n;
+    const float a = prelu_a ? __ldg(prelu_a) : 1.0f;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(idx % c8n);
+        const long r = idx / c8n;
+        const long t = r % L, b = r / L;
+        const float mean = __ldg(mean_rstd + 2 * b), rstd = __ldg(mean_rstd + 2 * b + 1);
+        long s_lo = t / P + 1, s_hi = (t + K) / P;
+        if (s_hi > S - 1) s_hi = S - 1;
+        float g[8], be[8], acc[8];
+        {
+            const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8), g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c8 + 1);
+            const float4 e0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8), e1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c8 + 1);
+            g[0] = g0.x; g[1] = g0.y; g[2] = g0.z; g[3] = g0.w; g[4] = g1.x; g[5] = g1.y; g[6] = g1.z; g[7] = g1.w;
+            be[0] = e0.x; be[1] = e0.y; be[2] = e0.z; be[3] = e0.w; be[4] = e1.x; be[5] = e1.y; be[6] = e1.z; be[7] = e1.w;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) acc[i] = 0.f;
+        for (long s = s_lo; s <= s_hi; ++s) {
+            const long k = t + K - s * P;
+            const long e = ((b * S + s) * K + k) * c8n + c8;
+            uint4 yv;
+            asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(yv.x), "=r"(yv.y), "=r"(yv.z), "=r"(yv.w) : "l"(y + e));
+            const uint4 xv = __ldg(xb + e);
+            const uint32_t yw[4] = {yv.x, yv.y, yv.z, yv.w}, xw[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float2 yf = unpack_h16x2<kF16>(yw[q]), xf = unpack_h16x2<kF16>(xw[q]);
+                float v0 = norm_res1(xf.x, yf.x, mean, rstd, g[2 * q], be[2 * q]);
+                float v1 = norm_res1(xf.y, yf.y, mean, rstd, g[2 * q + 1], be[2 * q + 1]);
+                v0 = v0 >= 0.f ? v0 : __fmul_rn(a, v0);
+                v1 = v1 >= 0.f ? v1 : __fmul_rn(a, v1);
+                acc[2 * q] = __fadd_rn(acc[2 * q], v0);
+                acc[2 * q + 1] = __fadd_rn(acc[2 * q + 1], v1);
+            }
+        }
+        float4* o = reinterpret_cast<float4*>(out) + idx * 2;
+        o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+        o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
 }
 
@@ -722,7 +774,7 @@ int dprnn_unfold(const float* y, float* x, int B, long L, int K, int P, int F, v
 }
 
 int dprnn_unfold_h16(const float* y, float* x, void* x_h16, int B, long L, int K, int P, int F, int h16, void* stream) {
-    DPRNN_CHECK_ARG(y && x && x_h16 && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);
+    DPRNN_CHECK_ARG(y && x_h16 && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);      // x may be NULL
     DPRNN_CHECK_H16(h16);
     const int S = dprnn_num_chunks(L, K, P);
     auto kern = h16 ? unfold_kernel<true> : unfold_kernel<false>;
@@ -741,6 +793,20 @@ int dprnn_fold_prelu(const float* x, float* out, int B, long L, int K, int P, in
     const int S = dprnn_num_chunks(L, K, P);
     fold_prelu_kernel<<<grid_for((long)B * L * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(x, out, B, L, S, K, P,
                                                                                            F / 4, prelu_a);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_norm_residual_fold_prelu_h16(const void* y_h16, const void* x_h16, const float* mean_rstd, const float* gamma,
+                                       const float* beta, float* out, int B, long L, int K, int P, int F,
+                                       const float* prelu_a, int h16, void* stream) {
+    DPRNN_CHECK_ARG(y_h16 && x_h16 && mean_rstd && gamma && beta && out && B > 0 && L > 0 && K > 0 && P > 0 && F % 8 == 0);
+    DPRNN_CHECK_ARG(((uintptr_t)y_h16 | (uintptr_t)x_h16 | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) % 16 == 0);
+    DPRNN_CHECK_H16(h16);
+    const int S = dprnn_num_chunks(L, K, P);
+    auto kern = h16 ? norm_residual_fold_prelu_kernel<true> : norm_residual_fold_prelu_kernel<false>;
+    kern<<<grid_for((long)B * L * (F / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint4*)y_h16, (const uint4*)x_h16, mean_rstd, gamma, beta, out, B, L, S, K, P, F / 8, prelu_a);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

@@ -51,6 +51,10 @@ class Engine(RaggedMixin):
         # only lives in L2 (linear_normres.cu; bit-identical to the two kernels); 2 = also discard y from L2 after its use
         self.tail_l2 = int(os.environ.get('DPRNN_TAIL_L2', '0'))
         self.tail_lead = int(os.environ.get('DPRNN_TAIL_LEAD', '2'))    # utterances its Linear pass may run ahead of its norm pass
+        # tensor-core modes, 16-bit residual stream: the last half-block's norm + residual is applied by the fold
+        # (dprnn_norm_residual_fold_prelu_h16) and the unfold writes the 16-bit copy only, so the fp32 [B,S,K,F] tensor never
+        # exists (3 x 1.59 GB of HBM traffic per forward at B = 64); bit-identical to the separate kernels (DPRNN_FOLD_FUSED=0)
+        self.fold_fused = os.environ.get('DPRNN_FOLD_FUSED', '1') == '1'
         self._row_off = {}
         self._streams = []
         self.use_graphs = True     # eval forwards of a repeated shape are captured into a CUDA graph and replayed
@@ -491,9 +495,13 @@ class Engine(RaggedMixin):
             y = self.gemm(enc, W['bott_wt'], B * L, F, N, bias=bias, bias_per_utt=bias_per_utt, rows_per_utt=L,
                           p_scale=s1, p_shift=s0, p_add=addc, rowscale=rowscale)
         S = L_.query('dprnn_num_chunks', L, K, P)
-        x = torch.empty((B, S, K, F), device=dev)
         rows = B * S * K
         bf16 = self.tc
+        # 16-bit residual stream (the default of the tensor-core modes): the fp32 [B,S,K,F] tensor never exists - the unfold
+        # writes the 16-bit copy only and the last half-block's norm + residual is applied by the fold (_masker_post)
+        x16_only = bool(bf16 and self.residual_bf16 and not self.fused_tail and self.fold_fused and len(sep.dprnn_blocks) > 0
+                        and F % 8 == 0)
+        x = None if x16_only else torch.empty((B, S, K, F), device=dev)
         s = dict(B=B, L=L, S=S, K=K, P=P, F=F, H=H, N=N, rows=rows, x=x, bf16=bf16, dev=dev)
         if bf16:
             if H != 128 or F != 128:
@@ -599,7 +607,10 @@ class Engine(RaggedMixin):
         if self._fuses_norm() and not last:
             s['pending_norm'] = (g_, b_)        # applied by the next half-block's LSTM kernel
             return
-        if self.residual_bf16:      # default: residual stream in 16 bits only; the last half-block writes the fp32 x for the fold
+        if self.residual_bf16 and last and s['x'] is None:
+            s['pending_fold'] = (g_, b_)        # applied by the fold: dprnn_norm_residual_fold_prelu_h16 (_masker_post)
+            return
+        if self.residual_bf16:      # residual stream in 16 bits only; the last half-block writes the fp32 x for the fold
             lib().call('dprnn_norm_residual_h16res', s['ybuf'], s['xb'], s['x'] if last else None, s['mr2'], g_, b_,
                        s['B'], s['S'] * s['K'], s['F'], self.h16, self._stream())
             return
@@ -633,7 +644,12 @@ class Engine(RaggedMixin):
         cfg, sep = self.model.cfg, self.model.separation
         B, L, K, P, F, N, x, dev, bf16 = s['B'], s['L'], s['K'], s['P'], s['F'], s['N'], s['x'], s['dev'], s['bf16']
         z = torch.empty((B, L, F), device=dev)
-        L_.call('dprnn_fold_prelu', x, z, B, L, K, P, F, sep.prelu.weight.detach(), st)
+        pend = s.pop('pending_fold', None)
+        if pend is not None:        # last norm + residual + PReLU + overlap-add in one pass over the 16-bit tensors
+            L_.call('dprnn_norm_residual_fold_prelu_h16', s['ybuf'], s['xb'], s['mr2'], pend[0], pend[1], z, B, L, K, P, F,
+                    sep.prelu.weight.detach(), self.h16, st)
+        else:
+            L_.call('dprnn_fold_prelu', x, z, B, L, K, P, F, sep.prelu.weight.detach(), st)
         act = EPI_SIGMOID if cfg['activation_type'] == 'sigmoid' else EPI_RELU
         masks = []
         for spk in speakers:
@@ -669,7 +685,7 @@ class Engine(RaggedMixin):
         if not self.use_graphs or self.model.training or L_.timing is not None or torch.cuda.is_current_stream_capturing():
             return fn(*inputs)
         key = (tag, tuple((tuple(t.shape), t.dtype, t.device.index) for t in inputs), self.precision, self.n_streams,
-               self.fast_act, self.conv_mode, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self.fuse_norm, self.tail_l2, self.tail_lead, self._graph_key())
+               self.fast_act, self.conv_mode, self.fused_tail, self.lstm_slices, self.lstm_pairs, self.lstm_pingpong, self.residual_bf16, self.fuse_norm, self.tail_l2, self.tail_lead, self.fold_fused, self._graph_key())
         ent = self._graphs.get(key)
         if ent is None:
             self._graphs[key] = 'seen'
