@@ -343,6 +343,18 @@ int dprnn_unfold_ragged(const float* y, float* x, const int* chunk_utt, const lo
 int dprnn_fold_prelu_ragged(const float* x, float* out, const int* frame_utt, const long* frame_off, const long* L,
                             const long* chunk_off, const long* S, long total_rows, int K, int P, int F,
                             const float* prelu_a, void* stream);
+/* dprnn_unfold_ragged also writing the 16-bit copy x_h16 (the rounding of dprnn_cast_h16); x may be NULL when the residual
+ * stream is kept in 16 bits only. */
+int dprnn_unfold_ragged_h16(const float* y, float* x, void* x_h16, const int* chunk_utt, const long* chunk_off,
+                            const long* frame_off, const long* L, long total_chunks, int K, int P, int F, int h16,
+                            void* stream);
+/* dprnn_norm_residual_fold_prelu_h16 on packed ragged batches: bit for bit dprnn_norm_residual_ragged_h16res (fp32 output)
+ * followed by dprnn_fold_prelu_ragged, without the fp32 chunk-space tensor between them. */
+int dprnn_norm_residual_fold_prelu_ragged_h16(const void* y_h16, const void* x_h16, const float* mean_rstd,
+                                              const float* gamma, const float* beta, float* out, const int* frame_utt,
+                                              const long* frame_off, const long* L, const long* chunk_off, const long* S,
+                                              long total_rows, int K, int P, int F, const float* prelu_a, int h16,
+                                              void* stream);
 /* dprnn_mask_decode for stride 1: out[frame_off[b]+t], t < T_b. */
 int dprnn_mask_decode_ragged(const float* mask, const float* enc, const float* wdec, float* out, const int* frame_utt,
                              const long* frame_off, const long* L, long total_rows, int N, int ksz, void* stream);

@@ -84,3 +84,20 @@ def test_ragged_rejects_train_mode_and_stride():
     model = P.DPRNNSpeTasNet(**KW, fusion_type='cat').train().cuda()
     with pytest.raises(NotImplementedError):
         model.forward_ragged([torch.zeros(1000).cuda()], [torch.zeros(1000).cuda()])
+
+
+@pytest.mark.parametrize('precision', ['bf16', 'fp16'])
+def test_ragged_fold_fused_is_bit_identical(precision):
+    """Engine.fold_fused on packed batches (dprnn_unfold_ragged_h16 + dprnn_norm_residual_fold_prelu_ragged_h16): no fp32
+    chunk-space tensor, no bit changed against unfold + cast ... norm (fp32 out) + fold."""
+    torch.manual_seed(8)
+    model = P.DPRNNSpeTasNet(**KW, fusion_type='film').eval().cuda()
+    model.precision = precision
+    mixes, refs = waves([a for a, _ in LENS], 7), waves([b for _, b in LENS], 8)
+    outs = []
+    with torch.no_grad():
+        for fused in (True, False):
+            model._engine.fold_fused = fused
+            outs.append(model.forward_ragged([m.cuda() for m in mixes], [r.cuda() for r in refs]))
+    (e1, l1), (e2, l2) = outs
+    assert all(torch.equal(a, b) for a, b in zip(e1, e2)) and all(torch.equal(a, b) for a, b in zip(l1, l2))

@@ -156,10 +156,11 @@ __global__ void norm_residual_ragged_bf16res_kernel(const uint2* __restrict__ y,
 }
 
 // ---------------------------------------------------------------- unfold / fold between frame and chunk space
+template <bool kF16>
 __global__ void unfold_ragged_kernel(const float* __restrict__ y, float* __restrict__ out,
                                      const int* __restrict__ chunk_utt, const long* __restrict__ chunk_off,
                                      const long* __restrict__ frame_off, const long* __restrict__ L, long total_chunks,
-                                     int K, int P, int f4n) {
+                                     int K, int P, int f4n, uint2* __restrict__ out_h16 = nullptr) {
     const long total = total_chunks * K * f4n;
     for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
         const int f4 = (int)(idx % f4n);
@@ -171,7 +172,9 @@ __global__ void unfold_ragged_kernel(const float* __restrict__ y, float* __restr
         const long t = s * P + k - K;
         float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
         if (t >= 0 && t < __ldg(L + b)) v = __ldg(reinterpret_cast<const float4*>(y) + (__ldg(frame_off + b) + t) * f4n + f4);
-        reinterpret_cast<float4*>(out)[idx] = v;
+        if (out) reinterpret_cast<float4*>(out)[idx] = v;
+        if (out_h16)         // 16-bit copy for the first tensor-core LSTM layer (the rounding of dprnn_cast_h16)
+            out_h16[idx] = make_uint2(pack_h16x2<kF16>(v.x, v.y), pack_h16x2<kF16>(v.z, v.w));
     }
 }
 
@@ -200,6 +203,55 @@ __global__ void fold_prelu_ragged_kernel(const float* __restrict__ x, float* __r
                 v.z = v.z >= 0.f ? v.z : a * v.z;
                 v.w = v.w >= 0.f ? v.w : a * v.w;
                 acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+        }
+        reinterpret_cast<float4*>(out)[idx] = acc;      // junk rows between utterances are zeroed
+    }
+}
+
+// The last half-block's norm + residual (16-bit residual stream), PReLU and overlap-add in one pass (the ragged twin of
+// norm_residual_fold_prelu_kernel in pointwise.cu): the per-element arithmetic is that of
+// norm_residual_ragged_bf16res_kernel followed by fold_prelu_ragged_kernel, in the same order - bit-identical.
+template <bool kF16>
+__global__ void norm_residual_fold_prelu_ragged_kernel(const uint2* __restrict__ y, const uint2* __restrict__ xb,
+                                                       const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
+                                                       const float* __restrict__ beta, float* __restrict__ out,
+                                                       const int* __restrict__ frame_utt, const long* __restrict__ frame_off,
+                                                       const long* __restrict__ L, const long* __restrict__ chunk_off,
+                                                       const long* __restrict__ S, long total_rows, int K, int P, int c4n,
+                                                       const float* __restrict__ prelu_a) {
+    const long total = total_rows * c4n;
+    const float a = prelu_a ? __ldg(prelu_a) : 1.0f;
+    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+        const int c4 = (int)(idx % c4n);
+        const long row = idx / c4n;
+        const int b = __ldg(frame_utt + row);
+        const long t = row - __ldg(frame_off + b);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (t < __ldg(L + b)) {
+            const float mean = __ldg(mean_rstd + 2 * b), rstd = __ldg(mean_rstd + 2 * b + 1);
+            const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c4);
+            const float4 be = __ldg(reinterpret_cast<const float4*>(beta) + c4);
+            const long Sb = __ldg(S + b), c0 = __ldg(chunk_off + b);
+            long s_lo = t / P + 1, s_hi = (t + K) / P;
+            if (s_hi > Sb - 1) s_hi = Sb - 1;
+            for (long s = s_lo; s <= s_hi; ++s) {
+                const long k = t + K - s * P;
+                const long e = ((c0 + s) * K + k) * c4n + c4;
+                const uint2 yr = __ldg(y + e), xr = __ldg(xb + e);
+                const float2 y01 = unpack_h16x2<kF16>(yr.x), y23 = unpack_h16x2<kF16>(yr.y);
+                const float2 x01 = unpack_h16x2<kF16>(xr.x), x23 = unpack_h16x2<kF16>(xr.y);
+                float4 v;
+                v.x = x01.x + ((y01.x - mean) * rstd * g.x + be.x);
+                v.y = x01.y + ((y01.y - mean) * rstd * g.y + be.y);
+                v.z = x23.x + ((y23.x - mean) * rstd * g.z + be.z);
+                v.w = x23.y + ((y23.y - mean) * rstd * g.w + be.w);
+                v.x = v.x >= 0.f ? v.x : __fmul_rn(a, v.x);
+                v.y = v.y >= 0.f ? v.y : __fmul_rn(a, v.y);
+                v.z = v.z >= 0.f ? v.z : __fmul_rn(a, v.z);
+                v.w = v.w >= 0.f ? v.w : __fmul_rn(a, v.w);
+                acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y);
+                acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
             }
         }
         reinterpret_cast<float4*>(out)[idx] = acc;      // junk rows between utterances are zeroed
@@ -447,8 +499,36 @@ int dprnn_norm_residual_ragged_bf16res(const void* y_bf16, void* x_bf16, float* 
 int dprnn_unfold_ragged(const float* y, float* x, const int* chunk_utt, const long* chunk_off, const long* frame_off,
                         const long* L, long total_chunks, int K, int P, int F, void* stream) {
     DPRNN_CHECK_ARG(y && x && chunk_utt && chunk_off && frame_off && L && total_chunks > 0 && K > 0 && P > 0 && F % 4 == 0);
-    unfold_ragged_kernel<<<rgrid(total_chunks * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+    unfold_ragged_kernel<false><<<rgrid(total_chunks * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(
         y, x, chunk_utt, chunk_off, frame_off, L, total_chunks, K, P, F / 4);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_unfold_ragged_h16(const float* y, float* x, void* x_h16, const int* chunk_utt, const long* chunk_off,
+                            const long* frame_off, const long* L, long total_chunks, int K, int P, int F, int h16,
+                            void* stream) {
+    DPRNN_CHECK_ARG(y && x_h16 && chunk_utt && chunk_off && frame_off && L && total_chunks > 0 && K > 0 && P > 0 && F % 4 == 0);
+    DPRNN_CHECK_ARG(h16 == DPRNN_H16_BF16 || h16 == DPRNN_H16_FP16);
+    auto kern = h16 ? unfold_ragged_kernel<true> : unfold_ragged_kernel<false>;
+    kern<<<rgrid(total_chunks * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        y, x, chunk_utt, chunk_off, frame_off, L, total_chunks, K, P, F / 4, (uint2*)x_h16);
+    DPRNN_CHECK_LAUNCH();
+    return 0;
+}
+
+int dprnn_norm_residual_fold_prelu_ragged_h16(const void* y_h16, const void* x_h16, const float* mean_rstd,
+                                              const float* gamma, const float* beta, float* out, const int* frame_utt,
+                                              const long* frame_off, const long* L, const long* chunk_off, const long* S,
+                                              long total_rows, int K, int P, int F, const float* prelu_a, int h16,
+                                              void* stream) {
+    DPRNN_CHECK_ARG(y_h16 && x_h16 && mean_rstd && gamma && beta && out && frame_utt && frame_off && L && chunk_off && S);
+    DPRNN_CHECK_ARG(total_rows > 0 && K > 0 && P > 0 && F % 4 == 0);
+    DPRNN_CHECK_ARG(h16 == DPRNN_H16_BF16 || h16 == DPRNN_H16_FP16);
+    auto kern = h16 ? norm_residual_fold_prelu_ragged_kernel<true> : norm_residual_fold_prelu_ragged_kernel<false>;
+    kern<<<rgrid(total_rows * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(
+        (const uint2*)y_h16, (const uint2*)x_h16, mean_rstd, gamma, beta, out, frame_utt, frame_off, L, chunk_off, S,
+        total_rows, K, P, F / 4, prelu_a);
     DPRNN_CHECK_LAUNCH();
     return 0;
 }

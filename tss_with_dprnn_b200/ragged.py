@@ -255,17 +255,23 @@ class RaggedMixin:
                                   p_scale=s1, p_shift=s0, p_add=addc, rowscale=rowscale)
         TC = lay.total_chunks
         rows = TC * K
-        x = torch.empty((rows, F), device=dev)
-        L_.call('dprnn_unfold_ragged', y, x, lay.chunk_utt, lay.chunk_off, lay.frame_off, lay.L_d, TC, K, P, F, st)
-        del y
         bf16 = self.tc
+        # 16-bit residual stream: the fp32 chunk-space tensor never exists - the unfold writes the 16-bit copy only and the last
+        # half-block's norm + residual is applied by the fold (the uniform path's Engine.fold_fused, same arithmetic)
+        x16_only = bool(bf16 and self.residual_bf16 and self.fold_fused and len(sep.dprnn_blocks) > 0)
+        pending_fold = None
+        x = None if x16_only else torch.empty((rows, F), device=dev)
         if bf16:
             if H != 128 or F != 128:
                 raise NotImplementedError('the tensor-core LSTM kernel is built for feature_size = hidden_size = 128')
             if self.precision == 'fp16' and not self.lstm_pingpong:
                 raise NotImplementedError("precision 'fp16' is built for the default LSTM kernel (lstm_pingpong = True)")
             xb = torch.empty((rows, F), device=dev, dtype=self.h16_dtype)
-            L_.call('dprnn_cast_h16', x, xb, rows * F, self.h16, st)
+            L_.call('dprnn_unfold_ragged_h16', y, x, xb, lay.chunk_utt, lay.chunk_off, lay.frame_off, lay.L_d, TC, K, P, F,
+                    self.h16, st)
+        else:
+            L_.call('dprnn_unfold_ragged', y, x, lay.chunk_utt, lay.chunk_off, lay.frame_off, lay.L_d, TC, K, P, F, st)
+        del y
         for blk, halves in zip(sep.dprnn_blocks, W['blocks']):
             for which, hw in enumerate(halves):
                 nd = hw['ndir']
@@ -287,8 +293,11 @@ class RaggedMixin:
                     self._linear_stats_ragged(hb, hw, ybuf, rows, nd * H, part, lay, eps, mr2)
                     if self.residual_bf16:      # opt-in bf16 residual stream (same arithmetic as the uniform path)
                         last = blk is sep.dprnn_blocks[len(sep.dprnn_blocks) - 1] and which == 1
-                        L_.call('dprnn_norm_residual_ragged_h16res', ybuf, xb, x if last else None, mr2, g_, b_,
-                                lay.chunk_utt, TC, K, F, self.h16, st)
+                        if last and x is None:
+                            pending_fold = (ybuf, mr2, g_, b_)      # applied by the fold below
+                        else:
+                            L_.call('dprnn_norm_residual_ragged_h16res', ybuf, xb, x if last else None, mr2, g_, b_,
+                                    lay.chunk_utt, TC, K, F, self.h16, st)
                     else:
                         L_.call('dprnn_norm_residual_ragged', ybuf, 1 + self.h16, x, mr2, g_, b_, lay.chunk_utt, TC, K, F, xb, st)
                     del hb, ybuf
@@ -309,8 +318,14 @@ class RaggedMixin:
                 L_.call('dprnn_norm_residual_ragged', yl, 0, x, mr2, g_, b_, lay.chunk_utt, TC, K, F, None, st)
                 del yl
         z = torch.empty((TR, F), device=dev)
-        L_.call('dprnn_fold_prelu_ragged', x, z, lay.frame_utt, lay.frame_off, lay.L_d, lay.chunk_off, lay.S_d, TR, K, P,
-                F, sep.prelu.weight.detach(), st)
+        if pending_fold is not None:
+            ybuf, mr2, g_, b_ = pending_fold
+            L_.call('dprnn_norm_residual_fold_prelu_ragged_h16', ybuf, xb, mr2, g_, b_, z, lay.frame_utt, lay.frame_off,
+                    lay.L_d, lay.chunk_off, lay.S_d, TR, K, P, F, sep.prelu.weight.detach(), self.h16, st)
+            del pending_fold, ybuf
+        else:
+            L_.call('dprnn_fold_prelu_ragged', x, z, lay.frame_utt, lay.frame_off, lay.L_d, lay.chunk_off, lay.S_d, TR, K, P,
+                    F, sep.prelu.weight.detach(), st)
         del x
         act = EPI_SIGMOID if cfg['activation_type'] == 'sigmoid' else EPI_RELU
         masks = []
