@@ -251,6 +251,28 @@ __global__ void unfold_kernel(const float* __restrict__ y, float* __restrict__ o
     }
 }
 
+// unfold with the 16-bit output only (the default of the tensor-core modes): 8 channels per thread and 32-bit index
+// arithmetic (the launcher checks that every index fits) - the generic kernel above spends its time in 64-bit divisions
+// once it no longer writes the fp32 copy.  Same values, same rounding.
+template <bool kF16>
+__global__ void unfold_h16_rows_kernel(const float4* __restrict__ y, uint4* __restrict__ out16, unsigned rows, unsigned L,
+                                       unsigned S, unsigned K, unsigned P, unsigned c8n) {
+    const unsigned total = rows * c8n;
+    for (unsigned idx = blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += gridDim.x * blockDim.x) {
+        const unsigned c8 = idx % c8n, row = idx / c8n;
+        const unsigned k = row % K, r2 = row / K;
+        const unsigned s = r2 % S, b = r2 / S;
+        const int t = (int)(s * P + k) - (int)K;
+        float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
+        if (t >= 0 && (unsigned)t < L) {
+            const float4* src = y + ((size_t)b * L + (unsigned)t) * (2 * c8n) + 2 * c8;
+            v0 = __ldg(src); v1 = __ldg(src + 1);
+        }
+        out16[idx] = make_uint4(pack_h16x2<kF16>(v0.x, v0.y), pack_h16x2<kF16>(v0.z, v0.w),
+                                pack_h16x2<kF16>(v1.x, v1.y), pack_h16x2<kF16>(v1.z, v1.w));
+    }
+}
+
 // fold (+ optional PReLU on the way in): out[b,t,:] = sum_{s: 0 <= t+K-sP < K} prelu(x[b,s,t+K-sP,:])
 __global__ void fold_prelu_kernel(const float* __restrict__ x, float* __restrict__ out, int B, long L, int S,
                                   int K, int P, int f4n, const float* __restrict__ prelu_a) {
@@ -280,19 +302,22 @@ __global__ void fold_prelu_kernel(const float* __restrict__ x, float* __restrict
 // of the last Linear output feeds exactly one output frame, so x + norm(y) never has to exist as an fp32 [B,S,K,F] tensor
 // (written by norm_residual_bf16res_kernel and read back by fold_prelu_kernel: 2 x 1.59 GB at B = 64).  Same arithmetic
 // in the same order as those two kernels (norm_res1, predicated multiply, sum over s ascending): bit-identical.
-template <bool kF16>
+// I = the integer type of the index arithmetic: unsigned when every index fits 32 bits (the launcher checks), else long -
+// the divisions are most of the kernel's instructions.
+template <bool kF16, typename I>
 __global__ void norm_residual_fold_prelu_kernel(const uint4* __restrict__ y, const uint4* __restrict__ xb,
                                                 const float* __restrict__ mean_rstd, const float* __restrict__ gamma,
-                                                const float* __restrict__ beta, float* __restrict__ out, int B, long L,
-                                                int S, int K, int P, int c8n, const float* __restrict__ prelu_a) {
-    const long total = (long)B * L * c8n;
+                                                const float* __restrict__ beta, float* __restrict__ out, int B_, long L_,
+                                                int S_, int K_, int P_, int c8n_, const float* __restrict__ prelu_a) {
+    const I L = (I)L_, S = (I)S_, K = (I)K_, P = (I)P_, c8n = (I)c8n_;
+    const I total = (I)B_ * L * c8n;
     const float a = prelu_a ? __ldg(prelu_a) : 1.0f;
-    for (long idx = blockIdx.x * (long)blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-        const int c8 = (int)(idx % c8n);
-        const long r = idx / c8n;
-        const long t = r % L, b = r / L;
+    for (I idx = (I)blockIdx.x * (I)blockDim.x + (I)threadIdx.x; idx < total; idx += (I)gridDim.x * (I)blockDim.x) {
+        const I c8 = idx % c8n;
+        const I r = idx / c8n;
+        const I t = r % L, b = r / L;
         const float mean = __ldg(mean_rstd + 2 * b), rstd = __ldg(mean_rstd + 2 * b + 1);
-        long s_lo = t / P + 1, s_hi = (t + K) / P;
+        I s_lo = t / P + 1, s_hi = (t + K) / P;
         if (s_hi > S - 1) s_hi = S - 1;
         float g[8], be[8], acc[8];
         {
@@ -303,9 +328,9 @@ __global__ void norm_residual_fold_prelu_kernel(const uint4* __restrict__ y, con
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) acc[i] = 0.f;
-        for (long s = s_lo; s <= s_hi; ++s) {
-            const long k = t + K - s * P;
-            const long e = ((b * S + s) * K + k) * c8n + c8;
+        for (I s = s_lo; s <= s_hi; ++s) {
+            const I k = t + K - s * P;
+            const size_t e = (size_t)(((b * S + s) * K + k) * c8n + c8);
             uint4 yv;
             asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];"
                          : "=r"(yv.x), "=r"(yv.y), "=r"(yv.z), "=r"(yv.w) : "l"(y + e));
@@ -322,7 +347,7 @@ __global__ void norm_residual_fold_prelu_kernel(const uint4* __restrict__ y, con
                 acc[2 * q + 1] = __fadd_rn(acc[2 * q + 1], v1);
             }
         }
-        float4* o = reinterpret_cast<float4*>(out) + idx * 2;
+        float4* o = reinterpret_cast<float4*>(out) + (size_t)idx * 2;
         o[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
         o[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
     }
@@ -777,6 +802,16 @@ int dprnn_unfold_h16(const float* y, float* x, void* x_h16, int B, long L, int K
     DPRNN_CHECK_ARG(y && x_h16 && B > 0 && L > 0 && K > 0 && P > 0 && F % 4 == 0);      // x may be NULL
     DPRNN_CHECK_H16(h16);
     const int S = dprnn_num_chunks(L, K, P);
+    const long rows = (long)B * S * K;
+    if (!x && F % 8 == 0 && rows * (F / 8) < (1L << 31) && (long)S * P + K < (1L << 31) && L < (1L << 31) &&
+        ((uintptr_t)y | (uintptr_t)x_h16) % 16 == 0) {
+        auto fast = h16 ? unfold_h16_rows_kernel<true> : unfold_h16_rows_kernel<false>;
+        fast<<<grid_for(rows * (F / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+            (const float4*)y, (uint4*)x_h16, (unsigned)rows, (unsigned)L, (unsigned)S, (unsigned)K, (unsigned)P,
+            (unsigned)(F / 8));
+        DPRNN_CHECK_LAUNCH();
+        return 0;
+    }
     auto kern = h16 ? unfold_kernel<true> : unfold_kernel<false>;
     kern<<<grid_for((long)B * S * K * (F / 4), 256), 256, 0, (cudaStream_t)stream>>>(y, x, B, L, S, K, P, F / 4,
                                                                                   (uint2*)x_h16);
@@ -804,7 +839,10 @@ int dprnn_norm_residual_fold_prelu_h16(const void* y_h16, const void* x_h16, con
     DPRNN_CHECK_ARG(((uintptr_t)y_h16 | (uintptr_t)x_h16 | (uintptr_t)out | (uintptr_t)gamma | (uintptr_t)beta) % 16 == 0);
     DPRNN_CHECK_H16(h16);
     const int S = dprnn_num_chunks(L, K, P);
-    auto kern = h16 ? norm_residual_fold_prelu_kernel<true> : norm_residual_fold_prelu_kernel<false>;
+    // 32-bit index arithmetic when the element counts of both spaces (+ one grid stride) fit
+    const bool i32 = (long)B * L * (F / 8) < (1L << 31) && (long)B * S * K * (F / 8) < (1L << 31) && L + K < (1L << 31);
+    auto kern = i32 ? (h16 ? norm_residual_fold_prelu_kernel<true, unsigned> : norm_residual_fold_prelu_kernel<false, unsigned>)
+                    : (h16 ? norm_residual_fold_prelu_kernel<true, long> : norm_residual_fold_prelu_kernel<false, long>);
     kern<<<grid_for((long)B * L * (F / 8), 256), 256, 0, (cudaStream_t)stream>>>(
         (const uint4*)y_h16, (const uint4*)x_h16, mean_rstd, gamma, beta, out, B, L, S, K, P, F / 8, prelu_a);
     DPRNN_CHECK_LAUNCH();
