@@ -681,17 +681,28 @@ def run_ours(args):
     dominant = 'dprnn_lstm_layer_bf16' if tcmode else 'dprnn_lstm_recurrence_f32'
     names = list(L.protos.keys())
     model.n_streams = 1
-    L.timing = {n: [] for n in names}
-    with torch.no_grad():
-        wl.resident(0)
-    torch.cuda.synchronize()
+    # three passes; the one with the smallest total is reported (the first single-stream pass pays for first-use effects -
+    # new buffer sizes, lazily loaded kernels - and a shared host can stall any one of them); every pass's dominant-kernel
+    # average launch is kept in roofline.passes_top_kernel_ms_avg
+    per_kernel, pass_totals, pass_dominant = {}, [], []
+    for _ in range(3):
+        L.timing = {n: [] for n in names}
+        with torch.no_grad():
+            wl.resident(0)
+        torch.cuda.synchronize()
+        pk = {}
+        for n, evs in L.timing.items():
+            if evs:
+                d = [a.elapsed_time(b) for a, b in evs]
+                pk[n] = {'launches': len(d), 'ms_total': sum(d), 'ms_avg': sum(d) / len(d)}
+        L.timing = None
+        tot = sum(v['ms_total'] for v in pk.values())
+        pass_totals.append(tot)
+        top = max(pk.values(), key=lambda v: v['ms_total']) if pk else None
+        pass_dominant.append(top['ms_avg'] if top else None)
+        if not per_kernel or tot <= min(pass_totals[:-1]):
+            per_kernel = pk
     model.n_streams = args.streams
-    per_kernel = {}
-    for n, evs in L.timing.items():
-        if evs:
-            d = [a.elapsed_time(b) for a, b in evs]
-            per_kernel[n] = {'launches': len(d), 'ms_total': sum(d), 'ms_avg': sum(d) / len(d)}
-    L.timing = None
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -756,6 +767,10 @@ def run_ours(args):
                             'the weight-gradient kernels of the previous half-block run on the side stream and share the HBM '
                             'bandwidth with it: DESIGN.md section 5.2'}
 
+    if roofline is not None:      # the three per-kernel passes: sum of all launches, and the top kernel's average launch, per pass
+        roofline['passes_total_ms'] = pass_totals
+        roofline['passes_top_kernel_ms_avg'] = pass_dominant
+        roofline['pass_reported'] = 'the pass with the smallest total (index %d)' % pass_totals.index(min(pass_totals))
     modes = gpu_ref = cfg5 = None
     if args.workload == 'cfg2':
         if args.modes and world == 1:
