@@ -129,3 +129,32 @@ def test_oracle_matches_live_reference_stagewise():
         assert O.peak_rel_err(blk, grabbed['blk_out']) < TOL
     for h in hooks:
         h.remove()
+
+
+@pytest.mark.parametrize('L,K,P_', [(1337, 100, 50), (249, 250, 125), (1, 20, 10), (3999, 250, 125)])
+def test_fold_can_apply_the_last_norm_and_residual(L, K, P_):
+    """The identity behind dprnn_norm_residual_fold_prelu_h16: every chunk position (s, k) feeds exactly
+    one output frame, so overlap_add(prelu(x + norm(y))) (dprnn.py:98-99,174,203-217) can be evaluated per frame t from the
+    two positions s in [t // P + 1, min((t + K) // P, S - 1)], k = t + K - s P - the index arithmetic of the CUDA kernel,
+    restated here with integer tensors and checked against the oracle's segmentation-map overlap-add."""
+    torch.manual_seed(L)
+    B, F = 2, 8
+    S = O.n_chunks(L, K, P_)
+    x, y = torch.randn(B, F, K, S, dtype=torch.float64), torch.randn(B, F, K, S, dtype=torch.float64)
+    gamma, beta, a = torch.randn(F, dtype=torch.float64), torch.randn(F, dtype=torch.float64), 0.25
+    v = x + O.chan_norm(y, gamma, beta, 1e-5)
+    want = O.overlap_add(torch.where(v >= 0, v, a * v), L, K, P_)
+    t = torch.arange(L)
+    got = torch.zeros(B, F, L, dtype=torch.float64)
+    covered = torch.zeros(L, dtype=torch.long)
+    s_lo, s_hi = t // P_ + 1, torch.clamp((t + K) // P_, max=S - 1)
+    for j in range(2):                                  # at most two chunks cover a frame when P = K / 2
+        s = s_lo + j
+        ok = s <= s_hi
+        k = t + K - s * P_
+        assert bool(((k >= 0) & (k < K))[ok].all())
+        got[:, :, ok] += torch.where(v >= 0, v, a * v)[:, :, k[ok], s[ok]]
+        covered += ok.long()
+    assert bool((s_lo + 2 > s_hi).all())                # never a third chunk
+    assert torch.equal(covered, torch.from_numpy(O.fold_coverage(L, K, P_)))
+    assert torch.allclose(got, want, rtol=0, atol=1e-12)
