@@ -158,3 +158,38 @@ def test_fold_can_apply_the_last_norm_and_residual(L, K, P_):
     assert bool((s_lo + 2 > s_hi).all())                # never a third chunk
     assert torch.equal(covered, torch.from_numpy(O.fold_coverage(L, K, P_)))
     assert torch.allclose(got, want, rtol=0, atol=1e-12)
+
+
+@pytest.mark.skipif(not os.path.isdir('/root/reference/src/models'), reason='live reference not mounted')
+@pytest.mark.parametrize('cls,T,Tr', [('tasnet', 24001, 0), ('spe', 30160, 24000), ('ira', 36720, 41000),
+                                      ('spe', 111920, 107360), ('spe', 251, 400)])
+def test_oracle_matches_live_reference_on_test_set_lengths(cls, T, Tr):
+    """whole-model compare against the LIVE reference on the lengths its test set holds (median 36 720,
+    maximum 111 920 samples; reference utterance longer or shorter than the mixture) - build container only, the fixtures
+    cover the 3-s shape.  One block keeps the CPU forwards short; every stage's length arithmetic is exercised."""
+    sys.path.insert(0, '/root/reference')
+    from src.models.dprnn import DPRNNTasNet
+    from src.models.dprnn_spe import DPRNNSpeTasNet
+    from src.models.dprnn_spe_ira import DPRNNSpeIRATasNet
+    kw = dict(input_size=64, feature_size=128, hidden_size=128, chunk_length=250, kernel_size=2, hop_length=125,
+              n_repeats=1, bidirectional=True, norm_type='ln', activation_type='sigmoid', dropout=0)
+    torch.manual_seed(T)
+    g = torch.Generator().manual_seed(T + 1)
+    B = 1 if T > 100000 else 2
+    mix = 0.05 * torch.randn(B, T, generator=g)
+    with torch.no_grad():
+        if cls == 'tasnet':
+            ref_model = DPRNNTasNet(**kw).eval()
+            want = ref_model(mix)
+            got = O.tasnet_forward(mix, ref_model.state_dict(), O.Config(n_repeats=1))
+            assert want.shape == got.shape == (B, 2, T)
+            assert O.peak_rel_err(got, want) < TOL
+            return
+        fusion = 'film' if cls == 'spe' else 'cat'
+        ref_model = (DPRNNSpeTasNet if cls == 'spe' else DPRNNSpeIRATasNet)(**kw, fusion_type=fusion).eval()
+        aux = 0.05 * torch.randn(B, Tr, generator=g)
+        want, wl = ref_model(mix, aux, torch.tensor(float(Tr)))
+        fwd = O.spe_forward if cls == 'spe' else O.ira_forward
+        got, gl = fwd(mix, aux, torch.tensor(float(Tr)), ref_model.state_dict(), O.Config(n_repeats=1, fusion_type=fusion))
+        assert want.shape == got.shape == (B, T)
+        assert O.peak_rel_err(got, want) < TOL and O.peak_rel_err(gl, wl) < 1e-5
